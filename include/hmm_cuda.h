@@ -1,0 +1,177 @@
+/*
+ * hmm_cuda.h -- C ABI of the B200-native continuous-HMM hot path (libhmmcu.so).
+ *
+ * The reference (edielsonpf/speech-recognition-hmm-continuous) has no FFI: its hot path is a set
+ * of K&R C functions called from two main()s.  This header is the boundary a maintainer binds
+ * INSTEAD of those functions; every entry point names the reference code it replaces.
+ *   T-FS = train/source/hmm-fs/hmm_continuous_fs.c        (diagonal-covariance trainer)
+ *   R-FS = test/source/recognition-fs/recognition_continuous_fs.c   (forward-score recogniser)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, caller-owned host buffers, `int` status (0 = ok, else a
+ *     HMMCU_E* code; hmmcu_last_error() gives the text).  No CPU fallback exists: every compute
+ *     entry point fails with HMMCU_ENODEV when no sm_100 device is present.
+ *   - one host thread per context; a context owns one device and one stream.
+ *   - model semantics are the reference's (T-FS:53-64): `inv_var` is the INVERSE variance held in
+ *     `cov_matrix`, `det` the product of variances; pi = [1,0,..,0]; the last state is final.
+ *   - all host arrays are row-major, double precision unless stated.
+ */
+#ifndef HMM_CUDA_H
+#define HMM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMMCU_OK 0
+#define HMMCU_EINVAL 1   /* bad argument / call order */
+#define HMMCU_ENODEV 2   /* no usable CUDA device */
+#define HMMCU_ECUDA 3    /* CUDA runtime error */
+#define HMMCU_ENOMEM 4
+#define HMMCU_EIO 5      /* host-side file error (hmmh_* only) */
+
+#define HMMCU_MAX_STATES 32 /* reference: MAX_STATES_NUMBER 20 (T-FS:41) */
+
+typedef struct hmmcu_ctx hmmcu_ctx;
+
+/* ---------------------------------------------------------------- context ---------------- */
+int hmmcu_create(int device, hmmcu_ctx **out);
+void hmmcu_destroy(hmmcu_ctx *ctx);
+const char *hmmcu_last_error(const hmmcu_ctx *ctx); /* ctx may be NULL: last create() error */
+int hmmcu_device_count(void);
+/* The context's CUDA stream as a cudaStream_t cast to void* (for callers that enqueue a
+ * collective on the statistics buffer, see hmmcu_stats_device). */
+void *hmmcu_stream(hmmcu_ctx *ctx);
+int hmmcu_synchronize(hmmcu_ctx *ctx);
+/* pinned host memory for the feature upload path */
+int hmmcu_host_alloc(void **p, uint64_t bytes);
+void hmmcu_host_free(void *p);
+
+/* ---------------------------------------------------------------- inputs ----------------- */
+/* Feature vectors of U utterances, ragged: utterance u owns frames [frame_off[u], frame_off[u+1])
+ * of x[F][D].  Replaces the per-frame fread loop (reading_coef, T-FS:527-548 / R-FS:518-539) that
+ * the reference runs twice per utterance per EM iteration and V times per test utterance.
+ * The data are copied to the device, centred and converted once. */
+int hmmcu_set_features(hmmcu_ctx *ctx, const double *x, const int64_t *frame_off, int U, int D);
+/* Same, but x is already a DEVICE pointer (features resident in HBM). */
+int hmmcu_set_features_device(hmmcu_ctx *ctx, const double *x_dev, const int64_t *frame_off, int U, int D);
+
+/* V models of identical topology, struct-of-arrays in the semantics of `struct state` /
+ * `struct mixture` (T-FS:53-64, R-FS:52-63) and transition_probab:
+ *   A[V][N][N]  c[V][N][M]  mu[V][N][M][D]  inv_var[V][N][M][D]  det[V][N][M]            */
+int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A, const double *c,
+                     const double *mu, const double *inv_var, const double *det);
+
+/* ---------------------------------------------------------------- emissions -------------- */
+/* Parity / debug export of calc_symbol_probab + calc_gaus (T-FS:1749-1841, R-FS:860-947) for
+ * utterance u against model v, as the device path computes them: logb[T][N] = log b_i(t), and
+ * (post != NULL) post[T][N][M] = c_m N_m / b_i, the normalised per-mixture posterior. */
+int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post);
+
+/* ---------------------------------------------------------------- recognition ------------ */
+/* logp[U][V] = log P(O_u, q_T = N-1 | model v): calc_symbol_probab + calc_alpha +
+ * calc_probability for every (utterance, model) cell -- the recogniser's inner loops
+ * R-FS:341-369.  Where the reference's linear-domain arithmetic underflows it yields NaN or
+ * -inf; with emulate_underflow != 0 those cells are reported as NaN / -inf too. */
+int hmmcu_forward_scores(hmmcu_ctx *ctx, double *logp, int emulate_underflow);
+
+/* sorting_probab + the label rule (R-FS:968-995, 380-388): label[u] = index[0], second[u] =
+ * index[1] of the reference's stable descending bubble sort, including its NaN behaviour.
+ * weight multiplies every score first (coef_model, R-FS:366).  second may be NULL. */
+int hmmcu_rank(hmmcu_ctx *ctx, const double *logp, int U, int V, double weight, int32_t *label,
+               int32_t *second);
+
+/* ---------------------------------------------------------------- Baum-Welch E-step ------ */
+/* Doubles per model in the statistics vector (this is also the all-reduce payload):
+ *   num_trans[N][N] den_trans[N] den_mix[N] S0[N][M] S1[N][M][D] S2c[N][M][D] sum_logp n_utt */
+int64_t hmmcu_stats_size(int N, int M, int D);
+
+/* One E-step over all utterances: utterance u is trained against model utt2model[u]
+ * (-1 = leave this utterance out, used for words that have already converged).
+ * Replaces the body of the EM do-loop, T-FS:272-321: calc_symbol_probab, calc_alpha, calc_beta,
+ * calc_transition_probab, calc_den_mix_coef, calc_mix_param, calc_probability.
+ * stats[V][hmmcu_stats_size] receives the sums (may be NULL: they stay on the device, see
+ * below); logp_utt[U] the per-utterance log-probabilities (may be NULL). */
+int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double *logp_utt);
+
+/* Device-side statistics for multi-GPU training: after hmmcu_estep(ctx, u2m, NULL, NULL) the
+ * caller all-reduces the buffer in place on hmmcu_stream() (one ncclAllReduce(sum, double) per EM
+ * iteration) and then downloads it. */
+double *hmmcu_stats_device(hmmcu_ctx *ctx, int64_t *n_doubles);
+int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats);
+
+/* ---------------------------------------------------------------- Viterbi ---------------- */
+/* The reference has NO Viterbi decoder; these follow its conventions (pi=[1,0..],
+ * final-state termination, lowest predecessor index on a tie).
+ * hmmcu_viterbi: utterance u against model utt2model[u], double-precision emissions;
+ *   score[U] and the state sequence path[F] (frame-aligned with the features).
+ * hmmcu_viterbi_scores: score[U][V] for every cell (single-precision emissions). */
+int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32_t *path);
+int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score);
+
+/* ---------------------------------------------------------------- instrumentation -------- */
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+int64_t hmmcu_launch_count(const hmmcu_ctx *ctx);
+/* Device time in ms of the most recent call's kernels, by name (CUDA events on the context's
+ * stream).  names: "emis", "fwdbwd", "accum", "score", "viterbi", "pack".  -1 if unknown. */
+double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name);
+void hmmcu_enable_timing(hmmcu_ctx *ctx, int on);
+
+/* ================================================================================================
+ * Host side (plain C, no device work): file formats, M-step, EM control, drop-in programs.
+ * ============================================================================================== */
+
+typedef struct hmmh_model {
+  char word[64];   /* reference: MAX_WORD_SIZE 50 */
+  int N, M, D;     /* states, mixtures per state, coefficients (param_number is 1) */
+  double *A;       /* [N][N] */
+  double *c;       /* [N][M] */
+  double *mu;      /* [N][M][D] */
+  double *inv_var; /* [N][M][D] */
+  double *det;     /* [N][M] */
+} hmmh_model;
+
+int hmmh_model_alloc(hmmh_model *m, int N, int M, int D);
+void hmmh_model_free(hmmh_model *m);
+
+/* Feature file: int32 D, then T x D doubles, T implied by EOF (T-FS:527-581).  *x is malloc'd. */
+int hmmh_read_features(const char *path, double **x, int *T, int *D);
+int hmmh_write_features(const char *path, const double *x, int T, int D);
+/* .hmm model file, layout of writing_model / reading_model (T-FS:2043-2146, 604-711).
+ * len_bytes: 8 = LP64 size_t header (what the reference writes here), 4 = the shipped 32-bit files,
+ * 0 = auto-detect on read. */
+int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes);
+int hmmh_write_model(const char *path, const hmmh_model *m);
+
+/* creating_initial_model (T-FS:732-1317): uniform left-to-right A, uniform segmentation, LBG
+ * splitting + 3 k-means passes, per-cluster variance and weights. */
+int hmmh_init_model(hmmh_model *m, const double *x, const int64_t *frame_off, int U);
+/* M-step from one model's statistics vector (T-FS:328-346, 1862-1955, 1338-1359). */
+int hmmh_mstep(hmmh_model *m, const double *stats);
+
+/* hmmcu_set_models from an array of V host models of identical topology. */
+int hmmh_upload_models(hmmcu_ctx *ctx, const hmmh_model *models, int V);
+
+/* All-reduce hook for multi-process training: called once per EM iteration with the DEVICE
+ * statistics buffer; must sum it in place across ranks on `stream`.  NULL = single process. */
+typedef int (*hmmh_allreduce_fn)(void *user, double *dev_buf, int64_t n_doubles, void *stream);
+
+/* The EM loop of the trainer's main() (T-FS:238-361) for V words at once: every word keeps its
+ * own convergence test |old - new| / |old| > 1e-3 (old starts at 1.0) and stops on its own
+ * iteration; the model returned is the one that produced the last E-step's probability.
+ * utt2model maps the context's utterances to models.  mean_logp[V], iterations[V] out. */
+int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2model, int U,
+               double *mean_logp, int *iterations, int max_iter, hmmh_allreduce_fn allreduce,
+               void *user);
+
+/* Drop-in programs: same argv, files and exit codes as the reference's main()s
+ * (T-FS:101-391 and R-FS:87-428). */
+int hmmh_train_main(int argc, char **argv);
+int hmmh_test_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMM_CUDA_H */

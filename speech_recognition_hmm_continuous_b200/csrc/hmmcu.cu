@@ -1,0 +1,596 @@
+// hmmcu.cu -- the C ABI of include/hmm_cuda.h over the kernels in kernels.cuh.
+// One context = one device + one stream; all work is enqueued on that stream and the entry
+// points that return host data synchronise it.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hmm_cuda.h"
+#include "kernels.cuh"
+
+using namespace hmmk;
+
+namespace {
+
+char g_create_err[512] = "";
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool used = false;
+};
+
+}  // namespace
+
+struct hmmcu_ctx {
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  char err[512] = "";
+  int64_t launches = 0;
+  int sm_count = 148;
+  bool timing = false;
+  std::map<std::string, Timer> timers;
+
+  // features
+  int U = 0, D = 0, DP = 0, Tmax = 0;
+  int64_t F = 0;
+  bool have_features = false;
+  DevBuf x64_own;            // when uploaded from the host
+  const double *d_x64 = nullptr;
+  DevBuf x32, ctr, off_d;
+  std::vector<int64_t> off;
+
+  // models
+  int V = 0, N = 0, M = 0, G = 0, Dm = 0;
+  bool have_models = false, pack_dirty = true;
+  DevBuf A, c, mu, iv, det, mu32, iv32, k32;
+
+  // training map
+  std::vector<int32_t> u2m;
+  DevBuf u2m_d, mus_d, mu_d, tiles_d;  // utt2model, model_utt_start, model_utts, emission tiles
+  int64_t n_train_tiles = 0;
+  int max_utts_per_model = 0;
+
+  // workspaces
+  DevBuf logb, post, gamma, alpha_ws, cs_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
+  int64_t stats_n = 0;
+};
+
+static int fail(hmmcu_ctx *c, int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(c ? c->err : g_create_err, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? HMMCU_ENOMEM : HMMCU_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                              \
+  do {                                                                                              \
+    ctx->launches++;                                                                                \
+    cudaError_t e_ = cudaGetLastError();                                                            \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(ctx, HMMCU_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static void t_begin(hmmcu_ctx *ctx, const char *name) {
+  if (!ctx->timing) return;
+  Timer &t = ctx->timers[name];
+  if (!t.a) {
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+  }
+  cudaEventRecord(t.a, ctx->st);
+}
+static void t_end(hmmcu_ctx *ctx, const char *name) {
+  if (!ctx->timing) return;
+  Timer &t = ctx->timers[name];
+  cudaEventRecord(t.b, ctx->st);
+  t.used = true;
+}
+
+extern "C" {
+
+int hmmcu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int hmmcu_create(int device, hmmcu_ctx **out) {
+  if (!out) return fail(nullptr, HMMCU_EINVAL, "hmmcu_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, HMMCU_ENODEV, "no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, HMMCU_EINVAL, "device %d out of range (%d present)", device, n);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, HMMCU_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, HMMCU_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  hmmcu_ctx *ctx = new hmmcu_ctx();
+  ctx->dev = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) {
+    fail(nullptr, HMMCU_ECUDA, "stream creation: %s", cudaGetErrorString(e));
+    delete ctx;
+    return HMMCU_ECUDA;
+  }
+  *out = ctx;
+  return HMMCU_OK;
+}
+
+void hmmcu_destroy(hmmcu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->dev);
+  cudaStreamSynchronize(ctx->st);
+  DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
+                    &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
+                    &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->cs_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
+                    &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out};
+  for (DevBuf *b : bufs) b->release();
+  for (auto &kv : ctx->timers) {
+    if (kv.second.a) cudaEventDestroy(kv.second.a);
+    if (kv.second.b) cudaEventDestroy(kv.second.b);
+  }
+  cudaStreamDestroy(ctx->st);
+  delete ctx;
+}
+
+const char *hmmcu_last_error(const hmmcu_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+void *hmmcu_stream(hmmcu_ctx *ctx) { return ctx ? (void *)ctx->st : nullptr; }
+int hmmcu_synchronize(hmmcu_ctx *ctx) {
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+int hmmcu_host_alloc(void **p, uint64_t bytes) { return cudaMallocHost(p, bytes) == cudaSuccess ? HMMCU_OK : HMMCU_ENOMEM; }
+void hmmcu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+int64_t hmmcu_launch_count(const hmmcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; }
+double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
+  auto it = ctx->timers.find(name);
+  if (it == ctx->timers.end() || !it->second.used) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(it->second.b) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+int64_t hmmcu_stats_size(int N, int M, int D) {
+  return (int64_t)N * N + 2 * N + (int64_t)N * M + 2 * (int64_t)N * M * D + 2;
+}
+
+// ---------------------------------------------------------------------------------- features ----
+static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const double *x_dev, const int64_t *frame_off,
+                               int U, int D) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (U < 0 || D < 1 || !frame_off || (U > 0 && !x_host && !x_dev)) return fail(ctx, HMMCU_EINVAL, "set_features: bad arguments");
+  const int DP = round_up(D + 1, 4);
+  if (DP > 256) return fail(ctx, HMMCU_EINVAL, "set_features: D=%d too large (max 251)", D);
+  if (frame_off[0] != 0) return fail(ctx, HMMCU_EINVAL, "set_features: frame_off[0] must be 0");
+  int Tmax = 0;
+  for (int u = 0; u < U; u++) {
+    int64_t T = frame_off[u + 1] - frame_off[u];
+    if (T < 1 || T > (1 << 30)) return fail(ctx, HMMCU_EINVAL, "set_features: utterance %d has %lld frames", u, (long long)T);
+    Tmax = std::max(Tmax, (int)T);
+  }
+  CK(cudaSetDevice(ctx->dev));
+  const int64_t F = U > 0 ? frame_off[U] : 0;
+  ctx->U = U; ctx->D = D; ctx->DP = DP; ctx->F = F; ctx->Tmax = Tmax;
+  ctx->off.assign(frame_off, frame_off + U + 1);
+  ctx->u2m.clear();
+  ctx->pack_dirty = true;  // the centre may move
+  ctx->have_features = true;
+  if (F == 0) return HMMCU_OK;
+  CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
+  CK(cudaMemcpyAsync(ctx->off_d.p, frame_off, sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
+  if (x_host) {
+    CK(ctx->x64_own.ensure(sizeof(double) * F * D));
+    CK(cudaMemcpyAsync(ctx->x64_own.p, x_host, sizeof(double) * F * D, cudaMemcpyHostToDevice, ctx->st));
+    ctx->d_x64 = ctx->x64_own.as<double>();
+  } else {
+    ctx->d_x64 = x_dev;
+  }
+  CK(ctx->x32.ensure(sizeof(float) * F * DP));
+  CK(ctx->ctr.ensure(sizeof(double) * DP));
+  t_begin(ctx, "pack");
+  k_center<<<1, 1024, 0, ctx->st>>>(ctx->d_x64, F, D, DP, ctx->ctr.as<double>());
+  LAUNCH_CHECK();
+  {
+    int64_t total = F * DP;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64, ctx->ctr.as<double>(), F, D, DP, ctx->x32.as<float>());
+    LAUNCH_CHECK();
+  }
+  t_end(ctx, "pack");
+  // the caller's host buffer may be reused as soon as we return
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+int hmmcu_set_features(hmmcu_ctx *ctx, const double *x, const int64_t *frame_off, int U, int D) {
+  return set_features_common(ctx, x, nullptr, frame_off, U, D);
+}
+int hmmcu_set_features_device(hmmcu_ctx *ctx, const double *x_dev, const int64_t *frame_off, int U, int D) {
+  return set_features_common(ctx, nullptr, x_dev, frame_off, U, D);
+}
+
+// ------------------------------------------------------------------------------------ models ----
+int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A, const double *c, const double *mu,
+                     const double *inv_var, const double *det) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (V < 1 || N < 1 || M < 1 || D < 1 || !A || !c || !mu || !inv_var || !det) return fail(ctx, HMMCU_EINVAL, "set_models: bad arguments");
+  if (N > 8) return fail(ctx, HMMCU_EINVAL, "set_models: N=%d states not supported yet (max 8)", N);
+  CK(cudaSetDevice(ctx->dev));
+  const int64_t G = (int64_t)N * M, VG = V * G;
+  CK(ctx->A.ensure(sizeof(double) * V * N * N));
+  CK(ctx->c.ensure(sizeof(double) * VG));
+  CK(ctx->mu.ensure(sizeof(double) * VG * D));
+  CK(ctx->iv.ensure(sizeof(double) * VG * D));
+  CK(ctx->det.ensure(sizeof(double) * VG));
+  CK(cudaMemcpyAsync(ctx->A.p, A, sizeof(double) * V * N * N, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->c.p, c, sizeof(double) * VG, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->mu.p, mu, sizeof(double) * VG * D, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->iv.p, inv_var, sizeof(double) * VG * D, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->det.p, det, sizeof(double) * VG, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
+  ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = (int)G;
+  ctx->Dm = D;
+  ctx->have_models = true;
+  ctx->pack_dirty = true;
+  return HMMCU_OK;
+}
+
+static int ensure_packed(hmmcu_ctx *ctx) {
+  if (!ctx->have_features || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "features and models must both be set first");
+  if (ctx->Dm != ctx->D) return fail(ctx, HMMCU_EINVAL, "models have D=%d but features have D=%d", ctx->Dm, ctx->D);
+  if (!ctx->pack_dirty) return HMMCU_OK;
+  const int64_t VG = (int64_t)ctx->V * ctx->G;
+  CK(ctx->mu32.ensure(sizeof(float) * VG * ctx->DP));
+  CK(ctx->iv32.ensure(sizeof(float) * VG * ctx->DP));
+  CK(ctx->k32.ensure(sizeof(float) * VG));
+  CK(ctx->ctr.ensure(sizeof(double) * ctx->DP));
+  if (ctx->F == 0) CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(double) * ctx->DP, ctx->st));
+  int64_t total = VG * ctx->DP;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+  t_begin(ctx, "pack");
+  k_pack_models<<<blocks, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                            ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->DP,
+                                            ctx->mu32.as<float>(), ctx->iv32.as<float>(), ctx->k32.as<float>());
+  LAUNCH_CHECK();
+  t_end(ctx, "pack");
+  ctx->pack_dirty = false;
+  return HMMCU_OK;
+}
+
+// --------------------------------------------------------------------------------- emissions ----
+static int emis_chunk_states(const hmmcu_ctx *ctx) { return std::max(1, std::min(ctx->N, 128 / ctx->M)); }
+
+}  // extern "C"
+template <bool POST>
+static int launch_emis(hmmcu_ctx *ctx, const EmisTile *tiles_dev, int64_t ntiles, float *logb, int64_t fbase, int64_t ldb,
+                       int decode, float *post) {
+  if (ntiles == 0) return HMMCU_OK;
+  const int SC = emis_chunk_states(ctx);
+  const size_t smem = emis_smem_bytes(SC * ctx->M, SC, ctx->DP);
+  if (smem > 227 * 1024) return fail(ctx, HMMCU_EINVAL, "M=%d mixtures x D=%d does not fit the emission kernel's shared memory", ctx->M, ctx->D);
+  CK(cudaFuncSetAttribute(k_emis_simt<POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_emis_simt<POST><<<(unsigned)ntiles, kEmisThreads, smem, ctx->st>>>(tiles_dev, ctx->x32.as<float>(), ctx->mu32.as<float>(),
+                                                                       ctx->iv32.as<float>(), ctx->k32.as<float>(), ctx->N,
+                                                                       ctx->M, ctx->DP, SC, logb, fbase, ldb, decode, post);
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
+extern "C" {
+int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
+  if (!ctx) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  int rc = ensure_packed(ctx);
+  if (rc) return rc;
+  if (u < 0 || u >= ctx->U || v < 0 || v >= ctx->V || !logb) return fail(ctx, HMMCU_EINVAL, "emissions: bad arguments");
+  const int64_t f0 = ctx->off[u];
+  const int T = (int)(ctx->off[u + 1] - f0);
+  std::vector<EmisTile> tiles;
+  for (int t = 0; t < T; t += kEmisTF) tiles.push_back({f0 + t, std::min(kEmisTF, T - t), v});
+  DevBuf tl, lb, ps;
+  CK(tl.ensure(sizeof(EmisTile) * tiles.size()));
+  CK(lb.ensure(sizeof(float) * T * ctx->N));
+  CK(ps.ensure(sizeof(float) * (size_t)T * ctx->G));
+  CK(cudaMemcpyAsync(tl.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+  // post is indexed by global frame: offset the pointer so that frame f0 lands at ps[0]
+  rc = launch_emis<true>(ctx, tl.as<EmisTile>(), (int64_t)tiles.size(), lb.as<float>(), f0, ctx->N, 0,
+                         ps.as<float>() - f0 * ctx->G);
+  if (rc) return rc;
+  std::vector<float> hl((size_t)T * ctx->N), hp((size_t)T * ctx->G);
+  CK(cudaMemcpyAsync(hl.data(), lb.p, sizeof(float) * hl.size(), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(hp.data(), ps.p, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (size_t k = 0; k < hl.size(); k++) logb[k] = (double)hl[k];
+  if (post)
+    for (size_t k = 0; k < hp.size(); k++) post[k] = (double)hp[k];
+  tl.release(); lb.release(); ps.release();
+  return HMMCU_OK;
+}
+
+// ----------------------------------------------------------------------- decode (all cells) ----
+}  // extern "C"
+template <int NS> struct ScoreLaunch {
+  static void fwd(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, int emulate) {
+    dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
+    k_fwd_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
+                                                         ctx->A.as<double>(), out, emulate);
+  }
+  static void vit(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out) {
+    dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
+    k_viterbi_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
+                                                             ctx->A.as<double>(), out);
+  }
+};
+
+#define DISPATCH_N(n, stmt)                       \
+  switch (n) {                                    \
+    case 1: { constexpr int NS = 1; stmt; } break; \
+    case 2: { constexpr int NS = 2; stmt; } break; \
+    case 3: { constexpr int NS = 3; stmt; } break; \
+    case 4: { constexpr int NS = 4; stmt; } break; \
+    case 5: { constexpr int NS = 5; stmt; } break; \
+    case 6: { constexpr int NS = 6; stmt; } break; \
+    case 7: { constexpr int NS = 7; stmt; } break; \
+    case 8: { constexpr int NS = 8; stmt; } break; \
+    default: return fail(ctx, HMMCU_EINVAL, "N=%d states not supported", n); \
+  }
+
+// mode 0: forward score, 1: Viterbi score
+static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
+  if (!ctx || !out_host) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  int rc = ensure_packed(ctx);
+  if (rc) return rc;
+  if (ctx->U == 0) return HMMCU_OK;
+  const int64_t S = (int64_t)ctx->V * ctx->N;
+  CK(ctx->score_d.ensure(sizeof(double) * (size_t)ctx->U * ctx->V));
+  // utterance batches so that the log-emission buffer stays under ~2 GiB
+  const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, (int64_t)(2048ll << 20) / (4 * S));
+  int u0 = 0;
+  std::vector<EmisTile> tiles;
+  while (u0 < ctx->U) {
+    int u1 = u0;
+    while (u1 < ctx->U && ctx->off[u1 + 1] - ctx->off[u0] <= budget_frames) u1++;
+    if (u1 == u0) u1 = u0 + 1;
+    const int64_t fb0 = ctx->off[u0], fb1 = ctx->off[u1];
+    CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
+    tiles.clear();
+    for (int64_t f = fb0; f < fb1; f += kEmisTF)
+      for (int v = 0; v < ctx->V; v++) tiles.push_back({f, (int)std::min<int64_t>(kEmisTF, fb1 - f), v});
+    CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
+    CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // `tiles` is reused by the next batch
+    t_begin(ctx, "emis");
+    rc = launch_emis<false>(ctx, ctx->tiles_dec.as<EmisTile>(), (int64_t)tiles.size(), ctx->logb.as<float>(), fb0, S, 1, nullptr);
+    if (rc) return rc;
+    t_end(ctx, "emis");
+    t_begin(ctx, mode == 0 ? "score" : "viterbi");
+    if (mode == 0) {
+      DISPATCH_N(ctx->N, ScoreLaunch<NS>::fwd(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>(), emulate));
+    } else {
+      DISPATCH_N(ctx->N, ScoreLaunch<NS>::vit(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>()));
+    }
+    LAUNCH_CHECK();
+    t_end(ctx, mode == 0 ? "score" : "viterbi");
+    u0 = u1;
+  }
+  CK(cudaMemcpyAsync(out_host, ctx->score_d.p, sizeof(double) * (size_t)ctx->U * ctx->V, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+extern "C" {
+int hmmcu_forward_scores(hmmcu_ctx *ctx, double *logp, int emulate_underflow) { return score_all(ctx, logp, 0, emulate_underflow); }
+int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score) { return score_all(ctx, score, 1, 0); }
+
+int hmmcu_rank(hmmcu_ctx *ctx, const double *logp, int U, int V, double weight, int32_t *label, int32_t *second) {
+  if (!ctx || !logp || !label || U < 0 || V < 1) return fail(ctx, HMMCU_EINVAL, "rank: bad arguments");
+  if (U == 0) return HMMCU_OK;
+  CK(cudaSetDevice(ctx->dev));
+  CK(ctx->rank_in.ensure(sizeof(double) * (size_t)U * V));
+  CK(ctx->rank_out.ensure(sizeof(int32_t) * 2 * (size_t)U));
+  CK(cudaMemcpyAsync(ctx->rank_in.p, logp, sizeof(double) * (size_t)U * V, cudaMemcpyHostToDevice, ctx->st));
+  k_rank<<<(U + 127) / 128, 128, 0, ctx->st>>>(ctx->rank_in.as<double>(), U, V, weight, ctx->rank_out.as<int32_t>(),
+                                               ctx->rank_out.as<int32_t>() + U);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(label, ctx->rank_out.p, sizeof(int32_t) * U, cudaMemcpyDeviceToHost, ctx->st));
+  if (second) CK(cudaMemcpyAsync(second, ctx->rank_out.as<int32_t>() + U, sizeof(int32_t) * U, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+// ------------------------------------------------------------------------------------ E-step ----
+static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
+  const int U = ctx->U, V = ctx->V;
+  if ((int)ctx->u2m.size() == U && memcmp(ctx->u2m.data(), utt2model, sizeof(int32_t) * U) == 0) return HMMCU_OK;
+  for (int u = 0; u < U; u++)
+    if (utt2model[u] < -1 || utt2model[u] >= V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, utt2model[u]);
+  std::vector<int32_t> start(V + 1, 0), utts(U);
+  for (int u = 0; u < U; u++)
+    if (utt2model[u] >= 0) start[utt2model[u] + 1]++;  // -1 = utterance masked out of this E-step
+  ctx->max_utts_per_model = 0;
+  for (int v = 0; v < V; v++) {
+    ctx->max_utts_per_model = std::max(ctx->max_utts_per_model, start[v + 1]);
+    start[v + 1] += start[v];
+  }
+  std::vector<int32_t> fill(start.begin(), start.end() - 1);
+  for (int u = 0; u < U; u++)
+    if (utt2model[u] >= 0) utts[fill[utt2model[u]]++] = u;
+  std::vector<EmisTile> tiles;
+  for (int u = 0; u < U; u++) {
+    if (utt2model[u] < 0) continue;
+    const int64_t f0 = ctx->off[u];
+    const int T = (int)(ctx->off[u + 1] - f0);
+    for (int t = 0; t < T; t += kEmisTF) tiles.push_back({f0 + t, std::min(kEmisTF, T - t), utt2model[u]});
+  }
+  ctx->n_train_tiles = (int64_t)tiles.size();
+  CK(ctx->u2m_d.ensure(sizeof(int32_t) * std::max(U, 1)));
+  CK(ctx->mus_d.ensure(sizeof(int32_t) * (V + 1)));
+  CK(ctx->mu_d.ensure(sizeof(int32_t) * std::max(U, 1)));
+  CK(ctx->tiles_d.ensure(sizeof(EmisTile) * std::max<size_t>(tiles.size(), 1)));
+  CK(cudaMemcpyAsync(ctx->u2m_d.p, utt2model, sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->mus_d.p, start.data(), sizeof(int32_t) * (V + 1), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->mu_d.p, utts.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->tiles_d.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->u2m.assign(utt2model, utt2model + U);
+  return HMMCU_OK;
+}
+
+int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double *logp_utt) {
+  if (!ctx) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  int rc = ensure_packed(ctx);
+  if (rc) return rc;
+  if (ctx->U > 0 && !utt2model) return fail(ctx, HMMCU_EINVAL, "estep: utt2model is NULL");
+  const int N = ctx->N, M = ctx->M, D = ctx->D, DP = ctx->DP, G = ctx->G, V = ctx->V, U = ctx->U;
+  const int64_t ss = hmmcu_stats_size(N, M, D);
+  const int64_t off_S0 = (int64_t)N * N + 2 * N, off_S1 = off_S0 + G, off_S2 = off_S1 + (int64_t)G * D,
+                off_lp = off_S2 + (int64_t)G * D;
+  ctx->stats_n = ss * V;
+  CK(ctx->stats.ensure(sizeof(double) * ctx->stats_n));
+  CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
+  if (U > 0) {
+    rc = set_train_map(ctx, utt2model);
+    if (rc) return rc;
+    const int64_t F = ctx->F;
+    CK(ctx->logb.ensure(sizeof(float) * F * N));
+    CK(ctx->post.ensure(sizeof(float) * F * G));
+    CK(ctx->gamma.ensure(sizeof(float) * F * N));
+    CK(ctx->alpha_ws.ensure(sizeof(double) * F * N));
+    CK(ctx->cs_ws.ensure(sizeof(double) * F));
+    CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
+    // 1. emissions + per-mixture posteriors
+    t_begin(ctx, "emis");
+    rc = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
+    if (rc) return rc;
+    t_end(ctx, "emis");
+    // 2. forward / backward, gamma, transition statistics, log-probabilities
+    t_begin(ctx, "fwdbwd");
+    {
+      const int blocks = (U + kFbWarps - 1) / kFbWarps;
+      DISPATCH_N(N, (k_fwdbwd<NS><<<blocks, kFbWarps * 32, 0, ctx->st>>>(
+                        ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
+                        ctx->alpha_ws.as<double>(), ctx->cs_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                        ss, off_lp, ctx->logp_utt_d.as<double>())));
+      LAUNCH_CHECK();
+    }
+    t_end(ctx, "fwdbwd");
+    // 3. mixture accumulators
+    t_begin(ctx, "accum");
+    {
+      const int NGG = kAccThreads / DP, GCH = NGG * kAccGPT;
+      const int nz = (G + GCH - 1) / GCH;
+      int nparts = std::max(1, (2 * ctx->sm_count + V * nz - 1) / (V * nz));
+      nparts = std::min(nparts, std::max(1, ctx->max_utts_per_model));
+      const size_t smem = sizeof(float) * (size_t)kAccTF * (DP + GCH);
+      dim3 grid(nparts, V, nz);
+      k_accum_simt<<<grid, kAccThreads, smem, ctx->st>>>(ctx->x32.as<float>(), ctx->gamma.as<float>(), ctx->post.as<float>(),
+                                                         ctx->mu32.as<float>(), ctx->off_d.as<int64_t>(),
+                                                         ctx->mus_d.as<int32_t>(), ctx->mu_d.as<int32_t>(), N, M, D, DP, nparts,
+                                                         ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2);
+      LAUNCH_CHECK();
+      const int64_t total = (int64_t)V * G * D;
+      k_finalize_stats<<<(unsigned)((total + 255) / 256), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, V, G, D, off_S0, off_S1,
+                                                                            ctx->ctr.as<double>());
+      LAUNCH_CHECK();
+    }
+    t_end(ctx, "accum");
+  }
+  if (logp_utt && U > 0) CK(cudaMemcpyAsync(logp_utt, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
+  if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
+  if (stats || logp_utt) CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+double *hmmcu_stats_device(hmmcu_ctx *ctx, int64_t *n_doubles) {
+  if (!ctx) return nullptr;
+  if (n_doubles) *n_doubles = ctx->stats_n;
+  return ctx->stats.as<double>();
+}
+
+int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats) {
+  if (!ctx || !stats) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+// ----------------------------------------------------------------------------------- Viterbi ----
+int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32_t *path) {
+  if (!ctx) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  if (!ctx->have_features || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "features and models must both be set first");
+  if (ctx->U == 0) return HMMCU_OK;
+  if (!utt2model || !score) return fail(ctx, HMMCU_EINVAL, "viterbi: bad arguments");
+  const int U = ctx->U;
+  for (int u = 0; u < U; u++)
+    if (utt2model[u] < 0 || utt2model[u] >= ctx->V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, utt2model[u]);
+  DevBuf map;
+  CK(map.ensure(sizeof(int32_t) * U));
+  CK(cudaMemcpyAsync(map.p, utt2model, sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+  CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
+  CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
+  CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
+  t_begin(ctx, "viterbi");
+  DISPATCH_N(ctx->N, (k_viterbi_path64<NS><<<(U + 1) / 2, 64, 0, ctx->st>>>(
+                         ctx->d_x64, ctx->off_d.as<int64_t>(), map.as<int32_t>(), ctx->A.as<double>(), ctx->c.as<double>(),
+                         ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), U, ctx->M, ctx->D,
+                         ctx->psi_ws.as<unsigned long long>(), ctx->logp_utt_d.as<double>(), ctx->path_d.as<int32_t>())));
+  LAUNCH_CHECK();
+  t_end(ctx, "viterbi");
+  CK(cudaMemcpyAsync(score, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
+  if (path) CK(cudaMemcpyAsync(path, ctx->path_d.p, sizeof(int32_t) * ctx->F, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  map.release();
+  return HMMCU_OK;
+}
+
+}  // extern "C"

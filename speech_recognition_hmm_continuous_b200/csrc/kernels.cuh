@@ -1,0 +1,737 @@
+// kernels.cuh -- CUDA kernels (sm_100a) of the continuous-HMM hot path: feature / model packing,
+// Gaussian-mixture emissions, scaled forward / backward with Baum-Welch accumulation, forward
+// scoring, Viterbi, ranking.  Reference rows are those of SURVEY.md section 8a:
+//   T-FS = train/source/hmm-fs/hmm_continuous_fs.c, R-FS = test/source/recognition-fs/...
+//
+// Numerical plan: features and means are centred per dimension in double
+// and stored in single precision; emissions are single-precision LOG densities; the recursions
+// keep their state (alpha^, beta~, c~) in double and rescale every frame by the frame's largest
+// log-density, which is algebraically the reference's 1/sum(alpha) scaling but cannot underflow;
+// sufficient statistics are accumulated block-locally in single precision over bounded spans and
+// flushed with double-precision atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace hmmk {
+
+constexpr float kNegInf = -INFINITY;
+// log of the smallest positive double (4.94e-324): below this the reference's linear-domain
+// densities are exactly 0.
+constexpr double kLogTrueMin = -744.4400719213812;
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------------
+// centre: per-dimension mean of up to 4096 evenly strided frames (deterministic, one block).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_center(const double *__restrict__ x, int64_t F, int D, int DP, double *__restrict__ ctr) {
+  __shared__ double part[16][64];
+  const int d = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 1024 threads = 64 dims x 16 groups
+  int64_t ns = F < 4096 ? F : 4096;
+  int64_t stride = F / ns;
+  for (int d0 = 0; d0 < DP; d0 += 64) {
+    double s = 0.0;
+    if (d0 + d < D)
+      for (int64_t k = grp; k < ns; k += 16) s += x[(k * stride) * D + d0 + d];
+    part[grp][d] = s;
+    __syncthreads();
+    if (grp == 0 && d0 + d < DP) {
+      double t = 0.0;
+      for (int g = 0; g < 16; g++) t += part[g][d];
+      ctr[d0 + d] = (d0 + d < D) ? t / (double)ns : 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+// x64[F][D] -> x32[F][DP] = (float)(x - ctr); column D holds 1.0 (so that the first-order
+// accumulator of that column is the occupancy S0), remaining pad columns 0.
+__global__ void k_pack_features(const double *__restrict__ x, const double *__restrict__ ctr, int64_t F, int D,
+                                int DP, float *__restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = F * DP;
+  for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t f = idx / DP;
+    int d = (int)(idx - f * DP);
+    float v;
+    if (d < D) v = (float)(x[f * D + d] - ctr[d]);
+    else v = (d == D) ? 1.0f : 0.0f;
+    out[idx] = v;
+  }
+}
+
+// Per Gaussian g (global index over V*N*M): mu32[g][DP] = mu - ctr, iv32[g][DP] = inverse variance
+// (0 in the pad columns), k32[g] = log c - 0.5 (D log 2pi + log|det|)   [calc_gaus T-FS:1821-1836 in
+// log form; c == 0 or det == 0 give -inf, i.e. density 0].
+__global__ void k_pack_models(const double *__restrict__ mu, const double *__restrict__ iv,
+                              const double *__restrict__ det, const double *__restrict__ c,
+                              const double *__restrict__ ctr, int64_t VG, int D, int DP, float *__restrict__ mu32,
+                              float *__restrict__ iv32, float *__restrict__ k32) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = VG * DP;
+  for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = idx / DP;
+    int d = (int)(idx - g * DP);
+    if (d < D) {
+      mu32[idx] = (float)(mu[g * D + d] - ctr[d]);
+      iv32[idx] = (float)iv[g * D + d];
+    } else {
+      mu32[idx] = 0.f;
+      iv32[idx] = 0.f;
+    }
+    if (d == 0) {
+      double dt = det[g], cc = c[g];
+      double k = -INFINITY;
+      if (dt != 0.0 && cc > 0.0) k = log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt)));
+      k32[g] = (float)k;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Emissions, CUDA-core version (calc_symbol_probab + calc_gaus, T-FS:1749-1841 / R-FS:860-947).
+// One CTA = one tile of <= 64 frames against one model; Gaussians are processed in chunks of whole
+// states (<= kGC Gaussians) staged in shared memory.
+//   logb[(f - fbase) * ldb + colbase(v) + i] = log sum_m c_m N_m(x_f)
+//   post[f * G + i*M + m] = c_m N_m / b_i   (training only)
+// ------------------------------------------------------------------------------------------------
+struct EmisTile {
+  int64_t f0;  // first frame (global index)
+  int nf;      // frames in the tile (<= 64)
+  int v;       // model
+};
+
+constexpr int kEmisTF = 64;       // frames per tile
+constexpr int kEmisThreads = 256;
+
+// dynamic shared memory: par[GC][DP] float2 (mu, iv) | xs[DP][64] | lnt[GC][65] | lbs[SC][64]
+__host__ __device__ inline size_t emis_smem_bytes(int GC, int SC, int DP) {
+  return sizeof(float) * ((size_t)GC * DP * 2 + (size_t)DP * kEmisTF + (size_t)GC * (kEmisTF + 1) + (size_t)SC * kEmisTF) + 16;
+}
+
+template <bool POST>
+__global__ void __launch_bounds__(kEmisThreads)
+k_emis_simt(const EmisTile *__restrict__ tiles, const float *__restrict__ x32, const float *__restrict__ mu32,
+            const float *__restrict__ iv32, const float *__restrict__ k32, int N, int M, int DP, int SC,
+            float *__restrict__ logb, int64_t fbase, int64_t ldb, int decode, float *__restrict__ post) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = N * M;
+  const int GC = SC * M;
+  float2 *par = reinterpret_cast<float2 *>(smem);
+  float *xs = smem + (size_t)GC * DP * 2;
+  float *lnt = xs + (size_t)DP * kEmisTF;
+  float *lbs = lnt + (size_t)GC * (kEmisTF + 1);
+
+  const EmisTile tile = tiles[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fh = warp & 1, gq = warp >> 1;  // frame half, Gaussian-group phase
+  const int fl = fh * 32 + lane;            // my frame inside the tile
+
+  // stage x transposed: xs[d][f]
+  for (int idx = tid; idx < kEmisTF * DP; idx += kEmisThreads) {
+    int f = idx / DP, d = idx - f * DP;
+    xs[d * kEmisTF + f] = (f < tile.nf) ? x32[(tile.f0 + f) * DP + d] : 0.f;
+  }
+  const int64_t gbase = (int64_t)tile.v * G;
+  const int64_t col0 = decode ? (int64_t)tile.v * N : 0;
+
+  for (int s0 = 0; s0 < N; s0 += SC) {
+    const int sc = min(SC, N - s0);
+    const int gc = sc * M;
+    const int64_t g0 = gbase + (int64_t)s0 * M;
+    __syncthreads();  // xs ready / previous chunk fully consumed
+    for (int idx = tid; idx < gc * DP; idx += kEmisThreads)
+      par[idx] = make_float2(mu32[g0 * DP + idx], iv32[g0 * DP + idx]);
+    __syncthreads();
+    // quadratic forms: 4 Gaussians per pass per thread
+    for (int j = gq * 4; j < gc; j += 16) {
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+      const int j1 = min(j + 1, gc - 1), j2 = min(j + 2, gc - 1), j3 = min(j + 3, gc - 1);
+      const float2 *p0 = par + (size_t)j * DP, *p1 = par + (size_t)j1 * DP, *p2 = par + (size_t)j2 * DP,
+                   *p3 = par + (size_t)j3 * DP;
+#pragma unroll 4
+      for (int d = 0; d < DP; d++) {
+        const float xv = xs[d * kEmisTF + fl];
+        float2 a = p0[d], b = p1[d], c = p2[d], e = p3[d];
+        float t0 = xv - a.x, t1 = xv - b.x, t2 = xv - c.x, t3 = xv - e.x;
+        q0 = fmaf(t0 * a.y, t0, q0);
+        q1 = fmaf(t1 * b.y, t1, q1);
+        q2 = fmaf(t2 * c.y, t2, q2);
+        q3 = fmaf(t3 * e.y, t3, q3);
+      }
+      lnt[(size_t)j * (kEmisTF + 1) + fl] = fmaf(-0.5f, q0, k32[g0 + j]);
+      if (j + 1 < gc) lnt[(size_t)(j + 1) * (kEmisTF + 1) + fl] = fmaf(-0.5f, q1, k32[g0 + j + 1]);
+      if (j + 2 < gc) lnt[(size_t)(j + 2) * (kEmisTF + 1) + fl] = fmaf(-0.5f, q2, k32[g0 + j + 2]);
+      if (j + 3 < gc) lnt[(size_t)(j + 3) * (kEmisTF + 1) + fl] = fmaf(-0.5f, q3, k32[g0 + j + 3]);
+    }
+    __syncthreads();
+    // log-sum-exp over the mixtures of each state
+    for (int idx = tid; idx < sc * kEmisTF; idx += kEmisThreads) {
+      int s = idx / kEmisTF, f = idx - s * kEmisTF;
+      const float *col = lnt + (size_t)(s * M) * (kEmisTF + 1) + f;
+      float mx = kNegInf;
+      for (int m = 0; m < M; m++) mx = fmaxf(mx, col[(size_t)m * (kEmisTF + 1)]);
+      float lb = kNegInf;
+      if (mx > kNegInf) {
+        float sum = 0.f;
+        for (int m = 0; m < M; m++) sum += __expf(col[(size_t)m * (kEmisTF + 1)] - mx);
+        lb = mx + __logf(sum);
+      }
+      lbs[s * kEmisTF + f] = lb;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < tile.nf * sc; idx += kEmisThreads) {
+      int f = idx / sc, s = idx - f * sc;
+      logb[(tile.f0 + f - fbase) * ldb + col0 + s0 + s] = lbs[s * kEmisTF + f];
+    }
+    if (POST) {
+      for (int idx = tid; idx < tile.nf * gc; idx += kEmisThreads) {
+        int f = idx / gc, g = idx - f * gc;
+        float lb = lbs[(g / M) * kEmisTF + f];
+        float p = (lb > kNegInf) ? __expf(lnt[(size_t)g * (kEmisTF + 1) + f] - lb) : 0.f;
+        post[(tile.f0 + f) * G + (int64_t)s0 * M + g] = p;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training recursion: one warp per utterance (calc_alpha, calc_beta, calc_transition_probab,
+// calc_den_mix_coef, calc_probability; T-FS:1380-1664).  Lanes own frames for everything that is
+// parallel in time (exp, gamma, xi terms, stores); the N x N recurrences run redundantly on all
+// lanes with the per-frame operands broadcast by shuffle.
+//   b~_i(t) = exp(logb_i(t) - m_t), m_t = max_i logb_i(t)
+//   alpha^ as the reference; c~_t = 1/sum alpha~;   beta~_t = beta^_t e^{m_t}
+//   gamma_t(i) = alpha^_t(i) beta~_t(i) / c~_t      (= alpha^ beta^ / c_t of the reference)
+// Outputs: gamma32[F][N]; per-model statistics head (num_trans, den_trans, den_mix, sum_logp,
+// n_utt) by double atomics; logp_utt[U].
+// ------------------------------------------------------------------------------------------------
+constexpr int kFbWarps = 2;
+
+template <int NS>
+__global__ void __launch_bounds__(kFbWarps * 32)
+k_fwdbwd(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
+         const double *__restrict__ Aall, int U, double *__restrict__ alpha_ws, double *__restrict__ cs_ws,
+         float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
+         double *__restrict__ logp_utt) {
+  __shared__ double sA[kFbWarps][NS * NS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * kFbWarps + warp;
+  if (u >= U) return;
+  const int v = u2m[u];
+  if (v < 0) {  // masked utterance (its model has converged)
+    if (lane == 0 && logp_utt) logp_utt[u] = 0.0;
+    return;
+  }
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  for (int k = lane; k < NS * NS; k += 32) sA[warp][k] = Aall[(int64_t)v * NS * NS + k];
+  __syncwarp();
+  const double *A = sA[warp];
+
+  // ---------------- forward ----------------
+  double al[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) al[i] = 0.0;
+  double lp_acc = 0.0;
+  for (int c0 = 0; c0 < T; c0 += 32) {
+    const int t = c0 + lane;
+    const bool valid = t < T;
+    float lbv[NS];
+    float mt = kNegInf;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      lbv[i] = valid ? logb[(base + t) * NS + i] : 0.f;
+      mt = fmaxf(mt, lbv[i]);
+    }
+    double bt[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) bt[i] = (mt > kNegInf) ? exp((double)lbv[i] - (double)mt) : 0.0;
+    double my_al[NS], my_sum = 1.0, my_c = 1.0;
+#pragma unroll
+    for (int i = 0; i < NS; i++) my_al[i] = 0.0;
+    const int ns = min(32, T - c0);
+    for (int s = 0; s < ns; s++) {
+      double b[NS], an[NS];
+#pragma unroll
+      for (int i = 0; i < NS; i++) b[i] = __shfl_sync(0xffffffffu, bt[i], s);
+      if (c0 + s == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) an[i] = (i == 0 ? 1.0 : 0.0) * b[i];  // pi = [1,0,..] T-FS:232-234
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          double aux = 0.0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) aux += al[j] * A[j * NS + i];
+          an[i] = aux * b[i];
+        }
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; i++) sum += an[i];
+      const double cs = 1.0 / sum;
+#pragma unroll
+      for (int i = 0; i < NS; i++) al[i] = an[i] * cs;
+      if (lane == s) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) my_al[i] = al[i];
+        my_sum = sum;
+        my_c = cs;
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) alpha_ws[(base + t) * NS + i] = my_al[i];
+      cs_ws[base + t] = my_c;
+      lp_acc += (double)mt + log(my_sum);  // -log c_t
+    }
+  }
+  double lp = warp_sum(lp_acc) + log(al[NS - 1]);  // calc_probability T-FS:1546-1549
+
+  // ---------------- backward + accumulators ----------------
+  double be[NS], bnext[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) { be[i] = 0.0; bnext[i] = 0.0; }
+  double acc_num[NS][2], acc_dt[NS], acc_dm[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
+  const int clast = ((T - 1) / 32) * 32;
+  for (int c0 = clast; c0 >= 0; c0 -= 32) {
+    const int t = c0 + lane;
+    const bool valid = t < T;
+    float lbv[NS];
+    float mt = kNegInf;
+    double my_al[NS], my_c = 1.0;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      lbv[i] = valid ? logb[(base + t) * NS + i] : 0.f;
+      mt = fmaxf(mt, lbv[i]);
+      my_al[i] = valid ? alpha_ws[(base + t) * NS + i] : 0.0;
+    }
+    if (valid) my_c = cs_ws[base + t];
+    double bt[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) bt[i] = (mt > kNegInf) ? exp((double)lbv[i] - (double)mt) : 0.0;
+    double my_be[NS], my_benext[NS], my_bnext[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) { my_be[i] = 0.0; my_benext[i] = 0.0; my_bnext[i] = 0.0; }
+    const int ns = min(32, T - c0);
+    for (int s = ns - 1; s >= 0; s--) {
+      const double ct = __shfl_sync(0xffffffffu, my_c, s);
+      double bn[NS];
+      if (c0 + s == T - 1) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) bn[i] = (i == NS - 1 ? 1.0 : 0.0) * ct;  // final state only T-FS:1484-1490
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          double aux = 0.0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) aux += be[j] * A[i * NS + j] * bnext[j];
+          bn[i] = aux * ct;
+        }
+      }
+      if (lane == s) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) { my_be[i] = bn[i]; my_benext[i] = be[i]; my_bnext[i] = bnext[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        be[i] = bn[i];
+        bnext[i] = __shfl_sync(0xffffffffu, bt[i], s);
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        const double g = my_al[i] * my_be[i] / my_c;  // alpha*beta/scale T-FS:1617,1658,1709
+        gamma[(base + t) * NS + i] = (float)g;
+        acc_dm[i] += g;
+        if (t < T - 1) {
+          acc_dt[i] += g;
+          acc_num[i][0] += my_al[i] * A[i * NS + i] * my_bnext[i] * my_benext[i];  // band j = i
+          if (i + 1 < NS) acc_num[i][1] += my_al[i] * A[i * NS + i + 1] * my_bnext[i + 1] * my_benext[i + 1];  // j = i+1
+        }
+      }
+    }
+  }
+  double *st = stats + (int64_t)v * stats_stride;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
+    double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
+    if (lane == 0) {
+      atomicAdd(st + i * NS + i, n0);
+      if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
+      atomicAdd(st + NS * NS + i, dt);
+      atomicAdd(st + NS * NS + NS + i, dm);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(st + off_sumlogp, lp);
+    atomicAdd(st + off_sumlogp + 1, 1.0);
+    if (logp_utt) logp_utt[u] = lp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mixture accumulators (calc_mix_param, T-FS:1691-1727), CUDA-core version.
+// CTA (part p, model v, Gaussian chunk gcx) walks the utterances of model v assigned to part p.
+// Thread (d, gg) owns column d of kAccGPT Gaussians g = k*NGG + gg of the chunk:
+//   s1 += w x_d (centred x; column D is the constant 1 -> S0),  s2 += w (x_d - mu_old)^2
+// with w = gamma_t(state(g)) * post_t(g).  Flushed by double atomics every <= kAccFlush frames.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAccThreads = 256;
+constexpr int kAccGPT = 8;     // Gaussians per thread
+constexpr int kAccTF = 32;     // frames staged per step
+constexpr int kAccFlush = 4096;
+
+__global__ void __launch_bounds__(kAccThreads)
+k_accum_simt(const float *__restrict__ x32, const float *__restrict__ gamma, const float *__restrict__ post,
+             const float *__restrict__ mu32, const int64_t *__restrict__ off,
+             const int32_t *__restrict__ model_utt_start, const int32_t *__restrict__ model_utts, int N, int M,
+             int D, int DP, int nparts, double *__restrict__ stats, int64_t stats_stride, int64_t off_S0,
+             int64_t off_S1, int64_t off_S2) {
+  extern __shared__ __align__(16) float smem[];
+  const int G = N * M;
+  const int NGG = kAccThreads / DP;   // Gaussian groups
+  const int GCH = NGG * kAccGPT;      // Gaussians per chunk
+  float *xs = smem;                   // [kAccTF][DP]
+  float *ws = smem + kAccTF * DP;     // [kAccTF][GCH]
+  const int part = blockIdx.x, v = blockIdx.y, g0 = blockIdx.z * GCH;
+  const int tid = threadIdx.x;
+  const int d = tid % DP, gg = tid / DP;
+  const bool active = gg < NGG;
+  const int gcn = min(GCH, G - g0);
+
+  float s1[kAccGPT], s2[kAccGPT], mu[kAccGPT];
+#pragma unroll
+  for (int k = 0; k < kAccGPT; k++) {
+    s1[k] = 0.f; s2[k] = 0.f;
+    int g = k * NGG + gg;
+    mu[k] = (active && g < gcn) ? mu32[((int64_t)v * G + g0 + g) * DP + d] : 0.f;
+  }
+  double *st = stats + (int64_t)v * stats_stride;
+  int since_flush = 0;
+
+  auto flush = [&]() {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < kAccGPT; k++) {
+        int g = k * NGG + gg;
+        if (g < gcn) {
+          if (d < D) {
+            atomicAdd(st + off_S1 + (int64_t)(g0 + g) * D + d, (double)s1[k]);
+            atomicAdd(st + off_S2 + (int64_t)(g0 + g) * D + d, (double)s2[k]);
+          } else if (d == D) {
+            atomicAdd(st + off_S0 + g0 + g, (double)s1[k]);
+          }
+        }
+        s1[k] = 0.f; s2[k] = 0.f;
+      }
+    }
+  };
+
+  const int ub = model_utt_start[v], ue = model_utt_start[v + 1];
+  for (int ui = ub + part; ui < ue; ui += nparts) {
+    const int u = model_utts[ui];
+    const int64_t base = off[u];
+    const int T = (int)(off[u + 1] - base);
+    for (int t0 = 0; t0 < T; t0 += kAccTF) {
+      const int nt = min(kAccTF, T - t0);
+      __syncthreads();
+      for (int idx = tid; idx < nt * DP; idx += kAccThreads) xs[idx] = x32[(base + t0) * DP + idx];
+      for (int idx = tid; idx < nt * gcn; idx += kAccThreads) {
+        int t = idx / gcn, g = idx - t * gcn;
+        float gm = gamma[(base + t0 + t) * N + (g0 + g) / M];
+        ws[t * GCH + g] = gm * post[(base + t0 + t) * G + g0 + g];
+      }
+      __syncthreads();
+      if (active) {
+        for (int t = 0; t < nt; t++) {
+          const float xv = xs[t * DP + d];
+          const float *wr = ws + t * GCH + gg;
+#pragma unroll
+          for (int k = 0; k < kAccGPT; k++) {
+            const float w = wr[k * NGG];
+            const float dif = xv - mu[k];
+            s1[k] = fmaf(w, xv, s1[k]);
+            s2[k] = fmaf(w * dif, dif, s2[k]);
+          }
+        }
+      }
+      since_flush += nt;
+      if (since_flush >= kAccFlush) { flush(); since_flush = 0; }
+    }
+  }
+  flush();
+}
+
+// S1 was accumulated on centred features: S1 += ctr * S0  (before any cross-rank reduction).
+__global__ void k_finalize_stats(double *__restrict__ stats, int64_t stats_stride, int V, int G, int D,
+                                 int64_t off_S0, int64_t off_S1, const double *__restrict__ ctr) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = (int64_t)V * G * D;
+  if (idx >= total) return;
+  int d = (int)(idx % D);
+  int64_t vg = idx / D;
+  int g = (int)(vg % G);
+  int64_t v = vg / G;
+  double *st = stats + v * stats_stride;
+  st[off_S1 + (int64_t)g * D + d] += ctr[d] * st[off_S0 + g];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode recursions: one THREAD per (utterance, model) cell; a warp covers 32 consecutive models
+// of one utterance so that every frame is one contiguous 32*N-float read of logb[f][V*N].
+// ------------------------------------------------------------------------------------------------
+constexpr int kScoreThreads = 128;
+
+// forward score (calc_alpha + calc_probability, R-FS:739-836)
+template <int NS>
+__global__ void __launch_bounds__(kScoreThreads)
+k_fwd_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off, int u0,
+            int V, const double *__restrict__ Aall, double *__restrict__ out, int emulate) {
+  const int v = blockIdx.x * kScoreThreads + threadIdx.x;
+  const int u = u0 + blockIdx.y;
+  if (v >= V) return;
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  double A[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) A[k] = Aall[(int64_t)v * NS * NS + k];
+  double al[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) al[i] = 0.0;
+  double lp = 0.0;
+  const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
+  for (int t = 0; t < T; t++, p += ldb) {
+    float lbv[NS];
+    float mt = kNegInf;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      lbv[i] = p[i];
+      if (emulate && (double)lbv[i] < kLogTrueMin) lbv[i] = kNegInf;  // the reference's density is exactly 0
+      mt = fmaxf(mt, lbv[i]);
+    }
+    double an[NS];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      double aux;
+      if (t == 0) aux = (i == 0) ? 1.0 : 0.0;
+      else {
+        aux = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; j++) aux += al[j] * A[j * NS + i];
+      }
+      double b = (mt > kNegInf) ? exp((double)lbv[i] - (double)mt) : 0.0;
+      an[i] = aux * b;
+      if (emulate && an[i] > 0.0 && log(an[i]) + (double)mt < kLogTrueMin) an[i] = 0.0;  // product underflow
+      sum += an[i];
+    }
+    const double cs = 1.0 / sum;
+#pragma unroll
+    for (int i = 0; i < NS; i++) al[i] = an[i] * cs;
+    lp += (double)mt + log(sum);
+  }
+  out[(int64_t)u * V + v] = lp + log(al[NS - 1]);
+}
+
+// Viterbi score, all cells (V1; no reference code).  delta in double, log domain.
+template <int NS>
+__global__ void __launch_bounds__(kScoreThreads)
+k_viterbi_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off,
+                int u0, int V, const double *__restrict__ Aall, double *__restrict__ out) {
+  const int v = blockIdx.x * kScoreThreads + threadIdx.x;
+  const int u = u0 + blockIdx.y;
+  if (v >= V) return;
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  double LA[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) LA[k] = log(Aall[(int64_t)v * NS * NS + k]);
+  double dl[NS];
+  const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
+#pragma unroll
+  for (int i = 0; i < NS; i++) dl[i] = (i == 0 ? 0.0 : -INFINITY) + (double)p[i];
+  p += ldb;
+  for (int t = 1; t < T; t++, p += ldb) {
+    double dn[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+      double best = dl[0] + LA[j];
+#pragma unroll
+      for (int i = 1; i < NS; i++) {
+        double c = dl[i] + LA[i * NS + j];
+        if (c > best) best = c;
+      }
+      dn[j] = best + (double)p[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NS; j++) dl[j] = dn[j];
+  }
+  out[(int64_t)u * V + v] = dl[NS - 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Viterbi with back-pointers for (utterance, its model) pairs in DOUBLE precision end to end:
+// emissions are recomputed from the double masters so that state sequences agree with a
+// double-precision CPU restatement.  One warp per utterance; lanes own frames for the emissions,
+// the delta recursion runs on all lanes; psi rows (N bytes per frame) go to a workspace and are
+// walked back in chunks of 32 frames.
+// ------------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(64)
+k_viterbi_path64(const double *__restrict__ x64, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
+                 const double *__restrict__ Aall, const double *__restrict__ call, const double *__restrict__ muall,
+                 const double *__restrict__ ivall, const double *__restrict__ detall, int U, int M, int D,
+                 unsigned long long *__restrict__ psi_ws, double *__restrict__ score, int32_t *__restrict__ path) {
+  __shared__ double sLA[2][NS * NS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * 2 + warp;
+  if (u >= U) return;
+  const int v = u2m[u];
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  for (int k = lane; k < NS * NS; k += 32) sLA[warp][k] = log(Aall[(int64_t)v * NS * NS + k]);
+  __syncwarp();
+  const double *LA = sLA[warp];
+  const int G = NS * M;
+  const double *c = call + (int64_t)v * G, *mu = muall + (int64_t)v * G * D, *iv = ivall + (int64_t)v * G * D,
+               *det = detall + (int64_t)v * G;
+  const double lognorm = 0.5 * (double)D * 1.8378770664093453;
+
+  double dl[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) dl[i] = 0.0;
+  for (int c0 = 0; c0 < T; c0 += 32) {
+    const int t = c0 + lane;
+    const bool valid = t < T;
+    double lb[NS];
+    // double-precision emissions of my frame: log sum_m c_m N_m  (log-sum-exp over mixtures)
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      double mx = -INFINITY, acc = 0.0;
+      if (valid) {
+        for (int m = 0; m < M; m++) {
+          const int g = i * M + m;
+          double q = 0.0;
+          const double *xr = x64 + (base + t) * D;
+          for (int d = 0; d < D; d++) {
+            double dif = xr[d] - mu[(int64_t)g * D + d];
+            q += dif * iv[(int64_t)g * D + d] * dif;
+          }
+          double dt = det[g], cc = c[g];
+          double ln = (dt != 0.0 && cc > 0.0) ? log(cc) - 0.5 * q - lognorm - 0.5 * log(fabs(dt)) : -INFINITY;
+          if (ln > mx) { acc = acc * exp(mx - ln) + 1.0; mx = ln; }
+          else if (ln > -INFINITY) acc += exp(ln - mx);
+        }
+      }
+      lb[i] = (mx > -INFINITY) ? mx + log(acc) : -INFINITY;
+    }
+    unsigned long long my_psi = 0ull;
+    const int ns = min(32, T - c0);
+    for (int s = 0; s < ns; s++) {
+      double b[NS], dn[NS];
+      unsigned long long ps = 0ull;
+#pragma unroll
+      for (int i = 0; i < NS; i++) b[i] = __shfl_sync(0xffffffffu, lb[i], s);
+      if (c0 + s == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) dn[i] = (i == 0 ? 0.0 : -INFINITY) + b[i];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+          double best = dl[0] + LA[j];
+          int arg = 0;
+#pragma unroll
+          for (int i = 1; i < NS; i++) {
+            double cnd = dl[i] + LA[i * NS + j];
+            if (cnd > best) { best = cnd; arg = i; }  // strict: lowest index wins a tie
+          }
+          dn[j] = best + b[j];
+          ps |= (unsigned long long)arg << (8 * j);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; i++) dl[i] = dn[i];
+      if (lane == s) my_psi = ps;
+    }
+    if (valid) psi_ws[base + t] = my_psi;
+  }
+  if (lane == 0) score[u] = dl[NS - 1];
+  // back-trace, final state N-1
+  int sidx = NS - 1;
+  const int clast = ((T - 1) / 32) * 32;
+  for (int c0 = clast; c0 >= 0; c0 -= 32) {
+    const int t = c0 + lane;
+    unsigned long long my_psi = (t < T) ? psi_ws[base + t] : 0ull;
+    int my_state = 0;
+    const int ns = min(32, T - c0);
+    for (int s = ns - 1; s >= 0; s--) {
+      if (lane == s) my_state = sidx;
+      unsigned long long ps = __shfl_sync(0xffffffffu, my_psi, s);
+      sidx = (int)((ps >> (8 * sidx)) & 0xffull);
+    }
+    if (t < T) path[base + t] = my_state;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ranking (sorting_probab + label rule, R-FS:968-995 and 380-388) without sorting: a NaN never
+// moves in the reference's bubble sort, every NaN-free run is sorted descending and stably on its
+// own; only positions 0 and 1 of the result are consumed.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rank(const double *__restrict__ logp, int U, int V, double weight, int32_t *__restrict__ label,
+                       int32_t *__restrict__ second) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const double *s = logp + (int64_t)u * V;
+  auto val = [&](int k) { return 0.0 + weight * s[k]; };  // probab[k] += coef_model*logP, R-FS:366
+  // run containing position 0: [0, e0)
+  int first, sec;
+  if (isnan(val(0))) {
+    first = 0;
+    // position 1: NaN stays; else max of run starting at 1
+    if (V < 2) sec = 0;
+    else if (isnan(val(1))) sec = 1;
+    else {
+      int best = 1;
+      for (int k = 2; k < V && !isnan(val(k)); k++)
+        if (val(k) > val(best)) best = k;
+      sec = best;
+    }
+  } else {
+    int best = 0, e0 = 1;
+    for (; e0 < V && !isnan(val(e0)); e0++)
+      if (val(e0) > val(best)) best = e0;
+    first = best;
+    if (V < 2) sec = 0;
+    else if (e0 < 2) sec = 1;  // position 1 is a NaN
+    else {
+      int b2 = -1;
+      for (int k = 0; k < e0; k++) {
+        if (k == best) continue;
+        if (b2 < 0 || val(k) > val(b2)) b2 = k;
+      }
+      sec = b2;
+    }
+  }
+  label[u] = first;
+  if (second) second[u] = sec;
+}
+
+}  // namespace hmmk

@@ -1,0 +1,330 @@
+"""Parity of the CUDA path (through the C ABI, libhmmcu.so) against the CPU oracle and the golden
+vectors the reference produced.  Tolerances are BASELINE.json's: labels and Viterbi state sequences
+bit-exact; log-likelihoods and re-estimated parameters within 1e-4 relative."""
+import glob
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+from oracle import ref as r
+from speech_recognition_hmm_continuous_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4  # north_star tolerance for floating-point results
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_model(ms, v):
+    return o.Model(ms.A[v], ms.c[v], ms.mu[v], ms.iv[v], ms.det[v], ms.words[v])
+
+
+def _synth(V, N, M, U, seed, tmin=60, tmax=120, D=39):
+    cen, s = synth.make_centres(V, N, M, D, seed=seed)
+    labels = np.arange(U) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=seed + 1, tmin=tmin, tmax=tmax)
+    ms = api.ModelSet.from_dict(synth.make_models(cen, s))
+    return ms, x, off, labels
+
+
+def _assert_params_close(ms, v, mo, tol=RTOL):
+    var_g, var_o = 1.0 / ms.iv[v], 1.0 / mo.iv
+    assert np.allclose(ms.A[v], mo.A, rtol=tol, atol=1e-12), "transitions"
+    assert np.allclose(ms.c[v], mo.c, rtol=tol, atol=1e-9), "weights"
+    assert np.allclose(var_g, var_o, rtol=tol), "variances"
+    assert (np.abs(ms.mu[v] - mo.mu) <= tol * np.maximum(np.abs(mo.mu), np.sqrt(var_o))).all(), "means"
+
+
+# ------------------------------------------------------------------------------- emissions ----
+@pytest.mark.parametrize("N,M", [(5, 3), (5, 16), (3, 128), (6, 1), (1, 1), (8, 2)])
+def test_emissions_match_oracle(ctx, N, M):
+    ms, x, off, labels = _synth(2, N, M, 3, seed=100 + N * M, tmin=50, tmax=130)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    for u, v in ((0, 0), (1, 1), (2, 1)):
+        logb, post = ctx.emissions(u, v)
+        b, p = o.emissions(_oracle_model(ms, v), x[off[u]:off[u + 1]])
+        with np.errstate(divide="ignore"):
+            lb = np.log(b)
+        fin = np.isfinite(lb)
+        assert np.allclose(logb[fin], lb[fin], rtol=2e-6, atol=2e-4)
+        assert np.abs(post - p).max() < 2e-4
+
+
+# ------------------------------------------------------------------------- forward scoring ----
+def test_forward_scores_and_labels_match_oracle(ctx):
+    ms, x, off, labels = _synth(7, 5, 3, 21, seed=7)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    got = ctx.forward_scores()
+    want = np.array([[o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]]) for v in range(ms.V)] for u in range(len(labels))])
+    assert np.allclose(got, want, rtol=RTOL, atol=0)
+    assert np.abs(got / want - 1).max() < 1e-6  # in practice far inside the bar
+    label, second = ctx.rank(got)
+    order = np.stack([o.rank(w) for w in want])
+    assert (label == order[:, 0]).all() and (second == order[:, 1]).all()
+    assert (label == labels).all()
+
+
+def test_golden_synth_c1_recognition(ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "synth_c1.npz"))
+    V, N, M, D = int(g["V"]), int(g["N"]), int(g["M"]), int(g["D"])
+    cen, s = synth.make_centres(V, N, M, D, seed=1234)
+    xt, offt = synth.make_utterances(cen, s, g["test_labels"], seed=4321, tmin=70, tmax=110)
+    ms = api.ModelSet(g["trained_A"], g["trained_c"], g["trained_mu"], g["trained_iv"], g["trained_det"])
+    ctx.set_features(xt, offt)
+    ctx.set_models(ms)
+    got = ctx.forward_scores()
+    assert np.allclose(got, g["score"], rtol=RTOL, atol=0)
+    label, second = ctx.rank(got)
+    assert (label == g["order"][:, 0]).all() and (second == g["order"][:, 1]).all()
+
+
+def test_rank_rule_with_nan_and_inf(ctx):
+    rng = np.random.default_rng(3)
+    sc = rng.standard_normal((200, 9))
+    sc[rng.random(sc.shape) < 0.25] = np.nan
+    sc[rng.random(sc.shape) < 0.1] = -np.inf
+    sc[:, 4] = sc[:, 2]
+    sc[0] = np.nan
+    label, second = ctx.rank(sc)
+    want = np.stack([o.rank(row) for row in sc])
+    assert (label == want[:, 0]).all() and (second == want[:, 1]).all()
+    l1, s1 = ctx.rank(sc[:, :1])
+    assert (l1 == 0).all()
+
+
+def test_shipped_fixtures_degenerate_regime(ctx, golden_dir):
+    """The reference's own 13 feature files against its 13 diagonal models: most cells underflow to
+    NaN / -inf in the reference.  With emulate_underflow the recognised labels must be the same."""
+    kat = json.load(open(os.path.join(golden_dir, "kat_diag.json")))
+    km = np.load(os.path.join(golden_dir, "kat_models.npz"))
+    words = [str(w) for w in km["words"]]
+    ms = api.ModelSet(km["A"], km["c"], km["mu"], km["iv"], km["det"], words)
+    files = sorted(glob.glob(os.path.join(golden_dir, "perfil", "*.perfil")))
+    xs = [api.read_features(f) for f in files]
+    off = np.concatenate([[0], np.cumsum([len(a) for a in xs])])
+    ctx.set_features(np.concatenate(xs), off)
+    ctx.set_models(ms)
+    got = ctx.forward_scores(emulate_underflow=True)
+    label, second = ctx.rank(got)
+    for u, rec in enumerate(kat["recognition"]):
+        ref_score = {w: float(v.replace("-nan", "nan")) for w, v in rec["sorted"]}
+        assert words[label[u]] == rec["sorted"][0][0], rec["spoken"]
+        for v, w in enumerate(words):
+            rs = ref_score[w]
+            if np.isfinite(rs):
+                assert np.isfinite(got[u, v]) and abs(got[u, v] - rs) <= RTOL * abs(rs), (rec["spoken"], w)
+            else:
+                assert not np.isfinite(got[u, v]), (rec["spoken"], w, got[u, v], rs)
+
+
+# --------------------------------------------------------------------------------- E-step ----
+@pytest.mark.parametrize("N,M,V,U", [(5, 3, 3, 9), (5, 16, 2, 6), (3, 128, 1, 2), (6, 1, 2, 4), (1, 2, 1, 2), (8, 2, 2, 4)])
+def test_estep_statistics_match_oracle(ctx, N, M, V, U):
+    ms, x, off, labels = _synth(V, N, M, U, seed=31 + N + M)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st, lp = o.estep(_oracle_model(ms, v), xv, offv)
+        sp = api.split_stats(stats[v], N, M, ms.D)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        assert abs(sp["sum_logp"] - st.sum_logp) <= RTOL * abs(st.sum_logp) and sp["n_utt"] == len(us)
+        for name in ("num_trans", "den_trans", "den_mix", "S0"):
+            want = getattr(st, name)
+            assert np.allclose(sp[name], want, rtol=RTOL, atol=1e-6 * np.abs(want).max()), name
+        # first / second order sums: compare through the quantities the M-step forms from them
+        S0 = np.maximum(st.S0, 1e-300)[..., None]
+        occ = st.S0 > 1e-3 * st.S0.max()
+        sd = np.sqrt(st.S2c / S0)
+        assert (np.abs(sp["S1"] / S0 - st.S1 / S0)[occ] <= RTOL * np.maximum(np.abs(st.S1 / S0), sd)[occ]).all(), "S1"
+        assert np.allclose((sp["S2c"] / S0)[occ], (st.S2c / S0)[occ], rtol=RTOL), "S2c"
+
+
+def test_estep_masked_utterances_and_empty(ctx):
+    ms, x, off, labels = _synth(2, 5, 3, 6, seed=55)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    full, _ = ctx.estep(labels)
+    masked = labels.copy()
+    masked[labels == 1] = -1
+    part, lpu = ctx.estep(masked)
+    assert np.allclose(part[0], full[0], rtol=1e-12) and (part[1] == 0).all() and (lpu[labels == 1] == 0).all()
+    ctx.set_features(np.zeros((0, 39)), np.zeros(1, dtype=np.int64))
+    st, lp = ctx.estep(np.zeros(0, dtype=np.int32))
+    assert (st == 0).all() and len(lp) == 0
+
+
+def test_short_and_single_frame_utterances(ctx):
+    """T = 1 and T < N: the final state is unreachable -> logP = -inf and no occupancy, as in the
+    reference (log(0) at T-FS:1549)."""
+    ms, x, off, labels = _synth(1, 5, 2, 3, seed=66, tmin=40, tmax=50)
+    off2 = np.array([0, 1, 4, off[1]], dtype=np.int64)
+    ctx.set_features(x[: off[1]], off2)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(np.zeros(3, dtype=np.int32))
+    mo = _oracle_model(ms, 0)
+    with np.errstate(all="ignore"):
+        want = [o.forward_score(mo, x[off2[u]:off2[u + 1]]) for u in range(3)]
+    assert lpu[0] == -np.inf and lpu[1] == -np.inf and want[0] == -np.inf and want[1] == -np.inf
+    assert abs(lpu[2] - want[2]) <= RTOL * abs(want[2])
+    sc = ctx.forward_scores()
+    assert sc[0, 0] == -np.inf and sc[1, 0] == -np.inf
+
+
+# ------------------------------------------------------------------------------- training ----
+def test_golden_synth_c1_training(ctx, golden_dir):
+    """Whole EM loop on the GPU from the reference's own initial models; iteration counts equal, mean
+    log-probabilities and every re-estimated parameter within 1e-4 of what the reference wrote."""
+    g = np.load(os.path.join(golden_dir, "synth_c1.npz"))
+    V, N, M, D = int(g["V"]), int(g["N"]), int(g["M"]), int(g["D"])
+    cen, s = synth.make_centres(V, N, M, D, seed=1234)
+    x, off = synth.make_utterances(cen, s, g["train_labels"], seed=1234, tmin=70, tmax=110)
+    ms = api.ModelSet(g["init_A"], g["init_c"], g["init_mu"], g["init_iv"], g["init_det"])
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, _ = ctx.estep(g["train_labels"])
+    for v in range(V):
+        sp = api.split_stats(stats[v], N, M, D)
+        for name in ("num_trans", "den_trans", "den_mix", "S0"):
+            want = g["stat_" + name][v]
+            assert np.allclose(sp[name], want, rtol=RTOL, atol=1e-6 * np.abs(want).max()), name
+        assert abs(sp["sum_logp"] - g["stat_sum_logp"][v]) <= RTOL * abs(g["stat_sum_logp"][v])
+    its, mean = ctx.train(ms, g["train_labels"])
+    assert (its == g["iterations"]).all()
+    assert np.allclose(mean, g["mean_logp"], rtol=RTOL)
+    for v in range(V):
+        mo = o.Model(g["trained_A"][v], g["trained_c"][v], g["trained_mu"][v], g["trained_iv"][v], g["trained_det"][v])
+        _assert_params_close(ms, v, mo)
+        assert np.allclose(np.log(ms.det[v]), np.log(mo.det), rtol=RTOL, atol=1e-3)
+
+
+def test_shipped_kats_training(ctx, golden_dir):
+    """The 13 shipped feature files, N=6 M=1: host init + GPU EM loop reproduces the
+    reference's mean log-probability and iteration count."""
+    kat = json.load(open(os.path.join(golden_dir, "kat_diag.json")))
+    for word, rec in kat["train"].items():
+        x = api.read_features(os.path.join(golden_dir, "perfil", rec["file"]))
+        off = np.array([0, len(x)], dtype=np.int64)
+        ms = api.init_model(6, 1, x, off, word)
+        ctx.set_features(x, off)
+        its, mean = ctx.train(ms, np.zeros(1, dtype=np.int32))
+        assert its[0] == rec["iterations"], word
+        assert abs(mean[0] - rec["mean_logp"]) <= RTOL * abs(rec["mean_logp"]), word
+
+
+# -------------------------------------------------------------------------------- Viterbi ----
+def test_viterbi_paths_bit_exact_and_scores(ctx):
+    ms, x, off, labels = _synth(4, 5, 3, 12, seed=91)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    score, path = ctx.viterbi(labels)
+    allsc = ctx.viterbi_scores()
+    fwd = ctx.forward_scores()
+    for u in range(len(labels)):
+        mo = _oracle_model(ms, labels[u])
+        b, _ = o.emissions(mo, x[off[u]:off[u + 1]], want_post=False)
+        s, p = o.viterbi(mo, b)
+        assert (path[off[u]:off[u + 1]] == p).all(), u
+        assert abs(score[u] - s) <= 1e-9 * abs(s)
+        assert abs(allsc[u, labels[u]] - s) <= 1e-5 * abs(s)
+    assert (allsc <= fwd + 1e-6 * np.abs(fwd)).all()
+    assert (np.argmax(allsc, axis=1) == labels).all()
+
+
+# ---------------------------------------------------------------------- drop-in programs ----
+def test_cli_train_then_test_matches_reference_outputs(golden_dir, tmp_path):
+    """bin/hmm_continuous_fs and bin/recognition_continuous_fs with the reference's argv on the
+    synth_c1 case: reports agree with the reference's (iterations, mean probability to 1e-4, labels)."""
+    g = np.load(os.path.join(golden_dir, "synth_c1.npz"))
+    V, N, M, D = int(g["V"]), int(g["N"]), int(g["M"]), int(g["D"])
+    cen, s = synth.make_centres(V, N, M, D, seed=1234)
+    x, off = synth.make_utterances(cen, s, g["train_labels"], seed=1234, tmin=70, tmax=110)
+    xt, offt = synth.make_utterances(cen, s, g["test_labels"], seed=4321, tmin=70, tmax=110)
+    bindir = os.path.join(os.path.dirname(api.LIB_PATH), "bin")
+    models = []
+    for v in range(V):
+        files = []
+        for u in np.nonzero(g["train_labels"] == v)[0]:
+            f = str(tmp_path / ("tr%d.bin" % u))
+            api.write_features(f, x[off[u]:off[u + 1]])
+            files.append(f)
+        lst = str(tmp_path / ("list%d.txt" % v))
+        open(lst, "w").write("\n".join(files) + "\n")
+        hmm = str(tmp_path / ("w%d.hmm" % v))
+        subprocess.run([os.path.join(bindir, "hmm_continuous_fs"), "word%d" % v, str(N), "1", str(M), lst, hmm],
+                       check=True, stdout=subprocess.DEVNULL)
+        mean, its = r.parse_train_report(hmm[:-4] + ".txt")
+        assert its == g["iterations"][v] and abs(mean - g["mean_logp"][v]) <= RTOL * abs(g["mean_logp"][v])
+        models.append(hmm)
+    tf = []
+    for u in range(len(offt) - 1):
+        f = str(tmp_path / ("te%d.bin" % u))
+        api.write_features(f, xt[offt[u]:offt[u + 1]])
+        tf.append(f)
+    open(str(tmp_path / "models.txt"), "w").write("\n".join(models) + "\n")
+    open(str(tmp_path / "feat.txt"), "w").write("\n".join(tf) + "\n")
+    open(str(tmp_path / "words.txt"), "w").write("\n".join("word%d" % v for v in g["test_labels"]) + "\n")
+    res = str(tmp_path / "res.txt")
+    subprocess.run([os.path.join(bindir, "recognition_continuous_fs"), "1", str(tmp_path / "models.txt"), "1",
+                    str(tmp_path / "feat.txt"), str(tmp_path / "words.txt"), res], check=True, stdout=subprocess.DEVNULL)
+    txt = open(res).read()
+    assert "Algorithm used for recognition: Forward" in txt
+    assert "Correct words: %d\nErrors: 0" % len(g["test_labels"]) in txt.split("Considering all the words:")[1]
+    if r.available("d39m16"):
+        # V != NUMBER_WORDS of the prebuilt reference binary only affects its stdout, not the result file
+        ref_res = str(tmp_path / "ref_res.txt")
+        r.run_test_cli("d39m16", str(tmp_path / "models.txt"), str(tmp_path / "feat.txt"), str(tmp_path / "words.txt"), ref_res)
+        strip = lambda t: [l for l in t.splitlines() if not l.startswith(("Date and time", "Average recognition time"))]
+        assert strip(txt) == strip(open(ref_res).read())
+
+
+# ------------------------------------------------- full-size, size-independent properties ----
+def test_c2_size_properties(ctx):
+    """BASELINE config 2 (N=5, M=16, 1000 utterances of ~300 frames): too big for the CPU oracle in a
+    test, so check identities that hold at any size: sum_m S0 = den_mix; band row sums of num_trans =
+    den_trans; den_mix - den_trans = last-frame occupancy >= 0; sum_i den_mix = sum_u w_u T_u <= F;
+    and E-step log-probabilities equal the decode path's forward scores."""
+    V, N, M, U = 10, 5, 16, 1000
+    cen, s = synth.make_centres(V, N, M, 39, seed=1234)
+    labels = np.arange(U) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=1234)
+    ms = api.ModelSet.from_dict(synth.make_models(cen, s))
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    assert np.isfinite(lpu).all()
+    T = np.diff(off)
+    for v in range(V):
+        sp = api.split_stats(stats[v], N, M, 39)
+        assert np.allclose(sp["S0"].sum(axis=1), sp["den_mix"], rtol=1e-5)
+        assert np.allclose(sp["num_trans"].sum(axis=1)[:-1], sp["den_trans"][:-1], rtol=1e-6)
+        assert (sp["den_mix"] - sp["den_trans"] >= -1e-9).all()
+        assert sp["den_mix"].sum() <= T[labels == v].sum() * (1 + 1e-9)
+        assert sp["n_utt"] == (labels == v).sum()
+        assert abs(sp["sum_logp"] - lpu[labels == v].sum()) <= 1e-9 * abs(sp["sum_logp"])
+    sub = np.arange(0, U, 50)
+    offs = np.concatenate([[0], np.cumsum(T[sub])])
+    ctx.set_features(np.concatenate([x[off[u]:off[u + 1]] for u in sub]), offs)
+    sc = ctx.forward_scores()
+    assert np.allclose(sc[np.arange(len(sub)), labels[sub]], lpu[sub], rtol=1e-6)
+    lab, _ = ctx.rank(sc)
+    assert (lab == labels[sub]).all()
+    # a spot check against the oracle on two utterances
+    for k in (0, 7):
+        u = sub[k]
+        want = o.forward_score(o.Model(ms.A[labels[u]], ms.c[labels[u]], ms.mu[labels[u]], ms.iv[labels[u]], ms.det[labels[u]]), x[off[u]:off[u + 1]])
+        assert abs(lpu[u] - want) <= RTOL * abs(want)

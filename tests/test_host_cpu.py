@@ -1,0 +1,127 @@
+"""Host-side logic of the product library (no GPU needed): C-ABI surface, file formats, initial-model
+builder, M-step -- each against the oracle restatement / the reference's formats."""
+import os
+import re
+import struct
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+from oracle import ref as r
+from speech_recognition_hmm_continuous_b200 import api, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_model(ms, v=0):
+    return o.Model(ms.A[v], ms.c[v], ms.mu[v], ms.iv[v], ms.det[v], ms.words[v])
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hmm_cuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(hmmcu_\w+|hmmh_\w+)\s*\(", hdr)) - {"hmmh_allreduce_fn"})
+    lib = api.load()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(set(api.EXPORTS)) == declared
+
+
+def test_no_device_fails_loudly():
+    lib = api.load()
+    if lib.hmmcu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.HmmCudaError) as e:
+        api.Context(0)
+    assert "no CPU path" in str(e.value) or "failed" in str(e.value)
+
+
+def _case(M, seed, U=4, N=5):
+    cen, s = synth.make_centres(1, N, M, 39, seed=seed)
+    return synth.make_utterances(cen, s, [0] * U, seed=seed + 1, tmin=50, tmax=90)
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 16])
+def test_init_model_bit_exact_with_oracle(M):
+    x, off = _case(M, 300 + M)
+    ms = api.init_model(5, M, x, off)
+    mo = o.init_model(5, M, x, off)
+    for name, a in (("A", ms.A), ("c", ms.c), ("mu", ms.mu), ("iv", ms.iv), ("det", ms.det)):
+        assert (a[0] == getattr(mo, name)).all(), name
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_mstep_bit_exact_with_oracle(M):
+    x, off = _case(M, 400 + M)
+    mo = o.init_model(5, M, x, off)
+    st, _ = o.estep(mo, x, off)
+    vec = np.concatenate([st.num_trans.ravel(), st.den_trans, st.den_mix, st.S0.ravel(), st.S1.ravel(), st.S2c.ravel(),
+                          [st.sum_logp, st.n_utt]])
+    assert len(vec) == api.stats_size(5, M, 39)
+    ms = api.ModelSet(mo.A[None], mo.c[None], mo.mu[None], mo.iv[None], mo.det[None])
+    # a state without occupancy keeps its parameters and has its inverse variance inverted again (reference quirk)
+    vec2 = vec.copy()
+    sp = api.split_stats(vec2, 5, M, 39)
+    sp["den_mix"][2] = 0.0
+    st.den_mix[2] = 0.0
+    api.mstep(ms, vec2[None])
+    o.mstep(mo, st)
+    for name, a in (("A", ms.A), ("c", ms.c), ("mu", ms.mu), ("iv", ms.iv), ("det", ms.det)):
+        assert (a[0] == getattr(mo, name)).all(), name
+
+
+def test_model_file_format(tmp_path):
+    x, off = _case(3, 77)
+    mo = o.init_model(5, 3, x, off, "palavra")
+    ms = api.ModelSet(mo.A[None], mo.c[None], mo.mu[None], mo.iv[None], mo.det[None], ["palavra"])
+    p = str(tmp_path / "m.hmm")
+    api.write_model(p, ms)
+    # byte-identical with the layout the reference writes (python restatement pinned in test_oracle_vs_ref)
+    q = str(tmp_path / "q.hmm")
+    r.write_model(q, mo)
+    assert open(p, "rb").read() == open(q, "rb").read()
+    back = api.read_model(p)
+    assert back.words == ["palavra"] and (back.mu == ms.mu).all() and (back.iv == ms.iv).all() and (back.A == ms.A).all()
+    # the shipped fixtures were written by a 32-bit build: 4-byte length header
+    raw = open(p, "rb").read()
+    p32 = str(tmp_path / "m32.hmm")
+    open(p32, "wb").write(struct.pack("<I", 7) + raw[8:])
+    b32 = api.read_model(p32)
+    assert b32.words == ["palavra"] and (b32.det == ms.det).all()
+
+
+@pytest.mark.skipif(not r.available("d39m16"), reason="oracle/_ref not built")
+def test_reads_model_written_by_reference(tmp_path):
+    x, off = _case(3, 78)
+    files = []
+    for u in range(len(off) - 1):
+        f = str(tmp_path / ("u%d.bin" % u))
+        api.write_features(f, x[off[u]:off[u + 1]])
+        files.append(f)
+    lst = str(tmp_path / "l.txt")
+    open(lst, "w").write("\n".join(files) + "\n")
+    r.run_train_cli("d39m16", "abc", 5, 3, lst, str(tmp_path / "m.hmm"))
+    a = api.read_model(str(tmp_path / "m.hmm"))
+    b = r.read_model(str(tmp_path / "m.hmm"))
+    assert a.words == ["abc"]
+    for name, arr in (("A", a.A), ("c", a.c), ("mu", a.mu), ("iv", a.iv), ("det", a.det)):
+        assert (arr[0] == getattr(b, name)).all()
+
+
+def test_feature_file_format(golden_dir, tmp_path):
+    f = os.path.join(golden_dir, "perfil", "mean_vc_186_f_03_ap_0225.perfil")
+    x = api.read_features(f)
+    assert x.shape == (151, 9) and (x == r.read_features(f)).all()
+    p = str(tmp_path / "x.bin")
+    api.write_features(p, x)
+    assert open(p, "rb").read() == open(f, "rb").read()
+
+
+def test_split_stats_layout():
+    N, M, D = 3, 2, 4
+    vec = np.arange(api.stats_size(N, M, D), dtype=np.float64)
+    sp = api.split_stats(vec, N, M, D)
+    assert sp["num_trans"][0, 0] == 0 and sp["den_trans"][0] == 9 and sp["den_mix"][0] == 12 and sp["S0"][0, 0] == 15
+    assert sp["S1"][0, 0, 0] == 21 and sp["S2c"][0, 0, 0] == 45 and sp["sum_logp"] == 69 and sp["n_utt"] == 70
