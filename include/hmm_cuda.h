@@ -49,6 +49,10 @@ int hmmcu_synchronize(hmmcu_ctx *ctx);
 int hmmcu_host_alloc(void **p, uint64_t bytes);
 void hmmcu_host_free(void *p);
 
+/* Tuning / A-B switches.  "tc_emis" (default 1): emissions on the tcgen05 tensor-core path; 0 selects
+ * the CUDA-core kernel (both are device code; results agree to single-precision round-off). */
+int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
+
 /* ---------------------------------------------------------------- inputs ----------------- */
 /* Feature vectors of U utterances, ragged: utterance u owns frames [frame_off[u], frame_off[u+1])
  * of x[F][D].  Replaces the per-frame fread loop (reading_coef, T-FS:527-548 / R-FS:518-539) that

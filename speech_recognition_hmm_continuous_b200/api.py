@@ -18,7 +18,7 @@ _lp = C.POINTER(C.c_int64)
 
 EXPORTS = [
     "hmmcu_create", "hmmcu_destroy", "hmmcu_last_error", "hmmcu_device_count", "hmmcu_stream", "hmmcu_synchronize",
-    "hmmcu_host_alloc", "hmmcu_host_free", "hmmcu_set_features", "hmmcu_set_features_device", "hmmcu_set_models",
+    "hmmcu_host_alloc", "hmmcu_host_free", "hmmcu_set_option", "hmmcu_set_features", "hmmcu_set_features_device", "hmmcu_set_models",
     "hmmcu_emissions", "hmmcu_forward_scores", "hmmcu_rank", "hmmcu_stats_size", "hmmcu_estep", "hmmcu_stats_device",
     "hmmcu_stats_download", "hmmcu_viterbi", "hmmcu_viterbi_scores", "hmmcu_launch_count", "hmmcu_last_kernel_ms",
     "hmmcu_enable_timing", "hmmh_model_alloc", "hmmh_model_free", "hmmh_read_features", "hmmh_write_features",
@@ -71,6 +71,7 @@ def load():
     lib.hmmcu_destroy.argtypes = [C.c_void_p]
     lib.hmmcu_synchronize.argtypes = [C.c_void_p]
     lib.hmmcu_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.hmmcu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.hmmcu_set_features.argtypes = [C.c_void_p, C.c_void_p, _lp, C.c_int, C.c_int]
     lib.hmmcu_set_features_device.argtypes = [C.c_void_p, C.c_void_p, _lp, C.c_int, C.c_int]
     lib.hmmcu_set_models.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
@@ -280,6 +281,9 @@ class Context:
                                      its.ctypes.data_as(C.POINTER(C.c_int)), int(max_iter),
                                      C.cast(cb, C.c_void_p) if cb else None, None), "hmmh_train")
         return its, mean
+
+    def set_option(self, key, value):
+        self._ck(self.lib.hmmcu_set_option(self.h, key.encode(), int(value)), "hmmcu_set_option")
 
     # ---- instrumentation ----
     def stream(self):

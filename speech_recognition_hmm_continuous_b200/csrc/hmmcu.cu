@@ -13,6 +13,7 @@
 
 #include "hmm_cuda.h"
 #include "kernels.cuh"
+#include "tc_kernels.cuh"
 
 using namespace hmmk;
 
@@ -77,6 +78,16 @@ struct hmmcu_ctx {
   int64_t n_train_tiles = 0;
   int max_utts_per_model = 0;
 
+  // tensor-core emission path (tc_kernels.cuh)
+  int use_tc = 1;
+  struct TcSet {
+    DevBuf images, kc, s0, ns;
+    int TN = 0, SCt = 0, nimg = 0;
+    bool dirty = true;
+  } tc_train, tc_dec;
+  DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec;
+  int64_t n_tc_tiles_train = 0;
+
   // workspaces
   DevBuf logb, post, gamma, alpha_ws, cs_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
   int64_t stats_n = 0;
@@ -122,7 +133,6 @@ static void t_end(hmmcu_ctx *ctx, const char *name) {
   t.used = true;
 }
 
-extern "C" {
 
 int hmmcu_device_count(void) {
   int n = 0;
@@ -164,7 +174,9 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->cs_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
-                    &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out};
+                    &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
+                    &ctx->tc_train.ns, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
+                    &ctx->frame_ids_d, &ctx->tc_tiles_dec};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -194,6 +206,11 @@ double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
   if (cudaEventSynchronize(it->second.b) != cudaSuccess) return -1.0;
   if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
+  if (!ctx || !key) return HMMCU_EINVAL;
+  if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value != 0; return HMMCU_OK; }
+  return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
   return (int64_t)N * N + 2 * N + (int64_t)N * M + 2 * (int64_t)N * M * D + 2;
@@ -300,13 +317,72 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   LAUNCH_CHECK();
   t_end(ctx, "pack");
   ctx->pack_dirty = false;
+  ctx->tc_train.dirty = true;
+  ctx->tc_dec.dirty = true;
+  return HMMCU_OK;
+}
+
+// ---- tensor-core path: W images ------------------------------------------------------------------
+static bool tc_supported(const hmmcu_ctx *ctx) {
+  if (!ctx->use_tc || ctx->M > kTcMaxTN || ctx->N > 8) return false;
+  const int SCt = std::max(1, kTcMaxTN / ctx->M);
+  const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * ctx->M, 16);
+  return tc_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
+}
+
+// mode 0: training images (per model, CT column tiles each); mode 1: decode images (all states concatenated)
+static int ensure_tc_images(hmmcu_ctx *ctx, int mode) {
+  hmmcu_ctx::TcSet &ts = mode == 0 ? ctx->tc_train : ctx->tc_dec;
+  if (!ts.dirty) return HMMCU_OK;
+  const int N = ctx->N, M = ctx->M, V = ctx->V;
+  const int SCmax = std::max(1, kTcMaxTN / M);
+  std::vector<int32_t> s0, ns;
+  if (mode == 0) {
+    ts.SCt = std::min(SCmax, N);
+    for (int v = 0; v < V; v++)
+      for (int s = 0; s < N; s += ts.SCt) { s0.push_back(v * N + s); ns.push_back(std::min(ts.SCt, N - s)); }
+  } else {
+    const int S = V * N;
+    ts.SCt = std::min(SCmax, S);
+    for (int s = 0; s < S; s += ts.SCt) { s0.push_back(s); ns.push_back(std::min(ts.SCt, S - s)); }
+  }
+  ts.TN = round_up(ts.SCt * M, 16);
+  ts.nimg = (int)s0.size();
+  const int KP = 2 * ctx->DP;
+  CK(ts.images.ensure(tc_image_bytes(ts.TN, KP) * ts.nimg));
+  CK(ts.kc.ensure(sizeof(float) * (size_t)ts.TN * ts.nimg));
+  CK(ts.s0.ensure(sizeof(int32_t) * ts.nimg));
+  CK(ts.ns.ensure(sizeof(int32_t) * ts.nimg));
+  CK(cudaMemcpyAsync(ts.s0.p, s0.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ts.ns.p, ns.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));  // s0 / ns are stack vectors
+  t_begin(ctx, "pack");
+  k_pack_w_tc<<<ts.nimg, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), ctx->c.as<double>(),
+                                           ctx->ctr.as<double>(), M, ctx->D, ctx->DP, ts.TN, ts.s0.as<int32_t>(), ts.ns.as<int32_t>(),
+                                           ts.images.as<float>(), ts.kc.as<float>());
+  LAUNCH_CHECK();
+  t_end(ctx, "pack");
+  ts.dirty = false;
+  return HMMCU_OK;
+}
+
+template <bool TRAIN>
+static int launch_emis_tc(hmmcu_ctx *ctx, const TcTile *tiles_dev, int ntiles, float *logb, int64_t fbase, int64_t ldb, float *post) {
+  if (ntiles == 0) return HMMCU_OK;
+  hmmcu_ctx::TcSet &ts = TRAIN ? ctx->tc_train : ctx->tc_dec;
+  const size_t smem = tc_emis_smem_bytes(ts.TN, 2 * ctx->DP);
+  CK(cudaFuncSetAttribute(k_emis_tc<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(ntiles, ctx->sm_count);
+  k_emis_tc<TRAIN><<<grid, kTcThreads, smem, ctx->st>>>(tiles_dev, ntiles, ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),
+                                                        ts.images.as<float>(), ts.kc.as<float>(), ts.nimg, ctx->N, ctx->M, ctx->DP,
+                                                        ts.TN, logb, fbase, ldb, ctx->V * ctx->N, ts.SCt, post);
+  LAUNCH_CHECK();
   return HMMCU_OK;
 }
 
 // --------------------------------------------------------------------------------- emissions ----
 static int emis_chunk_states(const hmmcu_ctx *ctx) { return std::max(1, std::min(ctx->N, 128 / ctx->M)); }
 
-}  // extern "C"
 template <bool POST>
 static int launch_emis(hmmcu_ctx *ctx, const EmisTile *tiles_dev, int64_t ntiles, float *logb, int64_t fbase, int64_t ldb,
                        int decode, float *post) {
@@ -322,7 +398,6 @@ static int launch_emis(hmmcu_ctx *ctx, const EmisTile *tiles_dev, int64_t ntiles
   return HMMCU_OK;
 }
 
-extern "C" {
 int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
   if (!ctx) return HMMCU_EINVAL;
   CK(cudaSetDevice(ctx->dev));
@@ -339,9 +414,29 @@ int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
   CK(ps.ensure(sizeof(float) * (size_t)T * ctx->G));
   CK(cudaMemcpyAsync(tl.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
   // post is indexed by global frame: offset the pointer so that frame f0 lands at ps[0]
-  rc = launch_emis<true>(ctx, tl.as<EmisTile>(), (int64_t)tiles.size(), lb.as<float>(), f0, ctx->N, 0,
-                         ps.as<float>() - f0 * ctx->G);
-  if (rc) return rc;
+  if (tc_supported(ctx)) {
+    if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
+    std::vector<int32_t> ids(T);
+    for (int t = 0; t < T; t++) ids[t] = (int32_t)(f0 + t);
+    std::vector<TcTile> tt;
+    const int CT = (ctx->N + ctx->tc_train.SCt - 1) / ctx->tc_train.SCt;
+    for (int ct = 0; ct < CT; ct++)
+      for (int t = 0; t < T; t += kTcRows) tt.push_back({t, std::min(kTcRows, T - t), v * CT + ct, ct * ctx->tc_train.SCt, v, 0});
+    DevBuf tl2;
+    CK(tl2.ensure(sizeof(TcTile) * tt.size()));
+    CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * T));
+    CK(cudaMemcpyAsync(tl2.p, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->frame_ids_d.p, ids.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->st));
+    ctx->u2m.clear();  // frame_ids_d was overwritten: the training map must be rebuilt
+    rc = launch_emis_tc<true>(ctx, tl2.as<TcTile>(), (int)tt.size(), lb.as<float>() - f0 * ctx->N, 0, ctx->N, ps.as<float>() - f0 * ctx->G);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->st));
+    tl2.release();
+  } else {
+    rc = launch_emis<true>(ctx, tl.as<EmisTile>(), (int64_t)tiles.size(), lb.as<float>(), f0, ctx->N, 0,
+                           ps.as<float>() - f0 * ctx->G);
+    if (rc) return rc;
+  }
   std::vector<float> hl((size_t)T * ctx->N), hp((size_t)T * ctx->G);
   CK(cudaMemcpyAsync(hl.data(), lb.p, sizeof(float) * hl.size(), cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaMemcpyAsync(hp.data(), ps.p, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost, ctx->st));
@@ -354,7 +449,6 @@ int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
 }
 
 // ----------------------------------------------------------------------- decode (all cells) ----
-}  // extern "C"
 template <int NS> struct ScoreLaunch {
   static void fwd(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, int emulate) {
     dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
@@ -400,16 +494,29 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     if (u1 == u0) u1 = u0 + 1;
     const int64_t fb0 = ctx->off[u0], fb1 = ctx->off[u1];
     CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
-    tiles.clear();
-    for (int64_t f = fb0; f < fb1; f += kEmisTF)
-      for (int v = 0; v < ctx->V; v++) tiles.push_back({f, (int)std::min<int64_t>(kEmisTF, fb1 - f), v});
-    CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
-    CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaStreamSynchronize(ctx->st));  // `tiles` is reused by the next batch
-    t_begin(ctx, "emis");
-    rc = launch_emis<false>(ctx, ctx->tiles_dec.as<EmisTile>(), (int64_t)tiles.size(), ctx->logb.as<float>(), fb0, S, 1, nullptr);
-    if (rc) return rc;
-    t_end(ctx, "emis");
+    if (tc_supported(ctx)) {
+      if ((rc = ensure_tc_images(ctx, 1)) != HMMCU_OK) return rc;
+      std::vector<TcTile> tt;
+      for (int64_t f = fb0; f < fb1; f += kTcRows) tt.push_back({(int32_t)(f - fb0), (int)std::min<int64_t>(kTcRows, fb1 - f), 0, 0, 0, 0});
+      CK(ctx->tc_tiles_dec.ensure(sizeof(TcTile) * tt.size()));
+      CK(cudaMemcpyAsync(ctx->tc_tiles_dec.p, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));
+      t_begin(ctx, "emis");
+      rc = launch_emis_tc<false>(ctx, ctx->tc_tiles_dec.as<TcTile>(), (int)tt.size(), ctx->logb.as<float>(), fb0, S, nullptr);
+      if (rc) return rc;
+      t_end(ctx, "emis");
+    } else {
+      tiles.clear();
+      for (int64_t f = fb0; f < fb1; f += kEmisTF)
+        for (int v = 0; v < ctx->V; v++) tiles.push_back({f, (int)std::min<int64_t>(kEmisTF, fb1 - f), v});
+      CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
+      CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));  // `tiles` is reused by the next batch
+      t_begin(ctx, "emis");
+      rc = launch_emis<false>(ctx, ctx->tiles_dec.as<EmisTile>(), (int64_t)tiles.size(), ctx->logb.as<float>(), fb0, S, 1, nullptr);
+      if (rc) return rc;
+      t_end(ctx, "emis");
+    }
     t_begin(ctx, mode == 0 ? "score" : "viterbi");
     if (mode == 0) {
       DISPATCH_N(ctx->N, ScoreLaunch<NS>::fwd(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>(), emulate));
@@ -425,7 +532,6 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   return HMMCU_OK;
 }
 
-extern "C" {
 int hmmcu_forward_scores(hmmcu_ctx *ctx, double *logp, int emulate_underflow) { return score_all(ctx, logp, 0, emulate_underflow); }
 int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score) { return score_all(ctx, score, 1, 0); }
 
@@ -470,6 +576,29 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
     for (int t = 0; t < T; t += kEmisTF) tiles.push_back({f0 + t, std::min(kEmisTF, T - t), utt2model[u]});
   }
   ctx->n_train_tiles = (int64_t)tiles.size();
+  {  // tensor-core tiles: the frames of each model, concatenated, in rows of 128
+    std::vector<int32_t> ids;
+    ids.reserve((size_t)ctx->F);
+    std::vector<TcTile> tt;
+    const int SCt = std::min(std::max(1, kTcMaxTN / ctx->M), ctx->N);
+    const int CT = (ctx->N + SCt - 1) / SCt;
+    for (int v = 0; v < V; v++) {
+      const int32_t r0 = (int32_t)ids.size();
+      for (int k = start[v]; k < start[v + 1]; k++) {
+        const int u = utts[k];
+        for (int64_t f = ctx->off[u]; f < ctx->off[u + 1]; f++) ids.push_back((int32_t)f);
+      }
+      const int32_t r1 = (int32_t)ids.size();
+      for (int ct = 0; ct < CT; ct++)
+        for (int32_t r = r0; r < r1; r += kTcRows) tt.push_back({r, std::min<int32_t>(kTcRows, r1 - r), v * CT + ct, ct * SCt, v, 0});
+    }
+    ctx->n_tc_tiles_train = (int64_t)tt.size();
+    CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
+    CK(ctx->tc_tiles_train.ensure(sizeof(TcTile) * std::max<size_t>(tt.size(), 1)));
+    CK(cudaMemcpyAsync(ctx->frame_ids_d.p, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->tc_tiles_train.p, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+  }
   CK(ctx->u2m_d.ensure(sizeof(int32_t) * std::max(U, 1)));
   CK(ctx->mus_d.ensure(sizeof(int32_t) * (V + 1)));
   CK(ctx->mu_d.ensure(sizeof(int32_t) * std::max(U, 1)));
@@ -507,8 +636,14 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     CK(ctx->cs_ws.ensure(sizeof(double) * F));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
     // 1. emissions + per-mixture posteriors
-    t_begin(ctx, "emis");
-    rc = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
+    if (tc_supported(ctx)) {
+      if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
+      t_begin(ctx, "emis");
+      rc = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, ctx->post.as<float>());
+    } else {
+      t_begin(ctx, "emis");
+      rc = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
+    }
     if (rc) return rc;
     t_end(ctx, "emis");
     // 2. forward / backward, gamma, transition statistics, log-probabilities
@@ -593,4 +728,3 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
   return HMMCU_OK;
 }
 
-}  // extern "C"

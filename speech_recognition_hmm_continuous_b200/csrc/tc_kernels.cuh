@@ -1,0 +1,322 @@
+// tc_kernels.cuh -- tensor-core (tcgen05 / TMEM) kernels for sm_100a.
+//
+// Emissions as a dense contraction (north_star; calc_gaus / calc_symbol_probab, T-FS:1749-1841):
+//   ln N_g(x_f) + ln c_g = kc[g] + sum_k Xaug[f][k] * W[g][k]
+//   Xaug[f] = [ x_0..x_{DP-1} | x_0^2..x_{DP-1}^2 ]            (x centred, DP = padded D)
+//   W[g]    = [ mu*iv         | -0.5*iv             ]            (pad columns 0)
+//   kc[g]   = ln c - 0.5 (D ln 2pi + ln|det|) - 0.5 sum mu^2 iv  (added in the epilogue, exact fp32)
+// computed with 3xTF32 (FP32-accurate split): every fp32 operand is split into hi = its top 11
+// mantissa bits and lo = the exact remainder; D = Ah*Bh + Al*Bh + Ah*Bl accumulates in one TMEM
+// tile through 3*KP/8 tcgen05.mma(kind::tf32, M=128, N=TN, K=8) instructions issued by one thread.
+// The epilogue reads the accumulator back with tcgen05.ld and fuses the per-state log-sum-exp over
+// the M mixtures (and, for training, the normalised per-mixture posteriors).
+//
+// Shared-memory operand layout (both operands K-major, SWIZZLE_NONE): one "slab" per K-step of 8
+// values; inside a slab the 8-row x 16-byte core matrices are stored contiguously (128 B); the two
+// K-chunks of a row group are 128 B apart (LBO), row groups 256 B apart (SBO):
+//   byte(row, k) = (k/8)*slab + (row/8)*256 + ((k%8)/4)*128 + (row%8)*16 + (k%4)*4
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace hmmk {
+
+constexpr int kTcRows = 128;       // frames per tile = UMMA M
+constexpr int kTcThreads = 256;    // 8 warps
+constexpr int kTcMaxTN = 192;      // Gaussians (columns) per tile, multiple of 16
+
+struct TcTile {
+  int32_t row0;    // TRAIN: index into frame_ids; DECODE: first frame of the tile relative to fbase
+  int32_t nrows;   // valid rows (<= 128)
+  int32_t img;     // first W image (TRAIN: the one image to use; DECODE: unused)
+  int32_t state0;  // TRAIN: first state (within the model) covered by the image; DECODE: unused
+  int32_t v;       // TRAIN: model; DECODE: unused
+  int32_t pad;
+};
+
+__host__ __device__ inline int tc_slab_bytes(int rows) { return rows * 32; }
+// bytes of one W image: hi and lo, KP/8 slabs each
+__host__ __device__ inline size_t tc_image_bytes(int TN, int KP) { return (size_t)2 * (KP / 8) * tc_slab_bytes(TN); }
+__host__ __device__ inline uint32_t tc_elem_off(int row, int k) {
+  return (uint32_t)((row >> 3) * 256 + (((k & 7) >> 2) * 128) + ((row & 7) * 16) + ((k & 3) * 4));
+}
+
+// ---- raw PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  // SWIZZLE_NONE, K-major: LBO = 128 B (between the two K-chunks), SBO = 256 B (between 8-row groups)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;
+}
+
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+  // c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10, K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t *mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(mbar);
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 8 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = __uint_as_float(__float_as_uint(v - hi) & 0xFFFFE000u);
+}
+
+// ---- W image packer ----------------------------------------------------------------------------
+// One image = TN Gaussian rows (whole states) x KP, hi slabs then lo slabs.  Image i covers global
+// states [img_state0[i], img_state0[i] + img_nstates[i]); rows beyond are zero with kc = -inf.
+__global__ void k_pack_w_tc(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
+                            const double *__restrict__ c, const double *__restrict__ ctr, int M, int D, int DP, int TN,
+                            const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
+                            float *__restrict__ images, float *__restrict__ kc) {
+  const int img = blockIdx.x;
+  const int KP = 2 * DP;
+  const size_t img_floats = tc_image_bytes(TN, KP) / 4;
+  float *hi = images + (size_t)img * img_floats;
+  float *lo = hi + img_floats / 2;
+  const int64_t g0 = (int64_t)img_state0[img] * M;
+  const int ng = img_nstates[img] * M;
+  for (int idx = threadIdx.x; idx < TN * KP; idx += blockDim.x) {
+    const int n = idx / KP, k = idx - n * KP;
+    const int part = k / DP, d = k - part * DP;
+    float val = 0.f;
+    if (n < ng && d < D) {
+      const double m = mu[(g0 + n) * D + d] - ctr[d], w = iv[(g0 + n) * D + d];
+      val = (float)(part == 0 ? m * w : -0.5 * w);
+    }
+    float h, l;
+    split_tf32(val, h, l);
+    const size_t o = (size_t)(k >> 3) * (tc_slab_bytes(TN) / 4) + tc_elem_off(n, k) / 4;
+    hi[o] = h;
+    lo[o] = l;
+  }
+  for (int n = threadIdx.x; n < TN; n += blockDim.x) {
+    double k = -INFINITY;
+    if (n < ng) {
+      const double dt = det[g0 + n], cc = c[g0 + n];
+      if (dt != 0.0 && cc > 0.0) {
+        double q = 0.0;
+        for (int d = 0; d < D; d++) {
+          const double m = mu[(g0 + n) * D + d] - ctr[d];
+          q += m * m * iv[(g0 + n) * D + d];
+        }
+        k = log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q;
+      }
+    }
+    kc[(size_t)img * TN + n] = (float)k;
+  }
+}
+
+// ---- emission GEMM ------------------------------------------------------------------------------
+// dynamic smem: A_hi | A_lo (KP/8 slabs of 4 KB each) | B image (hi, lo) | kc[TN] | lbs[N<=8][128] (TRAIN)
+__host__ __device__ inline size_t tc_emis_smem_bytes(int TN, int KP) {
+  return (size_t)2 * (KP / 8) * tc_slab_bytes(kTcRows) + tc_image_bytes(TN, KP) + sizeof(float) * TN + sizeof(float) * 8 * kTcRows + 1024;
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_emis_tc(const TcTile *__restrict__ tiles, int ntiles, const int32_t *__restrict__ frame_ids, const float *__restrict__ x32,
+          const float *__restrict__ images, const float *__restrict__ kcs, int nimages, int N, int M, int DP, int TN,
+          float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt, float *__restrict__ post) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int KP = 2 * DP, NSLAB = KP / 8;
+  const int aslab = tc_slab_bytes(kTcRows), bslab = tc_slab_bytes(TN);
+  uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *A_hi = sm, *A_lo = sm + (size_t)NSLAB * aslab;
+  uint8_t *B_hi = A_lo + (size_t)NSLAB * aslab, *B_lo = B_hi + (size_t)NSLAB * bslab;
+  float *kc = reinterpret_cast<float *>(B_lo + (size_t)NSLAB * bslab);
+  float *lbs = kc + TN;  // [8][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = N * M;
+
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < TN + 8) tmem_cols <<= 1;
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 0) mbar_init(&mbar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
+  uint32_t parity = 0;
+  int cur_img = -1;
+
+  // contiguous range of tiles per CTA (tiles are ordered by model, so W reloads are rare)
+  const int per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per, t_end = min(ntiles, t_begin + per);
+  for (int ti = t_begin; ti < t_end; ti++) {
+    const TcTile tile = tiles[ti];
+    // ---- A tile: [x | x^2] of 128 frames, split hi / lo, straight into the UMMA layout ----
+    {
+      const int r = tid & 127, half = tid >> 7;  // half 0: x columns, half 1: x^2 columns
+      int64_t f = -1;
+      if (r < tile.nrows) f = TRAIN ? (int64_t)frame_ids[tile.row0 + r] : fbase + tile.row0 + r;
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP);
+      for (int q = 0; q < DP / 4; q++) {
+        float4 xv = (f >= 0) ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (half) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
+        float4 h, l;
+        split_tf32(xv.x, h.x, l.x); split_tf32(xv.y, h.y, l.y); split_tf32(xv.z, h.z, l.z); split_tf32(xv.w, h.w, l.w);
+        const int k = half * DP + q * 4;
+        const uint32_t o = (uint32_t)(k >> 3) * aslab + tc_elem_off(r, k);
+        *reinterpret_cast<float4 *>(A_hi + o) = h;
+        *reinterpret_cast<float4 *>(A_lo + o) = l;
+      }
+    }
+    const int n_img = TRAIN ? 1 : nimages;
+    for (int ii = 0; ii < n_img; ii++) {
+      const int img = TRAIN ? tile.img : ii;
+      if (img != cur_img) {  // ---- B image (pre-packed in global memory in the smem layout) ----
+        const float4 *src = reinterpret_cast<const float4 *>(images + (size_t)img * (tc_image_bytes(TN, KP) / 4));
+        float4 *dst = reinterpret_cast<float4 *>(B_hi);
+        const int n16 = (int)(tc_image_bytes(TN, KP) / 16);
+        for (int i = tid; i < n16; i += kTcThreads) dst[i] = src[i];
+        for (int i = tid; i < TN; i += kTcThreads) kc[i] = kcs[(size_t)img * TN + i];
+        cur_img = img;
+      }
+      fence_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
+        uint32_t acc = 0;
+        for (int p = 0; p < 3; p++) {  // Ah*Bh, Al*Bh, Ah*Bl
+          const uint32_t a0 = (p == 1) ? a_lo : a_hi, b0 = (p == 2) ? b_lo : b_hi;
+          for (int j = 0; j < NSLAB; j++) {
+            tc_mma_tf32(tmem_d, make_smem_desc(a0 + j * aslab), make_smem_desc(b0 + j * bslab), idesc, acc);
+            acc = 1;
+          }
+        }
+        tc_commit(&mbar);
+      }
+      mbar_wait(&mbar, parity);
+      parity ^= 1;
+      tc_fence_after();
+
+      // ---- epilogue: thread <-> (row = 32*(warp%4) + lane, column half = warp/4), whole states ----
+      {
+        const int row = 32 * (warp & 3) + lane;
+        const int chalf = warp >> 2;
+        const int st_img0 = TRAIN ? tile.state0 : img * SCt;                 // first state of the image (global for DECODE)
+        const int st_lim = TRAIN ? N : S_total;
+        const int nst = max(0, min(SCt, st_lim - st_img0));                  // states present in this image
+        const int sh = (nst + 1) >> 1;
+        const int s_beg = chalf ? sh : 0, s_end = chalf ? nst : sh;          // my states within the image
+        const int c_beg = s_beg * M, c_end = s_end * M;
+        const uint32_t trow = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16);
+        const bool live = row < tile.nrows;
+        int64_t f = 0;
+        if (live) f = TRAIN ? (int64_t)frame_ids[tile.row0 + row] : fbase + tile.row0 + row;
+        float *lrow = TRAIN ? logb + f * N + st_img0 : logb + (f - fbase) * ldb + st_img0;
+        // pass 1: log-sum-exp per state (online), columns walked in aligned chunks of 8
+        {
+          float mx = kNegInf, sum = 0.f;
+          int mcount = 0, s = s_beg;
+          for (int c0 = c_beg & ~7; c0 < c_end; c0 += 8) {
+            float v[8];
+            tmem_ld8(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int col = c0 + j;
+              if (col >= c_beg && col < c_end) {
+                const float val = v[j] + kc[col];
+                if (val > mx) { sum = sum * __expf(mx - val) + 1.f; mx = val; }
+                else if (val > kNegInf) sum += __expf(val - mx);
+                if (++mcount == M) {
+                  const float lb = (mx > kNegInf) ? mx + __logf(sum) : kNegInf;
+                  if (live) lrow[s] = lb;
+                  if (TRAIN) lbs[(s - s_beg + chalf * 4) * kTcRows + row] = lb;
+                  s++; mcount = 0; mx = kNegInf; sum = 0.f;
+                }
+              }
+            }
+          }
+        }
+        // pass 2 (training): normalised per-mixture posteriors  c_m N_m / b_i
+        if (TRAIN) {
+          float *prow = post + f * G + (int64_t)st_img0 * M;
+          int mcount = 0, s = s_beg;
+          for (int c0 = c_beg & ~7; c0 < c_end; c0 += 8) {
+            float v[8];
+            tmem_ld8(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int col = c0 + j;
+              if (col >= c_beg && col < c_end) {
+                const float lb = lbs[(s - s_beg + chalf * 4) * kTcRows + row];
+                const float p = (lb > kNegInf) ? __expf(v[j] + kc[col] - lb) : 0.f;
+                if (live) prow[col] = p;
+                if (++mcount == M) { s++; mcount = 0; }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();  // accumulator, kc and lbs are free again
+    }
+  }
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+}  // namespace hmmk

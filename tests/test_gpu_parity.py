@@ -17,9 +17,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4  # north_star tolerance for floating-point results
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["tc", "simt"])
+def ctx(request):
+    """Every parity test runs twice: emissions on the tcgen05 tensor-core kernel (the default path) and
+    on the CUDA-core kernel (hmmcu_set_option "tc_emis" = 0)."""
     c = api.Context(0)
+    c.set_option("tc_emis", 1 if request.param == "tc" else 0)
     yield c
     c.close()
 
