@@ -49,8 +49,11 @@ int hmmcu_synchronize(hmmcu_ctx *ctx);
 int hmmcu_host_alloc(void **p, uint64_t bytes);
 void hmmcu_host_free(void *p);
 
-/* Tuning / A-B switches.  "tc_emis" (default 1): emissions on the tcgen05 tensor-core path; 0 selects
- * the CUDA-core kernel (both are device code; results agree to single-precision round-off). */
+/* Tuning / A-B switches.  "tc_emis": 1 (default) = emissions on the tcgen05 tensor-core path whenever
+ * its accuracy guard holds (the expanded quadratic loses ~1e-7 of sum|terms|; data whose centred
+ * range is huge against the model variances, like the reference's raw-Hz fixtures, go to the
+ * CUDA-core kernel, which evaluates (x-mu)^2 directly); 0 = always the CUDA-core kernel;
+ * 2 = always tensor cores.  Both are device code. */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 
 /* ---------------------------------------------------------------- inputs ----------------- */
@@ -119,7 +122,9 @@ int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx);
 /* Device time in ms of the most recent call's kernels, by name (CUDA events on the context's
- * stream).  names: "emis", "fwdbwd", "accum", "score", "viterbi", "pack".  -1 if unknown. */
+ * stream).  names: "emis", "fwdbwd", "accum", "score", "viterbi", "pack".  -1 if unknown.
+ * Two pseudo-names report state instead of time: "kappa" (accuracy-guard value) and "tc_active"
+ * (1 if the last emission launch ran on tensor cores). */
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name);
 void hmmcu_enable_timing(hmmcu_ctx *ctx, int on);
 

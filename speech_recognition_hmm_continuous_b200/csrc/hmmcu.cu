@@ -64,8 +64,12 @@ struct hmmcu_ctx {
   bool have_features = false;
   DevBuf x64_own;            // when uploaded from the host
   const double *d_x64 = nullptr;
-  DevBuf x32, ctr, off_d;
+  DevBuf x32, ctr, off_d, xabs_d;
   std::vector<int64_t> off;
+  std::vector<double> h_ctr;   // per-dimension centre (host copy)
+  std::vector<float> h_xabs;   // per-dimension max |x - ctr|
+  std::vector<double> h_ivmax, h_mumin, h_mumax;  // per-dimension model extremes (set_models)
+  double kappa = 0.0;          // bound on the summed magnitude of the expanded quadratic's terms
 
   // models
   int V = 0, N = 0, M = 0, G = 0, Dm = 0;
@@ -80,6 +84,7 @@ struct hmmcu_ctx {
 
   // tensor-core emission path (tc_kernels.cuh)
   int use_tc = 1;
+  bool last_tc = false;   // whether the most recent emission launch used the tensor-core kernel
   struct TcSet {
     DevBuf images, kc, s0, ns;
     int TN = 0, SCt = 0, nimg = 0;
@@ -175,7 +180,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->cs_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
-                    &ctx->tc_train.ns, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
+                    &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
@@ -200,6 +205,8 @@ void hmmcu_host_free(void *p) {
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; }
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
+  if (strcmp(name, "kappa") == 0) return ctx->kappa;            // accuracy-guard value of the current pack
+  if (strcmp(name, "tc_active") == 0) return ctx->last_tc ? 1.0 : 0.0;
   auto it = ctx->timers.find(name);
   if (it == ctx->timers.end() || !it->second.used) return -1.0;
   float ms = 0.f;
@@ -209,7 +216,7 @@ double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
 }
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (!ctx || !key) return HMMCU_EINVAL;
-  if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value != 0; return HMMCU_OK; }
+  if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -237,6 +244,8 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   ctx->u2m.clear();
   ctx->pack_dirty = true;  // the centre may move
   ctx->have_features = true;
+  ctx->h_ctr.assign(DP, 0.0);
+  ctx->h_xabs.assign(DP, 0.f);
   if (F == 0) return HMMCU_OK;
   CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
   CK(cudaMemcpyAsync(ctx->off_d.p, frame_off, sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
@@ -255,10 +264,15 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   {
     int64_t total = F * DP;
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64, ctx->ctr.as<double>(), F, D, DP, ctx->x32.as<float>());
+    CK(ctx->xabs_d.ensure(sizeof(unsigned int) * DP));
+    CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * DP, ctx->st));
+    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64, ctx->ctr.as<double>(), F, D, DP, ctx->x32.as<float>(),
+                                                ctx->xabs_d.as<unsigned int>());
     LAUNCH_CHECK();
   }
   t_end(ctx, "pack");
+  CK(cudaMemcpyAsync(ctx->h_ctr.data(), ctx->ctr.p, sizeof(double) * DP, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(ctx->h_xabs.data(), ctx->xabs_d.p, sizeof(float) * DP, cudaMemcpyDeviceToHost, ctx->st));
   // the caller's host buffer may be reused as soon as we return
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
@@ -290,6 +304,20 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
   CK(cudaMemcpyAsync(ctx->iv.p, inv_var, sizeof(double) * VG * D, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaMemcpyAsync(ctx->det.p, det, sizeof(double) * VG, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
+  {  // per-dimension extremes of the model set (host scan; feeds the accuracy guard of the tensor-core path)
+    ctx->h_ivmax.assign(D, 0.0);
+    ctx->h_mumin.assign(D, INFINITY);
+    ctx->h_mumax.assign(D, -INFINITY);
+    double *ivm = ctx->h_ivmax.data(), *mn = ctx->h_mumin.data(), *mx = ctx->h_mumax.data();
+    for (int64_t g = 0; g < VG; g++) {
+      const double *pi = inv_var + g * D, *pm = mu + g * D;
+      for (int d = 0; d < D; d++) {
+        ivm[d] = pi[d] > ivm[d] ? pi[d] : ivm[d];
+        mn[d] = pm[d] < mn[d] ? pm[d] : mn[d];
+        mx[d] = pm[d] > mx[d] ? pm[d] : mx[d];
+      }
+    }
+  }
   if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
   ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = (int)G;
   ctx->Dm = D;
@@ -319,12 +347,26 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   ctx->pack_dirty = false;
   ctx->tc_train.dirty = true;
   ctx->tc_dec.dirty = true;
+  // kappa = sum_d 2 * max(iv_d) * r_d^2, r_d = largest centred |x| or |mu| in dimension d: an upper bound on
+  // sum_k |Xaug_k W_k|.  The 3xTF32 contraction carries ~1e-7 of that magnitude as absolute error.
+  double kappa = 0.0;
+  for (int d = 0; d < ctx->D; d++) {
+    const double c0 = ctx->h_ctr.empty() ? 0.0 : ctx->h_ctr[d];
+    double r = ctx->h_xabs.empty() ? 0.0 : (double)ctx->h_xabs[d];
+    r = std::max(r, std::max(fabs(ctx->h_mumax[d] - c0), fabs(ctx->h_mumin[d] - c0)));
+    const double t = 2.0 * ctx->h_ivmax[d] * r * r;
+    kappa += (t == t) ? t : INFINITY;
+  }
+  ctx->kappa = kappa;
   return HMMCU_OK;
 }
 
 // ---- tensor-core path: W images ------------------------------------------------------------------
+// use_tc: 0 = never, 1 = when the accuracy guard allows it (default), 2 = always (testing)
+constexpr double kTcKappaMax = 1.0e4;
 static bool tc_supported(const hmmcu_ctx *ctx) {
   if (!ctx->use_tc || ctx->M > kTcMaxTN || ctx->N > 8) return false;
+  if (ctx->use_tc == 1 && !(ctx->kappa <= kTcKappaMax)) return false;
   const int SCt = std::max(1, kTcMaxTN / ctx->M);
   const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * ctx->M, 16);
   return tc_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
@@ -368,6 +410,7 @@ static int ensure_tc_images(hmmcu_ctx *ctx, int mode) {
 
 template <bool TRAIN>
 static int launch_emis_tc(hmmcu_ctx *ctx, const TcTile *tiles_dev, int ntiles, float *logb, int64_t fbase, int64_t ldb, float *post) {
+  ctx->last_tc = true;
   if (ntiles == 0) return HMMCU_OK;
   hmmcu_ctx::TcSet &ts = TRAIN ? ctx->tc_train : ctx->tc_dec;
   const size_t smem = tc_emis_smem_bytes(ts.TN, 2 * ctx->DP);
@@ -386,6 +429,7 @@ static int emis_chunk_states(const hmmcu_ctx *ctx) { return std::max(1, std::min
 template <bool POST>
 static int launch_emis(hmmcu_ctx *ctx, const EmisTile *tiles_dev, int64_t ntiles, float *logb, int64_t fbase, int64_t ldb,
                        int decode, float *post) {
+  ctx->last_tc = false;
   if (ntiles == 0) return HMMCU_OK;
   const int SC = emis_chunk_states(ctx);
   const size_t smem = emis_smem_bytes(SC * ctx->M, SC, ctx->DP);

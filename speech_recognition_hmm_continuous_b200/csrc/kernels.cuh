@@ -48,18 +48,27 @@ __global__ void k_center(const double *__restrict__ x, int64_t F, int D, int DP,
 
 // x64[F][D] -> x32[F][DP] = (float)(x - ctr); column D holds 1.0 (so that the first-order
 // accumulator of that column is the occupancy S0), remaining pad columns 0.
+// xabs[d] (float bits, zero-initialised) receives max |x - ctr| per dimension: the data radius that
+// decides whether the expanded quadratic of the tensor-core emission path is accurate enough.
 __global__ void k_pack_features(const double *__restrict__ x, const double *__restrict__ ctr, int64_t F, int D,
-                                int DP, float *__restrict__ out) {
+                                int DP, float *__restrict__ out, unsigned int *__restrict__ xabs) {
+  __shared__ unsigned int smax[256];
+  for (int i = threadIdx.x; i < DP; i += blockDim.x) smax[i] = 0u;
+  __syncthreads();
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = F * DP;
   for (; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t f = idx / DP;
     int d = (int)(idx - f * DP);
     float v;
-    if (d < D) v = (float)(x[f * D + d] - ctr[d]);
-    else v = (d == D) ? 1.0f : 0.0f;
+    if (d < D) {
+      v = (float)(x[f * D + d] - ctr[d]);
+      atomicMax(&smax[d], __float_as_uint(fabsf(v)));
+    } else v = (d == D) ? 1.0f : 0.0f;
     out[idx] = v;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) atomicMax(&xabs[i], smax[i]);
 }
 
 // Per Gaussian g (global index over V*N*M): mu32[g][DP] = mu - ctr, iv32[g][DP] = inverse variance

@@ -23,6 +23,7 @@ def ctx(request):
     on the CUDA-core kernel (hmmcu_set_option "tc_emis" = 0)."""
     c = api.Context(0)
     c.set_option("tc_emis", 1 if request.param == "tc" else 0)
+    c.path = request.param
     yield c
     c.close()
 
@@ -69,6 +70,7 @@ def test_forward_scores_and_labels_match_oracle(ctx):
     ctx.set_features(x, off)
     ctx.set_models(ms)
     got = ctx.forward_scores()
+    assert ctx.kernel_ms("tc_active") == (1 if ctx.path == "tc" else 0)
     want = np.array([[o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]]) for v in range(ms.V)] for u in range(len(labels))])
     assert np.allclose(got, want, rtol=RTOL, atol=0)
     assert np.abs(got / want - 1).max() < 1e-6  # in practice far inside the bar
@@ -119,6 +121,7 @@ def test_shipped_fixtures_degenerate_regime(ctx, golden_dir):
     ctx.set_features(np.concatenate(xs), off)
     ctx.set_models(ms)
     got = ctx.forward_scores(emulate_underflow=True)
+    assert ctx.kernel_ms("kappa") > 1e4 and ctx.kernel_ms("tc_active") == 0  # raw-Hz data: the accuracy guard picks the direct form
     label, second = ctx.rank(got)
     for u, rec in enumerate(kat["recognition"]):
         ref_score = {w: float(v.replace("-nan", "nan")) for w, v in rec["sorted"]}
