@@ -1,0 +1,282 @@
+// fb_kernels.cuh -- scaled forward / backward for Baum-Welch training (calc_alpha, calc_beta,
+// calc_transition_probab, calc_den_mix_coef, calc_probability; T-FS:1380-1664), latency-first.
+//
+// The recursion over time is a dependent chain; what bounds it is the latency of one step, not
+// throughput.  So one THREAD owns one utterance and keeps the whole state vector in registers
+// (no shuffles, no shared memory on the chain), the forward and the backward chains of an
+// utterance run concurrently in two different warps, and each scales by an exact power of two taken
+// from the exponent field of the step's sum (two integer instructions instead of a division):
+//   forward :  z_t = ((z_{t-1} A) o b~_t) 2^-e_t      b~_i(t) = exp(logb_i(t) - m_t), m_t = max_i logb_i(t)
+//   backward:  w_t = (A (b~_{t+1} o w_{t+1})) 2^-e'_t  w_{T-1} = [0,..,0,1]   (final state only, T-FS:1484)
+// Any positive per-frame scaling gives the same posteriors; the reference's c_t-scaled quantities
+// are recovered exactly from per-frame normalisation:
+//   alpha^_t(i) beta^_t(i) / c_t          = phi * z_t(i) w_t(i) / sum_j z_t(j) w_t(j)
+//   alpha^_t(i) a_ij b_j(t+1) beta^_t+1(j) = phi * z_t(i) a_ij q_j / sum_kl z_t(k) a_kl q_l,  q = b~_{t+1} o w_{t+1}
+// with phi = alpha^_{T-1}(N-1) (the reference's beta^ starts from the final state only, so its
+// gammas sum to phi, not to 1), and
+//   log P = sum_t m_t + ln2 sum_t e_t + log z_{T-1}(N-1)      (calc_probability, T-FS:1546-1549).
+// A second phase (one warp per utterance, lanes over frames) forms gamma and the transition sums.
+#pragma once
+#include "kernels.cuh"
+
+namespace hmmk {
+
+constexpr int kFbUtts = 8;        // utterances per CTA
+constexpr int kFbThreads = 256;   // 8 warps: warp 0 = forward chains, warp 1 = backward chains, then all combine
+
+// exp(y) for y <= 0 as a double: single-precision mantissa accuracy (the log-densities it is fed
+// are single precision), double-precision range.  y < -700 -> 0.
+__device__ __forceinline__ double exp_scaled(float y) {
+  const float yc = fmaxf(y, -700.f);  // branch-free: the chain's five exponentials must overlap
+  const float n = rintf(yc * 1.4426950408889634f);
+  float f = fmaf(yc, 1.4426950216293335f, -n);  // (float)log2(e)
+  f = fmaf(yc, 1.9259629911e-8f, f);            // log2(e) - (float)log2(e)
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));  // |f| <= 0.5: 2 ulp
+  const double d = (double)p;
+  const int hi = __double2hiint(d) + ((int)n << 20);
+  return (y < -700.f) ? 0.0 : __hiloint2double(hi, __double2loint(d));
+}
+
+// r = 2^-e with e the unbiased exponent of s (so that s*r is in [1,2)); e returned.  s == 0, denormal,
+// inf or NaN: r = 1, e = 0.
+__device__ __forceinline__ double pow2_scale(double s, int &e) {
+  const int be = (__double2hiint(s) >> 20) & 0x7ff;
+  if (be == 0 || be == 0x7ff) { e = 0; return 1.0; }
+  e = be - 1023;
+  return __hiloint2double((2046 - be) << 20, 0);
+}
+
+template <int NS>
+__device__ __forceinline__ void load_lb(const float *__restrict__ p, float (&l)[NS]) {
+#pragma unroll
+  for (int i = 0; i < NS; i++) l[i] = __ldg(p + i);
+}
+
+template <int NS, bool BANDED>
+__device__ __forceinline__ void fb_forward(const float *__restrict__ lb, int T, const double *__restrict__ A,
+                                           double *__restrict__ alpha, double &logp, double &phi) {
+  double a[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) a[k] = A[k];
+  double z[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) z[i] = 0.0;
+  double msum = 0.0;
+  int esum = 0;
+  float cur[NS], nxt[NS];
+  load_lb<NS>(lb, cur);
+  for (int t = 0; t < T; t++) {
+    load_lb<NS>(lb + (size_t)min(t + 1, T - 1) * NS, nxt);  // next step's operands are in flight during this step
+    float m = cur[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) m = fmaxf(m, cur[i]);
+    const float mf = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
+    double raw[NS];
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) raw[i] = 0.0;
+      raw[0] = exp_scaled(cur[0] - mf);  // pi = [1,0,..,0]  T-FS:232-234
+    } else {
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        double aux;
+        if (BANDED) {
+          aux = z[i] * a[i * NS + i];
+          if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
+        } else {
+          aux = 0.0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
+        }
+        raw[i] = aux * exp_scaled(cur[i] - mf);
+      }
+    }
+    double s = raw[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) s += raw[i];
+    int e;
+    const double r = pow2_scale(s, e);
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      z[i] = raw[i] * r;
+      alpha[(size_t)t * NS + i] = z[i];
+    }
+    esum += e;
+    msum += (double)m;
+#pragma unroll
+    for (int i = 0; i < NS; i++) cur[i] = nxt[i];
+  }
+  double s = z[0];
+#pragma unroll
+  for (int i = 1; i < NS; i++) s += z[i];
+  phi = z[NS - 1] / s;                                                  // alpha^_{T-1}(N-1)
+  logp = msum + 0.6931471805599453 * (double)esum + log(z[NS - 1]);    // calc_probability
+}
+
+template <int NS, bool BANDED>
+__device__ __forceinline__ void fb_backward(const float *__restrict__ lb, int T, const double *__restrict__ A,
+                                            double *__restrict__ beta) {
+  double a[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) a[k] = A[k];
+  double w[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    w[i] = (i == NS - 1) ? 1.0 : 0.0;
+    beta[(size_t)(T - 1) * NS + i] = w[i];
+  }
+  float cur[NS], nxt[NS];
+  load_lb<NS>(lb + (size_t)(T - 1) * NS, cur);
+  for (int t = T - 2; t >= 0; t--) {
+    load_lb<NS>(lb + (size_t)max(t, 0) * NS, nxt);  // logb of frame t, used by the next iteration
+    float m = cur[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) m = fmaxf(m, cur[i]);
+    double q[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) q[j] = exp_scaled(cur[j] - ((m > kNegInf) ? m : 0.f)) * w[j];
+    double raw[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      double aux;
+      if (BANDED) {
+        aux = a[i * NS + i] * q[i];
+        if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
+      } else {
+        aux = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
+      }
+      raw[i] = aux;
+    }
+    double s = raw[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) s += raw[i];
+    int e;
+    const double r = pow2_scale(s, e);
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      w[i] = raw[i] * r;
+      beta[(size_t)t * NS + i] = w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) cur[i] = nxt[i];
+  }
+}
+
+// Outputs: gamma32[F][N] (the reference's alpha^ beta^ / c, T-FS:1709); per-model statistics head
+// (num_trans, den_trans, den_mix, sum_logp, n_utt) by double atomics, one set per utterance;
+// logp_utt[U] (0 for masked utterances).
+template <int NS, bool BANDED>
+__global__ void __launch_bounds__(kFbThreads)
+k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
+     const double *__restrict__ Aall, int U, double *__restrict__ alpha_ws, double *__restrict__ beta_ws,
+     float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
+     double *__restrict__ logp_utt) {
+  __shared__ double sA[kFbUtts][NS * NS];
+  __shared__ double sphi[kFbUtts], slp[kFbUtts];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = blockIdx.x * kFbUtts;
+  for (int idx = tid; idx < kFbUtts * NS * NS; idx += kFbThreads) {
+    const int uu = idx / (NS * NS), k = idx - uu * NS * NS;
+    const int u = u0 + uu;
+    const int v = (u < U) ? u2m[u] : -1;
+    sA[uu][k] = (v >= 0) ? Aall[(int64_t)v * NS * NS + k] : 0.0;
+  }
+  __syncthreads();
+  // ---------------- phase 1: the two chains of each utterance, one thread each ----------------
+  if (warp < 2 && lane < kFbUtts) {
+    const int u = u0 + lane;
+    if (u < U && u2m[u] >= 0) {
+      const int64_t base = off[u];
+      const int T = (int)(off[u + 1] - base);
+      if (warp == 0) {
+        double lp, phi;
+        fb_forward<NS, BANDED>(logb + base * NS, T, sA[lane], alpha_ws + base * NS, lp, phi);
+        sphi[lane] = phi;
+        slp[lane] = lp;
+      } else {
+        fb_backward<NS, BANDED>(logb + base * NS, T, sA[lane], beta_ws + base * NS);
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- phase 2: one warp per utterance, lanes over frames ----------------
+  for (int uu = warp; uu < kFbUtts; uu += kFbThreads / 32) {
+    const int u = u0 + uu;
+    if (u >= U) continue;
+    const int v = u2m[u];
+    if (v < 0) {  // masked utterance (its model has converged)
+      if (lane == 0 && logp_utt) logp_utt[u] = 0.0;
+      continue;
+    }
+    const int64_t base = off[u];
+    const int T = (int)(off[u + 1] - base);
+    const double *A = sA[uu];
+    const double phi = sphi[uu];
+    double acc_num[NS][2], acc_dt[NS], acc_dm[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
+    for (int t = lane; t < T; t += 32) {
+      double al[NS], g[NS], G = 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        al[i] = alpha_ws[(base + t) * NS + i];
+        g[i] = al[i] * beta_ws[(base + t) * NS + i];
+        G += g[i];
+      }
+      const double sc = (G > 0.0) ? phi / G : 0.0;  // unreachable final state: no occupancy, as the reference
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        g[i] *= sc;  // alpha^ beta^ / c   T-FS:1617,1658,1709
+        gamma[(base + t) * NS + i] = (float)g[i];
+        acc_dm[i] += g[i];
+      }
+      if (t < T - 1) {
+        float l1[NS];
+        load_lb<NS>(logb + (base + t + 1) * NS, l1);
+        float m = l1[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) m = fmaxf(m, l1[i]);
+        double q[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * beta_ws[(base + t + 1) * NS + j];
+        double Z = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          double rb = 0.0;
+#pragma unroll
+          for (int j = 0; j < NS; j++) rb = fma(A[i * NS + j], q[j], rb);
+          Z = fma(al[i], rb, Z);
+        }
+        const double zs = (Z > 0.0) ? phi / Z : 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          acc_dt[i] += g[i];
+          acc_num[i][0] += al[i] * A[i * NS + i] * q[i] * zs;                              // band j = i   T-FS:1611
+          if (i + 1 < NS) acc_num[i][1] += al[i] * A[i * NS + i + 1] * q[i + 1] * zs;      // j = i + 1
+        }
+      }
+    }
+    double *st = stats + (int64_t)v * stats_stride;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      const double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
+      const double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
+      if (lane == 0) {
+        atomicAdd(st + i * NS + i, n0);
+        if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
+        atomicAdd(st + NS * NS + i, dt);
+        atomicAdd(st + NS * NS + NS + i, dm);
+      }
+    }
+    if (lane == 0) {
+      atomicAdd(st + off_sumlogp, slp[uu]);
+      atomicAdd(st + off_sumlogp + 1, 1.0);
+      if (logp_utt) logp_utt[u] = slp[uu];
+    }
+  }
+}
+
+}  // namespace hmmk

@@ -13,6 +13,7 @@
 
 #include "hmm_cuda.h"
 #include "kernels.cuh"
+#include "fb_kernels.cuh"
 #include "tc_kernels.cuh"
 
 using namespace hmmk;
@@ -74,6 +75,7 @@ struct hmmcu_ctx {
   // models
   int V = 0, N = 0, M = 0, G = 0, Dm = 0;
   bool have_models = false, pack_dirty = true;
+  bool banded = false;  // every A is upper-bidiagonal (the left-to-right DELTA=1 topology of T-FS:774-795)
   DevBuf A, c, mu, iv, det, mu32, iv32, k32;
 
   // training map
@@ -92,9 +94,14 @@ struct hmmcu_ctx {
   } tc_train, tc_dec;
   DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec;
   int64_t n_tc_tiles_train = 0;
+  // tensor-core accumulate kernel: W images per (model, block of 128 Gaussians) and its work units
+  DevBuf acc_images, acc_kc, acc_units, acc_dbg;
+  int debug_acc = 0;
+  bool acc_dirty = true;
+  int64_t n_acc_units = 0;
 
   // workspaces
-  DevBuf logb, post, gamma, alpha_ws, cs_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
+  DevBuf logb, post, gamma, alpha_ws, beta_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
   int64_t stats_n = 0;
 };
 
@@ -178,10 +185,10 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   cudaStreamSynchronize(ctx->st);
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
-                    &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->cs_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
+                    &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
-                    &ctx->frame_ids_d, &ctx->tc_tiles_dec};
+                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -217,6 +224,7 @@ double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (!ctx || !key) return HMMCU_EINVAL;
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
+  if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -317,6 +325,11 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
         mx[d] = pm[d] > mx[d] ? pm[d] : mx[d];
       }
     }
+    ctx->banded = true;
+    for (int64_t k = 0; k < (int64_t)V * N * N && ctx->banded; k++) {
+      const int i = (int)((k / N) % N), j = (int)(k % N);
+      if ((j < i || j > i + 1) && A[k] != 0.0) ctx->banded = false;
+    }
   }
   if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
   ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = (int)G;
@@ -347,6 +360,7 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   ctx->pack_dirty = false;
   ctx->tc_train.dirty = true;
   ctx->tc_dec.dirty = true;
+  ctx->acc_dirty = true;
   // kappa = sum_d 2 * max(iv_d) * r_d^2, r_d = largest centred |x| or |mu| in dimension d: an upper bound on
   // sum_k |Xaug_k W_k|.  The 3xTF32 contraction carries ~1e-7 of that magnitude as absolute error.
   double kappa = 0.0;
@@ -369,7 +383,23 @@ static bool tc_supported(const hmmcu_ctx *ctx) {
   if (ctx->use_tc == 1 && !(ctx->kappa <= kTcKappaMax)) return false;
   const int SCt = std::max(1, kTcMaxTN / ctx->M);
   const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * ctx->M, 16);
+  if (!tc_acc_fits(2 * ctx->DP)) return false;
   return tc_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
+}
+
+static int ensure_acc_images(hmmcu_ctx *ctx) {
+  if (!ctx->acc_dirty) return HMMCU_OK;
+  const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
+  CK(ctx->acc_images.ensure(tc_accT_image_bytes(KP) * nimg));
+  CK(ctx->acc_kc.ensure(sizeof(float) * 128 * (size_t)nimg));
+  t_begin(ctx, "pack");
+  k_pack_wT_tc<<<nimg, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), ctx->c.as<double>(),
+                                          ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP, ctx->acc_images.as<float>(),
+                                          ctx->acc_kc.as<float>());
+  LAUNCH_CHECK();
+  t_end(ctx, "pack");
+  ctx->acc_dirty = false;
+  return HMMCU_OK;
 }
 
 // mode 0: training images (per model, CT column tiles each); mode 1: decode images (all states concatenated)
@@ -637,6 +667,22 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
         for (int32_t r = r0; r < r1; r += kTcRows) tt.push_back({r, std::min<int32_t>(kTcRows, r1 - r), v * CT + ct, ct * SCt, v, 0});
     }
     ctx->n_tc_tiles_train = (int64_t)tt.size();
+    {  // accumulate-kernel units, ordered (model, row block, tile)
+      std::vector<TcTile> au;
+      const int nRB = (ctx->G + 127) / 128;
+      int32_t r0 = 0;
+      for (int v = 0; v < V; v++) {
+        int32_t nfr = 0;
+        for (int k = start[v]; k < start[v + 1]; k++) nfr += (int32_t)(ctx->off[utts[k] + 1] - ctx->off[utts[k]]);
+        for (int rb = 0; rb < nRB; rb++)
+          for (int32_t r = 0; r < nfr; r += kTcRows) au.push_back({r0 + r, std::min<int32_t>(kTcRows, nfr - r), v * nRB + rb, 0, v, rb});
+        r0 += nfr;
+      }
+      ctx->n_acc_units = (int64_t)au.size();
+      CK(ctx->acc_units.ensure(sizeof(TcTile) * std::max<size_t>(au.size(), 1)));
+      CK(cudaMemcpyAsync(ctx->acc_units.p, au.data(), sizeof(TcTile) * au.size(), cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));
+    }
     CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
     CK(ctx->tc_tiles_train.ensure(sizeof(TcTile) * std::max<size_t>(tt.size(), 1)));
     CK(cudaMemcpyAsync(ctx->frame_ids_d.p, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice, ctx->st));
@@ -674,16 +720,18 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     if (rc) return rc;
     const int64_t F = ctx->F;
     CK(ctx->logb.ensure(sizeof(float) * F * N));
-    CK(ctx->post.ensure(sizeof(float) * F * G));
+    const bool use_tc = tc_supported(ctx);
+    if (!use_tc) CK(ctx->post.ensure(sizeof(float) * F * G));
     CK(ctx->gamma.ensure(sizeof(float) * F * N));
     CK(ctx->alpha_ws.ensure(sizeof(double) * F * N));
-    CK(ctx->cs_ws.ensure(sizeof(double) * F));
+    CK(ctx->beta_ws.ensure(sizeof(double) * F * N));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
     // 1. emissions + per-mixture posteriors
-    if (tc_supported(ctx)) {
+    if (use_tc) {
       if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
+      if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
       t_begin(ctx, "emis");
-      rc = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, ctx->post.as<float>());
+      rc = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, nullptr);
     } else {
       t_begin(ctx, "emis");
       rc = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
@@ -693,17 +741,44 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     // 2. forward / backward, gamma, transition statistics, log-probabilities
     t_begin(ctx, "fwdbwd");
     {
-      const int blocks = (U + kFbWarps - 1) / kFbWarps;
-      DISPATCH_N(N, (k_fwdbwd<NS><<<blocks, kFbWarps * 32, 0, ctx->st>>>(
-                        ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
-                        ctx->alpha_ws.as<double>(), ctx->cs_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
-                        ss, off_lp, ctx->logp_utt_d.as<double>())));
+      const int blocks = (U + kFbUtts - 1) / kFbUtts;
+      if (ctx->banded) {
+        DISPATCH_N(N, (k_fb<NS, true><<<blocks, kFbThreads, 0, ctx->st>>>(
+                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
+                          ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                          ss, off_lp, ctx->logp_utt_d.as<double>())));
+      } else {
+        DISPATCH_N(N, (k_fb<NS, false><<<blocks, kFbThreads, 0, ctx->st>>>(
+                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
+                          ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                          ss, off_lp, ctx->logp_utt_d.as<double>())));
+      }
       LAUNCH_CHECK();
     }
     t_end(ctx, "fwdbwd");
     // 3. mixture accumulators
     t_begin(ctx, "accum");
-    {
+    if (use_tc) {
+      const size_t smem = tc_acc_smem_bytes(2 * DP);
+      CK(cudaFuncSetAttribute(k_accum_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::min<int64_t>(ctx->n_acc_units, ctx->sm_count);
+      if (ctx->debug_acc) {
+        CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
+        CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
+      }
+      if (grid > 0) {
+        k_accum_tc<<<grid, kTcThreads, smem, ctx->st>>>(ctx->acc_units.as<TcTile>(), (int)ctx->n_acc_units, ctx->frame_ids_d.as<int32_t>(),
+                                                        ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
+                                                        ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                        ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2,
+                                                        ctx->debug_acc ? ctx->acc_dbg.as<float>() : nullptr);
+        LAUNCH_CHECK();
+      }
+      const int64_t total = (int64_t)V * G * D;
+      k_finalize_stats<<<(unsigned)((total + 255) / 256), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, V, G, D, off_S0, off_S1,
+                                                                            off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>());
+      LAUNCH_CHECK();
+    } else {
       const int NGG = kAccThreads / DP, GCH = NGG * kAccGPT;
       const int nz = (G + GCH - 1) / GCH;
       int nparts = std::max(1, (2 * ctx->sm_count + V * nz - 1) / (V * nz));
@@ -717,7 +792,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       LAUNCH_CHECK();
       const int64_t total = (int64_t)V * G * D;
       k_finalize_stats<<<(unsigned)((total + 255) / 256), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, V, G, D, off_S0, off_S1,
-                                                                            ctx->ctr.as<double>());
+                                                                            off_S2, ctx->ctr.as<double>(), nullptr);
       LAUNCH_CHECK();
     }
     t_end(ctx, "accum");
@@ -732,6 +807,15 @@ double *hmmcu_stats_device(hmmcu_ctx *ctx, int64_t *n_doubles) {
   if (!ctx) return nullptr;
   if (n_doubles) *n_doubles = ctx->stats_n;
   return ctx->stats.as<double>();
+}
+
+// diagnostic: first unit's GEMM1 output (log2 c N), weights and GEMM2 output of the accumulate kernel
+extern "C" int hmmcu_debug_acc_read(hmmcu_ctx *ctx, float *out) {
+  if (!ctx || !out || !ctx->acc_dbg.p) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaMemcpyAsync(out, ctx->acc_dbg.p, sizeof(float) * 3 * 16384, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
 }
 
 int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats) {

@@ -489,8 +489,12 @@ k_accum_simt(const float *__restrict__ x32, const float *__restrict__ gamma, con
 }
 
 // S1 was accumulated on centred features: S1 += ctr * S0  (before any cross-rank reduction).
+// mu != nullptr (tensor-core accumulators): the second-order slot holds the raw centred moment
+// sum w x^2; turn it into the reference's sum w (x - mu_old)^2 (T-FS:1716-1719), in double:
+//   sum w (x - m)^2 = sum w x^2 - 2 m sum w x + m^2 sum w,   m = mu_old - ctr.
 __global__ void k_finalize_stats(double *__restrict__ stats, int64_t stats_stride, int V, int G, int D,
-                                 int64_t off_S0, int64_t off_S1, const double *__restrict__ ctr) {
+                                 int64_t off_S0, int64_t off_S1, int64_t off_S2, const double *__restrict__ ctr,
+                                 const double *__restrict__ mu) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t total = (int64_t)V * G * D;
   if (idx >= total) return;
@@ -499,7 +503,12 @@ __global__ void k_finalize_stats(double *__restrict__ stats, int64_t stats_strid
   int g = (int)(vg % G);
   int64_t v = vg / G;
   double *st = stats + v * stats_stride;
-  st[off_S1 + (int64_t)g * D + d] += ctr[d] * st[off_S0 + g];
+  const double s0 = st[off_S0 + g], s1 = st[off_S1 + (int64_t)g * D + d];
+  if (mu) {
+    const double m = mu[vg * D + d] - ctr[d];
+    st[off_S2 + (int64_t)g * D + d] = st[off_S2 + (int64_t)g * D + d] - 2.0 * m * s1 + m * m * s0;
+  }
+  st[off_S1 + (int64_t)g * D + d] = s1 + ctr[d] * s0;
 }
 
 // ------------------------------------------------------------------------------------------------
