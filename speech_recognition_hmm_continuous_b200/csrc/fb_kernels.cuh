@@ -15,6 +15,10 @@
 // with phi = alpha^_{T-1}(N-1) (the reference's beta^ starts from the final state only, so its
 // gammas sum to phi, not to 1), and
 //   log P = sum_t m_t + ln2 sum_t e_t + log z_{T-1}(N-1)      (calc_probability, T-FS:1546-1549).
+// The chain threads never touch global memory for their operands: all eight warps of the CTA stage
+// the next window of kFbWin frames of every utterance of the CTA into shared memory as b~ (double) and
+// m (float) -- forward window from the start of the utterance, backward window from its end -- so a
+// chain step is five LDS.64, the banded matvec, the power-of-two scaling and five STG.64.
 // A second phase (one warp per utterance, lanes over frames) forms gamma and the transition sums.
 #pragma once
 #include "kernels.cuh"
@@ -23,6 +27,7 @@ namespace hmmk {
 
 constexpr int kFbUtts = 8;        // utterances per CTA
 constexpr int kFbThreads = 256;   // 8 warps: warp 0 = forward chains, warp 1 = backward chains, then all combine
+constexpr int kFbWin = 128;       // frames per staged window
 
 // exp(y) for y <= 0 as a double: single-precision mantissa accuracy (the log-densities it is fed
 // are single precision), double-precision range.  y < -700 -> 0.
@@ -53,116 +58,8 @@ __device__ __forceinline__ void load_lb(const float *__restrict__ p, float (&l)[
   for (int i = 0; i < NS; i++) l[i] = __ldg(p + i);
 }
 
-template <int NS, bool BANDED>
-__device__ __forceinline__ void fb_forward(const float *__restrict__ lb, int T, const double *__restrict__ A,
-                                           double *__restrict__ alpha, double &logp, double &phi) {
-  double a[NS * NS];
-#pragma unroll
-  for (int k = 0; k < NS * NS; k++) a[k] = A[k];
-  double z[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) z[i] = 0.0;
-  double msum = 0.0;
-  int esum = 0;
-  float cur[NS], nxt[NS];
-  load_lb<NS>(lb, cur);
-  for (int t = 0; t < T; t++) {
-    load_lb<NS>(lb + (size_t)min(t + 1, T - 1) * NS, nxt);  // next step's operands are in flight during this step
-    float m = cur[0];
-#pragma unroll
-    for (int i = 1; i < NS; i++) m = fmaxf(m, cur[i]);
-    const float mf = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
-    double raw[NS];
-    if (t == 0) {
-#pragma unroll
-      for (int i = 0; i < NS; i++) raw[i] = 0.0;
-      raw[0] = exp_scaled(cur[0] - mf);  // pi = [1,0,..,0]  T-FS:232-234
-    } else {
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        double aux;
-        if (BANDED) {
-          aux = z[i] * a[i * NS + i];
-          if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
-        } else {
-          aux = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
-        }
-        raw[i] = aux * exp_scaled(cur[i] - mf);
-      }
-    }
-    double s = raw[0];
-#pragma unroll
-    for (int i = 1; i < NS; i++) s += raw[i];
-    int e;
-    const double r = pow2_scale(s, e);
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      z[i] = raw[i] * r;
-      alpha[(size_t)t * NS + i] = z[i];
-    }
-    esum += e;
-    msum += (double)m;
-#pragma unroll
-    for (int i = 0; i < NS; i++) cur[i] = nxt[i];
-  }
-  double s = z[0];
-#pragma unroll
-  for (int i = 1; i < NS; i++) s += z[i];
-  phi = z[NS - 1] / s;                                                  // alpha^_{T-1}(N-1)
-  logp = msum + 0.6931471805599453 * (double)esum + log(z[NS - 1]);    // calc_probability
-}
-
-template <int NS, bool BANDED>
-__device__ __forceinline__ void fb_backward(const float *__restrict__ lb, int T, const double *__restrict__ A,
-                                            double *__restrict__ beta) {
-  double a[NS * NS];
-#pragma unroll
-  for (int k = 0; k < NS * NS; k++) a[k] = A[k];
-  double w[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-    w[i] = (i == NS - 1) ? 1.0 : 0.0;
-    beta[(size_t)(T - 1) * NS + i] = w[i];
-  }
-  float cur[NS], nxt[NS];
-  load_lb<NS>(lb + (size_t)(T - 1) * NS, cur);
-  for (int t = T - 2; t >= 0; t--) {
-    load_lb<NS>(lb + (size_t)max(t, 0) * NS, nxt);  // logb of frame t, used by the next iteration
-    float m = cur[0];
-#pragma unroll
-    for (int i = 1; i < NS; i++) m = fmaxf(m, cur[i]);
-    double q[NS];
-#pragma unroll
-    for (int j = 0; j < NS; j++) q[j] = exp_scaled(cur[j] - ((m > kNegInf) ? m : 0.f)) * w[j];
-    double raw[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      double aux;
-      if (BANDED) {
-        aux = a[i * NS + i] * q[i];
-        if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
-      } else {
-        aux = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
-      }
-      raw[i] = aux;
-    }
-    double s = raw[0];
-#pragma unroll
-    for (int i = 1; i < NS; i++) s += raw[i];
-    int e;
-    const double r = pow2_scale(s, e);
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      w[i] = raw[i] * r;
-      beta[(size_t)t * NS + i] = w[i];
-    }
-#pragma unroll
-    for (int i = 0; i < NS; i++) cur[i] = nxt[i];
-  }
+__host__ __device__ inline size_t fb_smem_bytes(int NS) {
+  return (size_t)2 * kFbUtts * (kFbWin * NS + 2) * sizeof(double) + (size_t)kFbUtts * (kFbWin + 1) * sizeof(float);
 }
 
 // Outputs: gamma32[F][N] (the reference's alpha^ beta^ / c, T-FS:1709); per-model statistics head
@@ -174,8 +71,14 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
      const double *__restrict__ Aall, int U, double *__restrict__ alpha_ws, double *__restrict__ beta_ws,
      float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
      double *__restrict__ logp_utt) {
+  extern __shared__ __align__(16) uint8_t fb_smem[];
+  constexpr int US = kFbWin * NS + 2, MS = kFbWin + 1;  // per-utterance strides, padded: the 8 chain lanes hit 8 different banks
+  double *bf = reinterpret_cast<double *>(fb_smem);            // [2][kFbUtts][US]  b~: 0 = forward window, 1 = backward window
+  float *mf = reinterpret_cast<float *>(bf + 2 * kFbUtts * US);  // [kFbUtts][MS]   m of the forward window
   __shared__ double sA[kFbUtts][NS * NS];
   __shared__ double sphi[kFbUtts], slp[kFbUtts];
+  __shared__ int64_t sbase[kFbUtts];
+  __shared__ int sT[kFbUtts];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int u0 = blockIdx.x * kFbUtts;
   for (int idx = tid; idx < kFbUtts * NS * NS; idx += kFbThreads) {
@@ -184,22 +87,134 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
     const int v = (u < U) ? u2m[u] : -1;
     sA[uu][k] = (v >= 0) ? Aall[(int64_t)v * NS * NS + k] : 0.0;
   }
+  if (tid < kFbUtts) {
+    const int u = u0 + tid;
+    const bool live = u < U && u2m[u] >= 0;
+    sbase[tid] = live ? off[u] : 0;
+    sT[tid] = live ? (int)(off[u + 1] - off[u]) : 0;
+  }
   __syncthreads();
+  int Tmax = 0;
+#pragma unroll
+  for (int uu = 0; uu < kFbUtts; uu++) Tmax = max(Tmax, sT[uu]);
+
   // ---------------- phase 1: the two chains of each utterance, one thread each ----------------
-  if (warp < 2 && lane < kFbUtts) {
-    const int u = u0 + lane;
-    if (u < U && u2m[u] >= 0) {
-      const int64_t base = off[u];
-      const int T = (int)(off[u + 1] - base);
-      if (warp == 0) {
-        double lp, phi;
-        fb_forward<NS, BANDED>(logb + base * NS, T, sA[lane], alpha_ws + base * NS, lp, phi);
-        sphi[lane] = phi;
-        slp[lane] = lp;
-      } else {
-        fb_backward<NS, BANDED>(logb + base * NS, T, sA[lane], beta_ws + base * NS);
+  const bool chain = warp < 2 && lane < kFbUtts && sT[lane & (kFbUtts - 1)] > 0;
+  const int myT = chain ? sT[lane] : 0;
+  const int64_t mybase = chain ? sbase[lane] : 0;
+  double a[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) a[k] = chain ? sA[lane][k] : 0.0;
+  double z[NS];  // forward: z_t; backward: w_t
+#pragma unroll
+  for (int i = 0; i < NS; i++) z[i] = (warp == 1 && i == NS - 1) ? 1.0 : 0.0;
+  double msum = 0.0;
+  int esum = 0;
+  if (chain && warp == 1) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) beta_ws[(mybase + myT - 1) * NS + i] = z[i];  // final state only, T-FS:1484-1490
+  }
+  for (int w0 = 0; w0 < Tmax; w0 += kFbWin) {
+    __syncthreads();  // the previous window has been consumed
+    // stage: thread <-> (direction, utterance, frame of the window)
+    for (int it = tid; it < 2 * kFbUtts * kFbWin; it += kFbThreads) {
+      const int dir = it / (kFbUtts * kFbWin), rem = it - dir * (kFbUtts * kFbWin);
+      const int uu = rem / kFbWin, k = rem - uu * kFbWin;
+      const int T = sT[uu];
+      const int t = dir == 0 ? w0 + k : T - 1 - (w0 + k);
+      if (w0 + k < T) {
+        float l[NS];
+        load_lb<NS>(logb + (sbase[uu] + t) * NS, l);
+        float m = l[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
+        const float ms = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
+        double *dst = bf + (size_t)(dir * kFbUtts + uu) * US + k * NS;
+#pragma unroll
+        for (int i = 0; i < NS; i++) dst[i] = exp_scaled(l[i] - ms);
+        if (dir == 0) mf[uu * MS + k] = m;
       }
     }
+    __syncthreads();
+    if (chain && warp == 0) {  // forward: frames w0 .. w0+kFbWin-1
+      const double *bw = bf + (size_t)lane * US;
+      const int kend = min(kFbWin, myT - w0);
+      double *ap = alpha_ws + (mybase + w0) * NS;
+      for (int k = 0; k < kend; k++) {
+        double b[NS], raw[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) b[i] = bw[k * NS + i];
+        if (w0 + k == 0) {
+#pragma unroll
+          for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? b[0] : 0.0;  // pi = [1,0,..,0]  T-FS:232-234
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; i++) {
+            double aux;
+            if (BANDED) {
+              aux = z[i] * a[i * NS + i];
+              if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
+            } else {
+              aux = 0.0;
+#pragma unroll
+              for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
+            }
+            raw[i] = aux * b[i];
+          }
+        }
+        double s = raw[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) s += raw[i];
+        int e;
+        const double r = pow2_scale(s, e);
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          z[i] = raw[i] * r;
+          ap[(size_t)k * NS + i] = z[i];
+        }
+        esum += e;
+        msum += (double)mf[lane * MS + k];
+      }
+    } else if (chain && warp == 1) {  // backward: step j = w0 + k turns beta~_{T-1-j} into beta~_{T-2-j} with b~ of frame T-1-j
+      const double *bw = bf + (size_t)(kFbUtts + lane) * US;
+      const int kend = min(kFbWin, myT - 1 - w0);
+      for (int k = 0; k < kend; k++) {
+        double q[NS], raw[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) q[j] = bw[k * NS + j] * z[j];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          double aux;
+          if (BANDED) {
+            aux = a[i * NS + i] * q[i];
+            if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
+          } else {
+            aux = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
+          }
+          raw[i] = aux;
+        }
+        double s = raw[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) s += raw[i];
+        int e;
+        const double r = pow2_scale(s, e);
+        double *bp = beta_ws + (mybase + myT - 2 - (w0 + k)) * NS;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          z[i] = raw[i] * r;
+          bp[i] = z[i];
+        }
+      }
+    }
+  }
+  if (chain && warp == 0) {
+    double s = z[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) s += z[i];
+    sphi[lane] = z[NS - 1] / s;                                                      // alpha^_{T-1}(N-1)
+    slp[lane] = msum + 0.6931471805599453 * (double)esum + log(z[NS - 1]);          // calc_probability T-FS:1546-1549
   }
   __syncthreads();
   // ---------------- phase 2: one warp per utterance, lanes over frames ----------------

@@ -742,13 +742,14 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     t_begin(ctx, "fwdbwd");
     {
       const int blocks = (U + kFbUtts - 1) / kFbUtts;
+      const size_t fsm = fb_smem_bytes(N);
       if (ctx->banded) {
-        DISPATCH_N(N, (k_fb<NS, true><<<blocks, kFbThreads, 0, ctx->st>>>(
+        DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, true><<<blocks, kFbThreads, fsm, ctx->st>>>(
                           ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
                           ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       } else {
-        DISPATCH_N(N, (k_fb<NS, false><<<blocks, kFbThreads, 0, ctx->st>>>(
+        DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, false><<<blocks, kFbThreads, fsm, ctx->st>>>(
                           ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
                           ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
