@@ -109,6 +109,20 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
 double *hmmcu_stats_device(hmmcu_ctx *ctx, int64_t *n_doubles);
 int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats);
 
+/* Device-resident EM iteration.  The M-step of the trainer's main() (T-FS:326-352:
+ * updating_transition_probab, updating_mix_param, changing_zero_coef, calc_det, inv_matrix) applied on
+ * the device to the model set held by the context, from the statistics of the last hmmcu_estep
+ * (all-reduced in place by the caller when there are several ranks), together with the per-word
+ * stopping rule (T-FS:326-328, 358): model v is re-estimated iff it is still active and
+ * |old_v - sum_logp_v| / |old_v| > threshold (old starts at 1.0); otherwise it becomes inactive for
+ * good.  Nothing but 3V+1 doubles crosses PCIe per iteration.
+ *   hmmcu_em_reset : old_v = 1.0, every model active (call after hmmcu_set_models).
+ *   hmmcu_mstep    : sum_logp[V], n_utt[V], updated[V] out (each may be NULL).
+ *   hmmcu_get_models: downloads the current parameters (same layout as hmmcu_set_models; NULL = skip). */
+int hmmcu_em_reset(hmmcu_ctx *ctx);
+int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_utt, int32_t *updated);
+int hmmcu_get_models(hmmcu_ctx *ctx, double *A, double *c, double *mu, double *inv_var, double *det);
+
 /* ---------------------------------------------------------------- Viterbi ---------------- */
 /* The reference has NO Viterbi decoder; these follow its conventions (pi=[1,0..],
  * final-state termination, lowest predecessor index on a tie).
@@ -122,7 +136,7 @@ int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx);
 /* Device time in ms of the most recent call's kernels, by name (CUDA events on the context's
- * stream).  names: "emis", "fwdbwd", "accum", "score", "viterbi", "pack".  -1 if unknown.
+ * stream).  names: "emis", "fwdbwd", "accum", "mstep", "score", "viterbi", "pack".  -1 if unknown.
  * Two pseudo-names report state instead of time: "kappa" (accuracy-guard value) and "tc_active"
  * (1 if the last emission launch ran on tensor cores). */
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name);

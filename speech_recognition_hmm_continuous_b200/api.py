@@ -20,7 +20,7 @@ EXPORTS = [
     "hmmcu_create", "hmmcu_destroy", "hmmcu_last_error", "hmmcu_device_count", "hmmcu_stream", "hmmcu_synchronize",
     "hmmcu_host_alloc", "hmmcu_host_free", "hmmcu_set_option", "hmmcu_set_features", "hmmcu_set_features_device", "hmmcu_set_models",
     "hmmcu_emissions", "hmmcu_forward_scores", "hmmcu_rank", "hmmcu_stats_size", "hmmcu_estep", "hmmcu_stats_device",
-    "hmmcu_stats_download", "hmmcu_viterbi", "hmmcu_viterbi_scores", "hmmcu_launch_count", "hmmcu_last_kernel_ms",
+    "hmmcu_stats_download", "hmmcu_em_reset", "hmmcu_mstep", "hmmcu_get_models", "hmmcu_viterbi", "hmmcu_viterbi_scores", "hmmcu_launch_count", "hmmcu_last_kernel_ms",
     "hmmcu_enable_timing", "hmmh_model_alloc", "hmmh_model_free", "hmmh_read_features", "hmmh_write_features",
     "hmmh_read_model", "hmmh_write_model", "hmmh_init_model", "hmmh_mstep", "hmmh_upload_models", "hmmh_train",
     "hmmh_train_main", "hmmh_test_main",
@@ -81,6 +81,9 @@ def load():
     lib.hmmcu_rank.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, _ip, _ip]
     lib.hmmcu_estep.argtypes = [C.c_void_p, _ip, _dp, _dp]
     lib.hmmcu_stats_download.argtypes = [C.c_void_p, _dp]
+    lib.hmmcu_em_reset.argtypes = [C.c_void_p]
+    lib.hmmcu_mstep.argtypes = [C.c_void_p, C.c_double, _dp, _dp, _ip]
+    lib.hmmcu_get_models.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
     lib.hmmcu_viterbi.argtypes = [C.c_void_p, _ip, _dp, _ip]
     lib.hmmcu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.hmmcu_host_free.argtypes = [C.c_void_p]
@@ -255,6 +258,22 @@ class Context:
         stats = np.zeros((self.V, ss))
         self._ck(self.lib.hmmcu_stats_download(self.h, _d(stats)), "hmmcu_stats_download")
         return stats
+
+    def em_reset(self):
+        self._ck(self.lib.hmmcu_em_reset(self.h), "hmmcu_em_reset")
+
+    def mstep(self, threshold=1e-3):
+        """Device M-step + stopping rule on the model set held by the context -> (sum_logp, n_utt, updated)."""
+        lp, nu = np.zeros(self.V), np.zeros(self.V)
+        upd = np.zeros(self.V, dtype=np.int32)
+        self._ck(self.lib.hmmcu_mstep(self.h, float(threshold), _d(lp), _d(nu), upd.ctypes.data_as(_ip)), "hmmcu_mstep")
+        return lp, nu, upd
+
+    def get_models(self, D):
+        ms = ModelSet(np.zeros((self.V, self.N, self.N)), np.zeros((self.V, self.N, self.M)), np.zeros((self.V, self.N, self.M, D)),
+                      np.zeros((self.V, self.N, self.M, D)), np.zeros((self.V, self.N, self.M)))
+        self._ck(self.lib.hmmcu_get_models(self.h, _d(ms.A), _d(ms.c), _d(ms.mu), _d(ms.iv), _d(ms.det)), "hmmcu_get_models")
+        return ms
 
     def viterbi(self, utt2model):
         u2m = np.ascontiguousarray(utt2model, dtype=np.int32)

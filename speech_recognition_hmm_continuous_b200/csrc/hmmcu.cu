@@ -67,10 +67,12 @@ struct hmmcu_ctx {
   const double *d_x64 = nullptr;
   DevBuf x32, ctr, off_d, xabs_d;
   std::vector<int64_t> off;
-  std::vector<double> h_ctr;   // per-dimension centre (host copy)
-  std::vector<float> h_xabs;   // per-dimension max |x - ctr|
-  std::vector<double> h_ivmax, h_mumin, h_mumax;  // per-dimension model extremes (set_models)
   double kappa = 0.0;          // bound on the summed magnitude of the expanded quadratic's terms
+  bool kappa_stale = true;     // features or models changed since kappa was last read back
+  // device-resident EM control (hmmcu_em_reset / hmmcu_mstep)
+  DevBuf em_old, em_active, ctl_d, ext_d;
+  double *ctl_h = nullptr;     // pinned: [3V + 1] sum_logp, n_utt, updated, kappa
+  size_t ctl_cap = 0;
 
   // models
   int V = 0, N = 0, M = 0, G = 0, Dm = 0;
@@ -188,12 +190,13 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
-                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg};
+                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
+  if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -251,9 +254,8 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   ctx->off.assign(frame_off, frame_off + U + 1);
   ctx->u2m.clear();
   ctx->pack_dirty = true;  // the centre may move
+  ctx->kappa_stale = true;
   ctx->have_features = true;
-  ctx->h_ctr.assign(DP, 0.0);
-  ctx->h_xabs.assign(DP, 0.f);
   if (F == 0) return HMMCU_OK;
   CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
   CK(cudaMemcpyAsync(ctx->off_d.p, frame_off, sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
@@ -279,8 +281,6 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
     LAUNCH_CHECK();
   }
   t_end(ctx, "pack");
-  CK(cudaMemcpyAsync(ctx->h_ctr.data(), ctx->ctr.p, sizeof(double) * DP, cudaMemcpyDeviceToHost, ctx->st));
-  CK(cudaMemcpyAsync(ctx->h_xabs.data(), ctx->xabs_d.p, sizeof(float) * DP, cudaMemcpyDeviceToHost, ctx->st));
   // the caller's host buffer may be reused as soon as we return
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
@@ -312,30 +312,45 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
   CK(cudaMemcpyAsync(ctx->iv.p, inv_var, sizeof(double) * VG * D, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaMemcpyAsync(ctx->det.p, det, sizeof(double) * VG, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
-  {  // per-dimension extremes of the model set (host scan; feeds the accuracy guard of the tensor-core path)
-    ctx->h_ivmax.assign(D, 0.0);
-    ctx->h_mumin.assign(D, INFINITY);
-    ctx->h_mumax.assign(D, -INFINITY);
-    double *ivm = ctx->h_ivmax.data(), *mn = ctx->h_mumin.data(), *mx = ctx->h_mumax.data();
-    for (int64_t g = 0; g < VG; g++) {
-      const double *pi = inv_var + g * D, *pm = mu + g * D;
-      for (int d = 0; d < D; d++) {
-        ivm[d] = pi[d] > ivm[d] ? pi[d] : ivm[d];
-        mn[d] = pm[d] < mn[d] ? pm[d] : mn[d];
-        mx[d] = pm[d] > mx[d] ? pm[d] : mx[d];
-      }
-    }
-    ctx->banded = true;
-    for (int64_t k = 0; k < (int64_t)V * N * N && ctx->banded; k++) {
-      const int i = (int)((k / N) % N), j = (int)(k % N);
-      if ((j < i || j > i + 1) && A[k] != 0.0) ctx->banded = false;
-    }
+  ctx->banded = true;
+  for (int64_t k = 0; k < (int64_t)V * N * N && ctx->banded; k++) {
+    const int i = (int)((k / N) % N), j = (int)(k % N);
+    if ((j < i || j > i + 1) && A[k] != 0.0) ctx->banded = false;
   }
   if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
   ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = (int)G;
   ctx->Dm = D;
   ctx->have_models = true;
   ctx->pack_dirty = true;
+  ctx->kappa_stale = true;
+  return HMMCU_OK;
+}
+
+// model extremes -> ext_d, kappa -> kappa_out (device); no synchronisation
+static int launch_kappa(hmmcu_ctx *ctx, double *kappa_out) {
+  const int D = ctx->Dm, DP = round_up(D + 1, 4);
+  const int64_t VG = (int64_t)ctx->V * ctx->G;
+  CK(ctx->ext_d.ensure(sizeof(unsigned long long) * 2 * DP));
+  CK(cudaMemsetAsync(ctx->ext_d.p, 0, sizeof(unsigned long long) * 2 * DP, ctx->st));
+  const int ngrp = std::max(1, 256 / DP);
+  const int blocks = (int)std::min<int64_t>((VG + ngrp - 1) / ngrp, (int64_t)ctx->sm_count * 4);
+  k_model_extremes<<<blocks, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->ctr.as<double>(), VG, D, DP,
+                                               ctx->ext_d.as<unsigned long long>());
+  LAUNCH_CHECK();
+  k_kappa<<<1, 32, 0, ctx->st>>>(ctx->ext_d.as<unsigned long long>(), ctx->F > 0 ? ctx->xabs_d.as<unsigned int>() : nullptr, D, DP, kappa_out);
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
+static int ensure_ctl(hmmcu_ctx *ctx) {
+  const size_t n = 3 * (size_t)ctx->V + 1;
+  CK(ctx->ctl_d.ensure(sizeof(double) * n));
+  if (n > ctx->ctl_cap) {
+    if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
+    ctx->ctl_h = nullptr;
+    CK(cudaMallocHost((void **)&ctx->ctl_h, sizeof(double) * n));
+    ctx->ctl_cap = n;
+  }
   return HMMCU_OK;
 }
 
@@ -361,17 +376,15 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   ctx->tc_train.dirty = true;
   ctx->tc_dec.dirty = true;
   ctx->acc_dirty = true;
-  // kappa = sum_d 2 * max(iv_d) * r_d^2, r_d = largest centred |x| or |mu| in dimension d: an upper bound on
-  // sum_k |Xaug_k W_k|.  The 3xTF32 contraction carries ~1e-7 of that magnitude as absolute error.
-  double kappa = 0.0;
-  for (int d = 0; d < ctx->D; d++) {
-    const double c0 = ctx->h_ctr.empty() ? 0.0 : ctx->h_ctr[d];
-    double r = ctx->h_xabs.empty() ? 0.0 : (double)ctx->h_xabs[d];
-    r = std::max(r, std::max(fabs(ctx->h_mumax[d] - c0), fabs(ctx->h_mumin[d] - c0)));
-    const double t = 2.0 * ctx->h_ivmax[d] * r * r;
-    kappa += (t == t) ? t : INFINITY;
+  if (ctx->kappa_stale) {  // after set_features / set_models; hmmcu_mstep refreshes it with its own read-back
+    int rc = ensure_ctl(ctx);
+    if (rc) return rc;
+    if ((rc = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * ctx->V)) != HMMCU_OK) return rc;
+    CK(cudaMemcpyAsync(ctx->ctl_h + 3 * ctx->V, ctx->ctl_d.as<double>() + 3 * ctx->V, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->kappa = ctx->ctl_h[3 * ctx->V];
+    ctx->kappa_stale = false;
   }
-  ctx->kappa = kappa;
   return HMMCU_OK;
 }
 
@@ -801,6 +814,62 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
   if (logp_utt && U > 0) CK(cudaMemcpyAsync(logp_utt, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
   if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
   if (stats || logp_utt) CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+// ------------------------------------------------------------------------- device-resident EM ----
+int hmmcu_em_reset(hmmcu_ctx *ctx) {
+  if (!ctx || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "em_reset: set the models first");
+  CK(cudaSetDevice(ctx->dev));
+  const int V = ctx->V;
+  CK(ctx->em_old.ensure(sizeof(double) * V));
+  CK(ctx->em_active.ensure(sizeof(int) * V));
+  std::vector<double> one(V, 1.0);  // old_probab starts at 1.0, T-FS:228
+  std::vector<int> act(V, 1);
+  CK(cudaMemcpyAsync(ctx->em_old.p, one.data(), sizeof(double) * V, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->em_active.p, act.data(), sizeof(int) * V, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_utt, int32_t *updated) {
+  if (!ctx || !ctx->have_models || ctx->stats_n != hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm) * ctx->V || !ctx->em_old.p)
+    return fail(ctx, HMMCU_EINVAL, "mstep: needs hmmcu_em_reset and an E-step on the current model set");
+  CK(cudaSetDevice(ctx->dev));
+  const int V = ctx->V;
+  int rc = ensure_ctl(ctx);
+  if (rc) return rc;
+  t_begin(ctx, "mstep");
+  k_mstep<<<V, 256, 0, ctx->st>>>(ctx->stats.as<double>(), hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm), V, ctx->N, ctx->M, ctx->Dm, threshold,
+                                  1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->em_old.as<double>(), ctx->em_active.as<int>(), ctx->A.as<double>(),
+                                  ctx->c.as<double>(), ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                  ctx->ctl_d.as<double>());
+  LAUNCH_CHECK();
+  if ((rc = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc;
+  t_end(ctx, "mstep");
+  CK(cudaMemcpyAsync(ctx->ctl_h, ctx->ctl_d.p, sizeof(double) * (3 * (size_t)V + 1), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int v = 0; v < V; v++) {
+    if (sum_logp) sum_logp[v] = ctx->ctl_h[v];
+    if (n_utt) n_utt[v] = ctx->ctl_h[V + v];
+    if (updated) updated[v] = ctx->ctl_h[2 * V + v] != 0.0;
+  }
+  ctx->kappa = ctx->ctl_h[3 * V];
+  ctx->kappa_stale = false;
+  ctx->pack_dirty = true;
+  return HMMCU_OK;
+}
+
+int hmmcu_get_models(hmmcu_ctx *ctx, double *A, double *c, double *mu, double *inv_var, double *det) {
+  if (!ctx || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "get_models: no models");
+  CK(cudaSetDevice(ctx->dev));
+  const int64_t V = ctx->V, N = ctx->N, G = ctx->G, D = ctx->Dm;
+  if (A) CK(cudaMemcpyAsync(A, ctx->A.p, sizeof(double) * V * N * N, cudaMemcpyDeviceToHost, ctx->st));
+  if (c) CK(cudaMemcpyAsync(c, ctx->c.p, sizeof(double) * V * G, cudaMemcpyDeviceToHost, ctx->st));
+  if (mu) CK(cudaMemcpyAsync(mu, ctx->mu.p, sizeof(double) * V * G * D, cudaMemcpyDeviceToHost, ctx->st));
+  if (inv_var) CK(cudaMemcpyAsync(inv_var, ctx->iv.p, sizeof(double) * V * G * D, cudaMemcpyDeviceToHost, ctx->st));
+  if (det) CK(cudaMemcpyAsync(det, ctx->det.p, sizeof(double) * V * G, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }
 

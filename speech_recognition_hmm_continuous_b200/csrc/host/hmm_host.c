@@ -387,42 +387,53 @@ int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2mod
                int *iterations, int max_iter, hmmh_allreduce_fn allreduce, void *user) {
   if (!ctx || !models || V < 1 || (U > 0 && !utt2model)) return HMMCU_EINVAL;
   const int N = models[0].N, M = models[0].M, D = models[0].D;
-  const int64_t ss = hmmcu_stats_size(N, M, D);
-  const int64_t o_lp = ss - 2;
-  double *stats = (double *)malloc(sizeof(double) * ss * V);
-  double *old = (double *)malloc(sizeof(double) * V);
+  const size_t g = (size_t)N * M;
+  double *probab = (double *)malloc(sizeof(double) * V), *nutt = (double *)malloc(sizeof(double) * V);
+  int32_t *updated = (int32_t *)malloc(sizeof(int32_t) * V);
   char *active = (char *)malloc(V);
   int32_t *map = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
-  if (!stats || !old || !active || !map) return HMMCU_ENOMEM;
-  for (int v = 0; v < V; v++) { old[v] = 1.0; active[v] = 1; if (iterations) iterations[v] = 0; if (mean_logp) mean_logp[v] = 0.0; }
-  int rc = HMMCU_OK, n_active = V, it = 0;
-  while (n_active > 0 && (max_iter <= 0 || it < max_iter)) {
+  if (!probab || !nutt || !updated || !active || !map) return HMMCU_ENOMEM;
+  for (int v = 0; v < V; v++) { active[v] = 1; if (iterations) iterations[v] = 0; if (mean_logp) mean_logp[v] = 0.0; }
+  /* the model set goes up once; the E-step, the all-reduce and the M-step then stay on the device */
+  int rc = upload_models(ctx, models, V);
+  if (rc == HMMCU_OK) rc = hmmcu_em_reset(ctx);
+  int n_active = V, it = 0, remap = 1;
+  while (rc == HMMCU_OK && n_active > 0 && (max_iter <= 0 || it < max_iter)) {
     it++;
-    if ((rc = upload_models(ctx, models, V)) != HMMCU_OK) break;
-    for (int u = 0; u < U; u++) map[u] = active[utt2model[u]] ? utt2model[u] : -1;
+    if (remap) {
+      for (int u = 0; u < U; u++) map[u] = active[utt2model[u]] ? utt2model[u] : -1;
+      remap = 0;
+    }
     if ((rc = hmmcu_estep(ctx, map, NULL, NULL)) != HMMCU_OK) break;
     if (allreduce) {
       int64_t n = 0;
       double *dev = hmmcu_stats_device(ctx, &n);
       if ((rc = allreduce(user, dev, n, hmmcu_stream(ctx))) != HMMCU_OK) break;
     }
-    if ((rc = hmmcu_stats_download(ctx, stats)) != HMMCU_OK) break;
+    if ((rc = hmmcu_mstep(ctx, HM_THRESHOLD, probab, nutt, updated)) != HMMCU_OK) break;
     for (int v = 0; v < V; v++) {
       if (!active[v]) continue;
-      const double *st = stats + (size_t)v * ss;
-      const double probab = st[o_lp], n_utt = st[o_lp + 1];
-      const double variation = fabs((old[v] - probab) / old[v]);
       if (iterations) iterations[v] = it;
-      if (mean_logp) mean_logp[v] = probab / n_utt;
-      if (variation > HM_THRESHOLD) {
-        old[v] = probab;
-        hmmh_mstep(&models[v], st);
-      } else {
-        active[v] = 0;
-        n_active--;
-      }
+      if (mean_logp) mean_logp[v] = probab[v] / nutt[v];
+      if (!updated[v]) { active[v] = 0; n_active--; remap = 1; }
     }
   }
-  free(stats); free(old); free(active); free(map);
+  if (rc == HMMCU_OK) {  /* bring the trained parameters back into the caller's structs */
+    double *A = (double *)malloc(sizeof(double) * V * N * N), *c = (double *)malloc(sizeof(double) * V * g);
+    double *mu = (double *)malloc(sizeof(double) * V * g * D), *iv = (double *)malloc(sizeof(double) * V * g * D);
+    double *det = (double *)malloc(sizeof(double) * V * g);
+    if (!A || !c || !mu || !iv || !det) rc = HMMCU_ENOMEM;
+    else if ((rc = hmmcu_get_models(ctx, A, c, mu, iv, det)) == HMMCU_OK) {
+      for (int v = 0; v < V; v++) {
+        memcpy(models[v].A, A + (size_t)v * N * N, sizeof(double) * N * N);
+        memcpy(models[v].c, c + v * g, sizeof(double) * g);
+        memcpy(models[v].mu, mu + v * g * D, sizeof(double) * g * D);
+        memcpy(models[v].inv_var, iv + v * g * D, sizeof(double) * g * D);
+        memcpy(models[v].det, det + v * g, sizeof(double) * g);
+      }
+    }
+    free(A); free(c); free(mu); free(iv); free(det);
+  }
+  free(probab); free(nutt); free(updated); free(active); free(map);
   return rc;
 }

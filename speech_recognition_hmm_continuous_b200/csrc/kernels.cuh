@@ -752,4 +752,113 @@ __global__ void k_rank(const double *__restrict__ logp, int U, int V, double wei
   if (second) second[u] = sec;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// M-step on the device (updating_transition_probab T-FS:1862-1889, updating_mix_param T-FS:1911-1955,
+// changing_zero_coef T-FS:1338-1359, calc_det T-FS:1976-1991, inv_matrix T-FS:2012-2022) together with
+// the per-word stopping rule of the trainer's main() (T-FS:326-358): one CTA per model, everything in
+// double, the same operations in the same order as the host version hmmh_mstep().  Keeping it on the
+// device removes the statistics download and the model upload from every EM iteration.
+//   ctl[v] = sum_logp, ctl[V+v] = n_utt, ctl[2V+v] = 1 if model v was re-estimated, else 0.
+// Like the reference, det / inverse are recomputed for EVERY mixture of a re-estimated model, also
+// those of states with den_mix == 0 (whose stored inverse is thereby inverted again).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mstep(const double *__restrict__ stats, int64_t ss, int V, int N, int M, int D, double threshold, double floor_,
+        double *__restrict__ em_old, int *__restrict__ em_active, double *__restrict__ Aall, double *__restrict__ call,
+        double *__restrict__ muall, double *__restrict__ ivall, double *__restrict__ detall, double *__restrict__ ctl) {
+  __shared__ int s_upd;
+  const int v = blockIdx.x, tid = threadIdx.x, G = N * M;
+  const double *st = stats + (int64_t)v * ss;
+  if (tid == 0) {
+    const double probab = st[ss - 2], nutt = st[ss - 1];
+    ctl[v] = probab;
+    ctl[V + v] = nutt;
+    int u = 0;
+    if (em_active[v]) {
+      const double variation = fabs((em_old[v] - probab) / em_old[v]);
+      if (variation > threshold) { em_old[v] = probab; u = 1; }
+      else em_active[v] = 0;
+    }
+    ctl[2 * V + v] = (double)u;
+    s_upd = u;
+  }
+  __syncthreads();
+  if (!s_upd) return;
+  const double *num = st, *den = num + (int64_t)N * N, *denmix = den + N, *S0 = denmix + N;
+  const double *S1 = S0 + G, *S2 = S1 + (int64_t)G * D;
+  double *A = Aall + (int64_t)v * N * N, *c = call + (int64_t)v * G, *mu = muall + (int64_t)v * G * D;
+  double *iv = ivall + (int64_t)v * G * D, *det = detall + (int64_t)v * G;
+  for (int idx = tid; idx < N * N; idx += blockDim.x) {
+    const int i = idx / N;
+    if (den[i] != 0.0) A[idx] = num[idx] / den[i];
+  }
+  for (int idx = tid; idx < G * D; idx += blockDim.x) {
+    const int k = idx / D, i = k / M;
+    if (denmix[i] != 0.0) {
+      mu[idx] = S1[idx] / S0[k];
+      double var = S2[idx] / S0[k];
+      if (var < floor_) var = floor_;
+      iv[idx] = var;
+    }
+  }
+  for (int k = tid; k < G; k += blockDim.x) {
+    const int i = k / M;
+    if (denmix[i] != 0.0) c[k] = S0[k] / denmix[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {  // changing_zero_coef
+    double *w = c + i * M;
+    double s = 0.0;
+    for (int k = 0; k < M; k++) {
+      if (w[k] < floor_) w[k] = floor_;
+      s += w[k];
+    }
+    for (int k = 0; k < M; k++) w[k] /= s;
+  }
+  for (int k = tid; k < G; k += blockDim.x) {  // calc_det then inv_matrix
+    double *vv = iv + (int64_t)k * D;
+    double dt = 1.0;
+    for (int d = 0; d < D; d++) dt *= vv[d];
+    for (int d = 0; d < D; d++) vv[d] = 1.0 / vv[d];
+    det[k] = dt;
+  }
+}
+
+// Per-dimension extremes of the model set for the tensor-core accuracy guard: ext[d] = max iv_d,
+// ext[DP + d] = max |mu_d - ctr_d| as the bit patterns of non-negative doubles (ordered like integers);
+// NaN counts as +inf.  ext must be zeroed first.
+__global__ void k_model_extremes(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ ctr,
+                                 int64_t VG, int D, int DP, unsigned long long *__restrict__ ext) {
+  const int d = threadIdx.x % DP, grp = threadIdx.x / DP, ngrp = blockDim.x / DP;
+  if (d >= D || grp >= ngrp) return;
+  double ivm = 0.0, mum = 0.0;
+  const double c0 = ctr[d];
+  for (int64_t g = (int64_t)blockIdx.x * ngrp + grp; g < VG; g += (int64_t)gridDim.x * ngrp) {
+    double a = iv[g * D + d], b = fabs(mu[g * D + d] - c0);
+    if (!(a == a)) a = INFINITY;
+    if (!(b == b)) b = INFINITY;
+    ivm = fmax(ivm, a);
+    mum = fmax(mum, b);
+  }
+  atomicMax(ext + d, (unsigned long long)__double_as_longlong(ivm));
+  atomicMax(ext + DP + d, (unsigned long long)__double_as_longlong(mum));
+}
+
+// kappa = sum_d 2 max(iv_d) r_d^2, r_d = largest centred |x| or |mu| in dimension d: an upper bound on
+// sum_k |Xaug_k W_k|; the 3xTF32 contraction carries ~1e-7 of that magnitude as absolute error.
+__global__ void k_kappa(const unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs, int D, int DP,
+                        double *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double kappa = 0.0;
+  for (int d = 0; d < D; d++) {
+    const double ivm = __longlong_as_double((long long)ext[d]);
+    double r = __longlong_as_double((long long)ext[DP + d]);
+    if (xabs) r = fmax(r, (double)__uint_as_float(xabs[d]));
+    const double t = 2.0 * ivm * r * r;
+    kappa += (t == t) ? t : INFINITY;
+  }
+  *out = kappa;
+}
+
 }  // namespace hmmk

@@ -197,6 +197,33 @@ def test_short_and_single_frame_utterances(ctx):
     assert sc[0, 0] == -np.inf and sc[1, 0] == -np.inf
 
 
+def test_device_mstep_matches_host_mstep(ctx):
+    """hmmcu_mstep (M-step + stopping rule on the device) against hmmh_mstep, the host restatement that is
+    bit-exact with the compiled reference (tests/test_host_cpu.py): same parameters to rounding."""
+    ms, x, off, labels = _synth(3, 5, 3, 9, seed=77)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    ctx.em_reset()
+    want = ms.copy()
+    for it in range(2):
+        stats, _ = ctx.estep(labels)
+        lp, nu, upd = ctx.mstep()
+        api.mstep(want, stats)
+        got = ctx.get_models(ms.D)
+        assert upd.all() and (nu == 3).all()
+        assert np.allclose(lp, [api.split_stats(stats[v], 5, 3, ms.D)["sum_logp"] for v in range(3)], rtol=1e-15)
+        for name in ("A", "c", "mu", "iv", "det"):
+            assert np.allclose(getattr(got, name), getattr(want, name), rtol=1e-12, atol=0), (it, name)
+        want = got.copy()  # continue both from the same point
+    # a model whose log-probability no longer moves is frozen, and stays frozen
+    lp, nu, upd = ctx.mstep(threshold=1e9)
+    assert not upd.any()
+    frozen = ctx.get_models(ms.D)
+    ctx.estep(labels)
+    lp, nu, upd = ctx.mstep(threshold=-1.0)
+    assert not upd.any() and np.array_equal(ctx.get_models(ms.D).mu, frozen.mu)
+
+
 # ------------------------------------------------------------------------------- training ----
 def test_golden_synth_c1_training(ctx, golden_dir):
     """Whole EM loop on the GPU from the reference's own initial models; iteration counts equal, mean
