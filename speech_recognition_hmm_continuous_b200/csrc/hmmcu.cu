@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "fb_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "ws_kernels.cuh"
 
 using namespace hmmk;
 
@@ -93,9 +94,10 @@ struct hmmcu_ctx {
     DevBuf images, kc, s0, ns;
     int TN = 0, SCt = 0, nimg = 0;
     bool dirty = true;
-  } tc_train, tc_dec;
-  DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec;
-  int64_t n_tc_tiles_train = 0;
+  } tc_train, tc_dec, ws_train, ws_dec;
+  int use_ws = 1;  // warp-specialised pipelined emission kernel (0 = the single-buffered k_emis_tc)
+  DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec, ws_tiles_train;
+  int64_t n_tc_tiles_train = 0, n_ws_tiles_train = 0;
   // tensor-core accumulate kernel: W images per (model, block of 128 Gaussians) and its work units
   DevBuf acc_images, acc_kc, acc_units, acc_dbg;
   int debug_acc = 0;
@@ -190,7 +192,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
-                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d};
+                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
+                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -228,6 +231,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (!ctx || !key) return HMMCU_EINVAL;
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
+  if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -375,6 +379,8 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   ctx->pack_dirty = false;
   ctx->tc_train.dirty = true;
   ctx->tc_dec.dirty = true;
+  ctx->ws_train.dirty = true;
+  ctx->ws_dec.dirty = true;
   ctx->acc_dirty = true;
   if (ctx->kappa_stale) {  // after set_features / set_models; hmmcu_mstep refreshes it with its own read-back
     int rc = ensure_ctl(ctx);
@@ -448,6 +454,84 @@ static int ensure_tc_images(hmmcu_ctx *ctx, int mode) {
   LAUNCH_CHECK();
   t_end(ctx, "pack");
   ts.dirty = false;
+  return HMMCU_OK;
+}
+
+// ---- warp-specialised emission kernel: images and launch ----------------------------------------
+static bool ws_supported(const hmmcu_ctx *ctx) {
+  const int MPd = ws_pad_m(ctx->M);
+  if (!ctx->use_ws || MPd > kWsMaxTN) return false;
+  const int SCt = std::max(1, kWsMaxTN / MPd);
+  const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * MPd, 16);
+  return ws_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
+}
+
+static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
+  hmmcu_ctx::TcSet &ts = mode == 0 ? ctx->ws_train : ctx->ws_dec;
+  if (!ts.dirty) return HMMCU_OK;
+  const int N = ctx->N, M = ctx->M, V = ctx->V, MPd = ws_pad_m(M);
+  const int SCmax = std::max(1, kWsMaxTN / MPd);
+  std::vector<int32_t> s0, ns;
+  if (mode == 0) {
+    ts.SCt = std::min(SCmax, N);
+    for (int v = 0; v < V; v++)
+      for (int s = 0; s < N; s += ts.SCt) { s0.push_back(v * N + s); ns.push_back(std::min(ts.SCt, N - s)); }
+  } else {
+    const int S = V * N;
+    ts.SCt = std::min(SCmax, S);
+    for (int s = 0; s < S; s += ts.SCt) { s0.push_back(s); ns.push_back(std::min(ts.SCt, S - s)); }
+  }
+  const int TN = round_up(ts.SCt * MPd, 16);
+  const int KP = 2 * ctx->DP;
+  if (TN != ts.TN || (int)s0.size() != ts.nimg) {  // geometry changed: (re)upload the image table
+    ts.TN = TN;
+    ts.nimg = (int)s0.size();
+    CK(ts.images.ensure(ws_image_bytes(ts.TN, KP) * ts.nimg));
+    CK(ts.s0.ensure(sizeof(int32_t) * ts.nimg));
+    CK(ts.ns.ensure(sizeof(int32_t) * ts.nimg));
+    CK(cudaMemcpyAsync(ts.s0.p, s0.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ts.ns.p, ns.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // s0 / ns are stack vectors
+  }
+  t_begin(ctx, "pack");
+  k_pack_w_ws<<<ts.nimg, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), ctx->c.as<double>(),
+                                           ctx->ctr.as<double>(), M, MPd, ctx->D, ctx->DP, ts.TN, ts.s0.as<int32_t>(), ts.ns.as<int32_t>(),
+                                           ts.images.as<float>());
+  LAUNCH_CHECK();
+  t_end(ctx, "pack");
+  ts.dirty = false;
+  return HMMCU_OK;
+}
+
+// TRAIN: units = explicit list (nunits); decode: nunits = nimg * ntiles over nframes contiguous frames from fbase
+template <bool TRAIN>
+static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunits, int ntiles_dec, int nframes_dec, float *logb,
+                          int64_t fbase, int64_t ldb) {
+  ctx->last_tc = true;
+  if (nunits == 0) return HMMCU_OK;
+  if (nunits > 0x7fffffff) return fail(ctx, HMMCU_EINVAL, "emission units overflow");
+  hmmcu_ctx::TcSet &ts = TRAIN ? ctx->ws_train : ctx->ws_dec;
+  const size_t smem = ws_emis_smem_bytes(ts.TN, 2 * ctx->DP);
+  const int grid = (int)std::min<int64_t>(nunits, ctx->sm_count);
+  const int MPd = ws_pad_m(ctx->M);
+#define WS_LAUNCH(MPT)                                                                                                             \
+  do {                                                                                                                             \
+    CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+    k_emis_ws<TRAIN, MPT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,                    \
+                                                               ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),               \
+                                                               ts.images.as<float>(), ctx->N, MPd, ctx->DP, ts.TN, logb, fbase,    \
+                                                               ldb, ctx->V * ctx->N, ts.SCt);                                      \
+  } while (0)
+  switch (MPd) {
+    case 1: WS_LAUNCH(1); break;
+    case 2: WS_LAUNCH(2); break;
+    case 4: WS_LAUNCH(4); break;
+    case 8: WS_LAUNCH(8); break;
+    case 16: WS_LAUNCH(16); break;
+    default: WS_LAUNCH(0); break;
+  }
+#undef WS_LAUNCH
+  LAUNCH_CHECK();
   return HMMCU_OK;
 }
 
@@ -581,7 +665,14 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     if (u1 == u0) u1 = u0 + 1;
     const int64_t fb0 = ctx->off[u0], fb1 = ctx->off[u1];
     CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
-    if (tc_supported(ctx)) {
+    if (tc_supported(ctx) && ws_supported(ctx)) {
+      if ((rc = ensure_ws_images(ctx, 1)) != HMMCU_OK) return rc;
+      const int nfr = (int)(fb1 - fb0), ntl = (nfr + kTcRows - 1) / kTcRows;
+      t_begin(ctx, "emis");
+      rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+      if (rc) return rc;
+      t_end(ctx, "emis");
+    } else if (tc_supported(ctx)) {
       if ((rc = ensure_tc_images(ctx, 1)) != HMMCU_OK) return rc;
       std::vector<TcTile> tt;
       for (int64_t f = fb0; f < fb1; f += kTcRows) tt.push_back({(int32_t)(f - fb0), (int)std::min<int64_t>(kTcRows, fb1 - f), 0, 0, 0, 0});
@@ -680,6 +771,23 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
         for (int32_t r = r0; r < r1; r += kTcRows) tt.push_back({r, std::min<int32_t>(kTcRows, r1 - r), v * CT + ct, ct * SCt, v, 0});
     }
     ctx->n_tc_tiles_train = (int64_t)tt.size();
+    {  // the same tiles under the warp-specialised kernel's image geometry
+      std::vector<TcTile> wt;
+      const int SCw = std::min(std::max(1, kWsMaxTN / ws_pad_m(ctx->M)), ctx->N);
+      const int CTw = (ctx->N + SCw - 1) / SCw;
+      int32_t r0w = 0;
+      for (int v = 0; v < V; v++) {
+        int32_t nfr = 0;
+        for (int k = start[v]; k < start[v + 1]; k++) nfr += (int32_t)(ctx->off[utts[k] + 1] - ctx->off[utts[k]]);
+        for (int ct = 0; ct < CTw; ct++)
+          for (int32_t r = 0; r < nfr; r += kTcRows) wt.push_back({r0w + r, std::min<int32_t>(kTcRows, nfr - r), v * CTw + ct, ct * SCw, v, 0});
+        r0w += nfr;
+      }
+      ctx->n_ws_tiles_train = (int64_t)wt.size();
+      CK(ctx->ws_tiles_train.ensure(sizeof(TcTile) * std::max<size_t>(wt.size(), 1)));
+      CK(cudaMemcpyAsync(ctx->ws_tiles_train.p, wt.data(), sizeof(TcTile) * wt.size(), cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));
+    }
     {  // accumulate-kernel units, ordered (model, row block, tile)
       std::vector<TcTile> au;
       const int nRB = (ctx->G + 127) / 128;
@@ -740,7 +848,12 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     CK(ctx->beta_ws.ensure(sizeof(double) * F * N));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
     // 1. emissions + per-mixture posteriors
-    if (use_tc) {
+    if (use_tc && ws_supported(ctx)) {
+      if ((rc = ensure_ws_images(ctx, 0)) != HMMCU_OK) return rc;
+      if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
+      t_begin(ctx, "emis");
+      rc = launch_emis_ws<true>(ctx, ctx->ws_tiles_train.as<TcTile>(), ctx->n_ws_tiles_train, 0, 0, ctx->logb.as<float>(), 0, N);
+    } else if (use_tc) {
       if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
       if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
       t_begin(ctx, "emis");

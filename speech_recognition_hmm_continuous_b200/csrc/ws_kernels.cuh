@@ -1,0 +1,313 @@
+// ws_kernels.cuh -- warp-specialised, mbarrier-pipelined tcgen05 kernels for sm_100a.
+//
+// k_emis_ws: Gaussian-mixture emission log-likelihoods (calc_symbol_probab + calc_gaus, T-FS:1749-1841,
+// R-FS:860-947) as a dense contraction on the tensor pipe with the per-state log-sum-exp fused into
+// the epilogue.  One persistent CTA per SM, nine warps in three roles that only meet at mbarriers:
+//
+//   warps 4-7  LOADERS   read 128 raw frames (fp32, centred), form [x | x^2], split every value into
+//                        TF32 hi + lo and write the A operand straight into the UMMA shared-memory
+//                        layout of stage s; (re)load the W image when the unit's image changes
+//   warp  8    MMA       one thread issues 3*KP/8 tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) per
+//                        unit into TMEM accumulator stage a, commits to free the smem stage and to
+//                        publish the accumulator
+//   warps 0-3  EPILOGUE  tcgen05.ld the accumulator (one frame per thread), online log-sum-exp over
+//                        the M mixtures of each state, store log b
+//
+// Two shared-memory stages and two TMEM accumulator stages keep the tensor pipe busy while the next
+// frame tile is being expanded and the previous one reduced.  The additive constant kc[g] of every
+// Gaussian is added in the epilogue in FP32 (round to nearest): folding it into the contraction was
+// tried and rejected -- the tensor pipe's FP32 accumulation truncates, and a partial sum that starts
+// at |kc| ~ 150 loses ~5e-5 of log-likelihood per frame, systematically (posteriors then sum to 1 - 5e-5).
+// The epilogue forms log2(c_g N_g(x)) = fma(acc, log2 e, kc2[g]) with exactly the expression the
+// accumulate kernel uses, so that the posteriors it recomputes are consistent with log b.
+//
+// Units are (W image, 128-frame tile) pairs ordered image-major, each CTA takes a contiguous range:
+// training: explicit list (frames of one model gathered through frame_ids); decode: unit u = (u / ntiles,
+// u % ntiles) over the contiguous frames of the current utterance batch.
+//
+// Shared-memory operand layout (SWIZZLE_NONE, K-major, 16-byte chunks of 4 values), rows r, columns k:
+//   byte(r, k) = (r%8)*16 + (k%4)*4 + (k/4)*128 + (r/8)*P,   P = (KP/4)*128;   LBO = 128, SBO = P,
+//   K-step j starts at +256 j.   X stage = [hi: 16 P][lo: 16 P];  W image = [hi: (TN/8) P][lo: (TN/8) P].
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace hmmk {
+
+constexpr int kWsThreads = 288;   // 9 warps
+constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image
+
+// W image in global and shared memory: [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats]
+__host__ __device__ inline size_t ws_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 4) * 128 + (size_t)TN * 4; }
+__host__ __device__ inline size_t ws_stage_bytes(int KP) { return (size_t)2 * 16 * (KP / 4) * 128; }
+__host__ __device__ inline size_t ws_emis_smem_bytes(int TN, int KP) { return 2 * ws_stage_bytes(KP) + ws_image_bytes(TN, KP) + 1024 + 272; }
+
+// Mixtures per state as laid out in the W image: padded to a power of two (M <= 16) or to a multiple of
+// 16, so that state boundaries fall on the 16-column chunks the epilogue reads; pad mixtures have W = 0
+// and kc = -inf (density 0).
+__host__ __device__ inline int ws_pad_m(int M) {
+  if (M > 16) return (M + 15) / 16 * 16;
+  int p = 1;
+  while (p < M) p <<= 1;
+  return p;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// TF32 hi / lo split with round-to-nearest (ties away) done in two integer instructions per part; the
+// tensor core ignores the low 13 mantissa bits of its FP32 operands.  cvt.rna.tf32.f32 compiles to a
+// longer NaN-safe sequence on sm_100a; the values here are finite.
+__device__ __forceinline__ void split_tf32_fast(float v, float &hi, float &lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// W images for k_emis_ws: image i covers global states [img_state0[i], +img_nstates[i]), TN rows (whole
+// states; rows beyond are zero), followed by kc2[TN] = log2(e) (ln c - 0.5 (D ln 2pi + ln|det|) - 0.5 sum mu^2 iv),
+// -inf for a Gaussian with c == 0 or det == 0 (density 0 in the reference) and for the pad rows.
+__global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
+                            const double *__restrict__ c, const double *__restrict__ ctr, int M, int MP, int D, int DP, int TN,
+                            const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
+                            float *__restrict__ images) {
+  const int img = blockIdx.x;
+  const int KP = 2 * DP;
+  const uint32_t P = (uint32_t)(KP / 4) * 128;
+  const size_t img_floats = ws_image_bytes(TN, KP) / 4;
+  float *hi = images + (size_t)img * img_floats;
+  float *lo = hi + (size_t)(TN / 8) * (P / 4);
+  float *kc2 = lo + (size_t)(TN / 8) * (P / 4);
+  const int64_t s0g = img_state0[img];
+  const int nst = img_nstates[img];
+  // image row n = (state n / MP, mixture n % MP) -> Gaussian index, or -1 for a pad row
+  auto gauss_of = [&](int n) -> int64_t {
+    const int st = n / MP, m = n - st * MP;
+    return (st < nst && m < M) ? (s0g + st) * M + m : -1;
+  };
+  for (int idx = threadIdx.x; idx < TN * KP; idx += blockDim.x) {
+    const int n = idx / KP, k = idx - n * KP;
+    const int part = k / DP, d = k - part * DP;
+    const int64_t g = gauss_of(n);
+    float val = 0.f;
+    if (g >= 0 && d < D) {
+      const double m = mu[g * D + d] - ctr[d], w = iv[g * D + d];
+      val = (float)(part == 0 ? m * w : -0.5 * w);
+    }
+    float h, l;
+    split_tf32(val, h, l);
+    const size_t o = ((size_t)(n & 7) * 16 + (k & 3) * 4 + (size_t)(k >> 2) * 128 + (size_t)(n >> 3) * P) / 4;
+    hi[o] = h;
+    lo[o] = l;
+  }
+  for (int n = threadIdx.x; n < TN; n += blockDim.x) {
+    double k = -INFINITY;
+    const int64_t g = gauss_of(n);
+    if (g >= 0) {
+      const double dt = det[g], cc = c[g];
+      if (dt != 0.0 && cc > 0.0) {
+        double q = 0.0;
+        for (int d = 0; d < D; d++) {
+          const double m = mu[g * D + d] - ctr[d];
+          q += m * m * iv[g * D + d];
+        }
+        k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
+      }
+    }
+    kc2[n] = (float)k;
+  }
+}
+
+// units == nullptr: decode, unit u = (image u / ntiles_dec, frames [128 (u % ntiles_dec), ...) of the batch, nframes_dec in all)
+// MP: padded mixtures per state when <= 16 (1, 2, 4, 8, 16); 0 = a multiple of 16 given at run time (M)
+template <bool TRAIN, int MP>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nframes_dec, const int32_t *__restrict__ frame_ids,
+          const float *__restrict__ x32, const float *__restrict__ images, int N, int M, int DP, int TN, float *__restrict__ logb,
+          int64_t fbase, int64_t ldb, int S_total, int SCt) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int KP = 2 * DP, NSLAB = KP / 8;
+  const uint32_t P = (uint32_t)(KP / 4) * 128;
+  const uint32_t stage_bytes = 2 * 16 * P, w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
+  uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *Xs = sm;                        // [2 stages][hi | lo]
+  uint8_t *Ws = sm + 2 * stage_bytes;      // [hi | lo]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(Ws + w_bytes);
+  uint64_t *full = bars, *empty = bars + 2, *dfull = bars + 4, *dempty = bars + 6;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&full[s], 128);    // every loader thread arrives
+      mbar_init(&empty[s], 1);     // tcgen05.commit
+      mbar_init(&dfull[s], 1);     // tcgen05.commit
+      mbar_init(&dempty[s], 128);  // every epilogue thread arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem0 = *tmem_slot;
+
+  const int per = (nunits + gridDim.x - 1) / gridDim.x;
+  const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
+  auto get_unit = [&](int ui) -> TcTile {
+    if (TRAIN) return units[ui];
+    const int img = ui / ntiles_dec, t = ui - img * ntiles_dec;
+    return TcTile{t * kTcRows, min(kTcRows, nframes_dec - t * kTcRows), img, img * SCt, 0, 0};
+  };
+
+  if (warp >= 4 && warp < 8) {
+    // =================================== LOADERS ===================================
+    const int r = tid - 128;  // frame row of the tile
+    const uint32_t rbase = (uint32_t)(r & 7) * 16 + (uint32_t)(r >> 3) * P;
+    int cur_img = -1;
+    for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
+      const TcTile unit = get_unit(ui);
+      const int s = i & 1;
+      // this unit's frame, fetched before any waiting
+      int64_t f = -1;
+      if (r < unit.nrows) f = TRAIN ? (int64_t)frame_ids[unit.row0 + r] : fbase + unit.row0 + r;
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP);
+      if (unit.img != cur_img) {
+        // the tensor pipe may still be reading the old image: wait for the previous unit's MMAs
+        if (i >= 1) mbar_wait(&empty[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        const float4 *wsrc = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4));
+        float4 *wdst = reinterpret_cast<float4 *>(Ws);
+        for (int k = r; k < (int)(w_bytes / 16); k += 128) wdst[k] = __ldg(wsrc + k);
+        cur_img = unit.img;
+      }
+      mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);  // stage s is free (unit i-2 has been multiplied)
+      uint8_t *Xh = Xs + (size_t)s * stage_bytes, *Xl = Xh + 16 * P;
+      for (int q0 = 0; q0 < DP / 4; q0 += 5) {
+        float4 xv[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++)
+          xv[j] = (f >= 0 && q0 + j < DP / 4) ? __ldg(src + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          if (q0 + j < DP / 4) {
+            float4 h, l;
+            split_tf32_fast(xv[j].x, h.x, l.x); split_tf32_fast(xv[j].y, h.y, l.y); split_tf32_fast(xv[j].z, h.z, l.z); split_tf32_fast(xv[j].w, h.w, l.w);
+            uint32_t o = rbase + (uint32_t)(q0 + j) * 128;
+            *reinterpret_cast<float4 *>(Xh + o) = h;
+            *reinterpret_cast<float4 *>(Xl + o) = l;
+            float4 sq = make_float4(xv[j].x * xv[j].x, xv[j].y * xv[j].y, xv[j].z * xv[j].z, xv[j].w * xv[j].w);
+            split_tf32_fast(sq.x, h.x, l.x); split_tf32_fast(sq.y, h.y, l.y); split_tf32_fast(sq.z, h.z, l.z); split_tf32_fast(sq.w, h.w, l.w);
+            o += (uint32_t)(DP / 4) * 128;
+            *reinterpret_cast<float4 *>(Xh + o) = h;
+            *reinterpret_cast<float4 *>(Xl + o) = l;
+          }
+        }
+      }
+      fence_async_smem();  // my generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full[s]);
+    }
+  } else if (warp == 8) {
+    // =================================== MMA ISSUER ===================================
+    const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
+    for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&full[s], ph);          // operands landed
+      mbar_wait(&dempty[s], ph ^ 1);    // accumulator stage drained by the epilogue (unit i-2)
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t xh = smem_u32(Xs + (size_t)s * stage_bytes), xl = xh + 16 * P;
+        const uint32_t wh = smem_u32(Ws), wl = wh + (uint32_t)(TN / 8) * P;
+        const uint32_t d = tmem0 + (uint32_t)s * 256;
+        uint32_t acc = 0;
+        for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
+          const uint32_t a0 = (p == 1) ? xl : xh, b0 = (p == 2) ? wl : wh;
+          for (int j = 0; j < NSLAB; j++) {
+            tc_mma_tf32(d, make_smem_desc2(a0 + j * 256, 128, P), make_smem_desc2(b0 + j * 256, 128, P), idesc, acc);
+            acc = 1;
+          }
+        }
+        tc_commit(&empty[s]);   // smem stage (and, for the loaders' image switch, W) free when these MMAs retire
+        tc_commit(&dfull[s]);   // accumulator ready
+      }
+      __syncwarp();
+    }
+  } else {
+    // =================================== EPILOGUE ===================================
+    const int row = 32 * warp + lane;  // warps 0..3 <-> TMEM lanes 32w..32w+31
+    const uint32_t trow = (uint32_t)(32 * warp) << 16;
+    for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
+      const TcTile unit = get_unit(ui);
+      const int s = i & 1;
+      mbar_wait(&dfull[s], (i >> 1) & 1);
+      tc_fence_after();
+      const int st_lim = TRAIN ? N : S_total;
+      const int nst = max(0, min(SCt, st_lim - unit.state0));  // states present in this image
+      const int mp = MP ? MP : M;  // M here is the padded count
+      const int ncols = nst * mp;
+      const bool live = row < unit.nrows;
+      int64_t f = 0;
+      if (live) f = TRAIN ? (int64_t)frame_ids[unit.row0 + row] : fbase + unit.row0 + row;
+      float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
+      const uint32_t d = tmem0 + (uint32_t)s * 256 + trow;
+      // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
+      // shared-memory image may already belong to a later unit
+      const float4 *kc4 = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4);
+      float mx = kNegInf, sum = 0.f;  // running state (MP == 0 only)
+      int chunks = 0, st = 0;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        const float4 k0 = __ldg(kc4 + c0 / 4), k1 = __ldg(kc4 + c0 / 4 + 1), k2 = __ldg(kc4 + c0 / 4 + 2), k3 = __ldg(kc4 + c0 / 4 + 3);
+        const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+        uint32_t v[16];
+        tmem_ld16(d + c0, v);
+        float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
+#pragma unroll
+        for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kc[j]);
+        if (MP) {  // 16 / MP whole states in this chunk, each reduced independently
+#pragma unroll
+          for (int g = 0; g < 16 / (MP ? MP : 16); g++) {
+            float m = val[g * MP];
+#pragma unroll
+            for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
+            const float ms = (m > kNegInf) ? m : 0.f;
+            float sm_ = 0.f;
+#pragma unroll
+            for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
+            const float lb = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
+            if (live && st + g < nst) lrow[st + g] = lb;
+          }
+          st += 16 / (MP ? MP : 16);
+        } else {  // one state spans M/16 chunks: online log-sum-exp across chunks
+          float m = val[0];
+#pragma unroll
+          for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
+          const float mn = fmaxf(mx, m);
+          const float ms = (mn > kNegInf) ? mn : 0.f;
+          float sm_ = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
+          sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
+          mx = mn;
+          if (++chunks == mp / 16) {
+            const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
+            if (live) lrow[st] = lb;
+            st++; chunks = 0; mx = kNegInf; sum = 0.f;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&dempty[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem0, 512);
+}
+
+}  // namespace hmmk
