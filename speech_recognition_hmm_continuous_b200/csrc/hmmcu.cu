@@ -460,7 +460,7 @@ static int ensure_tc_images(hmmcu_ctx *ctx, int mode) {
 // ---- warp-specialised emission kernel: images and launch ----------------------------------------
 static bool ws_supported(const hmmcu_ctx *ctx) {
   const int MPd = ws_pad_m(ctx->M);
-  if (!ctx->use_ws || MPd > kWsMaxTN) return false;
+  if (!ctx->use_ws || MPd > kWsMaxTN || ctx->DP > 40) return false;
   const int SCt = std::max(1, kWsMaxTN / MPd);
   const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * MPd, 16);
   return ws_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
@@ -514,13 +514,18 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
   const size_t smem = ws_emis_smem_bytes(ts.TN, 2 * ctx->DP);
   const int grid = (int)std::min<int64_t>(nunits, ctx->sm_count);
   const int MPd = ws_pad_m(ctx->M);
+  if (ctx->debug_acc & 2) {
+    CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
+    CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
+  }
 #define WS_LAUNCH(MPT)                                                                                                             \
   do {                                                                                                                             \
     CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
     k_emis_ws<TRAIN, MPT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,                    \
                                                                ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),               \
                                                                ts.images.as<float>(), ctx->N, MPd, ctx->DP, ts.TN, logb, fbase,    \
-                                                               ldb, ctx->V * ctx->N, ts.SCt);                                      \
+                                                               ldb, ctx->V * ctx->N, ts.SCt,                                       \
+                                                               (ctx->debug_acc & 2) ? (long long *)ctx->acc_dbg.p : nullptr);      \
   } while (0)
   switch (MPd) {
     case 1: WS_LAUNCH(1); break;
@@ -889,7 +894,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       const size_t smem = tc_acc_smem_bytes(2 * DP);
       CK(cudaFuncSetAttribute(k_accum_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units, ctx->sm_count);
-      if (ctx->debug_acc) {
+      if (ctx->debug_acc & 1) {
         CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
         CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
       }
@@ -898,7 +903,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
                                                         ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
                                                         ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
                                                         ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2,
-                                                        ctx->debug_acc ? ctx->acc_dbg.as<float>() : nullptr);
+                                                        (ctx->debug_acc & 1) ? ctx->acc_dbg.as<float>() : nullptr);
         LAUNCH_CHECK();
       }
       const int64_t total = (int64_t)V * G * D;

@@ -70,6 +70,24 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp.  The MMA issue loops run under this predicate with warp-uniform operands
+// (TMEM base re-broadcast with __shfl_sync) so that ptxas keeps descriptors in uniform registers; under
+// `if (lane == 0)` it wrapped every tcgen05.mma in an ELECT / R2UR.BROADCAST waterfall loop (~120 cycles
+// per issue, measured with scripts/debug_ws_timeline.py).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t"
+      "}\n"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t *mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
@@ -242,18 +260,22 @@ k_emis_tc(const TcTile *__restrict__ tiles, int ntiles, const int32_t *__restric
       fence_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
-        uint32_t acc = 0;
-        for (int p = 0; p < 3; p++) {  // Ah*Bh, Al*Bh, Ah*Bl
-          const uint32_t a0 = (p == 1) ? a_lo : a_hi, b0 = (p == 2) ? b_lo : b_hi;
-          for (int j = 0; j < NSLAB; j++) {
-            tc_mma_tf32(tmem_d, make_smem_desc(a0 + j * aslab), make_smem_desc(b0 + j * bslab), idesc, acc);
-            acc = 1;
+        const uint32_t td = __shfl_sync(0xffffffffu, tmem_d, 0);
+        if (elect_one_sync()) {
+          const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
+          uint32_t acc = 0;
+          for (int p = 0; p < 3; p++) {  // Ah*Bh, Al*Bh, Ah*Bl
+            const uint32_t a0 = (p == 1) ? a_lo : a_hi, b0 = (p == 2) ? b_lo : b_hi;
+            for (int j = 0; j < NSLAB; j++) {
+              tc_mma_tf32(td, make_smem_desc(a0 + j * aslab), make_smem_desc(b0 + j * bslab), idesc, acc);
+              acc = 1;
+            }
           }
+          tc_commit(&mbar);
         }
-        tc_commit(&mbar);
+        __syncwarp();
       }
       mbar_wait(&mbar, parity);
       parity ^= 1;
@@ -390,6 +412,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -597,18 +627,23 @@ k_accum_tc(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
     tc_fence_before();
     __syncthreads();
     // ---- GEMM1: L[g][f] ----
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      const uint32_t xh = smem_u32(Xh), xl = smem_u32(Xl);
-      uint32_t accf = 0;
-      for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
-        const uint32_t a0 = tm_w + ((p == 1) ? KP : 0), b0 = (p == 2) ? xl : xh;
-        for (int j = 0; j < NSLAB; j++) {
-          tc_mma_tf32_ts(tm_d1, a0 + j * 8, make_smem_desc2(b0 + j * 256, 128, PX), idesc1, accf);
-          accf = 1;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
+      if (elect_one_sync()) {
+        const uint64_t xh = make_smem_desc2(smem_u32(Xh), 128, PX), xl = make_smem_desc2(smem_u32(Xl), 128, PX);
+        uint32_t accf = 0;
+        for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
+          const uint32_t a0 = tb + kAccTmW + ((p == 1) ? KP : 0);
+          const uint64_t b0 = (p == 2) ? xl : xh;
+          for (int j = 0; j < NSLAB; j++) {
+            tc_mma_tf32_ts(tb, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);  // +256 B per K-step
+            accf = 1;
+          }
         }
+        tc_commit(&mbar);
       }
-      tc_commit(&mbar);
+      __syncwarp();
     }
     mbar_wait(&mbar, parity);
     parity ^= 1;
@@ -643,18 +678,23 @@ k_accum_tc(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
     tc_fence_before();
     __syncthreads();
     // ---- GEMM2: S[g][k] += sum_f w[g][f] Xaug[f][k] ----
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      const uint32_t xh = smem_u32(XTh), xl = smem_u32(XTl);
-      uint32_t accf = since_flush > 0 ? 1u : 0u;
-      for (int p = 0; p < 3; p++) {  // wh*Xh, wl*Xh, wh*Xl
-        const uint32_t a0 = (p == 1) ? tm_wl : tm_d1, b0 = (p == 2) ? xl : xh;
-        for (int j = 0; j < 16; j++) {
-          tc_mma_tf32_ts(tm_d2, a0 + j * 8, make_smem_desc2(b0 + j * 256, 128, 4096), idesc2, accf);
-          accf = 1;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
+      if (elect_one_sync()) {
+        const uint64_t xh = make_smem_desc2(smem_u32(XTh), 128, 4096), xl = make_smem_desc2(smem_u32(XTl), 128, 4096);
+        uint32_t accf = since_flush > 0 ? 1u : 0u;
+        for (int p = 0; p < 3; p++) {  // wh*Xh, wl*Xh, wh*Xl
+          const uint32_t a0 = tb + ((p == 1) ? 128 : 0);
+          const uint64_t b0 = (p == 2) ? xl : xh;
+          for (int j = 0; j < 16; j++) {
+            tc_mma_tf32_ts(tb + 256, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc2, accf);
+            accf = 1;
+          }
         }
+        tc_commit(&mbar);
       }
-      tc_commit(&mbar);
+      __syncwarp();
     }
     mbar_wait(&mbar, parity);
     parity ^= 1;

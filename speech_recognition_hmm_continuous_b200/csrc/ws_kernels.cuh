@@ -4,16 +4,23 @@
 // R-FS:860-947) as a dense contraction on the tensor pipe with the per-state log-sum-exp fused into
 // the epilogue.  One persistent CTA per SM, nine warps in three roles that only meet at mbarriers:
 //
-//   warps 4-7  LOADERS   read 128 raw frames (fp32, centred), form [x | x^2], split every value into
-//                        TF32 hi + lo and write the A operand straight into the UMMA shared-memory
-//                        layout of stage s; (re)load the W image when the unit's image changes
+//   warps 4-7  LOADERS   read 128 raw frames (fp32, centred; prefetched three levels ahead), form
+//                        [x | x^2], split every value into TF32 hi + lo and write the A operand with
+//                        tcgen05.st into TENSOR MEMORY stage a (one frame per lane); (re)load the W
+//                        image into shared memory when the unit's image changes
 //   warp  8    MMA       one thread issues 3*KP/8 tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) per
-//                        unit into TMEM accumulator stage a, commits to free the smem stage and to
-//                        publish the accumulator
-//   warps 0-3  EPILOGUE  tcgen05.ld the accumulator (one frame per thread), online log-sum-exp over
-//                        the M mixtures of each state, store log b
+//                        unit, A from TMEM, B = W from shared memory, into TMEM accumulator stage a,
+//                        commits to free the operand stage and to publish the accumulator
+//   warps 0-3  EPILOGUE  tcgen05.ld the accumulator (one frame per thread), log-sum-exp over the M
+//                        mixtures of each state, store log b
 //
-// Two shared-memory stages and two TMEM accumulator stages keep the tensor pipe busy while the next
+// Why the frame operand lives in TMEM: with both operands in shared memory a K = 8 TF32 MMA of
+// 128 x 80 reads (128 + 80) x 32 B = 6.6 KB for 40 cycles of math -- more than the 128 B/cycle the
+// shared memory delivers; measured 120 cycles per MMA (scripts/debug_ws_timeline.py).  From TMEM the
+// A operand costs no shared-memory bandwidth, the loaders need no generic->async proxy fence for it,
+// and 160 KB of shared memory are freed.
+//
+// Two operand stages and two accumulator stages in TMEM keep the tensor pipe busy while the next
 // frame tile is being expanded and the previous one reduced.  The additive constant kc[g] of every
 // Gaussian is added in the epilogue in FP32 (round to nearest): folding it into the contraction was
 // tried and rejected -- the tensor pipe's FP32 accumulation truncates, and a partial sum that starts
@@ -25,9 +32,11 @@
 // training: explicit list (frames of one model gathered through frame_ids); decode: unit u = (u / ntiles,
 // u % ntiles) over the contiguous frames of the current utterance batch.
 //
-// Shared-memory operand layout (SWIZZLE_NONE, K-major, 16-byte chunks of 4 values), rows r, columns k:
-//   byte(r, k) = (r%8)*16 + (k%4)*4 + (k/4)*128 + (r/8)*P,   P = (KP/4)*128;   LBO = 128, SBO = P,
-//   K-step j starts at +256 j.   X stage = [hi: 16 P][lo: 16 P];  W image = [hi: (TN/8) P][lo: (TN/8) P].
+// W image in shared memory (SWIZZLE_NONE, K-major, 16-byte chunks of 4 values), rows g, columns k:
+//   byte(g, k) = (g%8)*16 + (k%4)*4 + (k/4)*128 + (g/8)*P,   P = (KP/4)*128;   LBO = 128, SBO = P,
+//   K-step j starts at +256 j;  image = [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats].
+// TMEM columns: operand stage a at 160 a: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)] (KP <= 80);
+//               accumulator stage a at 320 + 96 a (TN <= 96).
 #pragma once
 #include "tc_kernels.cuh"
 
@@ -38,8 +47,7 @@ constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image
 
 // W image in global and shared memory: [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats]
 __host__ __device__ inline size_t ws_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 4) * 128 + (size_t)TN * 4; }
-__host__ __device__ inline size_t ws_stage_bytes(int KP) { return (size_t)2 * 16 * (KP / 4) * 128; }
-__host__ __device__ inline size_t ws_emis_smem_bytes(int TN, int KP) { return 2 * ws_stage_bytes(KP) + ws_image_bytes(TN, KP) + 1024 + 272; }
+__host__ __device__ inline size_t ws_emis_smem_bytes(int TN, int KP) { return ws_image_bytes(TN, KP) + 1024 + 272; }
 
 // Mixtures per state as laid out in the W image: padded to a power of two (M <= 16) or to a multiple of
 // 16, so that state boundaries fall on the 16-column chunks the epilogue reads; pad mixtures have W = 0
@@ -129,14 +137,17 @@ template <bool TRAIN, int MP>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nframes_dec, const int32_t *__restrict__ frame_ids,
           const float *__restrict__ x32, const float *__restrict__ images, int N, int M, int DP, int TN, float *__restrict__ logb,
-          int64_t fbase, int64_t ldb, int S_total, int SCt) {
+          int64_t fbase, int64_t ldb, int S_total, int SCt, long long *__restrict__ tdbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int KP = 2 * DP, NSLAB = KP / 8;
+  // optional timeline of CTA 0 (diagnostics): tdbg[unit][8] clock stamps
+  auto stamp = [&](int i, int slot) {
+    if (tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) tdbg[i * 8 + slot] = clock64();
+  };
   const uint32_t P = (uint32_t)(KP / 4) * 128;
-  const uint32_t stage_bytes = 2 * 16 * P, w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
+  const uint32_t w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
   uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *Xs = sm;                        // [2 stages][hi | lo]
-  uint8_t *Ws = sm + 2 * stage_bytes;      // [hi | lo]
+  uint8_t *Ws = sm;                        // [hi | lo]
   uint64_t *bars = reinterpret_cast<uint64_t *>(Ws + w_bytes);
   uint64_t *full = bars, *empty = bars + 2, *dfull = bars + 4, *dempty = bars + 6;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
@@ -169,14 +180,32 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     // =================================== LOADERS ===================================
     const int r = tid - 128;  // frame row of the tile
     const uint32_t rbase = (uint32_t)(r & 7) * 16 + (uint32_t)(r >> 3) * P;
+    constexpr int kQ = 10;  // float4 per row held in registers (DP <= 40)
+    const int nq = DP / 4;
+    // Global loads run three levels ahead of the expansion so that no latency is exposed per unit:
+    // unit descriptor (i+3) -> frame id (i+2) -> feature row (i+1), while unit i is split and stored.
+    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
+    auto frame_of = [&](const TcTile &u) -> int64_t {
+      if (r >= u.nrows) return -1;
+      return TRAIN ? (int64_t)__ldg(frame_ids + u.row0 + r) : fbase + u.row0 + r;
+    };
+    auto load_row = [&](int64_t f, float4 (&xv)[kQ]) {
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP);
+#pragma unroll
+      for (int j = 0; j < kQ; j++) xv[j] = (f >= 0 && j < nq) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    TcTile d0 = unit_at(u_begin), d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
+    int64_t f1 = frame_of(d1);
+    float4 xv[kQ];
+    load_row(frame_of(d0), xv);
     int cur_img = -1;
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
-      const TcTile unit = get_unit(ui);
+      const TcTile unit = d0;
       const int s = i & 1;
-      // this unit's frame, fetched before any waiting
-      int64_t f = -1;
-      if (r < unit.nrows) f = TRAIN ? (int64_t)frame_ids[unit.row0 + r] : fbase + unit.row0 + r;
-      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP);
+      float4 xn[kQ];
+      load_row(f1, xn);                      // rows of unit i+1
+      const int64_t f2 = frame_of(d2);       // frame id of unit i+2
+      const TcTile d3 = unit_at(ui + 3);     // descriptor of unit i+3
       if (unit.img != cur_img) {
         // the tensor pipe may still be reading the old image: wait for the previous unit's MMAs
         if (i >= 1) mbar_wait(&empty[(i - 1) & 1], ((i - 1) >> 1) & 1);
@@ -185,31 +214,43 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         for (int k = r; k < (int)(w_bytes / 16); k += 128) wdst[k] = __ldg(wsrc + k);
         cur_img = unit.img;
       }
-      mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);  // stage s is free (unit i-2 has been multiplied)
-      uint8_t *Xh = Xs + (size_t)s * stage_bytes, *Xl = Xh + 16 * P;
-      for (int q0 = 0; q0 < DP / 4; q0 += 5) {
-        float4 xv[5];
+      if (warp == 4) stamp(i, 0);
+      mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);  // operand stage s is free (unit i-2 has been multiplied)
+      if (warp == 4) stamp(i, 1);
+      tc_fence_after();
+      const uint32_t xa = tmem0 + (uint32_t)s * 160 + ((uint32_t)(32 * (warp & 3)) << 16);  // my lane, stage s
+      // 16 columns at a time: chunk c of [x | x^2] covers float4 4c .. 4c+3 of the doubled row
 #pragma unroll
-        for (int j = 0; j < 5; j++)
-          xv[j] = (f >= 0 && q0 + j < DP / 4) ? __ldg(src + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 2 * kQ / 4; c++) {
+        if (c * 16 < KP) {
+          uint32_t vh[16], vl[16];
 #pragma unroll
-        for (int j = 0; j < 5; j++) {
-          if (q0 + j < DP / 4) {
-            float4 h, l;
-            split_tf32_fast(xv[j].x, h.x, l.x); split_tf32_fast(xv[j].y, h.y, l.y); split_tf32_fast(xv[j].z, h.z, l.z); split_tf32_fast(xv[j].w, h.w, l.w);
-            uint32_t o = rbase + (uint32_t)(q0 + j) * 128;
-            *reinterpret_cast<float4 *>(Xh + o) = h;
-            *reinterpret_cast<float4 *>(Xl + o) = l;
-            float4 sq = make_float4(xv[j].x * xv[j].x, xv[j].y * xv[j].y, xv[j].z * xv[j].z, xv[j].w * xv[j].w);
-            split_tf32_fast(sq.x, h.x, l.x); split_tf32_fast(sq.y, h.y, l.y); split_tf32_fast(sq.z, h.z, l.z); split_tf32_fast(sq.w, h.w, l.w);
-            o += (uint32_t)(DP / 4) * 128;
-            *reinterpret_cast<float4 *>(Xh + o) = h;
-            *reinterpret_cast<float4 *>(Xl + o) = l;
+          for (int q = 0; q < 4; q++) {
+            const int j = c * 4 + q;  // float4 index in [x | x^2]; static after unrolling
+            float4 xx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < nq) xx = xv[j < kQ ? j : 0];
+            else if (j < 2 * nq) {
+              const float4 t = xv[(j - nq) < kQ && (j - nq) >= 0 ? (j - nq) : 0];
+              xx = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
+            }
+            float h, l;
+            split_tf32_fast(xx.x, h, l); vh[q * 4 + 0] = __float_as_uint(h); vl[q * 4 + 0] = __float_as_uint(l);
+            split_tf32_fast(xx.y, h, l); vh[q * 4 + 1] = __float_as_uint(h); vl[q * 4 + 1] = __float_as_uint(l);
+            split_tf32_fast(xx.z, h, l); vh[q * 4 + 2] = __float_as_uint(h); vl[q * 4 + 2] = __float_as_uint(l);
+            split_tf32_fast(xx.w, h, l); vh[q * 4 + 3] = __float_as_uint(h); vl[q * 4 + 3] = __float_as_uint(l);
           }
+          tmem_st16(xa + c * 16, vh);
+          tmem_st16(xa + 80 + c * 16, vl);
         }
       }
-      fence_async_smem();  // my generic-proxy writes -> visible to the tensor core (async proxy)
+      tmem_wait_st();
+      tc_fence_before();
+      fence_async_smem();  // the W image (generic-proxy writes) -> visible to the tensor core
       mbar_arrive(&full[s]);
+      if (warp == 4) stamp(i, 2);
+#pragma unroll
+      for (int j = 0; j < kQ; j++) xv[j] = xn[j];
+      d0 = d1; d1 = d2; d2 = d3; f1 = f2;
     }
   } else if (warp == 8) {
     // =================================== MMA ISSUER ===================================
@@ -218,24 +259,29 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       mbar_wait(&full[s], ph);          // operands landed
+      stamp(i, 3);
       mbar_wait(&dempty[s], ph ^ 1);    // accumulator stage drained by the epilogue (unit i-2)
+      stamp(i, 4);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t xh = smem_u32(Xs + (size_t)s * stage_bytes), xl = xh + 16 * P;
-        const uint32_t wh = smem_u32(Ws), wl = wh + (uint32_t)(TN / 8) * P;
-        const uint32_t d = tmem0 + (uint32_t)s * 256;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
+      if (elect_one_sync()) {
+        const uint32_t xh = tb + (uint32_t)s * 160, xl = xh + 80;
+        const uint64_t wh = make_smem_desc2(smem_u32(Ws), 128, P), wl = make_smem_desc2(smem_u32(Ws) + (uint32_t)(TN / 8) * P, 128, P);
+        const uint32_t d = tb + 320 + (uint32_t)s * 96;
         uint32_t acc = 0;
         for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
-          const uint32_t a0 = (p == 1) ? xl : xh, b0 = (p == 2) ? wl : wh;
+          const uint32_t a0 = (p == 1) ? xl : xh;
+          const uint64_t b0 = (p == 2) ? wl : wh;
           for (int j = 0; j < NSLAB; j++) {
-            tc_mma_tf32(d, make_smem_desc2(a0 + j * 256, 128, P), make_smem_desc2(b0 + j * 256, 128, P), idesc, acc);
+            tc_mma_tf32_ts(d, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc, acc);  // +256 B per K-step, in 16-byte units
             acc = 1;
           }
         }
-        tc_commit(&empty[s]);   // smem stage (and, for the loaders' image switch, W) free when these MMAs retire
+        tc_commit(&empty[s]);   // operand stage (and, for the loaders' image switch, W) free when these MMAs retire
         tc_commit(&dfull[s]);   // accumulator ready
       }
       __syncwarp();
+      stamp(i, 5);
     }
   } else {
     // =================================== EPILOGUE ===================================
@@ -245,6 +291,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       const TcTile unit = get_unit(ui);
       const int s = i & 1;
       mbar_wait(&dfull[s], (i >> 1) & 1);
+      if (warp == 0) stamp(i, 6);
       tc_fence_after();
       const int st_lim = TRAIN ? N : S_total;
       const int nst = max(0, min(SCt, st_lim - unit.state0));  // states present in this image
@@ -254,54 +301,62 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       int64_t f = 0;
       if (live) f = TRAIN ? (int64_t)frame_ids[unit.row0 + row] : fbase + unit.row0 + row;
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
-      const uint32_t d = tmem0 + (uint32_t)s * 256 + trow;
+      const uint32_t d = tmem0 + 320 + (uint32_t)s * 96 + trow;
       // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
       // shared-memory image may already belong to a later unit
       const float4 *kc4 = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4);
       float mx = kNegInf, sum = 0.f;  // running state (MP == 0 only)
       int chunks = 0, st = 0;
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        const float4 k0 = __ldg(kc4 + c0 / 4), k1 = __ldg(kc4 + c0 / 4 + 1), k2 = __ldg(kc4 + c0 / 4 + 2), k3 = __ldg(kc4 + c0 / 4 + 3);
-        const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
-        uint32_t v[16];
-        tmem_ld16(d + c0, v);
-        float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
+      constexpr int kMaxCh = kWsMaxTN / 16;
+      uint32_t v[kMaxCh][16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kc[j]);
-        if (MP) {  // 16 / MP whole states in this chunk, each reduced independently
+      for (int c = 0; c < kMaxCh; c++)  // every accumulator column of my frame in flight at once
+        if (c * 16 < ncols) tmem_ld16_nowait(d + c * 16, v[c]);
+      tmem_wait_ld();
 #pragma unroll
-          for (int g = 0; g < 16 / (MP ? MP : 16); g++) {
-            float m = val[g * MP];
+      for (int c = 0; c < kMaxCh; c++) {
+        if (c * 16 < ncols) {
+          const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+          const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+          float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
 #pragma unroll
-            for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
-            const float ms = (m > kNegInf) ? m : 0.f;
+          for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kc[j]);
+          if (MP) {  // 16 / MP whole states in this chunk, each reduced independently
+#pragma unroll
+            for (int g = 0; g < 16 / (MP ? MP : 16); g++) {
+              float m = val[g * MP];
+#pragma unroll
+              for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
+              const float ms = (m > kNegInf) ? m : 0.f;
+              float sm_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
+              const float lb = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
+              if (live && st + g < nst) lrow[st + g] = lb;
+            }
+            st += 16 / (MP ? MP : 16);
+          } else {  // one state spans M/16 chunks: online log-sum-exp across chunks
+            float m = val[0];
+#pragma unroll
+            for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
+            const float mn = fmaxf(mx, m);
+            const float ms = (mn > kNegInf) ? mn : 0.f;
             float sm_ = 0.f;
 #pragma unroll
-            for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
-            const float lb = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
-            if (live && st + g < nst) lrow[st + g] = lb;
-          }
-          st += 16 / (MP ? MP : 16);
-        } else {  // one state spans M/16 chunks: online log-sum-exp across chunks
-          float m = val[0];
-#pragma unroll
-          for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
-          const float mn = fmaxf(mx, m);
-          const float ms = (mn > kNegInf) ? mn : 0.f;
-          float sm_ = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
-          sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
-          mx = mn;
-          if (++chunks == mp / 16) {
-            const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
-            if (live) lrow[st] = lb;
-            st++; chunks = 0; mx = kNegInf; sum = 0.f;
+            for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
+            sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
+            mx = mn;
+            if (++chunks == mp / 16) {
+              const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
+              if (live) lrow[st] = lb;
+              st++; chunks = 0; mx = kNegInf; sum = 0.f;
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&dempty[s]);
+      if (warp == 0) stamp(i, 7);
     }
   }
   tc_fence_before();
