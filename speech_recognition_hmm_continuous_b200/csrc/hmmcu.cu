@@ -99,7 +99,9 @@ struct hmmcu_ctx {
   DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec, ws_tiles_train;
   int64_t n_tc_tiles_train = 0, n_ws_tiles_train = 0;
   // tensor-core accumulate kernel: W images per (model, block of 128 Gaussians) and its work units
-  DevBuf acc_images, acc_kc, acc_units, acc_dbg;
+  DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64;
+  int64_t n_acc_units64 = 0;
+  int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
   int debug_acc = 0;
   bool acc_dirty = true;
   int64_t n_acc_units = 0;
@@ -193,7 +195,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
-                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train};
+                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -232,6 +234,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
+  if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -808,6 +811,20 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
       CK(ctx->acc_units.ensure(sizeof(TcTile) * std::max<size_t>(au.size(), 1)));
       CK(cudaMemcpyAsync(ctx->acc_units.p, au.data(), sizeof(TcTile) * au.size(), cudaMemcpyHostToDevice, ctx->st));
       CK(cudaStreamSynchronize(ctx->st));
+      // the same units in sub-tiles of kAccSub frames for the warp-specialised kernel
+      std::vector<TcTile> a64;
+      r0 = 0;
+      for (int v = 0; v < V; v++) {
+        int32_t nfr = 0;
+        for (int k = start[v]; k < start[v + 1]; k++) nfr += (int32_t)(ctx->off[utts[k] + 1] - ctx->off[utts[k]]);
+        for (int rb = 0; rb < nRB; rb++)
+          for (int32_t r = 0; r < nfr; r += kAccSub) a64.push_back({r0 + r, std::min<int32_t>(kAccSub, nfr - r), v * nRB + rb, 0, v, rb});
+        r0 += nfr;
+      }
+      ctx->n_acc_units64 = (int64_t)a64.size();
+      CK(ctx->acc_units64.ensure(sizeof(TcTile) * std::max<size_t>(a64.size(), 1)));
+      CK(cudaMemcpyAsync(ctx->acc_units64.p, a64.data(), sizeof(TcTile) * a64.size(), cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaStreamSynchronize(ctx->st));
     }
     CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
     CK(ctx->tc_tiles_train.ensure(sizeof(TcTile) * std::max<size_t>(tt.size(), 1)));
@@ -890,7 +907,22 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     t_end(ctx, "fwdbwd");
     // 3. mixture accumulators
     t_begin(ctx, "accum");
-    if (use_tc) {
+    if (use_tc && ctx->use_ws_acc && DP <= 40 && ws_acc_smem_bytes(2 * DP) <= 227 * 1024) {
+      const size_t smem = ws_acc_smem_bytes(2 * DP);
+      CK(cudaFuncSetAttribute(k_accum_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::min<int64_t>(ctx->n_acc_units64, ctx->sm_count);
+      if (grid > 0) {
+        k_accum_ws<<<grid, kWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
+                                                        ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
+                                                        ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                        ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2);
+        LAUNCH_CHECK();
+      }
+      const int64_t total = (int64_t)V * G * D;
+      k_finalize_stats<<<(unsigned)((total + 255) / 256), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, V, G, D, off_S0, off_S1,
+                                                                            off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>());
+      LAUNCH_CHECK();
+    } else if (use_tc) {
       const size_t smem = tc_acc_smem_bytes(2 * DP);
       CK(cudaFuncSetAttribute(k_accum_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units, ctx->sm_count);

@@ -365,4 +365,341 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   if (warp == 8) tmem_dealloc(tmem0, 512);
 }
 
+
+// ================================================================================================
+// k_accum_ws: mixture accumulators (calc_mix_param, T-FS:1691-1727), warp-specialised and pipelined.
+// Same mathematics as k_accum_tc (tc_kernels.cuh): per sub-tile of 64 frames of one model and block of
+// 128 Gaussians
+//   GEMM1  L[g][f]  = sum_k W[g][k] Xaug[f][k]           A = W (TMEM, parked per image), B = X  (smem)
+//   w[g][f] = gamma_f(s(g)) exp(L + kc[g] - logb_f(s(g)))  epilogue, in place in TMEM (hi) + beside it (lo)
+//   GEMM2  S[g][k] += sum_f w[g][f] Xaug[f][k]           A = w (TMEM), B = XT (smem)
+// but the three activities run concurrently on different warps and meet only at mbarriers:
+//   warps 4-7  LOADERS   features three levels ahead in registers; build X (frames x columns) and XT
+//                        (columns x frames), both TF32 hi / lo, and the per-frame weight exponents cfs
+//   warp  8    MMA       issues GEMM1(i), then GEMM2(i-1): the tensor pipe works on the next sub-tile's
+//                        GEMM1 while the epilogue turns the previous L into weights
+//   warps 0-3  EPILOGUE  L -> w with tcgen05.ld / tcgen05.st; every kAccDrain sub-tiles move S from TMEM
+//                        (FP32, truncating accumulation) into FP32 registers (round to nearest); flush
+//                        them with double atomics when the CTA's (model, Gaussian block) changes; load
+//                        the next image's W into TMEM
+// Two shared-memory stages (X, XT, cfs) and two TMEM stages (L / w_hi, w_lo).
+// TMEM columns: [0,128) L / w_hi x2 | [128,256) w_lo x2 | [256, 256+KP2) S | [352, 352+2KP) W_hi, W_lo
+// Shared-memory layouts (SWIZZLE_NONE K-major, 16-byte chunks):
+//   X  : byte(f, k) = (f%8)*16 + (k%4)*4 + (k/4)*128 + (f/8)*PX     PX = (KP/4)*128   (8 frame groups)
+//   XT : byte(k, f) = (k%8)*16 + (f%4)*4 + (f/4)*128 + (k/8)*2048   (KP2/8 column groups)
+// ================================================================================================
+constexpr int kAccSub = 64;     // frames per sub-tile
+constexpr int kAccDrain = 8;    // sub-tiles accumulated in TMEM before S moves to registers
+
+__host__ __device__ inline size_t ws_acc_stage_bytes(int KP) { return (size_t)2 * 8 * (KP / 4) * 128 + (size_t)2 * (tc_kp2(KP) / 8) * 2048 + 64 * 8 * 4; }
+__host__ __device__ inline size_t ws_acc_smem_bytes(int KP) { return 2 * ws_acc_stage_bytes(KP) + 1024 + 256; }
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restrict__ frame_ids, const float *__restrict__ x32,
+           const float *__restrict__ images, const float *__restrict__ kcT, const float *__restrict__ logb,
+           const float *__restrict__ gamma, int N, int M, int G, int D, int DP, double *__restrict__ stats,
+           int64_t stats_stride, int64_t off_S0, int64_t off_S1, int64_t off_S2) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int KP = 2 * DP, KP2 = tc_kp2(KP), NSLAB = KP / 8, nq = DP / 4;
+  const uint32_t PX = (uint32_t)(KP / 4) * 128;
+  const uint32_t x_bytes = 8 * PX, xt_bytes = (uint32_t)(KP2 / 8) * 2048;
+  const uint32_t stage_bytes = 2 * x_bytes + 2 * xt_bytes + 64 * 8 * 4;
+  uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * stage_bytes);
+  uint64_t *x_full = bars, *x_free = bars + 2, *d1_full = bars + 4, *w_full = bars + 6, *s_full = bars + 8, *s_free = bars + 9,
+           *wimg_full = bars + 10;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&x_full[s], 128);
+      mbar_init(&x_free[s], 1);
+      mbar_init(&d1_full[s], 1);
+      mbar_init(&w_full[s], 128);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(wimg_full, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem0 = *tmem_slot;
+
+  const int per = (nunits + gridDim.x - 1) / gridDim.x;
+  const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
+  const int n_my = max(0, u_end - u_begin);
+  auto img_at = [&](int ui) -> int { return (ui >= u_begin && ui < u_end) ? __ldg(&units[ui].img) : -1; };
+
+  if (warp >= 4 && warp < 8) {
+    // =================================== LOADERS ===================================
+    const int t = tid - 128;
+    const int xr = t & 63, xq0 = (t >> 6) * ((nq + 1) / 2);           // X: row xr, float4 [xq0, xq1)
+    const int xq1 = min(nq, xq0 + (nq + 1) / 2);
+    const int fg = t >> 3, nl = t & 7;                                // XT: frames 4fg..4fg+3, columns nl + 8k
+    constexpr int kXQ = 5, kTK = 5;                                   // DP <= 40
+    struct Pre { float4 x[kXQ]; float xt[kTK][4]; float gm[8], lb[8]; };
+    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? units[ui] : TcTile{0, 0, -1, 0, 0, 0}; };
+    struct Fids { int fx; int ft[4]; };
+    auto fids_of = [&](const TcTile &u) -> Fids {
+      Fids f;
+      f.fx = (xr < u.nrows) ? __ldg(frame_ids + u.row0 + xr) : -1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) f.ft[j] = (4 * fg + j < u.nrows) ? __ldg(frame_ids + u.row0 + 4 * fg + j) : -1;
+      return f;
+    };
+    auto load_pre = [&](const Fids &f, Pre &p) {
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (int64_t)(f.fx < 0 ? 0 : f.fx) * DP);
+#pragma unroll
+      for (int j = 0; j < kXQ; j++) p.x[j] = (f.fx >= 0 && xq0 + j < xq1) ? __ldg(src + xq0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kTK; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          p.xt[k][j] = (f.ft[j] >= 0 && nl + 8 * k < DP) ? __ldg(x32 + (int64_t)f.ft[j] * DP + nl + 8 * k) : 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const bool ok = t < 64 && f.fx >= 0 && s < N;
+        p.gm[s] = ok ? __ldg(gamma + (int64_t)f.fx * N + s) : 0.f;
+        p.lb[s] = ok ? __ldg(logb + (int64_t)f.fx * N + s) : 0.f;
+      }
+    };
+    TcTile d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
+    Fids f1 = fids_of(d1);
+    Pre cur, nxt;
+    {
+      const TcTile d0 = unit_at(u_begin);
+      load_pre(fids_of(d0), cur);
+    }
+    for (int i = 0; i < n_my; i++) {
+      const int s = i & 1;
+      load_pre(f1, nxt);                               // operands of unit i+1
+      const Fids f2 = fids_of(d2);                     // frame ids of unit i+2
+      const TcTile d3 = unit_at(u_begin + i + 3);      // descriptor of unit i+3
+      mbar_wait(&x_free[s], ((i >> 1) & 1) ^ 1);       // stage s: GEMM2 of unit i-2 has retired
+      uint8_t *Xh = sm + (size_t)s * stage_bytes, *Xl = Xh + x_bytes, *XTh = Xl + x_bytes, *XTl = XTh + xt_bytes;
+      float *cfs = reinterpret_cast<float *>(XTl + xt_bytes);
+      {  // X
+        const uint32_t rbase = (uint32_t)(xr & 7) * 16 + (uint32_t)(xr >> 3) * PX;
+#pragma unroll
+        for (int j = 0; j < kXQ; j++) {
+          if (xq0 + j < xq1) {
+            const float4 xx = cur.x[j];
+            float4 h, l;
+            split_tf32_fast(xx.x, h.x, l.x); split_tf32_fast(xx.y, h.y, l.y); split_tf32_fast(xx.z, h.z, l.z); split_tf32_fast(xx.w, h.w, l.w);
+            uint32_t o = rbase + (uint32_t)(xq0 + j) * 128;
+            *reinterpret_cast<float4 *>(Xh + o) = h;
+            *reinterpret_cast<float4 *>(Xl + o) = l;
+            split_tf32_fast(xx.x * xx.x, h.x, l.x); split_tf32_fast(xx.y * xx.y, h.y, l.y);
+            split_tf32_fast(xx.z * xx.z, h.z, l.z); split_tf32_fast(xx.w * xx.w, h.w, l.w);
+            o += (uint32_t)nq * 128;
+            *reinterpret_cast<float4 *>(Xh + o) = h;
+            *reinterpret_cast<float4 *>(Xl + o) = l;
+          }
+        }
+      }
+      {  // XT: rows n (x) and n + DP (x^2), 16-byte chunk = frames 4fg..4fg+3
+#pragma unroll
+        for (int k = 0; k < kTK; k++) {
+          const int n = nl + 8 * k;
+          if (n < DP) {
+            float4 h, l;
+            split_tf32_fast(cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1], h.y, l.y);
+            split_tf32_fast(cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3], h.w, l.w);
+            uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+            *reinterpret_cast<float4 *>(XTh + o) = h;
+            *reinterpret_cast<float4 *>(XTl + o) = l;
+            split_tf32_fast(cur.xt[k][0] * cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1] * cur.xt[k][1], h.y, l.y);
+            split_tf32_fast(cur.xt[k][2] * cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3] * cur.xt[k][3], h.w, l.w);
+            const int n2 = n + DP;
+            o = (uint32_t)(n2 & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n2 >> 3) * 2048;
+            *reinterpret_cast<float4 *>(XTh + o) = h;
+            *reinterpret_cast<float4 *>(XTl + o) = l;
+          }
+        }
+        if (KP2 > KP && nl == 0) {  // pad rows of GEMM2's N
+          for (int n = KP; n < KP2; n++) {
+            const uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+            *reinterpret_cast<float4 *>(XTh + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(XTl + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      if (t < 64) {  // weight exponent of frame t per state: log2(gamma) - logb log2(e); -inf = no weight
+#pragma unroll
+        for (int st = 0; st < 8; st++) {
+          float cf = kNegInf;
+          if (st < N && cur.gm[st] > 0.f && cur.lb[st] > kNegInf) cf = __log2f(cur.gm[st]) - cur.lb[st] * 1.4426950408889634f;
+          cfs[t * 8 + st] = cf;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&x_full[s]);
+      cur = nxt;
+      d1 = d2; d2 = d3; f1 = f2;
+    }
+  } else if (warp == 8) {
+    // =================================== MMA ISSUER ===================================
+    const uint32_t idesc1 = make_idesc_tf32(128, kAccSub), idesc2 = make_idesc_tf32(128, KP2);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
+    int cnt = 0, ndrain = 0, nimg = 0, pending = -1;
+    bool need_s_free = false;
+    auto issue_g2 = [&](int j, bool last_j) {
+      const int sj = j & 1;
+      mbar_wait(&w_full[sj], (j >> 1) & 1);
+      if (need_s_free) { mbar_wait(s_free, (ndrain - 1) & 1); need_s_free = false; }
+      tc_fence_after();
+      cnt++;
+      const bool drain = last_j || cnt == kAccDrain;
+      if (elect_one_sync()) {
+        const uint8_t *XTh = sm + (size_t)sj * stage_bytes + 2 * x_bytes;
+        const uint64_t bh = make_smem_desc2(smem_u32(XTh), 128, 2048), bl = make_smem_desc2(smem_u32(XTh + xt_bytes), 128, 2048);
+        uint32_t accf = cnt > 1 ? 1u : 0u;
+        for (int p = 0; p < 3; p++) {  // wh*Xh, wl*Xh, wh*Xl
+          const uint32_t a0 = tb + (uint32_t)sj * 64 + ((p == 1) ? 128 : 0);
+          const uint64_t b0 = (p == 2) ? bl : bh;
+          for (int k = 0; k < kAccSub / 8; k++) {
+            tc_mma_tf32_ts(tb + 256, a0 + k * 8, b0 + (uint64_t)(k * 16), idesc2, accf);
+            accf = 1;
+          }
+        }
+        tc_commit(&x_free[sj]);
+        if (drain) tc_commit(s_full);
+      }
+      __syncwarp();
+      if (drain) { ndrain++; need_s_free = true; cnt = 0; }
+    };
+    for (int i = 0; i < n_my; i++) {
+      const int ui = u_begin + i, s = i & 1;
+      const int img = img_at(ui);
+      const bool first = (i == 0) || img != img_at(ui - 1);
+      const bool last = (i == n_my - 1) || img != img_at(ui + 1);
+      if (first) { mbar_wait(wimg_full, nimg & 1); nimg++; }
+      mbar_wait(&x_full[s], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint8_t *Xh = sm + (size_t)s * stage_bytes;
+        const uint64_t bh = make_smem_desc2(smem_u32(Xh), 128, PX), bl = make_smem_desc2(smem_u32(Xh + x_bytes), 128, PX);
+        uint32_t accf = 0;
+        for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
+          const uint32_t a0 = tb + kAccTmW + ((p == 1) ? KP : 0);
+          const uint64_t b0 = (p == 2) ? bl : bh;
+          for (int j = 0; j < NSLAB; j++) {
+            tc_mma_tf32_ts(tb + (uint32_t)s * 64, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);
+            accf = 1;
+          }
+        }
+        tc_commit(&d1_full[s]);
+      }
+      __syncwarp();
+      if (pending >= 0) { issue_g2(pending, false); pending = -1; }
+      if (last) issue_g2(i, true);
+      else pending = i;
+    }
+  } else {
+    // =================================== EPILOGUE ===================================
+    const int row = 32 * warp + lane;
+    const uint32_t trow = (uint32_t)(32 * warp) << 16;
+    constexpr int kMaxCol = 80;  // KP2 <= 80 (tc_acc_fits)
+    float acc[kMaxCol];
+#pragma unroll
+    for (int k = 0; k < kMaxCol; k++) acc[k] = 0.f;
+    int cnt = 0, ndrain = 0;
+    float kcr = kNegInf;
+    int st = 0, cur_v = 0, cur_rb = 0;
+    for (int i = 0; i < n_my; i++) {
+      const int ui = u_begin + i, s = i & 1;
+      const int img = img_at(ui);
+      const bool first = (i == 0) || img != img_at(ui - 1);
+      const bool last = (i == n_my - 1) || img != img_at(ui + 1);
+      if (first) {  // W (hi | lo) of this (model, Gaussian block) -> TMEM, one Gaussian per lane
+        const TcTile unit = units[ui];
+        cur_v = unit.v; cur_rb = unit.pad;
+        const float *im = images + (size_t)img * (tc_accT_image_bytes(KP) / 4) + (size_t)row * 2 * KP;
+        for (int ch = 0; ch < 2 * KP / 16; ch++) {
+          uint32_t r[16];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(im + ch * 16 + q * 4));
+            r[q * 4 + 0] = __float_as_uint(a.x); r[q * 4 + 1] = __float_as_uint(a.y); r[q * 4 + 2] = __float_as_uint(a.z); r[q * 4 + 3] = __float_as_uint(a.w);
+          }
+          tmem_st16(tmem0 + kAccTmW + trow + ch * 16, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(wimg_full);
+        const int g = cur_rb * 128 + row;
+        kcr = (g < G) ? __ldg(kcT + (size_t)img * 128 + row) : kNegInf;
+        st = min(g / M, 7);
+      }
+      mbar_wait(&d1_full[s], (i >> 1) & 1);
+      tc_fence_after();
+      const float *cfs = reinterpret_cast<const float *>(sm + (size_t)s * stage_bytes + 2 * x_bytes + 2 * xt_bytes);
+      {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; c++) tmem_ld16_nowait(tmem0 + (uint32_t)s * 64 + trow + c * 16, v[c]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t vl[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            const float y = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kcr + cfs[(c * 16 + j) * 8 + st]);
+            float w = ex2_approx(y);
+            if (!(y > -150.f)) w = 0.f;  // -inf, NaN (inf - inf) and underflow
+            float h, l;
+            split_tf32_fast(w, h, l);
+            v[c][j] = __float_as_uint(h);
+            vl[j] = __float_as_uint(l);
+          }
+          tmem_st16(tmem0 + (uint32_t)s * 64 + trow + c * 16, v[c]);
+          tmem_st16(tmem0 + 128 + (uint32_t)s * 64 + trow + c * 16, vl);
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(&w_full[s]);
+      cnt++;
+      if (last || cnt == kAccDrain) {  // S: TMEM (FP32, truncating) -> registers (round to nearest)
+        mbar_wait(s_full, ndrain & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < kMaxCol / 16; c++) {
+          if (c * 16 < KP2) {
+            uint32_t v[16];
+            tmem_ld16(tmem0 + 256 + trow + c * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[c * 16 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(s_free);
+        ndrain++; cnt = 0;
+        if (last) {  // the CTA leaves this (model, Gaussian block): registers -> statistics
+          const int g = cur_rb * 128 + row;
+          double *stp = stats + (int64_t)cur_v * stats_stride;
+#pragma unroll
+          for (int k = 0; k < kMaxCol; k++) {
+            if (k < KP2 && g < G) {
+              const double a = (double)acc[k];
+              if (k < D) atomicAdd(stp + off_S1 + (int64_t)g * D + k, a);
+              else if (k == D) atomicAdd(stp + off_S0 + g, a);
+              else if (k >= DP && k < DP + D) atomicAdd(stp + off_S2 + (int64_t)g * D + (k - DP), a);
+            }
+            acc[k] = 0.f;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem0, 512);
+}
+
 }  // namespace hmmk
