@@ -12,9 +12,9 @@ ctx = api.Context(0)
 ctx.set_features(x, off); ctx.set_models(ms); ctx.em_reset()
 for _ in range(3):
     ctx.estep(labels, download=False, want_logp=False)
-ctx.set_option("debug_acc", 2)
 mode = sys.argv[1] if len(sys.argv) > 1 else "train"
-if mode == "train":
+ctx.set_option("debug_acc", 4 if mode == "acc" else 2)
+if mode in ("train", "acc"):
     ctx.estep(labels, download=False, want_logp=False)
 else:
     ctx.forward_scores()
@@ -24,7 +24,9 @@ ctx.lib.hmmcu_debug_acc_read(ctx.h, buf.ctypes.data_as(C.c_void_p))
 t = buf.view(np.int64)[:64 * 8].reshape(64, 8)
 t0 = t[t > 0].min()
 names = ["ld:top", "ld:empty", "ld:arrive", "mma:full", "mma:dempty", "mma:issued", "epi:dfull", "epi:arrive"]
+if mode == "acc":
+    names = ["ld:top", "ld:free", "ld:arrive", "mma:xfull", "mma:g1", "mma:g2", "epi:d1full", "epi:wfull"]
 print("unit " + " ".join("%10s" % n for n in names))
-for i in range(20):
+for i in range(40):
     if t[i].max() == 0: break
     print("%4d " % i + " ".join("%10d" % (v - t0 if v > 0 else -1) for v in t[i]))

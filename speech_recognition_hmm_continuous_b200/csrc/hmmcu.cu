@@ -909,13 +909,18 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     t_begin(ctx, "accum");
     if (use_tc && ctx->use_ws_acc && DP <= 40 && ws_acc_smem_bytes(2 * DP) <= 227 * 1024) {
       const size_t smem = ws_acc_smem_bytes(2 * DP);
+      if (ctx->debug_acc & 4) {
+        CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
+        CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
+      }
       CK(cudaFuncSetAttribute(k_accum_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units64, ctx->sm_count);
       if (grid > 0) {
-        k_accum_ws<<<grid, kWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
+        k_accum_ws<<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
                                                         ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
                                                         ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
-                                                        ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2);
+                                                        ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2,
+                                                        (ctx->debug_acc & 4) ? (long long *)ctx->acc_dbg.p : nullptr);
         LAUNCH_CHECK();
       }
       const int64_t total = (int64_t)V * G * D;

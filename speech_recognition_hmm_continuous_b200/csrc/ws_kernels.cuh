@@ -65,12 +65,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// TF32 hi / lo split with round-to-nearest (ties away) done in two integer instructions per part; the
-// tensor core ignores the low 13 mantissa bits of its FP32 operands.  cvt.rna.tf32.f32 compiles to a
-// longer NaN-safe sequence on sm_100a; the values here are finite.
+// TF32 hi / lo split: hi = v rounded to nearest (ties away) to 11 significant bits with two integer
+// instructions, lo = v - hi exactly (FP32); the tensor core ignores the low 13 mantissa bits of lo, which
+// costs at most 2^-23 |v|, unbiased because lo has either sign.  (cvt.rna.tf32.f32 compiles to a longer
+// NaN-safe sequence on sm_100a, and a rounded lo doubles the load on the ALU pipe, which is what bounds
+// the loader and epilogue warps.)  The values here are finite.
 __device__ __forceinline__ void split_tf32_fast(float v, float &hi, float &lo) {
   hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
+  lo = v - hi;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// non-blocking poll (try_wait may suspend the thread for a long time when the phase is not complete)
+__device__ __forceinline__ bool mbar_try(uint64_t *mbar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(mbar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
@@ -373,33 +392,39 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 //   GEMM1  L[g][f]  = sum_k W[g][k] Xaug[f][k]           A = W (TMEM, parked per image), B = X  (smem)
 //   w[g][f] = gamma_f(s(g)) exp(L + kc[g] - logb_f(s(g)))  epilogue, in place in TMEM (hi) + beside it (lo)
 //   GEMM2  S[g][k] += sum_f w[g][f] Xaug[f][k]           A = w (TMEM), B = XT (smem)
-// but the three activities run concurrently on different warps and meet only at mbarriers:
-//   warps 4-7  LOADERS   features three levels ahead in registers; build X (frames x columns) and XT
-//                        (columns x frames), both TF32 hi / lo, and the per-frame weight exponents cfs
-//   warp  8    MMA       issues GEMM1(i), then GEMM2(i-1): the tensor pipe works on the next sub-tile's
-//                        GEMM1 while the epilogue turns the previous L into weights
-//   warps 0-3  EPILOGUE  L -> w with tcgen05.ld / tcgen05.st; every kAccDrain sub-tiles move S from TMEM
-//                        (FP32, truncating accumulation) into FP32 registers (round to nearest); flush
-//                        them with double atomics when the CTA's (model, Gaussian block) changes; load
-//                        the next image's W into TMEM
+// but the activities run concurrently on different warps and meet only at mbarriers (17 warps):
+//   warps  8-11 X LOADERS   features three levels ahead in registers; X (frames x columns), TF32 hi / lo,
+//                           and the per-frame weight exponents cfs
+//   warps 12-15 XT LOADERS  the same tile transposed (columns x frames), TF32 hi / lo
+//   warp  16    MMA         issues whichever of GEMM1(next unit) / GEMM2(oldest unit) has its inputs,
+//                           so neither the loaders nor the epilogue wait on the other's hand-off
+//   warps  0-7  EPILOGUE    L -> w with tcgen05.ld / tcgen05.st (warp w: TMEM lanes 32 (w%4).., frames
+//                           32 (w/4)..); every kAccDrain sub-tiles S moves from TMEM (FP32, truncating
+//                           accumulation) to FP32 registers (round to nearest, 40 columns per thread);
+//                           double atomics when the CTA's (model, Gaussian block) changes; loads the next
+//                           image's W into TMEM
 // Two shared-memory stages (X, XT, cfs) and two TMEM stages (L / w_hi, w_lo).
 // TMEM columns: [0,128) L / w_hi x2 | [128,256) w_lo x2 | [256, 256+KP2) S | [352, 352+2KP) W_hi, W_lo
 // Shared-memory layouts (SWIZZLE_NONE K-major, 16-byte chunks):
 //   X  : byte(f, k) = (f%8)*16 + (k%4)*4 + (k/4)*128 + (f/8)*PX     PX = (KP/4)*128   (8 frame groups)
 //   XT : byte(k, f) = (k%8)*16 + (f%4)*4 + (f/4)*128 + (k/8)*2048   (KP2/8 column groups)
 // ================================================================================================
-constexpr int kAccSub = 64;     // frames per sub-tile
-constexpr int kAccDrain = 8;    // sub-tiles accumulated in TMEM before S moves to registers
+constexpr int kAccSub = 64;        // frames per sub-tile
+constexpr int kAccDrain = 8;       // sub-tiles accumulated in TMEM before S moves to registers
+constexpr int kAccWsThreads = 544; // 17 warps
 
 __host__ __device__ inline size_t ws_acc_stage_bytes(int KP) { return (size_t)2 * 8 * (KP / 4) * 128 + (size_t)2 * (tc_kp2(KP) / 8) * 2048 + 64 * 8 * 4; }
 __host__ __device__ inline size_t ws_acc_smem_bytes(int KP) { return 2 * ws_acc_stage_bytes(KP) + 1024 + 256; }
 
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __launch_bounds__(kAccWsThreads, 1)
 k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restrict__ frame_ids, const float *__restrict__ x32,
            const float *__restrict__ images, const float *__restrict__ kcT, const float *__restrict__ logb,
            const float *__restrict__ gamma, int N, int M, int G, int D, int DP, double *__restrict__ stats,
-           int64_t stats_stride, int64_t off_S0, int64_t off_S1, int64_t off_S2) {
+           int64_t stats_stride, int64_t off_S0, int64_t off_S1, int64_t off_S2, long long *__restrict__ tdbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  auto stamp = [&](int i, int slot) {  // latest arrival over the warps of a role
+    if (tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) atomicMax((unsigned long long *)&tdbg[i * 8 + slot], (unsigned long long)clock64());
+  };
   const int KP = 2 * DP, KP2 = tc_kp2(KP), NSLAB = KP / 8, nq = DP / 4;
   const uint32_t PX = (uint32_t)(KP / 4) * 128;
   const uint32_t x_bytes = 8 * PX, xt_bytes = (uint32_t)(KP2 / 8) * 2048;
@@ -413,17 +438,17 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
 
   if (tid == 0) {
     for (int s = 0; s < 2; s++) {
-      mbar_init(&x_full[s], 128);
-      mbar_init(&x_free[s], 1);
-      mbar_init(&d1_full[s], 1);
-      mbar_init(&w_full[s], 128);
+      mbar_init(&x_full[s], 256);   // X and XT loaders
+      mbar_init(&x_free[s], 1);     // tcgen05.commit after GEMM2
+      mbar_init(&d1_full[s], 1);    // tcgen05.commit after GEMM1
+      mbar_init(&w_full[s], 256);   // epilogue threads
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(wimg_full, 128);
+    mbar_init(s_free, 256);
+    mbar_init(wimg_full, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -433,99 +458,56 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
   const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
   const int n_my = max(0, u_end - u_begin);
   auto img_at = [&](int ui) -> int { return (ui >= u_begin && ui < u_end) ? __ldg(&units[ui].img) : -1; };
+  auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? units[ui] : TcTile{0, 0, -1, 0, 0, 0}; };
 
-  if (warp >= 4 && warp < 8) {
-    // =================================== LOADERS ===================================
-    const int t = tid - 128;
-    const int xr = t & 63, xq0 = (t >> 6) * ((nq + 1) / 2);           // X: row xr, float4 [xq0, xq1)
+  if (warp >= 8 && warp < 12) {
+    // =================================== X LOADERS ===================================
+    const int t = tid - 256;
+    const int xr = t & 63, xq0 = (t >> 6) * ((nq + 1) / 2);  // row xr, float4 [xq0, xq1)
     const int xq1 = min(nq, xq0 + (nq + 1) / 2);
-    const int fg = t >> 3, nl = t & 7;                                // XT: frames 4fg..4fg+3, columns nl + 8k
-    constexpr int kXQ = 5, kTK = 5;                                   // DP <= 40
-    struct Pre { float4 x[kXQ]; float xt[kTK][4]; float gm[8], lb[8]; };
-    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? units[ui] : TcTile{0, 0, -1, 0, 0, 0}; };
-    struct Fids { int fx; int ft[4]; };
-    auto fids_of = [&](const TcTile &u) -> Fids {
-      Fids f;
-      f.fx = (xr < u.nrows) ? __ldg(frame_ids + u.row0 + xr) : -1;
+    constexpr int kXQ = 5;                                   // DP <= 40
+    struct Pre { float4 x[kXQ]; float gm[8], lb[8]; };
+    auto fid_of = [&](const TcTile &u) -> int { return (xr < u.nrows) ? __ldg(frame_ids + u.row0 + xr) : -1; };
+    auto load_pre = [&](int f, Pre &p) {
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (int64_t)(f < 0 ? 0 : f) * DP);
 #pragma unroll
-      for (int j = 0; j < 4; j++) f.ft[j] = (4 * fg + j < u.nrows) ? __ldg(frame_ids + u.row0 + 4 * fg + j) : -1;
-      return f;
-    };
-    auto load_pre = [&](const Fids &f, Pre &p) {
-      const float4 *src = reinterpret_cast<const float4 *>(x32 + (int64_t)(f.fx < 0 ? 0 : f.fx) * DP);
-#pragma unroll
-      for (int j = 0; j < kXQ; j++) p.x[j] = (f.fx >= 0 && xq0 + j < xq1) ? __ldg(src + xq0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < kTK; k++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          p.xt[k][j] = (f.ft[j] >= 0 && nl + 8 * k < DP) ? __ldg(x32 + (int64_t)f.ft[j] * DP + nl + 8 * k) : 0.f;
+      for (int j = 0; j < kXQ; j++) p.x[j] = (f >= 0 && xq0 + j < xq1) ? __ldg(src + xq0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int s = 0; s < 8; s++) {
-        const bool ok = t < 64 && f.fx >= 0 && s < N;
-        p.gm[s] = ok ? __ldg(gamma + (int64_t)f.fx * N + s) : 0.f;
-        p.lb[s] = ok ? __ldg(logb + (int64_t)f.fx * N + s) : 0.f;
+        const bool ok = t < 64 && f >= 0 && s < N;
+        p.gm[s] = ok ? __ldg(gamma + (int64_t)f * N + s) : 0.f;
+        p.lb[s] = ok ? __ldg(logb + (int64_t)f * N + s) : 0.f;
       }
     };
     TcTile d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
-    Fids f1 = fids_of(d1);
+    int f1 = fid_of(d1);
     Pre cur, nxt;
-    {
-      const TcTile d0 = unit_at(u_begin);
-      load_pre(fids_of(d0), cur);
-    }
+    load_pre(fid_of(unit_at(u_begin)), cur);
+    const uint32_t rbase = (uint32_t)(xr & 7) * 16 + (uint32_t)(xr >> 3) * PX;
     for (int i = 0; i < n_my; i++) {
       const int s = i & 1;
       load_pre(f1, nxt);                               // operands of unit i+1
-      const Fids f2 = fids_of(d2);                     // frame ids of unit i+2
+      const int f2 = fid_of(d2);                       // frame id of unit i+2
       const TcTile d3 = unit_at(u_begin + i + 3);      // descriptor of unit i+3
+      if (warp == 8) stamp(i, 0);
       mbar_wait(&x_free[s], ((i >> 1) & 1) ^ 1);       // stage s: GEMM2 of unit i-2 has retired
-      uint8_t *Xh = sm + (size_t)s * stage_bytes, *Xl = Xh + x_bytes, *XTh = Xl + x_bytes, *XTl = XTh + xt_bytes;
-      float *cfs = reinterpret_cast<float *>(XTl + xt_bytes);
-      {  // X
-        const uint32_t rbase = (uint32_t)(xr & 7) * 16 + (uint32_t)(xr >> 3) * PX;
+      if (warp == 8) stamp(i, 1);
+      const uint32_t Xh = smem_u32(sm) + (uint32_t)s * stage_bytes, Xl = Xh + x_bytes;
+      float *cfs = reinterpret_cast<float *>(sm + (size_t)s * stage_bytes + 2 * x_bytes + 2 * xt_bytes);
 #pragma unroll
-        for (int j = 0; j < kXQ; j++) {
-          if (xq0 + j < xq1) {
-            const float4 xx = cur.x[j];
-            float4 h, l;
-            split_tf32_fast(xx.x, h.x, l.x); split_tf32_fast(xx.y, h.y, l.y); split_tf32_fast(xx.z, h.z, l.z); split_tf32_fast(xx.w, h.w, l.w);
-            uint32_t o = rbase + (uint32_t)(xq0 + j) * 128;
-            *reinterpret_cast<float4 *>(Xh + o) = h;
-            *reinterpret_cast<float4 *>(Xl + o) = l;
-            split_tf32_fast(xx.x * xx.x, h.x, l.x); split_tf32_fast(xx.y * xx.y, h.y, l.y);
-            split_tf32_fast(xx.z * xx.z, h.z, l.z); split_tf32_fast(xx.w * xx.w, h.w, l.w);
-            o += (uint32_t)nq * 128;
-            *reinterpret_cast<float4 *>(Xh + o) = h;
-            *reinterpret_cast<float4 *>(Xl + o) = l;
-          }
-        }
-      }
-      {  // XT: rows n (x) and n + DP (x^2), 16-byte chunk = frames 4fg..4fg+3
-#pragma unroll
-        for (int k = 0; k < kTK; k++) {
-          const int n = nl + 8 * k;
-          if (n < DP) {
-            float4 h, l;
-            split_tf32_fast(cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1], h.y, l.y);
-            split_tf32_fast(cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3], h.w, l.w);
-            uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
-            *reinterpret_cast<float4 *>(XTh + o) = h;
-            *reinterpret_cast<float4 *>(XTl + o) = l;
-            split_tf32_fast(cur.xt[k][0] * cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1] * cur.xt[k][1], h.y, l.y);
-            split_tf32_fast(cur.xt[k][2] * cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3] * cur.xt[k][3], h.w, l.w);
-            const int n2 = n + DP;
-            o = (uint32_t)(n2 & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n2 >> 3) * 2048;
-            *reinterpret_cast<float4 *>(XTh + o) = h;
-            *reinterpret_cast<float4 *>(XTl + o) = l;
-          }
-        }
-        if (KP2 > KP && nl == 0) {  // pad rows of GEMM2's N
-          for (int n = KP; n < KP2; n++) {
-            const uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
-            *reinterpret_cast<float4 *>(XTh + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(XTl + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int j = 0; j < kXQ; j++) {
+        if (xq0 + j < xq1) {
+          const float4 xx = cur.x[j];
+          float4 h, l;
+          split_tf32_fast(xx.x, h.x, l.x); split_tf32_fast(xx.y, h.y, l.y); split_tf32_fast(xx.z, h.z, l.z); split_tf32_fast(xx.w, h.w, l.w);
+          uint32_t o = rbase + (uint32_t)(xq0 + j) * 128;
+          st_shared_v4(Xh + o, h);
+          st_shared_v4(Xl + o, l);
+          split_tf32_fast(xx.x * xx.x, h.x, l.x); split_tf32_fast(xx.y * xx.y, h.y, l.y);
+          split_tf32_fast(xx.z * xx.z, h.z, l.z); split_tf32_fast(xx.w * xx.w, h.w, l.w);
+          o += (uint32_t)nq * 128;
+          st_shared_v4(Xh + o, h);
+          st_shared_v4(Xl + o, l);
         }
       }
       if (t < 64) {  // weight exponent of frame t per state: log2(gamma) - logb log2(e); -inf = no weight
@@ -538,22 +520,106 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
       }
       fence_async_smem();
       mbar_arrive(&x_full[s]);
+      stamp(i, 2);
       cur = nxt;
       d1 = d2; d2 = d3; f1 = f2;
     }
-  } else if (warp == 8) {
+  } else if (warp >= 12 && warp < 16) {
+    // =================================== XT LOADERS ===================================
+    const int t = tid - 384;
+    const int fg = t >> 3, nl = t & 7;  // frames 4fg..4fg+3, columns nl + 8k
+    constexpr int kTK = 5;              // DP <= 40
+    struct Fids { int ft[4]; };
+    auto fids_of = [&](const TcTile &u) -> Fids {
+      Fids f;
+#pragma unroll
+      for (int j = 0; j < 4; j++) f.ft[j] = (4 * fg + j < u.nrows) ? __ldg(frame_ids + u.row0 + 4 * fg + j) : -1;
+      return f;
+    };
+    struct Pre { float xt[kTK][4]; };
+    auto load_pre = [&](const Fids &f, Pre &p) {
+#pragma unroll
+      for (int k = 0; k < kTK; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          p.xt[k][j] = (f.ft[j] >= 0 && nl + 8 * k < DP) ? __ldg(x32 + (int64_t)f.ft[j] * DP + nl + 8 * k) : 0.f;
+    };
+    TcTile d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
+    Fids f1 = fids_of(d1);
+    Pre cur, nxt;
+    load_pre(fids_of(unit_at(u_begin)), cur);
+    for (int i = 0; i < n_my; i++) {
+      const int s = i & 1;
+      load_pre(f1, nxt);
+      const Fids f2 = fids_of(d2);
+      const TcTile d3 = unit_at(u_begin + i + 3);
+      mbar_wait(&x_free[s], ((i >> 1) & 1) ^ 1);
+      const uint32_t XTh = smem_u32(sm) + (uint32_t)s * stage_bytes + 2 * x_bytes, XTl = XTh + xt_bytes;
+#pragma unroll
+      for (int k = 0; k < kTK; k++) {  // rows n (x) and n + DP (x^2), 16-byte chunk = frames 4fg..4fg+3
+        const int n = nl + 8 * k;
+        if (n < DP) {
+          float4 h, l;
+          split_tf32_fast(cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1], h.y, l.y);
+          split_tf32_fast(cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3], h.w, l.w);
+          uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+          st_shared_v4(XTh + o, h);
+          st_shared_v4(XTl + o, l);
+          split_tf32_fast(cur.xt[k][0] * cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1] * cur.xt[k][1], h.y, l.y);
+          split_tf32_fast(cur.xt[k][2] * cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3] * cur.xt[k][3], h.w, l.w);
+          const int n2 = n + DP;
+          o = (uint32_t)(n2 & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n2 >> 3) * 2048;
+          st_shared_v4(XTh + o, h);
+          st_shared_v4(XTl + o, l);
+        }
+      }
+      if (KP2 > KP && nl == 0) {  // pad rows of GEMM2's N
+        for (int n = KP; n < KP2; n++) {
+          const uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+          st_shared_v4(XTh + o, make_float4(0.f, 0.f, 0.f, 0.f));
+          st_shared_v4(XTl + o, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&x_full[s]);
+      stamp(i, 2);
+      cur = nxt;
+      d1 = d2; d2 = d3; f1 = f2;
+    }
+  } else if (warp == 16) {
     // =================================== MMA ISSUER ===================================
     const uint32_t idesc1 = make_idesc_tf32(128, kAccSub), idesc2 = make_idesc_tf32(128, KP2);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
-    int cnt = 0, ndrain = 0, nimg = 0, pending = -1;
+    // GEMM1(i) needs x_full(i) (and the image's W); GEMM2(j) needs w_full(j) (and S drained).  Whichever
+    // is ready goes first; GEMM1 may run at most one unit ahead of GEMM2 (two TMEM / smem stages).
+    int cnt = 0, ndrain = 0, nimg = 0, g1 = 0, g2 = 0;
     bool need_s_free = false;
-    auto issue_g2 = [&](int j, bool last_j) {
+    // image boundaries of the units at the two cursors, kept in registers (one load per advance)
+    int img_g1m = -1, img_g1 = img_at(u_begin), img_g2 = img_g1, img_g2p = img_at(u_begin + 1);
+    auto issue_g1 = [&](int i) {
+      const int s = i & 1;
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint8_t *Xh = sm + (size_t)s * stage_bytes;
+        const uint64_t bh = make_smem_desc2(smem_u32(Xh), 128, PX), bl = make_smem_desc2(smem_u32(Xh + x_bytes), 128, PX);
+        uint32_t accf = 0;
+        for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
+          const uint32_t a0 = tb + kAccTmW + ((p == 1) ? KP : 0);
+          const uint64_t b0 = (p == 2) ? bl : bh;
+          for (int j = 0; j < NSLAB; j++) {
+            tc_mma_tf32_ts(tb + (uint32_t)s * 64, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);
+            accf = 1;
+          }
+        }
+        tc_commit(&d1_full[s]);
+      }
+      __syncwarp();
+    };
+    auto issue_g2 = [&](int j) {
       const int sj = j & 1;
-      mbar_wait(&w_full[sj], (j >> 1) & 1);
-      if (need_s_free) { mbar_wait(s_free, (ndrain - 1) & 1); need_s_free = false; }
       tc_fence_after();
       cnt++;
-      const bool drain = last_j || cnt == kAccDrain;
+      const bool drain = img_g2p != img_g2 || cnt == kAccDrain;  // last unit of its image (or of this CTA), or S is due
       if (elect_one_sync()) {
         const uint8_t *XTh = sm + (size_t)sj * stage_bytes + 2 * x_bytes;
         const uint64_t bh = make_smem_desc2(smem_u32(XTh), 128, 2048), bl = make_smem_desc2(smem_u32(XTh + xt_bytes), 128, 2048);
@@ -572,38 +638,47 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
       __syncwarp();
       if (drain) { ndrain++; need_s_free = true; cnt = 0; }
     };
-    for (int i = 0; i < n_my; i++) {
-      const int ui = u_begin + i, s = i & 1;
-      const int img = img_at(ui);
-      const bool first = (i == 0) || img != img_at(ui - 1);
-      const bool last = (i == n_my - 1) || img != img_at(ui + 1);
-      if (first) { mbar_wait(wimg_full, nimg & 1); nimg++; }
-      mbar_wait(&x_full[s], (i >> 1) & 1);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        const uint8_t *Xh = sm + (size_t)s * stage_bytes;
-        const uint64_t bh = make_smem_desc2(smem_u32(Xh), 128, PX), bl = make_smem_desc2(smem_u32(Xh + x_bytes), 128, PX);
-        uint32_t accf = 0;
-        for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
-          const uint32_t a0 = tb + kAccTmW + ((p == 1) ? KP : 0);
-          const uint64_t b0 = (p == 2) ? bl : bh;
-          for (int j = 0; j < NSLAB; j++) {
-            tc_mma_tf32_ts(tb + (uint32_t)s * 64, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);
-            accf = 1;
-          }
+    while (g2 < n_my) {
+      bool did = false;
+      const bool first_g1 = img_g1 != img_g1m;
+      // a new image's first GEMM1 only after the old image's last GEMM2 has been issued
+      if (g1 < n_my && g1 - g2 <= 1 && (!first_g1 || g1 == g2)) {
+        bool ok = mbar_try(&x_full[g1 & 1], (g1 >> 1) & 1);
+        if (ok && first_g1) ok = mbar_try(wimg_full, nimg & 1);
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) {
+          if (first_g1) nimg++;
+          stamp(g1, 3);
+          issue_g1(g1);
+          stamp(g1, 4);
+          g1++;
+          img_g1m = img_g1;
+          img_g1 = img_at(u_begin + g1);
+          did = true;
         }
-        tc_commit(&d1_full[s]);
       }
-      __syncwarp();
-      if (pending >= 0) { issue_g2(pending, false); pending = -1; }
-      if (last) issue_g2(i, true);
-      else pending = i;
+      if (!did && g2 < g1) {
+        bool ok = mbar_try(&w_full[g2 & 1], (g2 >> 1) & 1);
+        if (ok && need_s_free) ok = mbar_try(s_free, (ndrain - 1) & 1);
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) {
+          need_s_free = false;
+          issue_g2(g2);
+          stamp(g2, 5);
+          g2++;
+          img_g2 = img_g2p;
+          img_g2p = img_at(u_begin + g2 + 1);
+        }
+      }
     }
   } else {
-    // =================================== EPILOGUE ===================================
-    const int row = 32 * warp + lane;
-    const uint32_t trow = (uint32_t)(32 * warp) << 16;
-    constexpr int kMaxCol = 80;  // KP2 <= 80 (tc_acc_fits)
+    // =================================== EPILOGUE (warps 0-7) ===================================
+    const int q = warp & 3, hb = warp >> 2;  // TMEM lane quarter; frame half (and column half of S)
+    const int row = 32 * q + lane;
+    const uint32_t trow = (uint32_t)(32 * q) << 16;
+    constexpr int kMaxCol = 40;  // KP2 <= 80 (tc_acc_fits): 5 groups of 8 columns per thread
+    const int nc8 = KP2 / 8;
+    const int c8_beg = hb ? (nc8 + 1) / 2 : 0, c8_end = hb ? nc8 : (nc8 + 1) / 2;
     float acc[kMaxCol];
 #pragma unroll
     for (int k = 0; k < kMaxCol; k++) acc[k] = 0.f;
@@ -615,16 +690,16 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
       const int img = img_at(ui);
       const bool first = (i == 0) || img != img_at(ui - 1);
       const bool last = (i == n_my - 1) || img != img_at(ui + 1);
-      if (first) {  // W (hi | lo) of this (model, Gaussian block) -> TMEM, one Gaussian per lane
+      if (first) {  // W (hi | lo) of this (model, Gaussian block) -> TMEM, one Gaussian per lane; halves split the columns
         const TcTile unit = units[ui];
         cur_v = unit.v; cur_rb = unit.pad;
         const float *im = images + (size_t)img * (tc_accT_image_bytes(KP) / 4) + (size_t)row * 2 * KP;
-        for (int ch = 0; ch < 2 * KP / 16; ch++) {
+        for (int ch = hb; ch < 2 * KP / 16; ch += 2) {
           uint32_t r[16];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(im + ch * 16 + q * 4));
-            r[q * 4 + 0] = __float_as_uint(a.x); r[q * 4 + 1] = __float_as_uint(a.y); r[q * 4 + 2] = __float_as_uint(a.z); r[q * 4 + 3] = __float_as_uint(a.w);
+          for (int qq = 0; qq < 4; qq++) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(im + ch * 16 + qq * 4));
+            r[qq * 4 + 0] = __float_as_uint(a.x); r[qq * 4 + 1] = __float_as_uint(a.y); r[qq * 4 + 2] = __float_as_uint(a.z); r[qq * 4 + 3] = __float_as_uint(a.w);
           }
           tmem_st16(tmem0 + kAccTmW + trow + ch * 16, r);
         }
@@ -636,44 +711,46 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
         st = min(g / M, 7);
       }
       mbar_wait(&d1_full[s], (i >> 1) & 1);
+      if (warp == 0) stamp(i, 6);
       tc_fence_after();
       const float *cfs = reinterpret_cast<const float *>(sm + (size_t)s * stage_bytes + 2 * x_bytes + 2 * xt_bytes);
-      {
-        uint32_t v[4][16];
+      {  // my 32 frames: accumulator columns [32 hb, 32 hb + 32)
+        uint32_t v[2][16];
 #pragma unroll
-        for (int c = 0; c < 4; c++) tmem_ld16_nowait(tmem0 + (uint32_t)s * 64 + trow + c * 16, v[c]);
+        for (int c = 0; c < 2; c++) tmem_ld16_nowait(tmem0 + (uint32_t)s * 64 + trow + (hb * 2 + c) * 16, v[c]);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < 2; c++) {
+          const int c0 = (hb * 2 + c) * 16;
           uint32_t vl[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            const float y = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kcr + cfs[(c * 16 + j) * 8 + st]);
-            float w = ex2_approx(y);
-            if (!(y > -150.f)) w = 0.f;  // -inf, NaN (inf - inf) and underflow
+            const float y = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kcr + cfs[(c0 + j) * 8 + st]);
+            const float w = ex2_approx(y);  // ex2(-inf) = +0 and underflow flushes to 0: no weight; y is never NaN
             float h, l;
             split_tf32_fast(w, h, l);
             v[c][j] = __float_as_uint(h);
             vl[j] = __float_as_uint(l);
           }
-          tmem_st16(tmem0 + (uint32_t)s * 64 + trow + c * 16, v[c]);
-          tmem_st16(tmem0 + 128 + (uint32_t)s * 64 + trow + c * 16, vl);
+          tmem_st16(tmem0 + (uint32_t)s * 64 + trow + c0, v[c]);
+          tmem_st16(tmem0 + 128 + (uint32_t)s * 64 + trow + c0, vl);
         }
-        tmem_wait_st();
       }
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&w_full[s]);
+      stamp(i, 7);
       cnt++;
       if (last || cnt == kAccDrain) {  // S: TMEM (FP32, truncating) -> registers (round to nearest)
         mbar_wait(s_full, ndrain & 1);
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < kMaxCol / 16; c++) {
-          if (c * 16 < KP2) {
-            uint32_t v[16];
-            tmem_ld16(tmem0 + 256 + trow + c * 16, v);
+        for (int c = 0; c < kMaxCol / 8; c++) {
+          if (c8_beg + c < c8_end) {
+            float v[8];
+            tmem_ld8(tmem0 + 256 + trow + (c8_beg + c) * 8, v);
 #pragma unroll
-            for (int j = 0; j < 16; j++) acc[c * 16 + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 8; j++) acc[c * 8 + j] += v[j];
           }
         }
         tc_fence_before();
@@ -683,14 +760,18 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
           const int g = cur_rb * 128 + row;
           double *stp = stats + (int64_t)cur_v * stats_stride;
 #pragma unroll
-          for (int k = 0; k < kMaxCol; k++) {
-            if (k < KP2 && g < G) {
-              const double a = (double)acc[k];
-              if (k < D) atomicAdd(stp + off_S1 + (int64_t)g * D + k, a);
-              else if (k == D) atomicAdd(stp + off_S0 + g, a);
-              else if (k >= DP && k < DP + D) atomicAdd(stp + off_S2 + (int64_t)g * D + (k - DP), a);
+          for (int c = 0; c < kMaxCol / 8; c++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int k = (c8_beg + c) * 8 + j;
+              if (c8_beg + c < c8_end && g < G) {
+                const double a = (double)acc[c * 8 + j];
+                if (k < D) atomicAdd(stp + off_S1 + (int64_t)g * D + k, a);
+                else if (k == D) atomicAdd(stp + off_S0 + g, a);
+                else if (k >= DP && k < DP + D) atomicAdd(stp + off_S2 + (int64_t)g * D + (k - DP), a);
+              }
+              acc[c * 8 + j] = 0.f;
             }
-            acc[k] = 0.f;
           }
         }
       }
@@ -699,7 +780,7 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem0, 512);
+  if (warp == 16) tmem_dealloc(tmem0, 512);
 }
 
 }  // namespace hmmk
