@@ -71,7 +71,7 @@ struct hmmcu_ctx {
   double kappa = 0.0;          // bound on the summed magnitude of the expanded quadratic's terms
   bool kappa_stale = true;     // features or models changed since kappa was last read back
   // device-resident EM control (hmmcu_em_reset / hmmcu_mstep)
-  DevBuf em_old, em_active, ctl_d, ext_d;
+  DevBuf em_old, em_active, ctl_d, ext_d, upd_d;
   double *ctl_h = nullptr;     // pinned: [3V + 1] sum_logp, n_utt, updated, kappa
   size_t ctl_cap = 0;
 
@@ -79,7 +79,8 @@ struct hmmcu_ctx {
   int V = 0, N = 0, M = 0, G = 0, Dm = 0;
   bool have_models = false, pack_dirty = true;
   bool banded = false;  // every A is upper-bidiagonal (the left-to-right DELTA=1 topology of T-FS:774-795)
-  DevBuf A, c, mu, iv, det, mu32, iv32, k32;
+  DevBuf A, c, mu, iv, det, mu32, iv32, k32, kc2;
+  bool kc_dirty = true, simt_dirty = true;
 
   // training map
   std::vector<int32_t> u2m;
@@ -190,11 +191,11 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->st);
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
-                    &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
+                    &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->kc2, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
-                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
+                    &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
@@ -337,14 +338,13 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
 static int launch_kappa(hmmcu_ctx *ctx, double *kappa_out) {
   const int D = ctx->Dm, DP = round_up(D + 1, 4);
   const int64_t VG = (int64_t)ctx->V * ctx->G;
-  CK(ctx->ext_d.ensure(sizeof(unsigned long long) * 2 * DP));
-  CK(cudaMemsetAsync(ctx->ext_d.p, 0, sizeof(unsigned long long) * 2 * DP, ctx->st));
+  CK(ctx->ext_d.ensure(sizeof(unsigned long long) * (2 * DP + 1)));  // extremes + the finished-block counter
+  CK(cudaMemsetAsync(ctx->ext_d.p, 0, sizeof(unsigned long long) * (2 * DP + 1), ctx->st));
   const int ngrp = std::max(1, 256 / DP);
   const int blocks = (int)std::min<int64_t>((VG + ngrp - 1) / ngrp, (int64_t)ctx->sm_count * 4);
   k_model_extremes<<<blocks, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->ctr.as<double>(), VG, D, DP,
-                                               ctx->ext_d.as<unsigned long long>());
-  LAUNCH_CHECK();
-  k_kappa<<<1, 32, 0, ctx->st>>>(ctx->ext_d.as<unsigned long long>(), ctx->F > 0 ? ctx->xabs_d.as<unsigned int>() : nullptr, D, DP, kappa_out);
+                                               ctx->ext_d.as<unsigned long long>(), ctx->F > 0 ? ctx->xabs_d.as<unsigned int>() : nullptr,
+                                               reinterpret_cast<unsigned int *>(ctx->ext_d.as<unsigned long long>() + 2 * DP), kappa_out);
   LAUNCH_CHECK();
   return HMMCU_OK;
 }
@@ -365,21 +365,11 @@ static int ensure_packed(hmmcu_ctx *ctx) {
   if (!ctx->have_features || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "features and models must both be set first");
   if (ctx->Dm != ctx->D) return fail(ctx, HMMCU_EINVAL, "models have D=%d but features have D=%d", ctx->Dm, ctx->D);
   if (!ctx->pack_dirty) return HMMCU_OK;
-  const int64_t VG = (int64_t)ctx->V * ctx->G;
-  CK(ctx->mu32.ensure(sizeof(float) * VG * ctx->DP));
-  CK(ctx->iv32.ensure(sizeof(float) * VG * ctx->DP));
-  CK(ctx->k32.ensure(sizeof(float) * VG));
   CK(ctx->ctr.ensure(sizeof(double) * ctx->DP));
   if (ctx->F == 0) CK(cudaMemsetAsync(ctx->ctr.p, 0, sizeof(double) * ctx->DP, ctx->st));
-  int64_t total = VG * ctx->DP;
-  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-  t_begin(ctx, "pack");
-  k_pack_models<<<blocks, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
-                                            ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->DP,
-                                            ctx->mu32.as<float>(), ctx->iv32.as<float>(), ctx->k32.as<float>());
-  LAUNCH_CHECK();
-  t_end(ctx, "pack");
   ctx->pack_dirty = false;
+  ctx->simt_dirty = true;  // the packed forms below are rebuilt on first use
+  ctx->kc_dirty = true;
   ctx->tc_train.dirty = true;
   ctx->tc_dec.dirty = true;
   ctx->ws_train.dirty = true;
@@ -394,6 +384,37 @@ static int ensure_packed(hmmcu_ctx *ctx) {
     ctx->kappa = ctx->ctl_h[3 * ctx->V];
     ctx->kappa_stale = false;
   }
+  return HMMCU_OK;
+}
+
+// CUDA-core kernels' parameter arrays (mu32, iv32, k32), built only when that path runs
+static int ensure_simt_pack(hmmcu_ctx *ctx) {
+  if (!ctx->simt_dirty) return HMMCU_OK;
+  const int64_t VG = (int64_t)ctx->V * ctx->G;
+  CK(ctx->mu32.ensure(sizeof(float) * VG * ctx->DP));
+  CK(ctx->iv32.ensure(sizeof(float) * VG * ctx->DP));
+  CK(ctx->k32.ensure(sizeof(float) * VG));
+  int64_t total = VG * ctx->DP;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+  t_begin(ctx, "pack");
+  k_pack_models<<<blocks, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                            ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->DP,
+                                            ctx->mu32.as<float>(), ctx->iv32.as<float>(), ctx->k32.as<float>());
+  LAUNCH_CHECK();
+  t_end(ctx, "pack");
+  ctx->simt_dirty = false;
+  return HMMCU_OK;
+}
+
+// additive constants of all Gaussians (log2 units), shared by the tensor-core W packers
+static int ensure_kc(hmmcu_ctx *ctx) {
+  if (!ctx->kc_dirty) return HMMCU_OK;
+  const int64_t VG = (int64_t)ctx->V * ctx->G;
+  CK(ctx->kc2.ensure(sizeof(float) * VG));
+  k_pack_kc<<<(unsigned)((VG + 127) / 128), 128, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                                               ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->kc2.as<float>());
+  LAUNCH_CHECK();
+  ctx->kc_dirty = false;
   return HMMCU_OK;
 }
 
@@ -414,10 +435,12 @@ static int ensure_acc_images(hmmcu_ctx *ctx) {
   const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
   CK(ctx->acc_images.ensure(tc_accT_image_bytes(KP) * nimg));
   CK(ctx->acc_kc.ensure(sizeof(float) * 128 * (size_t)nimg));
+  int rc = ensure_kc(ctx);
+  if (rc) return rc;
   t_begin(ctx, "pack");
-  k_pack_wT_tc<<<nimg, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), ctx->c.as<double>(),
-                                          ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP, ctx->acc_images.as<float>(),
-                                          ctx->acc_kc.as<float>());
+  k_pack_wT_tc<<<dim3((128 * KP + 255) / 256, nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                        ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP,
+                                                                        ctx->acc_images.as<float>(), ctx->acc_kc.as<float>());
   LAUNCH_CHECK();
   t_end(ctx, "pack");
   ctx->acc_dirty = false;
@@ -496,10 +519,14 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
     CK(cudaMemcpyAsync(ts.ns.p, ns.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));  // s0 / ns are stack vectors
   }
+  {
+    int rc = ensure_kc(ctx);
+    if (rc) return rc;
+  }
   t_begin(ctx, "pack");
-  k_pack_w_ws<<<ts.nimg, 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), ctx->c.as<double>(),
-                                           ctx->ctr.as<double>(), M, MPd, ctx->D, ctx->DP, ts.TN, ts.s0.as<int32_t>(), ts.ns.as<int32_t>(),
-                                           ts.images.as<float>());
+  k_pack_w_ws<<<dim3((ts.TN * KP + 255) / 256, ts.nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                            ctx->ctr.as<double>(), M, MPd, ctx->D, ctx->DP, ts.TN,
+                                                                            ts.s0.as<int32_t>(), ts.ns.as<int32_t>(), ts.images.as<float>());
   LAUNCH_CHECK();
   t_end(ctx, "pack");
   ts.dirty = false;
@@ -566,6 +593,10 @@ static int launch_emis(hmmcu_ctx *ctx, const EmisTile *tiles_dev, int64_t ntiles
                        int decode, float *post) {
   ctx->last_tc = false;
   if (ntiles == 0) return HMMCU_OK;
+  {
+    int rc = ensure_simt_pack(ctx);
+    if (rc) return rc;
+  }
   const int SC = emis_chunk_states(ctx);
   const size_t smem = emis_smem_bytes(SC * ctx->M, SC, ctx->DP);
   if (smem > 227 * 1024) return fail(ctx, HMMCU_EINVAL, "M=%d mixtures x D=%d does not fit the emission kernel's shared memory", ctx->M, ctx->D);
@@ -948,6 +979,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
                                                                             off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>());
       LAUNCH_CHECK();
     } else {
+      if ((rc = ensure_simt_pack(ctx)) != HMMCU_OK) return rc;
       const int NGG = kAccThreads / DP, GCH = NGG * kAccGPT;
       const int nz = (G + GCH - 1) / GCH;
       int nparts = std::max(1, (2 * ctx->sm_count + V * nz - 1) / (V * nz));
@@ -995,10 +1027,15 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   int rc = ensure_ctl(ctx);
   if (rc) return rc;
   t_begin(ctx, "mstep");
-  k_mstep<<<V, 256, 0, ctx->st>>>(ctx->stats.as<double>(), hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm), V, ctx->N, ctx->M, ctx->Dm, threshold,
-                                  1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->em_old.as<double>(), ctx->em_active.as<int>(), ctx->A.as<double>(),
-                                  ctx->c.as<double>(), ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
-                                  ctx->ctl_d.as<double>());
+  const int64_t ssz = hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm);
+  CK(ctx->upd_d.ensure(sizeof(int) * V));
+  k_mstep_ctl<<<(V + 127) / 128, 128, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, V, threshold, ctx->em_old.as<double>(),
+                                                    ctx->em_active.as<int>(), ctx->ctl_d.as<double>(), ctx->upd_d.as<int>());
+  LAUNCH_CHECK();
+  k_mstep_apply<<<dim3(1 + (ctx->G + 7) / 8, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, ctx->N, ctx->M, ctx->Dm,
+                                                                     1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->upd_d.as<int>(),
+                                                                     ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(),
+                                                                     ctx->iv.as<double>(), ctx->det.as<double>());
   LAUNCH_CHECK();
   if ((rc = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc;
   t_end(ctx, "mstep");

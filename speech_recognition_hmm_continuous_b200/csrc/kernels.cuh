@@ -763,102 +763,119 @@ __global__ void k_rank(const double *__restrict__ logp, int U, int V, double wei
 // Like the reference, det / inverse are recomputed for EVERY mixture of a re-estimated model, also
 // those of states with den_mix == 0 (whose stored inverse is thereby inverted again).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_mstep(const double *__restrict__ stats, int64_t ss, int V, int N, int M, int D, double threshold, double floor_,
-        double *__restrict__ em_old, int *__restrict__ em_active, double *__restrict__ Aall, double *__restrict__ call,
-        double *__restrict__ muall, double *__restrict__ ivall, double *__restrict__ detall, double *__restrict__ ctl) {
-  __shared__ int s_upd;
-  const int v = blockIdx.x, tid = threadIdx.x, G = N * M;
+// Step 1: the stopping rule, one thread per model.  upd[v] = 1 iff model v is re-estimated now.
+__global__ void k_mstep_ctl(const double *__restrict__ stats, int64_t ss, int V, double threshold, double *__restrict__ em_old,
+                            int *__restrict__ em_active, double *__restrict__ ctl, int *__restrict__ upd) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
   const double *st = stats + (int64_t)v * ss;
-  if (tid == 0) {
-    const double probab = st[ss - 2], nutt = st[ss - 1];
-    ctl[v] = probab;
-    ctl[V + v] = nutt;
-    int u = 0;
-    if (em_active[v]) {
-      const double variation = fabs((em_old[v] - probab) / em_old[v]);
-      if (variation > threshold) { em_old[v] = probab; u = 1; }
-      else em_active[v] = 0;
-    }
-    ctl[2 * V + v] = (double)u;
-    s_upd = u;
+  const double probab = st[ss - 2], nutt = st[ss - 1];
+  ctl[v] = probab;
+  ctl[V + v] = nutt;
+  int u = 0;
+  if (em_active[v]) {
+    const double variation = fabs((em_old[v] - probab) / em_old[v]);  // T-FS:326
+    if (variation > threshold) { em_old[v] = probab; u = 1; }
+    else em_active[v] = 0;
   }
-  __syncthreads();
-  if (!s_upd) return;
+  ctl[2 * V + v] = (double)u;
+  upd[v] = u;
+}
+
+// Step 2: re-estimation.  grid = (1 + ceil(G / 8), V); block x = 0 does the transitions and the mixture
+// weights of model y, block x >= 1 eight Gaussians, one warp each (lanes over the coefficients; the
+// determinant is the product in index order, as calc_det forms it).
+__global__ void __launch_bounds__(256)
+k_mstep_apply(const double *__restrict__ stats, int64_t ss, int N, int M, int D, double floor_, const int *__restrict__ upd,
+              double *__restrict__ Aall, double *__restrict__ call, double *__restrict__ muall, double *__restrict__ ivall,
+              double *__restrict__ detall) {
+  const int v = blockIdx.y, tid = threadIdx.x, G = N * M;
+  if (!upd[v]) return;
+  const double *st = stats + (int64_t)v * ss;
   const double *num = st, *den = num + (int64_t)N * N, *denmix = den + N, *S0 = denmix + N;
   const double *S1 = S0 + G, *S2 = S1 + (int64_t)G * D;
-  double *A = Aall + (int64_t)v * N * N, *c = call + (int64_t)v * G, *mu = muall + (int64_t)v * G * D;
-  double *iv = ivall + (int64_t)v * G * D, *det = detall + (int64_t)v * G;
-  for (int idx = tid; idx < N * N; idx += blockDim.x) {
-    const int i = idx / N;
-    if (den[i] != 0.0) A[idx] = num[idx] / den[i];
-  }
-  for (int idx = tid; idx < G * D; idx += blockDim.x) {
-    const int k = idx / D, i = k / M;
-    if (denmix[i] != 0.0) {
-      mu[idx] = S1[idx] / S0[k];
-      double var = S2[idx] / S0[k];
-      if (var < floor_) var = floor_;
-      iv[idx] = var;
+  if (blockIdx.x == 0) {
+    double *A = Aall + (int64_t)v * N * N, *c = call + (int64_t)v * G;
+    for (int idx = tid; idx < N * N; idx += blockDim.x) {
+      const int i = idx / N;
+      if (den[i] != 0.0) A[idx] = num[idx] / den[i];
     }
-  }
-  for (int k = tid; k < G; k += blockDim.x) {
-    const int i = k / M;
-    if (denmix[i] != 0.0) c[k] = S0[k] / denmix[i];
-  }
-  __syncthreads();
-  for (int i = tid; i < N; i += blockDim.x) {  // changing_zero_coef
-    double *w = c + i * M;
-    double s = 0.0;
-    for (int k = 0; k < M; k++) {
-      if (w[k] < floor_) w[k] = floor_;
-      s += w[k];
+    for (int i = tid; i < N; i += blockDim.x) {  // updating_mix_param's weights, then changing_zero_coef
+      double *w = c + i * M;
+      if (denmix[i] != 0.0)
+        for (int k = 0; k < M; k++) w[k] = S0[i * M + k] / denmix[i];
+      double s = 0.0;
+      for (int k = 0; k < M; k++) {
+        if (w[k] < floor_) w[k] = floor_;
+        s += w[k];
+      }
+      for (int k = 0; k < M; k++) w[k] /= s;
     }
-    for (int k = 0; k < M; k++) w[k] /= s;
+    return;
   }
-  for (int k = tid; k < G; k += blockDim.x) {  // calc_det then inv_matrix
-    double *vv = iv + (int64_t)k * D;
-    double dt = 1.0;
-    for (int d = 0; d < D; d++) dt *= vv[d];
-    for (int d = 0; d < D; d++) vv[d] = 1.0 / vv[d];
-    det[k] = dt;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int k = (blockIdx.x - 1) * 8 + warp;
+  if (k >= G) return;
+  const int i = k / M;
+  double *mu = muall + ((int64_t)v * G + k) * D, *iv = ivall + ((int64_t)v * G + k) * D;
+  const bool fresh = denmix[i] != 0.0;
+  const double s0 = S0[k];
+  double dt = 1.0;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    double var = 1.0;
+    if (d < D) {
+      if (fresh) {
+        mu[d] = S1[(int64_t)k * D + d] / s0;
+        var = S2[(int64_t)k * D + d] / s0;
+        if (var < floor_) var = floor_;
+      } else var = iv[d];  // not re-estimated: the stored inverse is inverted again, as the reference does
+      iv[d] = 1.0 / var;
+    }
+    const int nd = min(32, D - d0);
+    for (int j = 0; j < nd; j++) dt *= __shfl_sync(0xffffffffu, var, j);  // calc_det: product in index order
   }
+  if (lane == 0) detall[(int64_t)v * G + k] = dt;
 }
 
 // Per-dimension extremes of the model set for the tensor-core accuracy guard: ext[d] = max iv_d,
 // ext[DP + d] = max |mu_d - ctr_d| as the bit patterns of non-negative doubles (ordered like integers);
 // NaN counts as +inf.  ext must be zeroed first.
 __global__ void k_model_extremes(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ ctr,
-                                 int64_t VG, int D, int DP, unsigned long long *__restrict__ ext) {
+                                 int64_t VG, int D, int DP, unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs,
+                                 unsigned int *__restrict__ done, double *__restrict__ kappa_out) {
   const int d = threadIdx.x % DP, grp = threadIdx.x / DP, ngrp = blockDim.x / DP;
-  if (d >= D || grp >= ngrp) return;
-  double ivm = 0.0, mum = 0.0;
-  const double c0 = ctr[d];
-  for (int64_t g = (int64_t)blockIdx.x * ngrp + grp; g < VG; g += (int64_t)gridDim.x * ngrp) {
-    double a = iv[g * D + d], b = fabs(mu[g * D + d] - c0);
-    if (!(a == a)) a = INFINITY;
-    if (!(b == b)) b = INFINITY;
-    ivm = fmax(ivm, a);
-    mum = fmax(mum, b);
+  if (d < D && grp < ngrp) {
+    double ivm = 0.0, mum = 0.0;
+    const double c0 = ctr[d];
+    for (int64_t g = (int64_t)blockIdx.x * ngrp + grp; g < VG; g += (int64_t)gridDim.x * ngrp) {
+      double a = iv[g * D + d], b = fabs(mu[g * D + d] - c0);
+      if (!(a == a)) a = INFINITY;
+      if (!(b == b)) b = INFINITY;
+      ivm = fmax(ivm, a);
+      mum = fmax(mum, b);
+    }
+    atomicMax(ext + d, (unsigned long long)__double_as_longlong(ivm));
+    atomicMax(ext + DP + d, (unsigned long long)__double_as_longlong(mum));
   }
-  atomicMax(ext + d, (unsigned long long)__double_as_longlong(ivm));
-  atomicMax(ext + DP + d, (unsigned long long)__double_as_longlong(mum));
-}
-
-// kappa = sum_d 2 max(iv_d) r_d^2, r_d = largest centred |x| or |mu| in dimension d: an upper bound on
-// sum_k |Xaug_k W_k|; the 3xTF32 contraction carries ~1e-7 of that magnitude as absolute error.
-__global__ void k_kappa(const unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs, int D, int DP,
-                        double *__restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // the last block to finish turns the extremes into kappa = sum_d 2 max(iv_d) r_d^2, r_d = largest centred |x| or
+  // |mu| in dimension d: an upper bound on sum_k |Xaug_k W_k|; the 3xTF32 contraction carries ~1e-7 of it as error
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
   double kappa = 0.0;
-  for (int d = 0; d < D; d++) {
-    const double ivm = __longlong_as_double((long long)ext[d]);
-    double r = __longlong_as_double((long long)ext[DP + d]);
-    if (xabs) r = fmax(r, (double)__uint_as_float(xabs[d]));
+  for (int dd = 0; dd < D; dd++) {
+    const double ivm = __longlong_as_double((long long)atomicAdd(ext + dd, 0ull));
+    double r = __longlong_as_double((long long)atomicAdd(ext + DP + dd, 0ull));
+    if (xabs) r = fmax(r, (double)__uint_as_float(xabs[dd]));
     const double t = 2.0 * ivm * r * r;
     kappa += (t == t) ? t : INFINITY;
   }
-  *out = kappa;
+  *kappa_out = kappa;
 }
 
 }  // namespace hmmk

@@ -434,15 +434,34 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// kc2[g] = log2(e) (ln c - 0.5 (D ln 2pi + ln|det|) - 0.5 sum (mu - ctr)^2 iv), -inf for a Gaussian of density 0
+// (c == 0 or det == 0): the additive constant of every Gaussian, one thread each, shared by all W packers.
+__global__ void k_pack_kc(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
+                          const double *__restrict__ c, const double *__restrict__ ctr, int64_t VG, int D, float *__restrict__ kc2) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= VG) return;
+  double k = -INFINITY;
+  const double dt = det[g], cc = c[g];
+  if (dt != 0.0 && cc > 0.0) {
+    double q = 0.0;
+    for (int d = 0; d < D; d++) {
+      const double m = mu[g * D + d] - ctr[d];
+      q += m * m * iv[g * D + d];
+    }
+    k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
+  }
+  kc2[g] = (float)k;
+}
+
 // W images for the accumulate kernel: image (v, rb) = Gaussians [rb*128, rb*128+128) of model v, row-major
 // [128][Wh[KP] | Wl[KP]]; rows beyond G are zero with kc = -inf.  kcT is pre-multiplied by log2(e).
-__global__ void k_pack_wT_tc(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
-                             const double *__restrict__ c, const double *__restrict__ ctr, int G, int nRB, int D, int DP,
-                             float *__restrict__ images, float *__restrict__ kcT) {
-  const int img = blockIdx.x, v = img / nRB, rb = img - v * nRB;
+__global__ void k_pack_wT_tc(const double *__restrict__ mu, const double *__restrict__ iv, const float *__restrict__ kc2all,
+                             const double *__restrict__ ctr, int G, int nRB, int D, int DP, float *__restrict__ images,
+                             float *__restrict__ kcT) {
+  const int img = blockIdx.y, v = img / nRB, rb = img - v * nRB;
   const int KP = 2 * DP;
   float *im = images + (size_t)img * (tc_accT_image_bytes(KP) / 4);
-  for (int idx = threadIdx.x; idx < 128 * KP; idx += blockDim.x) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * KP; idx += gridDim.x * blockDim.x) {
     const int r = idx / KP, k = idx - r * KP;
     const int part = k / DP, d = k - part * DP;
     const int g = rb * 128 + r;
@@ -456,23 +475,7 @@ __global__ void k_pack_wT_tc(const double *__restrict__ mu, const double *__rest
     split_tf32(val, h, l);
     im[(size_t)r * 2 * KP + k] = h;
     im[(size_t)r * 2 * KP + KP + k] = l;
-  }
-  for (int r = threadIdx.x; r < 128; r += blockDim.x) {
-    const int g = rb * 128 + r;
-    double k = -INFINITY;
-    if (g < G) {
-      const int64_t gg = (int64_t)v * G + g;
-      const double dt = det[gg], cc = c[gg];
-      if (dt != 0.0 && cc > 0.0) {
-        double q = 0.0;
-        for (int d = 0; d < D; d++) {
-          const double m = mu[gg * D + d] - ctr[d];
-          q += m * m * iv[gg * D + d];
-        }
-        k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
-      }
-    }
-    kcT[(size_t)img * 128 + r] = (float)k;
+    if (k == 0) kcT[(size_t)img * 128 + r] = (g < G) ? kc2all[(int64_t)v * G + g] : kNegInf;
   }
 }
 

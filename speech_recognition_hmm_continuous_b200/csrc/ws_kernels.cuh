@@ -99,11 +99,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
 // W images for k_emis_ws: image i covers global states [img_state0[i], +img_nstates[i]), TN rows (whole
 // states; rows beyond are zero), followed by kc2[TN] = log2(e) (ln c - 0.5 (D ln 2pi + ln|det|) - 0.5 sum mu^2 iv),
 // -inf for a Gaussian with c == 0 or det == 0 (density 0 in the reference) and for the pad rows.
-__global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
-                            const double *__restrict__ c, const double *__restrict__ ctr, int M, int MP, int D, int DP, int TN,
+__global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restrict__ iv, const float *__restrict__ kc2all,
+                            const double *__restrict__ ctr, int M, int MP, int D, int DP, int TN,
                             const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
                             float *__restrict__ images) {
-  const int img = blockIdx.x;
+  const int img = blockIdx.y;
   const int KP = 2 * DP;
   const uint32_t P = (uint32_t)(KP / 4) * 128;
   const size_t img_floats = ws_image_bytes(TN, KP) / 4;
@@ -117,7 +117,7 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
     const int st = n / MP, m = n - st * MP;
     return (st < nst && m < M) ? (s0g + st) * M + m : -1;
   };
-  for (int idx = threadIdx.x; idx < TN * KP; idx += blockDim.x) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TN * KP; idx += gridDim.x * blockDim.x) {
     const int n = idx / KP, k = idx - n * KP;
     const int part = k / DP, d = k - part * DP;
     const int64_t g = gauss_of(n);
@@ -131,22 +131,7 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
     const size_t o = ((size_t)(n & 7) * 16 + (k & 3) * 4 + (size_t)(k >> 2) * 128 + (size_t)(n >> 3) * P) / 4;
     hi[o] = h;
     lo[o] = l;
-  }
-  for (int n = threadIdx.x; n < TN; n += blockDim.x) {
-    double k = -INFINITY;
-    const int64_t g = gauss_of(n);
-    if (g >= 0) {
-      const double dt = det[g], cc = c[g];
-      if (dt != 0.0 && cc > 0.0) {
-        double q = 0.0;
-        for (int d = 0; d < D; d++) {
-          const double m = mu[g * D + d] - ctr[d];
-          q += m * m * iv[g * D + d];
-        }
-        k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
-      }
-    }
-    kc2[n] = (float)k;
+    if (k == 0) kc2[n] = (g >= 0) ? kc2all[g] : kNegInf;
   }
 }
 
