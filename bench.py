@@ -219,7 +219,9 @@ def run_ours(args):
         t = torch.tensor([ms_dec], dtype=torch.float64, device=torch.device("cuda", local))
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kn = ("emis", "score") if name == "forward" else ("logb64", "viterbi")
         dec[name] = {"frames_per_s": F * world / (float(t.item()) * 1e-3), "ms": float(t.item()),
+                     "kernel_ms": {k: ctx.kernel_ms(k) for k in kn},
                      "frame_model_pairs_per_s": (F * V * world / (float(t.item()) * 1e-3)) if name == "forward" else None}
 
     pk = peaks()

@@ -136,7 +136,7 @@ int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx);
 /* Device time in ms of the most recent call's kernels, by name (CUDA events on the context's
- * stream).  names: "emis", "fwdbwd", "accum", "mstep", "score", "viterbi", "pack".  -1 if unknown.
+ * stream).  names: "emis", "fwdbwd", "accum", "mstep", "score", "viterbi", "logb64", "pack".  -1 if unknown.
  * Two pseudo-names report state instead of time: "kappa" (accuracy-guard value) and "tc_active"
  * (1 if the last emission launch ran on tensor cores). */
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name);

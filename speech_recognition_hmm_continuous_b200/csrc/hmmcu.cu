@@ -16,6 +16,7 @@
 #include "fb_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "ws_kernels.cuh"
+#include "vit_kernels.cuh"
 
 using namespace hmmk;
 
@@ -54,6 +55,12 @@ struct Timer {
 struct hmmcu_ctx {
   int dev = 0;
   cudaStream_t st = nullptr;
+  // feature upload pipeline: chunk copies on their own stream, packed on `st` as they land
+  cudaStream_t st_copy = nullptr;
+  static constexpr int kUpChunks = 16;
+  cudaEvent_t ev_chunk[kUpChunks] = {};
+  cudaEvent_t ev_idle = nullptr;
+  double *ctr_h = nullptr;  // pinned [256]
   char err[512] = "";
   int64_t launches = 0;
   int sm_count = 148;
@@ -108,7 +115,7 @@ struct hmmcu_ctx {
   int64_t n_acc_units = 0;
 
   // workspaces
-  DevBuf logb, post, gamma, alpha_ws, beta_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
+  DevBuf logb, logb64, post, gamma, alpha_ws, beta_ws, stats, logp_utt_d, score_d, psi_ws, path_d, tiles_dec, rank_in, rank_out;
   int64_t stats_n = 0;
 };
 
@@ -182,6 +189,15 @@ int hmmcu_create(int device, hmmcu_ctx **out) {
     delete ctx;
     return HMMCU_ECUDA;
   }
+  bool ok = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_idle, cudaEventDisableTiming) == cudaSuccess &&
+            cudaMallocHost((void **)&ctx->ctr_h, sizeof(double) * 256) == cudaSuccess;
+  for (int k = 0; ok && k < hmmcu_ctx::kUpChunks; k++) ok = cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    fail(nullptr, HMMCU_ECUDA, "upload pipeline creation: %s", cudaGetErrorString(cudaGetLastError()));
+    hmmcu_destroy(ctx);
+    return HMMCU_ECUDA;
+  }
   *out = ctx;
   return HMMCU_OK;
 }
@@ -196,13 +212,18 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
-                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64};
+                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
   if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
+  if (ctx->ctr_h) cudaFreeHost(ctx->ctr_h);
+  for (cudaEvent_t e : ctx->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (ctx->ev_idle) cudaEventDestroy(ctx->ev_idle);
+  if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
   cudaStreamDestroy(ctx->st);
   delete ctx;
 }
@@ -258,39 +279,91 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   }
   CK(cudaSetDevice(ctx->dev));
   const int64_t F = U > 0 ? frame_off[U] : 0;
+  // same utterance geometry as before (the trainer re-reading its feature files every iteration,
+  // T-FS:272-321): the training map built from it stays valid
+  const bool same_geometry = ctx->have_features && ctx->U == U && ctx->D == D && (int)ctx->off.size() == U + 1 &&
+                             memcmp(ctx->off.data(), frame_off, sizeof(int64_t) * (U + 1)) == 0;
   ctx->U = U; ctx->D = D; ctx->DP = DP; ctx->F = F; ctx->Tmax = Tmax;
-  ctx->off.assign(frame_off, frame_off + U + 1);
-  ctx->u2m.clear();
+  if (!same_geometry) {
+    ctx->off.assign(frame_off, frame_off + U + 1);
+    ctx->u2m.clear();
+  }
   ctx->pack_dirty = true;  // the centre may move
   ctx->kappa_stale = true;
   ctx->have_features = true;
   if (F == 0) return HMMCU_OK;
   CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
-  CK(cudaMemcpyAsync(ctx->off_d.p, frame_off, sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
-  if (x_host) {
-    CK(ctx->x64_own.ensure(sizeof(double) * F * D));
-    CK(cudaMemcpyAsync(ctx->x64_own.p, x_host, sizeof(double) * F * D, cudaMemcpyHostToDevice, ctx->st));
-    ctx->d_x64 = ctx->x64_own.as<double>();
-  } else {
-    ctx->d_x64 = x_dev;
-  }
+  if (!same_geometry) CK(cudaMemcpyAsync(ctx->off_d.p, ctx->off.data(), sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
   CK(ctx->x32.ensure(sizeof(float) * F * DP));
   CK(ctx->ctr.ensure(sizeof(double) * DP));
-  t_begin(ctx, "pack");
-  k_center<<<1, 1024, 0, ctx->st>>>(ctx->d_x64, F, D, DP, ctx->ctr.as<double>());
-  LAUNCH_CHECK();
-  {
-    int64_t total = F * DP;
-    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-    CK(ctx->xabs_d.ensure(sizeof(unsigned int) * DP));
-    CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * DP, ctx->st));
-    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64, ctx->ctr.as<double>(), F, D, DP, ctx->x32.as<float>(),
+  CK(ctx->xabs_d.ensure(sizeof(unsigned int) * DP));
+  auto pack_range = [&](int64_t f0, int64_t f1) -> int {
+    const int64_t total = (f1 - f0) * DP;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64 + f0 * D, ctx->ctr.as<double>(), f1 - f0, D, DP, ctx->x32.as<float>() + f0 * DP,
                                                 ctx->xabs_d.as<unsigned int>());
     LAUNCH_CHECK();
+    return HMMCU_OK;
+  };
+  if (x_host) {
+    // Upload pipeline: the copy engine streams the frames in chunks on its own stream while the host
+    // forms the centre from the same strided sample k_center takes (same summation order), and `st`
+    // packs every chunk as soon as it has landed.  The copy and the packing overlap; only the last
+    // chunk's packing is exposed.
+    CK(ctx->x64_own.ensure(sizeof(double) * F * D));
+    ctx->d_x64 = ctx->x64_own.as<double>();
+    CK(cudaEventRecord(ctx->ev_idle, ctx->st));            // earlier kernels may still read the old features
+    CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_idle, 0));
+    const int nch = (int)std::max<int64_t>(1, std::min<int64_t>(hmmcu_ctx::kUpChunks, F / 4096));
+    const int64_t per = (F + nch - 1) / nch;
+    for (int k = 0; k < nch; k++) {
+      const int64_t f0 = k * per, f1 = std::min(F, f0 + per);
+      if (f1 > f0) CK(cudaMemcpyAsync(ctx->x64_own.as<double>() + f0 * D, x_host + f0 * D, sizeof(double) * (f1 - f0) * D, cudaMemcpyHostToDevice, ctx->st_copy));
+      CK(cudaEventRecord(ctx->ev_chunk[k], ctx->st_copy));
+    }
+    {  // the centre, on the host, while the copy engine runs (k_center's sample and order: 16 interleaved partial sums)
+      const int64_t ns = F < 4096 ? F : 4096, stride = F / ns;
+      for (int d = 0; d < DP; d++) {
+        double t = 0.0;
+        if (d < D) {
+          double part[16];
+          for (int g = 0; g < 16; g++) {
+            double sacc = 0.0;
+            for (int64_t k = g; k < ns; k += 16) sacc += x_host[(k * stride) * D + d];
+            part[g] = sacc;
+          }
+          for (int g = 0; g < 16; g++) t += part[g];
+          t /= (double)ns;
+        }
+        ctx->ctr_h[d] = t;
+      }
+      CK(cudaMemcpyAsync(ctx->ctr.p, ctx->ctr_h, sizeof(double) * DP, cudaMemcpyHostToDevice, ctx->st));
+      CK(cudaEventRecord(ctx->ev_idle, ctx->st));  // ctr_h is free again once this has run
+    }
+    CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * DP, ctx->st));
+    t_begin(ctx, "pack");
+    for (int k = 0; k < nch; k++) {
+      const int64_t f0 = k * per, f1 = std::min(F, f0 + per);
+      CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[k], 0));
+      if (f1 > f0) {
+        int rc = pack_range(f0, f1);
+        if (rc) return rc;
+      }
+    }
+    t_end(ctx, "pack");
+    // the caller's host buffer may be reused as soon as we return
+    CK(cudaStreamSynchronize(ctx->st_copy));
+    CK(cudaEventSynchronize(ctx->ev_idle));
+  } else {
+    ctx->d_x64 = x_dev;
+    t_begin(ctx, "pack");
+    k_center<<<1, 1024, 0, ctx->st>>>(ctx->d_x64, F, D, DP, ctx->ctr.as<double>());
+    LAUNCH_CHECK();
+    CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * DP, ctx->st));
+    int rc = pack_range(0, F);
+    if (rc) return rc;
+    t_end(ctx, "pack");
   }
-  t_end(ctx, "pack");
-  // the caller's host buffer may be reused as soon as we return
-  CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }
 
@@ -661,14 +734,43 @@ int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
 // ----------------------------------------------------------------------- decode (all cells) ----
 template <int NS> struct ScoreLaunch {
   static void fwd(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, int emulate) {
-    dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
-    k_fwd_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
-                                                         ctx->A.as<double>(), out, emulate);
+    if (emulate) {  // the reference's linear-domain underflow, cell by cell (slow path, drop-in recogniser)
+      dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
+      k_fwd_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
+                                                           ctx->A.as<double>(), out, emulate);
+      return;
+    }
+    const unsigned grid = (unsigned)(((int64_t)nu * ctx->V + kCellThreads - 1) / kCellThreads);
+    if (ctx->banded)
+      k_fwd_cells<NS, true><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                ctx->A.as<double>(), out);
+    else
+      k_fwd_cells<NS, false><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                 ctx->A.as<double>(), out);
   }
   static void vit(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out) {
-    dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
-    k_viterbi_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
-                                                             ctx->A.as<double>(), out);
+    const unsigned grid = (unsigned)(((int64_t)nu * ctx->V + kCellThreads - 1) / kCellThreads);
+    if (ctx->banded)
+      k_vit_cells<NS, true><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                ctx->A.as<double>(), out);
+    else
+      k_vit_cells<NS, false><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                 ctx->A.as<double>(), out);
+  }
+  static cudaError_t path(hmmcu_ctx *ctx, const double *logb64, const int32_t *map, double *score, int32_t *path) {
+    const size_t smem = vit_smem_bytes(NS);
+    const int grid = (ctx->U + kVitUtts - 1) / kVitUtts;
+    cudaError_t e;
+    if (ctx->banded) {
+      if ((e = cudaFuncSetAttribute(k_viterbi<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      k_viterbi<NS, true><<<grid, kVitThreads, smem, ctx->st>>>(logb64, ctx->off_d.as<int64_t>(), map, ctx->A.as<double>(), ctx->U,
+                                                                ctx->psi_ws.as<unsigned long long>(), score, path);
+    } else {
+      if ((e = cudaFuncSetAttribute(k_viterbi<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      k_viterbi<NS, false><<<grid, kVitThreads, smem, ctx->st>>>(logb64, ctx->off_d.as<int64_t>(), map, ctx->A.as<double>(), ctx->U,
+                                                                 ctx->psi_ws.as<unsigned long long>(), score, path);
+    }
+    return cudaSuccess;
   }
 };
 
@@ -1098,17 +1200,41 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
   const int U = ctx->U;
   for (int u = 0; u < U; u++)
     if (utt2model[u] < 0 || utt2model[u] >= ctx->V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, utt2model[u]);
+  if (ctx->Dm != ctx->D) return fail(ctx, HMMCU_EINVAL, "models have D=%d but features have D=%d", ctx->Dm, ctx->D);
+  const size_t lsm = logb64_smem_bytes(ctx->M, ctx->D);
+  if (lsm > 227 * 1024) return fail(ctx, HMMCU_EINVAL, "M=%d mixtures x D=%d does not fit the double-precision emission kernel", ctx->M, ctx->D);
+  std::vector<EmisTile> tiles;
+  for (int u = 0; u < U; u++) {
+    const int64_t f0 = ctx->off[u];
+    const int T = (int)(ctx->off[u + 1] - f0);
+    for (int t = 0; t < T; t += kLbFrames) tiles.push_back({f0 + t, std::min(kLbFrames, T - t), utt2model[u]});
+  }
   DevBuf map;
   CK(map.ensure(sizeof(int32_t) * U));
   CK(cudaMemcpyAsync(map.p, utt2model, sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+  CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
+  CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+  CK(ctx->logb64.ensure(sizeof(double) * (size_t)ctx->F * ctx->N));
   CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
   CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
   CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
+  t_begin(ctx, "logb64");
+  if (ctx->D == 39) {  // the MFCC + delta + delta-delta layout every config uses
+    CK(cudaFuncSetAttribute(k_logb64<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+    k_logb64<39><<<(unsigned)tiles.size(), kLbFrames, lsm, ctx->st>>>(ctx->tiles_dec.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
+                                                                     ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                                                     ctx->N, ctx->M, ctx->D, ctx->logb64.as<double>());
+  } else {
+    CK(cudaFuncSetAttribute(k_logb64<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+    k_logb64<0><<<(unsigned)tiles.size(), kLbFrames, lsm, ctx->st>>>(ctx->tiles_dec.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
+                                                                    ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                                                    ctx->N, ctx->M, ctx->D, ctx->logb64.as<double>());
+  }
+  LAUNCH_CHECK();
+  t_end(ctx, "logb64");
   t_begin(ctx, "viterbi");
-  DISPATCH_N(ctx->N, (k_viterbi_path64<NS><<<(U + 1) / 2, 64, 0, ctx->st>>>(
-                         ctx->d_x64, ctx->off_d.as<int64_t>(), map.as<int32_t>(), ctx->A.as<double>(), ctx->c.as<double>(),
-                         ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(), U, ctx->M, ctx->D,
-                         ctx->psi_ws.as<unsigned long long>(), ctx->logp_utt_d.as<double>(), ctx->path_d.as<int32_t>())));
+  DISPATCH_N(ctx->N, CK(ScoreLaunch<NS>::path(ctx, ctx->logb64.as<double>(), map.as<int32_t>(), ctx->logp_utt_d.as<double>(),
+                                               path ? ctx->path_d.as<int32_t>() : nullptr)));
   LAUNCH_CHECK();
   t_end(ctx, "viterbi");
   CK(cudaMemcpyAsync(score, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));

@@ -512,8 +512,8 @@ __global__ void k_finalize_stats(double *__restrict__ stats, int64_t stats_strid
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decode recursions: one THREAD per (utterance, model) cell; a warp covers 32 consecutive models
-// of one utterance so that every frame is one contiguous 32*N-float read of logb[f][V*N].
+// Forward score with the reference's linear-domain underflow emulated (the drop-in recogniser's
+// path): one THREAD per (utterance, model) cell.  The fast scorers are in vit_kernels.cuh.
 // ------------------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;
 
@@ -566,146 +566,6 @@ k_fwd_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const in
     lp += (double)mt + log(sum);
   }
   out[(int64_t)u * V + v] = lp + log(al[NS - 1]);
-}
-
-// Viterbi score, all cells (V1; no reference code).  delta in double, log domain.
-template <int NS>
-__global__ void __launch_bounds__(kScoreThreads)
-k_viterbi_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off,
-                int u0, int V, const double *__restrict__ Aall, double *__restrict__ out) {
-  const int v = blockIdx.x * kScoreThreads + threadIdx.x;
-  const int u = u0 + blockIdx.y;
-  if (v >= V) return;
-  const int64_t base = off[u];
-  const int T = (int)(off[u + 1] - base);
-  double LA[NS * NS];
-#pragma unroll
-  for (int k = 0; k < NS * NS; k++) LA[k] = log(Aall[(int64_t)v * NS * NS + k]);
-  double dl[NS];
-  const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
-#pragma unroll
-  for (int i = 0; i < NS; i++) dl[i] = (i == 0 ? 0.0 : -INFINITY) + (double)p[i];
-  p += ldb;
-  for (int t = 1; t < T; t++, p += ldb) {
-    double dn[NS];
-#pragma unroll
-    for (int j = 0; j < NS; j++) {
-      double best = dl[0] + LA[j];
-#pragma unroll
-      for (int i = 1; i < NS; i++) {
-        double c = dl[i] + LA[i * NS + j];
-        if (c > best) best = c;
-      }
-      dn[j] = best + (double)p[j];
-    }
-#pragma unroll
-    for (int j = 0; j < NS; j++) dl[j] = dn[j];
-  }
-  out[(int64_t)u * V + v] = dl[NS - 1];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Viterbi with back-pointers for (utterance, its model) pairs in DOUBLE precision end to end:
-// emissions are recomputed from the double masters so that state sequences agree with a
-// double-precision CPU restatement.  One warp per utterance; lanes own frames for the emissions,
-// the delta recursion runs on all lanes; psi rows (N bytes per frame) go to a workspace and are
-// walked back in chunks of 32 frames.
-// ------------------------------------------------------------------------------------------------
-template <int NS>
-__global__ void __launch_bounds__(64)
-k_viterbi_path64(const double *__restrict__ x64, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-                 const double *__restrict__ Aall, const double *__restrict__ call, const double *__restrict__ muall,
-                 const double *__restrict__ ivall, const double *__restrict__ detall, int U, int M, int D,
-                 unsigned long long *__restrict__ psi_ws, double *__restrict__ score, int32_t *__restrict__ path) {
-  __shared__ double sLA[2][NS * NS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x * 2 + warp;
-  if (u >= U) return;
-  const int v = u2m[u];
-  const int64_t base = off[u];
-  const int T = (int)(off[u + 1] - base);
-  for (int k = lane; k < NS * NS; k += 32) sLA[warp][k] = log(Aall[(int64_t)v * NS * NS + k]);
-  __syncwarp();
-  const double *LA = sLA[warp];
-  const int G = NS * M;
-  const double *c = call + (int64_t)v * G, *mu = muall + (int64_t)v * G * D, *iv = ivall + (int64_t)v * G * D,
-               *det = detall + (int64_t)v * G;
-  const double lognorm = 0.5 * (double)D * 1.8378770664093453;
-
-  double dl[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) dl[i] = 0.0;
-  for (int c0 = 0; c0 < T; c0 += 32) {
-    const int t = c0 + lane;
-    const bool valid = t < T;
-    double lb[NS];
-    // double-precision emissions of my frame: log sum_m c_m N_m  (log-sum-exp over mixtures)
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      double mx = -INFINITY, acc = 0.0;
-      if (valid) {
-        for (int m = 0; m < M; m++) {
-          const int g = i * M + m;
-          double q = 0.0;
-          const double *xr = x64 + (base + t) * D;
-          for (int d = 0; d < D; d++) {
-            double dif = xr[d] - mu[(int64_t)g * D + d];
-            q += dif * iv[(int64_t)g * D + d] * dif;
-          }
-          double dt = det[g], cc = c[g];
-          double ln = (dt != 0.0 && cc > 0.0) ? log(cc) - 0.5 * q - lognorm - 0.5 * log(fabs(dt)) : -INFINITY;
-          if (ln > mx) { acc = acc * exp(mx - ln) + 1.0; mx = ln; }
-          else if (ln > -INFINITY) acc += exp(ln - mx);
-        }
-      }
-      lb[i] = (mx > -INFINITY) ? mx + log(acc) : -INFINITY;
-    }
-    unsigned long long my_psi = 0ull;
-    const int ns = min(32, T - c0);
-    for (int s = 0; s < ns; s++) {
-      double b[NS], dn[NS];
-      unsigned long long ps = 0ull;
-#pragma unroll
-      for (int i = 0; i < NS; i++) b[i] = __shfl_sync(0xffffffffu, lb[i], s);
-      if (c0 + s == 0) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) dn[i] = (i == 0 ? 0.0 : -INFINITY) + b[i];
-      } else {
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          double best = dl[0] + LA[j];
-          int arg = 0;
-#pragma unroll
-          for (int i = 1; i < NS; i++) {
-            double cnd = dl[i] + LA[i * NS + j];
-            if (cnd > best) { best = cnd; arg = i; }  // strict: lowest index wins a tie
-          }
-          dn[j] = best + b[j];
-          ps |= (unsigned long long)arg << (8 * j);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NS; i++) dl[i] = dn[i];
-      if (lane == s) my_psi = ps;
-    }
-    if (valid) psi_ws[base + t] = my_psi;
-  }
-  if (lane == 0) score[u] = dl[NS - 1];
-  // back-trace, final state N-1
-  int sidx = NS - 1;
-  const int clast = ((T - 1) / 32) * 32;
-  for (int c0 = clast; c0 >= 0; c0 -= 32) {
-    const int t = c0 + lane;
-    unsigned long long my_psi = (t < T) ? psi_ws[base + t] : 0ull;
-    int my_state = 0;
-    const int ns = min(32, T - c0);
-    for (int s = ns - 1; s >= 0; s--) {
-      if (lane == s) my_state = sidx;
-      unsigned long long ps = __shfl_sync(0xffffffffu, my_psi, s);
-      sidx = (int)((ps >> (8 * sidx)) & 0xffull);
-    }
-    if (t < T) path[base + t] = my_state;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
