@@ -21,12 +21,17 @@ else:
 ctx.synchronize()
 buf = np.zeros(3 * 16384, dtype=np.float32)
 ctx.lib.hmmcu_debug_acc_read(ctx.h, buf.ctypes.data_as(C.c_void_p))
-t = buf.view(np.int64)[:64 * 8].reshape(64, 8)
+W = 16 if mode == "acc" else 8
+t = buf.view(np.int64)[:64 * W].reshape(64, W)[:, :15 if mode == "acc" else 8]
 t0 = t[t > 0].min()
 names = ["ld:top", "ld:empty", "ld:arrive", "mma:full", "mma:dempty", "mma:issued", "epi:dfull", "epi:arrive"]
 if mode == "acc":
-    names = ["ld:top", "ld:free", "ld:arrive", "mma:xfull", "mma:g1", "mma:g2", "epi:d1full", "epi:wfull"]
+    names = ["ld:top", "ld:free", "ld:arrive", "mma:xfull", "mma:g1", "mma:g2", "epi:d1full", "epi:wfull", "g2:start", "g2:issued", "e0:arrive", "e0:top", "e0:ld", "e0:math", "e0:st"]
 print("unit " + " ".join("%10s" % n for n in names))
-for i in range(40):
+for i in range(64):
     if t[i].max() == 0: break
     print("%4d " % i + " ".join("%10d" % (v - t0 if v > 0 else -1) for v in t[i]))
+
+if mode == "acc":
+    g = buf.view(np.int64)
+    print("kernel entry %d, after init %d, role ends %s, after final sync %d" % (g[1024] - t0, g[1025] - t0, [int(v - t0) for v in g[1026:1046]], g[1050] - t0))

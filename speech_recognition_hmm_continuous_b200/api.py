@@ -171,6 +171,10 @@ class Context:
         if timing:
             self.lib.hmmcu_enable_timing(self.h, 1)
 
+    def enable_timing(self, on=True):
+        """Per-kernel device timers (kernel_ms); turns the CUDA-graph replay of the EM iteration off."""
+        self.lib.hmmcu_enable_timing(self.h, 1 if on else 0)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.hmmcu_destroy(self.h)

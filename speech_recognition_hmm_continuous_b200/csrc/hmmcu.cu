@@ -23,12 +23,14 @@ using namespace hmmk;
 namespace {
 
 char g_create_err[512] = "";
+uint64_t g_alloc_epoch = 0;  // bumped whenever a device buffer moves: cached CUDA graphs hold raw pointers
 
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_epoch++;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -38,7 +40,7 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { cudaFree(p); g_alloc_epoch++; }
     p = nullptr;
     cap = 0;
   }
@@ -48,6 +50,16 @@ struct DevBuf {
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   bool used = false;
+};
+
+// A launch sequence captured once and replayed: the EM iteration is a dozen short kernels, and launching
+// them one by one costs more host time than they run.
+struct GraphSlot {
+  cudaGraphExec_t exec = nullptr;
+  uint64_t key = 0;
+  int seen = 0;
+  int64_t nlaunch = 0;
+  bool bad = false;
 };
 
 }  // namespace
@@ -65,6 +77,10 @@ struct hmmcu_ctx {
   int64_t launches = 0;
   int sm_count = 148;
   bool timing = false;
+  int use_graph = 1;          // replay the E-step / M-step launch sequences as CUDA graphs ("graphs" option)
+  uint64_t cfg_epoch = 0;     // bumped by everything that changes what those sequences launch
+  GraphSlot g_estep, g_mstep;
+  int train_path = 0;         // emission / accumulate path of the last E-step: 0 CUDA cores, 1 k_emis_tc, 2 warp-specialised
   std::map<std::string, Timer> timers;
 
   // features
@@ -107,7 +123,7 @@ struct hmmcu_ctx {
   DevBuf tc_tiles_train, frame_ids_d, tc_tiles_dec, ws_tiles_train;
   int64_t n_tc_tiles_train = 0, n_ws_tiles_train = 0;
   // tensor-core accumulate kernel: W images per (model, block of 128 Gaussians) and its work units
-  DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64;
+  DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
   int debug_acc = 0;
@@ -159,6 +175,48 @@ static void t_end(hmmcu_ctx *ctx, const char *name) {
   t.used = true;
 }
 
+
+// enqueue() issues a fixed launch sequence on ctx->st.  The first two calls under a key run it directly (lazy
+// allocations and function attributes settle), the third captures it, later ones replay the graph.
+template <typename F>
+static int run_graphed(hmmcu_ctx *ctx, GraphSlot &gs, uint64_t key, F &&enqueue) {
+  // (per-kernel timing records events between the kernels; events recorded by graph nodes cannot be timed)
+  if (!ctx->use_graph || ctx->timing || gs.bad) return enqueue();
+  key = key * 0x9E3779B97F4A7C15ull + g_alloc_epoch * 1000003ull + ctx->cfg_epoch;
+  if (gs.key != key) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs.exec = nullptr;
+    gs.key = key;
+    gs.seen = 0;
+  }
+  if (gs.exec) {
+    CK(cudaGraphLaunch(gs.exec, ctx->st));
+    ctx->launches += gs.nlaunch;
+    return HMMCU_OK;
+  }
+  if (++gs.seen < 3) return enqueue();
+  const int64_t l0 = ctx->launches;
+  if (cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    gs.bad = true;
+    return enqueue();
+  }
+  const int rc = enqueue();
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->st, &g);
+  if (rc == HMMCU_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&gs.exec, g, 0);
+  if (g) cudaGraphDestroy(g);
+  if (rc != HMMCU_OK || e != cudaSuccess || !gs.exec) {  // not capturable here: run it the plain way from now on
+    cudaGetLastError();
+    gs.exec = nullptr;
+    gs.bad = true;
+    ctx->launches = l0;
+    return rc != HMMCU_OK ? rc : enqueue();
+  }
+  gs.nlaunch = ctx->launches - l0;
+  CK(cudaGraphLaunch(gs.exec, ctx->st));
+  return HMMCU_OK;
+}
 
 int hmmcu_device_count(void) {
   int n = 0;
@@ -212,12 +270,14 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
-                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64};
+                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
     if (kv.second.b) cudaEventDestroy(kv.second.b);
   }
+  if (ctx->g_estep.exec) cudaGraphExecDestroy(ctx->g_estep.exec);
+  if (ctx->g_mstep.exec) cudaGraphExecDestroy(ctx->g_mstep.exec);
   if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
   if (ctx->ctr_h) cudaFreeHost(ctx->ctr_h);
   for (cudaEvent_t e : ctx->ev_chunk)
@@ -240,19 +300,23 @@ void hmmcu_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
-void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; }
+void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; ctx->cfg_epoch++; }
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
   if (strcmp(name, "kappa") == 0) return ctx->kappa;            // accuracy-guard value of the current pack
   if (strcmp(name, "tc_active") == 0) return ctx->last_tc ? 1.0 : 0.0;
   auto it = ctx->timers.find(name);
   if (it == ctx->timers.end() || !it->second.used) return -1.0;
   float ms = 0.f;
-  if (cudaEventSynchronize(it->second.b) != cudaSuccess) return -1.0;
-  if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.0;
+  if (cudaEventSynchronize(it->second.b) != cudaSuccess || cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.0;
+  }
   return (double)ms;
 }
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (!ctx || !key) return HMMCU_EINVAL;
+  ctx->cfg_epoch++;
+  if (strcmp(key, "graphs") == 0) { ctx->use_graph = value; return HMMCU_OK; }
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
@@ -287,6 +351,7 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   if (!same_geometry) {
     ctx->off.assign(frame_off, frame_off + U + 1);
     ctx->u2m.clear();
+    ctx->cfg_epoch++;
   }
   ctx->pack_dirty = true;  // the centre may move
   ctx->kappa_stale = true;
@@ -404,6 +469,7 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
   ctx->have_models = true;
   ctx->pack_dirty = true;
   ctx->kappa_stale = true;
+  ctx->cfg_epoch++;
   return HMMCU_OK;
 }
 
@@ -430,6 +496,7 @@ static int ensure_ctl(hmmcu_ctx *ctx) {
     ctx->ctl_h = nullptr;
     CK(cudaMallocHost((void **)&ctx->ctl_h, sizeof(double) * n));
     ctx->ctl_cap = n;
+    g_alloc_epoch++;
   }
   return HMMCU_OK;
 }
@@ -480,13 +547,19 @@ static int ensure_simt_pack(hmmcu_ctx *ctx) {
 }
 
 // additive constants of all Gaussians (log2 units), shared by the tensor-core W packers
+static int launch_pack_kc(hmmcu_ctx *ctx) {
+  const int64_t VG = (int64_t)ctx->V * ctx->G;
+  k_pack_kc<<<(unsigned)((VG * 32 + 255) / 256), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
+                                                                    ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->kc2.as<float>());
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
 static int ensure_kc(hmmcu_ctx *ctx) {
   if (!ctx->kc_dirty) return HMMCU_OK;
   const int64_t VG = (int64_t)ctx->V * ctx->G;
   CK(ctx->kc2.ensure(sizeof(float) * VG));
-  k_pack_kc<<<(unsigned)((VG + 127) / 128), 128, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
-                                                               ctx->c.as<double>(), ctx->ctr.as<double>(), VG, ctx->D, ctx->kc2.as<float>());
-  LAUNCH_CHECK();
+  int rc = launch_pack_kc(ctx);
+  if (rc) return rc;
   ctx->kc_dirty = false;
   return HMMCU_OK;
 }
@@ -503,6 +576,15 @@ static bool tc_supported(const hmmcu_ctx *ctx) {
   return tc_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
 }
 
+static int launch_pack_acc(hmmcu_ctx *ctx) {
+  const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
+  k_pack_wT_tc<<<dim3((128 * KP + 255) / 256, nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                        ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP,
+                                                                        ctx->acc_images.as<float>(), ctx->acc_kc.as<float>());
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
 static int ensure_acc_images(hmmcu_ctx *ctx) {
   if (!ctx->acc_dirty) return HMMCU_OK;
   const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
@@ -511,10 +593,7 @@ static int ensure_acc_images(hmmcu_ctx *ctx) {
   int rc = ensure_kc(ctx);
   if (rc) return rc;
   t_begin(ctx, "pack");
-  k_pack_wT_tc<<<dim3((128 * KP + 255) / 256, nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
-                                                                        ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP,
-                                                                        ctx->acc_images.as<float>(), ctx->acc_kc.as<float>());
-  LAUNCH_CHECK();
+  if ((rc = launch_pack_acc(ctx)) != HMMCU_OK) return rc;
   t_end(ctx, "pack");
   ctx->acc_dirty = false;
   return HMMCU_OK;
@@ -565,6 +644,15 @@ static bool ws_supported(const hmmcu_ctx *ctx) {
   return ws_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
 }
 
+static int launch_pack_ws(hmmcu_ctx *ctx, hmmcu_ctx::TcSet &ts) {
+  const int KP = 2 * ctx->DP;
+  k_pack_w_ws<<<dim3((ts.TN * KP + 255) / 256, ts.nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                            ctx->ctr.as<double>(), ctx->M, ws_pad_m(ctx->M), ctx->D, ctx->DP, ts.TN,
+                                                                            ts.s0.as<int32_t>(), ts.ns.as<int32_t>(), ts.images.as<float>());
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
 static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
   hmmcu_ctx::TcSet &ts = mode == 0 ? ctx->ws_train : ctx->ws_dec;
   if (!ts.dirty) return HMMCU_OK;
@@ -597,10 +685,10 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
     if (rc) return rc;
   }
   t_begin(ctx, "pack");
-  k_pack_w_ws<<<dim3((ts.TN * KP + 255) / 256, ts.nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
-                                                                            ctx->ctr.as<double>(), M, MPd, ctx->D, ctx->DP, ts.TN,
-                                                                            ts.s0.as<int32_t>(), ts.ns.as<int32_t>(), ts.images.as<float>());
-  LAUNCH_CHECK();
+  {
+    int rc = launch_pack_ws(ctx, ts);
+    if (rc) return rc;
+  }
   t_end(ctx, "pack");
   ts.dirty = false;
   return HMMCU_OK;
@@ -957,6 +1045,29 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
       ctx->n_acc_units64 = (int64_t)a64.size();
       CK(ctx->acc_units64.ensure(sizeof(TcTile) * std::max<size_t>(a64.size(), 1)));
       CK(cudaMemcpyAsync(ctx->acc_units64.p, a64.data(), sizeof(TcTile) * a64.size(), cudaMemcpyHostToDevice, ctx->st));
+      {  // scratch slots of k_accum_ws: CTA c covers units [c per, (c+1) per) and writes the partial sums of
+         // its j-th distinct image (j < kAccSlots) into slot c kAccSlots + j; per image, the slots to add up
+        const int64_t nun = (int64_t)a64.size();
+        const int grid = (int)std::min<int64_t>(nun, ctx->sm_count);
+        const int nimg = V * nRB;
+        std::vector<std::vector<int32_t>> lists(nimg);
+        if (grid > 0) {
+          const int64_t per = (nun + grid - 1) / grid;
+          for (int c = 0; c < grid; c++) {
+            int j = -1, prev = -1;
+            for (int64_t k = c * per; k < std::min(nun, (c + 1) * per); k++) {
+              if (a64[k].img != prev) { prev = a64[k].img; j++; if (j < kAccSlots) lists[prev].push_back(c * kAccSlots + j); }
+            }
+          }
+        }
+        std::vector<int32_t> sstart(nimg + 1, 0), sids;
+        for (int i = 0; i < nimg; i++) { sids.insert(sids.end(), lists[i].begin(), lists[i].end()); sstart[i + 1] = (int32_t)sids.size(); }
+        CK(ctx->acc_slot_start.ensure(sizeof(int32_t) * sstart.size()));
+        CK(ctx->acc_slot_ids.ensure(sizeof(int32_t) * std::max<size_t>(sids.size(), 1)));
+        CK(cudaMemcpyAsync(ctx->acc_slot_start.p, sstart.data(), sizeof(int32_t) * sstart.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->acc_slot_ids.p, sids.data(), sizeof(int32_t) * sids.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(ctx->acc_scratch.ensure(sizeof(float) * (size_t)std::max(grid, 1) * kAccSlots * tc_kp2(2 * ctx->DP) * 128));
+      }
       CK(cudaStreamSynchronize(ctx->st));
     }
     CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
@@ -975,6 +1086,7 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
   CK(cudaMemcpyAsync(ctx->tiles_d.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   ctx->u2m.assign(utt2model, utt2model + U);
+  ctx->cfg_epoch++;
   return HMMCU_OK;
 }
 
@@ -990,34 +1102,44 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
                 off_lp = off_S2 + (int64_t)G * D;
   ctx->stats_n = ss * V;
   CK(ctx->stats.ensure(sizeof(double) * ctx->stats_n));
-  CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
+  // ---- preparation (host work, allocations, packed model forms): everything the launch sequence needs ----
+  const bool use_tc = U > 0 && tc_supported(ctx);
+  const bool ws_emis = use_tc && ws_supported(ctx);
+  const bool ws_acc = use_tc && ctx->use_ws_acc && DP <= 40 && ws_acc_smem_bytes(2 * DP) <= 227 * 1024;
   if (U > 0) {
     rc = set_train_map(ctx, utt2model);
     if (rc) return rc;
     const int64_t F = ctx->F;
     CK(ctx->logb.ensure(sizeof(float) * F * N));
-    const bool use_tc = tc_supported(ctx);
     if (!use_tc) CK(ctx->post.ensure(sizeof(float) * F * G));
     CK(ctx->gamma.ensure(sizeof(float) * F * N));
     CK(ctx->alpha_ws.ensure(sizeof(double) * F * N));
     CK(ctx->beta_ws.ensure(sizeof(double) * F * N));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
-    // 1. emissions + per-mixture posteriors
-    if (use_tc && ws_supported(ctx)) {
+    if (ws_emis) {
       if ((rc = ensure_ws_images(ctx, 0)) != HMMCU_OK) return rc;
-      if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
-      t_begin(ctx, "emis");
-      rc = launch_emis_ws<true>(ctx, ctx->ws_tiles_train.as<TcTile>(), ctx->n_ws_tiles_train, 0, 0, ctx->logb.as<float>(), 0, N);
     } else if (use_tc) {
       if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
-      if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
-      t_begin(ctx, "emis");
-      rc = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, nullptr);
-    } else {
-      t_begin(ctx, "emis");
-      rc = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
     }
-    if (rc) return rc;
+    if (use_tc) {
+      if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
+    } else {
+      if ((rc = ensure_simt_pack(ctx)) != HMMCU_OK) return rc;
+    }
+    if (ctx->debug_acc & 5) CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
+  }
+  ctx->train_path = ws_emis ? 2 : use_tc ? 1 : 0;
+  // ---- the launch sequence: statistics cleared, emissions, forward-backward, accumulators ----
+  auto enqueue = [&]() -> int {
+    CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
+    if (U == 0) return HMMCU_OK;
+    int rc2;
+    // 1. emissions (+ per-mixture posteriors on the CUDA-core path)
+    t_begin(ctx, "emis");
+    if (ws_emis) rc2 = launch_emis_ws<true>(ctx, ctx->ws_tiles_train.as<TcTile>(), ctx->n_ws_tiles_train, 0, 0, ctx->logb.as<float>(), 0, N);
+    else if (use_tc) rc2 = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, nullptr);
+    else rc2 = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
+    if (rc2) return rc2;
     t_end(ctx, "emis");
     // 2. forward / backward, gamma, transition statistics, log-probabilities
     t_begin(ctx, "fwdbwd");
@@ -1040,34 +1162,38 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     t_end(ctx, "fwdbwd");
     // 3. mixture accumulators
     t_begin(ctx, "accum");
-    if (use_tc && ctx->use_ws_acc && DP <= 40 && ws_acc_smem_bytes(2 * DP) <= 227 * 1024) {
+    if (ws_acc) {
       const size_t smem = ws_acc_smem_bytes(2 * DP);
-      if (ctx->debug_acc & 4) {
-        CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
-        CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
-      }
-      CK(cudaFuncSetAttribute(k_accum_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (ctx->debug_acc & 4) CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units64, ctx->sm_count);
       if (grid > 0) {
-        k_accum_ws<<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
-                                                        ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
-                                                        ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
-                                                        ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2,
-                                                        (ctx->debug_acc & 4) ? (long long *)ctx->acc_dbg.p : nullptr);
+        if (ctx->debug_acc & 4) {
+          CK(cudaFuncSetAttribute(k_accum_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_accum_ws<true><<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
+                                                                 ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
+                                                                 ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                                 ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2, ctx->acc_scratch.as<float>(),
+                                                                 (long long *)ctx->acc_dbg.p);
+        } else {
+          CK(cudaFuncSetAttribute(k_accum_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_accum_ws<false><<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
+                                                                  ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
+                                                                  ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                                  ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2, ctx->acc_scratch.as<float>(),
+                                                                  nullptr);
+        }
         LAUNCH_CHECK();
       }
-      const int64_t total = (int64_t)V * G * D;
-      k_finalize_stats<<<(unsigned)((total + 255) / 256), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, V, G, D, off_S0, off_S1,
-                                                                            off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>());
+      k_finalize_slots<<<dim3((G + 3) / 4, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, G, D, DP, tc_kp2(2 * DP), (G + 127) / 128, off_S0,
+                                                                  off_S1, off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>(),
+                                                                  ctx->acc_scratch.as<float>(), ctx->acc_slot_start.as<int32_t>(),
+                                                                  ctx->acc_slot_ids.as<int32_t>());
       LAUNCH_CHECK();
     } else if (use_tc) {
       const size_t smem = tc_acc_smem_bytes(2 * DP);
       CK(cudaFuncSetAttribute(k_accum_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units, ctx->sm_count);
-      if (ctx->debug_acc & 1) {
-        CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
-        CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
-      }
+      if (ctx->debug_acc & 1) CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
       if (grid > 0) {
         k_accum_tc<<<grid, kTcThreads, smem, ctx->st>>>(ctx->acc_units.as<TcTile>(), (int)ctx->n_acc_units, ctx->frame_ids_d.as<int32_t>(),
                                                         ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
@@ -1081,7 +1207,6 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
                                                                             off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>());
       LAUNCH_CHECK();
     } else {
-      if ((rc = ensure_simt_pack(ctx)) != HMMCU_OK) return rc;
       const int NGG = kAccThreads / DP, GCH = NGG * kAccGPT;
       const int nz = (G + GCH - 1) / GCH;
       int nparts = std::max(1, (2 * ctx->sm_count + V * nz - 1) / (V * nz));
@@ -1099,7 +1224,11 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       LAUNCH_CHECK();
     }
     t_end(ctx, "accum");
-  }
+    return HMMCU_OK;
+  };
+  const uint64_t key = 1u | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 7) << 5);
+  ctx->last_tc = use_tc;
+  if ((rc = run_graphed(ctx, ctx->g_estep, key, enqueue)) != HMMCU_OK) return rc;
   if (logp_utt && U > 0) CK(cudaMemcpyAsync(logp_utt, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
   if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
   if (stats || logp_utt) CK(cudaStreamSynchronize(ctx->st));
@@ -1128,20 +1257,42 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   const int V = ctx->V;
   int rc = ensure_ctl(ctx);
   if (rc) return rc;
-  t_begin(ctx, "mstep");
   const int64_t ssz = hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm);
   CK(ctx->upd_d.ensure(sizeof(int) * V));
-  k_mstep_ctl<<<(V + 127) / 128, 128, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, V, threshold, ctx->em_old.as<double>(),
-                                                    ctx->em_active.as<int>(), ctx->ctl_d.as<double>(), ctx->upd_d.as<int>());
-  LAUNCH_CHECK();
-  k_mstep_apply<<<dim3(1 + (ctx->G + 7) / 8, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, ctx->N, ctx->M, ctx->Dm,
-                                                                     1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->upd_d.as<int>(),
-                                                                     ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(),
-                                                                     ctx->iv.as<double>(), ctx->det.as<double>());
-  LAUNCH_CHECK();
-  if ((rc = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc;
-  t_end(ctx, "mstep");
-  CK(cudaMemcpyAsync(ctx->ctl_h, ctx->ctl_d.p, sizeof(double) * (3 * (size_t)V + 1), cudaMemcpyDeviceToHost, ctx->st));
+  {
+    const int DP = round_up(ctx->Dm + 1, 4);
+    CK(ctx->ext_d.ensure(sizeof(unsigned long long) * (2 * DP + 1)));
+  }
+  // The warp-specialised tensor-core path will want its packed model forms again right after this M-step: they
+  // are rebuilt here, inside the same launch sequence, instead of lazily by the next E-step.
+  const bool repack = ctx->train_path == 2 && !ctx->pack_dirty && !ctx->ws_train.dirty && !ctx->acc_dirty && !ctx->kc_dirty &&
+                      ctx->have_features && ctx->Dm == ctx->D;
+  auto enqueue = [&]() -> int {
+    t_begin(ctx, "mstep");
+    k_mstep_ctl<<<(V + 127) / 128, 128, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, V, threshold, ctx->em_old.as<double>(),
+                                                      ctx->em_active.as<int>(), ctx->ctl_d.as<double>(), ctx->upd_d.as<int>());
+    LAUNCH_CHECK();
+    k_mstep_apply<<<dim3(1 + (ctx->G + 7) / 8, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, ctx->N, ctx->M, ctx->Dm,
+                                                                       1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->upd_d.as<int>(),
+                                                                       ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(),
+                                                                       ctx->iv.as<double>(), ctx->det.as<double>());
+    LAUNCH_CHECK();
+    int rc2;
+    if ((rc2 = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc2;
+    t_end(ctx, "mstep");
+    if (repack) {
+      t_begin(ctx, "pack");
+      if ((rc2 = launch_pack_kc(ctx)) != HMMCU_OK) return rc2;
+      if ((rc2 = launch_pack_ws(ctx, ctx->ws_train)) != HMMCU_OK) return rc2;
+      if ((rc2 = launch_pack_acc(ctx)) != HMMCU_OK) return rc2;
+      t_end(ctx, "pack");
+    }
+    CK(cudaMemcpyAsync(ctx->ctl_h, ctx->ctl_d.p, sizeof(double) * (3 * (size_t)V + 1), cudaMemcpyDeviceToHost, ctx->st));
+    return HMMCU_OK;
+  };
+  uint64_t tbits;
+  memcpy(&tbits, &threshold, sizeof(tbits));
+  if ((rc = run_graphed(ctx, ctx->g_mstep, (tbits * 31u) ^ (repack ? 2u : 0u), enqueue)) != HMMCU_OK) return rc;
   CK(cudaStreamSynchronize(ctx->st));
   for (int v = 0; v < V; v++) {
     if (sum_logp) sum_logp[v] = ctx->ctl_h[v];
@@ -1150,7 +1301,14 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   }
   ctx->kappa = ctx->ctl_h[3 * V];
   ctx->kappa_stale = false;
-  ctx->pack_dirty = true;
+  if (repack) {  // the forms of the training path are current; every other packed form is stale
+    ctx->simt_dirty = true;
+    ctx->tc_train.dirty = true;
+    ctx->tc_dec.dirty = true;
+    ctx->ws_dec.dirty = true;
+  } else {
+    ctx->pack_dirty = true;
+  }
   return HMMCU_OK;
 }
 

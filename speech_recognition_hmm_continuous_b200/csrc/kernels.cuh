@@ -725,17 +725,27 @@ __global__ void k_model_extremes(const double *__restrict__ mu, const double *__
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!last || threadIdx.x != 0) return;
+  if (!last) return;
   __threadfence();
-  double kappa = 0.0;
-  for (int dd = 0; dd < D; dd++) {
-    const double ivm = __longlong_as_double((long long)atomicAdd(ext + dd, 0ull));
-    double r = __longlong_as_double((long long)atomicAdd(ext + DP + dd, 0ull));
+  // the finished extremes, one dimension per thread (the L2 copies: other blocks wrote them with atomics)
+  __shared__ double part[8];
+  double t = 0.0;
+  for (int dd = threadIdx.x; dd < D; dd += blockDim.x) {
+    const double ivm = __longlong_as_double((long long)__ldcg(ext + dd));
+    double r = __longlong_as_double((long long)__ldcg(ext + DP + dd));
     if (xabs) r = fmax(r, (double)__uint_as_float(xabs[dd]));
-    const double t = 2.0 * ivm * r * r;
-    kappa += (t == t) ? t : INFINITY;
+    const double u = 2.0 * ivm * r * r;
+    t += (u == u) ? u : INFINITY;
   }
-  *kappa_out = kappa;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 8) part[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double kappa = 0.0;
+    for (int w = 0; w < min(8, (int)(blockDim.x + 31) / 32); w++) kappa += part[w];
+    *kappa_out = kappa;
+  }
 }
 
 }  // namespace hmmk

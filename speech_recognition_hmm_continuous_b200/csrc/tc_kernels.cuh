@@ -438,19 +438,23 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // (c == 0 or det == 0): the additive constant of every Gaussian, one thread each, shared by all W packers.
 __global__ void k_pack_kc(const double *__restrict__ mu, const double *__restrict__ iv, const double *__restrict__ det,
                           const double *__restrict__ c, const double *__restrict__ ctr, int64_t VG, int D, float *__restrict__ kc2) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per Gaussian, lanes over the dimensions (coalesced reads of mu / iv, shuffle reduction)
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (g >= VG) return;
-  double k = -INFINITY;
-  const double dt = det[g], cc = c[g];
-  if (dt != 0.0 && cc > 0.0) {
-    double q = 0.0;
-    for (int d = 0; d < D; d++) {
-      const double m = mu[g * D + d] - ctr[d];
-      q += m * m * iv[g * D + d];
-    }
-    k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
+  double q = 0.0;
+  for (int d = lane; d < D; d += 32) {
+    const double m = mu[g * D + d] - ctr[d];
+    q += m * m * iv[g * D + d];
   }
-  kc2[g] = (float)k;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if (lane == 0) {
+    double k = -INFINITY;
+    const double dt = det[g], cc = c[g];
+    if (dt != 0.0 && cc > 0.0) k = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
+    kc2[g] = (float)k;
+  }
 }
 
 // W images for the accumulate kernel: image (v, rb) = Gaussians [rb*128, rb*128+128) of model v, row-major

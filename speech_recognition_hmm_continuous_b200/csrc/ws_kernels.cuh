@@ -96,6 +96,43 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
 
+// Shared-window (32-bit address) forms: a generic pointer into dynamic shared memory costs a
+// generic->shared conversion (three uniform instructions) at every use.
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory"); }
+__device__ __forceinline__ void tc_commit_a(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int lds_i32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
 // W images for k_emis_ws: image i covers global states [img_state0[i], +img_nstates[i]), TN rows (whole
 // states; rows beyond are zero), followed by kc2[TN] = log2(e) (ln c - 0.5 (D ln 2pi + ln|det|) - 0.5 sum mu^2 iv),
 // -inf for a Gaussian with c == 0 or det == 0 (density 0 in the reference) and for the pad rows.
@@ -291,8 +328,20 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     // =================================== EPILOGUE ===================================
     const int row = 32 * warp + lane;  // warps 0..3 <-> TMEM lanes 32w..32w+31
     const uint32_t trow = (uint32_t)(32 * warp) << 16;
+    // unit descriptors two ahead and the frame id one ahead, so that no global-memory latency sits
+    // between the accumulator becoming ready and its reduction
+    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
+    auto frame_of = [&](const TcTile &u) -> int64_t {
+      if (row >= u.nrows) return 0;
+      return TRAIN ? (int64_t)__ldg(frame_ids + u.row0 + row) : fbase + u.row0 + row;
+    };
+    TcTile un0 = unit_at(u_begin), un1 = unit_at(u_begin + 1);
+    int64_t fcur = frame_of(un0);
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
-      const TcTile unit = get_unit(ui);
+      const TcTile unit = un0;
+      const int64_t f = fcur;
+      const int64_t fnext = frame_of(un1);
+      const TcTile un2 = unit_at(ui + 2);
       const int s = i & 1;
       mbar_wait(&dfull[s], (i >> 1) & 1);
       if (warp == 0) stamp(i, 6);
@@ -302,8 +351,6 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       const int mp = MP ? MP : M;  // M here is the padded count
       const int ncols = nst * mp;
       const bool live = row < unit.nrows;
-      int64_t f = 0;
-      if (live) f = TRAIN ? (int64_t)frame_ids[unit.row0 + row] : fbase + unit.row0 + row;
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
       const uint32_t d = tmem0 + 320 + (uint32_t)s * 96 + trow;
       // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
@@ -361,6 +408,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       tc_fence_before();
       mbar_arrive(&dempty[s]);
       if (warp == 0) stamp(i, 7);
+      un0 = un1; un1 = un2; fcur = fnext;
     }
   }
   tc_fence_before();
@@ -377,12 +425,13 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 //   GEMM1  L[g][f]  = sum_k W[g][k] Xaug[f][k]           A = W (TMEM, parked per image), B = X  (smem)
 //   w[g][f] = gamma_f(s(g)) exp(L + kc[g] - logb_f(s(g)))  epilogue, in place in TMEM (hi) + beside it (lo)
 //   GEMM2  S[g][k] += sum_f w[g][f] Xaug[f][k]           A = w (TMEM), B = XT (smem)
-// but the activities run concurrently on different warps and meet only at mbarriers (17 warps):
+// but the activities run concurrently on different warps and meet only at mbarriers (18 warps):
 //   warps  8-11 X LOADERS   features three levels ahead in registers; X (frames x columns), TF32 hi / lo,
 //                           and the per-frame weight exponents cfs
 //   warps 12-15 XT LOADERS  the same tile transposed (columns x frames), TF32 hi / lo
-//   warp  16    MMA         issues whichever of GEMM1(next unit) / GEMM2(oldest unit) has its inputs,
-//                           so neither the loaders nor the epilogue wait on the other's hand-off
+//   warp  16    GEMM1 MMA   issues GEMM1 of the next unit as soon as its X tile (and the image's W) is there
+//   warp  17    GEMM2 MMA   issues GEMM2 of the oldest unit as soon as its weights are there; two issuers
+//                           because one warp's instruction stream serialised the whole pipeline
 //   warps  0-7  EPILOGUE    L -> w with tcgen05.ld / tcgen05.st (warp w: TMEM lanes 32 (w%4).., frames
 //                           32 (w/4)..); every kAccDrain sub-tiles S moves from TMEM (FP32, truncating
 //                           accumulation) to FP32 registers (round to nearest, 40 columns per thread);
@@ -394,91 +443,122 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 //   X  : byte(f, k) = (f%8)*16 + (k%4)*4 + (k/4)*128 + (f/8)*PX     PX = (KP/4)*128   (8 frame groups)
 //   XT : byte(k, f) = (k%8)*16 + (f%4)*4 + (f/4)*128 + (k/8)*2048   (KP2/8 column groups)
 // ================================================================================================
-constexpr int kAccSub = 64;        // frames per sub-tile
-constexpr int kAccDrain = 8;       // sub-tiles accumulated in TMEM before S moves to registers
-constexpr int kAccWsThreads = 544; // 17 warps
+constexpr int kAccSub = 32;        // frames per sub-tile
+constexpr int kAccStages = 4;      // sub-tiles in flight (shared-memory and TMEM stages)
+constexpr int kAccDrain = 16;      // sub-tiles accumulated in TMEM before S moves out (512 frames)
+constexpr int kAccLdWarps = 5;     // warps per loader role (X, XT)
+constexpr int kAccG1Warp = 8 + 2 * kAccLdWarps;  // GEMM1 issuer; the GEMM2 issuer is the next warp
+constexpr int kAccWsThreads = (kAccG1Warp + 2) * 32;  // 20 warps
+constexpr int kAccSlots = 2;        // scratch slots per CTA for the partial sums of its first images
+constexpr int kAccImgCap = 2048;   // unit -> image ids of this CTA's range cached in shared memory
 
-__host__ __device__ inline size_t ws_acc_stage_bytes(int KP) { return (size_t)2 * 8 * (KP / 4) * 128 + (size_t)2 * (tc_kp2(KP) / 8) * 2048 + 64 * 8 * 4; }
-__host__ __device__ inline size_t ws_acc_smem_bytes(int KP) { return 2 * ws_acc_stage_bytes(KP) + 1024 + 256; }
+// one stage: X hi | X lo (4 frame groups x PX) | XT hi | XT lo (KP2/8 column groups x 1024) | cfs[8][32]
+__host__ __device__ inline size_t ws_acc_stage_bytes(int KP) {
+  return (size_t)2 * (kAccSub / 8) * (KP / 4) * 128 + (size_t)2 * (tc_kp2(KP) / 8) * (kAccSub / 4) * 128 + kAccSub * 8 * 4;
+}
+// stages | barriers (256 B) | image ids | S accumulator [KP2][128] floats | 1 KB alignment slack
+__host__ __device__ inline size_t ws_acc_smem_bytes(int KP) {
+  return kAccStages * ws_acc_stage_bytes(KP) + 1024 + 256 + kAccImgCap * 4 + (size_t)tc_kp2(KP) * 128 * 4;
+}
 
+template <bool DBG>
 __global__ void __launch_bounds__(kAccWsThreads, 1)
 k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restrict__ frame_ids, const float *__restrict__ x32,
            const float *__restrict__ images, const float *__restrict__ kcT, const float *__restrict__ logb,
            const float *__restrict__ gamma, int N, int M, int G, int D, int DP, double *__restrict__ stats,
-           int64_t stats_stride, int64_t off_S0, int64_t off_S1, int64_t off_S2, long long *__restrict__ tdbg) {
+           int64_t stats_stride, int64_t off_S0, int64_t off_S1, int64_t off_S2, float *__restrict__ scratch,
+           long long *__restrict__ tdbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  auto stamp = [&](int i, int slot) {  // latest arrival over the warps of a role
-    if (tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) atomicMax((unsigned long long *)&tdbg[i * 8 + slot], (unsigned long long)clock64());
+  if (DBG && tdbg && blockIdx.x == 0 && threadIdx.x == 0) tdbg[1024] = clock64();
+  auto stamp = [&](int i, int slot) {  // latest arrival over the warps of a role (diagnostic build only)
+    if (DBG && tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) atomicMax((unsigned long long *)&tdbg[i * 16 + slot], (unsigned long long)clock64());
   };
+  constexpr int NST = kAccStages, SUB = kAccSub;
   const int KP = 2 * DP, KP2 = tc_kp2(KP), NSLAB = KP / 8, nq = DP / 4;
-  const uint32_t PX = (uint32_t)(KP / 4) * 128;
-  const uint32_t x_bytes = 8 * PX, xt_bytes = (uint32_t)(KP2 / 8) * 2048;
-  const uint32_t stage_bytes = 2 * x_bytes + 2 * xt_bytes + 64 * 8 * 4;
-  uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 2 * stage_bytes);
-  uint64_t *x_full = bars, *x_free = bars + 2, *d1_full = bars + 4, *w_full = bars + 6, *s_full = bars + 8, *s_free = bars + 9,
-           *wimg_full = bars + 10;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 11);
+  const uint32_t PX = (uint32_t)(KP / 4) * 128;            // X: bytes per group of 8 frames
+  constexpr uint32_t PT = (SUB / 4) * 128;                 // XT: bytes per group of 8 columns
+  const uint32_t x_bytes = (SUB / 8) * PX, xt_bytes = (uint32_t)(KP2 / 8) * PT;
+  const uint32_t cfs_off = 2 * x_bytes + 2 * xt_bytes;
+  const uint32_t stage_bytes = cfs_off + SUB * 8 * 4;
+  // everything in shared memory is addressed through the 32-bit shared window
+  const uint32_t sm0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = sm0 + NST * stage_bytes;
+  const uint32_t x_full = bars, x_free = bars + 8 * NST, d1_full = bars + 16 * NST, w_full = bars + 24 * NST, s_full = bars + 32 * NST,
+                 s_free = s_full + 8, wimg_full = s_full + 16, tmem_slot = s_full + 24;
+  const uint32_t simg = bars + 256;                        // int32 [kAccImgCap]
+  const uint32_t sacc = simg + kAccImgCap * 4;             // float [KP2][128]: S per (column, Gaussian lane)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    for (int s = 0; s < 2; s++) {
-      mbar_init(&x_full[s], 256);   // X and XT loaders
-      mbar_init(&x_free[s], 1);     // tcgen05.commit after GEMM2
-      mbar_init(&d1_full[s], 1);    // tcgen05.commit after GEMM1
-      mbar_init(&w_full[s], 256);   // epilogue threads
-    }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(wimg_full, 256);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 16) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem0 = *tmem_slot;
-
   const int per = (nunits + gridDim.x - 1) / gridDim.x;
   const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
   const int n_my = max(0, u_end - u_begin);
-  auto img_at = [&](int ui) -> int { return (ui >= u_begin && ui < u_end) ? __ldg(&units[ui].img) : -1; };
+  // The MMA issuers and the epilogue look at image boundaries several times per unit; the ids are staged once.
+  for (int k = tid; k < min(n_my, kAccImgCap); k += kAccWsThreads)
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(simg + 4 * k), "r"(__ldg(&units[u_begin + k].img)) : "memory");
+  for (int k = tid; k < KP2 * 128; k += kAccWsThreads) sts_f32(sacc + 4 * k, 0.f);
+
+  if (tid == 0) {
+    auto init = [](uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); };
+    for (int s = 0; s < NST; s++) {
+      init(x_full + 8 * s, 2 * kAccLdWarps * 32);   // X and XT loaders
+      init(x_free + 8 * s, 1);     // tcgen05.commit after GEMM2
+      init(d1_full + 8 * s, 1);    // tcgen05.commit after GEMM1
+      init(w_full + 8 * s, 256);   // epilogue threads
+    }
+    init(s_full, 1);
+    init(s_free, 256);
+    init(wimg_full, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kAccG1Warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem0 = (uint32_t)lds_i32(tmem_slot);
+  if (DBG && tdbg && blockIdx.x == 0 && threadIdx.x == 0) tdbg[1025] = clock64();
+
+  auto img_at = [&](int ui) -> int {
+    if (ui < u_begin || ui >= u_end) return -1;
+    return (ui - u_begin < kAccImgCap) ? lds_i32(simg + 4 * (ui - u_begin)) : __ldg(&units[ui].img);
+  };
   auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? units[ui] : TcTile{0, 0, -1, 0, 0, 0}; };
 
-  if (warp >= 8 && warp < 12) {
+  if (warp >= 8 && warp < 8 + kAccLdWarps) {
     // =================================== X LOADERS ===================================
+    // thread <-> (frame row xr, column part): float4 [xq0, xq1) of the row, and the weight exponents of
+    // states part, part + NPART of that frame.  Global loads run ahead of the expansion: unit descriptor
+    // (i+3) -> frame id (i+2) -> operands (i+1), while unit i is split and stored.
     const int t = tid - 256;
-    const int xr = t & 63, xq0 = (t >> 6) * ((nq + 1) / 2);  // row xr, float4 [xq0, xq1)
-    const int xq1 = min(nq, xq0 + (nq + 1) / 2);
-    constexpr int kXQ = 5;                                   // DP <= 40
-    struct Pre { float4 x[kXQ]; float gm[8], lb[8]; };
-    auto fid_of = [&](const TcTile &u) -> int { return (xr < u.nrows) ? __ldg(frame_ids + u.row0 + xr) : -1; };
+    constexpr int NPART = kAccLdWarps * 32 / SUB;            // 5
+    const int xr = t & (SUB - 1), part = t / SUB;
+    const int qper = (nq + NPART - 1) / NPART;
+    const int xq0 = min(nq, part * qper), xq1 = min(nq, xq0 + qper);  // float4 [xq0, xq1)
+    constexpr int kXQ = (10 + NPART - 1) / NPART;            // DP <= 40
+    constexpr int kCS = (8 + NPART - 1) / NPART;             // states per thread
+    struct Pre { float4 x[kXQ]; float gm[kCS], lb[kCS]; };
+    auto desc_at = [&](int ui) -> int2 { return ui < u_end ? __ldg(reinterpret_cast<const int2 *>(units + ui)) : make_int2(0, 0); };  // (row0, nrows)
+    auto fid_of = [&](const int2 &u) -> int { return (xr < u.y) ? __ldg(frame_ids + u.x + xr) : -1; };
     auto load_pre = [&](int f, Pre &p) {
       const float4 *src = reinterpret_cast<const float4 *>(x32 + (int64_t)(f < 0 ? 0 : f) * DP);
 #pragma unroll
       for (int j = 0; j < kXQ; j++) p.x[j] = (f >= 0 && xq0 + j < xq1) ? __ldg(src + xq0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < 8; s++) {
-        const bool ok = t < 64 && f >= 0 && s < N;
-        p.gm[s] = ok ? __ldg(gamma + (int64_t)f * N + s) : 0.f;
-        p.lb[s] = ok ? __ldg(logb + (int64_t)f * N + s) : 0.f;
+      for (int c = 0; c < kCS; c++) {
+        const int st = part + c * NPART;
+        const bool ok = f >= 0 && st < N;
+        p.gm[c] = ok ? __ldg(gamma + (int64_t)f * N + st) : 0.f;
+        p.lb[c] = ok ? __ldg(logb + (int64_t)f * N + st) : 0.f;
       }
     };
-    TcTile d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
-    int f1 = fid_of(d1);
-    Pre cur, nxt;
-    load_pre(fid_of(unit_at(u_begin)), cur);
     const uint32_t rbase = (uint32_t)(xr & 7) * 16 + (uint32_t)(xr >> 3) * PX;
-    for (int i = 0; i < n_my; i++) {
-      const int s = i & 1;
-      load_pre(f1, nxt);                               // operands of unit i+1
-      const int f2 = fid_of(d2);                       // frame id of unit i+2
-      const TcTile d3 = unit_at(u_begin + i + 3);      // descriptor of unit i+3
+    auto expand = [&](int i, const Pre &cur) {
+      const int s = i % NST;
       if (warp == 8) stamp(i, 0);
-      mbar_wait(&x_free[s], ((i >> 1) & 1) ^ 1);       // stage s: GEMM2 of unit i-2 has retired
+      mbar_wait_a(x_free + 8 * s, ((i / NST) & 1) ^ 1);  // stage s: GEMM2 of unit i-NST has retired
       if (warp == 8) stamp(i, 1);
-      const uint32_t Xh = smem_u32(sm) + (uint32_t)s * stage_bytes, Xl = Xh + x_bytes;
-      float *cfs = reinterpret_cast<float *>(sm + (size_t)s * stage_bytes + 2 * x_bytes + 2 * xt_bytes);
+      const uint32_t Xh = sm0 + (uint32_t)s * stage_bytes, Xl = Xh + x_bytes;
 #pragma unroll
       for (int j = 0; j < kXQ; j++) {
         if (xq0 + j < xq1) {
@@ -495,186 +575,204 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
           st_shared_v4(Xl + o, l);
         }
       }
-      if (t < 64) {  // weight exponent of frame t per state: log2(gamma) - logb log2(e); -inf = no weight
+      // weight exponent of frame xr per state: log2(gamma) - logb log2(e); -inf = no weight.  cfs[state][frame]
+      const uint32_t cfs = Xh + cfs_off + 4 * xr;
 #pragma unroll
-        for (int st = 0; st < 8; st++) {
+      for (int c = 0; c < kCS; c++) {
+        const int st = part + c * NPART;
+        if (st < 8) {
           float cf = kNegInf;
-          if (st < N && cur.gm[st] > 0.f && cur.lb[st] > kNegInf) cf = __log2f(cur.gm[st]) - cur.lb[st] * 1.4426950408889634f;
-          cfs[t * 8 + st] = cf;
+          if (cur.gm[c] > 0.f && cur.lb[c] > kNegInf) cf = __log2f(cur.gm[c]) - cur.lb[c] * 1.4426950408889634f;
+          sts_f32(cfs + st * SUB * 4, cf);
         }
       }
       fence_async_smem();
-      mbar_arrive(&x_full[s]);
+      mbar_arrive_a(x_full + 8 * s);
       stamp(i, 2);
-      cur = nxt;
-      d1 = d2; d2 = d3; f1 = f2;
+    };
+    int2 d1 = desc_at(u_begin + 1), d2 = desc_at(u_begin + 2);
+    int f1 = fid_of(d1);
+    Pre pa, pb;
+    load_pre(fid_of(desc_at(u_begin)), pa);
+    for (int i = 0; i < n_my; i += 2) {  // two units per trip: the prefetch buffers swap roles instead of being copied
+      load_pre(f1, pb);                                // operands of unit i+1
+      int f2 = fid_of(d2);                             // frame id of unit i+2
+      int2 d3 = desc_at(u_begin + i + 3);              // descriptor of unit i+3
+      expand(i, pa);
+      if (i + 1 < n_my) {
+        load_pre(f2, pa);
+        f1 = fid_of(d3);
+        d2 = desc_at(u_begin + i + 4);
+        expand(i + 1, pb);
+      }
     }
-  } else if (warp >= 12 && warp < 16) {
+  } else if (warp >= 8 + kAccLdWarps && warp < 8 + 2 * kAccLdWarps) {
     // =================================== XT LOADERS ===================================
-    const int t = tid - 384;
-    const int fg = t >> 3, nl = t & 7;  // frames 4fg..4fg+3, columns nl + 8k
-    constexpr int kTK = 5;              // DP <= 40
+    const int t = tid - (256 + kAccLdWarps * 32);
+    constexpr int NFG = SUB / 4, NNL = kAccLdWarps * 32 / NFG;  // 8 frame groups of 4; 20 column lanes
+    const int fg = t / NNL, nl = t % NNL;                       // frames 4fg..4fg+3, columns nl + NNL k
+    constexpr int kTK = (40 + NNL - 1) / NNL;                   // DP <= 40
     struct Fids { int ft[4]; };
-    auto fids_of = [&](const TcTile &u) -> Fids {
+    auto desc_at = [&](int ui) -> int2 { return ui < u_end ? __ldg(reinterpret_cast<const int2 *>(units + ui)) : make_int2(0, 0); };
+    auto fids_of = [&](const int2 &u) -> Fids {
       Fids f;
 #pragma unroll
-      for (int j = 0; j < 4; j++) f.ft[j] = (4 * fg + j < u.nrows) ? __ldg(frame_ids + u.row0 + 4 * fg + j) : -1;
+      for (int j = 0; j < 4; j++) f.ft[j] = (4 * fg + j < u.y) ? __ldg(frame_ids + u.x + 4 * fg + j) : -1;
       return f;
     };
     struct Pre { float xt[kTK][4]; };
     auto load_pre = [&](const Fids &f, Pre &p) {
 #pragma unroll
-      for (int k = 0; k < kTK; k++)
+      for (int j = 0; j < 4; j++) {
+        const float *src = x32 + (int64_t)(f.ft[j] < 0 ? 0 : f.ft[j]) * DP + nl;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          p.xt[k][j] = (f.ft[j] >= 0 && nl + 8 * k < DP) ? __ldg(x32 + (int64_t)f.ft[j] * DP + nl + 8 * k) : 0.f;
+        for (int k = 0; k < kTK; k++) p.xt[k][j] = (f.ft[j] >= 0 && nl + NNL * k < DP) ? __ldg(src + NNL * k) : 0.f;
+      }
     };
-    TcTile d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
-    Fids f1 = fids_of(d1);
-    Pre cur, nxt;
-    load_pre(fids_of(unit_at(u_begin)), cur);
-    for (int i = 0; i < n_my; i++) {
-      const int s = i & 1;
-      load_pre(f1, nxt);
-      const Fids f2 = fids_of(d2);
-      const TcTile d3 = unit_at(u_begin + i + 3);
-      mbar_wait(&x_free[s], ((i >> 1) & 1) ^ 1);
-      const uint32_t XTh = smem_u32(sm) + (uint32_t)s * stage_bytes + 2 * x_bytes, XTl = XTh + xt_bytes;
+    auto expand = [&](int i, const Pre &cur) {
+      const int s = i % NST;
+      mbar_wait_a(x_free + 8 * s, ((i / NST) & 1) ^ 1);
+      const uint32_t XTh = sm0 + (uint32_t)s * stage_bytes + 2 * x_bytes, XTl = XTh + xt_bytes;
 #pragma unroll
       for (int k = 0; k < kTK; k++) {  // rows n (x) and n + DP (x^2), 16-byte chunk = frames 4fg..4fg+3
-        const int n = nl + 8 * k;
+        const int n = nl + NNL * k;
         if (n < DP) {
           float4 h, l;
           split_tf32_fast(cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1], h.y, l.y);
           split_tf32_fast(cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3], h.w, l.w);
-          uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+          uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * PT;
           st_shared_v4(XTh + o, h);
           st_shared_v4(XTl + o, l);
           split_tf32_fast(cur.xt[k][0] * cur.xt[k][0], h.x, l.x); split_tf32_fast(cur.xt[k][1] * cur.xt[k][1], h.y, l.y);
           split_tf32_fast(cur.xt[k][2] * cur.xt[k][2], h.z, l.z); split_tf32_fast(cur.xt[k][3] * cur.xt[k][3], h.w, l.w);
           const int n2 = n + DP;
-          o = (uint32_t)(n2 & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n2 >> 3) * 2048;
+          o = (uint32_t)(n2 & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n2 >> 3) * PT;
           st_shared_v4(XTh + o, h);
           st_shared_v4(XTl + o, l);
         }
       }
       if (KP2 > KP && nl == 0) {  // pad rows of GEMM2's N
         for (int n = KP; n < KP2; n++) {
-          const uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * 2048;
+          const uint32_t o = (uint32_t)(n & 7) * 16 + (uint32_t)fg * 128 + (uint32_t)(n >> 3) * PT;
           st_shared_v4(XTh + o, make_float4(0.f, 0.f, 0.f, 0.f));
           st_shared_v4(XTl + o, make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
       fence_async_smem();
-      mbar_arrive(&x_full[s]);
+      mbar_arrive_a(x_full + 8 * s);
       stamp(i, 2);
-      cur = nxt;
-      d1 = d2; d2 = d3; f1 = f2;
+    };
+    int2 d1 = desc_at(u_begin + 1), d2 = desc_at(u_begin + 2);
+    Fids f1 = fids_of(d1);
+    Pre pa, pb;
+    load_pre(fids_of(desc_at(u_begin)), pa);
+    for (int i = 0; i < n_my; i += 2) {
+      load_pre(f1, pb);
+      Fids f2 = fids_of(d2);
+      int2 d3 = desc_at(u_begin + i + 3);
+      expand(i, pa);
+      if (i + 1 < n_my) {
+        load_pre(f2, pa);
+        f1 = fids_of(d3);
+        d2 = desc_at(u_begin + i + 4);
+        expand(i + 1, pb);
+      }
     }
-  } else if (warp == 16) {
-    // =================================== MMA ISSUER ===================================
-    const uint32_t idesc1 = make_idesc_tf32(128, kAccSub), idesc2 = make_idesc_tf32(128, KP2);
+  } else if (warp == kAccG1Warp) {
+    // =================================== GEMM1 ISSUER ===================================
+    // GEMM1(i) needs x_full(i) -- which the loaders give only after GEMM2(i-NST) has retired, so the L / w
+    // stage it overwrites is free -- and, for the first unit of an image, that image's W in tensor memory.
+    // The two GEMMs are issued by two different warps: one warp's instruction stream (descriptor
+    // arithmetic, barrier polls) was the serial bottleneck of the whole pipeline when it issued both.
+    const uint32_t idesc1 = make_idesc_tf32(128, SUB);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
-    // GEMM1(i) needs x_full(i) (and the image's W); GEMM2(j) needs w_full(j) (and S drained).  Whichever
-    // is ready goes first; GEMM1 may run at most one unit ahead of GEMM2 (two TMEM / smem stages).
-    int cnt = 0, ndrain = 0, nimg = 0, g1 = 0, g2 = 0;
-    bool need_s_free = false;
-    // image boundaries of the units at the two cursors, kept in registers (one load per advance)
-    int img_g1m = -1, img_g1 = img_at(u_begin), img_g2 = img_g1, img_g2p = img_at(u_begin + 1);
-    auto issue_g1 = [&](int i) {
-      const int s = i & 1;
+    int nimg = 0, img_prev = -1;
+    for (int i = 0; i < n_my; i++) {
+      const int s = i % NST;
+      const int img = img_at(u_begin + i);
+      mbar_wait_a(x_full + 8 * s, (i / NST) & 1);
+      if (img != img_prev) { mbar_wait_a(wimg_full, nimg & 1); nimg++; img_prev = img; }
+      stamp(i, 3);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint8_t *Xh = sm + (size_t)s * stage_bytes;
-        const uint64_t bh = make_smem_desc2(smem_u32(Xh), 128, PX), bl = make_smem_desc2(smem_u32(Xh + x_bytes), 128, PX);
-        uint32_t accf = 0;
-        for (int p = 0; p < 3; p++) {  // Wh*Xh, Wl*Xh, Wh*Xl
-          const uint32_t a0 = tb + kAccTmW + ((p == 1) ? KP : 0);
-          const uint64_t b0 = (p == 2) ? bl : bh;
-          for (int j = 0; j < NSLAB; j++) {
-            tc_mma_tf32_ts(tb + (uint32_t)s * 64, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);
-            accf = 1;
+        const uint32_t Xh = sm0 + (uint32_t)s * stage_bytes;
+        const uint64_t bh = make_smem_desc2(Xh, 128, PX), bl = make_smem_desc2(Xh + x_bytes, 128, PX);
+        const uint32_t d = tb + (uint32_t)s * SUB, wh = tb + kAccTmW, wl = wh + KP;
+        if (NSLAB == 10) {  // D = 39: fully unrolled, addresses are immediates
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, wh + j * 8, bh + (uint64_t)(j * 16), idesc1, j > 0);  // Wh*Xh
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, wl + j * 8, bh + (uint64_t)(j * 16), idesc1, 1);      // Wl*Xh
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, wh + j * 8, bl + (uint64_t)(j * 16), idesc1, 1);      // Wh*Xl
+        } else {
+          uint32_t accf = 0;
+          for (int p = 0; p < 3; p++) {
+            const uint32_t a0 = (p == 1) ? wl : wh;
+            const uint64_t b0 = (p == 2) ? bl : bh;
+            for (int j = 0; j < NSLAB; j++) {
+              tc_mma_tf32_ts(d, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc1, accf);
+              accf = 1;
+            }
           }
         }
-        tc_commit(&d1_full[s]);
+        tc_commit_a(d1_full + 8 * s);
       }
       __syncwarp();
-    };
-    auto issue_g2 = [&](int j) {
-      const int sj = j & 1;
+      stamp(i, 4);
+    }
+  } else if (warp == kAccG1Warp + 1) {
+    // =================================== GEMM2 ISSUER ===================================
+    // GEMM2(j) needs the weights of unit j (w_full) and, after a drain, S handed back by the epilogue.
+    const uint32_t idesc2 = make_idesc_tf32(128, KP2);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
+    int cnt = 0, ndrain = 0;
+    bool need_s_free = false;
+    for (int j = 0; j < n_my; j++) {
+      const int sj = j % NST;
+      const bool last_of_img = img_at(u_begin + j + 1) != img_at(u_begin + j);  // also true for this CTA's last unit
+      mbar_wait_a(w_full + 8 * sj, (j / NST) & 1);
+      if (need_s_free) { mbar_wait_a(s_free, (ndrain - 1) & 1); need_s_free = false; }
+      stamp(j, 8);
       tc_fence_after();
       cnt++;
-      const bool drain = img_g2p != img_g2 || cnt == kAccDrain;  // last unit of its image (or of this CTA), or S is due
+      const bool drain = last_of_img || cnt == kAccDrain;
       if (elect_one_sync()) {
-        const uint8_t *XTh = sm + (size_t)sj * stage_bytes + 2 * x_bytes;
-        const uint64_t bh = make_smem_desc2(smem_u32(XTh), 128, 2048), bl = make_smem_desc2(smem_u32(XTh + xt_bytes), 128, 2048);
-        uint32_t accf = cnt > 1 ? 1u : 0u;
-        for (int p = 0; p < 3; p++) {  // wh*Xh, wl*Xh, wh*Xl
-          const uint32_t a0 = tb + (uint32_t)sj * 64 + ((p == 1) ? 128 : 0);
-          const uint64_t b0 = (p == 2) ? bl : bh;
-          for (int k = 0; k < kAccSub / 8; k++) {
-            tc_mma_tf32_ts(tb + 256, a0 + k * 8, b0 + (uint64_t)(k * 16), idesc2, accf);
-            accf = 1;
-          }
-        }
-        tc_commit(&x_free[sj]);
-        if (drain) tc_commit(s_full);
+        const uint32_t XTh = sm0 + (uint32_t)sj * stage_bytes + 2 * x_bytes;
+        const uint64_t bh = make_smem_desc2(XTh, 128, PT), bl = make_smem_desc2(XTh + xt_bytes, 128, PT);
+        const uint32_t wh = tb + (uint32_t)sj * SUB, wl = wh + 128, d = tb + 256;
+#pragma unroll
+        for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wh + k * 8, bh + (uint64_t)(k * 16), idesc2, (cnt > 1 || k > 0) ? 1u : 0u);  // wh*Xh
+#pragma unroll
+        for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wl + k * 8, bh + (uint64_t)(k * 16), idesc2, 1);                              // wl*Xh
+#pragma unroll
+        for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wh + k * 8, bl + (uint64_t)(k * 16), idesc2, 1);                              // wh*Xl
+        if (DBG && tdbg && blockIdx.x == 0 && j < 64) tdbg[j * 16 + 9] = clock64();
+        tc_commit_a(x_free + 8 * sj);
+        if (drain) tc_commit_a(s_full);
       }
       __syncwarp();
       if (drain) { ndrain++; need_s_free = true; cnt = 0; }
-    };
-    while (g2 < n_my) {
-      bool did = false;
-      const bool first_g1 = img_g1 != img_g1m;
-      // a new image's first GEMM1 only after the old image's last GEMM2 has been issued
-      if (g1 < n_my && g1 - g2 <= 1 && (!first_g1 || g1 == g2)) {
-        bool ok = mbar_try(&x_full[g1 & 1], (g1 >> 1) & 1);
-        if (ok && first_g1) ok = mbar_try(wimg_full, nimg & 1);
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) {
-          if (first_g1) nimg++;
-          stamp(g1, 3);
-          issue_g1(g1);
-          stamp(g1, 4);
-          g1++;
-          img_g1m = img_g1;
-          img_g1 = img_at(u_begin + g1);
-          did = true;
-        }
-      }
-      if (!did && g2 < g1) {
-        bool ok = mbar_try(&w_full[g2 & 1], (g2 >> 1) & 1);
-        if (ok && need_s_free) ok = mbar_try(s_free, (ndrain - 1) & 1);
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) {
-          need_s_free = false;
-          issue_g2(g2);
-          stamp(g2, 5);
-          g2++;
-          img_g2 = img_g2p;
-          img_g2p = img_at(u_begin + g2 + 1);
-        }
-      }
+      stamp(j, 5);
     }
   } else {
     // =================================== EPILOGUE (warps 0-7) ===================================
     const int q = warp & 3, hb = warp >> 2;  // TMEM lane quarter; frame half (and column half of S)
     const int row = 32 * q + lane;
     const uint32_t trow = (uint32_t)(32 * q) << 16;
-    constexpr int kMaxCol = 40;  // KP2 <= 80 (tc_acc_fits): 5 groups of 8 columns per thread
+    constexpr int FH = SUB / 2;  // frames per thread and unit (16)
+    static_assert(FH == 16, "one 16-column TMEM load per thread");
     const int nc8 = KP2 / 8;
     const int c8_beg = hb ? (nc8 + 1) / 2 : 0, c8_end = hb ? nc8 : (nc8 + 1) / 2;
-    float acc[kMaxCol];
-#pragma unroll
-    for (int k = 0; k < kMaxCol; k++) acc[k] = 0.f;
-    int cnt = 0, ndrain = 0;
+    const uint32_t my_acc = sacc + 4 * row;  // + 512 per column
+    int cnt = 0, ndrain = 0, nflush = 0;
     float kcr = kNegInf;
     int st = 0, cur_v = 0, cur_rb = 0;
+    bool dead = false;  // every lane of this warp is a pad row of the current Gaussian block
+    int img_prev = -1, img = img_at(u_begin), img_next = img_at(u_begin + 1);
     for (int i = 0; i < n_my; i++) {
-      const int ui = u_begin + i, s = i & 1;
-      const int img = img_at(ui);
-      const bool first = (i == 0) || img != img_at(ui - 1);
-      const bool last = (i == n_my - 1) || img != img_at(ui + 1);
+      const int ui = u_begin + i, s = i % NST;
+      const bool first = img != img_prev, last = img != img_next;
       if (first) {  // W (hi | lo) of this (model, Gaussian block) -> TMEM, one Gaussian per lane; halves split the columns
         const TcTile unit = units[ui];
         cur_v = unit.v; cur_rb = unit.pad;
@@ -690,82 +788,141 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(wimg_full);
+        mbar_arrive_a(wimg_full);
         const int g = cur_rb * 128 + row;
         kcr = (g < G) ? __ldg(kcT + (size_t)img * 128 + row) : kNegInf;
         st = min(g / M, 7);
+        dead = cur_rb * 128 + 32 * q >= G;
       }
-      mbar_wait(&d1_full[s], (i >> 1) & 1);
+      mbar_wait_a(d1_full + 8 * s, (i / NST) & 1);
       if (warp == 0) stamp(i, 6);
-      tc_fence_after();
-      const float *cfs = reinterpret_cast<const float *>(sm + (size_t)s * stage_bytes + 2 * x_bytes + 2 * xt_bytes);
-      {  // my 32 frames: accumulator columns [32 hb, 32 hb + 32)
-        uint32_t v[2][16];
-#pragma unroll
-        for (int c = 0; c < 2; c++) tmem_ld16_nowait(tmem0 + (uint32_t)s * 64 + trow + (hb * 2 + c) * 16, v[c]);
+      if (!dead) {  // my FH frames: accumulator columns [FH hb, FH hb + FH) of stage s.  (The rows of a dead warp
+                    // feed only pad rows of S, which are never read.)
+        tc_fence_after();
+        const int c0 = hb * FH;
+        const uint32_t tl = tmem0 + (uint32_t)s * SUB + trow + c0;
+        uint32_t v[16], vl[16];
+        tmem_ld16_nowait(tl, v);
+        const uint32_t cfs = sm0 + (uint32_t)s * stage_bytes + cfs_off + (uint32_t)(st * SUB + c0) * 4;
+        const float4 e0 = lds_v4(cfs), e1 = lds_v4(cfs + 16), e2 = lds_v4(cfs + 32), e3 = lds_v4(cfs + 48);
+        const float ce[16] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2.x, e2.y, e2.z, e2.w, e3.x, e3.y, e3.z, e3.w};
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int c0 = (hb * 2 + c) * 16;
-          uint32_t vl[16];
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const float y = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kcr + cfs[(c0 + j) * 8 + st]);
-            const float w = ex2_approx(y);  // ex2(-inf) = +0 and underflow flushes to 0: no weight; y is never NaN
-            float h, l;
-            split_tf32_fast(w, h, l);
-            v[c][j] = __float_as_uint(h);
-            vl[j] = __float_as_uint(l);
-          }
-          tmem_st16(tmem0 + (uint32_t)s * 64 + trow + c0, v[c]);
-          tmem_st16(tmem0 + 128 + (uint32_t)s * 64 + trow + c0, vl);
+        for (int j = 0; j < 16; j++) {
+          const float y = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kcr + ce[j]);
+          const float w = ex2_approx(y);  // ex2(-inf) = +0 and underflow flushes to 0: no weight; y is never NaN
+          float h, l;
+          split_tf32_fast(w, h, l);
+          v[j] = __float_as_uint(h);
+          vl[j] = __float_as_uint(l);
         }
+        tmem_st16(tl, v);
+        tmem_st16(tl + 128, vl);
+        tmem_wait_st();
+        tc_fence_before();
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&w_full[s]);
+      mbar_arrive_a(w_full + 8 * s);
       stamp(i, 7);
       cnt++;
-      if (last || cnt == kAccDrain) {  // S: TMEM (FP32, truncating) -> registers (round to nearest)
-        mbar_wait(s_full, ndrain & 1);
+      if (last || cnt == kAccDrain) {  // S: TMEM (FP32, truncating) -> shared memory (round to nearest)
+        mbar_wait_a(s_full, ndrain & 1);
         tc_fence_after();
+        for (int c = c8_beg; c < c8_end; c++) {
+          float v[8];
+          tmem_ld8(tmem0 + 256 + trow + c * 8, v);
 #pragma unroll
-        for (int c = 0; c < kMaxCol / 8; c++) {
-          if (c8_beg + c < c8_end) {
-            float v[8];
-            tmem_ld8(tmem0 + 256 + trow + (c8_beg + c) * 8, v);
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc[c * 8 + j] += v[j];
+          for (int j = 0; j < 8; j++) {
+            const uint32_t a = my_acc + (uint32_t)(c * 8 + j) * 512;
+            sts_f32(a, lds_f32(a) + v[j]);
           }
         }
         tc_fence_before();
-        mbar_arrive(s_free);
+        mbar_arrive_a(s_free);
         ndrain++; cnt = 0;
-        if (last) {  // the CTA leaves this (model, Gaussian block): registers -> statistics
-          const int g = cur_rb * 128 + row;
-          double *stp = stats + (int64_t)cur_v * stats_stride;
-#pragma unroll
-          for (int c = 0; c < kMaxCol / 8; c++) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int k = (c8_beg + c) * 8 + j;
-              if (c8_beg + c < c8_end && g < G) {
-                const double a = (double)acc[c * 8 + j];
-                if (k < D) atomicAdd(stp + off_S1 + (int64_t)g * D + k, a);
-                else if (k == D) atomicAdd(stp + off_S0 + g, a);
-                else if (k >= DP && k < DP + D) atomicAdd(stp + off_S2 + (int64_t)g * D + (k - DP), a);
+        if (last) {  // the CTA leaves this (model, Gaussian block)
+          if (scratch && nflush < kAccSlots) {
+            // partial sums of this CTA's first images go to its own scratch slots (plain coalesced stores);
+            // k_finalize_slots adds the slots of every image in a fixed order.  Atomics from all CTAs at once
+            // were a tail of several microseconds, and their order was not reproducible.
+            // slot layout [row][KP2]: the finalising kernel reads rows; 16-byte stores here
+            float *sl = scratch + ((size_t)(blockIdx.x * kAccSlots + nflush) * 128 + row) * KP2;
+            for (int k = c8_beg * 8; k < c8_end * 8; k += 4) {
+              const uint32_t a = my_acc + (uint32_t)k * 512;
+              const float4 val = make_float4(lds_f32(a), lds_f32(a + 512), lds_f32(a + 1024), lds_f32(a + 1536));
+              sts_f32(a, 0.f); sts_f32(a + 512, 0.f); sts_f32(a + 1024, 0.f); sts_f32(a + 1536, 0.f);
+              *reinterpret_cast<float4 *>(sl + k) = val;
+            }
+          } else {  // a CTA that walks through many small images: double atomics, uncontended there
+            const int g = cur_rb * 128 + row;
+            double *stp = stats + (int64_t)cur_v * stats_stride;
+            for (int k = c8_beg * 8; k < c8_end * 8; k++) {
+              const uint32_t a = my_acc + (uint32_t)k * 512;
+              const double val = (double)lds_f32(a);
+              sts_f32(a, 0.f);
+              if (g < G) {
+                if (k < D) atomicAdd(stp + off_S1 + (int64_t)g * D + k, val);
+                else if (k == D) atomicAdd(stp + off_S0 + g, val);
+                else if (k >= DP && k < DP + D) atomicAdd(stp + off_S2 + (int64_t)g * D + (k - DP), val);
               }
-              acc[c * 8 + j] = 0.f;
             }
           }
+          nflush++;
         }
       }
+      img_prev = img; img = img_next; img_next = img_at(ui + 2);
     }
   }
+  if (DBG && tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tdbg[1026 + warp] = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 16) tmem_dealloc(tmem0, 512);
+  if (DBG && tdbg && blockIdx.x == 0 && threadIdx.x == 0) tdbg[1050] = clock64();
+  if (warp == kAccG1Warp) tmem_dealloc(tmem0, 512);
+}
+
+// Adds the scratch slots of k_accum_ws to the statistics (in double, fixed order) and finishes them as
+// k_finalize_stats does: S1 += ctr S0 (features were centred), S2 = sum w x^2 - 2 m sum w x + m^2 sum w with
+// m = mu_old - ctr (the reference's sum w (x - mu_old)^2, T-FS:1716-1719).  One block = 4 whole Gaussians of
+// one model (thread = (Gaussian, dimension)), so that S0 is read by everyone before one thread rewrites it.
+__global__ void __launch_bounds__(256)
+k_finalize_slots(double *__restrict__ stats, int64_t stats_stride, int G, int D, int DP, int KP2, int nRB, int64_t off_S0,
+                 int64_t off_S1, int64_t off_S2, const double *__restrict__ ctr, const double *__restrict__ mu,
+                 const float *__restrict__ scratch, const int32_t *__restrict__ slot_start, const int32_t *__restrict__ slot_ids) {
+  const int v = blockIdx.y, g = blockIdx.x * 4 + (threadIdx.x >> 6), d = threadIdx.x & 63;
+  const bool live = g < G, lived = live && d < D;
+  double *st = stats + (int64_t)v * stats_stride;
+  // the 4 Gaussians of a block lie in one block of 128 (4 divides 128): one slot list, staged in shared memory so
+  // that the scratch loads below do not wait on the list
+  __shared__ int32_t sslot[256];
+  const int img = v * nRB + ((blockIdx.x * 4) >> 7);
+  const int k0 = slot_start[img], nk = slot_start[img + 1] - k0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const int row = g & 127;
+  if (live) {
+    s0 = st[off_S0 + g];
+    if (lived) { s1 = st[off_S1 + (int64_t)g * D + d]; s2 = st[off_S2 + (int64_t)g * D + d]; }
+  }
+  for (int kb = 0; kb < nk; kb += 256) {
+    __syncthreads();
+    if (kb + (int)threadIdx.x < nk) sslot[threadIdx.x] = slot_ids[k0 + kb + threadIdx.x];
+    __syncthreads();
+    const int kn = min(256, nk - kb);
+    if (live) {
+#pragma unroll 4
+      for (int k = 0; k < kn; k++) {
+        const float *sl = scratch + ((size_t)sslot[k] * 128 + row) * KP2;
+        s0 += (double)sl[D];
+        if (lived) { s1 += (double)sl[d]; s2 += (double)sl[DP + d]; }
+      }
+    }
+  }
+  __syncthreads();
+  if (lived) {
+    const double m = mu[((int64_t)v * G + g) * D + d] - ctr[d];
+    st[off_S2 + (int64_t)g * D + d] = s2 - 2.0 * m * s1 + m * m * s0;
+    st[off_S1 + (int64_t)g * D + d] = s1 + ctr[d] * s0;
+  }
+  if (live && d == 0) st[off_S0 + g] = s0;
 }
 
 }  // namespace hmmk
