@@ -3,9 +3,9 @@
 //
 // The recursion over time is a dependent chain; what bounds it is the latency of one step, not
 // throughput.  So one THREAD owns one utterance and keeps the whole state vector in registers
-// (no shuffles, no shared memory on the chain), the forward and the backward chains of an
-// utterance run concurrently in two different warps, and each scales by an exact power of two taken
-// from the exponent field of the step's sum (two integer instructions instead of a division):
+// (no shuffles on the chain), the forward and the backward chains of an utterance run concurrently in
+// two different warps, and each step rescales by an exact power of two taken from the largest exponent
+// field of the step's components (integer instructions only; no division, no logarithm, no sum):
 //   forward :  z_t = ((z_{t-1} A) o b~_t) 2^-e_t      b~_i(t) = exp(logb_i(t) - m_t), m_t = max_i logb_i(t)
 //   backward:  w_t = (A (b~_{t+1} o w_{t+1})) 2^-e'_t  w_{T-1} = [0,..,0,1]   (final state only, T-FS:1484)
 // Any positive per-frame scaling gives the same posteriors; the reference's c_t-scaled quantities
@@ -15,19 +15,21 @@
 // with phi = alpha^_{T-1}(N-1) (the reference's beta^ starts from the final state only, so its
 // gammas sum to phi, not to 1), and
 //   log P = sum_t m_t + ln2 sum_t e_t + log z_{T-1}(N-1)      (calc_probability, T-FS:1546-1549).
-// The chain threads never touch global memory for their operands: all eight warps of the CTA stage
-// the next window of kFbWin frames of every utterance of the CTA into shared memory as b~ (double) and
-// m (float) -- forward window from the start of the utterance, backward window from its end -- so a
-// chain step is five LDS.64, the banded matvec, the power-of-two scaling and five STG.64.
-// A second phase (one warp per utterance, lanes over frames) forms gamma and the transition sums.
+// The chain threads never touch global memory for their operands: the six other warps of the CTA stage
+// the NEXT window of kFbWin frames of every utterance of the CTA into shared memory as b~ (double) while
+// the chains consume the current one (two buffers) -- forward window from the start of the utterance,
+// backward window from its end -- so a chain step is NS LDS.64, the banded matvec, the power-of-two
+// scaling and two 16-byte stores of the scaled vector in single precision (rows of 8 floats).
+// A second phase (one warp per utterance, lanes over frames) forms gamma, the transition sums and sum m_t.
 #pragma once
 #include "kernels.cuh"
 
 namespace hmmk {
 
 constexpr int kFbUtts = 8;        // utterances per CTA
-constexpr int kFbThreads = 256;   // 8 warps: warp 0 = forward chains, warp 1 = backward chains, then all combine
-constexpr int kFbWin = 128;       // frames per staged window
+constexpr int kFbThreads = 256;   // 8 warps: warp 0 = forward chains, warp 1 = backward chains, warps 2-7 stage; then all combine
+constexpr int kFbWin = 64;        // frames per staged window
+constexpr int kFbRow = 8;         // floats per row of the alpha / beta workspaces (NS <= 8)
 
 // exp(y) for y <= 0 as a double: single-precision mantissa accuracy (the log-densities it is fed
 // are single precision), double-precision range.  y < -700 -> 0.
@@ -59,22 +61,53 @@ __device__ __forceinline__ void load_lb(const float *__restrict__ p, float (&l)[
 }
 
 __host__ __device__ inline size_t fb_smem_bytes(int NS) {
-  return (size_t)2 * kFbUtts * (kFbWin * NS + 2) * sizeof(double) + (size_t)kFbUtts * (kFbWin + 1) * sizeof(float);
+  return (size_t)2 * 2 * kFbUtts * (kFbWin * NS + 2) * sizeof(double);  // [buffer][direction][utterance][window]
+}
+
+// 2^-(E - 1023) for the largest exponent field E of the non-negative components v[]; 1 when that field is 0
+// (all zero / denormal) or 0x7ff (inf / NaN).  e = E - 1023 (0 in the degenerate cases).
+template <int NS>
+__device__ __forceinline__ double pow2_scale_max(const double (&v)[NS], int &e) {
+  int be = __double2hiint(v[0]) >> 20;
+#pragma unroll
+  for (int i = 1; i < NS; i++) be = max(be, __double2hiint(v[i]) >> 20);
+  const bool ok = be > 0 && be < 0x7ff;
+  e = ok ? be - 1023 : 0;
+  return __hiloint2double(ok ? (2046 - be) << 20 : 0x3ff00000, 0);
+}
+
+template <int NS>
+__device__ __forceinline__ void store_row(float *__restrict__ p, const double (&z)[NS]) {
+  float f[kFbRow];
+#pragma unroll
+  for (int i = 0; i < kFbRow; i++) f[i] = (i < NS) ? (float)z[i] : 0.f;
+  *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  if (NS > 4) *reinterpret_cast<float4 *>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <int NS>
+__device__ __forceinline__ void load_row(const float *__restrict__ p, double (&z)[NS]) {
+  const float4 a = *reinterpret_cast<const float4 *>(p);
+  float f[kFbRow] = {a.x, a.y, a.z, a.w, 0.f, 0.f, 0.f, 0.f};
+  if (NS > 4) {
+    const float4 b = *reinterpret_cast<const float4 *>(p + 4);
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < NS; i++) z[i] = (double)f[i];
 }
 
 // Outputs: gamma32[F][N] (the reference's alpha^ beta^ / c, T-FS:1709); per-model statistics head
 // (num_trans, den_trans, den_mix, sum_logp, n_utt) by double atomics, one set per utterance;
-// logp_utt[U] (0 for masked utterances).
+// logp_utt[U] (0 for masked utterances).  alpha_ws / beta_ws: float [F][kFbRow] workspaces.
 template <int NS, bool BANDED>
 __global__ void __launch_bounds__(kFbThreads)
 k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-     const double *__restrict__ Aall, int U, double *__restrict__ alpha_ws, double *__restrict__ beta_ws,
+     const double *__restrict__ Aall, int U, float *__restrict__ alpha_ws, float *__restrict__ beta_ws,
      float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
      double *__restrict__ logp_utt) {
   extern __shared__ __align__(16) uint8_t fb_smem[];
-  constexpr int US = kFbWin * NS + 2, MS = kFbWin + 1;  // per-utterance strides, padded: the 8 chain lanes hit 8 different banks
-  double *bf = reinterpret_cast<double *>(fb_smem);            // [2][kFbUtts][US]  b~: 0 = forward window, 1 = backward window
-  float *mf = reinterpret_cast<float *>(bf + 2 * kFbUtts * US);  // [kFbUtts][MS]   m of the forward window
+  constexpr int US = kFbWin * NS + 2;  // per-utterance stride, padded: the 8 chain lanes hit 8 different banks
+  double *bf = reinterpret_cast<double *>(fb_smem);  // [2 buffers][2 directions][kFbUtts][US]  b~
   __shared__ double sA[kFbUtts][NS * NS];
   __shared__ double sphi[kFbUtts], slp[kFbUtts];
   __shared__ int64_t sbase[kFbUtts];
@@ -98,6 +131,43 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
 #pragma unroll
   for (int uu = 0; uu < kFbUtts; uu++) Tmax = max(Tmax, sT[uu]);
 
+  // Staging of window w0 into buffer `buf` by `nthr` threads (index t0): item <-> (direction, utterance, frame).
+  // Three items per pass so that their loads are in flight together.
+  auto stage = [&](int w0, int buf, int t0, int nthr) {
+    constexpr int NIT = 2 * kFbUtts * kFbWin, PASS = 3;
+    double *dstb = bf + (size_t)buf * 2 * kFbUtts * US;
+    for (int it0 = t0; it0 < NIT; it0 += PASS * nthr) {
+      float l[PASS][NS];
+      double *dst[PASS];
+#pragma unroll
+      for (int p = 0; p < PASS; p++) {
+        const int it = it0 + p * nthr;
+        dst[p] = nullptr;
+        if (it < NIT) {
+          const int dir = it / (kFbUtts * kFbWin), rem = it - dir * (kFbUtts * kFbWin);
+          const int uu = rem / kFbWin, k = rem - uu * kFbWin;
+          const int T = sT[uu];
+          if (w0 + k < T) {
+            const int t = dir == 0 ? w0 + k : T - 1 - (w0 + k);
+            load_lb<NS>(logb + (sbase[uu] + t) * NS, l[p]);
+            dst[p] = dstb + (size_t)(dir * kFbUtts + uu) * US + k * NS;
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < PASS; p++) {
+        if (dst[p]) {
+          float m = l[p][0];
+#pragma unroll
+          for (int i = 1; i < NS; i++) m = fmaxf(m, l[p][i]);
+          const float ms = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
+#pragma unroll
+          for (int i = 0; i < NS; i++) dst[p][i] = exp_scaled(l[p][i] - ms);
+        }
+      }
+    }
+  };
+
   // ---------------- phase 1: the two chains of each utterance, one thread each ----------------
   const bool chain = warp < 2 && lane < kFbUtts && sT[lane & (kFbUtts - 1)] > 0;
   const int myT = chain ? sT[lane] : 0;
@@ -108,38 +178,18 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
   double z[NS];  // forward: z_t; backward: w_t
 #pragma unroll
   for (int i = 0; i < NS; i++) z[i] = (warp == 1 && i == NS - 1) ? 1.0 : 0.0;
-  double msum = 0.0;
   int esum = 0;
-  if (chain && warp == 1) {
-#pragma unroll
-    for (int i = 0; i < NS; i++) beta_ws[(mybase + myT - 1) * NS + i] = z[i];  // final state only, T-FS:1484-1490
-  }
-  for (int w0 = 0; w0 < Tmax; w0 += kFbWin) {
-    __syncthreads();  // the previous window has been consumed
-    // stage: thread <-> (direction, utterance, frame of the window)
-    for (int it = tid; it < 2 * kFbUtts * kFbWin; it += kFbThreads) {
-      const int dir = it / (kFbUtts * kFbWin), rem = it - dir * (kFbUtts * kFbWin);
-      const int uu = rem / kFbWin, k = rem - uu * kFbWin;
-      const int T = sT[uu];
-      const int t = dir == 0 ? w0 + k : T - 1 - (w0 + k);
-      if (w0 + k < T) {
-        float l[NS];
-        load_lb<NS>(logb + (sbase[uu] + t) * NS, l);
-        float m = l[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
-        const float ms = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
-        double *dst = bf + (size_t)(dir * kFbUtts + uu) * US + k * NS;
-#pragma unroll
-        for (int i = 0; i < NS; i++) dst[i] = exp_scaled(l[i] - ms);
-        if (dir == 0) mf[uu * MS + k] = m;
-      }
-    }
-    __syncthreads();
-    if (chain && warp == 0) {  // forward: frames w0 .. w0+kFbWin-1
-      const double *bw = bf + (size_t)lane * US;
+  if (chain && warp == 1) store_row<NS>(beta_ws + (mybase + myT - 1) * kFbRow, z);  // final state only, T-FS:1484-1490
+  stage(0, 0, tid, kFbThreads);
+  __syncthreads();
+  for (int w0 = 0, wi = 0; w0 < Tmax; w0 += kFbWin, wi++) {
+    const double *bcur = bf + (size_t)(wi & 1) * 2 * kFbUtts * US;
+    if (warp >= 2) {
+      if (w0 + kFbWin < Tmax) stage(w0 + kFbWin, (wi + 1) & 1, tid - 64, kFbThreads - 64);
+    } else if (chain && warp == 0) {  // forward: frames w0 .. w0+kFbWin-1
+      const double *bw = bcur + (size_t)lane * US;
       const int kend = min(kFbWin, myT - w0);
-      double *ap = alpha_ws + (mybase + w0) * NS;
+      float *ap = alpha_ws + (mybase + w0) * kFbRow;
       for (int k = 0; k < kend; k++) {
         double b[NS], raw[NS];
 #pragma unroll
@@ -162,21 +212,15 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
             raw[i] = aux * b[i];
           }
         }
-        double s = raw[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) s += raw[i];
         int e;
-        const double r = pow2_scale(s, e);
+        const double r = pow2_scale_max<NS>(raw, e);
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-          z[i] = raw[i] * r;
-          ap[(size_t)k * NS + i] = z[i];
-        }
+        for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+        store_row<NS>(ap + (size_t)k * kFbRow, z);
         esum += e;
-        msum += (double)mf[lane * MS + k];
       }
     } else if (chain && warp == 1) {  // backward: step j = w0 + k turns beta~_{T-1-j} into beta~_{T-2-j} with b~ of frame T-1-j
-      const double *bw = bf + (size_t)(kFbUtts + lane) * US;
+      const double *bw = bcur + (size_t)(kFbUtts + lane) * US;
       const int kend = min(kFbWin, myT - 1 - w0);
       for (int k = 0; k < kend; k++) {
         double q[NS], raw[NS];
@@ -195,26 +239,21 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
           }
           raw[i] = aux;
         }
-        double s = raw[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) s += raw[i];
         int e;
-        const double r = pow2_scale(s, e);
-        double *bp = beta_ws + (mybase + myT - 2 - (w0 + k)) * NS;
+        const double r = pow2_scale_max<NS>(raw, e);
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-          z[i] = raw[i] * r;
-          bp[i] = z[i];
-        }
+        for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+        store_row<NS>(beta_ws + (mybase + myT - 2 - (w0 + k)) * kFbRow, z);
       }
     }
+    __syncthreads();  // window consumed, next one staged
   }
   if (chain && warp == 0) {
     double s = z[0];
 #pragma unroll
     for (int i = 1; i < NS; i++) s += z[i];
-    sphi[lane] = z[NS - 1] / s;                                                      // alpha^_{T-1}(N-1)
-    slp[lane] = msum + 0.6931471805599453 * (double)esum + log(z[NS - 1]);          // calc_probability T-FS:1546-1549
+    sphi[lane] = z[NS - 1] / s;                                       // alpha^_{T-1}(N-1)
+    slp[lane] = 0.6931471805599453 * (double)esum + log(z[NS - 1]);  // + sum m_t, added in phase 2
   }
   __syncthreads();
   // ---------------- phase 2: one warp per utterance, lanes over frames ----------------
@@ -230,15 +269,24 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
     const int T = (int)(off[u + 1] - base);
     const double *A = sA[uu];
     const double phi = sphi[uu];
-    double acc_num[NS][2], acc_dt[NS], acc_dm[NS];
+    double acc_num[NS][2], acc_dt[NS], acc_dm[NS], acc_m = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
     for (int t = lane; t < T; t += 32) {
-      double al[NS], g[NS], G = 0.0;
+      double al[NS], be[NS], g[NS], G = 0.0;
+      load_row<NS>(alpha_ws + (base + t) * kFbRow, al);
+      load_row<NS>(beta_ws + (base + t) * kFbRow, be);
+      {
+        float l0[NS];
+        load_lb<NS>(logb + (base + t) * NS, l0);
+        float m = l0[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) m = fmaxf(m, l0[i]);
+        acc_m += (double)m;  // sum_t m_t  (calc_probability); -inf when a frame has no density at all
+      }
 #pragma unroll
       for (int i = 0; i < NS; i++) {
-        al[i] = alpha_ws[(base + t) * NS + i];
-        g[i] = al[i] * beta_ws[(base + t) * NS + i];
+        g[i] = al[i] * be[i];
         G += g[i];
       }
       const double sc = (G > 0.0) ? phi / G : 0.0;  // unreachable final state: no occupancy, as the reference
@@ -254,9 +302,10 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
         float m = l1[0];
 #pragma unroll
         for (int i = 1; i < NS; i++) m = fmaxf(m, l1[i]);
-        double q[NS];
+        double q[NS], b1[NS];
+        load_row<NS>(beta_ws + (base + t + 1) * kFbRow, b1);
 #pragma unroll
-        for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * beta_ws[(base + t + 1) * NS + j];
+        for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * b1[j];
         double Z = 0.0;
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -286,10 +335,12 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
         atomicAdd(st + NS * NS + NS + i, dm);
       }
     }
+    const double msum = warp_sum(acc_m);
     if (lane == 0) {
-      atomicAdd(st + off_sumlogp, slp[uu]);
+      const double lp = slp[uu] + msum;  // calc_probability T-FS:1546-1549
+      atomicAdd(st + off_sumlogp, lp);
       atomicAdd(st + off_sumlogp + 1, 1.0);
-      if (logp_utt) logp_utt[u] = slp[uu];
+      if (logp_utt) logp_utt[u] = lp;
     }
   }
 }

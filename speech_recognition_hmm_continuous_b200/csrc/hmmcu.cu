@@ -1113,8 +1113,8 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     CK(ctx->logb.ensure(sizeof(float) * F * N));
     if (!use_tc) CK(ctx->post.ensure(sizeof(float) * F * G));
     CK(ctx->gamma.ensure(sizeof(float) * F * N));
-    CK(ctx->alpha_ws.ensure(sizeof(double) * F * N));
-    CK(ctx->beta_ws.ensure(sizeof(double) * F * N));
+    CK(ctx->alpha_ws.ensure(sizeof(float) * F * kFbRow));
+    CK(ctx->beta_ws.ensure(sizeof(float) * F * kFbRow));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
     if (ws_emis) {
       if ((rc = ensure_ws_images(ctx, 0)) != HMMCU_OK) return rc;
@@ -1149,12 +1149,12 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       if (ctx->banded) {
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, true><<<blocks, kFbThreads, fsm, ctx->st>>>(
                           ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
-                          ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                          ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       } else {
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, false><<<blocks, kFbThreads, fsm, ctx->st>>>(
                           ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
-                          ctx->alpha_ws.as<double>(), ctx->beta_ws.as<double>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                          ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       }
       LAUNCH_CHECK();
