@@ -709,14 +709,19 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
     CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
     CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
   }
-#define WS_LAUNCH(MPT)                                                                                                             \
+#define WS_LAUNCH2(MPT, DBGT)                                                                                                      \
   do {                                                                                                                             \
-    CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-    k_emis_ws<TRAIN, MPT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,                    \
-                                                               ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),               \
-                                                               ts.images.as<float>(), ctx->N, MPd, ctx->DP, ts.TN, logb, fbase,    \
-                                                               ldb, ctx->V * ctx->N, ts.SCt,                                       \
-                                                               (ctx->debug_acc & 2) ? (long long *)ctx->acc_dbg.p : nullptr);      \
+    CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT, DBGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    k_emis_ws<TRAIN, MPT, DBGT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,              \
+                                                                     ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),         \
+                                                                     ts.images.as<float>(), ctx->N, MPd, ctx->DP, ts.TN, logb,     \
+                                                                     fbase, ldb, ctx->V * ctx->N, ts.SCt,                          \
+                                                                     DBGT ? (long long *)ctx->acc_dbg.p : nullptr);                \
+  } while (0)
+#define WS_LAUNCH(MPT)                                         \
+  do {                                                         \
+    if (ctx->debug_acc & 2) WS_LAUNCH2(MPT, true);             \
+    else WS_LAUNCH2(MPT, false);                               \
   } while (0)
   switch (MPd) {
     case 1: WS_LAUNCH(1); break;
@@ -726,6 +731,7 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
     case 16: WS_LAUNCH(16); break;
     default: WS_LAUNCH(0); break;
   }
+#undef WS_LAUNCH2
 #undef WS_LAUNCH
   LAUNCH_CHECK();
   return HMMCU_OK;

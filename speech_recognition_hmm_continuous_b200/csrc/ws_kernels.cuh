@@ -42,7 +42,7 @@
 
 namespace hmmk {
 
-constexpr int kWsThreads = 288;   // 9 warps
+constexpr int kWsThreads = 544;   // 17 warps: 8 epilogue, 8 loaders, MMA issuer
 constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image
 
 // W image in global and shared memory: [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats]
@@ -76,6 +76,9 @@ __device__ __forceinline__ void split_tf32_fast(float v, float &hi, float &lo) {
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const float4 &v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 // non-blocking poll (try_wait may suspend the thread for a long time when the phase is not complete)
 __device__ __forceinline__ bool mbar_try(uint64_t *mbar, uint32_t parity) {
@@ -174,40 +177,44 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
 
 // units == nullptr: decode, unit u = (image u / ntiles_dec, frames [128 (u % ntiles_dec), ...) of the batch, nframes_dec in all)
 // MP: padded mixtures per state when <= 16 (1, 2, 4, 8, 16); 0 = a multiple of 16 given at run time (M)
-template <bool TRAIN, int MP>
+// Warps: 0-7 epilogue (lane quarter w & 3; column groups of parity w >> 2), 8-15 loaders (lane quarter w & 3;
+// chunks 0-2 / 3-4 of the doubled row), 16 MMA issuer.
+template <bool TRAIN, int MP, bool DBG>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nframes_dec, const int32_t *__restrict__ frame_ids,
           const float *__restrict__ x32, const float *__restrict__ images, int N, int M, int DP, int TN, float *__restrict__ logb,
           int64_t fbase, int64_t ldb, int S_total, int SCt, long long *__restrict__ tdbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int KP = 2 * DP, NSLAB = KP / 8;
-  // optional timeline of CTA 0 (diagnostics): tdbg[unit][8] clock stamps
+  // optional timeline of CTA 0 (diagnostic build): tdbg[unit][8] clock stamps
   auto stamp = [&](int i, int slot) {
-    if (tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) tdbg[i * 8 + slot] = clock64();
+    if (DBG && tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) tdbg[i * 8 + slot] = clock64();
   };
   const uint32_t P = (uint32_t)(KP / 4) * 128;
   const uint32_t w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
-  uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *Ws = sm;                        // [hi | lo]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(Ws + w_bytes);
-  uint64_t *full = bars, *empty = bars + 2, *dfull = bars + 4, *dempty = bars + 6;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  const uint32_t Ws = (smem_u32(smem_raw) + 1023u) & ~1023u;  // [hi | lo], shared-window address
+  const uint32_t bars = Ws + w_bytes;
+  const uint32_t full = bars, empty = bars + 16, dfull = bars + 32, dempty = bars + 48, tmem_slot = bars + 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    auto init = [](uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); };
     for (int s = 0; s < 2; s++) {
-      mbar_init(&full[s], 128);    // every loader thread arrives
-      mbar_init(&empty[s], 1);     // tcgen05.commit
-      mbar_init(&dfull[s], 1);     // tcgen05.commit
-      mbar_init(&dempty[s], 128);  // every epilogue thread arrives
+      init(full + 8 * s, 256);    // every loader thread arrives
+      init(empty + 8 * s, 1);     // tcgen05.commit
+      init(dfull + 8 * s, 1);     // tcgen05.commit
+      init(dempty + 8 * s, 256);  // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem0 = *tmem_slot;
+  const uint32_t tmem0 = (uint32_t)lds_i32(tmem_slot);
 
   const int per = (nunits + gridDim.x - 1) / gridDim.x;
   const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
@@ -216,165 +223,179 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     const int img = ui / ntiles_dec, t = ui - img * ntiles_dec;
     return TcTile{t * kTcRows, min(kTcRows, nframes_dec - t * kTcRows), img, img * SCt, 0, 0};
   };
+  auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 8 && warp < 16) {
     // =================================== LOADERS ===================================
-    const int r = tid - 128;  // frame row of the tile
-    const uint32_t rbase = (uint32_t)(r & 7) * 16 + (uint32_t)(r >> 3) * P;
-    constexpr int kQ = 10;  // float4 per row held in registers (DP <= 40)
+    const int q = warp & 3, h = (warp - 8) >> 2;
+    const int r = 32 * q + lane;  // frame row of the tile = TMEM lane
+    constexpr int kQ = 5;         // float4 per thread: half a row (DP <= 40)
     const int nq = DP / 4;
+    const int j0 = h * kQ;        // this thread expands float4 [j0, j0 + kQ) of the row: x -> columns 4j.., x^2 -> columns DP + 4j..
     // Global loads run three levels ahead of the expansion so that no latency is exposed per unit:
     // unit descriptor (i+3) -> frame id (i+2) -> feature row (i+1), while unit i is split and stored.
-    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
     auto frame_of = [&](const TcTile &u) -> int64_t {
       if (r >= u.nrows) return -1;
       return TRAIN ? (int64_t)__ldg(frame_ids + u.row0 + r) : fbase + u.row0 + r;
     };
     auto load_row = [&](int64_t f, float4 (&xv)[kQ]) {
-      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP);
+      const float4 *src = reinterpret_cast<const float4 *>(x32 + (f < 0 ? 0 : f) * DP) + j0;
 #pragma unroll
-      for (int j = 0; j < kQ; j++) xv[j] = (f >= 0 && j < nq) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < kQ; j++) xv[j] = (f >= 0 && j0 + j < nq) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    TcTile d0 = unit_at(u_begin), d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
-    int64_t f1 = frame_of(d1);
-    float4 xv[kQ];
-    load_row(frame_of(d0), xv);
+    const uint32_t xa0 = tmem0 + ((uint32_t)(32 * q) << 16);  // my lane
     int cur_img = -1;
-    for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
-      const TcTile unit = d0;
+    auto split4 = [](const float4 &v, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+      float hh, ll;
+      split_tf32_fast(v.x, hh, ll); hi[0] = __float_as_uint(hh); lo[0] = __float_as_uint(ll);
+      split_tf32_fast(v.y, hh, ll); hi[1] = __float_as_uint(hh); lo[1] = __float_as_uint(ll);
+      split_tf32_fast(v.z, hh, ll); hi[2] = __float_as_uint(hh); lo[2] = __float_as_uint(ll);
+      split_tf32_fast(v.w, hh, ll); hi[3] = __float_as_uint(hh); lo[3] = __float_as_uint(ll);
+    };
+    auto expand = [&](int i, const TcTile &unit, const float4 (&xv)[kQ]) {
       const int s = i & 1;
-      float4 xn[kQ];
-      load_row(f1, xn);                      // rows of unit i+1
-      const int64_t f2 = frame_of(d2);       // frame id of unit i+2
-      const TcTile d3 = unit_at(ui + 3);     // descriptor of unit i+3
       if (unit.img != cur_img) {
         // the tensor pipe may still be reading the old image: wait for the previous unit's MMAs
-        if (i >= 1) mbar_wait(&empty[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        if (i >= 1) mbar_wait_a(empty + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);
         const float4 *wsrc = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4));
-        float4 *wdst = reinterpret_cast<float4 *>(Ws);
-        for (int k = r; k < (int)(w_bytes / 16); k += 128) wdst[k] = __ldg(wsrc + k);
+        for (int k = tid - 256; k < (int)(w_bytes / 16); k += 256) st_shared_v4(Ws + 16 * k, __ldg(wsrc + k));
         cur_img = unit.img;
       }
-      if (warp == 4) stamp(i, 0);
-      mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);  // operand stage s is free (unit i-2 has been multiplied)
-      if (warp == 4) stamp(i, 1);
+      if (warp == 8) stamp(i, 0);
+      mbar_wait_a(empty + 8 * s, ((i >> 1) & 1) ^ 1);  // operand stage s is free (unit i-2 has been multiplied)
+      if (warp == 8) stamp(i, 1);
       tc_fence_after();
-      const uint32_t xa = tmem0 + (uint32_t)s * 160 + ((uint32_t)(32 * (warp & 3)) << 16);  // my lane, stage s
-      // 16 columns at a time: chunk c of [x | x^2] covers float4 4c .. 4c+3 of the doubled row
+      // stage s: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)], 4 columns per store
+      const uint32_t xa = xa0 + (uint32_t)s * 160 + 4 * j0;
 #pragma unroll
-      for (int c = 0; c < 2 * kQ / 4; c++) {
-        if (c * 16 < KP) {
-          uint32_t vh[16], vl[16];
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int j = c * 4 + q;  // float4 index in [x | x^2]; static after unrolling
-            float4 xx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < nq) xx = xv[j < kQ ? j : 0];
-            else if (j < 2 * nq) {
-              const float4 t = xv[(j - nq) < kQ && (j - nq) >= 0 ? (j - nq) : 0];
-              xx = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
-            }
-            float h, l;
-            split_tf32_fast(xx.x, h, l); vh[q * 4 + 0] = __float_as_uint(h); vl[q * 4 + 0] = __float_as_uint(l);
-            split_tf32_fast(xx.y, h, l); vh[q * 4 + 1] = __float_as_uint(h); vl[q * 4 + 1] = __float_as_uint(l);
-            split_tf32_fast(xx.z, h, l); vh[q * 4 + 2] = __float_as_uint(h); vl[q * 4 + 2] = __float_as_uint(l);
-            split_tf32_fast(xx.w, h, l); vh[q * 4 + 3] = __float_as_uint(h); vl[q * 4 + 3] = __float_as_uint(l);
-          }
-          tmem_st16(xa + c * 16, vh);
-          tmem_st16(xa + 80 + c * 16, vl);
+      for (int j = 0; j < kQ; j++) {
+        if (j0 + j < nq) {
+          const float4 t = xv[j];
+          uint32_t vh[4], vl[4];
+          split4(t, vh, vl);
+          tmem_st4(xa + 4 * j, vh);
+          tmem_st4(xa + 80 + 4 * j, vl);
+          split4(make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w), vh, vl);
+          tmem_st4(xa + DP + 4 * j, vh);
+          tmem_st4(xa + 80 + DP + 4 * j, vl);
         }
       }
       tmem_wait_st();
       tc_fence_before();
       fence_async_smem();  // the W image (generic-proxy writes) -> visible to the tensor core
-      mbar_arrive(&full[s]);
-      if (warp == 4) stamp(i, 2);
-#pragma unroll
-      for (int j = 0; j < kQ; j++) xv[j] = xn[j];
-      d0 = d1; d1 = d2; d2 = d3; f1 = f2;
+      mbar_arrive_a(full + 8 * s);
+      if (warp == 8) stamp(i, 2);
+    };
+    TcTile d0 = unit_at(u_begin), d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
+    int64_t f1 = frame_of(d1);
+    float4 xa_[kQ], xb_[kQ];
+    load_row(frame_of(d0), xa_);
+    for (int ui = u_begin, i = 0; ui < u_end; ui += 2, i += 2) {  // two units per trip: the row buffers swap roles
+      load_row(f1, xb_);                     // rows of unit i+1
+      int64_t f2 = frame_of(d2);             // frame id of unit i+2
+      TcTile d3 = unit_at(ui + 3);           // descriptor of unit i+3
+      expand(i, d0, xa_);
+      if (ui + 1 < u_end) {
+        load_row(f2, xa_);                   // rows of unit i+2
+        f1 = frame_of(d3);                   // frame id of unit i+3
+        const TcTile d4 = unit_at(ui + 4);
+        expand(i + 1, d1, xb_);
+        d0 = d2; d1 = d3; d2 = d4;
+      }
     }
-  } else if (warp == 8) {
+  } else if (warp == 16) {
     // =================================== MMA ISSUER ===================================
     const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
       const int s = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      mbar_wait(&full[s], ph);          // operands landed
+      mbar_wait_a(full + 8 * s, ph);          // operands landed
       stamp(i, 3);
-      mbar_wait(&dempty[s], ph ^ 1);    // accumulator stage drained by the epilogue (unit i-2)
+      mbar_wait_a(dempty + 8 * s, ph ^ 1);    // accumulator stage drained by the epilogue (unit i-2)
       stamp(i, 4);
       tc_fence_after();
-      const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
       if (elect_one_sync()) {
         const uint32_t xh = tb + (uint32_t)s * 160, xl = xh + 80;
-        const uint64_t wh = make_smem_desc2(smem_u32(Ws), 128, P), wl = make_smem_desc2(smem_u32(Ws) + (uint32_t)(TN / 8) * P, 128, P);
+        const uint64_t wh = make_smem_desc2(Ws, 128, P), wl = make_smem_desc2(Ws + (uint32_t)(TN / 8) * P, 128, P);
         const uint32_t d = tb + 320 + (uint32_t)s * 96;
-        uint32_t acc = 0;
-        for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
-          const uint32_t a0 = (p == 1) ? xl : xh;
-          const uint64_t b0 = (p == 2) ? wl : wh;
-          for (int j = 0; j < NSLAB; j++) {
-            tc_mma_tf32_ts(d, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc, acc);  // +256 B per K-step, in 16-byte units
-            acc = 1;
+        if (NSLAB == 10) {  // D = 39: fully unrolled
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, xh + j * 8, wh + (uint64_t)(j * 16), idesc, j > 0);  // Xh*Wh
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, xl + j * 8, wh + (uint64_t)(j * 16), idesc, 1);      // Xl*Wh
+#pragma unroll
+          for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, xh + j * 8, wl + (uint64_t)(j * 16), idesc, 1);      // Xh*Wl
+        } else {
+          uint32_t acc = 0;
+          for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
+            const uint32_t a0 = (p == 1) ? xl : xh;
+            const uint64_t b0 = (p == 2) ? wl : wh;
+            for (int j = 0; j < NSLAB; j++) {
+              tc_mma_tf32_ts(d, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc, acc);  // +256 B per K-step, in 16-byte units
+              acc = 1;
+            }
           }
         }
-        tc_commit(&empty[s]);   // operand stage (and, for the loaders' image switch, W) free when these MMAs retire
-        tc_commit(&dfull[s]);   // accumulator ready
+        tc_commit_a(empty + 8 * s);   // operand stage (and, for the loaders' image switch, W) free when these MMAs retire
+        tc_commit_a(dfull + 8 * s);   // accumulator ready
       }
       __syncwarp();
       stamp(i, 5);
     }
   } else {
-    // =================================== EPILOGUE ===================================
-    const int row = 32 * warp + lane;  // warps 0..3 <-> TMEM lanes 32w..32w+31
-    const uint32_t trow = (uint32_t)(32 * warp) << 16;
+    // =================================== EPILOGUE (warps 0-7) ===================================
+    const int q = warp & 3, h = warp >> 2;
+    const int row = 32 * q + lane;  // TMEM lane
+    const uint32_t trow = (uint32_t)(32 * q) << 16;
     // unit descriptors two ahead and the frame id one ahead, so that no global-memory latency sits
     // between the accumulator becoming ready and its reduction
-    auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
     auto frame_of = [&](const TcTile &u) -> int64_t {
       if (row >= u.nrows) return 0;
       return TRAIN ? (int64_t)__ldg(frame_ids + u.row0 + row) : fbase + u.row0 + row;
     };
     TcTile un0 = unit_at(u_begin), un1 = unit_at(u_begin + 1);
     int64_t fcur = frame_of(un0);
+    const int mp = MP ? MP : M;               // M here is the padded count
+    const int cpg = MP ? 1 : mp / 16;         // chunks per group: a chunk of 16/MP whole states, or one state of M/16 chunks
+    const int spg = MP ? 16 / (MP ? MP : 16) : 1;  // states per group
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
       const TcTile unit = un0;
       const int64_t f = fcur;
       const int64_t fnext = frame_of(un1);
       const TcTile un2 = unit_at(ui + 2);
       const int s = i & 1;
-      mbar_wait(&dfull[s], (i >> 1) & 1);
+      mbar_wait_a(dfull + 8 * s, (i >> 1) & 1);
       if (warp == 0) stamp(i, 6);
       tc_fence_after();
       const int st_lim = TRAIN ? N : S_total;
       const int nst = max(0, min(SCt, st_lim - unit.state0));  // states present in this image
-      const int mp = MP ? MP : M;  // M here is the padded count
-      const int ncols = nst * mp;
+      const int ngroups = (nst + spg - 1) / spg;
       const bool live = row < unit.nrows;
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
       const uint32_t d = tmem0 + 320 + (uint32_t)s * 96 + trow;
       // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
       // shared-memory image may already belong to a later unit
       const float4 *kc4 = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4);
-      float mx = kNegInf, sum = 0.f;  // running state (MP == 0 only)
-      int chunks = 0, st = 0;
-      constexpr int kMaxCh = kWsMaxTN / 16;
-      uint32_t v[kMaxCh][16];
+      constexpr int kMaxG = (kWsMaxTN / 16 + 1) / 2;  // groups per warp when a group is one chunk
+      if (MP) {
+        // my groups: g = h, h + 2, ...; every accumulator chunk of mine in flight at once
+        uint32_t v[kMaxG][16];
 #pragma unroll
-      for (int c = 0; c < kMaxCh; c++)  // every accumulator column of my frame in flight at once
-        if (c * 16 < ncols) tmem_ld16_nowait(d + c * 16, v[c]);
-      tmem_wait_ld();
+        for (int k = 0; k < kMaxG; k++)
+          if (h + 2 * k < ngroups) tmem_ld16_nowait(d + (h + 2 * k) * 16, v[k]);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < kMaxCh; c++) {
-        if (c * 16 < ncols) {
-          const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
-          const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
-          float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
+        for (int k = 0; k < kMaxG; k++) {
+          const int c = h + 2 * k;
+          if (c < ngroups) {
+            const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+            const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+            float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
 #pragma unroll
-          for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[c][j]), 1.4426950408889634f, kc[j]);
-          if (MP) {  // 16 / MP whole states in this chunk, each reduced independently
+            for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[k][j]), 1.4426950408889634f, kc[j]);
 #pragma unroll
-            for (int g = 0; g < 16 / (MP ? MP : 16); g++) {
+            for (int g = 0; g < 16 / (MP ? MP : 16); g++) {  // 16 / MP whole states in this chunk, each reduced independently
               float m = val[g * MP];
 #pragma unroll
               for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
@@ -383,10 +404,24 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 #pragma unroll
               for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
               const float lb = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
-              if (live && st + g < nst) lrow[st + g] = lb;
+              const int st = c * (16 / (MP ? MP : 16)) + g;
+              if (live && st < nst) lrow[st] = lb;
             }
-            st += 16 / (MP ? MP : 16);
-          } else {  // one state spans M/16 chunks: online log-sum-exp across chunks
+          }
+        }
+      } else {
+        // one state spans cpg chunks: online log-sum-exp across its chunks; my states: h, h + 2, ...
+        for (int st = h; st < nst; st += 2) {
+          float mx = kNegInf, sum = 0.f;
+          for (int cc = 0; cc < cpg; cc++) {
+            const int c = st * cpg + cc;
+            uint32_t v[16];
+            tmem_ld16(d + c * 16, v);
+            const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+            const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+            float val[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kc[j]);
             float m = val[0];
 #pragma unroll
             for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
@@ -397,16 +432,13 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
             for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
             sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
             mx = mn;
-            if (++chunks == mp / 16) {
-              const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
-              if (live) lrow[st] = lb;
-              st++; chunks = 0; mx = kNegInf; sum = 0.f;
-            }
           }
+          const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
+          if (live) lrow[st] = lb;
         }
       }
       tc_fence_before();
-      mbar_arrive(&dempty[s]);
+      mbar_arrive_a(dempty + 8 * s);
       if (warp == 0) stamp(i, 7);
       un0 = un1; un1 = un2; fcur = fnext;
     }
@@ -414,7 +446,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem0, 512);
+  if (warp == 16) tmem_dealloc(tmem0, 512);
 }
 
 
