@@ -256,13 +256,93 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "decode": dec,
         "wall_s_timed_region": wall,
     }
+    ctx.close()
+    del xdev, flush
+    if world == 1 and not args.no_regimes:
+        out["regimes"] = run_regimes(api, local, pk, tf32_peak_tflops(torch.device("cuda", local)))
     if rank == 0:
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(w, budget_s=args.cpu_seconds)
         print(json.dumps(out))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def tf32_peak_tflops(device):
+    """Dense TF32 throughput of this GPU by the protocol of MEASURED_PEAKS.json (library GEMM 8192^3,
+    best of 10, CUDA events): the denominator of the tensor-pipe roofline.  Measurement only."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device=device)
+        b = torch.randn(8192, 8192, device=device)
+        best = 1e9
+        for _ in range(3):
+            torch.matmul(a, b)
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+REGIMES = {
+    # bounded slices of BASELINE configs[3] and configs[4]: the decode / large-mixture regimes where the
+    # emission contraction is tensor-pipe bound and the cell scorers are HBM bound
+    "c4_slice": dict(V=1000, N=5, M=3, U=200, desc="configs[3] slice: 1,000-word model set (N=5, M=3), 200 of 100k utterances"),
+    "c5_slice": dict(V=200, N=3, M=128, U=200, desc="configs[4] slice: N=3, M=128, 200 of 2,000 models, 200 utterances"),
+}
+
+
+def run_regimes(api, local, pk, tf32_peak):
+    """Decode legs at the shapes where the north-star roofline targets apply (device-resident features):
+    emissions of every frame against the whole model set (tensor pipe), forward / Viterbi cell scorers (HBM)."""
+    import torch
+    from speech_recognition_hmm_continuous_b200 import synth
+    out = {}
+    for name, w in REGIMES.items():
+        V, N, M, U = w["V"], w["N"], w["M"], w["U"]
+        cen, s = synth.make_centres(V, N, M, D, seed=77)
+        labels = (np.arange(U) % V).astype(np.int32)
+        x, off = synth.make_utterances(cen, s, labels, seed=78)
+        F = int(off[-1])
+        ctx = api.Context(local, timing=True)
+        xdev = torch.from_numpy(x).to(torch.device("cuda", local))
+        ctx.set_features_device(xdev.data_ptr(), off, D)
+        ctx.set_models(api.ModelSet.from_dict(synth.make_models(cen, s)))
+        res = {"workload": w["desc"], "frames": F, "models": V, "gaussians_per_frame": V * N * M}
+        for leg, fn in (("forward", ctx.forward_scores), ("viterbi", ctx.viterbi_scores)):
+            fn()
+            em, sc = [], []
+            for _ in range(3):
+                sco = fn()
+                em.append(ctx.kernel_ms("emis"))
+                sc.append(ctx.kernel_ms("score" if leg == "forward" else "viterbi"))
+            em_ms, sc_ms = float(np.median(em)), float(np.median(sc))
+            flops = 2.0 * K_AUG * V * N * M * F               # algorithmic; the 3xTF32 scheme issues three times as many
+            sbytes = 4.0 * N * V * F + (N * V * F if leg == "viterbi" else 0.0)   # SURVEY 8d: 4N (+N) bytes per (frame, model)
+            res[leg] = {
+                "emis_ms": em_ms, "score_ms": sc_ms,
+                "emis_tflops_algorithmic": flops / (em_ms * 1e-3) / 1e12,
+                "emis_frac_tf32_peak_algorithmic": flops / (em_ms * 1e-3) / 1e12 / tf32_peak,
+                "emis_frac_tf32_peak_issued_3x": 3.0 * flops / (em_ms * 1e-3) / 1e12 / tf32_peak,
+                "score_gbs": sbytes / (sc_ms * 1e-3) / 1e9, "score_frac_hbm": sbytes / (sc_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                "frames_per_s": F / ((em_ms + sc_ms) * 1e-3), "frame_model_pairs_per_s": F * V / ((em_ms + sc_ms) * 1e-3),
+            }
+        lab, _ = ctx.rank(sco)
+        res["top1_matches_generating_word"] = float(np.mean(lab == labels))
+        out[name] = res
+        ctx.close()
+        del xdev
+    out["tf32_peak_tflops"] = tf32_peak
+    out["tf32_peak_note"] = "library TF32 GEMM 8192^3 measured in this run (same protocol as MEASURED_PEAKS.json); 3xTF32 issues 3 MMAs per algorithmic MMA"
+    return out
 
 
 # ========================================================================== reference arm ====
@@ -384,6 +464,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the decode-regime legs (c4 / c5 slices)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -3,16 +3,16 @@ import ctypes as C, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from speech_recognition_hmm_continuous_b200 import api, synth
-V, N, M, U = 10, 5, 16, 1000
+mode = sys.argv[1] if len(sys.argv) > 1 else "train"
+V, N, M, U = (1000, 5, 3, 50) if mode == "dec4" else (100, 3, 128, 50) if mode == "dec5" else (10, 5, 16, 1000)
 cen, s = synth.make_centres(V, N, M, 39, seed=1234)
 labels = (np.arange(U) % V).astype(np.int32)
 x, off = synth.make_utterances(cen, s, labels, seed=1234)
 ms = api.ModelSet.from_dict(synth.make_models(cen, s))
 ctx = api.Context(0)
 ctx.set_features(x, off); ctx.set_models(ms); ctx.em_reset()
-for _ in range(3):
+for _ in range(3 if mode in ("train", "acc") else 0):
     ctx.estep(labels, download=False, want_logp=False)
-mode = sys.argv[1] if len(sys.argv) > 1 else "train"
 ctx.set_option("debug_acc", 4 if mode == "acc" else 2)
 if mode in ("train", "acc"):
     ctx.estep(labels, download=False, want_logp=False)

@@ -636,11 +636,19 @@ static int ensure_tc_images(hmmcu_ctx *ctx, int mode) {
 }
 
 // ---- warp-specialised emission kernel: images and launch ----------------------------------------
+// image geometry of the warp-specialised emission kernel: whole states per image (SCt) and its columns (TN)
+static void ws_geometry(const hmmcu_ctx *ctx, int nstates_avail, int &SCt, int &TN) {
+  const int MPd = ws_pad_m(ctx->M);
+  if (MPd <= 16) SCt = std::min((kWsMaxTN / 16) * ws_states_per_chunk(MPd), nstates_avail);
+  else if (MPd <= kWsMaxTN) SCt = std::min(std::min(kWsMaxTN / MPd, kWsXch), nstates_avail);
+  else SCt = 1;  // one wide state per image
+  TN = round_up(ws_image_cols(MPd, SCt), 16);
+}
 static bool ws_supported(const hmmcu_ctx *ctx) {
   const int MPd = ws_pad_m(ctx->M);
-  if (!ctx->use_ws || MPd > kWsMaxTN || ctx->DP > 40) return false;
-  const int SCt = std::max(1, kWsMaxTN / MPd);
-  const int TN = round_up(std::min(SCt, ctx->V * ctx->N) * MPd, 16);
+  if (!ctx->use_ws || MPd > kWsMaxTN1 || ctx->DP > 40) return false;
+  int SCt, TN;
+  ws_geometry(ctx, ctx->V * ctx->N, SCt, TN);
   return ws_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
 }
 
@@ -656,19 +664,18 @@ static int launch_pack_ws(hmmcu_ctx *ctx, hmmcu_ctx::TcSet &ts) {
 static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
   hmmcu_ctx::TcSet &ts = mode == 0 ? ctx->ws_train : ctx->ws_dec;
   if (!ts.dirty) return HMMCU_OK;
-  const int N = ctx->N, M = ctx->M, V = ctx->V, MPd = ws_pad_m(M);
-  const int SCmax = std::max(1, kWsMaxTN / MPd);
+  const int N = ctx->N, V = ctx->V;
   std::vector<int32_t> s0, ns;
+  int TN;
   if (mode == 0) {
-    ts.SCt = std::min(SCmax, N);
+    ws_geometry(ctx, N, ts.SCt, TN);
     for (int v = 0; v < V; v++)
       for (int s = 0; s < N; s += ts.SCt) { s0.push_back(v * N + s); ns.push_back(std::min(ts.SCt, N - s)); }
   } else {
     const int S = V * N;
-    ts.SCt = std::min(SCmax, S);
+    ws_geometry(ctx, S, ts.SCt, TN);
     for (int s = 0; s < S; s += ts.SCt) { s0.push_back(s); ns.push_back(std::min(ts.SCt, S - s)); }
   }
-  const int TN = round_up(ts.SCt * MPd, 16);
   const int KP = 2 * ctx->DP;
   if (TN != ts.TN || (int)s0.size() != ts.nimg) {  // geometry changed: (re)upload the image table
     ts.TN = TN;
@@ -1008,7 +1015,8 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
     ctx->n_tc_tiles_train = (int64_t)tt.size();
     {  // the same tiles under the warp-specialised kernel's image geometry
       std::vector<TcTile> wt;
-      const int SCw = std::min(std::max(1, kWsMaxTN / ws_pad_m(ctx->M)), ctx->N);
+      int SCw, TNw;
+      ws_geometry(ctx, ctx->N, SCw, TNw);
       const int CTw = (ctx->N + SCw - 1) / SCw;
       int32_t r0w = 0;
       for (int v = 0; v < V; v++) {

@@ -43,20 +43,31 @@
 namespace hmmk {
 
 constexpr int kWsThreads = 544;   // 17 warps: 8 epilogue, 8 loaders, MMA issuer
-constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image
+constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image (two operand stages in tensor memory)
+constexpr int kWsMaxTN1 = 176;    // ... of an image that holds one wide state (a single operand stage)
+constexpr int kWsXch = 6;         // states per image when a state spans several 16-column chunks (M > 16)
 
 // W image in global and shared memory: [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats]
 __host__ __device__ inline size_t ws_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 4) * 128 + (size_t)TN * 4; }
 __host__ __device__ inline size_t ws_emis_smem_bytes(int TN, int KP) { return ws_image_bytes(TN, KP) + 1024 + 272; }
 
-// Mixtures per state as laid out in the W image: padded to a power of two (M <= 16) or to a multiple of
-// 16, so that state boundaries fall on the 16-column chunks the epilogue reads; pad mixtures have W = 0
-// and kc = -inf (density 0).
+// Mixtures per state as laid out in the W image.  M <= 16: padded to a power of two, so that a 16-column chunk
+// holds 16 / MP whole states and the epilogue can store a chunk's log b with 16- / 8-byte stores (measured at the
+// 1,000-word decode shape: M = 3 laid out unpadded, five states and one pad column per chunk, needs 4-byte
+// stores and runs 2x slower than M = 3 padded to 4); M > 16: padded to a multiple of 16 (a state spans M / 16
+// chunks).  State boundaries never cut through a chunk.  Pad columns have W = 0 and kc = -inf (density 0).
 __host__ __device__ inline int ws_pad_m(int M) {
   if (M > 16) return (M + 15) / 16 * 16;
   int p = 1;
   while (p < M) p <<= 1;
   return p;
+}
+// states per 16-column chunk (M <= 16), and the columns an image of `nstates` whole states occupies
+__host__ __device__ inline int ws_states_per_chunk(int MPd) { return MPd <= 16 ? 16 / MPd : 1; }
+__host__ __device__ inline int ws_image_cols(int MPd, int nstates) {
+  if (MPd > 16) return nstates * MPd;
+  const int spc = 16 / MPd;
+  return (nstates + spc - 1) / spc * 16;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -152,9 +163,16 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
   float *kc2 = lo + (size_t)(TN / 8) * (P / 4);
   const int64_t s0g = img_state0[img];
   const int nst = img_nstates[img];
-  // image row n = (state n / MP, mixture n % MP) -> Gaussian index, or -1 for a pad row
+  // image row n -> Gaussian index, or -1 for a pad row: chunk n / 16 holds states (n / 16) spc .. of MP columns each
+  // (MP <= 16); a state of MP > 16 columns spans MP / 16 chunks
   auto gauss_of = [&](int n) -> int64_t {
-    const int st = n / MP, m = n - st * MP;
+    int st, m;
+    if (MP > 16) { st = n / MP; m = n - st * MP; }
+    else {
+      const int spc = 16 / MP, c = n >> 4, w = n & 15;
+      if (w >= spc * MP) return -1;
+      st = c * spc + w / MP; m = w % MP;
+    }
     return (st < nst && m < M) ? (s0g + st) * M + m : -1;
   };
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TN * KP; idx += gridDim.x * blockDim.x) {
@@ -215,6 +233,11 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem0 = (uint32_t)lds_i32(tmem_slot);
+  // TMEM columns: AST operand stages of 160 [x_hi | x2_hi | x_lo | x2_lo], then two accumulator stages of ACS.
+  // Images wider than 96 columns (one state of up to 176 mixtures) leave room for a single operand stage.
+  const int AST = TN > 96 ? 1 : 2;
+  const uint32_t ACS = TN > 96 ? (uint32_t)TN : 96u, acc0 = (uint32_t)AST * 160;
+  __shared__ float2 xch[2][4][32][kWsXch];  // partial (max, sum) of the odd chunks' warp, per unit parity / quarter / lane / state
 
   const int per = (nunits + gridDim.x - 1) / gridDim.x;
   const int u_begin = blockIdx.x * per, u_end = min(nunits, u_begin + per);
@@ -253,16 +276,16 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       split_tf32_fast(v.w, hh, ll); hi[3] = __float_as_uint(hh); lo[3] = __float_as_uint(ll);
     };
     auto expand = [&](int i, const TcTile &unit, const float4 (&xv)[kQ]) {
-      const int s = i & 1;
+      const int s = i % AST, ku = i / AST;  // operand stage and its use count
       if (unit.img != cur_img) {
         // the tensor pipe may still be reading the old image: wait for the previous unit's MMAs
-        if (i >= 1) mbar_wait_a(empty + 8 * ((i - 1) & 1), ((i - 1) >> 1) & 1);
+        if (i >= 1) mbar_wait_a(empty + 8 * ((i - 1) % AST), ((i - 1) / AST) & 1);
         const float4 *wsrc = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4));
         for (int k = tid - 256; k < (int)(w_bytes / 16); k += 256) st_shared_v4(Ws + 16 * k, __ldg(wsrc + k));
         cur_img = unit.img;
       }
       if (warp == 8) stamp(i, 0);
-      mbar_wait_a(empty + 8 * s, ((i >> 1) & 1) ^ 1);  // operand stage s is free (unit i-2 has been multiplied)
+      mbar_wait_a(empty + 8 * s, (ku & 1) ^ 1);  // operand stage s is free (unit i-AST has been multiplied)
       if (warp == 8) stamp(i, 1);
       tc_fence_after();
       // stage s: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)], 4 columns per store
@@ -308,17 +331,17 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
-      const int s = i & 1;
+      const int s = i & 1, sa = i % AST;
       const uint32_t ph = (i >> 1) & 1;
-      mbar_wait_a(full + 8 * s, ph);          // operands landed
+      mbar_wait_a(full + 8 * sa, (i / AST) & 1);  // operands landed
       stamp(i, 3);
       mbar_wait_a(dempty + 8 * s, ph ^ 1);    // accumulator stage drained by the epilogue (unit i-2)
       stamp(i, 4);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint32_t xh = tb + (uint32_t)s * 160, xl = xh + 80;
+        const uint32_t xh = tb + (uint32_t)sa * 160, xl = xh + 80;
         const uint64_t wh = make_smem_desc2(Ws, 128, P), wl = make_smem_desc2(Ws + (uint32_t)(TN / 8) * P, 128, P);
-        const uint32_t d = tb + 320 + (uint32_t)s * 96;
+        const uint32_t d = tb + acc0 + (uint32_t)s * ACS;
         if (NSLAB == 10) {  // D = 39: fully unrolled
 #pragma unroll
           for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, xh + j * 8, wh + (uint64_t)(j * 16), idesc, j > 0);  // Xh*Wh
@@ -337,7 +360,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
             }
           }
         }
-        tc_commit_a(empty + 8 * s);   // operand stage (and, for the loaders' image switch, W) free when these MMAs retire
+        tc_commit_a(empty + 8 * sa);  // operand stage (and, for the loaders' image switch, W) free when these MMAs retire
         tc_commit_a(dfull + 8 * s);   // accumulator ready
       }
       __syncwarp();
@@ -358,7 +381,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     int64_t fcur = frame_of(un0);
     const int mp = MP ? MP : M;               // M here is the padded count
     const int cpg = MP ? 1 : mp / 16;         // chunks per group: a chunk of 16/MP whole states, or one state of M/16 chunks
-    const int spg = MP ? 16 / (MP ? MP : 16) : 1;  // states per group
+    const int spg = MP ? 16 / (MP ? MP : 16) : 1;  // states per group (16 % MP pad columns close a chunk)
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
       const TcTile unit = un0;
       const int64_t f = fcur;
@@ -373,7 +396,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       const int ngroups = (nst + spg - 1) / spg;
       const bool live = row < unit.nrows;
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
-      const uint32_t d = tmem0 + 320 + (uint32_t)s * 96 + trow;
+      const uint32_t d = tmem0 + acc0 + (uint32_t)s * ACS + trow;
       // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
       // shared-memory image may already belong to a later unit
       const float4 *kc4 = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4);
@@ -394,8 +417,10 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
             float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
 #pragma unroll
             for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[k][j]), 1.4426950408889634f, kc[j]);
+            constexpr int SPC = 16 / (MP ? MP : 16);  // whole states in this chunk, each reduced independently
+            float lbv[SPC];
 #pragma unroll
-            for (int g = 0; g < 16 / (MP ? MP : 16); g++) {  // 16 / MP whole states in this chunk, each reduced independently
+            for (int g = 0; g < SPC; g++) {
               float m = val[g * MP];
 #pragma unroll
               for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
@@ -403,38 +428,79 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
               float sm_ = 0.f;
 #pragma unroll
               for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
-              const float lb = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
-              const int st = c * (16 / (MP ? MP : 16)) + g;
-              if (live && st < nst) lrow[st] = lb;
+              lbv[g] = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
+            }
+            // the chunk's states are contiguous in the output row: 16- / 8-byte stores when the row allows it (a lane
+            // per frame makes every 4-byte store its own memory transaction)
+            float *dst = lrow + c * SPC;
+            if (live) {
+              if (SPC % 4 == 0 && c * SPC + SPC <= nst && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int g = 0; g + 3 < SPC; g += 4) *reinterpret_cast<float4 *>(dst + g) = make_float4(lbv[g], lbv[g + 1], lbv[g + 2], lbv[g + 3]);
+              } else if (SPC % 2 == 0 && c * SPC + SPC <= nst && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+#pragma unroll
+                for (int g = 0; g + 1 < SPC; g += 2) *reinterpret_cast<float2 *>(dst + g) = make_float2(lbv[g], lbv[g + 1]);
+              } else {
+#pragma unroll
+                for (int g = 0; g < SPC; g++)
+                  if (c * SPC + g < nst) dst[g] = lbv[g];
+              }
             }
           }
         }
       } else {
-        // one state spans cpg chunks: online log-sum-exp across its chunks; my states: h, h + 2, ...
-        for (int st = h; st < nst; st += 2) {
-          float mx = kNegInf, sum = 0.f;
-          for (int cc = 0; cc < cpg; cc++) {
-            const int c = st * cpg + cc;
-            uint32_t v[16];
-            tmem_ld16(d + c * 16, v);
-            const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
-            const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
-            float val[16];
+        // One state spans cpg chunks.  The two warps of a lane quarter take the even / the odd chunks of every
+        // state (online log-sum-exp over their own chunks); the odd warp hands its partial (max, sum) over
+        // through shared memory and the even warp merges and stores.
+        float pmx[kWsXch], psum[kWsXch];
 #pragma unroll
-            for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kc[j]);
-            float m = val[0];
+        for (int sx = 0; sx < kWsXch; sx++) {
+          pmx[sx] = kNegInf; psum[sx] = 0.f;
+          if (sx < nst) {
+            float mx = kNegInf, sum = 0.f;
+            for (int cc = h; cc < cpg; cc += 2) {
+              const int c = sx * cpg + cc;
+              uint32_t v[16];
+              tmem_ld16(d + c * 16, v);
+              const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+              const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
+              float val[16];
 #pragma unroll
-            for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
-            const float mn = fmaxf(mx, m);
-            const float ms = (mn > kNegInf) ? mn : 0.f;
-            float sm_ = 0.f;
+              for (int j = 0; j < 16; j++) val[j] = fmaf(__uint_as_float(v[j]), 1.4426950408889634f, kc[j]);
+              float m = val[0];
 #pragma unroll
-            for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
-            sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
-            mx = mn;
+              for (int j = 1; j < 16; j++) m = fmaxf(m, val[j]);
+              const float mn = fmaxf(mx, m);
+              const float ms = (mn > kNegInf) ? mn : 0.f;
+              float sm_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; j++) sm_ += ex2_approx(val[j] - ms);
+              sum = fmaf(sum, ex2_approx(((mx > kNegInf) ? mx : ms) - ms), sm_);
+              mx = mn;
+            }
+            pmx[sx] = mx; psum[sx] = sum;
           }
-          const float lb = (mx > kNegInf) ? (mx + __log2f(sum)) * 0.6931471805599453f : kNegInf;
-          if (live) lrow[st] = lb;
+        }
+        if (h == 1) {
+#pragma unroll
+          for (int sx = 0; sx < kWsXch; sx++)
+            if (sx < nst) xch[i & 1][q][lane][sx] = make_float2(pmx[sx], psum[sx]);
+          // (bar.sync, not bar.arrive: this warp can be a whole unit ahead of its partner, and two arrivals of
+          // the same warp would complete a barrier phase on their own)
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+          for (int sx = 0; sx < kWsXch; sx++) {
+            if (sx < nst) {
+              const float2 o = xch[i & 1][q][lane][sx];
+              const float mn = fmaxf(pmx[sx], o.x);
+              const float ms = (mn > kNegInf) ? mn : 0.f;
+              const float sum = psum[sx] * ex2_approx(((pmx[sx] > kNegInf) ? pmx[sx] : ms) - ms) + o.y * ex2_approx(((o.x > kNegInf) ? o.x : ms) - ms);
+              const float lb = (mn > kNegInf) ? (mn + __log2f(sum)) * 0.6931471805599453f : kNegInf;
+              if (live) lrow[sx] = lb;
+            }
+          }
         }
       }
       tc_fence_before();
