@@ -208,6 +208,7 @@ def run_ours(args):
     # decode leg (forward scoring of every utterance against all V models + ranking; then Viterbi)
     ctx.set_features_device(xdev.data_ptr(), off, D)
     ctx.set_models(ms)
+    ctx.enable_timing(True)  # per-kernel timers for the decode legs (no graph replay involved there)
     dec = {}
     for name, fn in (("forward", lambda: ctx.rank(ctx.forward_scores())), ("viterbi", lambda: ctx.viterbi(labels))):
         for _ in range(3):
@@ -240,9 +241,13 @@ def run_ours(args):
         "mstep": dict(bytes=8.0 * V * api.stats_size(N, M, D), flops=0.0),
     }
     dom = max(kms, key=lambda k: kms[k])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
     ach = alg[dom]["bytes"] / (kms[dom] * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"], "kernel_ms": kms,
+                "traffic": traffic, "peak_source": pk["source"], "kernel_ms": kms,
                 "tensor_view": {"achieved_tflops": alg[dom]["flops"] / (kms[dom] * 1e-3) / 1e12, "note": "algorithmic 2*K*G*F flops of the same kernel"}}
     out = {
         "metric": "frames/sec per Baum-Welch EM iteration", "value": value, "unit": "frames/s", "n_gpus": world,

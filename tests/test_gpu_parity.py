@@ -367,3 +367,86 @@ def test_c2_size_properties(ctx):
         u = sub[k]
         want = o.forward_score(o.Model(ms.A[labels[u]], ms.c[labels[u]], ms.mu[labels[u]], ms.iv[labels[u]], ms.det[labels[u]]), x[off[u]:off[u + 1]])
         assert abs(lpu[u] - want) <= RTOL * abs(want)
+
+
+# ------------------------------------------------------ new code paths of this round's kernels ----
+def test_graph_replay_gives_the_same_em_iterations():
+    """The E-step / M-step launch sequences are replayed as CUDA graphs from the third call on: five EM
+    iterations with and without graphs must produce the same models and log-likelihoods (the scratch-slot
+    reduction makes the statistics order-deterministic, so the comparison is tight)."""
+    ms, x, off, labels = _synth(3, 5, 4, 12, seed=808)
+    out = []
+    for graphs in (1, 0):
+        c = api.Context(0)
+        c.set_option("graphs", graphs)
+        c.set_features(x, off)
+        c.set_models(ms)
+        c.em_reset()
+        lps = []
+        for _ in range(5):
+            c.estep(labels, download=False, want_logp=False)
+            lp, nu, upd = c.mstep(threshold=-1.0)
+            lps.append(lp.copy())
+        out.append((np.array(lps), c.get_models(ms.D)))
+        c.close()
+    (lp_g, m_g), (lp_p, m_p) = out
+    assert np.allclose(lp_g, lp_p, rtol=1e-9)
+    for name in ("A", "c", "mu", "iv"):
+        assert np.allclose(getattr(m_g, name), getattr(m_p, name), rtol=1e-7, atol=1e-12), name
+    assert (np.diff(lp_g.sum(1)) > -1e-6 * np.abs(lp_g.sum(1)[:-1])).all()  # EM does not decrease the likelihood
+
+
+def test_chunked_upload_matches_device_resident_features():
+    """hmmcu_set_features (chunked copy pipelined with packing, centre formed on the host) and
+    hmmcu_set_features_device (k_center on the device) must give the same packed features."""
+    torch = pytest.importorskip("torch")
+    ms, x, off, labels = _synth(2, 5, 3, 40, seed=909, tmin=200, tmax=300)   # > 4096 frames: several chunks
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    st_h, lp_h = c.estep(labels)
+    xd = torch.from_numpy(x).cuda()
+    c.set_features_device(xd.data_ptr(), off, x.shape[1])
+    st_d, lp_d = c.estep(labels)
+    c.close()
+    assert np.allclose(lp_h, lp_d, rtol=1e-12) and np.allclose(st_h, st_d, rtol=1e-9, atol=1e-9)
+
+
+def test_many_small_models_take_the_atomic_flush_path(ctx):
+    """A CTA of the accumulate kernel that walks through more than two (model, Gaussian block) images flushes
+    the later ones with atomics instead of scratch slots; both must add up to the oracle's statistics."""
+    V, U = 24, 48
+    ms, x, off, labels = _synth(V, 3, 2, U, seed=1010, tmin=6, tmax=14)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    for v in (0, 7, V - 1):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st, lp = o.estep(_oracle_model(ms, v), xv, offv)
+        sp = api.split_stats(stats[v], 3, 2, ms.D)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        assert np.allclose(sp["S0"], st.S0, rtol=RTOL, atol=1e-6 * st.S0.max())
+        assert np.allclose(sp["num_trans"], st.num_trans, rtol=RTOL, atol=1e-6 * st.num_trans.max())
+
+
+@pytest.mark.parametrize("N,M,D", [(4, 2, 13), (5, 32, 39), (2, 160, 39)])
+def test_decode_paths_other_shapes(ctx, N, M, D):
+    """Forward scores / labels and Viterbi paths for feature widths other than 39 (generic k_logb64), for a
+    state that spans several 16-column chunks (M = 32) and for a wide state (M = 160: single operand stage)."""
+    ms, x, off, labels = _synth(3, N, M, 6, seed=1111 + M, D=D)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    sc = ctx.forward_scores()
+    vs, path = ctx.viterbi(labels)
+    for u in range(6):
+        for v in range(3):
+            want = o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]])
+            assert abs(sc[u, v] - want) <= RTOL * abs(want)
+        mo = _oracle_model(ms, labels[u])
+        b, _ = o.emissions(mo, x[off[u]:off[u + 1]], want_post=False)
+        s_o, p_o = o.viterbi(mo, b)
+        assert (path[off[u]:off[u + 1]] == p_o).all() and abs(vs[u] - s_o) <= 1e-9 * abs(s_o)
+    lab, _ = ctx.rank(sc)
+    assert (lab == labels).all()
