@@ -272,16 +272,42 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
     double acc_num[NS][2], acc_dt[NS], acc_dm[NS], acc_m = 0.0;
 #pragma unroll
     for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
-    for (int t = lane; t < T; t += 32) {
-      double al[NS], be[NS], g[NS], G = 0.0;
-      load_row<NS>(alpha_ws + (base + t) * kFbRow, al);
-      load_row<NS>(beta_ws + (base + t) * kFbRow, be);
-      {
-        float l0[NS];
-        load_lb<NS>(logb + (base + t) * NS, l0);
-        float m = l0[0];
+    // the rows of frame t + 32 are fetched while frame t is being worked on (the loop is latency bound otherwise)
+    struct Raw { float4 a0, a1, b0, b1, c0, c1; float l0[NS], l1[NS]; };
+    auto fetch = [&](int t, Raw &r) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.a0 = r.a1 = r.b0 = r.b1 = r.c0 = r.c1 = z4;
 #pragma unroll
-        for (int i = 1; i < NS; i++) m = fmaxf(m, l0[i]);
+      for (int i = 0; i < NS; i++) r.l0[i] = r.l1[i] = 0.f;
+      if (t < T) {
+        const float4 *pa = reinterpret_cast<const float4 *>(alpha_ws + (base + t) * kFbRow);
+        const float4 *pb = reinterpret_cast<const float4 *>(beta_ws + (base + t) * kFbRow);
+        r.a0 = pa[0]; r.b0 = pb[0];
+        if (NS > 4) { r.a1 = pa[1]; r.b1 = pb[1]; }
+        load_lb<NS>(logb + (base + t) * NS, r.l0);
+        if (t < T - 1) {
+          r.c0 = pb[2];  // beta row of frame t + 1 (rows are kFbRow = 8 floats)
+          if (NS > 4) r.c1 = pb[3];
+          load_lb<NS>(logb + (base + t + 1) * NS, r.l1);
+        }
+      }
+    };
+    auto unpack = [](const float4 &x0, const float4 &x1, double (&o)[NS]) {
+      const float f[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < NS; i++) o[i] = (double)f[i];
+    };
+    Raw cur, nxt;
+    fetch(lane, cur);
+    for (int t = lane; t < T; t += 32) {
+      fetch(t + 32, nxt);
+      double al[NS], be[NS], g[NS], G = 0.0;
+      unpack(cur.a0, cur.a1, al);
+      unpack(cur.b0, cur.b1, be);
+      {
+        float m = cur.l0[0];
+#pragma unroll
+        for (int i = 1; i < NS; i++) m = fmaxf(m, cur.l0[i]);
         acc_m += (double)m;  // sum_t m_t  (calc_probability); -inf when a frame has no density at all
       }
 #pragma unroll
@@ -297,15 +323,13 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
         acc_dm[i] += g[i];
       }
       if (t < T - 1) {
-        float l1[NS];
-        load_lb<NS>(logb + (base + t + 1) * NS, l1);
-        float m = l1[0];
+        float m = cur.l1[0];
 #pragma unroll
-        for (int i = 1; i < NS; i++) m = fmaxf(m, l1[i]);
+        for (int i = 1; i < NS; i++) m = fmaxf(m, cur.l1[i]);
         double q[NS], b1[NS];
-        load_row<NS>(beta_ws + (base + t + 1) * kFbRow, b1);
+        unpack(cur.c0, cur.c1, b1);
 #pragma unroll
-        for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * b1[j];
+        for (int j = 0; j < NS; j++) q[j] = exp_scaled(cur.l1[j] - ((m > kNegInf) ? m : 0.f)) * b1[j];
         double Z = 0.0;
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -322,6 +346,7 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
           if (i + 1 < NS) acc_num[i][1] += al[i] * A[i * NS + i + 1] * q[i + 1] * zs;      // j = i + 1
         }
       }
+      cur = nxt;
     }
     double *st = stats + (int64_t)v * stats_stride;
 #pragma unroll
