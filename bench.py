@@ -126,6 +126,8 @@ def run_ours(args):
     G = N * M
 
     ctx = api.Context(local, timing=False)
+    if args.upload_chunks:
+        ctx.set_option("upload_chunks", args.upload_chunks)
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
     ms = api.ModelSet.from_dict(mods)
 
@@ -470,6 +472,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-regimes", action="store_true", help="skip the decode-regime legs (c4 / c5 slices)")
+    ap.add_argument("--upload-chunks", type=int, default=0, help="override the library's upload chunk count (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
