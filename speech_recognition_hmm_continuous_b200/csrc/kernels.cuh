@@ -216,186 +216,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Training recursion: one warp per utterance (calc_alpha, calc_beta, calc_transition_probab,
-// calc_den_mix_coef, calc_probability; T-FS:1380-1664).  Lanes own frames for everything that is
-// parallel in time (exp, gamma, xi terms, stores); the N x N recurrences run redundantly on all
-// lanes with the per-frame operands broadcast by shuffle.
-//   b~_i(t) = exp(logb_i(t) - m_t), m_t = max_i logb_i(t)
-//   alpha^ as the reference; c~_t = 1/sum alpha~;   beta~_t = beta^_t e^{m_t}
-//   gamma_t(i) = alpha^_t(i) beta~_t(i) / c~_t      (= alpha^ beta^ / c_t of the reference)
-// Outputs: gamma32[F][N]; per-model statistics head (num_trans, den_trans, den_mix, sum_logp,
-// n_utt) by double atomics; logp_utt[U].
-// ------------------------------------------------------------------------------------------------
-constexpr int kFbWarps = 2;
-
-template <int NS>
-__global__ void __launch_bounds__(kFbWarps * 32)
-k_fwdbwd(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-         const double *__restrict__ Aall, int U, double *__restrict__ alpha_ws, double *__restrict__ cs_ws,
-         float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
-         double *__restrict__ logp_utt) {
-  __shared__ double sA[kFbWarps][NS * NS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x * kFbWarps + warp;
-  if (u >= U) return;
-  const int v = u2m[u];
-  if (v < 0) {  // masked utterance (its model has converged)
-    if (lane == 0 && logp_utt) logp_utt[u] = 0.0;
-    return;
-  }
-  const int64_t base = off[u];
-  const int T = (int)(off[u + 1] - base);
-  for (int k = lane; k < NS * NS; k += 32) sA[warp][k] = Aall[(int64_t)v * NS * NS + k];
-  __syncwarp();
-  const double *A = sA[warp];
-
-  // ---------------- forward ----------------
-  double al[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) al[i] = 0.0;
-  double lp_acc = 0.0;
-  for (int c0 = 0; c0 < T; c0 += 32) {
-    const int t = c0 + lane;
-    const bool valid = t < T;
-    float lbv[NS];
-    float mt = kNegInf;
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      lbv[i] = valid ? logb[(base + t) * NS + i] : 0.f;
-      mt = fmaxf(mt, lbv[i]);
-    }
-    double bt[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) bt[i] = (mt > kNegInf) ? exp((double)lbv[i] - (double)mt) : 0.0;
-    double my_al[NS], my_sum = 1.0, my_c = 1.0;
-#pragma unroll
-    for (int i = 0; i < NS; i++) my_al[i] = 0.0;
-    const int ns = min(32, T - c0);
-    for (int s = 0; s < ns; s++) {
-      double b[NS], an[NS];
-#pragma unroll
-      for (int i = 0; i < NS; i++) b[i] = __shfl_sync(0xffffffffu, bt[i], s);
-      if (c0 + s == 0) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) an[i] = (i == 0 ? 1.0 : 0.0) * b[i];  // pi = [1,0,..] T-FS:232-234
-      } else {
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          double aux = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) aux += al[j] * A[j * NS + i];
-          an[i] = aux * b[i];
-        }
-      }
-      double sum = 0.0;
-#pragma unroll
-      for (int i = 0; i < NS; i++) sum += an[i];
-      const double cs = 1.0 / sum;
-#pragma unroll
-      for (int i = 0; i < NS; i++) al[i] = an[i] * cs;
-      if (lane == s) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) my_al[i] = al[i];
-        my_sum = sum;
-        my_c = cs;
-      }
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < NS; i++) alpha_ws[(base + t) * NS + i] = my_al[i];
-      cs_ws[base + t] = my_c;
-      lp_acc += (double)mt + log(my_sum);  // -log c_t
-    }
-  }
-  double lp = warp_sum(lp_acc) + log(al[NS - 1]);  // calc_probability T-FS:1546-1549
-
-  // ---------------- backward + accumulators ----------------
-  double be[NS], bnext[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) { be[i] = 0.0; bnext[i] = 0.0; }
-  double acc_num[NS][2], acc_dt[NS], acc_dm[NS];
-#pragma unroll
-  for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
-  const int clast = ((T - 1) / 32) * 32;
-  for (int c0 = clast; c0 >= 0; c0 -= 32) {
-    const int t = c0 + lane;
-    const bool valid = t < T;
-    float lbv[NS];
-    float mt = kNegInf;
-    double my_al[NS], my_c = 1.0;
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      lbv[i] = valid ? logb[(base + t) * NS + i] : 0.f;
-      mt = fmaxf(mt, lbv[i]);
-      my_al[i] = valid ? alpha_ws[(base + t) * NS + i] : 0.0;
-    }
-    if (valid) my_c = cs_ws[base + t];
-    double bt[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) bt[i] = (mt > kNegInf) ? exp((double)lbv[i] - (double)mt) : 0.0;
-    double my_be[NS], my_benext[NS], my_bnext[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) { my_be[i] = 0.0; my_benext[i] = 0.0; my_bnext[i] = 0.0; }
-    const int ns = min(32, T - c0);
-    for (int s = ns - 1; s >= 0; s--) {
-      const double ct = __shfl_sync(0xffffffffu, my_c, s);
-      double bn[NS];
-      if (c0 + s == T - 1) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) bn[i] = (i == NS - 1 ? 1.0 : 0.0) * ct;  // final state only T-FS:1484-1490
-      } else {
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          double aux = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) aux += be[j] * A[i * NS + j] * bnext[j];
-          bn[i] = aux * ct;
-        }
-      }
-      if (lane == s) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) { my_be[i] = bn[i]; my_benext[i] = be[i]; my_bnext[i] = bnext[i]; }
-      }
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        be[i] = bn[i];
-        bnext[i] = __shfl_sync(0xffffffffu, bt[i], s);
-      }
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        const double g = my_al[i] * my_be[i] / my_c;  // alpha*beta/scale T-FS:1617,1658,1709
-        gamma[(base + t) * NS + i] = (float)g;
-        acc_dm[i] += g;
-        if (t < T - 1) {
-          acc_dt[i] += g;
-          acc_num[i][0] += my_al[i] * A[i * NS + i] * my_bnext[i] * my_benext[i];  // band j = i
-          if (i + 1 < NS) acc_num[i][1] += my_al[i] * A[i * NS + i + 1] * my_bnext[i + 1] * my_benext[i + 1];  // j = i+1
-        }
-      }
-    }
-  }
-  double *st = stats + (int64_t)v * stats_stride;
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-    double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
-    double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
-    if (lane == 0) {
-      atomicAdd(st + i * NS + i, n0);
-      if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
-      atomicAdd(st + NS * NS + i, dt);
-      atomicAdd(st + NS * NS + NS + i, dm);
-    }
-  }
-  if (lane == 0) {
-    atomicAdd(st + off_sumlogp, lp);
-    atomicAdd(st + off_sumlogp + 1, 1.0);
-    if (logp_utt) logp_utt[u] = lp;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Mixture accumulators (calc_mix_param, T-FS:1691-1727), CUDA-core version.
 // CTA (part p, model v, Gaussian chunk gcx) walks the utterances of model v assigned to part p.
 // Thread (d, gg) owns column d of kAccGPT Gaussians g = k*NGG + gg of the chunk:
