@@ -74,6 +74,13 @@ int hmmcu_set_features_device(hmmcu_ctx *ctx, const double *x_dev, const int64_t
 int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A, const double *c,
                      const double *mu, const double *inv_var, const double *det);
 
+/* creating_initial_model (T-FS:732-1317) on the device for V words at once, from the context's features:
+ * utterance u belongs to word utt2model[u] (-1 = not used).  Uniform left-to-right A, uniform segmentation,
+ * LBG splitting (x1.005 / x0.995) with three k-means passes per level and the empty-cell rule, per-cluster
+ * variances (floored at 1e-5) and weights.  The models are left in the context as hmmcu_set_models would leave
+ * them (hmmcu_get_models reads them back) and are bit-identical to hmmh_init_model()'s.  D <= 64, M <= 255. */
+int hmmcu_init_models(hmmcu_ctx *ctx, const int32_t *utt2model, int V, int N, int M);
+
 /* ---------------------------------------------------------------- emissions -------------- */
 /* Parity / debug export of calc_symbol_probab + calc_gaus (T-FS:1749-1841, R-FS:860-947) for
  * utterance u against model v, as the device path computes them: logb[T][N] = log b_i(t), and
@@ -139,7 +146,7 @@ int hmmcu_viterbi_scores(hmmcu_ctx *ctx, double *score);
 /* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
 int64_t hmmcu_launch_count(const hmmcu_ctx *ctx);
 /* Device time in ms of the most recent call's kernels, by name (CUDA events on the context's
- * stream).  names: "emis", "fwdbwd", "accum", "mstep", "score", "viterbi", "logb64", "pack".  -1 if unknown.
+ * stream).  names: "emis", "fwdbwd", "accum", "mstep", "score", "viterbi", "logb64", "pack", "init".  -1 if unknown.
  * Two pseudo-names report state instead of time: "kappa" (accuracy-guard value) and "tc_active"
  * (1 if the last emission launch ran on tensor cores). */
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name);

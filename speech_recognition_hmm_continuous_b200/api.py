@@ -19,7 +19,7 @@ _lp = C.POINTER(C.c_int64)
 EXPORTS = [
     "hmmcu_create", "hmmcu_destroy", "hmmcu_last_error", "hmmcu_device_count", "hmmcu_stream", "hmmcu_synchronize",
     "hmmcu_host_alloc", "hmmcu_host_free", "hmmcu_set_option", "hmmcu_set_features", "hmmcu_set_features_device", "hmmcu_set_models",
-    "hmmcu_emissions", "hmmcu_forward_scores", "hmmcu_rank", "hmmcu_stats_size", "hmmcu_estep", "hmmcu_stats_device",
+    "hmmcu_init_models", "hmmcu_emissions", "hmmcu_forward_scores", "hmmcu_rank", "hmmcu_stats_size", "hmmcu_estep", "hmmcu_stats_device",
     "hmmcu_stats_download", "hmmcu_em_reset", "hmmcu_mstep", "hmmcu_get_models", "hmmcu_viterbi", "hmmcu_viterbi_scores", "hmmcu_launch_count", "hmmcu_last_kernel_ms",
     "hmmcu_enable_timing", "hmmh_model_alloc", "hmmh_model_free", "hmmh_read_features", "hmmh_write_features",
     "hmmh_read_model", "hmmh_write_model", "hmmh_init_model", "hmmh_mstep", "hmmh_upload_models", "hmmh_train",
@@ -76,6 +76,7 @@ def load():
     lib.hmmcu_set_features_device.argtypes = [C.c_void_p, C.c_void_p, _lp, C.c_int, C.c_int]
     lib.hmmcu_set_models.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
     lib.hmmcu_emissions.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+    lib.hmmcu_init_models.argtypes = [C.c_void_p, _ip, C.c_int, C.c_int, C.c_int]
     lib.hmmcu_forward_scores.argtypes = [C.c_void_p, _dp, C.c_int]
     lib.hmmcu_viterbi_scores.argtypes = [C.c_void_p, _dp]
     lib.hmmcu_rank.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, C.c_double, _ip, _ip]
@@ -215,6 +216,13 @@ class Context:
         self.V, self.N, self.M = ms.V, ms.N, ms.M
         self._ck(self.lib.hmmcu_set_models(self.h, ms.V, ms.N, ms.M, ms.D, _d(ms.A), _d(ms.c), _d(ms.mu), _d(ms.iv), _d(ms.det)),
                  "hmmcu_set_models")
+
+    def init_models(self, utt2model, V, N, M):
+        """hmmcu_init_models: the reference's initial-model builder for V words on the device -> ModelSet."""
+        u2m = np.ascontiguousarray(utt2model, dtype=np.int32)
+        self._ck(self.lib.hmmcu_init_models(self.h, u2m.ctypes.data_as(_ip), int(V), int(N), int(M)), "hmmcu_init_models")
+        self.V, self.N, self.M = int(V), int(N), int(M)
+        return self.get_models(self.D)
 
     # ---- compute ----
     def emissions(self, u, v):

@@ -17,6 +17,7 @@
 #include "tc_kernels.cuh"
 #include "ws_kernels.cuh"
 #include "vit_kernels.cuh"
+#include "init_kernels.cuh"
 
 using namespace hmmk;
 
@@ -108,7 +109,8 @@ struct hmmcu_ctx {
 
   // training map
   std::vector<int32_t> u2m;
-  DevBuf u2m_d, mus_d, mu_d, tiles_d;  // utt2model, model_utt_start, model_utts, emission tiles
+  DevBuf u2m_d, mus_d, mu_d, tiles_d;
+  DevBuf in_lst, in_off, in_vk, in_cent, in_sum, in_dist, in_cnt, in_idx, in_dd, in_ord;  // initial-model builder  // utt2model, model_utt_start, model_utts, emission tiles
   int64_t n_train_tiles = 0;
   int max_utts_per_model = 0;
 
@@ -271,7 +273,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
-                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids};
+                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
+                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -473,6 +476,124 @@ int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A
   if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
   ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = (int)G;
   ctx->Dm = D;
+  ctx->have_models = true;
+  ctx->pack_dirty = true;
+  ctx->kappa_stale = true;
+  ctx->cfg_epoch++;
+  return HMMCU_OK;
+}
+
+// ------------------------------------------------------------- initial models on the device ----
+// creating_initial_model (T-FS:732-1317) for V words at once from the context's features: utterance u belongs
+// to word utt2model[u] (-1 = not used).  The models are left in the context exactly as hmmcu_set_models would
+// leave them (read them back with hmmcu_get_models).  Bit-identical to hmmh_init_model(), see init_kernels.cuh.
+int hmmcu_init_models(hmmcu_ctx *ctx, const int32_t *utt2model, int V, int N, int M) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (!ctx->have_features || ctx->U < 1 || !ctx->d_x64) return fail(ctx, HMMCU_EINVAL, "init_models: set the features first");
+  if (!utt2model || V < 1 || N < 1 || N > 8 || M < 1 || M > 255) return fail(ctx, HMMCU_EINVAL, "init_models: bad arguments (N <= 8, M <= 255)");
+  const int D = ctx->D, U = ctx->U;
+  if (D > 64) return fail(ctx, HMMCU_EINVAL, "init_models: D=%d not supported on the device (max 64); use hmmh_init_model", D);
+  CK(cudaSetDevice(ctx->dev));
+  const int VN = V * N;
+  // the frames of every (word, state) in the reference's order: utterance by utterance, uniform segments (T-FS:1005-1013)
+  std::vector<int32_t> cntv((size_t)VN + 1, 0);
+  for (int u = 0; u < U; u++) {
+    const int v = utt2model[u];
+    if (v < -1 || v >= V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, v);
+    if (v < 0) continue;
+    const int T = (int)(ctx->off[u + 1] - ctx->off[u]), q = T / N, r = T % N;
+    for (int k = 0; k < N; k++) cntv[(size_t)v * N + k + 1] += q + (k < r ? 1 : 0);
+  }
+  for (int i = 0; i < VN; i++) cntv[i + 1] += cntv[i];
+  const int64_t E = cntv[VN];
+  if (E == 0) return fail(ctx, HMMCU_EINVAL, "init_models: no frames");
+  std::vector<int32_t> lst((size_t)E), vk((size_t)E), fill(cntv.begin(), cntv.end() - 1);
+  for (int u = 0; u < U; u++) {
+    const int v = utt2model[u];
+    if (v < 0) continue;
+    const int64_t f0 = ctx->off[u];
+    const int T = (int)(ctx->off[u + 1] - f0), q = T / N, r = T % N;
+    int t = 0;
+    for (int k = 0; k < N; k++) {
+      const int len = q + (k < r ? 1 : 0);
+      int32_t &w = fill[(size_t)v * N + k];
+      for (int j = 0; j < len; j++, t++) { lst[w] = (int32_t)(f0 + t); vk[w] = v * N + k; w++; }
+    }
+  }
+  const size_t GD = (size_t)VN * M * D, G = (size_t)VN * M;
+  CK(ctx->in_lst.ensure(sizeof(int32_t) * E));
+  CK(ctx->in_vk.ensure(sizeof(int32_t) * E));
+  CK(ctx->in_off.ensure(sizeof(int32_t) * (VN + 1)));
+  CK(ctx->in_cent.ensure(sizeof(double) * GD));
+  CK(ctx->in_sum.ensure(sizeof(double) * GD));
+  CK(ctx->in_dist.ensure(sizeof(double) * G));
+  CK(ctx->in_cnt.ensure(sizeof(double) * G));
+  CK(ctx->in_idx.ensure((size_t)E));
+  CK(ctx->in_dd.ensure(sizeof(double) * E));
+  CK(ctx->in_ord.ensure(sizeof(int) * G));
+  CK(ctx->A.ensure(sizeof(double) * VN * N));
+  CK(ctx->c.ensure(sizeof(double) * G));
+  CK(ctx->mu.ensure(sizeof(double) * GD));
+  CK(ctx->iv.ensure(sizeof(double) * GD));
+  CK(ctx->det.ensure(sizeof(double) * G));
+  CK(cudaMemcpyAsync(ctx->in_lst.p, lst.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->in_vk.p, vk.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->in_off.p, cntv.data(), sizeof(int32_t) * (VN + 1), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemsetAsync(ctx->in_cent.p, 0, sizeof(double) * GD, ctx->st));
+  CK(cudaMemsetAsync(ctx->in_dist.p, 0, sizeof(double) * G, ctx->st));
+  const double *x = ctx->d_x64;
+  auto classify = [&](int have) -> int {
+    k_init_classify<<<(unsigned)((E + 255) / 256), 256, 0, ctx->st>>>(x, ctx->in_lst.as<int32_t>(), ctx->in_vk.as<int32_t>(), E, ctx->in_cent.as<double>(), M, D,
+                                                                     have, ctx->in_idx.as<uint8_t>(), ctx->in_dd.as<double>());
+    LAUNCH_CHECK();
+    return HMMCU_OK;
+  };
+  auto accumulate = [&](int have, int mode, bool all) -> int {
+    const int warps = VN * have;
+    k_init_accumulate<<<(warps * 32 + 127) / 128, 128, 0, ctx->st>>>(x, ctx->in_lst.as<int32_t>(), ctx->in_off.as<int32_t>(), ctx->in_idx.as<uint8_t>(),
+                                                                    ctx->in_dd.as<double>(), ctx->in_cent.as<double>(), VN, M, D, have, mode, all,
+                                                                    ctx->in_sum.as<double>(), ctx->in_dist.as<double>(), ctx->in_cnt.as<double>());
+    LAUNCH_CHECK();
+    return HMMCU_OK;
+  };
+  auto update = [&](int have, int have_next) -> int {
+    k_init_update<<<(VN + 63) / 64, 64, 0, ctx->st>>>(ctx->in_cent.as<double>(), ctx->in_sum.as<double>(), ctx->in_dist.as<double>(), ctx->in_cnt.as<double>(),
+                                                     VN, M, D, have, have_next, ctx->in_ord.as<int>());
+    LAUNCH_CHECK();
+    return HMMCU_OK;
+  };
+  auto split_to = [&](int have) { return have >= M ? have : (2 * have < M ? 2 * have : M); };
+  int rc;
+  t_begin(ctx, "init");
+  // one centroid per state (T-FS:996-1030), then the first split
+  if ((rc = accumulate(1, 0, true)) != HMMCU_OK) return rc;
+  int have = split_to(1);
+  if ((rc = update(1, have)) != HMMCU_OK) return rc;
+  while (have > 1) {  // three k-means passes per level (T-FS:1034-1094); the last one also splits for the next level
+    for (int pass = 0; pass < 3; pass++) {
+      if ((rc = classify(have)) != HMMCU_OK) return rc;
+      if ((rc = accumulate(have, 0, false)) != HMMCU_OK) return rc;
+      const int nxt = (pass == 2) ? split_to(have) : have;
+      if ((rc = update(have, nxt)) != HMMCU_OK) return rc;
+      if (pass == 2) {
+        if (nxt == have) have = 0;  // M reached: done
+        else have = nxt;
+      }
+    }
+  }
+  // variances and weights (init_mix_param, T-FS:864-932)
+  if ((rc = classify(M)) != HMMCU_OK) return rc;
+  if ((rc = accumulate(M, 1, M == 1)) != HMMCU_OK) return rc;
+  k_init_finish<<<(VN + 63) / 64, 64, 0, ctx->st>>>(ctx->in_cent.as<double>(), ctx->in_sum.as<double>(), ctx->in_cnt.as<double>(), ctx->in_off.as<int32_t>(), V, N,
+                                                   M, D, ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(), ctx->iv.as<double>(),
+                                                   ctx->det.as<double>());
+  LAUNCH_CHECK();
+  t_end(ctx, "init");
+  CK(cudaStreamSynchronize(ctx->st));  // the host vectors above were copied asynchronously
+  if (V != ctx->V || N != ctx->N || M != ctx->M) ctx->u2m.clear();
+  ctx->V = V; ctx->N = N; ctx->M = M; ctx->G = N * M;
+  ctx->Dm = D;
+  ctx->banded = true;  // the DELTA = 1 band
   ctx->have_models = true;
   ctx->pack_dirty = true;
   ctx->kappa_stale = true;

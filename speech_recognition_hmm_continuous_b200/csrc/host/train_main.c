@@ -104,6 +104,11 @@ int hmmh_train_main(int argc, char **argv) {
   fclose(fl);
   if (U == 0) die("file %s not found \n", list);
 
+  hmmcu_ctx *ctx = NULL;
+  if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+  if (hmmcu_set_features(ctx, x, off, U, D) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
+  int32_t *u2m = (int32_t *)calloc((size_t)U, sizeof(int32_t));
+
   hmmh_model m;
   memset(&m, 0, sizeof(m));
   if (argc == 2 * P + 6) {
@@ -111,15 +116,18 @@ int hmmh_train_main(int argc, char **argv) {
     if (m.D != D) die("reading error on file %s \n", argv[argc - 1]);
   } else {
     if (hmmh_model_alloc(&m, N, M, D) != HMMCU_OK) die("error on allocating memory. %s\n", "");
-    hmmh_init_model(&m, x, off, U);
+    /* creating_initial_model (T-FS:226, 732-1317): on the device (bit-identical to the host version, which stays
+     * as the path for feature widths / mixture counts the device builder does not take) */
+    if (D <= 64 && M <= 255 && N <= 8) {
+      if (hmmcu_init_models(ctx, u2m, 1, N, M) != HMMCU_OK || hmmcu_get_models(ctx, m.A, m.c, m.mu, m.inv_var, m.det) != HMMCU_OK)
+        die("GPU error: %s \n", hmmcu_last_error(ctx));
+    } else {
+      hmmh_init_model(&m, x, off, U);
+    }
   }
   memset(m.word, 0, sizeof(m.word));
   strncpy(m.word, word, sizeof(m.word) - 1);
 
-  hmmcu_ctx *ctx = NULL;
-  if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
-  if (hmmcu_set_features(ctx, x, off, U, D) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
-  int32_t *u2m = (int32_t *)calloc((size_t)U, sizeof(int32_t));
   double mean = 0.0;
   int iters = 0;
   printf("\r\nCreating HMM using Forward-Backward algorithm (Baum-Welch)");

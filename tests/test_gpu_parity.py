@@ -450,3 +450,23 @@ def test_decode_paths_other_shapes(ctx, N, M, D):
         assert (path[off[u]:off[u + 1]] == p_o).all() and abs(vs[u] - s_o) <= 1e-9 * abs(s_o)
     lab, _ = ctx.rank(sc)
     assert (lab == labels).all()
+
+
+@pytest.mark.parametrize("N,M", [(5, 1), (5, 3), (5, 16), (3, 6), (6, 2)])
+def test_device_initial_models_are_bit_identical_to_the_host_builder(N, M):
+    """hmmcu_init_models (creating_initial_model, T-FS:732-1317, for all words at once on the device) against
+    hmmh_init_model, the host restatement that tests/test_host_cpu.py pins to the oracle: same IEEE operations in
+    the same order, so every parameter must be equal bit for bit."""
+    V, U = 3, 12
+    ms, x, off, labels = _synth(V, N, max(M, 2), U, seed=4242 + N * M, tmin=40, tmax=90)
+    c = api.Context(0)
+    c.set_features(x, off)
+    got = c.init_models(labels, V, N, M)
+    c.close()
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])]).astype(np.int64)
+        want = api.init_model(N, M, xv, offv)
+        for name in ("A", "c", "mu", "iv", "det"):
+            assert np.array_equal(getattr(got, name)[v], getattr(want, name)[0]), (v, name)
