@@ -232,6 +232,27 @@ def run_ours(args):
                      "kernel_ms": {k: ctx.kernel_ms(k) for k in kn},
                      "frame_model_pairs_per_s": (F * V * world / (float(t.item()) * 1e-3)) if name == "forward" else None}
 
+    # initial-model builder (creating_initial_model, T-FS:732-1317): all words on the device vs the host builder
+    # (single-threaded C, one word after the other) -- what the drop-in trainer pays before its first EM iteration
+    init = None
+    if world == 1:
+        ctx.set_features_device(xdev.data_ptr(), off, D)
+        ctx.init_models(labels, V, N, M)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ctx.init_models(labels, V, N, M)
+        dev_ms = (time.perf_counter() - t0) / reps * 1e3
+        us0 = np.nonzero(labels == 0)[0]
+        x0 = np.concatenate([x[off[u]:off[u + 1]] for u in us0])
+        off0 = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us0])]).astype(np.int64)
+        t0 = time.perf_counter()
+        api.init_model(N, M, x0, off0)
+        host_ms_word = (time.perf_counter() - t0) * 1e3
+        init = {"device_ms_all_words": dev_ms, "host_ms_one_word": host_ms_word, "host_ms_all_words_extrapolated": host_ms_word * V,
+                "note": "wall clock incl. the read-back of the models; results are bit-identical (tests)"}
+        ctx.set_models(ms)
     pk = peaks()
     ms_step = tot_ms / args.steps
     value = F * world / (ms_step * 1e-3)
@@ -260,7 +281,7 @@ def run_ours(args):
         "e2e": {"value": F * world / (e2e_ms / e2e_steps * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": int(x.nbytes + off.nbytes),
                 "d2h_bytes_per_step": int(8 * (3 * V + 1))},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "decode": dec,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "decode": dec, "init_model": init,
         "wall_s_timed_region": wall,
     }
     ctx.close()
