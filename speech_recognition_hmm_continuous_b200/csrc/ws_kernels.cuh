@@ -197,7 +197,8 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
 // MP: padded mixtures per state when <= 16 (1, 2, 4, 8, 16); 0 = a multiple of 16 given at run time (M)
 // Warps: 0-7 epilogue (lane quarter w & 3; column groups of parity w >> 2), 8-15 loaders (lane quarter w & 3;
 // chunks 0-2 / 3-4 of the doubled row), 16 MMA issuer.
-template <bool TRAIN, int MP, bool DBG>
+// MR: mixtures of a state that are real (MR <= MP; the others are pad columns the log-sum-exp may skip), 0 = all MP
+template <bool TRAIN, int MP, bool DBG, int MR = 0>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nframes_dec, const int32_t *__restrict__ frame_ids,
           const float *__restrict__ x32, const float *__restrict__ images, int N, int M, int DP, int TN, float *__restrict__ logb,
@@ -237,6 +238,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   // Images wider than 96 columns (one state of up to 176 mixtures) leave room for a single operand stage.
   const int AST = TN > 96 ? 1 : 2;
   const uint32_t ACS = TN > 96 ? (uint32_t)TN : 96u, acc0 = (uint32_t)AST * 160;
+  __shared__ __align__(16) float skc[2][kWsMaxTN1];  // kc2 of the image the epilogue works on (two slots: image switches alternate)
   __shared__ float2 xch[2][4][32][kWsXch];  // partial (max, sum) of the odd chunks' warp, per unit parity / quarter / lane / state
 
   const int per = (nunits + gridDim.x - 1) / gridDim.x;
@@ -382,8 +384,21 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     const int mp = MP ? MP : M;               // M here is the padded count
     const int cpg = MP ? 1 : mp / 16;         // chunks per group: a chunk of 16/MP whole states, or one state of M/16 chunks
     const int spg = MP ? 16 / (MP ? MP : 16) : 1;  // states per group (16 % MP pad columns close a chunk)
+    int epi_img = -1, nsw = 0;
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
       const TcTile unit = un0;
+      if (unit.img != epi_img) {
+        // The additive constants of a new image go to shared memory once (global loads of them in every unit sat on
+        // the critical path: the L1 lines do not survive the feature and image streams).  All eight epilogue warps
+        // walk the units in the same order, so they meet here; two slots, so nobody overwrites what a slower warp
+        // still reads.
+        epi_img = unit.img;
+        const float *kcg = images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4;
+        for (int c = tid; c < TN; c += 256) skc[nsw & 1][c] = __ldg(kcg + c);
+        asm volatile("bar.sync 9, 256;" ::: "memory");
+        nsw++;
+      }
+      const float *kcs = skc[(nsw - 1) & 1];
       const int64_t f = fcur;
       const int64_t fnext = frame_of(un1);
       const TcTile un2 = unit_at(ui + 2);
@@ -397,9 +412,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       const bool live = row < unit.nrows;
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
       const uint32_t d = tmem0 + acc0 + (uint32_t)s * ACS + trow;
-      // kc2 of this unit's image from global memory (L1-resident, same address for the whole warp): the
-      // shared-memory image may already belong to a later unit
-      const float4 *kc4 = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4);
+      const float4 *kc4 = reinterpret_cast<const float4 *>(kcs);  // warp-uniform addresses: broadcast loads
       constexpr int kMaxG = (kWsMaxTN / 16 + 1) / 2;  // groups per warp when a group is one chunk
       if (MP) {
         // my groups: g = h, h + 2, ...; every accumulator chunk of mine in flight at once
@@ -412,7 +425,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         for (int k = 0; k < kMaxG; k++) {
           const int c = h + 2 * k;
           if (c < ngroups) {
-            const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+            const float4 k0 = kc4[c * 4], k1 = kc4[c * 4 + 1], k2 = kc4[c * 4 + 2], k3 = kc4[c * 4 + 3];
             const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
             float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
 #pragma unroll
@@ -421,13 +434,14 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
             float lbv[SPC];
 #pragma unroll
             for (int g = 0; g < SPC; g++) {
+              constexpr int MU = MR ? MR : MP;  // columns MU .. MP-1 of a state are pad (density 0)
               float m = val[g * MP];
 #pragma unroll
-              for (int j = 1; j < MP; j++) m = fmaxf(m, val[g * MP + j]);
+              for (int j = 1; j < MU; j++) m = fmaxf(m, val[g * MP + j]);
               const float ms = (m > kNegInf) ? m : 0.f;
               float sm_ = 0.f;
 #pragma unroll
-              for (int j = 0; j < MP; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
+              for (int j = 0; j < MU; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
               lbv[g] = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
             }
             // the chunk's states are contiguous in the output row: 16- / 8-byte stores when the row allows it (a lane
@@ -462,7 +476,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
               const int c = sx * cpg + cc;
               uint32_t v[16];
               tmem_ld16(d + c * 16, v);
-              const float4 k0 = __ldg(kc4 + c * 4), k1 = __ldg(kc4 + c * 4 + 1), k2 = __ldg(kc4 + c * 4 + 2), k3 = __ldg(kc4 + c * 4 + 3);
+              const float4 k0 = kc4[c * 4], k1 = kc4[c * 4 + 1], k2 = kc4[c * 4 + 2], k3 = kc4[c * 4 + 3];
               const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
               float val[16];
 #pragma unroll
