@@ -110,6 +110,12 @@ struct hmmcu_ctx {
   // training map
   std::vector<int32_t> u2m;
   DevBuf u2m_d, mus_d, mu_d, tiles_d;
+  DevBuf vit_map, vit_tiles;
+  std::vector<int32_t> vit_u2m;
+  int64_t n_vit_tiles = 0;
+  uint64_t feat_epoch = 1, vit_epoch = 0;  // feat_epoch: bumped when the utterance geometry changes
+  int32_t *path_h = nullptr;   // pinned staging for hmmcu_viterbi's path
+  size_t path_h_cap = 0;
   DevBuf in_lst, in_off, in_vk, in_cent, in_sum, in_dist, in_cnt, in_idx, in_dd, in_ord;  // initial-model builder  // utt2model, model_utt_start, model_utts, emission tiles
   int64_t n_train_tiles = 0;
   int max_utts_per_model = 0;
@@ -274,7 +280,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
-                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord};
+                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -284,6 +290,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   if (ctx->g_mstep.exec) cudaGraphExecDestroy(ctx->g_mstep.exec);
   if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
   if (ctx->ctr_h) cudaFreeHost(ctx->ctr_h);
+  if (ctx->path_h) cudaFreeHost(ctx->path_h);
   for (cudaEvent_t e : ctx->ev_chunk)
     if (e) cudaEventDestroy(e);
   if (ctx->ev_idle) cudaEventDestroy(ctx->ev_idle);
@@ -357,6 +364,7 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
     ctx->off.assign(frame_off, frame_off + U + 1);
     ctx->u2m.clear();
     ctx->cfg_epoch++;
+    ctx->feat_epoch++;
   }
   ctx->pack_dirty = true;  // the centre may move
   ctx->kappa_stale = true;
@@ -1508,17 +1516,23 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
   if (ctx->Dm != ctx->D) return fail(ctx, HMMCU_EINVAL, "models have D=%d but features have D=%d", ctx->Dm, ctx->D);
   const size_t lsm = logb64_smem_bytes(ctx->M, ctx->D);
   if (lsm > 227 * 1024) return fail(ctx, HMMCU_EINVAL, "M=%d mixtures x D=%d does not fit the double-precision emission kernel", ctx->M, ctx->D);
-  std::vector<EmisTile> tiles;
-  for (int u = 0; u < U; u++) {
-    const int64_t f0 = ctx->off[u];
-    const int T = (int)(ctx->off[u + 1] - f0);
-    for (int t = 0; t < T; t += kLbFrames) tiles.push_back({f0 + t, std::min(kLbFrames, T - t), utt2model[u]});
+  // tiles and the utterance -> model map only change with the utterance geometry or utt2model: kept between calls
+  if (ctx->vit_epoch != ctx->feat_epoch || (int)ctx->vit_u2m.size() != U || memcmp(ctx->vit_u2m.data(), utt2model, sizeof(int32_t) * U) != 0) {
+    std::vector<EmisTile> tiles;
+    for (int u = 0; u < U; u++) {
+      const int64_t f0 = ctx->off[u];
+      const int T = (int)(ctx->off[u + 1] - f0);
+      for (int t = 0; t < T; t += kLbFrames) tiles.push_back({f0 + t, std::min(kLbFrames, T - t), utt2model[u]});
+    }
+    CK(ctx->vit_map.ensure(sizeof(int32_t) * U));
+    CK(cudaMemcpyAsync(ctx->vit_map.p, utt2model, sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+    CK(ctx->vit_tiles.ensure(sizeof(EmisTile) * tiles.size()));
+    CK(cudaMemcpyAsync(ctx->vit_tiles.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->n_vit_tiles = (int64_t)tiles.size();
+    ctx->vit_u2m.assign(utt2model, utt2model + U);
+    ctx->vit_epoch = ctx->feat_epoch;
   }
-  DevBuf map;
-  CK(map.ensure(sizeof(int32_t) * U));
-  CK(cudaMemcpyAsync(map.p, utt2model, sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
-  CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
-  CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
   CK(ctx->logb64.ensure(sizeof(double) * (size_t)ctx->F * ctx->N));
   CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
   CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
@@ -1526,26 +1540,35 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
   t_begin(ctx, "logb64");
   if (ctx->D == 39) {  // the MFCC + delta + delta-delta layout every config uses
     CK(cudaFuncSetAttribute(k_logb64<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-    k_logb64<39><<<(unsigned)tiles.size(), kLbFrames, lsm, ctx->st>>>(ctx->tiles_dec.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
+    k_logb64<39><<<(unsigned)ctx->n_vit_tiles, kLbFrames, lsm, ctx->st>>>(ctx->vit_tiles.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
                                                                      ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
                                                                      ctx->N, ctx->M, ctx->D, ctx->logb64.as<double>());
   } else {
     CK(cudaFuncSetAttribute(k_logb64<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-    k_logb64<0><<<(unsigned)tiles.size(), kLbFrames, lsm, ctx->st>>>(ctx->tiles_dec.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
+    k_logb64<0><<<(unsigned)ctx->n_vit_tiles, kLbFrames, lsm, ctx->st>>>(ctx->vit_tiles.as<EmisTile>(), ctx->d_x64, ctx->c.as<double>(),
                                                                     ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
                                                                     ctx->N, ctx->M, ctx->D, ctx->logb64.as<double>());
   }
   LAUNCH_CHECK();
   t_end(ctx, "logb64");
   t_begin(ctx, "viterbi");
-  DISPATCH_N(ctx->N, CK(ScoreLaunch<NS>::path(ctx, ctx->logb64.as<double>(), map.as<int32_t>(), ctx->logp_utt_d.as<double>(),
+  DISPATCH_N(ctx->N, CK(ScoreLaunch<NS>::path(ctx, ctx->logb64.as<double>(), ctx->vit_map.as<int32_t>(), ctx->logp_utt_d.as<double>(),
                                                path ? ctx->path_d.as<int32_t>() : nullptr)));
   LAUNCH_CHECK();
   t_end(ctx, "viterbi");
   CK(cudaMemcpyAsync(score, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
-  if (path) CK(cudaMemcpyAsync(path, ctx->path_d.p, sizeof(int32_t) * ctx->F, cudaMemcpyDeviceToHost, ctx->st));
+  if (path) {  // through pinned staging: a copy into pageable memory is staged by the driver in small pieces
+    if ((size_t)ctx->F > ctx->path_h_cap) {
+      if (ctx->path_h) cudaFreeHost(ctx->path_h);
+      ctx->path_h = nullptr;
+      ctx->path_h_cap = 0;
+      CK(cudaMallocHost((void **)&ctx->path_h, sizeof(int32_t) * (size_t)ctx->F));
+      ctx->path_h_cap = (size_t)ctx->F;
+    }
+    CK(cudaMemcpyAsync(ctx->path_h, ctx->path_d.p, sizeof(int32_t) * ctx->F, cudaMemcpyDeviceToHost, ctx->st));
+  }
   CK(cudaStreamSynchronize(ctx->st));
-  map.release();
+  if (path) memcpy(path, ctx->path_h, sizeof(int32_t) * (size_t)ctx->F);
   return HMMCU_OK;
 }
 
