@@ -401,6 +401,18 @@ def write_features(path, x):
         raise HmmCudaError("hmmh_write_features(%s) failed (%d)" % (path, rc))
 
 
+def shard_utterances(off, rank, world):
+    """Utterances [u0, u1) of rank `rank` out of `world`: contiguous, balanced by frame count (the
+    utterances are partitioned across the GPUs by contiguous frame count; every rank keeps the full model set and
+    the sufficient statistics are summed with one all-reduce per EM iteration)."""
+    off = np.asarray(off, dtype=np.int64)
+    U, F = len(off) - 1, int(off[-1])
+    cuts = [int(np.searchsorted(off, (k * F + world - 1) // world, side="left")) for k in range(world + 1)]
+    cuts[0], cuts[-1] = 0, U
+    cuts = np.maximum.accumulate(np.minimum(cuts, U))
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
 def stack_models(sets):
     """Concatenates single-topology ModelSets along V."""
     return ModelSet(np.concatenate([s.A for s in sets]), np.concatenate([s.c for s in sets]), np.concatenate([s.mu for s in sets]),
