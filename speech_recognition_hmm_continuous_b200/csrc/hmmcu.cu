@@ -135,6 +135,7 @@ struct hmmcu_ctx {
   DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
+  int use_seg_fb = 1;  // time-parallel forward-backward (k_fb_seg) when the utterances fit in shared memory (0 = k_fb)
   int debug_acc = 0;
   bool acc_dirty = true;
   int64_t n_acc_units = 0;
@@ -333,6 +334,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
+  if (strcmp(key, "seg_fb") == 0) { ctx->use_seg_fb = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1299,6 +1301,22 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     // 2. forward / backward, gamma, transition statistics, log-probabilities
     t_begin(ctx, "fwdbwd");
     {
+      if (ctx->use_seg_fb && fb_seg_fits(N, ctx->Tmax)) {
+        const int blocks = (U + kSegUtts - 1) / kSegUtts;
+        const size_t fsm = fb_seg_smem_bytes(N, ctx->Tmax);
+        if (ctx->banded) {
+          DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, true><<<blocks, kSegThreads, fsm, ctx->st>>>(
+                            ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
+                            ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                            ss, off_lp, ctx->logp_utt_d.as<double>())));
+        } else {
+          DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, false><<<blocks, kSegThreads, fsm, ctx->st>>>(
+                            ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
+                            ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
+                            ss, off_lp, ctx->logp_utt_d.as<double>())));
+        }
+        LAUNCH_CHECK();
+      } else {
       const int blocks = (U + kFbUtts - 1) / kFbUtts;
       const size_t fsm = fb_smem_bytes(N);
       if (ctx->banded) {
@@ -1313,6 +1331,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       }
       LAUNCH_CHECK();
+      }
     }
     t_end(ctx, "fwdbwd");
     // 3. mixture accumulators
