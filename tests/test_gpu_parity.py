@@ -470,3 +470,34 @@ def test_device_initial_models_are_bit_identical_to_the_host_builder(N, M):
         want = api.init_model(N, M, xv, offv)
         for name in ("A", "c", "mu", "iv", "det"):
             assert np.array_equal(getattr(got, name)[v], getattr(want, name)[0]), (v, name)
+
+
+def test_time_parallel_and_windowed_forward_backward_agree():
+    """k_fb_seg (segments, unit vectors, boundary combination) against k_fb (one chain per utterance, windows):
+    same statistics and log-likelihoods; ragged lengths including T < 8 segments; and an utterance too long for
+    the time-parallel kernel's shared memory takes the windowed kernel on its own."""
+    ms, x, off, labels = _synth(2, 5, 3, 10, seed=777, tmin=3, tmax=140)
+    out = []
+    for seg in (1, 0):
+        c = api.Context(0)
+        c.set_option("seg_fb", seg)
+        c.set_features(x, off)
+        c.set_models(ms)
+        out.append(c.estep(labels))
+        c.close()
+    (st1, lp1), (st0, lp0) = out
+    fin = np.isfinite(lp0)
+    assert (np.isfinite(lp1) == fin).all() and np.allclose(lp1[fin], lp0[fin], rtol=1e-9)
+    sf = np.isfinite(st0)  # sum_logp is -inf for a word with an utterance shorter than its state chain
+    assert (np.isfinite(st1) == sf).all() and (st1[~sf] == st0[~sf]).all()
+    assert np.allclose(st1[sf], st0[sf], rtol=2e-5, atol=1e-6 * np.abs(st0[sf]).max())
+    # a long utterance (T x N beyond the shared-memory budget of k_fb_seg): the library falls back by itself
+    msl, xl, offl, labl = _synth(1, 5, 2, 2, seed=778, tmin=1100, tmax=1200)
+    c = api.Context(0)
+    c.set_features(xl, offl)
+    c.set_models(msl)
+    _, lpl = c.estep(labl)
+    c.close()
+    for u in range(2):
+        want = o.forward_score(_oracle_model(msl, 0), xl[offl[u]:offl[u + 1]])
+        assert abs(lpl[u] - want) <= RTOL * abs(want)
