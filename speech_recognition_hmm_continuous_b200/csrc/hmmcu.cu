@@ -1358,7 +1358,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
         }
         LAUNCH_CHECK();
       }
-      k_finalize_slots<<<dim3((G + 3) / 4, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ss, G, D, DP, tc_kp2(2 * DP), (G + 127) / 128, off_S0,
+      k_finalize_slots<<<dim3(G, V), 64 * kFinParts, 0, ctx->st>>>(ctx->stats.as<double>(), ss, G, D, DP, tc_kp2(2 * DP), (G + 127) / 128, off_S0,
                                                                   off_S1, off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>(),
                                                                   ctx->acc_scratch.as<float>(), ctx->acc_slot_start.as<int32_t>(),
                                                                   ctx->acc_slot_ids.as<int32_t>());

@@ -994,47 +994,42 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
 
 // Adds the scratch slots of k_accum_ws to the statistics (in double, fixed order) and finishes them as
 // k_finalize_stats does: S1 += ctr S0 (features were centred), S2 = sum w x^2 - 2 m sum w x + m^2 sum w with
-// m = mu_old - ctr (the reference's sum w (x - mu_old)^2, T-FS:1716-1719).  One block = 4 whole Gaussians of
-// one model (thread = (Gaussian, dimension)), so that S0 is read by everyone before one thread rewrites it.
-__global__ void __launch_bounds__(256)
+// m = mu_old - ctr (the reference's sum w (x - mu_old)^2, T-FS:1716-1719).  One block = one Gaussian: thread
+// (dimension d, part p) adds every fourth slot of the Gaussian's image, the four parts are combined in a fixed order
+// through shared memory (so the result does not depend on scheduling), and S0 is read by everyone before one thread
+// rewrites it.
+constexpr int kFinParts = 4;
+__global__ void __launch_bounds__(64 * kFinParts)
 k_finalize_slots(double *__restrict__ stats, int64_t stats_stride, int G, int D, int DP, int KP2, int nRB, int64_t off_S0,
                  int64_t off_S1, int64_t off_S2, const double *__restrict__ ctr, const double *__restrict__ mu,
                  const float *__restrict__ scratch, const int32_t *__restrict__ slot_start, const int32_t *__restrict__ slot_ids) {
-  const int v = blockIdx.y, g = blockIdx.x * 4 + (threadIdx.x >> 6), d = threadIdx.x & 63;
-  const bool live = g < G, lived = live && d < D;
+  const int v = blockIdx.y, g = blockIdx.x, d = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const bool lived = d < D;
   double *st = stats + (int64_t)v * stats_stride;
-  // the 4 Gaussians of a block lie in one block of 128 (4 divides 128): one slot list, staged in shared memory so
-  // that the scratch loads below do not wait on the list
-  __shared__ int32_t sslot[256];
-  const int img = v * nRB + ((blockIdx.x * 4) >> 7);
+  __shared__ double sp[kFinParts][3][64];
+  const int img = v * nRB + (g >> 7), row = g & 127;
   const int k0 = slot_start[img], nk = slot_start[img + 1] - k0;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  const int row = g & 127;
-  if (live) {
-    s0 = st[off_S0 + g];
-    if (lived) { s1 = st[off_S1 + (int64_t)g * D + d]; s2 = st[off_S2 + (int64_t)g * D + d]; }
+  for (int k = part; k < nk; k += kFinParts) {
+    const float *sl = scratch + ((size_t)slot_ids[k0 + k] * 128 + row) * KP2;
+    s0 += (double)sl[D];
+    if (lived) { s1 += (double)sl[d]; s2 += (double)sl[DP + d]; }
   }
-  for (int kb = 0; kb < nk; kb += 256) {
-    __syncthreads();
-    if (kb + (int)threadIdx.x < nk) sslot[threadIdx.x] = slot_ids[k0 + kb + threadIdx.x];
-    __syncthreads();
-    const int kn = min(256, nk - kb);
-    if (live) {
-#pragma unroll 4
-      for (int k = 0; k < kn; k++) {
-        const float *sl = scratch + ((size_t)sslot[k] * 128 + row) * KP2;
-        s0 += (double)sl[D];
-        if (lived) { s1 += (double)sl[d]; s2 += (double)sl[DP + d]; }
-      }
-    }
-  }
+  sp[part][0][d] = s0; sp[part][1][d] = s1; sp[part][2][d] = s2;
+  // the statistics the atomic path may have left (CTAs that walked through many small images)
+  const double b0 = st[off_S0 + g];
+  const double b1 = lived ? st[off_S1 + (int64_t)g * D + d] : 0.0, b2 = lived ? st[off_S2 + (int64_t)g * D + d] : 0.0;
   __syncthreads();
+  if (part != 0) return;
+  s0 = b0; s1 = b1; s2 = b2;
+#pragma unroll
+  for (int p = 0; p < kFinParts; p++) { s0 += sp[p][0][d]; s1 += sp[p][1][d]; s2 += sp[p][2][d]; }
   if (lived) {
     const double m = mu[((int64_t)v * G + g) * D + d] - ctr[d];
     st[off_S2 + (int64_t)g * D + d] = s2 - 2.0 * m * s1 + m * m * s0;
     st[off_S1 + (int64_t)g * D + d] = s1 + ctr[d] * s0;
   }
-  if (live && d == 0) st[off_S0 + g] = s0;
+  if (d == 0) st[off_S0 + g] = s0;
 }
 
 }  // namespace hmmk
