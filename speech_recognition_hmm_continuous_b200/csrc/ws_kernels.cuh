@@ -2,17 +2,18 @@
 //
 // k_emis_ws: Gaussian-mixture emission log-likelihoods (calc_symbol_probab + calc_gaus, T-FS:1749-1841,
 // R-FS:860-947) as a dense contraction on the tensor pipe with the per-state log-sum-exp fused into
-// the epilogue.  One persistent CTA per SM, nine warps in three roles that only meet at mbarriers:
+// the epilogue.  One persistent CTA per SM, 17 warps in three roles that only meet at mbarriers:
 //
-//   warps 4-7  LOADERS   read 128 raw frames (fp32, centred; prefetched three levels ahead), form
+//   warps 8-15 LOADERS   read 128 raw frames (fp32, centred; prefetched three levels ahead), form
 //                        [x | x^2], split every value into TF32 hi + lo and write the A operand with
-//                        tcgen05.st into TENSOR MEMORY stage a (one frame per lane); (re)load the W
-//                        image into shared memory when the unit's image changes
-//   warp  8    MMA       one thread issues 3*KP/8 tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) per
-//                        unit, A from TMEM, B = W from shared memory, into TMEM accumulator stage a,
+//                        tcgen05.st into TENSOR MEMORY (two warps per lane quarter, half a row per thread);
+//                        (re)load the W image into shared memory when the unit's image changes
+//   warp  16   MMA       one thread issues 3*KP/8 tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) per
+//                        unit, A from TMEM, B = W from shared memory, into a TMEM accumulator stage,
 //                        commits to free the operand stage and to publish the accumulator
-//   warps 0-3  EPILOGUE  tcgen05.ld the accumulator (one frame per thread), log-sum-exp over the M
-//                        mixtures of each state, store log b
+//   warps 0-7  EPILOGUE  tcgen05.ld the accumulator (one frame per thread, two warps per lane quarter taking
+//                        the 16-column groups of even / odd index), log-sum-exp over the M mixtures of each
+//                        state (additive constants of the image from shared memory), store log b
 //
 // Why the frame operand lives in TMEM: with both operands in shared memory a K = 8 TF32 MMA of
 // 128 x 80 reads (128 + 80) x 32 B = 6.6 KB for 40 cycles of math -- more than the 128 B/cycle the
@@ -36,7 +37,8 @@
 //   byte(g, k) = (g%8)*16 + (k%4)*4 + (k/4)*128 + (g/8)*P,   P = (KP/4)*128;   LBO = 128, SBO = P,
 //   K-step j starts at +256 j;  image = [hi: (TN/8) P][lo: (TN/8) P][kc2: TN floats].
 // TMEM columns: operand stage a at 160 a: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)] (KP <= 80);
-//               accumulator stage a at 320 + 96 a (TN <= 96).
+//               accumulator stage a at 320 + 96 a (TN <= 96); an image of one wide state (96 < TN <= 176) has a
+//               single operand stage and its two accumulator stages at 160 + TN a.
 #pragma once
 #include "tc_kernels.cuh"
 
@@ -532,28 +534,30 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 
 // ================================================================================================
 // k_accum_ws: mixture accumulators (calc_mix_param, T-FS:1691-1727), warp-specialised and pipelined.
-// Same mathematics as k_accum_tc (tc_kernels.cuh): per sub-tile of 64 frames of one model and block of
+// Same mathematics as k_accum_tc (tc_kernels.cuh): per sub-tile of 32 frames of one model and block of
 // 128 Gaussians
 //   GEMM1  L[g][f]  = sum_k W[g][k] Xaug[f][k]           A = W (TMEM, parked per image), B = X  (smem)
 //   w[g][f] = gamma_f(s(g)) exp(L + kc[g] - logb_f(s(g)))  epilogue, in place in TMEM (hi) + beside it (lo)
 //   GEMM2  S[g][k] += sum_f w[g][f] Xaug[f][k]           A = w (TMEM), B = XT (smem)
-// but the activities run concurrently on different warps and meet only at mbarriers (18 warps):
-//   warps  8-11 X LOADERS   features three levels ahead in registers; X (frames x columns), TF32 hi / lo,
+// but the activities run concurrently on different warps and meet only at mbarriers (20 warps):
+//   warps  8-12 X LOADERS   features three levels ahead in registers; X (frames x columns), TF32 hi / lo,
 //                           and the per-frame weight exponents cfs
-//   warps 12-15 XT LOADERS  the same tile transposed (columns x frames), TF32 hi / lo
-//   warp  16    GEMM1 MMA   issues GEMM1 of the next unit as soon as its X tile (and the image's W) is there
-//   warp  17    GEMM2 MMA   issues GEMM2 of the oldest unit as soon as its weights are there; two issuers
+//   warps 13-17 XT LOADERS  the same tile transposed (columns x frames), TF32 hi / lo
+//   warp  18    GEMM1 MMA   issues GEMM1 of the next unit as soon as its X tile (and the image's W) is there
+//   warp  19    GEMM2 MMA   issues GEMM2 of the oldest unit as soon as its weights are there; two issuers
 //                           because one warp's instruction stream serialised the whole pipeline
 //   warps  0-7  EPILOGUE    L -> w with tcgen05.ld / tcgen05.st (warp w: TMEM lanes 32 (w%4).., frames
-//                           32 (w/4)..); every kAccDrain sub-tiles S moves from TMEM (FP32, truncating
-//                           accumulation) to FP32 registers (round to nearest, 40 columns per thread);
-//                           double atomics when the CTA's (model, Gaussian block) changes; loads the next
-//                           image's W into TMEM
-// Two shared-memory stages (X, XT, cfs) and two TMEM stages (L / w_hi, w_lo).
-// TMEM columns: [0,128) L / w_hi x2 | [128,256) w_lo x2 | [256, 256+KP2) S | [352, 352+2KP) W_hi, W_lo
+//                           16 (w/4)..); every kAccDrain sub-tiles S moves from TMEM (FP32, truncating
+//                           accumulation) to FP32 in shared memory (round to nearest); when the CTA's (model,
+//                           Gaussian block) changes, the partial sums go to the CTA's scratch slot (plain
+//                           stores; k_finalize_slots adds the slots in a fixed order); loads the next image's
+//                           W into TMEM
+// Four shared-memory stages (X, XT, cfs) and four TMEM stages (L / w_hi, w_lo): with two, the GEMMs of one unit
+// and the expansion / weight epilogue of the next alternated instead of overlapping (tensor pipe active < 30 %).
+// TMEM columns: [0,128) L / w_hi x4 | [128,256) w_lo x4 | [256, 256+KP2) S | [352, 352+2KP) W_hi, W_lo
 // Shared-memory layouts (SWIZZLE_NONE K-major, 16-byte chunks):
-//   X  : byte(f, k) = (f%8)*16 + (k%4)*4 + (k/4)*128 + (f/8)*PX     PX = (KP/4)*128   (8 frame groups)
-//   XT : byte(k, f) = (k%8)*16 + (f%4)*4 + (f/4)*128 + (k/8)*2048   (KP2/8 column groups)
+//   X  : byte(f, k) = (f%8)*16 + (k%4)*4 + (k/4)*128 + (f/8)*PX     PX = (KP/4)*128   (4 frame groups)
+//   XT : byte(k, f) = (k%8)*16 + (f%4)*4 + (f/4)*128 + (k/8)*1024   (KP2/8 column groups)
 // ================================================================================================
 constexpr int kAccSub = 32;        // frames per sub-tile
 constexpr int kAccStages = 4;      // sub-tiles in flight (shared-memory and TMEM stages)
