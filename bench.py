@@ -141,6 +141,13 @@ def run_ours(args):
             dist.all_reduce(t)
 
     ar = allreduce if world > 1 else None
+    ar_kind = "torch.distributed (nccl)"
+    if world > 1 and not args.torch_allreduce:
+        try:  # the collective on the context's own stream through the NCCL C API
+            ar = api.NcclAllReduce(rank, world)
+            ar_kind = "ncclAllReduce on the context's stream"
+        except Exception as e:  # noqa: BLE001
+            print("direct NCCL unavailable (%s); using torch.distributed" % e, file=sys.stderr)
     # pinned host copy of the features (e2e leg) and a device-resident copy (value leg)
     xpin = torch.from_numpy(x).pin_memory()
     xdev = xpin.to(torch.device("cuda", local))
@@ -278,7 +285,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "frames_per_gpu": F, "utterances_per_gpu": U, "words": V,
-                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "utterances sharded, 1 all-reduce of statistics per iteration" if world > 1 else "single GPU"},
+                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": ("utterances sharded, 1 all-reduce of statistics per iteration (%s)" % ar_kind) if world > 1 else "single GPU"},
         "e2e": {"value": F * world / (e2e_ms / e2e_steps * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": int(x.nbytes + off.nbytes),
                 "d2h_bytes_per_step": int(8 * (3 * V + 1))},
@@ -494,6 +501,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-regimes", action="store_true", help="skip the decode-regime legs (c4 / c5 slices)")
+    ap.add_argument("--torch-allreduce", action="store_true", help="all-reduce through torch.distributed instead of the NCCL C API")
     ap.add_argument("--upload-chunks", type=int, default=0, help="override the library's upload chunk count (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

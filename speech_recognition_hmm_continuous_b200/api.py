@@ -401,6 +401,48 @@ def write_features(path, x):
         raise HmmCudaError("hmmh_write_features(%s) failed (%d)" % (path, rc))
 
 
+class NcclAllReduce:
+    """ncclAllReduce(sum, double) in place on the context's own stream, straight through the NCCL C API (the
+    library torch ships): what INTEGRATION.md shows a C caller doing between hmmcu_estep and hmmcu_mstep.
+    Going through torch.distributed instead puts the collective on torch's internal NCCL stream behind two
+    event hand-offs, which costs more than the 0.5 MB all-reduce itself.  The unique id travels through the
+    already initialised torch.distributed group."""
+
+    class _Uid(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+
+    def __init__(self, rank, world):
+        import glob
+        import torch
+        import torch.distributed as dist
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+        self.lib = C.CDLL(cands[0] if cands else "libnccl.so.2")
+        self.lib.ncclGetUniqueId.argtypes = [C.POINTER(self._Uid)]
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, self._Uid, C.c_int]
+        self.lib.ncclAllReduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+        uid = self._Uid()
+        if rank == 0 and self.lib.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise HmmCudaError("ncclGetUniqueId failed")
+        box = [bytes(uid.internal)]
+        dist.broadcast_object_list(box, src=0)
+        C.memmove(C.byref(uid), box[0], 128)
+        self.comm = C.c_void_p()
+        rc = self.lib.ncclCommInitRank(C.byref(self.comm), int(world), uid, int(rank))
+        if rc != 0:
+            raise HmmCudaError("ncclCommInitRank failed (%d)" % rc)
+
+    def __call__(self, dev_ptr, n_doubles, stream_ptr):
+        rc = self.lib.ncclAllReduce(C.c_void_p(dev_ptr), C.c_void_p(dev_ptr), int(n_doubles), 8, 0, self.comm, C.c_void_p(stream_ptr))  # ncclDouble, ncclSum
+        if rc != 0:
+            raise HmmCudaError("ncclAllReduce failed (%d)" % rc)
+
+    def close(self):
+        if getattr(self, "comm", None):
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
 def shard_utterances(off, rank, world):
     """Utterances [u0, u1) of rank `rank` out of `world`: contiguous, balanced by frame count (the
     utterances are partitioned across the GPUs by contiguous frame count; every rank keeps the full model set and
