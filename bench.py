@@ -119,6 +119,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    numa = None
+    if not args.no_affinity:
+        # keep this rank (and therefore the first touch of its host buffers, pinned staging included) on the CPUs
+        # of the NUMA node its GPU hangs off: with eight ranks uploading at once, remote-node pinned memory halves
+        # the host-to-device rate
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = sorted(os.sched_getaffinity(0))
+            numa = "%d cpus [%d..%d]" % (len(numa), numa[0], numa[-1])
+        except Exception as e:  # noqa: BLE001
+            numa = "unavailable: %s" % e
     w = WORKLOADS[args.workload]
     x, off, labels, mods = make_workload(w, rank)
     F = int(off[-1])
@@ -285,7 +298,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload + ": " + w["desc"], "frames_per_gpu": F, "utterances_per_gpu": U, "words": V,
-                   "l2": "flushed between timed iterations (256 MiB write)", "parallelism": ("utterances sharded, 1 all-reduce of statistics per iteration (%s)" % ar_kind) if world > 1 else "single GPU"},
+                   "l2": "flushed between timed iterations (256 MiB write)", "cpu_affinity": numa, "parallelism": ("utterances sharded, 1 all-reduce of statistics per iteration (%s)" % ar_kind) if world > 1 else "single GPU"},
         "e2e": {"value": F * world / (e2e_ms / e2e_steps * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": int(x.nbytes + off.nbytes),
                 "d2h_bytes_per_step": int(8 * (3 * V + 1))},
@@ -501,6 +514,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-regimes", action="store_true", help="skip the decode-regime legs (c4 / c5 slices)")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--torch-allreduce", action="store_true", help="all-reduce through torch.distributed instead of the NCCL C API")
     ap.add_argument("--upload-chunks", type=int, default=0, help="override the library's upload chunk count (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
