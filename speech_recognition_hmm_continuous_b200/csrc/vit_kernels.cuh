@@ -27,6 +27,7 @@ namespace hmmk {
 // ------------------------------------------------------------------------------------------------
 // k_logb64
 // ------------------------------------------------------------------------------------------------
+constexpr int kLbGroup = 4;    // mixtures evaluated together
 constexpr int kLbFrames = 64;  // frames (= threads) per CTA; same tiling as EmisTile (<= 64 frames of one utterance)
 
 // smem: par[M][D] double2 (mu, iv) | lc[M] (log c, or -inf for a dead mixture) | hl[M] (0.5 log|det|)
@@ -65,35 +66,50 @@ k_logb64(const EmisTile *__restrict__ tiles, const double *__restrict__ x64, con
     }
     __syncthreads();
     double mx = -INFINITY, acc = 0.0;
-    // two mixtures per pass: two independent accumulation chains keep the FP64 pipe busy
-    for (int m = 0; m < M; m += 2) {
-      const bool two = m + 1 < M;
-      const double2 *pm0 = par + (size_t)m * D, *pm1 = par + (size_t)(two ? m + 1 : m) * D;
-      double q0 = 0.0, q1 = 0.0;
+    // kLbGroup mixtures per pass: independent accumulation chains and independent exponentials keep the FP64 pipe
+    // busy (one mixture at a time is a single dependent chain of ~40-instruction exp() calls)
+    for (int m0 = 0; m0 < M; m0 += kLbGroup) {
+      double q[kLbGroup];
+      const double2 *pm[kLbGroup];
+#pragma unroll
+      for (int h = 0; h < kLbGroup; h++) {
+        q[h] = 0.0;
+        pm[h] = par + (size_t)min(m0 + h, M - 1) * D;
+      }
       if (DREG > 0) {
 #pragma unroll
         for (int d = 0; d < DREG; d++) {
-          const double2 p0 = pm0[d], p1 = pm1[d];
-          const double d0 = xreg[d] - p0.x, d1 = xreg[d] - p1.x;
-          q0 += d0 * p0.y * d0;
-          q1 += d1 * p1.y * d1;
+#pragma unroll
+          for (int h = 0; h < kLbGroup; h++) {
+            const double2 p = pm[h][d];
+            const double df = xreg[d] - p.x;
+            q[h] += df * p.y * df;
+          }
         }
       } else {
         for (int d = 0; d < D; d++) {
-          const double2 p0 = pm0[d], p1 = pm1[d];
           const double xv = xr[d];
-          const double d0 = xv - p0.x, d1 = xv - p1.x;
-          q0 += d0 * p0.y * d0;
-          q1 += d1 * p1.y * d1;
+#pragma unroll
+          for (int h = 0; h < kLbGroup; h++) {
+            const double2 p = pm[h][d];
+            const double df = xv - p.x;
+            q[h] += df * p.y * df;
+          }
         }
       }
+      double ln[kLbGroup], gm = -INFINITY;
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        if (h == 1 && !two) break;
-        const double lc = slc[m + h];
-        const double ln = (lc > -INFINITY) ? lc - 0.5 * (h ? q1 : q0) - lognorm - shl[m + h] : -INFINITY;
-        if (ln > mx) { acc = acc * exp(mx - ln) + 1.0; mx = ln; }
-        else if (ln > -INFINITY) acc += exp(ln - mx);
+      for (int h = 0; h < kLbGroup; h++) {
+        const bool ok = m0 + h < M && slc[min(m0 + h, M - 1)] > -INFINITY;
+        ln[h] = ok ? slc[m0 + h] - 0.5 * q[h] - lognorm - shl[m0 + h] : -INFINITY;
+        gm = fmax(gm, ln[h]);
+      }
+      if (gm > -INFINITY) {
+        if (gm > mx) { acc *= exp(mx - gm); mx = gm; }  // exp(-inf) = 0 on the first group
+        double sg = 0.0;
+#pragma unroll
+        for (int h = 0; h < kLbGroup; h++) sg += (ln[h] > -INFINITY) ? exp(ln[h] - mx) : 0.0;
+        acc += sg;
       }
     }
     if (live) logb64[f * N + i] = (mx > -INFINITY) ? mx + log(acc) : -INFINITY;
