@@ -44,7 +44,8 @@
 
 namespace hmmk {
 
-constexpr int kWsThreads = 544;   // 17 warps: 8 epilogue, 8 loaders, MMA issuer
+constexpr int kWsEpiWarps = 8;    // epilogue warps (a multiple of 4: TMEM lane quarters; 12 measured slower: 80 registers per thread)
+constexpr int kWsThreads = (kWsEpiWarps + 9) * 32;   // epilogue, 8 loaders, MMA issuer
 constexpr int kWsMaxTN = 96;      // Gaussians (columns) per W image (two operand stages in tensor memory)
 constexpr int kWsMaxTN1 = 176;    // ... of an image that holds one wide state (a single operand stage)
 constexpr int kWsXch = 6;         // states per image when a state spans several 16-column chunks (M > 16)
@@ -224,11 +225,11 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       init(full + 8 * s, 256);    // every loader thread arrives
       init(empty + 8 * s, 1);     // tcgen05.commit
       init(dfull + 8 * s, 1);     // tcgen05.commit
-      init(dempty + 8 * s, 256);  // every epilogue thread arrives
+      init(dempty + 8 * s, kWsEpiWarps * 32);  // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) {
+  if (warp == kWsEpiWarps + 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -252,9 +253,9 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   };
   auto unit_at = [&](int ui) -> TcTile { return ui < u_end ? get_unit(ui) : TcTile{0, 0, -1, 0, 0, 0}; };
 
-  if (warp >= 8 && warp < 16) {
+  if (warp >= kWsEpiWarps && warp < kWsEpiWarps + 8) {
     // =================================== LOADERS ===================================
-    const int q = warp & 3, h = (warp - 8) >> 2;
+    const int q = warp & 3, h = (warp - kWsEpiWarps) >> 2;
     const int r = 32 * q + lane;  // frame row of the tile = TMEM lane
     constexpr int kQ = 5;         // float4 per thread: half a row (DP <= 40)
     const int nq = DP / 4;
@@ -285,12 +286,12 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         // the tensor pipe may still be reading the old image: wait for the previous unit's MMAs
         if (i >= 1) mbar_wait_a(empty + 8 * ((i - 1) % AST), ((i - 1) / AST) & 1);
         const float4 *wsrc = reinterpret_cast<const float4 *>(images + (size_t)unit.img * (img_bytes / 4));
-        for (int k = tid - 256; k < (int)(w_bytes / 16); k += 256) st_shared_v4(Ws + 16 * k, __ldg(wsrc + k));
+        for (int k = tid - kWsEpiWarps * 32; k < (int)(w_bytes / 16); k += 256) st_shared_v4(Ws + 16 * k, __ldg(wsrc + k));
         cur_img = unit.img;
       }
-      if (warp == 8) stamp(i, 0);
+      if (warp == kWsEpiWarps) stamp(i, 0);
       mbar_wait_a(empty + 8 * s, (ku & 1) ^ 1);  // operand stage s is free (unit i-AST has been multiplied)
-      if (warp == 8) stamp(i, 1);
+      if (warp == kWsEpiWarps) stamp(i, 1);
       tc_fence_after();
       // stage s: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)], 4 columns per store
       const uint32_t xa = xa0 + (uint32_t)s * 160 + 4 * j0;
@@ -311,7 +312,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       tc_fence_before();
       fence_async_smem();  // the W image (generic-proxy writes) -> visible to the tensor core
       mbar_arrive_a(full + 8 * s);
-      if (warp == 8) stamp(i, 2);
+      if (warp == kWsEpiWarps) stamp(i, 2);
     };
     TcTile d0 = unit_at(u_begin), d1 = unit_at(u_begin + 1), d2 = unit_at(u_begin + 2);
     int64_t f1 = frame_of(d1);
@@ -330,7 +331,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         d0 = d2; d1 = d3; d2 = d4;
       }
     }
-  } else if (warp == 16) {
+  } else if (warp == kWsEpiWarps + 8) {
     // =================================== MMA ISSUER ===================================
     const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
@@ -371,7 +372,8 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       stamp(i, 5);
     }
   } else {
-    // =================================== EPILOGUE (warps 0-7) ===================================
+    // =================================== EPILOGUE (warps 0 .. kWsEpiWarps-1) ===================================
+    constexpr int EH = kWsEpiWarps / 4;  // warps per TMEM lane quarter: column groups g with g % EH == h
     const int q = warp & 3, h = warp >> 2;
     const int row = 32 * q + lane;  // TMEM lane
     const uint32_t trow = (uint32_t)(32 * q) << 16;
@@ -396,8 +398,8 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         // still reads.
         epi_img = unit.img;
         const float *kcg = images + (size_t)unit.img * (img_bytes / 4) + w_bytes / 4;
-        for (int c = tid; c < TN; c += 256) skc[nsw & 1][c] = __ldg(kcg + c);
-        asm volatile("bar.sync 9, 256;" ::: "memory");
+        for (int c = tid; c < TN; c += kWsEpiWarps * 32) skc[nsw & 1][c] = __ldg(kcg + c);
+        asm volatile("bar.sync 9, %0;" ::"n"(kWsEpiWarps * 32) : "memory");
         nsw++;
       }
       const float *kcs = skc[(nsw - 1) & 1];
@@ -415,17 +417,17 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       float *lrow = TRAIN ? logb + f * N + unit.state0 : logb + (f - fbase) * ldb + unit.state0;
       const uint32_t d = tmem0 + acc0 + (uint32_t)s * ACS + trow;
       const float4 *kc4 = reinterpret_cast<const float4 *>(kcs);  // warp-uniform addresses: broadcast loads
-      constexpr int kMaxG = (kWsMaxTN / 16 + 1) / 2;  // groups per warp when a group is one chunk
+      constexpr int kMaxG = (kWsMaxTN / 16 + EH - 1) / EH;  // groups per warp when a group is one chunk
       if (MP) {
-        // my groups: g = h, h + 2, ...; every accumulator chunk of mine in flight at once
+        // my groups: g = h, h + EH, ...; every accumulator chunk of mine in flight at once
         uint32_t v[kMaxG][16];
 #pragma unroll
         for (int k = 0; k < kMaxG; k++)
-          if (h + 2 * k < ngroups) tmem_ld16_nowait(d + (h + 2 * k) * 16, v[k]);
+          if (h + EH * k < ngroups) tmem_ld16_nowait(d + (h + EH * k) * 16, v[k]);
         tmem_wait_ld();
 #pragma unroll
         for (int k = 0; k < kMaxG; k++) {
-          const int c = h + 2 * k;
+          const int c = h + EH * k;
           if (c < ngroups) {
             const float4 k0 = kc4[c * 4], k1 = kc4[c * 4 + 1], k2 = kc4[c * 4 + 2], k3 = kc4[c * 4 + 3];
             const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
@@ -469,6 +471,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
         // state (online log-sum-exp over their own chunks); the odd warp hands its partial (max, sum) over
         // through shared memory and the even warp merges and stores.
         float pmx[kWsXch], psum[kWsXch];
+        if (h < 2) {
 #pragma unroll
         for (int sx = 0; sx < kWsXch; sx++) {
           pmx[sx] = kNegInf; psum[sx] = 0.f;
@@ -497,6 +500,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
             pmx[sx] = mx; psum[sx] = sum;
           }
         }
+        }
         if (h == 1) {
 #pragma unroll
           for (int sx = 0; sx < kWsXch; sx++)
@@ -504,7 +508,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
           // (bar.sync, not bar.arrive: this warp can be a whole unit ahead of its partner, and two arrivals of
           // the same warp would complete a barrier phase on their own)
           asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        } else {
+        } else if (h == 0) {
           asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
 #pragma unroll
           for (int sx = 0; sx < kWsXch; sx++) {
@@ -528,7 +532,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 16) tmem_dealloc(tmem0, 512);
+  if (warp == kWsEpiWarps + 8) tmem_dealloc(tmem0, 512);
 }
 
 
