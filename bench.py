@@ -36,6 +36,7 @@ WORKLOADS = {
     # name: V words, N states, M mixtures, U utterances per GPU, description
     "c2": dict(V=10, N=5, M=16, U=1000, desc="BASELINE configs[1]: N=5 M=16 D=39, 10 words, 1000 utterances (~300 frames) per GPU"),
     "c1": dict(V=10, N=5, M=3, U=220, desc="BASELINE configs[0]: N=5 M=3 D=39, 10 words, 22 utterances per word"),
+    "c3": dict(V=10, N=5, M=16, U=12500, desc="BASELINE configs[2] shard: N=5 M=16 D=39, 10 words, 12,500 utterances (100k over 8 GPUs) per GPU"),
     "c5": dict(V=20, N=3, M=128, U=1000, desc="BASELINE configs[4] slice: N=3 M=128 D=39, 20 of 2000 models, 1000 utterances"),
 }
 D = 39

@@ -1,4 +1,5 @@
 // FP64 / FP32 FMA issue rate and dependent-chain latency on the device (one-off probe).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/ubench/dp_rate scripts/ubench/dp_rate.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 template <typename T, int CH>
