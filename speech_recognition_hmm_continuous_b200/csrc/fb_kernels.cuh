@@ -762,4 +762,237 @@ k_fb_seg(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
   }
 }
 
+// ================================================================================================
+// k_fb_wide + k_fb_gamma: the recursions for MANY utterances (a C3 shard: 12,500 per GPU).
+// With thousands of utterances there are enough independent chains to fill the machine without cutting them up:
+// one thread per (utterance, direction), every lane of every warp busy, log-emissions read straight from global
+// memory four frames ahead (as the decode scorers do), b~ formed on the fly.  The third phase (gamma, xi, den
+// sums) is a kernel of its own, one warp per utterance.  At 1,000 utterances this is slower than k_fb_seg (2,000
+// threads cannot hide a 300-step chain); hmmcu_estep picks by the number of utterances.
+// ================================================================================================
+constexpr int kWideThreads = 128;
+constexpr int kWidePF = 4;
+
+template <int NS, bool BANDED>
+__global__ void __launch_bounds__(kWideThreads)
+k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
+          const double *__restrict__ Aall, int U, float *__restrict__ alpha_ws, float *__restrict__ beta_ws,
+          double *__restrict__ phi_utt, double *__restrict__ lp_utt) {
+  const int cid = blockIdx.x * kWideThreads + threadIdx.x;
+  if (cid >= 2 * U) return;
+  const int dir = cid / U, u = cid - dir * U;  // forward chains first: the lanes of a warp share a direction
+  const int v = u2m[u];
+  if (v < 0) return;
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  double a[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) a[k] = Aall[(int64_t)v * NS * NS + k];
+  double z[NS];
+  const float *p = logb + base * NS;
+  float nxt[kWidePF][NS];
+  if (dir == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) z[i] = 0.0;
+    int esum = 0;
+#pragma unroll
+    for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)min(k, T - 1) * NS, nxt[k]);
+    for (int t0 = 0; t0 < T; t0 += kWidePF) {
+      float cur[kWidePF][NS];
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
+      }
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)min(t0 + kWidePF + k, T - 1) * NS, nxt[k]);
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) {
+        const int t = t0 + k;
+        if (t < T) {
+          float m = cur[k][0];
+#pragma unroll
+          for (int i = 1; i < NS; i++) m = fmaxf(m, cur[k][i]);
+          const float ms = (m > kNegInf) ? m : 0.f;
+          double raw[NS];
+          if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? exp_scaled(cur[k][0] - ms) : 0.0;  // pi = [1,0,..,0]
+          } else {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+              double aux;
+              if (BANDED) {
+                aux = z[i] * a[i * NS + i];
+                if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
+              } else {
+                aux = 0.0;
+#pragma unroll
+                for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
+              }
+              raw[i] = aux * exp_scaled(cur[k][i] - ms);
+            }
+          }
+          int e;
+          const double r = pow2_scale_max<NS>(raw, e);
+#pragma unroll
+          for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+          esum += e;
+          store_row<NS>(alpha_ws + (base + t) * kFbRow, z);
+        }
+      }
+    }
+    double sm = z[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) sm += z[i];
+    phi_utt[u] = z[NS - 1] / sm;                                            // alpha^_{T-1}(N-1)
+    lp_utt[u] = 0.6931471805599453 * (double)esum + log(z[NS - 1]);        // + sum m_t, added by k_fb_gamma
+  } else {
+    // backward: w_{T-1} = e_{N-1}; step t = T-2 .. 0 uses the emissions of frame t + 1
+#pragma unroll
+    for (int i = 0; i < NS; i++) z[i] = (i == NS - 1) ? 1.0 : 0.0;
+    store_row<NS>(beta_ws + (base + T - 1) * kFbRow, z);
+#pragma unroll
+    for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)max(T - 1 - k, 0) * NS, nxt[k]);  // frames T-1, T-2, ..
+    for (int s0 = 0; s0 < T - 1; s0 += kWidePF) {  // step s: t = T-2-s, emissions of frame T-1-s
+      float cur[kWidePF][NS];
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
+      }
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)max(T - 1 - (s0 + kWidePF + k), 0) * NS, nxt[k]);
+#pragma unroll
+      for (int k = 0; k < kWidePF; k++) {
+        const int sx = s0 + k;
+        if (sx < T - 1) {
+          float m = cur[k][0];
+#pragma unroll
+          for (int i = 1; i < NS; i++) m = fmaxf(m, cur[k][i]);
+          const float ms = (m > kNegInf) ? m : 0.f;
+          double q[NS], raw[NS];
+#pragma unroll
+          for (int j = 0; j < NS; j++) q[j] = exp_scaled(cur[k][j] - ms) * z[j];
+#pragma unroll
+          for (int i = 0; i < NS; i++) {
+            double aux;
+            if (BANDED) {
+              aux = a[i * NS + i] * q[i];
+              if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
+            } else {
+              aux = 0.0;
+#pragma unroll
+              for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
+            }
+            raw[i] = aux;
+          }
+          int e;
+          const double r = pow2_scale_max<NS>(raw, e);
+#pragma unroll
+          for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+          store_row<NS>(beta_ws + (base + T - 2 - sx) * kFbRow, z);
+        }
+      }
+    }
+  }
+}
+
+// third phase for k_fb_wide: one warp per utterance, lanes over frames (the same arithmetic as k_fb's phase 2)
+constexpr int kGammaWarps = 8;
+template <int NS>
+__global__ void __launch_bounds__(kGammaWarps * 32)
+k_fb_gamma(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
+           const double *__restrict__ Aall, int U, const float *__restrict__ alpha_ws, const float *__restrict__ beta_ws,
+           const double *__restrict__ phi_utt, const double *__restrict__ lp_utt, float *__restrict__ gamma,
+           double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp, double *__restrict__ logp_utt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * kGammaWarps + warp;
+  if (u >= U) return;
+  const int v = u2m[u];
+  if (v < 0) {  // masked utterance (its model has converged)
+    if (lane == 0 && logp_utt) logp_utt[u] = 0.0;
+    return;
+  }
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  double A[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) A[k] = Aall[(int64_t)v * NS * NS + k];
+  const double phi = phi_utt[u];
+  double acc_num[NS][2], acc_dt[NS], acc_dm[NS], acc_m = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
+  for (int t = lane; t < T; t += 32) {
+    double al[NS], be[NS], g[NS], G = 0.0;
+    load_row<NS>(alpha_ws + (base + t) * kFbRow, al);
+    load_row<NS>(beta_ws + (base + t) * kFbRow, be);
+    {
+      float l0[NS];
+      load_lb<NS>(logb + (base + t) * NS, l0);
+      float m = l0[0];
+#pragma unroll
+      for (int i = 1; i < NS; i++) m = fmaxf(m, l0[i]);
+      acc_m += (double)m;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      g[i] = al[i] * be[i];
+      G += g[i];
+    }
+    const double sc = (G > 0.0) ? phi / G : 0.0;  // unreachable final state: no occupancy, as the reference
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      g[i] *= sc;  // alpha^ beta^ / c   T-FS:1617,1658,1709
+      gamma[(base + t) * NS + i] = (float)g[i];
+      acc_dm[i] += g[i];
+    }
+    if (t < T - 1) {
+      float l1[NS];
+      load_lb<NS>(logb + (base + t + 1) * NS, l1);
+      float m = l1[0];
+#pragma unroll
+      for (int i = 1; i < NS; i++) m = fmaxf(m, l1[i]);
+      double q[NS], b1[NS];
+      load_row<NS>(beta_ws + (base + t + 1) * kFbRow, b1);
+#pragma unroll
+      for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * b1[j];
+      double Z = 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        double rb = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; j++) rb = fma(A[i * NS + j], q[j], rb);
+        Z = fma(al[i], rb, Z);
+      }
+      const double zs = (Z > 0.0) ? phi / Z : 0.0;
+#pragma unroll
+      for (int i = 0; i < NS; i++) {
+        acc_dt[i] += g[i];
+        acc_num[i][0] += al[i] * A[i * NS + i] * q[i] * zs;                              // band j = i   T-FS:1611
+        if (i + 1 < NS) acc_num[i][1] += al[i] * A[i * NS + i + 1] * q[i + 1] * zs;      // j = i + 1
+      }
+    }
+  }
+  double *st = stats + (int64_t)v * stats_stride;
+#pragma unroll
+  for (int i = 0; i < NS; i++) {
+    const double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
+    const double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
+    if (lane == 0) {
+      atomicAdd(st + i * NS + i, n0);
+      if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
+      atomicAdd(st + NS * NS + i, dt);
+      atomicAdd(st + NS * NS + NS + i, dm);
+    }
+  }
+  const double msum = warp_sum(acc_m);
+  if (lane == 0) {
+    const double lp = lp_utt[u] + msum;  // calc_probability T-FS:1546-1549
+    atomicAdd(st + off_sumlogp, lp);
+    atomicAdd(st + off_sumlogp + 1, 1.0);
+    if (logp_utt) logp_utt[u] = lp;
+  }
+}
+
 }  // namespace hmmk

@@ -109,7 +109,7 @@ struct hmmcu_ctx {
 
   // training map
   std::vector<int32_t> u2m;
-  DevBuf u2m_d, mus_d, mu_d, tiles_d;
+  DevBuf u2m_d, mus_d, mu_d, tiles_d, phi_utt_d, lp_part_d;
   DevBuf vit_map, vit_tiles;
   std::vector<int32_t> vit_u2m;
   int64_t n_vit_tiles = 0;
@@ -136,6 +136,7 @@ struct hmmcu_ctx {
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
   int use_seg_fb = 1;  // time-parallel forward-backward (k_fb_seg) when the utterances fit in shared memory (0 = k_fb)
+  int use_wide_fb = 1; // 1 = thread-per-chain forward-backward (k_fb_wide) beyond kWideMinUtts utterances, 2 = always, 0 = never
   int debug_acc = 0;
   bool acc_dirty = true;
   int64_t n_acc_units = 0;
@@ -281,7 +282,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
-                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles};
+                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles, &ctx->phi_utt_d, &ctx->lp_part_d};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -335,6 +336,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "seg_fb") == 0) { ctx->use_seg_fb = value; return HMMCU_OK; }
+  if (strcmp(key, "wide_fb") == 0) { ctx->use_wide_fb = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1273,6 +1275,8 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     CK(ctx->alpha_ws.ensure(sizeof(float) * F * kFbRow));
     CK(ctx->beta_ws.ensure(sizeof(float) * F * kFbRow));
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
+    CK(ctx->phi_utt_d.ensure(sizeof(double) * U));
+    CK(ctx->lp_part_d.ensure(sizeof(double) * U));
     if (ws_emis) {
       if ((rc = ensure_ws_images(ctx, 0)) != HMMCU_OK) return rc;
     } else if (use_tc) {
@@ -1301,7 +1305,26 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
     // 2. forward / backward, gamma, transition statistics, log-probabilities
     t_begin(ctx, "fwdbwd");
     {
-      if (ctx->use_seg_fb && fb_seg_fits(N, ctx->Tmax)) {
+      // many utterances: one thread per chain fills the machine (a k_fb_seg CTA holds four utterances and two fit per SM)
+      constexpr int kWideMinUtts = 1536;
+      if (ctx->use_wide_fb == 2 || (ctx->use_wide_fb == 1 && U >= kWideMinUtts)) {
+        const int blocks = (2 * U + kWideThreads - 1) / kWideThreads;
+        if (ctx->banded) {
+          DISPATCH_N(N, (k_fb_wide<NS, true><<<blocks, kWideThreads, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
+                                                                                  ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
+                                                                                  ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
+        } else {
+          DISPATCH_N(N, (k_fb_wide<NS, false><<<blocks, kWideThreads, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
+                                                                                   ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
+                                                                                   ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
+        }
+        LAUNCH_CHECK();
+        DISPATCH_N(N, (k_fb_gamma<NS><<<(U + kGammaWarps - 1) / kGammaWarps, kGammaWarps * 32, 0, ctx->st>>>(
+                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(),
+                          ctx->beta_ws.as<float>(), ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>(), ctx->gamma.as<float>(),
+                          ctx->stats.as<double>(), ss, off_lp, ctx->logp_utt_d.as<double>())));
+        LAUNCH_CHECK();
+      } else if (ctx->use_seg_fb && fb_seg_fits(N, ctx->Tmax)) {
         const int blocks = (U + kSegUtts - 1) / kSegUtts;
         const size_t fsm = fb_seg_smem_bytes(N, ctx->Tmax);
         if (ctx->banded) {

@@ -478,14 +478,18 @@ def test_time_parallel_and_windowed_forward_backward_agree():
     the time-parallel kernel's shared memory takes the windowed kernel on its own."""
     ms, x, off, labels = _synth(2, 5, 3, 10, seed=777, tmin=3, tmax=140)
     out = []
-    for seg in (1, 0):
+    for seg, wide in ((1, 0), (0, 0), (0, 2)):
         c = api.Context(0)
         c.set_option("seg_fb", seg)
+        c.set_option("wide_fb", wide)  # 2 = the thread-per-chain kernels (k_fb_wide + k_fb_gamma) whatever the count
         c.set_features(x, off)
         c.set_models(ms)
         out.append(c.estep(labels))
         c.close()
-    (st1, lp1), (st0, lp0) = out
+    (st1, lp1), (st0, lp0), (st2, lp2) = out
+    assert (np.isfinite(lp2) == np.isfinite(lp0)).all() and np.allclose(lp2[np.isfinite(lp0)], lp0[np.isfinite(lp0)], rtol=1e-9)
+    sf2 = np.isfinite(st0)
+    assert (np.isfinite(st2) == sf2).all() and np.allclose(st2[sf2], st0[sf2], rtol=2e-5, atol=1e-6 * np.abs(st0[sf2]).max())
     fin = np.isfinite(lp0)
     assert (np.isfinite(lp1) == fin).all() and np.allclose(lp1[fin], lp0[fin], rtol=1e-9)
     sf = np.isfinite(st0)  # sum_logp is -inf for a word with an utterance shorter than its state chain
