@@ -901,7 +901,7 @@ k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const
 // third phase for k_fb_wide: one warp per utterance, lanes over frames (the same arithmetic as k_fb's phase 2)
 constexpr int kGammaWarps = 8;
 template <int NS>
-__global__ void __launch_bounds__(kGammaWarps * 32)
+__global__ void __launch_bounds__(kGammaWarps * 32, 2)
 k_fb_gamma(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
            const double *__restrict__ Aall, int U, const float *__restrict__ alpha_ws, const float *__restrict__ beta_ws,
            const double *__restrict__ phi_utt, const double *__restrict__ lp_utt, float *__restrict__ gamma,
