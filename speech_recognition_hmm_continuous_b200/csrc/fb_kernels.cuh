@@ -773,6 +773,10 @@ k_fb_seg(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
 constexpr int kWideThreads = 128;
 constexpr int kWidePF = 4;
 
+// Log-emissions are fetched in chunks of four frames aligned to the absolute frame index: 4 x NS floats = NS
+// 16-byte loads (a lane per utterance makes every load instruction touch 32 sectors, so the fewer the better).
+// The chunk of the next four frames is in flight while the current one is consumed; a chunk may reach a few
+// frames beyond the utterance or the buffer (the allocation has slack), those frames are skipped.
 template <int NS, bool BANDED>
 __global__ void __launch_bounds__(kWideThreads)
 k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
@@ -789,35 +793,39 @@ k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const
 #pragma unroll
   for (int k = 0; k < NS * NS; k++) a[k] = Aall[(int64_t)v * NS * NS + k];
   double z[NS];
-  const float *p = logb + base * NS;
-  float nxt[kWidePF][NS];
+  const float4 *lb4 = reinterpret_cast<const float4 *>(logb);
+  auto load_chunk = [&](int64_t c, float (&buf)[4 * NS]) {
+    const float4 *p = lb4 + c * NS;
+#pragma unroll
+    for (int q = 0; q < NS; q++) {
+      const float4 x = __ldg(p + q);
+      buf[4 * q] = x.x; buf[4 * q + 1] = x.y; buf[4 * q + 2] = x.z; buf[4 * q + 3] = x.w;
+    }
+  };
+  float nxt[4 * NS], cur[4 * NS];
   if (dir == 0) {
 #pragma unroll
     for (int i = 0; i < NS; i++) z[i] = 0.0;
     int esum = 0;
+    const int64_t c0 = base >> 2, c1 = (base + T - 1) >> 2;
+    load_chunk(c0, nxt);
+    for (int64_t c = c0; c <= c1; c++) {
 #pragma unroll
-    for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)min(k, T - 1) * NS, nxt[k]);
-    for (int t0 = 0; t0 < T; t0 += kWidePF) {
-      float cur[kWidePF][NS];
+      for (int q = 0; q < 4 * NS; q++) cur[q] = nxt[q];
+      if (c < c1) load_chunk(c + 1, nxt);
 #pragma unroll
-      for (int k = 0; k < kWidePF; k++) {
+      for (int k = 0; k < 4; k++) {
+        const int64_t f = 4 * c + k;
+        if (f >= base && f < base + T) {
+          const float *l = cur + k * NS;
+          float m = l[0];
 #pragma unroll
-        for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
-      }
-#pragma unroll
-      for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)min(t0 + kWidePF + k, T - 1) * NS, nxt[k]);
-#pragma unroll
-      for (int k = 0; k < kWidePF; k++) {
-        const int t = t0 + k;
-        if (t < T) {
-          float m = cur[k][0];
-#pragma unroll
-          for (int i = 1; i < NS; i++) m = fmaxf(m, cur[k][i]);
+          for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
           const float ms = (m > kNegInf) ? m : 0.f;
           double raw[NS];
-          if (t == 0) {
+          if (f == base) {
 #pragma unroll
-            for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? exp_scaled(cur[k][0] - ms) : 0.0;  // pi = [1,0,..,0]
+            for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? exp_scaled(l[0] - ms) : 0.0;  // pi = [1,0,..,0]
           } else {
 #pragma unroll
             for (int i = 0; i < NS; i++) {
@@ -830,7 +838,7 @@ k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const
 #pragma unroll
                 for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
               }
-              raw[i] = aux * exp_scaled(cur[k][i] - ms);
+              raw[i] = aux * exp_scaled(l[i] - ms);
             }
           }
           int e;
@@ -838,7 +846,7 @@ k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const
 #pragma unroll
           for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
           esum += e;
-          store_row<NS>(alpha_ws + (base + t) * kFbRow, z);
+          store_row<NS>(alpha_ws + f * kFbRow, z);
         }
       }
     }
@@ -848,50 +856,48 @@ k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const
     phi_utt[u] = z[NS - 1] / sm;                                            // alpha^_{T-1}(N-1)
     lp_utt[u] = 0.6931471805599453 * (double)esum + log(z[NS - 1]);        // + sum m_t, added by k_fb_gamma
   } else {
-    // backward: w_{T-1} = e_{N-1}; step t = T-2 .. 0 uses the emissions of frame t + 1
+    // backward: w_{T-1} = e_{N-1}; frame f = T-1 .. 1 (relative) turns w_f into w_{f-1} with the emissions of frame f
 #pragma unroll
     for (int i = 0; i < NS; i++) z[i] = (i == NS - 1) ? 1.0 : 0.0;
     store_row<NS>(beta_ws + (base + T - 1) * kFbRow, z);
+    if (T > 1) {
+      const int64_t chi = (base + T - 1) >> 2, clo = (base + 1) >> 2;
+      load_chunk(chi, nxt);
+      for (int64_t c = chi; c >= clo; c--) {
 #pragma unroll
-    for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)max(T - 1 - k, 0) * NS, nxt[k]);  // frames T-1, T-2, ..
-    for (int s0 = 0; s0 < T - 1; s0 += kWidePF) {  // step s: t = T-2-s, emissions of frame T-1-s
-      float cur[kWidePF][NS];
+        for (int q = 0; q < 4 * NS; q++) cur[q] = nxt[q];
+        if (c > clo) load_chunk(c - 1, nxt);
 #pragma unroll
-      for (int k = 0; k < kWidePF; k++) {
+        for (int k = 3; k >= 0; k--) {
+          const int64_t f = 4 * c + k;
+          if (f >= base + 1 && f <= base + T - 1) {
+            const float *l = cur + k * NS;
+            float m = l[0];
 #pragma unroll
-        for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
-      }
+            for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
+            const float ms = (m > kNegInf) ? m : 0.f;
+            double q[NS], raw[NS];
 #pragma unroll
-      for (int k = 0; k < kWidePF; k++) load_lb<NS>(p + (int64_t)max(T - 1 - (s0 + kWidePF + k), 0) * NS, nxt[k]);
+            for (int j = 0; j < NS; j++) q[j] = exp_scaled(l[j] - ms) * z[j];
 #pragma unroll
-      for (int k = 0; k < kWidePF; k++) {
-        const int sx = s0 + k;
-        if (sx < T - 1) {
-          float m = cur[k][0];
+            for (int i = 0; i < NS; i++) {
+              double aux;
+              if (BANDED) {
+                aux = a[i * NS + i] * q[i];
+                if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
+              } else {
+                aux = 0.0;
 #pragma unroll
-          for (int i = 1; i < NS; i++) m = fmaxf(m, cur[k][i]);
-          const float ms = (m > kNegInf) ? m : 0.f;
-          double q[NS], raw[NS];
-#pragma unroll
-          for (int j = 0; j < NS; j++) q[j] = exp_scaled(cur[k][j] - ms) * z[j];
-#pragma unroll
-          for (int i = 0; i < NS; i++) {
-            double aux;
-            if (BANDED) {
-              aux = a[i * NS + i] * q[i];
-              if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
-            } else {
-              aux = 0.0;
-#pragma unroll
-              for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
+                for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
+              }
+              raw[i] = aux;
             }
-            raw[i] = aux;
-          }
-          int e;
-          const double r = pow2_scale_max<NS>(raw, e);
+            int e;
+            const double r = pow2_scale_max<NS>(raw, e);
 #pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
-          store_row<NS>(beta_ws + (base + T - 2 - sx) * kFbRow, z);
+            for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+            store_row<NS>(beta_ws + (f - 1) * kFbRow, z);
+          }
         }
       }
     }
