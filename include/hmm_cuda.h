@@ -19,6 +19,7 @@
 #ifndef HMM_CUDA_H
 #define HMM_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -69,6 +70,19 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 int hmmcu_set_features(hmmcu_ctx *ctx, const double *x, const int64_t *frame_off, int U, int D);
 /* Same, but x is already a DEVICE pointer (features resident in HBM). */
 int hmmcu_set_features_device(hmmcu_ctx *ctx, const double *x_dev, const int64_t *frame_off, int U, int D);
+
+/* Streaming form of hmmcu_set_features for the ingest pipeline (hmmh_ingest below): announce the geometry, hand
+ * over frame ranges [first_frame, first_frame + n_frames) of x[.][D] as they become available (each call enqueues
+ * an asynchronous copy; *ticket tells hmmcu_features_wait when the source buffer may be reused; at most 16 tickets
+ * are in flight), then _end forms the centre and the packed rows on the device.  The context ends up in the same
+ * state as after hmmcu_set_features on the concatenated buffer.  Replaces the same fread loop as above. */
+int hmmcu_features_begin(hmmcu_ctx *ctx, const int64_t *frame_off, int U, int D);
+int hmmcu_features_append(hmmcu_ctx *ctx, const double *x, int64_t first_frame, int64_t n_frames, int *ticket);
+int hmmcu_features_wait(hmmcu_ctx *ctx, int ticket);
+int hmmcu_features_end(hmmcu_ctx *ctx);
+/* Pinned staging buffer `slot` (0..3) of at least `bytes`, owned by the context and kept until hmmcu_destroy
+ * (NULL on failure): what hmmh_ingest reads the files into. */
+void *hmmcu_staging(hmmcu_ctx *ctx, int slot, uint64_t bytes);
 
 /* V models of identical topology, struct-of-arrays in the semantics of `struct state` /
  * `struct mixture` (T-FS:53-64, R-FS:52-63) and transition_probab:
@@ -174,6 +188,35 @@ void hmmh_model_free(hmmh_model *m);
 /* Feature file: int32 D, then T x D doubles, T implied by EOF (T-FS:527-581).  *x is malloc'd. */
 int hmmh_read_features(const char *path, double **x, int *T, int *D);
 int hmmh_write_features(const char *path, const double *x, int T, int D);
+
+/* Many-files reader (replaces the list walk + per-frame fread of T-FS:272-321, 527-548 and
+ * R-FS:341-369, 518-539).  hmmh_read_list: the whitespace-separated names of a list file.  hmmh_scan_features:
+ * frame offsets of U files from their sizes (frame_off[U+1]) and D from the first header.  hmmh_ingest: scan, then
+ * a pool of `nthreads` readers (0 = $HMMCU_INGEST_THREADS or min(16, cores)) fills pinned staging buffers that are
+ * streamed to the device through hmmcu_features_begin/append/end while the next ones are read; no host copy of the
+ * corpus is kept.  *bad_file = index of the file that failed (HMMCU_EIO: missing, short, wrong D, or empty).
+ * hmmh_ingest_to is the same pipeline into any sink (the CPU tests use a memory sink). */
+typedef struct hmmh_sink {
+  void *user;
+  int (*begin)(void *user, const int64_t *frame_off, int U, int D);
+  int (*append)(void *user, const double *x, int64_t first_frame, int64_t n_frames, int *ticket);
+  int (*wait)(void *user, int ticket);
+  int (*end)(void *user);
+  void *(*stage_alloc)(void *user, int slot, size_t bytes); /* staging buffer `slot` (0..2), owned by the sink; NULL = malloc/free */
+} hmmh_sink;
+typedef struct hmmh_ingest_stats {
+  double scan_s, stage_s, read_s, total_s; /* fstat pass; getting the staging buffers; read + hand-off; everything incl. the sink's end() */
+  int64_t bytes;                  /* feature payload */
+  int batches, threads;
+} hmmh_ingest_stats;
+int hmmh_read_list(const char *list_path, char ***paths, int *n);
+void hmmh_free_list(char **paths, int n);
+int hmmh_scan_features(const char *const *paths, int U, int nthreads, int *D, int64_t *frame_off, int *bad_file);
+int hmmh_ingest_to(const hmmh_sink *sink, const char *const *paths, int U, int nthreads, int64_t stage_frames,
+                   int64_t *frame_off, int *D, int *bad_file, hmmh_ingest_stats *stats);
+int hmmh_ingest(hmmcu_ctx *ctx, const char *const *paths, int U, int nthreads, int64_t *frame_off, int *D,
+                int *bad_file, hmmh_ingest_stats *stats);
+
 /* .hmm model file, layout of writing_model / reading_model (T-FS:2043-2146, 604-711).
  * len_bytes: 8 = LP64 size_t header (what the reference writes here), 4 = the shipped 32-bit files,
  * 0 = auto-detect on read. */

@@ -24,6 +24,8 @@ EXPORTS = [
     "hmmcu_enable_timing", "hmmh_model_alloc", "hmmh_model_free", "hmmh_read_features", "hmmh_write_features",
     "hmmh_read_model", "hmmh_write_model", "hmmh_init_model", "hmmh_mstep", "hmmh_upload_models", "hmmh_train",
     "hmmh_train_main", "hmmh_test_main",
+    "hmmcu_features_begin", "hmmcu_features_append", "hmmcu_features_wait", "hmmcu_features_end", "hmmcu_staging",
+    "hmmh_read_list", "hmmh_free_list", "hmmh_scan_features", "hmmh_ingest_to", "hmmh_ingest",
 ]
 
 
@@ -39,6 +41,22 @@ class _CModel(C.Structure):
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 _lib = None
+
+
+class IngestStats(C.Structure):  # hmmh_ingest_stats
+    _fields_ = [("scan_s", C.c_double), ("stage_s", C.c_double), ("read_s", C.c_double), ("total_s", C.c_double), ("bytes", C.c_int64),
+                ("batches", C.c_int), ("threads", C.c_int)]
+
+
+_SinkBegin = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int)
+_SinkAppend = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64, C.c_int64, C.POINTER(C.c_int))
+_SinkWait = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+_SinkEnd = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class _CSink(C.Structure):  # hmmh_sink
+    _fields_ = [("user", C.c_void_p), ("begin", _SinkBegin), ("append", _SinkAppend), ("wait", _SinkWait), ("end", _SinkEnd),
+                ("stage_alloc", C.c_void_p)]
 
 
 def _libc_free(p):
@@ -95,6 +113,15 @@ def load():
     lib.hmmh_read_features.argtypes = [C.c_char_p, C.POINTER(_dp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.hmmh_write_features.argtypes = [C.c_char_p, _dp, C.c_int, C.c_int]
     lib.hmmh_init_model.argtypes = [C.POINTER(_CModel), _dp, _lp, C.c_int]
+    lib.hmmcu_features_begin.argtypes = [C.c_void_p, _lp, C.c_int, C.c_int]
+    lib.hmmcu_features_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int)]
+    lib.hmmcu_features_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.hmmcu_features_end.argtypes = [C.c_void_p]
+    lib.hmmh_scan_features.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(C.c_int), _lp, C.POINTER(C.c_int)]
+    lib.hmmh_ingest_to.argtypes = [C.POINTER(_CSink), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int64, _lp, C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), C.POINTER(IngestStats)]
+    lib.hmmh_ingest.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, _lp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(IngestStats)]
     lib.hmmh_mstep.argtypes = [C.POINTER(_CModel), _dp]
     lib.hmmh_upload_models.argtypes = [C.c_void_p, C.POINTER(_CModel), C.c_int]
     lib.hmmh_train.argtypes = [C.c_void_p, C.POINTER(_CModel), C.c_int, _ip, C.c_int, _dp, C.POINTER(C.c_int), C.c_int,
@@ -211,6 +238,33 @@ class Context:
         self.U, self.D, self.F = len(off) - 1, D, int(off[-1])
         self.off = off
         self._ck(self.lib.hmmcu_set_features_device(self.h, dev_ptr, off.ctypes.data_as(_lp), self.U, D), "hmmcu_set_features_device")
+
+    def ingest(self, paths, threads=0):
+        """Feature files -> HBM through the many-files reader (hmmh_ingest); returns (off, D, IngestStats)."""
+        U = len(paths)
+        arr = (C.c_char_p * U)(*[os.fsencode(p) for p in paths])
+        off = np.zeros(U + 1, dtype=np.int64)
+        D, bad, st = C.c_int(), C.c_int(-1), IngestStats()
+        rc = self.lib.hmmh_ingest(self.h, arr, U, threads, off.ctypes.data_as(_lp), C.byref(D), C.byref(bad), C.byref(st))
+        if rc == 5:
+            raise HmmCudaError("hmmh_ingest: cannot read %s" % (paths[bad.value] if bad.value >= 0 else "?"))
+        self._ck(rc, "hmmh_ingest")
+        self.U, self.D, self.F, self.off = U, D.value, int(off[-1]), off
+        return off, D.value, st
+
+    def features_stream(self, off, D, chunks):
+        """hmmcu_features_begin / append / end over (first_frame, ndarray) pairs -- the streaming form of set_features."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self.U, self.D, self.F, self.off = len(off) - 1, D, int(off[-1]), off
+        self._ck(self.lib.hmmcu_features_begin(self.h, off.ctypes.data_as(_lp), self.U, D), "hmmcu_features_begin")
+        keep = []
+        for f0, xc in chunks:
+            xc = _f64(xc)
+            keep.append(xc)  # pageable sources are staged by the runtime before the call returns; kept anyway
+            t = C.c_int()
+            self._ck(self.lib.hmmcu_features_append(self.h, xc.ctypes.data, int(f0), xc.shape[0], C.byref(t)), "hmmcu_features_append")
+            self._ck(self.lib.hmmcu_features_wait(self.h, t.value), "hmmcu_features_wait")
+        self._ck(self.lib.hmmcu_features_end(self.h), "hmmcu_features_end")
 
     def set_models(self, ms):
         self.V, self.N, self.M = ms.V, ms.N, ms.M
@@ -391,6 +445,47 @@ def read_features(path):
     x = np.ctypeslib.as_array(p, (T.value, D.value)).copy() if T.value > 0 else np.zeros((0, D.value))
     _libc_free(p)
     return x
+
+
+def scan_features(paths, threads=0):
+    """Frame offsets and D of a list of feature files from their sizes (hmmh_scan_features)."""
+    lib = load()
+    U = len(paths)
+    arr = (C.c_char_p * U)(*[os.fsencode(p) for p in paths])
+    off = np.zeros(U + 1, dtype=np.int64)
+    D, bad = C.c_int(), C.c_int(-1)
+    rc = lib.hmmh_scan_features(arr, U, threads, C.byref(D), off.ctypes.data_as(_lp), C.byref(bad))
+    if rc:
+        raise HmmCudaError("hmmh_scan_features failed (%d) at file %d" % (rc, bad.value))
+    return off, D.value
+
+
+def ingest_to_memory(paths, threads=0, stage_frames=0):
+    """The ingest pipeline of hmmh_ingest into a numpy array instead of the device (host logic tests):
+    returns (x[F][D], off, IngestStats)."""
+    lib = load()
+    U = len(paths)
+    arr = (C.c_char_p * U)(*[os.fsencode(p) for p in paths])
+    off = np.zeros(U + 1, dtype=np.int64)
+    box = {"x": None, "log": []}
+
+    def begin(user, foff, u, d):
+        box["x"] = np.full((int(foff[u]), d), np.nan)
+        return 0
+
+    def append(user, xp, f0, n, ticket):
+        d = box["x"].shape[1]
+        box["x"][f0:f0 + n] = np.ctypeslib.as_array(xp, (n, d))
+        box["log"].append((int(f0), int(n)))
+        ticket[0] = len(box["log"]) % 16
+        return 0
+
+    sink = _CSink(None, _SinkBegin(begin), _SinkAppend(append), _SinkWait(lambda user, t: 0), _SinkEnd(lambda user: 0), None)
+    D, bad, st = C.c_int(), C.c_int(-1), IngestStats()
+    rc = lib.hmmh_ingest_to(C.byref(sink), arr, U, threads, stage_frames, off.ctypes.data_as(_lp), C.byref(D), C.byref(bad), C.byref(st))
+    if rc:
+        raise HmmCudaError("hmmh_ingest_to failed (%d) at file %d" % (rc, bad.value))
+    return box["x"], off, st, box["log"]
 
 
 def write_features(path, x):

@@ -74,6 +74,11 @@ struct hmmcu_ctx {
   int up_chunks = 4;         // "upload_chunks" option
   cudaEvent_t ev_chunk[kUpChunks] = {};
   cudaEvent_t ev_idle = nullptr;
+  bool stream_open = false;  // between hmmcu_features_begin and _end
+  void *stage_h[4] = {};     // pinned staging buffers of the ingest pipeline (hmmcu_staging), kept for the context's life
+  size_t stage_cap[4] = {};
+  int64_t stream_frames = 0;
+  int stream_next = 0;
   double *ctr_h = nullptr;  // pinned [256]
   char err[512] = "";
   int64_t launches = 0;
@@ -296,6 +301,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   for (cudaEvent_t e : ctx->ev_chunk)
     if (e) cudaEventDestroy(e);
   if (ctx->ev_idle) cudaEventDestroy(ctx->ev_idle);
+  for (void *p : ctx->stage_h)
+    if (p) cudaFreeHost(p);
   if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
   cudaStreamDestroy(ctx->st);
   delete ctx;
@@ -344,10 +351,8 @@ int64_t hmmcu_stats_size(int N, int M, int D) {
 }
 
 // ---------------------------------------------------------------------------------- features ----
-static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const double *x_dev, const int64_t *frame_off,
-                               int U, int D) {
-  if (!ctx) return HMMCU_EINVAL;
-  if (U < 0 || D < 1 || !frame_off || (U > 0 && !x_host && !x_dev)) return fail(ctx, HMMCU_EINVAL, "set_features: bad arguments");
+// geometry of a new feature set: validation, offsets, buffers (shared by the one-shot and the streaming upload)
+static int features_geometry(hmmcu_ctx *ctx, const int64_t *frame_off, int U, int D) {
   const int DP = round_up(D + 1, 4);
   if (DP > 256) return fail(ctx, HMMCU_EINVAL, "set_features: D=%d too large (max 251)", D);
   if (frame_off[0] != 0) return fail(ctx, HMMCU_EINVAL, "set_features: frame_off[0] must be 0");
@@ -373,20 +378,47 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
   ctx->pack_dirty = true;  // the centre may move
   ctx->kappa_stale = true;
   ctx->have_features = true;
+  ctx->stream_open = false;
   if (F == 0) return HMMCU_OK;
   CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
   if (!same_geometry) CK(cudaMemcpyAsync(ctx->off_d.p, ctx->off.data(), sizeof(int64_t) * (U + 1), cudaMemcpyHostToDevice, ctx->st));
   CK(ctx->x32.ensure(sizeof(float) * F * DP));
   CK(ctx->ctr.ensure(sizeof(double) * DP));
   CK(ctx->xabs_d.ensure(sizeof(unsigned int) * DP));
-  auto pack_range = [&](int64_t f0, int64_t f1) -> int {
-    const int64_t total = (f1 - f0) * DP;
-    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-    k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64 + f0 * D, ctx->ctr.as<double>(), f1 - f0, D, DP, ctx->x32.as<float>() + f0 * DP,
-                                                ctx->xabs_d.as<unsigned int>());
-    LAUNCH_CHECK();
-    return HMMCU_OK;
-  };
+  return HMMCU_OK;
+}
+
+static int pack_range(hmmcu_ctx *ctx, int64_t f0, int64_t f1) {
+  const int D = ctx->D, DP = ctx->DP;
+  const int64_t total = (f1 - f0) * DP;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+  k_pack_features<<<blocks, 256, 0, ctx->st>>>(ctx->d_x64 + f0 * D, ctx->ctr.as<double>(), f1 - f0, D, DP, ctx->x32.as<float>() + f0 * DP,
+                                              ctx->xabs_d.as<unsigned int>());
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
+// centre + packed fp32 rows from fp64 features already in device memory
+static int pack_from_device(hmmcu_ctx *ctx) {
+  t_begin(ctx, "pack");
+  k_center<<<1, 1024, 0, ctx->st>>>(ctx->d_x64, ctx->F, ctx->D, ctx->DP, ctx->ctr.as<double>());
+  LAUNCH_CHECK();
+  CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * ctx->DP, ctx->st));
+  int rc = pack_range(ctx, 0, ctx->F);
+  if (rc) return rc;
+  t_end(ctx, "pack");
+  return HMMCU_OK;
+}
+
+static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const double *x_dev, const int64_t *frame_off,
+                               int U, int D) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (U < 0 || D < 1 || !frame_off || (U > 0 && !x_host && !x_dev)) return fail(ctx, HMMCU_EINVAL, "set_features: bad arguments");
+  int rc0 = features_geometry(ctx, frame_off, U, D);
+  if (rc0) return rc0;
+  const int DP = ctx->DP;
+  const int64_t F = ctx->F;
+  if (F == 0) return HMMCU_OK;
   if (x_host) {
     // Upload pipeline: the copy engine streams the frames in chunks on its own stream while the host
     // forms the centre from the same strided sample k_center takes (same summation order), and `st`
@@ -433,7 +465,7 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
       const int64_t f0 = cb[k], f1 = cb[k + 1];
       CK(cudaStreamWaitEvent(ctx->st, ctx->ev_chunk[k], 0));
       if (f1 > f0) {
-        int rc = pack_range(f0, f1);
+        int rc = pack_range(ctx, f0, f1);
         if (rc) return rc;
       }
     }
@@ -443,15 +475,77 @@ static int set_features_common(hmmcu_ctx *ctx, const double *x_host, const doubl
     CK(cudaEventSynchronize(ctx->ev_idle));
   } else {
     ctx->d_x64 = x_dev;
-    t_begin(ctx, "pack");
-    k_center<<<1, 1024, 0, ctx->st>>>(ctx->d_x64, F, D, DP, ctx->ctr.as<double>());
-    LAUNCH_CHECK();
-    CK(cudaMemsetAsync(ctx->xabs_d.p, 0, sizeof(unsigned int) * DP, ctx->st));
-    int rc = pack_range(0, F);
-    if (rc) return rc;
-    t_end(ctx, "pack");
+    return pack_from_device(ctx);
   }
   return HMMCU_OK;
+}
+
+// Streaming upload for the ingest pipeline: the caller announces the geometry, then hands over
+// frame ranges in any order from (ideally pinned) staging buffers as its readers fill them; every range is copied
+// asynchronously on the copy stream and the ticket tells when the staging buffer may be refilled.  _end forms the
+// centre and the packed rows on the device exactly as hmmcu_set_features_device does, so the context ends up in
+// the same state as after hmmcu_set_features on the concatenated buffer.
+// Pinned staging buffer `slot` (0..3) of at least `bytes`, owned by the context and reused across ingests: pinning
+// costs ~0.3 ms per MiB, more than reading the same bytes from the page cache.
+void *hmmcu_staging(hmmcu_ctx *ctx, int slot, uint64_t bytes) {
+  if (!ctx || slot < 0 || slot >= 4) return nullptr;
+  if (ctx->stage_cap[slot] >= bytes) return ctx->stage_h[slot];
+  if (cudaSetDevice(ctx->dev) != cudaSuccess) return nullptr;
+  if (ctx->stage_h[slot]) { cudaStreamSynchronize(ctx->st_copy); cudaFreeHost(ctx->stage_h[slot]); }
+  ctx->stage_h[slot] = nullptr;
+  ctx->stage_cap[slot] = 0;
+  if (cudaHostAlloc(&ctx->stage_h[slot], bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ctx->stage_cap[slot] = bytes;
+  return ctx->stage_h[slot];
+}
+
+int hmmcu_features_begin(hmmcu_ctx *ctx, const int64_t *frame_off, int U, int D) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (U < 1 || D < 1 || !frame_off) return fail(ctx, HMMCU_EINVAL, "features_begin: bad arguments");
+  int rc = features_geometry(ctx, frame_off, U, D);
+  if (rc) return rc;
+  ctx->have_features = false;  // until _end
+  CK(ctx->x64_own.ensure(sizeof(double) * ctx->F * D));
+  ctx->d_x64 = ctx->x64_own.as<double>();
+  CK(cudaEventRecord(ctx->ev_idle, ctx->st));  // earlier kernels may still read the old features
+  CK(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_idle, 0));
+  ctx->stream_open = true;
+  ctx->stream_frames = 0;
+  ctx->stream_next = 0;
+  return HMMCU_OK;
+}
+
+int hmmcu_features_append(hmmcu_ctx *ctx, const double *x, int64_t first_frame, int64_t n_frames, int *ticket) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (!ctx->stream_open) return fail(ctx, HMMCU_EINVAL, "features_append: no hmmcu_features_begin");
+  if (!x || first_frame < 0 || n_frames < 1 || first_frame + n_frames > ctx->F) return fail(ctx, HMMCU_EINVAL, "features_append: bad frame range");
+  CK(cudaSetDevice(ctx->dev));
+  const int slot = ctx->stream_next;
+  ctx->stream_next = (slot + 1) % hmmcu_ctx::kUpChunks;
+  CK(cudaMemcpyAsync(ctx->x64_own.as<double>() + first_frame * ctx->D, x, sizeof(double) * n_frames * ctx->D, cudaMemcpyHostToDevice, ctx->st_copy));
+  CK(cudaEventRecord(ctx->ev_chunk[slot], ctx->st_copy));
+  ctx->stream_frames += n_frames;
+  if (ticket) *ticket = slot;
+  return HMMCU_OK;
+}
+
+int hmmcu_features_wait(hmmcu_ctx *ctx, int ticket) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (ticket < 0 || ticket >= hmmcu_ctx::kUpChunks) return fail(ctx, HMMCU_EINVAL, "features_wait: bad ticket");
+  CK(cudaEventSynchronize(ctx->ev_chunk[ticket]));
+  return HMMCU_OK;
+}
+
+int hmmcu_features_end(hmmcu_ctx *ctx) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (!ctx->stream_open) return fail(ctx, HMMCU_EINVAL, "features_end: no hmmcu_features_begin");
+  if (ctx->stream_frames != ctx->F) return fail(ctx, HMMCU_EINVAL, "features_end: %lld of %lld frames appended", (long long)ctx->stream_frames, (long long)ctx->F);
+  CK(cudaSetDevice(ctx->dev));
+  ctx->stream_open = false;
+  CK(cudaEventRecord(ctx->ev_idle, ctx->st_copy));
+  CK(cudaStreamWaitEvent(ctx->st, ctx->ev_idle, 0));
+  ctx->have_features = true;
+  return pack_from_device(ctx);
 }
 
 int hmmcu_set_features(hmmcu_ctx *ctx, const double *x, const int64_t *frame_off, int U, int D) {

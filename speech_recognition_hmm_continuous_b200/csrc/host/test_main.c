@@ -97,30 +97,18 @@ int hmmh_test_main(int argc, char **argv) {
   g_out = fopen(result, "w");
   if (!g_out) die("can't open file %s \n", result);
   char (*spoken)[WSTR] = NULL;
-  double *x = NULL;
-  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * 2);
-  size_t cap = 0, frames = 0;
+  char **paths = NULL;
   int U = 0, D = models[0].D;
-  off[0] = 0;
   char w[WSTR], path[STR];
   while (fscanf(fw, "%49s", w) == 1) {
     if (fscanf(ff, "%99s", path) != 1) die("reading error on file %s \n", feat_list);
-    double *xu; int T, d;
-    if (hmmh_read_features(path, &xu, &T, &d) != HMMCU_OK) die("file %s not found \n", path);
-    if (d != D) die("reading error on file %s \n", path);
-    if (frames + T > cap) {
-      cap = (frames + T) * 2;
-      x = (double *)realloc(x, sizeof(double) * cap * D);
-    }
-    memcpy(x + frames * D, xu, sizeof(double) * (size_t)T * D);
-    free(xu);
-    frames += T;
     spoken = (char (*)[WSTR])realloc(spoken, (size_t)(U + 1) * WSTR);
     strncpy(spoken[U], w, WSTR);
-    off = (int64_t *)realloc(off, sizeof(int64_t) * (U + 3));
-    off[++U] = (int64_t)frames;
+    paths = (char **)realloc(paths, sizeof(char *) * (size_t)(U + 1));
+    paths[U++] = strdup(path);
   }
   fclose(ff); fclose(fw);
+  int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
 
   /* writing_header R-FS:1014-1031 (weight printed through an int*, as the reference does) */
   int wbits;
@@ -142,7 +130,12 @@ int hmmh_test_main(int argc, char **argv) {
   if (U > 0) {
     hmmcu_ctx *ctx = NULL;
     if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
-    if (hmmcu_set_features(ctx, x, off, U, D) != HMMCU_OK || hmmh_upload_models(ctx, models, V) != HMMCU_OK ||
+    /* every test file is read once (the reference re-reads it for each model, R-FS:341-369), by the many-files reader */
+    int d = 0, bad = -1;
+    int rc = hmmh_ingest(ctx, (const char *const *)paths, U, 0, off, &d, &bad, NULL);
+    if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : feat_list);
+    if (rc == HMMCU_OK && d != D) die("reading error on file %s \n", paths[0]);
+    if (rc != HMMCU_OK || hmmh_upload_models(ctx, models, V) != HMMCU_OK ||
         hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK || hmmcu_rank(ctx, logp, U, V, weight, label, second) != HMMCU_OK)
       die("GPU error: %s \n", hmmcu_last_error(ctx));
     hmmcu_destroy(ctx);
@@ -198,6 +191,8 @@ int hmmh_test_main(int argc, char **argv) {
   }
   fclose(g_out);
   for (int v = 0; v < V; v++) hmmh_model_free(&models[v]);
-  free(models); free(x); free(off); free(spoken); free(logp); free(label); free(second); free(wrong);
+  for (int u = 0; u < U; u++) free(paths[u]);
+  free(paths);
+  free(models); free(off); free(spoken); free(logp); free(label); free(second); free(wrong);
   return 0;
 }

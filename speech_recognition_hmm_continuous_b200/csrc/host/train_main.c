@@ -76,37 +76,21 @@ int hmmh_train_main(int argc, char **argv) {
   strtok(txt, "."); /* T-FS:205-207 */
   strcat(txt, ".txt");
 
-  /* the whole training list, once (the reference re-reads every file twice per iteration) */
-  FILE *fl = fopen(list, "r");
-  if (!fl) die("file %s not found \n", list);
-  char path[NAME_SIZE];
-  double *x = NULL;
-  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * 2);
-  size_t cap = 0, frames = 0;
-  int U = 0, D = 0;
-  off[0] = 0;
-  while (fscanf(fl, "%99s", path) == 1) {
-    double *xu; int T, d;
-    printf("\r\nOpenning %s", path);
-    if (hmmh_read_features(path, &xu, &T, &d) != HMMCU_OK) die("file %s not found \n", path);
-    if (U == 0) D = d;
-    if (d != D) die("reading error on file %s \n", path);
-    if (frames + T > cap) {
-      cap = (frames + T) * 2;
-      x = (double *)realloc(x, sizeof(double) * cap * D);
-    }
-    memcpy(x + frames * D, xu, sizeof(double) * (size_t)T * D);
-    free(xu);
-    frames += T;
-    off = (int64_t *)realloc(off, sizeof(int64_t) * (U + 3));
-    off[++U] = (int64_t)frames;
-  }
-  fclose(fl);
+  /* the whole training list, once (the reference re-reads every file twice per iteration): the many-files
+   * reader streams it into HBM through pinned staging, no host copy is kept (ingest.c) */
+  char **paths = NULL;
+  int U = 0, D = 0, bad = -1;
+  if (hmmh_read_list(list, &paths, &U) != HMMCU_OK) die("file %s not found \n", list);
   if (U == 0) die("file %s not found \n", list);
+  for (int u = 0; u < U; u++) printf("\r\nOpenning %s", paths[u]);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * ((size_t)U + 1));
+  if (!off) die("error on allocating memory. %s\n", "");
 
   hmmcu_ctx *ctx = NULL;
   if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
-  if (hmmcu_set_features(ctx, x, off, U, D) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
+  int rc = hmmh_ingest(ctx, (const char *const *)paths, U, 0, off, &D, &bad, NULL);
+  if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : list);
+  if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
   int32_t *u2m = (int32_t *)calloc((size_t)U, sizeof(int32_t));
 
   hmmh_model m;
@@ -121,8 +105,17 @@ int hmmh_train_main(int argc, char **argv) {
     if (D <= 64 && M <= 255 && N <= 8) {
       if (hmmcu_init_models(ctx, u2m, 1, N, M) != HMMCU_OK || hmmcu_get_models(ctx, m.A, m.c, m.mu, m.inv_var, m.det) != HMMCU_OK)
         die("GPU error: %s \n", hmmcu_last_error(ctx));
-    } else {
+    } else { /* shapes the device builder does not take: the host builder, from a host copy of the corpus */
+      double *x = (double *)malloc(sizeof(double) * (size_t)off[U] * D);
+      if (!x) die("error on allocating memory. %s\n", "");
+      for (int u = 0; u < U; u++) {
+        double *xu; int T, d;
+        if (hmmh_read_features(paths[u], &xu, &T, &d) != HMMCU_OK || d != D || T != (int)(off[u + 1] - off[u])) die("reading error on file %s \n", paths[u]);
+        memcpy(x + off[u] * D, xu, sizeof(double) * (size_t)T * D);
+        free(xu);
+      }
       hmmh_init_model(&m, x, off, U);
+      free(x);
     }
   }
   memset(m.word, 0, sizeof(m.word));
@@ -148,6 +141,7 @@ int hmmh_train_main(int argc, char **argv) {
   write_report(txt, out, word, m.N, m.M, list, t0, t1, cpu, U, mean, iters);
   printf("\r\nmean probability: %f, iterations: %d\r\n", mean, iters);
   hmmh_model_free(&m);
-  free(x); free(off); free(u2m);
+  hmmh_free_list(paths, U);
+  free(off); free(u2m);
   return 0;
 }

@@ -412,6 +412,38 @@ def test_chunked_upload_matches_device_resident_features():
     assert np.allclose(lp_h, lp_d, rtol=1e-12) and np.allclose(st_h, st_d, rtol=1e-9, atol=1e-9)
 
 
+def test_ingest_pipeline_and_streamed_upload_match_set_features(tmp_path):
+    """feature files -> pinned staging -> HBM through hmmh_ingest, and the streaming C ABI under it with
+    ranges appended out of order, leave the context in the same state as hmmcu_set_features on the host buffer."""
+    ms, x, off, labels = _synth(2, 5, 3, 40, seed=909, tmin=200, tmax=300)
+    paths = []
+    for u in range(len(off) - 1):
+        p = str(tmp_path / ("u%03d.bin" % u))
+        api.write_features(p, x[off[u]:off[u + 1]])
+        paths.append(p)
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    st_h, lp_h = c.estep(labels)
+    fw_h = c.forward_scores()
+    off_i, D, st = c.ingest(paths, threads=4)
+    assert D == x.shape[1] and np.array_equal(off_i, off) and st.bytes == x.nbytes and st.batches >= 1
+    st_i, lp_i = c.estep(labels)
+    fw_i = c.forward_scores()
+    F = int(off[-1])
+    cuts = [0, 1000, 1001, 4096, F]
+    order = [2, 0, 3, 1]
+    c.features_stream(off, x.shape[1], [(cuts[k], x[cuts[k]:cuts[k + 1]]) for k in order])
+    st_s, lp_s = c.estep(labels)
+    with pytest.raises(api.HmmCudaError, match="frames appended"):
+        c.features_stream(off, x.shape[1], [(0, x[:100])])
+    c.close()
+    assert np.allclose(lp_h, lp_i, rtol=1e-12) and np.allclose(st_h, st_i, rtol=1e-9, atol=1e-9)
+    assert np.allclose(lp_i, lp_s, rtol=1e-12), np.abs(lp_i - lp_s).max()
+    assert np.allclose(st_i, st_s, rtol=1e-9, atol=1e-9, equal_nan=True)
+    assert np.allclose(fw_h, fw_i, rtol=1e-12), np.abs(fw_h - fw_i).max()
+
+
 def test_many_small_models_take_the_atomic_flush_path(ctx):
     """A CTA of the accumulate kernel that walks through more than two (model, Gaussian block) images flushes
     the later ones with atomics instead of scratch slots; both must add up to the oracle's statistics."""

@@ -125,3 +125,69 @@ def test_split_stats_layout():
     sp = api.split_stats(vec, N, M, D)
     assert sp["num_trans"][0, 0] == 0 and sp["den_trans"][0] == 9 and sp["den_mix"][0] == 12 and sp["S0"][0, 0] == 15
     assert sp["S1"][0, 0, 0] == 21 and sp["S2c"][0, 0, 0] == 45 and sp["sum_logp"] == 69 and sp["n_utt"] == 70
+
+
+# ---- many-files reader: the pipeline of hmmh_ingest driven into a memory sink ----
+def _write_files(tmp_path, lens, D=7, seed=5):
+    rng = np.random.default_rng(seed)
+    paths, xs = [], []
+    for i, T in enumerate(lens):
+        x = rng.standard_normal((T, D))
+        p = str(tmp_path / ("f%04d.bin" % i))
+        api.write_features(p, x)
+        paths.append(p)
+        xs.append(x)
+    return paths, xs
+
+
+@pytest.mark.parametrize("threads,stage_frames", [(1, 0), (4, 0), (8, 64), (3, 1)])
+def test_ingest_pipeline_matches_per_file_reader(tmp_path, threads, stage_frames):
+    lens = [1, 17, 300, 250, 64, 2, 349, 33, 90, 128, 5, 77] * 3   # ragged, including one-frame utterances
+    paths, xs = _write_files(tmp_path, lens)
+    x, off, st, log = api.ingest_to_memory(paths, threads=threads, stage_frames=stage_frames)
+    assert off.tolist() == np.concatenate([[0], np.cumsum(lens)]).tolist()
+    assert np.array_equal(x, np.concatenate(xs))          # bit-exact and every frame delivered exactly once
+    assert sum(n for _, n in log) == sum(lens) and st.bytes == 8 * 7 * sum(lens)
+    if stage_frames:   # batches respect the staging size except for single longer utterances; consecutive and ordered
+        assert all(n <= max(stage_frames, max(lens)) for _, n in log)
+        assert [f for f, _ in log] == np.concatenate([[0], np.cumsum([n for _, n in log])[:-1]]).tolist()
+        assert st.batches == len(log) > 1
+    # the per-file reader sees the same frames
+    for p, xr in zip(paths[:4], xs[:4]):
+        assert np.array_equal(api.read_features(p), xr)
+
+
+def test_ingest_scan_drops_a_trailing_partial_frame_and_reports_bad_files(tmp_path):
+    paths, xs = _write_files(tmp_path, [10, 20, 30])
+    with open(paths[1], "ab") as f:
+        f.write(b"\0" * 13)                                 # a torn last frame (T-FS:536 reads until fread fails)
+    off, D = api.scan_features(paths)
+    assert D == 7 and off.tolist() == [0, 10, 30, 60]
+    x, off2, _, _ = api.ingest_to_memory(paths, threads=2)
+    assert np.array_equal(x, np.concatenate(xs))
+    with pytest.raises(api.HmmCudaError, match="file 2"):
+        api.ingest_to_memory(paths[:2] + [str(tmp_path / "missing.bin")])
+    other = [str(tmp_path / "d9.bin")]
+    api.write_features(other[0], np.zeros((5, 9)))
+    with pytest.raises(api.HmmCudaError, match="file 3"):    # a file of another width
+        api.ingest_to_memory(paths + other)
+    empty = str(tmp_path / "empty.bin")
+    with open(empty, "wb") as f:
+        f.write(struct.pack("i", 7))
+    with pytest.raises(api.HmmCudaError, match="file 1"):    # header only: no frames
+        api.ingest_to_memory([paths[0], empty])
+
+
+def test_read_list_tokens(tmp_path):
+    import ctypes as C
+    lib = api.load()
+    lst = tmp_path / "list.txt"
+    lst.write_text("a.bin  b.bin\n\n c.bin\t" + "x" * 120 + "\n")
+    pp, n = C.POINTER(C.c_char_p)(), C.c_int()
+    lib.hmmh_read_list.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_char_p)), C.POINTER(C.c_int)]
+    assert lib.hmmh_read_list(str(lst).encode(), C.byref(pp), C.byref(n)) == 0
+    toks = [pp[i].decode() for i in range(n.value)]
+    # fscanf("%99s") semantics: a 120-character token arrives as 99 + 21 characters (T-FS:272, char[100])
+    assert toks == ["a.bin", "b.bin", "c.bin", "x" * 99, "x" * 21]
+    lib.hmmh_free_list.argtypes = [C.POINTER(C.c_char_p), C.c_int]
+    lib.hmmh_free_list(pp, n.value)
