@@ -223,6 +223,26 @@ int hmmh_ingest(hmmcu_ctx *ctx, const char *const *paths, int U, int nthreads, i
 int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes);
 int hmmh_write_model(const char *path, const hmmh_model *m);
 
+/* Bulk .hmm I/O: V model files of one topology <-> the struct-of-arrays layout of hmmcu_set_models.
+ * Replaces the recogniser's model-list walk (R-FS:214-238) and its one-fread-per-field reading_model (R-FS:612-712):
+ * one read per file, a pool of `nthreads` (0 = as hmmh_ingest), parsed straight into the arrays.  Files with the 4-byte
+ * length header shipped with the reference are accepted; the writer produces the bytes of hmmh_write_model.
+ * *bad_file = index of the file that failed (HMMCU_EIO: unreadable / truncated; HMMCU_EINVAL: another topology). */
+typedef struct hmmh_model_set {
+  int V, N, M, D;
+  char (*word)[64]; /* [V], NUL-terminated */
+  double *A;        /* [V][N][N] */
+  double *c;        /* [V][N][M] */
+  double *mu;       /* [V][N][M][D] */
+  double *inv_var;  /* [V][N][M][D] */
+  double *det;      /* [V][N][M] */
+} hmmh_model_set;
+int hmmh_model_set_alloc(hmmh_model_set *s, int V, int N, int M, int D);
+void hmmh_model_set_free(hmmh_model_set *s);
+int hmmh_read_model_set(const char *const *paths, int V, int nthreads, hmmh_model_set *s, int *bad_file);
+int hmmh_write_model_set(const char *const *paths, const hmmh_model_set *s, int nthreads, int *bad_file);
+int hmmh_upload_model_set(hmmcu_ctx *ctx, const hmmh_model_set *s);
+
 /* creating_initial_model (T-FS:732-1317): uniform left-to-right A, uniform segmentation, LBG
  * splitting + 3 k-means passes, per-cluster variance and weights. */
 int hmmh_init_model(hmmh_model *m, const double *x, const int64_t *frame_off, int U);

@@ -25,6 +25,7 @@ EXPORTS = [
     "hmmh_read_model", "hmmh_write_model", "hmmh_init_model", "hmmh_mstep", "hmmh_upload_models", "hmmh_train",
     "hmmh_train_main", "hmmh_test_main",
     "hmmcu_features_begin", "hmmcu_features_append", "hmmcu_features_wait", "hmmcu_features_end", "hmmcu_staging",
+    "hmmh_model_set_alloc", "hmmh_model_set_free", "hmmh_read_model_set", "hmmh_write_model_set", "hmmh_upload_model_set",
     "hmmh_read_list", "hmmh_free_list", "hmmh_scan_features", "hmmh_ingest_to", "hmmh_ingest",
 ]
 
@@ -35,6 +36,11 @@ class HmmCudaError(RuntimeError):
 
 class _CModel(C.Structure):
     _fields_ = [("word", C.c_char * 64), ("N", C.c_int), ("M", C.c_int), ("D", C.c_int), ("A", _dp), ("c", _dp),
+                ("mu", _dp), ("inv_var", _dp), ("det", _dp)]
+
+
+class _CModelSet(C.Structure):  # hmmh_model_set
+    _fields_ = [("V", C.c_int), ("N", C.c_int), ("M", C.c_int), ("D", C.c_int), ("word", C.POINTER(C.c_char * 64)), ("A", _dp), ("c", _dp),
                 ("mu", _dp), ("inv_var", _dp), ("det", _dp)]
 
 
@@ -113,6 +119,10 @@ def load():
     lib.hmmh_read_features.argtypes = [C.c_char_p, C.POINTER(_dp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.hmmh_write_features.argtypes = [C.c_char_p, _dp, C.c_int, C.c_int]
     lib.hmmh_init_model.argtypes = [C.POINTER(_CModel), _dp, _lp, C.c_int]
+    lib.hmmh_model_set_free.argtypes = [C.POINTER(_CModelSet)]
+    lib.hmmh_read_model_set.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_CModelSet), C.POINTER(C.c_int)]
+    lib.hmmh_write_model_set.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_CModelSet), C.c_int, C.POINTER(C.c_int)]
+    lib.hmmh_upload_model_set.argtypes = [C.c_void_p, C.POINTER(_CModelSet)]
     lib.hmmcu_features_begin.argtypes = [C.c_void_p, _lp, C.c_int, C.c_int]
     lib.hmmcu_features_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int)]
     lib.hmmcu_features_wait.argtypes = [C.c_void_p, C.c_int]
@@ -432,6 +442,38 @@ def write_model(path, ms, v=0):
     rc = lib.hmmh_write_model(path.encode(), C.byref(cm[v]))
     if rc:
         raise HmmCudaError("hmmh_write_model(%s) failed (%d)" % (path, rc))
+
+
+def read_model_set(paths, threads=0):
+    """V .hmm files of one topology -> ModelSet through the bulk reader (hmmh_read_model_set)."""
+    lib = load()
+    V = len(paths)
+    arr = (C.c_char_p * V)(*[os.fsencode(p) for p in paths])
+    cs, bad = _CModelSet(), C.c_int(-1)
+    rc = lib.hmmh_read_model_set(arr, V, threads, C.byref(cs), C.byref(bad))
+    if rc:
+        raise HmmCudaError("hmmh_read_model_set failed (%d) at file %d" % (rc, bad.value))
+    N, M, D = cs.N, cs.M, cs.D
+    ms = ModelSet(np.ctypeslib.as_array(cs.A, (V, N, N)).copy(), np.ctypeslib.as_array(cs.c, (V, N, M)).copy(),
+                  np.ctypeslib.as_array(cs.mu, (V, N, M, D)).copy(), np.ctypeslib.as_array(cs.inv_var, (V, N, M, D)).copy(),
+                  np.ctypeslib.as_array(cs.det, (V, N, M)).copy(), [cs.word[v].value.decode() for v in range(V)])
+    lib.hmmh_model_set_free(C.byref(cs))
+    return ms
+
+
+def write_model_set(paths, ms, threads=0):
+    """ModelSet -> one .hmm file per word (hmmh_write_model_set), the bytes hmmh_write_model produces."""
+    lib = load()
+    assert len(paths) == ms.V
+    arr = (C.c_char_p * ms.V)(*[os.fsencode(p) for p in paths])
+    words = ((C.c_char * 64) * ms.V)()
+    for v in range(ms.V):
+        words[v].value = ms.words[v].encode()[:63]
+    cs = _CModelSet(ms.V, ms.N, ms.M, ms.D, C.cast(words, C.POINTER(C.c_char * 64)), _d(ms.A), _d(ms.c), _d(ms.mu), _d(ms.iv), _d(ms.det))
+    bad = C.c_int(-1)
+    rc = lib.hmmh_write_model_set(arr, C.byref(cs), threads, C.byref(bad))
+    if rc:
+        raise HmmCudaError("hmmh_write_model_set failed (%d) at file %d" % (rc, bad.value))
 
 
 def read_features(path):

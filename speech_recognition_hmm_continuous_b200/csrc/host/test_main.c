@@ -3,8 +3,9 @@
  *   recognition_continuous_fs K modelslist_1..K weight_1..K featlist_1.. wordsfile resultfile
  * Same argv, list / feature / .hmm formats and result-file text.  All (utterance, model) forward
  * scores are computed on the GPU in one batch; ranking follows sorting_probab including its NaN
- * behaviour.  Deliberate limits: K (model sets) is 1, as MAX_MODELS_NUMBER is (R-FS:40); all models
- * must share one topology; one feature stream.
+ * behaviour.  K model sets per word (weighted sum of their log-probabilities, R-FS:326-364) are taken although the
+ * reference is compiled with MAX_MODELS_NUMBER 1 (R-FS:40).  Deliberate limits: the models of one set share one
+ * topology; one feature stream per set.
  * Reproduced quirks: the weight is printed through an int* with "%.2d" (R-FS:1016,1029); the last
  * per-word block lists wrong words only for the first `models_number` vocabulary entries (R-FS:400).
  */
@@ -29,7 +30,7 @@ static FILE *g_out;
 
 /* writing_result_word R-FS:1110-1150 */
 static void write_word_block(int correct, int error, int second, int nwords, const char *spoken, const int *wrong,
-                             hmmh_model *models, double cpu_time, int frames) {
+                             const hmmh_model_set *models, double cpu_time, int frames) {
   int sum = correct + error;
   double per = (double)correct / (double)sum;
   cpu_time /= sum;
@@ -43,7 +44,7 @@ static void write_word_block(int correct, int error, int second, int nwords, con
   if (error != 0) {
     fprintf(g_out, "Wrong words: \n");
     for (int i = 0; i < nwords; i++)
-      if (wrong[i] != 0) fprintf(g_out, "%s: %d time%s\n", models[i].word, wrong[i], wrong[i] == 1 ? "" : "s");
+      if (wrong[i] != 0) fprintf(g_out, "%s: %d time%s\n", models->word[i], wrong[i], wrong[i] == 1 ? "" : "s");
   }
   fprintf(g_out, "Average recognition time: %.2f sec. \n", cpu_time);
   fprintf(g_out, "Average word length: %d frames \n", frames);
@@ -67,77 +68,97 @@ int hmmh_test_main(int argc, char **argv) {
     puts("output_file: name of output file ");
     exit(1);
   }
+  /* K model sets per word, each with its own feature list (one stream each) and weighting coefficient; the
+   * score of word k is sum_j coef_j * logP_j(u, k), accumulated in set order from 0.0 (R-FS:284, 326-364) */
   const int K = atoi(argv[1]);
-  if (K != 1) die("models_number %s is not supported: one model set per word \n", argv[1]);
-  const double weight = atof(argv[3]);
-  const char *models_list = argv[2], *feat_list = argv[4], *words_file = argv[argc - 2], *result = argv[argc - 1];
+  if (K < 1 || K > 16 || argc != 3 * K + 4) die("models_number %s does not match the argument list (one feature list per model set) \n", argv[1]);
+  double weight[16];
+  for (int j = 0; j < K; j++) weight[j] = atof(argv[K + 2 + j]);
+  const char *words_file = argv[argc - 2], *result = argv[argc - 1];
 
-  /* model set */
-  FILE *fm = fopen(models_list, "rb");
-  if (!fm) die("file %s not found \n", models_list);
-  hmmh_model *models = NULL;
-  int V = 0;
-  char name[STR];
-  printf("\r\nLoading Models\r\n");
-  while (fscanf(fm, "%99s", name) == 1) {
-    models = (hmmh_model *)realloc(models, sizeof(hmmh_model) * (V + 1));
-    memset(&models[V], 0, sizeof(hmmh_model));
-    if (hmmh_read_model(name, &models[V], 0) != HMMCU_OK) die("file %s not found \n", name);
-    if (V > 0 && (models[V].N != models[0].N || models[V].M != models[0].M || models[V].D != models[0].D))
-      die("model %s has a different topology: not supported \n", name);
-    V++;
-  }
-  fclose(fm);
-  if (V == 0) die("file %s not found \n", models_list);
-
-  /* test utterances: line i of the feature list pairs with line i of the words file */
-  FILE *ff = fopen(feat_list, "r"), *fw = fopen(words_file, "r");
-  if (!ff) die("file %s not found \n", feat_list);
+  /* the spoken words: line i pairs with line i of every feature list */
+  FILE *fw = fopen(words_file, "r");
   if (!fw) die("file %s not found \n", words_file);
+  char (*spoken)[WSTR] = NULL;
+  int U = 0;
+  char w[WSTR];
+  while (fscanf(fw, "%49s", w) == 1) {
+    spoken = (char (*)[WSTR])realloc(spoken, (size_t)(U + 1) * WSTR);
+    strncpy(spoken[U++], w, WSTR);
+  }
+  fclose(fw);
+  for (int j = 0; j < K; j++) { /* opening_file_read of every list before any work, R-FS:203, 259-266 */
+    FILE *f = fopen(argv[2 + j], "rb");
+    if (!f) die("file %s not found \n", argv[2 + j]);
+    fclose(f);
+    f = fopen(argv[2 + 2 * K + j], "r");
+    if (!f) die("file %s not found \n", argv[2 + 2 * K + j]);
+    fclose(f);
+  }
   g_out = fopen(result, "w");
   if (!g_out) die("can't open file %s \n", result);
-  char (*spoken)[WSTR] = NULL;
-  char **paths = NULL;
-  int U = 0, D = models[0].D;
-  char w[WSTR], path[STR];
-  while (fscanf(fw, "%49s", w) == 1) {
-    if (fscanf(ff, "%99s", path) != 1) die("reading error on file %s \n", feat_list);
-    spoken = (char (*)[WSTR])realloc(spoken, (size_t)(U + 1) * WSTR);
-    strncpy(spoken[U], w, WSTR);
-    paths = (char **)realloc(paths, sizeof(char *) * (size_t)(U + 1));
-    paths[U++] = strdup(path);
-  }
-  fclose(ff); fclose(fw);
-  int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
 
-  /* writing_header R-FS:1014-1031 (weight printed through an int*, as the reference does) */
-  int wbits;
-  memcpy(&wbits, &weight, sizeof(int));
+  /* writing_header R-FS:1014-1031.  The reference hands its double coef_model[] to an int* parameter: entry i
+   * printed with "%.2d" is the i-th 32-bit word of the array, reproduced here. */
+  int wbits[32];
+  memcpy(wbits, weight, sizeof(double) * (size_t)K);
   fprintf(g_out, "Isolated word recognition using Continuous HMM (diagonal covariance matrix). It is considered a final state. \n");
   fprintf(g_out, "Algorithm used for recognition: Forward \n");
   fprintf(g_out, "Number of models: %d  \n", K);
-  fprintf(g_out, "Model name %d: %s\n", 1, models_list);
-  fprintf(g_out, "Weighting coefficient of model %d:%.2d\n", 1, wbits);
+  for (int j = 0; j < K; j++) {
+    fprintf(g_out, "Model name %d: %s\n", j + 1, argv[2 + j]);
+    fprintf(g_out, "Weighting coefficient of model %d:%.2d\n", j + 1, wbits[j]);
+  }
   fprintf(g_out, "Date and time: %s \n\n", date);
 
   struct tms tb;
   times(&tb);
   double old_aux = tb.tms_utime / 60.0;
 
-  /* the hot path: every (utterance, model) forward score, then the ranking rule */
-  double *logp = (double *)malloc(sizeof(double) * (size_t)(U > 0 ? U : 1) * V);
+  /* the hot path, per model set: all files of its feature list into HBM (read once; the reference re-reads every
+   * test file for each model, R-FS:341-369), the whole model list in one go (modelset.c), every (utterance, model)
+   * forward score in one batch; then the ranking rule on the weighted sums */
+  hmmh_model_set models;
+  memset(&models, 0, sizeof(models));
+  int V = 0;
+  double *probab = NULL, *logp = NULL;
+  int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
   int32_t *label = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1)), *second = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
-  if (U > 0) {
-    hmmcu_ctx *ctx = NULL;
-    if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
-    /* every test file is read once (the reference re-reads it for each model, R-FS:341-369), by the many-files reader */
-    int d = 0, bad = -1;
+  hmmcu_ctx *ctx = NULL;
+  if (U > 0 && hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+  for (int j = 0; j < K; j++) {
+    const char *models_list = argv[2 + j], *feat_list = argv[2 + 2 * K + j];
+    char **mpaths = NULL;
+    int Vj = 0, badm = -1;
+    printf("\r\nLoading Models\r\n");
+    if (hmmh_read_list(models_list, &mpaths, &Vj) != HMMCU_OK || Vj == 0) die("file %s not found \n", models_list);
+    hmmh_model_set_free(&models); /* the words of the LAST set name the vocabulary (R-FS:231 overwrites word[]) */
+    int mrc = hmmh_read_model_set((const char *const *)mpaths, Vj, 0, &models, &badm);
+    if (mrc == HMMCU_EINVAL) die("model %s has a different topology: not supported \n", badm >= 0 ? mpaths[badm] : models_list);
+    if (mrc != HMMCU_OK) die("file %s not found \n", badm >= 0 ? mpaths[badm] : models_list);
+    hmmh_free_list(mpaths, Vj);
+    if (j == 0) {
+      V = Vj;
+      probab = (double *)calloc((size_t)(U > 0 ? U : 1) * V, sizeof(double)); /* probab[i] = 0.0, R-FS:284 */
+      logp = (double *)malloc(sizeof(double) * (size_t)(U > 0 ? U : 1) * V);
+    } else if (Vj != V) {
+      die("model list %s has a different number of words \n", models_list);
+    }
+    if (U == 0) continue;
+    char **paths = NULL;
+    int nf = 0, d = 0, bad = -1;
+    if (hmmh_read_list(feat_list, &paths, &nf) != HMMCU_OK) die("file %s not found \n", feat_list);
+    if (nf < U) die("reading error on file %s \n", feat_list);
     int rc = hmmh_ingest(ctx, (const char *const *)paths, U, 0, off, &d, &bad, NULL);
     if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : feat_list);
-    if (rc == HMMCU_OK && d != D) die("reading error on file %s \n", paths[0]);
-    if (rc != HMMCU_OK || hmmh_upload_models(ctx, models, V) != HMMCU_OK ||
-        hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK || hmmcu_rank(ctx, logp, U, V, weight, label, second) != HMMCU_OK)
+    if (rc == HMMCU_OK && d != models.D) die("reading error on file %s \n", paths[0]);
+    if (rc != HMMCU_OK || hmmh_upload_model_set(ctx, &models) != HMMCU_OK || hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK)
       die("GPU error: %s \n", hmmcu_last_error(ctx));
+    for (size_t k = 0; k < (size_t)U * V; k++) probab[k] += weight[j] * logp[k];
+    hmmh_free_list(paths, nf);
+  }
+  if (U > 0) {
+    if (hmmcu_rank(ctx, probab, U, V, 1.0, label, second) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
     hmmcu_destroy(ctx);
   }
   times(&tb);
@@ -154,7 +175,7 @@ int hmmh_test_main(int argc, char **argv) {
       if (strcmp(last, " ") != 0) {
         double cpu_time = batch_cpu * (correct + error) / U;
         sum_cpu += cpu_time;
-        write_word_block(correct, error, nsecond, V, last, wrong, models, cpu_time, word_frames);
+        write_word_block(correct, error, nsecond, V, last, wrong, &models, cpu_time, word_frames);
         sum_correct += correct; sum_error += error; sum_second += nsecond; total_frames += word_frames;
         word_frames = correct = error = nsecond = 0;
         for (int i = 0; i < V; i++) wrong[i] = 0;
@@ -162,12 +183,12 @@ int hmmh_test_main(int argc, char **argv) {
       fprintf(g_out, "\nSpoken word: %s\n", spoken[u]);
     }
     word_frames += (int)(off[u + 1] - off[u]);
-    printf("\r\nSpoken word: %s -> %s : %f\r\n", spoken[u], models[label[u]].word, weight * logp[(size_t)u * V + label[u]]);
-    if (strncmp(spoken[u], models[label[u]].word, WSTR) == 0) correct++;
+    printf("\r\nSpoken word: %s -> %s : %f\r\n", spoken[u], models.word[label[u]], probab[(size_t)u * V + label[u]]);
+    if (strncmp(spoken[u], models.word[label[u]], WSTR) == 0) correct++;
     else {
       error++;
       wrong[label[u]]++;
-      if (V > 1 && strncmp(spoken[u], models[second[u]].word, WSTR) == 0) nsecond++;
+      if (V > 1 && strncmp(spoken[u], models.word[second[u]], WSTR) == 0) nsecond++;
     }
     strncpy(last, spoken[u], WSTR);
   }
@@ -175,7 +196,7 @@ int hmmh_test_main(int argc, char **argv) {
   if (U > 0) {
     double cpu_time = batch_cpu * (correct + error) / U;
     sum_cpu += cpu_time;
-    write_word_block(correct, error, nsecond, K /* sic, R-FS:400 */, last, wrong, models, cpu_time, word_frames);
+    write_word_block(correct, error, nsecond, K /* sic, R-FS:400 */, last, wrong, &models, cpu_time, word_frames);
     sum_correct += correct; sum_error += error; sum_second += nsecond; total_frames += word_frames;
     /* writing_total_result R-FS:1170-1194 */
     int sum = sum_correct + sum_error;
@@ -190,9 +211,7 @@ int hmmh_test_main(int argc, char **argv) {
     fprintf(g_out, "Average word length: %d frames \n", total_frames / sum);
   }
   fclose(g_out);
-  for (int v = 0; v < V; v++) hmmh_model_free(&models[v]);
-  for (int u = 0; u < U; u++) free(paths[u]);
-  free(paths);
-  free(models); free(off); free(spoken); free(logp); free(label); free(second); free(wrong);
+  hmmh_model_set_free(&models);
+  free(off); free(spoken); free(logp); free(probab); free(label); free(second); free(wrong);
   return 0;
 }

@@ -4,6 +4,7 @@ bit-exact; log-likelihoods and re-estimated parameters within 1e-4 relative."""
 import glob
 import json
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -329,6 +330,48 @@ def test_cli_train_then_test_matches_reference_outputs(golden_dir, tmp_path):
         r.run_test_cli("d39m16", str(tmp_path / "models.txt"), str(tmp_path / "feat.txt"), str(tmp_path / "words.txt"), ref_res)
         strip = lambda t: [l for l in t.splitlines() if not l.startswith(("Date and time", "Average recognition time"))]
         assert strip(txt) == strip(open(ref_res).read())
+
+
+def test_cli_two_model_sets_weighted_sum(tmp_path):
+    """recognition_continuous_fs with models_number = 2 (R-FS:326-364): two model sets of different topology and
+    feature width, each with its own feature list; the score of a word is sum_j coef_j * logP_j and the label its
+    argmax.  Expected values from the oracle's forward scorer on every (utterance, word, set)."""
+    V, labels = 4, [0, 1, 2, 3, 2, 0]
+    sets = []
+    for j, (N, M, D) in enumerate(((5, 3, 39), (3, 2, 13))):
+        cen, sc = synth.make_centres(V, N, M, D, seed=21 + j)
+        ms = api.ModelSet.from_dict(synth.make_models(cen, sc), ["word%d" % v for v in range(V)])
+        x, off = synth.make_utterances(cen, sc, labels, seed=31 + j, tmin=40, tmax=70)
+        mp = [str(tmp_path / ("s%dw%d.hmm" % (j, v))) for v in range(V)]
+        api.write_model_set(mp, ms)
+        fp = []
+        for u in range(len(labels)):
+            fp.append(str(tmp_path / ("s%du%d.bin" % (j, u))))
+            api.write_features(fp[-1], x[off[u]:off[u + 1]])
+        open(str(tmp_path / ("models%d.txt" % j)), "w").write("\n".join(mp) + "\n")
+        open(str(tmp_path / ("feat%d.txt" % j)), "w").write("\n".join(fp) + "\n")
+        sets.append((ms, x, off))
+    open(str(tmp_path / "words.txt"), "w").write("\n".join("word%d" % v for v in labels) + "\n")
+    coef = (0.75, 0.25)
+    want = np.zeros((len(labels), V))
+    for j, (ms, x, off) in enumerate(sets):
+        for u in range(len(labels)):
+            for v in range(V):
+                mo = o.Model(ms.A[v], ms.c[v], ms.mu[v], ms.iv[v], ms.det[v])
+                want[u, v] += coef[j] * o.forward_score(mo, x[off[u]:off[u + 1]])
+    res = str(tmp_path / "res.txt")
+    bindir = os.path.join(os.path.dirname(api.LIB_PATH), "bin")
+    out = subprocess.run([os.path.join(bindir, "recognition_continuous_fs"), "2", str(tmp_path / "models0.txt"), str(tmp_path / "models1.txt"),
+                          str(coef[0]), str(coef[1]), str(tmp_path / "feat0.txt"), str(tmp_path / "feat1.txt"), str(tmp_path / "words.txt"), res],
+                         check=True, stdout=subprocess.PIPE).stdout.decode()
+    got = re.findall(r"Spoken word: (\S+) -> (\S+) : (\S+)", out)
+    assert len(got) == len(labels)
+    for u, (spoken, rec, score) in enumerate(got):
+        assert spoken == "word%d" % labels[u] and rec == "word%d" % int(np.argmax(want[u]))
+        assert abs(float(score) - want[u].max()) <= RTOL * abs(want[u].max())
+    txt = open(res).read()
+    assert "Number of models: 2" in txt and "Model name 2: %s" % (tmp_path / "models1.txt") in txt
+    assert "Correct words: %d\nErrors: 0" % len(labels) in txt.split("Considering all the words:")[1]
 
 
 # ------------------------------------------------- full-size, size-independent properties ----

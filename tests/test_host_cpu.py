@@ -191,3 +191,73 @@ def test_read_list_tokens(tmp_path):
     assert toks == ["a.bin", "b.bin", "c.bin", "x" * 99, "x" * 21]
     lib.hmmh_free_list.argtypes = [C.POINTER(C.c_char_p), C.c_int]
     lib.hmmh_free_list(pp, n.value)
+
+
+# ---- bulk .hmm I/O ----
+def _random_set(V, N, M, D, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.random((V, N, N))
+    return api.ModelSet(A, rng.random((V, N, M)), rng.standard_normal((V, N, M, D)), rng.random((V, N, M, D)) + 0.1,
+                        rng.random((V, N, M)) + 1e-3, ["w%03d_%s" % (v, "x" * (v % 40)) for v in range(V)])
+
+
+@pytest.mark.parametrize("threads", [1, 7])
+def test_model_set_bulk_io_is_byte_identical_to_the_single_file_path(tmp_path, threads):
+    V, N, M, D = 37, 5, 3, 39
+    ms = _random_set(V, N, M, D, 77)
+    one = [str(tmp_path / ("one%03d.hmm" % v)) for v in range(V)]
+    bulk = [str(tmp_path / ("bulk%03d.hmm" % v)) for v in range(V)]
+    for v in range(V):
+        api.write_model(one[v], ms, v)
+    api.write_model_set(bulk, ms, threads=threads)
+    for a, b in zip(one, bulk):
+        assert open(a, "rb").read() == open(b, "rb").read()
+    back = api.read_model_set(one, threads=threads)
+    assert back.words == ms.words
+    for k in ("A", "c", "mu", "iv", "det"):
+        assert np.array_equal(getattr(back, k), getattr(ms, k)), k
+    single = api.read_model(one[5])
+    assert np.array_equal(single.mu[0], back.mu[5]) and single.words[0] == back.words[5]
+
+
+def test_model_set_reader_takes_32_bit_headers_and_reports_bad_files(tmp_path):
+    ms = _random_set(4, 3, 2, 5, 3)
+    paths = [str(tmp_path / ("m%d.hmm" % v)) for v in range(4)]
+    api.write_model_set(paths, ms)
+    raw = open(paths[2], "rb").read()                         # the shipped fixtures carry a 4-byte length
+    open(paths[2], "wb").write(raw[:4] + raw[8:])
+    back = api.read_model_set(paths)
+    assert np.array_equal(back.mu, ms.mu) and back.words == ms.words
+    open(paths[3], "wb").write(open(paths[3], "rb").read()[:-8])   # truncated
+    with pytest.raises(api.HmmCudaError, match=r"\(5\) at file 3"):
+        api.read_model_set(paths)
+    other = str(tmp_path / "other.hmm")
+    api.write_model_set([other], _random_set(1, 3, 4, 5, 1))        # another mixture count
+    with pytest.raises(api.HmmCudaError, match=r"\(1\) at file 1"):
+        api.read_model_set([paths[0], other, paths[1]])
+    with pytest.raises(api.HmmCudaError, match="at file 0"):
+        api.read_model_set([str(tmp_path / "missing.hmm")])
+
+
+def test_model_set_reader_reads_reference_written_files(tmp_path):
+    """Models written by the compiled reference trainer come back identical through the bulk reader."""
+    if not r.available("d39m16"):
+        pytest.skip("compiled reference not present")
+    paths = []
+    for w in range(2):
+        x, off = _case(3, 78 + w)
+        files = []
+        for u in range(len(off) - 1):
+            f = str(tmp_path / ("w%du%d.bin" % (w, u)))
+            api.write_features(f, x[off[u]:off[u + 1]])
+            files.append(f)
+        lst = str(tmp_path / ("l%d.txt" % w))
+        open(lst, "w").write("\n".join(files) + "\n")
+        paths.append(str(tmp_path / ("m%d.hmm" % w)))
+        r.run_train_cli("d39m16", "word%d" % w, 5, 3, lst, paths[-1])
+    back = api.read_model_set(paths)
+    assert back.words == ["word0", "word1"]
+    for w in range(2):
+        b = r.read_model(paths[w])
+        for name, arr in (("A", back.A), ("c", back.c), ("mu", back.mu), ("iv", back.iv), ("det", back.det)):
+            assert (arr[w] == getattr(b, name)).all()
