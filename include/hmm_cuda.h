@@ -90,6 +90,19 @@ void *hmmcu_staging(hmmcu_ctx *ctx, int slot, uint64_t bytes);
 int hmmcu_set_models(hmmcu_ctx *ctx, int V, int N, int M, int D, const double *A, const double *c,
                      const double *mu, const double *inv_var, const double *det);
 
+/* Multi-stream models (param_number > 1): the emission probability of a state is the PRODUCT over the feature streams
+ * of the stream's mixture density (calc_alpha / calc_beta / calc_transition_probab, T-FS:1406-1409, 1500-1503,
+ * 1606-1609; recogniser R-FS:341-364), every stream with its own coefficient count, mixture count and feature files.
+ * Here every stream is a context of its own (hmmcu_set_features / hmmcu_set_models with the stream's D and M, the
+ * same A, the same utterance lengths, the same device).  After hmmcu_link_streams(primary, others, n):
+ *   hmmcu_estep(primary)  computes every stream's log-emissions, adds them, runs ONE forward-backward pass, and
+ *     accumulates every stream's mixture statistics with the joint state posteriors; the transition statistics,
+ *     den_mix, sum_logP and n_utt are copied into the linked contexts' statistics, so hmmcu_mstep (and
+ *     hmmcu_stats_device / _download) on EACH context gives that stream's update (T-FS:328-346);
+ *   hmmcu_forward_scores / hmmcu_viterbi_scores / hmmcu_viterbi (primary) score the product model.
+ * Linked contexts run on the primary's stream; n = 0 unlinks; hmmcu_destroy unlinks. */
+int hmmcu_link_streams(hmmcu_ctx *primary, hmmcu_ctx *const *others, int n);
+
 /* creating_initial_model (T-FS:732-1317) on the device for V words at once, from the context's features:
  * utterance u belongs to word utt2model[u] (-1 = not used).  Uniform left-to-right A, uniform segmentation,
  * LBG splitting (x1.005 / x0.995) with three k-means passes per level and the empty-cell rule, per-cluster

@@ -51,4 +51,6 @@ build_variant() {  # tag coef mix params words number_words
 build_variant stock   9   3 1   50 13
 build_variant d39m16  39  16 1 1000 10
 build_variant d39m128 39 128 1 2000 10
+# two feature streams (param_number = 2) at the stock sizes: pins the multi-stream restatement (tests/golden/synth_p2.npz)
+build_variant p2      9   3 2   50 2
 echo "build_ref: built $(ls "$OUT" | wc -l) files in $OUT"

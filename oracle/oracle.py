@@ -173,3 +173,77 @@ def viterbi(m, b):
     with np.errstate(divide="ignore"):
         s = lib().orc_viterbi(m.N, T, _d(m.A), _d(b), path.ctypes.data_as(_ip))
     return s, path
+
+
+# ---- multi-stream models (param_number > 1) ---------------------------------------------------
+# The reference multiplies the per-stream mixture densities inside calc_alpha / calc_beta /
+# calc_transition_probab (T-FS:1406-1409, 1427-1431, 1500-1503, 1606-1609) and keeps one set of mixture
+# accumulators per stream (T-FS:303-318); the recogniser does the same product (R-FS:341-364, 762-791).
+# Restated here on top of the single-stream primitives above (which are pinned against the compiled
+# reference): the product of the streams' b is handed to orc_forward / orc_backward, the accumulators
+# follow calc_transition_probab / calc_den_mix_coef / calc_mix_param (T-FS:1577-1727) in numpy.
+# Pinned against the reference's own trainer and recogniser run with two streams: tests/golden/synth_p2.npz.
+def estep_streams(models, xs, off, delta=1):
+    """models[p], xs[p] = model / features of stream p (same A, same utterance lengths).
+    -> ([Stats per stream] (transition statistics identical in all), logp per utterance)."""
+    P = len(models)
+    m0 = models[0]
+    N = m0.N
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    U = len(off) - 1
+    sts = [Stats(m.N, m.M, m.D) for m in models]
+    lpu = np.zeros(U)
+    for u in range(U):
+        sl = slice(int(off[u]), int(off[u + 1]))
+        bp = [emissions(models[p], xs[p][sl]) for p in range(P)]
+        b = bp[0][0].copy()
+        for p in range(1, P):
+            b = b * bp[p][0]                                  # product *= symbol_probab[j][i][k], stream order
+        alpha, scale = forward(m0, b)
+        beta = backward(m0, b, scale)
+        lpu[u] = logprob(alpha, scale)
+        T = b.shape[0]
+        num = np.zeros((N, N)); den = np.zeros(N)
+        for i in range(N):                                    # calc_transition_probab, T-FS:1577-1620
+            for j in range(i, min(N, i + delta + 1)):
+                num[i, j] = np.sum(alpha[:T - 1, i] * m0.A[i, j] * b[1:, j] * beta[1:, j])
+            den[i] = np.sum(alpha[:T - 1, i] * beta[:T - 1, i] / scale[:T - 1])
+        gamma = alpha * beta / scale[:, None]                 # calc_den_mix_coef / calc_mix_param
+        for p in range(P):
+            st, m, x = sts[p], models[p], _f64(xs[p])[sl]
+            st.num_trans += num; st.den_trans += den; st.den_mix += gamma.sum(0)
+            w = gamma[:, :, None] * bp[p][1]                  # [T][N][M]
+            st.S0 += w.sum(0)
+            st.S1 += np.einsum("tnm,td->nmd", w, x)
+            dev = x[:, None, None, :] - m.mu[None]
+            st.S2c += np.einsum("tnm,tnmd->nmd", w, dev * dev)
+            st.sum_logp += lpu[u]; st.n_utt += 1
+    return sts, lpu
+
+
+def train_streams(models, xs, off, max_iter=0, threshold=1e-3):
+    """EM loop of T-FS:238-361 for one word with several streams, in place.  -> (iterations, mean logP)."""
+    old, it = 1.0, 0
+    while True:
+        it += 1
+        sts, lpu = estep_streams(models, xs, off)
+        probab = float(np.sum(lpu))
+        var = abs((old - probab) / old)
+        if not var > threshold or (max_iter and it >= max_iter):
+            return it, probab / len(lpu)
+        old = probab
+        A = None
+        for m, st in zip(models, sts):
+            mstep(m, st)
+            A = m.A if A is None else A
+            m.A[...] = A                                      # one transition matrix (identical statistics anyway)
+
+
+def forward_score_streams(models, xs):
+    b = None
+    for m, x in zip(models, xs):
+        bp = emissions(m, x, want_post=False)[0]
+        b = bp if b is None else b * bp
+    alpha, scale = forward(models[0], b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return logprob(alpha, scale)

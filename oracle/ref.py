@@ -252,6 +252,33 @@ def read_model(path, len_bytes=8):
     return Model(A, c, mu, iv, det, word)
 
 
+def read_model_streams(path, len_bytes=8):
+    """.hmm with P >= 1 feature streams -> [Model per stream] (all carrying the same A and word)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    p = 0
+    ln = struct.unpack("<Q" if len_bytes == 8 else "<I", raw[p : p + len_bytes])[0]; p += len_bytes
+    word = raw[p : p + ln].decode(); p += ln
+    N, P = struct.unpack("<ii", raw[p : p + 8]); p += 8
+    Ms = struct.unpack("<%di" % P, raw[p : p + 4 * P]); p += 4 * P
+    Ds = struct.unpack("<%di" % P, raw[p : p + 4 * P]); p += 4 * P
+    def take(n):
+        nonlocal p
+        a = np.frombuffer(raw, dtype="<f8", count=n, offset=p).copy(); p += 8 * n
+        return a
+    A = take(N * N).reshape(N, N)
+    out = []
+    for M, D in zip(Ms, Ds):
+        c = np.zeros((N, M)); mu = np.zeros((N, M, D)); iv = np.zeros((N, M, D)); det = np.zeros((N, M))
+        for i in range(N):
+            c[i] = take(M)
+            for j in range(M):
+                mu[i, j] = take(D); det[i, j] = take(1)[0]; iv[i, j] = take(D)
+        out.append(Model(A, c, mu, iv, det, word))
+    assert p == len(raw), (p, len(raw))
+    return out
+
+
 def write_model(path, m):
     with open(path, "wb") as f:
         w = m.word.encode()

@@ -24,7 +24,7 @@ EXPORTS = [
     "hmmcu_enable_timing", "hmmh_model_alloc", "hmmh_model_free", "hmmh_read_features", "hmmh_write_features",
     "hmmh_read_model", "hmmh_write_model", "hmmh_init_model", "hmmh_mstep", "hmmh_upload_models", "hmmh_train",
     "hmmh_train_main", "hmmh_test_main",
-    "hmmcu_features_begin", "hmmcu_features_append", "hmmcu_features_wait", "hmmcu_features_end", "hmmcu_staging",
+    "hmmcu_features_begin", "hmmcu_features_append", "hmmcu_features_wait", "hmmcu_features_end", "hmmcu_staging", "hmmcu_link_streams",
     "hmmh_model_set_alloc", "hmmh_model_set_free", "hmmh_read_model_set", "hmmh_write_model_set", "hmmh_upload_model_set",
     "hmmh_read_list", "hmmh_free_list", "hmmh_scan_features", "hmmh_ingest_to", "hmmh_ingest",
 ]
@@ -123,6 +123,7 @@ def load():
     lib.hmmh_read_model_set.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_CModelSet), C.POINTER(C.c_int)]
     lib.hmmh_write_model_set.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_CModelSet), C.c_int, C.POINTER(C.c_int)]
     lib.hmmh_upload_model_set.argtypes = [C.c_void_p, C.POINTER(_CModelSet)]
+    lib.hmmcu_link_streams.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
     lib.hmmcu_features_begin.argtypes = [C.c_void_p, _lp, C.c_int, C.c_int]
     lib.hmmcu_features_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int)]
     lib.hmmcu_features_wait.argtypes = [C.c_void_p, C.c_int]
@@ -275,6 +276,12 @@ class Context:
             self._ck(self.lib.hmmcu_features_append(self.h, xc.ctypes.data, int(f0), xc.shape[0], C.byref(t)), "hmmcu_features_append")
             self._ck(self.lib.hmmcu_features_wait(self.h, t.value), "hmmcu_features_wait")
         self._ck(self.lib.hmmcu_features_end(self.h), "hmmcu_features_end")
+
+    def link_streams(self, others):
+        """Make this context the primary of a multi-stream model; `others` = the contexts of the further streams."""
+        arr = (C.c_void_p * max(1, len(others)))(*[c.h for c in others])
+        self._ck(self.lib.hmmcu_link_streams(self.h, arr, len(others)), "hmmcu_link_streams")
+        self._linked = list(others)
 
     def set_models(self, ms):
         self.V, self.N, self.M = ms.V, ms.N, ms.M

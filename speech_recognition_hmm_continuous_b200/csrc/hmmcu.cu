@@ -68,6 +68,12 @@ struct GraphSlot {
 struct hmmcu_ctx {
   int dev = 0;
   cudaStream_t st = nullptr;
+  // multi-stream models (hmmcu_link_streams): the further feature streams of this (primary) context, and on a linked
+  // context its primary.  Linked contexts run on the primary's CUDA stream; st_own is the stream to destroy.
+  cudaStream_t st_own = nullptr;
+  std::vector<hmmcu_ctx *> linked;
+  hmmcu_ctx *primary = nullptr;
+  DevBuf logb_joint;  // sum over the streams of the log-emissions [F][N] (training)
   // feature upload pipeline: chunk copies on their own stream, packed on `st` as they land
   cudaStream_t st_copy = nullptr;
   static constexpr int kUpChunks = 16;
@@ -263,6 +269,7 @@ int hmmcu_create(int device, hmmcu_ctx **out) {
     delete ctx;
     return HMMCU_ECUDA;
   }
+  ctx->st_own = ctx->st;
   bool ok = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_idle, cudaEventDisableTiming) == cudaSuccess &&
             cudaMallocHost((void **)&ctx->ctr_h, sizeof(double) * 256) == cudaSuccess;
@@ -276,10 +283,28 @@ int hmmcu_create(int device, hmmcu_ctx **out) {
   return HMMCU_OK;
 }
 
+static void unlink_streams(hmmcu_ctx *ctx) {
+  if (ctx->primary) {  // a linked context leaves its primary
+    auto &l = ctx->primary->linked;
+    l.erase(std::remove(l.begin(), l.end(), ctx), l.end());
+    cudaStreamSynchronize(ctx->st);
+    ctx->st = ctx->st_own;
+    ctx->primary = nullptr;
+  }
+  for (hmmcu_ctx *q : ctx->linked) {  // a primary releases its streams
+    cudaStreamSynchronize(ctx->st);
+    q->st = q->st_own;
+    q->primary = nullptr;
+  }
+  ctx->linked.clear();
+}
+
 void hmmcu_destroy(hmmcu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->st);
+  unlink_streams(ctx);
+  ctx->logb_joint.release();
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->kc2, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
                     &ctx->post, &ctx->gamma, &ctx->alpha_ws, &ctx->stats, &ctx->logp_utt_d, &ctx->score_d,
@@ -304,7 +329,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   for (void *p : ctx->stage_h)
     if (p) cudaFreeHost(p);
   if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
-  cudaStreamDestroy(ctx->st);
+  cudaStreamDestroy(ctx->st_own);
   delete ctx;
 }
 
@@ -348,6 +373,54 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
   return (int64_t)N * N + 2 * N + (int64_t)N * M + 2 * (int64_t)N * M * D + 2;
+}
+
+// --------------------------------------------------------------------------- feature streams ----
+// Multi-stream models (param_number > 1, T-FS:1406-1409 / R-FS:341-364): b_i(t) is the PRODUCT of the per-stream
+// mixture densities.  Every stream lives in its own context (own features, own mixtures, the same A, the same
+// utterance geometry); linking makes `primary` add the log-emissions of the others before its recursions, and makes
+// the others accumulate their mixture statistics with the primary's state posteriors.  n = 0 unlinks.
+int hmmcu_link_streams(hmmcu_ctx *primary, hmmcu_ctx *const *others, int n) {
+  if (!primary || n < 0 || (n > 0 && !others)) return HMMCU_EINVAL;
+  if (primary->primary) return fail(primary, HMMCU_EINVAL, "link_streams: this context is itself linked to another");
+  hmmcu_ctx *ctx = primary;  // for CK
+  CK(cudaSetDevice(primary->dev));
+  unlink_streams(primary);
+  for (int k = 0; k < n; k++) {
+    hmmcu_ctx *q = others[k];
+    if (!q || q == primary || q->primary || !q->linked.empty() || q->dev != primary->dev) {
+      unlink_streams(primary);
+      return fail(primary, HMMCU_EINVAL, "link_streams: stream %d must be another, unlinked context on the same device", k + 1);
+    }
+    CK(cudaStreamSynchronize(q->st));
+    q->st = primary->st;
+    q->primary = primary;
+    primary->linked.push_back(q);
+  }
+  return HMMCU_OK;
+}
+
+// the linked contexts must describe the same utterances and the same model topology as their primary
+static int check_linked(hmmcu_ctx *ctx) {
+  for (hmmcu_ctx *q : ctx->linked) {
+    if (!q->have_features || !q->have_models) return fail(ctx, HMMCU_EINVAL, "a linked stream has no features or models");
+    if (q->U != ctx->U || q->off != ctx->off) return fail(ctx, HMMCU_EINVAL, "linked streams differ in their utterance lengths");
+    if (q->V != ctx->V || q->N != ctx->N) return fail(ctx, HMMCU_EINVAL, "linked streams differ in words or states (V=%d/%d, N=%d/%d)", ctx->V, q->V, ctx->N, q->N);
+  }
+  return HMMCU_OK;
+}
+
+__global__ void k_add_logb(float *__restrict__ out, const float *__restrict__ a, const float *__restrict__ b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
+// the per-word statistics every stream shares: [num_trans N*N, den_trans N, den_mix N] at the head, [sum_logP, n_utt] at the tail
+__global__ void k_copy_shared_stats(double *__restrict__ dst, int64_t ss_dst, const double *__restrict__ src, int64_t ss_src, int V, int head) {
+  const int v = blockIdx.x;
+  if (v >= V) return;
+  for (int k = threadIdx.x; k < head + 2; k += blockDim.x) {
+    if (k < head) dst[v * ss_dst + k] = src[v * ss_src + k];
+    else dst[v * ss_dst + ss_dst - 2 + (k - head)] = src[v * ss_src + ss_src - 2 + (k - head)];
+  }
 }
 
 // ---------------------------------------------------------------------------------- features ----
@@ -1128,53 +1201,72 @@ template <int NS> struct ScoreLaunch {
   }
 
 // mode 0: forward score, 1: Viterbi score
+// log-emissions of frames [fb0, fb1) against all V models of context c into c->logb ([frames][V*N])
+static int decode_emissions(hmmcu_ctx *ctx, int64_t fb0, int64_t fb1) {
+  const int64_t S = (int64_t)ctx->V * ctx->N;
+  int rc;
+  CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
+  if (tc_supported(ctx) && ws_supported(ctx)) {
+    if ((rc = ensure_ws_images(ctx, 1)) != HMMCU_OK) return rc;
+    const int nfr = (int)(fb1 - fb0), ntl = (nfr + kTcRows - 1) / kTcRows;
+    t_begin(ctx, "emis");
+    rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+    if (rc) return rc;
+    t_end(ctx, "emis");
+  } else if (tc_supported(ctx)) {
+    if ((rc = ensure_tc_images(ctx, 1)) != HMMCU_OK) return rc;
+    std::vector<TcTile> tt;
+    for (int64_t f = fb0; f < fb1; f += kTcRows) tt.push_back({(int32_t)(f - fb0), (int)std::min<int64_t>(kTcRows, fb1 - f), 0, 0, 0, 0});
+    CK(ctx->tc_tiles_dec.ensure(sizeof(TcTile) * tt.size()));
+    CK(cudaMemcpyAsync(ctx->tc_tiles_dec.p, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    t_begin(ctx, "emis");
+    rc = launch_emis_tc<false>(ctx, ctx->tc_tiles_dec.as<TcTile>(), (int)tt.size(), ctx->logb.as<float>(), fb0, S, nullptr);
+    if (rc) return rc;
+    t_end(ctx, "emis");
+  } else {
+    std::vector<EmisTile> tiles;
+    for (int64_t f = fb0; f < fb1; f += kEmisTF)
+      for (int v = 0; v < ctx->V; v++) tiles.push_back({f, (int)std::min<int64_t>(kEmisTF, fb1 - f), v});
+    CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
+    CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // `tiles` goes out of scope
+    t_begin(ctx, "emis");
+    rc = launch_emis<false>(ctx, ctx->tiles_dec.as<EmisTile>(), (int64_t)tiles.size(), ctx->logb.as<float>(), fb0, S, 1, nullptr);
+    if (rc) return rc;
+    t_end(ctx, "emis");
+  }
+  return HMMCU_OK;
+}
+
+// mode 0: forward score, 1: Viterbi score
 static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   if (!ctx || !out_host) return HMMCU_EINVAL;
+  if (ctx->primary) return fail(ctx, HMMCU_EINVAL, "scores: this context is a linked stream; call its primary");
   CK(cudaSetDevice(ctx->dev));
   int rc = ensure_packed(ctx);
   if (rc) return rc;
+  if ((rc = check_linked(ctx)) != HMMCU_OK) return rc;
+  for (hmmcu_ctx *q : ctx->linked)
+    if ((rc = ensure_packed(q)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
   if (ctx->U == 0) return HMMCU_OK;
   const int64_t S = (int64_t)ctx->V * ctx->N;
   CK(ctx->score_d.ensure(sizeof(double) * (size_t)ctx->U * ctx->V));
   // utterance batches so that the log-emission buffer stays under ~2 GiB
   const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, (int64_t)(2048ll << 20) / (4 * S));
   int u0 = 0;
-  std::vector<EmisTile> tiles;
   while (u0 < ctx->U) {
     int u1 = u0;
     while (u1 < ctx->U && ctx->off[u1 + 1] - ctx->off[u0] <= budget_frames) u1++;
     if (u1 == u0) u1 = u0 + 1;
     const int64_t fb0 = ctx->off[u0], fb1 = ctx->off[u1];
-    CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
-    if (tc_supported(ctx) && ws_supported(ctx)) {
-      if ((rc = ensure_ws_images(ctx, 1)) != HMMCU_OK) return rc;
-      const int nfr = (int)(fb1 - fb0), ntl = (nfr + kTcRows - 1) / kTcRows;
-      t_begin(ctx, "emis");
-      rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
-      if (rc) return rc;
-      t_end(ctx, "emis");
-    } else if (tc_supported(ctx)) {
-      if ((rc = ensure_tc_images(ctx, 1)) != HMMCU_OK) return rc;
-      std::vector<TcTile> tt;
-      for (int64_t f = fb0; f < fb1; f += kTcRows) tt.push_back({(int32_t)(f - fb0), (int)std::min<int64_t>(kTcRows, fb1 - f), 0, 0, 0, 0});
-      CK(ctx->tc_tiles_dec.ensure(sizeof(TcTile) * tt.size()));
-      CK(cudaMemcpyAsync(ctx->tc_tiles_dec.p, tt.data(), sizeof(TcTile) * tt.size(), cudaMemcpyHostToDevice, ctx->st));
-      CK(cudaStreamSynchronize(ctx->st));
-      t_begin(ctx, "emis");
-      rc = launch_emis_tc<false>(ctx, ctx->tc_tiles_dec.as<TcTile>(), (int)tt.size(), ctx->logb.as<float>(), fb0, S, nullptr);
-      if (rc) return rc;
-      t_end(ctx, "emis");
-    } else {
-      tiles.clear();
-      for (int64_t f = fb0; f < fb1; f += kEmisTF)
-        for (int v = 0; v < ctx->V; v++) tiles.push_back({f, (int)std::min<int64_t>(kEmisTF, fb1 - f), v});
-      CK(ctx->tiles_dec.ensure(sizeof(EmisTile) * tiles.size()));
-      CK(cudaMemcpyAsync(ctx->tiles_dec.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
-      CK(cudaStreamSynchronize(ctx->st));  // `tiles` is reused by the next batch
-      t_begin(ctx, "emis");
-      rc = launch_emis<false>(ctx, ctx->tiles_dec.as<EmisTile>(), (int64_t)tiles.size(), ctx->logb.as<float>(), fb0, S, 1, nullptr);
-      if (rc) return rc;
-      t_end(ctx, "emis");
+    if ((rc = decode_emissions(ctx, fb0, fb1)) != HMMCU_OK) return rc;
+    for (hmmcu_ctx *q : ctx->linked) {  // multi-stream models: the product of the streams' densities (R-FS:341-364)
+      if ((rc = decode_emissions(q, fb0, fb1)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
+      const int64_t n = (fb1 - fb0) * S;
+      k_add_logb<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->logb.as<float>(),
+                                                                                                     q->logb.as<float>(), n);
+      LAUNCH_CHECK();
     }
     t_begin(ctx, mode == 0 ? "score" : "viterbi");
     if (mode == 0) {
@@ -1343,8 +1435,10 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
   return HMMCU_OK;
 }
 
-int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double *logp_utt) {
-  if (!ctx) return HMMCU_EINVAL;
+// phases: 1 = clear the statistics + emissions, 2 = forward-backward, 4 = mixture accumulators.  fb_logb / acc_gamma
+// replace the context's own log-emissions in the recursions / its own state posteriors in the accumulators
+// (multi-stream models); with all phases and no replacement this is the plain single-stream E-step.
+static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, const float *fb_logb, const float *acc_gamma) {
   CK(cudaSetDevice(ctx->dev));
   int rc = ensure_packed(ctx);
   if (rc) return rc;
@@ -1385,18 +1479,23 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
   }
   ctx->train_path = ws_emis ? 2 : use_tc ? 1 : 0;
   // ---- the launch sequence: statistics cleared, emissions, forward-backward, accumulators ----
+  const float *lb_fb = fb_logb ? fb_logb : ctx->logb.as<float>();
+  const float *gm_acc = acc_gamma ? acc_gamma : ctx->gamma.as<float>();
   auto enqueue = [&]() -> int {
-    CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
+    if (phases & 1) CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
     if (U == 0) return HMMCU_OK;
     int rc2;
     // 1. emissions (+ per-mixture posteriors on the CUDA-core path)
+    if (phases & 1) {
     t_begin(ctx, "emis");
     if (ws_emis) rc2 = launch_emis_ws<true>(ctx, ctx->ws_tiles_train.as<TcTile>(), ctx->n_ws_tiles_train, 0, 0, ctx->logb.as<float>(), 0, N);
     else if (use_tc) rc2 = launch_emis_tc<true>(ctx, ctx->tc_tiles_train.as<TcTile>(), (int)ctx->n_tc_tiles_train, ctx->logb.as<float>(), 0, N, nullptr);
     else rc2 = launch_emis<true>(ctx, ctx->tiles_d.as<EmisTile>(), ctx->n_train_tiles, ctx->logb.as<float>(), 0, N, 0, ctx->post.as<float>());
     if (rc2) return rc2;
     t_end(ctx, "emis");
+    }
     // 2. forward / backward, gamma, transition statistics, log-probabilities
+    if (phases & 2) {
     t_begin(ctx, "fwdbwd");
     {
       // many utterances: one thread per chain fills the machine (a k_fb_seg CTA holds four utterances and two fit per SM)
@@ -1404,17 +1503,17 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       if (ctx->use_wide_fb == 2 || (ctx->use_wide_fb == 1 && U >= kWideMinUtts)) {
         const int blocks = (2 * U + kWideThreads - 1) / kWideThreads;
         if (ctx->banded) {
-          DISPATCH_N(N, (k_fb_wide<NS, true><<<blocks, kWideThreads, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
+          DISPATCH_N(N, (k_fb_wide<NS, true><<<blocks, kWideThreads, 0, ctx->st>>>(lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
                                                                                   ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
                                                                                   ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
         } else {
-          DISPATCH_N(N, (k_fb_wide<NS, false><<<blocks, kWideThreads, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
+          DISPATCH_N(N, (k_fb_wide<NS, false><<<blocks, kWideThreads, 0, ctx->st>>>(lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
                                                                                    ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
                                                                                    ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
         }
         LAUNCH_CHECK();
         DISPATCH_N(N, (k_fb_gamma<NS><<<(U + kGammaWarps - 1) / kGammaWarps, kGammaWarps * 32, 0, ctx->st>>>(
-                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(),
+                          lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(),
                           ctx->beta_ws.as<float>(), ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>(), ctx->gamma.as<float>(),
                           ctx->stats.as<double>(), ss, off_lp, ctx->logp_utt_d.as<double>())));
         LAUNCH_CHECK();
@@ -1423,12 +1522,12 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
         const size_t fsm = fb_seg_smem_bytes(N, ctx->Tmax);
         if (ctx->banded) {
           DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, true><<<blocks, kSegThreads, fsm, ctx->st>>>(
-                            ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
+                            lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
                             ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                             ss, off_lp, ctx->logp_utt_d.as<double>())));
         } else {
           DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, false><<<blocks, kSegThreads, fsm, ctx->st>>>(
-                            ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
+                            lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
                             ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                             ss, off_lp, ctx->logp_utt_d.as<double>())));
         }
@@ -1438,12 +1537,12 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       const size_t fsm = fb_smem_bytes(N);
       if (ctx->banded) {
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, true><<<blocks, kFbThreads, fsm, ctx->st>>>(
-                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
+                          lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
                           ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       } else {
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb<NS, false><<<blocks, kFbThreads, fsm, ctx->st>>>(
-                          ctx->logb.as<float>(), ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
+                          lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U,
                           ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
                           ss, off_lp, ctx->logp_utt_d.as<double>())));
       }
@@ -1451,7 +1550,9 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       }
     }
     t_end(ctx, "fwdbwd");
+    }
     // 3. mixture accumulators
+    if (!(phases & 4)) return HMMCU_OK;
     t_begin(ctx, "accum");
     if (ws_acc) {
       const size_t smem = ws_acc_smem_bytes(2 * DP);
@@ -1462,14 +1563,14 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
           CK(cudaFuncSetAttribute(k_accum_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_accum_ws<true><<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
                                                                  ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
-                                                                 ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                                 ctx->logb.as<float>(), gm_acc, N, M, G, D, DP,
                                                                  ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2, ctx->acc_scratch.as<float>(),
                                                                  (long long *)ctx->acc_dbg.p);
         } else {
           CK(cudaFuncSetAttribute(k_accum_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           k_accum_ws<false><<<grid, kAccWsThreads, smem, ctx->st>>>(ctx->acc_units64.as<TcTile>(), (int)ctx->n_acc_units64, ctx->frame_ids_d.as<int32_t>(),
                                                                   ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
-                                                                  ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                                  ctx->logb.as<float>(), gm_acc, N, M, G, D, DP,
                                                                   ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2, ctx->acc_scratch.as<float>(),
                                                                   nullptr);
         }
@@ -1488,7 +1589,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       if (grid > 0) {
         k_accum_tc<<<grid, kTcThreads, smem, ctx->st>>>(ctx->acc_units.as<TcTile>(), (int)ctx->n_acc_units, ctx->frame_ids_d.as<int32_t>(),
                                                         ctx->x32.as<float>(), ctx->acc_images.as<float>(), ctx->acc_kc.as<float>(),
-                                                        ctx->logb.as<float>(), ctx->gamma.as<float>(), N, M, G, D, DP,
+                                                        ctx->logb.as<float>(), gm_acc, N, M, G, D, DP,
                                                         ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2,
                                                         (ctx->debug_acc & 1) ? ctx->acc_dbg.as<float>() : nullptr);
         LAUNCH_CHECK();
@@ -1504,7 +1605,7 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
       nparts = std::min(nparts, std::max(1, ctx->max_utts_per_model));
       const size_t smem = sizeof(float) * (size_t)kAccTF * (DP + GCH);
       dim3 grid(nparts, V, nz);
-      k_accum_simt<<<grid, kAccThreads, smem, ctx->st>>>(ctx->x32.as<float>(), ctx->gamma.as<float>(), ctx->post.as<float>(),
+      k_accum_simt<<<grid, kAccThreads, smem, ctx->st>>>(ctx->x32.as<float>(), gm_acc, ctx->post.as<float>(),
                                                          ctx->mu32.as<float>(), ctx->off_d.as<int64_t>(),
                                                          ctx->mus_d.as<int32_t>(), ctx->mu_d.as<int32_t>(), N, M, D, DP, nparts,
                                                          ctx->stats.as<double>(), ss, off_S0, off_S1, off_S2);
@@ -1519,7 +1620,42 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
   };
   const uint64_t key = 1u | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 7) << 5);
   ctx->last_tc = use_tc;
-  if ((rc = run_graphed(ctx, ctx->g_estep, key, enqueue)) != HMMCU_OK) return rc;
+  if (phases != 7 || fb_logb || acc_gamma) return enqueue();  // pieces of a multi-stream E-step: plain launches
+  return run_graphed(ctx, ctx->g_estep, key, enqueue);
+}
+
+int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double *logp_utt) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (ctx->primary) return fail(ctx, HMMCU_EINVAL, "estep: this context is a linked stream; call its primary");
+  int rc;
+  const int U = ctx->U;
+  if (ctx->linked.empty()) {
+    if ((rc = estep_core(ctx, utt2model, 7, nullptr, nullptr)) != HMMCU_OK) return rc;
+  } else {
+    // multi-stream: per-stream emissions, their sum, ONE pair of recursions, per-stream accumulators
+    if ((rc = check_linked(ctx)) != HMMCU_OK) return rc;
+    if ((rc = estep_core(ctx, utt2model, 1, nullptr, nullptr)) != HMMCU_OK) return rc;
+    for (hmmcu_ctx *q : ctx->linked)
+      if ((rc = estep_core(q, utt2model, 1, nullptr, nullptr)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
+    const int64_t n = ctx->F * ctx->N;
+    if (U > 0 && n > 0) {
+      CK(ctx->logb_joint.ensure(sizeof(float) * n));
+      const float *acc = ctx->logb.as<float>();
+      const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+      for (hmmcu_ctx *q : ctx->linked) {
+        k_add_logb<<<blocks, 256, 0, ctx->st>>>(ctx->logb_joint.as<float>(), acc, q->logb.as<float>(), n);
+        LAUNCH_CHECK();
+        acc = ctx->logb_joint.as<float>();
+      }
+    }
+    if ((rc = estep_core(ctx, utt2model, 6, ctx->logb_joint.as<float>(), nullptr)) != HMMCU_OK) return rc;
+    for (hmmcu_ctx *q : ctx->linked) {
+      if ((rc = estep_core(q, utt2model, 4, nullptr, ctx->gamma.as<float>())) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
+      k_copy_shared_stats<<<ctx->V, 64, 0, ctx->st>>>(q->stats.as<double>(), q->stats_n / q->V, ctx->stats.as<double>(), ctx->stats_n / ctx->V, ctx->V,
+                                                      ctx->N * ctx->N + 2 * ctx->N);
+      LAUNCH_CHECK();
+    }
+  }
   if (logp_utt && U > 0) CK(cudaMemcpyAsync(logp_utt, ctx->logp_utt_d.p, sizeof(double) * U, cudaMemcpyDeviceToHost, ctx->st));
   if (stats) CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
   if (stats || logp_utt) CK(cudaStreamSynchronize(ctx->st));
@@ -1640,15 +1776,13 @@ int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats) {
 }
 
 // ----------------------------------------------------------------------------------- Viterbi ----
-int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32_t *path) {
-  if (!ctx) return HMMCU_EINVAL;
-  CK(cudaSetDevice(ctx->dev));
-  if (!ctx->have_features || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "features and models must both be set first");
-  if (ctx->U == 0) return HMMCU_OK;
-  if (!utt2model || !score) return fail(ctx, HMMCU_EINVAL, "viterbi: bad arguments");
+__global__ void k_add_f64(double *__restrict__ acc, const double *__restrict__ b, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[i] += b[i];
+}
+
+// double-precision log-emissions of every utterance against its own model into ctx->logb64 ([F][N])
+static int viterbi_logb64(hmmcu_ctx *ctx, const int32_t *utt2model) {
   const int U = ctx->U;
-  for (int u = 0; u < U; u++)
-    if (utt2model[u] < 0 || utt2model[u] >= ctx->V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, utt2model[u]);
   if (ctx->Dm != ctx->D) return fail(ctx, HMMCU_EINVAL, "models have D=%d but features have D=%d", ctx->Dm, ctx->D);
   const size_t lsm = logb64_smem_bytes(ctx->M, ctx->D);
   if (lsm > 227 * 1024) return fail(ctx, HMMCU_EINVAL, "M=%d mixtures x D=%d does not fit the double-precision emission kernel", ctx->M, ctx->D);
@@ -1670,9 +1804,6 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
     ctx->vit_epoch = ctx->feat_epoch;
   }
   CK(ctx->logb64.ensure(sizeof(double) * (size_t)ctx->F * ctx->N));
-  CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
-  CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
-  CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
   t_begin(ctx, "logb64");
   if (ctx->D == 39) {  // the MFCC + delta + delta-delta layout every config uses
     CK(cudaFuncSetAttribute(k_logb64<39>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
@@ -1687,6 +1818,31 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
   }
   LAUNCH_CHECK();
   t_end(ctx, "logb64");
+  return HMMCU_OK;
+}
+
+int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32_t *path) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (ctx->primary) return fail(ctx, HMMCU_EINVAL, "viterbi: this context is a linked stream; call its primary");
+  CK(cudaSetDevice(ctx->dev));
+  if (!ctx->have_features || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "features and models must both be set first");
+  if (ctx->U == 0) return HMMCU_OK;
+  if (!utt2model || !score) return fail(ctx, HMMCU_EINVAL, "viterbi: bad arguments");
+  const int U = ctx->U;
+  for (int u = 0; u < U; u++)
+    if (utt2model[u] < 0 || utt2model[u] >= ctx->V) return fail(ctx, HMMCU_EINVAL, "utt2model[%d]=%d out of range", u, utt2model[u]);
+  int rc = check_linked(ctx);
+  if (rc) return rc;
+  if ((rc = viterbi_logb64(ctx, utt2model)) != HMMCU_OK) return rc;
+  for (hmmcu_ctx *q : ctx->linked) {  // multi-stream models: log b = sum over the streams
+    if ((rc = viterbi_logb64(q, utt2model)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
+    const int64_t n = ctx->F * ctx->N;
+    k_add_f64<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->st>>>(ctx->logb64.as<double>(), q->logb64.as<double>(), n);
+    LAUNCH_CHECK();
+  }
+  CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
+  CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
+  CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
   t_begin(ctx, "viterbi");
   DISPATCH_N(ctx->N, CK(ScoreLaunch<NS>::path(ctx, ctx->logb64.as<double>(), ctx->vit_map.as<int32_t>(), ctx->logp_utt_d.as<double>(),
                                                path ? ctx->path_d.as<int32_t>() : nullptr)));

@@ -126,3 +126,45 @@ def test_viterbi_properties():
     b, _ = o.emissions(m1, x[: off[1]], want_post=False)
     sc, path = o.viterbi(m1, b)
     assert abs(sc - o.forward_score(m1, x[: off[1]])) < 1e-9 * abs(sc)
+
+
+# ---- two feature streams (param_number = 2): the reference's own trainer and recogniser ----
+def _p2_word(g, v, train=True):
+    lab = g["train_labels"] if train else g["test_labels"]
+    off = g["off"] if train else g["offt"]
+    us = np.nonzero(lab == v)[0] if train else np.arange(len(lab))
+    xs = []
+    for p in range(2):
+        x = g[("x%d" if train else "xt%d") % p]
+        xs.append(np.concatenate([x[off[u]:off[u + 1]] for u in us]))
+    o2 = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])]).astype(np.int64)
+    return xs, o2
+
+
+def test_two_stream_training_matches_reference(golden_dir):
+    """Multi-stream restatement (oracle.estep_streams / train_streams) against the reference trainer run with
+    param_number = 2: iterations, mean log-probability and every trained parameter of both streams."""
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    N = int(g["N"])
+    for v in range(int(g["V"])):
+        xs, off = _p2_word(g, v)
+        models = [o.init_model(N, int(g["M"][p]), xs[p], off) for p in range(2)]
+        assert np.array_equal(models[0].A, models[1].A)
+        its, mean = o.train_streams(models, xs, off)
+        assert its == g["iterations"][v]
+        assert abs(mean - g["mean_logp"][v]) <= 1e-9 * abs(g["mean_logp"][v]) + 1e-6   # report prints %f
+        for p in range(2):
+            for k in ("A", "c", "mu", "iv", "det"):
+                want = g["trained_s%d_%s" % (p, k)][v]
+                assert np.allclose(getattr(models[p], k), want, rtol=1e-9, atol=1e-12), (v, p, k)
+
+
+def test_two_stream_recognition_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    xs, off = _p2_word(g, 0, train=False)
+    for u in range(len(off) - 1):
+        for v in range(int(g["V"])):
+            ms = [o.Model(*[g["trained_s%d_%s" % (p, k)][v] for k in ("A", "c", "mu", "iv", "det")]) for p in range(2)]
+            s = o.forward_score_streams(ms, [x[off[u]:off[u + 1]] for x in xs])
+            assert abs(s - g["score"][u, v]) <= 1e-6 + 1e-9 * abs(s)                       # printed with %f
+    assert (np.argmax(g["score"], axis=1) == g["test_labels"]).all()
