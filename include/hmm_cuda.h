@@ -235,6 +235,11 @@ int hmmh_ingest(hmmcu_ctx *ctx, const char *const *paths, int U, int nthreads, i
  * 0 = auto-detect on read. */
 int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes);
 int hmmh_write_model(const char *path, const hmmh_model *m);
+/* The same file with P >= 1 feature streams (param_number, T-FS:2075-2100): stream p comes back as streams[p]
+ * (its own M and D; the shared A and word in each).  HMMCU_EINVAL if the file holds more than max_streams. */
+#define HMMH_MAX_STREAMS 6 /* MAX_PARAMETERS_NUMBER, T-FS:36 */
+int hmmh_read_model_streams(const char *path, hmmh_model *streams, int max_streams, int *P, int len_bytes);
+int hmmh_write_model_streams(const char *path, const hmmh_model *streams, int P);
 
 /* Bulk .hmm I/O: V model files of one topology <-> the struct-of-arrays layout of hmmcu_set_models.
  * Replaces the recogniser's model-list walk (R-FS:214-238) and its one-fread-per-field reading_model (R-FS:612-712):
@@ -276,6 +281,11 @@ typedef int (*hmmh_allreduce_fn)(void *user, double *dev_buf, int64_t n_doubles,
 int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2model, int U,
                double *mean_logp, int *iterations, int max_iter, hmmh_allreduce_fn allreduce,
                void *user);
+
+/* The same loop for models of P feature streams: ctxs[p] holds the features of stream p, models[p * V + v] is stream p
+ * of word v; ctxs[1..P-1] are linked to ctxs[0] for the duration of the call (hmmcu_link_streams). */
+int hmmh_train_streams(hmmcu_ctx *const *ctxs, int P, hmmh_model *models, int V, const int32_t *utt2model, int U,
+                       double *mean_logp, int *iterations, int max_iter, hmmh_allreduce_fn allreduce, void *user);
 
 /* Drop-in programs: same argv, files and exit codes as the reference's main()s
  * (T-FS:101-391 and R-FS:87-428). */

@@ -70,7 +70,10 @@ int hmmh_write_features(const char *path, const double *x, int T, int D) {
  * mixture mean[D], det, inv_var[D]   (writer T-FS:2058-2144, reader T-FS:612-712 / R-FS:612-712). */
 static int rd(FILE *f, void *p, size_t n) { return fread(p, 1, n, f) == n; }
 
-int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes) {
+/* P >= 1 feature streams in one file: N, P, M[P], D[P], A, then stream by stream the states' mixtures.  Stream p comes
+ * back as streams[p] (own M and D, the shared A and word copied into each). */
+int hmmh_read_model_streams(const char *path, hmmh_model *streams, int max_streams, int *P_out, int len_bytes) {
+  if (!path || !streams || max_streams < 1 || !P_out) return HMMCU_EINVAL;
   FILE *f = fopen(path, "rb");
   if (!f) return HMMCU_EIO;
   unsigned char head[8];
@@ -79,52 +82,76 @@ int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes) {
   memcpy(&len8, head, 8); memcpy(&len4, head, 4);
   if (len_bytes == 0) len_bytes = (len8 < 64) ? 8 : 4; /* a 4-byte header followed by text never reads as a small u64 */
   size_t len = len_bytes == 8 ? (size_t)len8 : (size_t)len4;
-  if (len >= sizeof(m->word)) { fclose(f); return HMMCU_EIO; }
-  fseek(f, len_bytes, SEEK_SET);
-  memset(m->word, 0, sizeof(m->word));
-  int N, P, M, D;
-  if (!rd(f, m->word, len) || !rd(f, &N, 4) || !rd(f, &P, 4)) { fclose(f); return HMMCU_EIO; }
-  if (P != 1 || N < 1 || N > HMMCU_MAX_STATES) { fclose(f); return HMMCU_EINVAL; } /* multi-stream is out of scope (SURVEY #16) */
-  if (!rd(f, &M, 4) || !rd(f, &D, 4) || M < 1 || D < 1 || M > 4096 || D > 4096) { fclose(f); return HMMCU_EIO; }
   char word[64];
-  memcpy(word, m->word, sizeof(word));
-  int rc = hmmh_model_alloc(m, N, M, D);
-  if (rc) { fclose(f); return rc; }
-  memcpy(m->word, word, sizeof(word));
-  int ok = rd(f, m->A, sizeof(double) * N * N);
-  for (int i = 0; ok && i < N; i++) {
-    ok = rd(f, m->c + (size_t)i * M, sizeof(double) * M);
-    for (int j = 0; ok && j < M; j++) {
-      size_t k = (size_t)i * M + j;
-      ok = rd(f, m->mu + k * D, sizeof(double) * D) && rd(f, m->det + k, sizeof(double)) &&
-           rd(f, m->inv_var + k * D, sizeof(double) * D);
+  if (len >= sizeof(word)) { fclose(f); return HMMCU_EIO; }
+  fseek(f, len_bytes, SEEK_SET);
+  memset(word, 0, sizeof(word));
+  int N, P, M[HMMH_MAX_STREAMS], D[HMMH_MAX_STREAMS];
+  if (!rd(f, word, len) || !rd(f, &N, 4) || !rd(f, &P, 4)) { fclose(f); return HMMCU_EIO; }
+  if (P < 1 || P > HMMH_MAX_STREAMS || P > max_streams || N < 1 || N > HMMCU_MAX_STATES) { fclose(f); return HMMCU_EINVAL; }
+  if (!rd(f, M, 4 * (size_t)P) || !rd(f, D, 4 * (size_t)P)) { fclose(f); return HMMCU_EIO; }
+  for (int p = 0; p < P; p++)
+    if (M[p] < 1 || D[p] < 1 || M[p] > 4096 || D[p] > 4096) { fclose(f); return HMMCU_EIO; }
+  int rc = HMMCU_OK, got = 0;
+  for (; got < P && rc == HMMCU_OK; got++) {
+    rc = hmmh_model_alloc(&streams[got], N, M[got], D[got]);
+    if (rc == HMMCU_OK) memcpy(streams[got].word, word, sizeof(word));
+  }
+  int ok = rc == HMMCU_OK && rd(f, streams[0].A, sizeof(double) * N * N);
+  for (int p = 0; ok && p < P; p++) {
+    hmmh_model *m = &streams[p];
+    if (p > 0) memcpy(m->A, streams[0].A, sizeof(double) * N * N);
+    for (int i = 0; ok && i < N; i++) {
+      ok = rd(f, m->c + (size_t)i * m->M, sizeof(double) * m->M);
+      for (int j = 0; ok && j < m->M; j++) {
+        size_t k = (size_t)i * m->M + j;
+        ok = rd(f, m->mu + k * m->D, sizeof(double) * m->D) && rd(f, m->det + k, sizeof(double)) &&
+             rd(f, m->inv_var + k * m->D, sizeof(double) * m->D);
+      }
     }
   }
   fclose(f);
-  if (!ok) { hmmh_model_free(m); return HMMCU_EIO; }
+  if (!ok) {
+    for (int p = 0; p < got; p++) hmmh_model_free(&streams[p]);
+    return rc != HMMCU_OK ? rc : HMMCU_EIO;
+  }
+  *P_out = P;
   return HMMCU_OK;
 }
 
-int hmmh_write_model(const char *path, const hmmh_model *m) {
+int hmmh_read_model(const char *path, hmmh_model *m, int len_bytes) {
+  int P = 0;
+  return hmmh_read_model_streams(path, m, 1, &P, len_bytes); /* a multi-stream file gives HMMCU_EINVAL here */
+}
+
+int hmmh_write_model_streams(const char *path, const hmmh_model *streams, int P) {
+  if (!path || !streams || P < 1 || P > HMMH_MAX_STREAMS) return HMMCU_EINVAL;
   FILE *f = fopen(path, "wb");
   if (!f) return HMMCU_EIO;
-  size_t len = strlen(m->word);
-  int P = 1;
-  int ok = fwrite(&len, sizeof(size_t), 1, f) == 1 && fwrite(m->word, 1, len, f) == len &&
-           fwrite(&m->N, sizeof(int), 1, f) == 1 && fwrite(&P, sizeof(int), 1, f) == 1 &&
-           fwrite(&m->M, sizeof(int), 1, f) == 1 && fwrite(&m->D, sizeof(int), 1, f) == 1 &&
-           fwrite(m->A, sizeof(double), (size_t)m->N * m->N, f) == (size_t)m->N * m->N;
-  for (int i = 0; ok && i < m->N; i++) {
-    ok = fwrite(m->c + (size_t)i * m->M, sizeof(double), m->M, f) == (size_t)m->M;
-    for (int j = 0; ok && j < m->M; j++) {
-      size_t k = (size_t)i * m->M + j;
-      ok = fwrite(m->mu + k * m->D, sizeof(double), m->D, f) == (size_t)m->D && fwrite(m->det + k, sizeof(double), 1, f) == 1 &&
-           fwrite(m->inv_var + k * m->D, sizeof(double), m->D, f) == (size_t)m->D;
+  const hmmh_model *m0 = &streams[0];
+  size_t len = strlen(m0->word);
+  int ok = fwrite(&len, sizeof(size_t), 1, f) == 1 && fwrite(m0->word, 1, len, f) == len &&
+           fwrite(&m0->N, sizeof(int), 1, f) == 1 && fwrite(&P, sizeof(int), 1, f) == 1;
+  for (int p = 0; ok && p < P; p++) ok = fwrite(&streams[p].M, sizeof(int), 1, f) == 1;
+  for (int p = 0; ok && p < P; p++) ok = fwrite(&streams[p].D, sizeof(int), 1, f) == 1;
+  ok = ok && fwrite(m0->A, sizeof(double), (size_t)m0->N * m0->N, f) == (size_t)m0->N * m0->N;
+  for (int p = 0; ok && p < P; p++) {
+    const hmmh_model *m = &streams[p];
+    if (m->N != m0->N) ok = 0;
+    for (int i = 0; ok && i < m->N; i++) {
+      ok = fwrite(m->c + (size_t)i * m->M, sizeof(double), m->M, f) == (size_t)m->M;
+      for (int j = 0; ok && j < m->M; j++) {
+        size_t k = (size_t)i * m->M + j;
+        ok = fwrite(m->mu + k * m->D, sizeof(double), m->D, f) == (size_t)m->D && fwrite(m->det + k, sizeof(double), 1, f) == 1 &&
+             fwrite(m->inv_var + k * m->D, sizeof(double), m->D, f) == (size_t)m->D;
+      }
     }
   }
   fclose(f);
   return ok ? HMMCU_OK : HMMCU_EIO;
 }
+
+int hmmh_write_model(const char *path, const hmmh_model *m) { return hmmh_write_model_streams(path, m, 1); }
 
 /* ------------------------------------------------------------------ small helpers ----------- */
 /* changing_zero_coef T-FS:1338-1359 */
@@ -381,22 +408,27 @@ static int upload_models(hmmcu_ctx *ctx, const hmmh_model *models, int V) {
 
 int hmmh_upload_models(hmmcu_ctx *ctx, const hmmh_model *models, int V) { return upload_models(ctx, models, V); }
 
-/* T-FS:238-361 for V words at once.  Every word keeps the reference's own stopping rule; a word
- * that has converged drops out of the following E-steps (its utterances are masked with -1). */
-int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2model, int U, double *mean_logp,
-               int *iterations, int max_iter, hmmh_allreduce_fn allreduce, void *user) {
-  if (!ctx || !models || V < 1 || (U > 0 && !utt2model)) return HMMCU_EINVAL;
-  const int N = models[0].N, M = models[0].M, D = models[0].D;
-  const size_t g = (size_t)N * M;
+/* T-FS:238-361 for V words at once and P feature streams (models[p * V + v] = stream p of word v; ctxs[p] holds
+ * stream p's features; ctxs[1..] are linked to ctxs[0] here).  Every word keeps the reference's own stopping rule; a
+ * word that has converged drops out of the following E-steps (its utterances are masked with -1). */
+int hmmh_train_streams(hmmcu_ctx *const *ctxs, int P, hmmh_model *models, int V, const int32_t *utt2model, int U, double *mean_logp,
+                       int *iterations, int max_iter, hmmh_allreduce_fn allreduce, void *user) {
+  if (!ctxs || P < 1 || P > HMMH_MAX_STREAMS || !models || V < 1 || (U > 0 && !utt2model)) return HMMCU_EINVAL;
+  hmmcu_ctx *ctx = ctxs[0];
   double *probab = (double *)malloc(sizeof(double) * V), *nutt = (double *)malloc(sizeof(double) * V);
-  int32_t *updated = (int32_t *)malloc(sizeof(int32_t) * V);
+  double *probab_q = (double *)malloc(sizeof(double) * V), *nutt_q = (double *)malloc(sizeof(double) * V);
+  int32_t *updated = (int32_t *)malloc(sizeof(int32_t) * V), *updated_q = (int32_t *)malloc(sizeof(int32_t) * V);
   char *active = (char *)malloc(V);
   int32_t *map = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
-  if (!probab || !nutt || !updated || !active || !map) return HMMCU_ENOMEM;
+  if (!probab || !nutt || !probab_q || !nutt_q || !updated || !updated_q || !active || !map) return HMMCU_ENOMEM;
   for (int v = 0; v < V; v++) { active[v] = 1; if (iterations) iterations[v] = 0; if (mean_logp) mean_logp[v] = 0.0; }
-  /* the model set goes up once; the E-step, the all-reduce and the M-step then stay on the device */
-  int rc = upload_models(ctx, models, V);
-  if (rc == HMMCU_OK) rc = hmmcu_em_reset(ctx);
+  /* the model sets go up once; the E-step, the all-reduce and the M-step then stay on the device */
+  int rc = HMMCU_OK;
+  for (int p = 0; p < P && rc == HMMCU_OK; p++) {
+    rc = upload_models(ctxs[p], models + (size_t)p * V, V);
+    if (rc == HMMCU_OK) rc = hmmcu_em_reset(ctxs[p]);
+  }
+  if (rc == HMMCU_OK && P > 1) rc = hmmcu_link_streams(ctx, ctxs + 1, P - 1);
   int n_active = V, it = 0, remap = 1;
   while (rc == HMMCU_OK && n_active > 0 && (max_iter <= 0 || it < max_iter)) {
     it++;
@@ -405,12 +437,15 @@ int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2mod
       remap = 0;
     }
     if ((rc = hmmcu_estep(ctx, map, NULL, NULL)) != HMMCU_OK) break;
-    if (allreduce) {
+    for (int p = 0; allreduce && p < P && rc == HMMCU_OK; p++) {
       int64_t n = 0;
-      double *dev = hmmcu_stats_device(ctx, &n);
-      if ((rc = allreduce(user, dev, n, hmmcu_stream(ctx))) != HMMCU_OK) break;
+      double *dev = hmmcu_stats_device(ctxs[p], &n);
+      rc = allreduce(user, dev, n, hmmcu_stream(ctxs[p]));
     }
+    if (rc != HMMCU_OK) break;
     if ((rc = hmmcu_mstep(ctx, HM_THRESHOLD, probab, nutt, updated)) != HMMCU_OK) break;
+    for (int p = 1; p < P && rc == HMMCU_OK; p++) rc = hmmcu_mstep(ctxs[p], HM_THRESHOLD, probab_q, nutt_q, updated_q);
+    if (rc != HMMCU_OK) break;
     for (int v = 0; v < V; v++) {
       if (!active[v]) continue;
       if (iterations) iterations[v] = it;
@@ -418,22 +453,32 @@ int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2mod
       if (!updated[v]) { active[v] = 0; n_active--; remap = 1; }
     }
   }
-  if (rc == HMMCU_OK) {  /* bring the trained parameters back into the caller's structs */
+  for (int p = 0; p < P && rc == HMMCU_OK; p++) {  /* bring the trained parameters back into the caller's structs */
+    hmmh_model *mp = models + (size_t)p * V;
+    const int N = mp[0].N, M = mp[0].M, D = mp[0].D;
+    const size_t g = (size_t)N * M;
     double *A = (double *)malloc(sizeof(double) * V * N * N), *c = (double *)malloc(sizeof(double) * V * g);
     double *mu = (double *)malloc(sizeof(double) * V * g * D), *iv = (double *)malloc(sizeof(double) * V * g * D);
     double *det = (double *)malloc(sizeof(double) * V * g);
     if (!A || !c || !mu || !iv || !det) rc = HMMCU_ENOMEM;
-    else if ((rc = hmmcu_get_models(ctx, A, c, mu, iv, det)) == HMMCU_OK) {
+    else if ((rc = hmmcu_get_models(ctxs[p], A, c, mu, iv, det)) == HMMCU_OK) {
       for (int v = 0; v < V; v++) {
-        memcpy(models[v].A, A + (size_t)v * N * N, sizeof(double) * N * N);
-        memcpy(models[v].c, c + v * g, sizeof(double) * g);
-        memcpy(models[v].mu, mu + v * g * D, sizeof(double) * g * D);
-        memcpy(models[v].inv_var, iv + v * g * D, sizeof(double) * g * D);
-        memcpy(models[v].det, det + v * g, sizeof(double) * g);
+        memcpy(mp[v].A, A + (size_t)v * N * N, sizeof(double) * N * N);
+        memcpy(mp[v].c, c + v * g, sizeof(double) * g);
+        memcpy(mp[v].mu, mu + v * g * D, sizeof(double) * g * D);
+        memcpy(mp[v].inv_var, iv + v * g * D, sizeof(double) * g * D);
+        memcpy(mp[v].det, det + v * g, sizeof(double) * g);
       }
     }
     free(A); free(c); free(mu); free(iv); free(det);
   }
-  free(probab); free(nutt); free(updated); free(active); free(map);
+  if (P > 1) hmmcu_link_streams(ctx, NULL, 0);
+  free(probab); free(nutt); free(probab_q); free(nutt_q); free(updated); free(updated_q); free(active); free(map);
   return rc;
+}
+
+int hmmh_train(hmmcu_ctx *ctx, hmmh_model *models, int V, const int32_t *utt2model, int U, double *mean_logp,
+               int *iterations, int max_iter, hmmh_allreduce_fn allreduce, void *user) {
+  if (!ctx) return HMMCU_EINVAL;
+  return hmmh_train_streams(&ctx, 1, models, V, utt2model, U, mean_logp, iterations, max_iter, allreduce, user);
 }

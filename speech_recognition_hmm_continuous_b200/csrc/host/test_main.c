@@ -5,7 +5,8 @@
  * scores are computed on the GPU in one batch; ranking follows sorting_probab including its NaN
  * behaviour.  K model sets per word (weighted sum of their log-probabilities, R-FS:326-364) are taken although the
  * reference is compiled with MAX_MODELS_NUMBER 1 (R-FS:40).  Deliberate limits: the models of one set share one
- * topology; one feature stream per set.
+ * topology; a set whose models carry P feature streams takes P feature lists and is scored through linked contexts
+ * (product of the streams' densities, R-FS:341-364).
  * Reproduced quirks: the weight is printed through an int* with "%.2d" (R-FS:1016,1029); the last
  * per-word block lists wrong words only for the first `models_number` vocabulary entries (R-FS:400).
  */
@@ -30,7 +31,7 @@ static FILE *g_out;
 
 /* writing_result_word R-FS:1110-1150 */
 static void write_word_block(int correct, int error, int second, int nwords, const char *spoken, const int *wrong,
-                             const hmmh_model_set *models, double cpu_time, int frames) {
+                             char (*words)[64], double cpu_time, int frames) {
   int sum = correct + error;
   double per = (double)correct / (double)sum;
   cpu_time /= sum;
@@ -44,7 +45,7 @@ static void write_word_block(int correct, int error, int second, int nwords, con
   if (error != 0) {
     fprintf(g_out, "Wrong words: \n");
     for (int i = 0; i < nwords; i++)
-      if (wrong[i] != 0) fprintf(g_out, "%s: %d time%s\n", models->word[i], wrong[i], wrong[i] == 1 ? "" : "s");
+      if (wrong[i] != 0) fprintf(g_out, "%s: %d time%s\n", words[i], wrong[i], wrong[i] == 1 ? "" : "s");
   }
   fprintf(g_out, "Average recognition time: %.2f sec. \n", cpu_time);
   fprintf(g_out, "Average word length: %d frames \n", frames);
@@ -71,7 +72,7 @@ int hmmh_test_main(int argc, char **argv) {
   /* K model sets per word, each with its own feature list (one stream each) and weighting coefficient; the
    * score of word k is sum_j coef_j * logP_j(u, k), accumulated in set order from 0.0 (R-FS:284, 326-364) */
   const int K = atoi(argv[1]);
-  if (K < 1 || K > 16 || argc != 3 * K + 4) die("models_number %s does not match the argument list (one feature list per model set) \n", argv[1]);
+  if (K < 1 || K > 16 || argc < 3 * K + 4) die("models_number %s does not match the argument list \n", argv[1]);
   double weight[16];
   for (int j = 0; j < K; j++) weight[j] = atof(argv[K + 2 + j]);
   const char *words_file = argv[argc - 2], *result = argv[argc - 1];
@@ -91,8 +92,10 @@ int hmmh_test_main(int argc, char **argv) {
     FILE *f = fopen(argv[2 + j], "rb");
     if (!f) die("file %s not found \n", argv[2 + j]);
     fclose(f);
-    f = fopen(argv[2 + 2 * K + j], "r");
-    if (!f) die("file %s not found \n", argv[2 + 2 * K + j]);
+  }
+  for (int a = 2 + 2 * K; a < argc - 2; a++) {
+    FILE *f = fopen(argv[a], "r");
+    if (!f) die("file %s not found \n", argv[a]);
     fclose(f);
   }
   g_out = fopen(result, "w");
@@ -118,25 +121,24 @@ int hmmh_test_main(int argc, char **argv) {
   /* the hot path, per model set: all files of its feature list into HBM (read once; the reference re-reads every
    * test file for each model, R-FS:341-369), the whole model list in one go (modelset.c), every (utterance, model)
    * forward score in one batch; then the ranking rule on the weighted sums */
-  hmmh_model_set models;
-  memset(&models, 0, sizeof(models));
+  char (*words)[64] = NULL; /* the words of the LAST set name the vocabulary (R-FS:231 overwrites word[]) */
   int V = 0;
   double *probab = NULL, *logp = NULL;
-  int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
+  int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t)), *offq = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
   int32_t *label = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1)), *second = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
   hmmcu_ctx *ctx = NULL;
   if (U > 0 && hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+  int fl = 2 + 2 * K; /* argv index of the set's first feature list: a set with P streams takes P lists (R-FS:259-266) */
   for (int j = 0; j < K; j++) {
-    const char *models_list = argv[2 + j], *feat_list = argv[2 + 2 * K + j];
+    const char *models_list = argv[2 + j];
     char **mpaths = NULL;
-    int Vj = 0, badm = -1;
+    int Vj = 0, badm = -1, Pj = 0;
     printf("\r\nLoading Models\r\n");
     if (hmmh_read_list(models_list, &mpaths, &Vj) != HMMCU_OK || Vj == 0) die("file %s not found \n", models_list);
-    hmmh_model_set_free(&models); /* the words of the LAST set name the vocabulary (R-FS:231 overwrites word[]) */
-    int mrc = hmmh_read_model_set((const char *const *)mpaths, Vj, 0, &models, &badm);
-    if (mrc == HMMCU_EINVAL) die("model %s has a different topology: not supported \n", badm >= 0 ? mpaths[badm] : models_list);
-    if (mrc != HMMCU_OK) die("file %s not found \n", badm >= 0 ? mpaths[badm] : models_list);
-    hmmh_free_list(mpaths, Vj);
+    hmmh_model probe[HMMH_MAX_STREAMS];
+    memset(probe, 0, sizeof(probe));
+    if (hmmh_read_model_streams(mpaths[0], probe, HMMH_MAX_STREAMS, &Pj, 0) != HMMCU_OK) die("file %s not found \n", mpaths[0]);
+    if (fl + Pj > argc - 2) die("the argument list is too short for the feature streams of %s \n", models_list);
     if (j == 0) {
       V = Vj;
       probab = (double *)calloc((size_t)(U > 0 ? U : 1) * V, sizeof(double)); /* probab[i] = 0.0, R-FS:284 */
@@ -144,19 +146,65 @@ int hmmh_test_main(int argc, char **argv) {
     } else if (Vj != V) {
       die("model list %s has a different number of words \n", models_list);
     }
-    if (U == 0) continue;
-    char **paths = NULL;
-    int nf = 0, d = 0, bad = -1;
-    if (hmmh_read_list(feat_list, &paths, &nf) != HMMCU_OK) die("file %s not found \n", feat_list);
-    if (nf < U) die("reading error on file %s \n", feat_list);
-    int rc = hmmh_ingest(ctx, (const char *const *)paths, U, 0, off, &d, &bad, NULL);
-    if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : feat_list);
-    if (rc == HMMCU_OK && d != models.D) die("reading error on file %s \n", paths[0]);
-    if (rc != HMMCU_OK || hmmh_upload_model_set(ctx, &models) != HMMCU_OK || hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK)
-      die("GPU error: %s \n", hmmcu_last_error(ctx));
-    for (size_t k = 0; k < (size_t)U * V; k++) probab[k] += weight[j] * logp[k];
-    hmmh_free_list(paths, nf);
+    words = (char (*)[64])realloc(words, (size_t)V * 64);
+    hmmh_model_set models;
+    memset(&models, 0, sizeof(models));
+    hmmh_model *sm = NULL; /* [Pj][V] when the set has several streams */
+    if (Pj == 1) { /* the whole model list in one go, parsed into the layout hmmcu_set_models takes (modelset.c) */
+      int mrc = hmmh_read_model_set((const char *const *)mpaths, V, 0, &models, &badm);
+      if (mrc == HMMCU_EINVAL) die("model %s has a different topology: not supported \n", badm >= 0 ? mpaths[badm] : models_list);
+      if (mrc != HMMCU_OK) die("file %s not found \n", badm >= 0 ? mpaths[badm] : models_list);
+      memcpy(words, models.word, (size_t)V * 64);
+    } else {
+      sm = (hmmh_model *)calloc((size_t)Pj * V, sizeof(hmmh_model));
+      for (int v = 0; v < V; v++) {
+        hmmh_model tmp[HMMH_MAX_STREAMS];
+        int Pv = 0;
+        memset(tmp, 0, sizeof(tmp));
+        if (hmmh_read_model_streams(mpaths[v], tmp, HMMH_MAX_STREAMS, &Pv, 0) != HMMCU_OK) die("file %s not found \n", mpaths[v]);
+        if (Pv != Pj) die("model %s has a different topology: not supported \n", mpaths[v]);
+        for (int p = 0; p < Pj; p++) {
+          if (tmp[p].N != probe[p].N || tmp[p].M != probe[p].M || tmp[p].D != probe[p].D) die("model %s has a different topology: not supported \n", mpaths[v]);
+          sm[(size_t)p * V + v] = tmp[p];
+        }
+        memcpy(words[v], tmp[0].word, 64);
+      }
+    }
+    hmmh_free_list(mpaths, Vj);
+    if (U > 0) {
+      hmmcu_ctx *cx[HMMH_MAX_STREAMS];
+      cx[0] = ctx;
+      for (int p = 0; p < Pj; p++) { /* every stream's feature list into its own context (read once, ingest.c) */
+        const char *feat_list = argv[fl + p];
+        char **paths = NULL;
+        int nf = 0, d = 0, bad = -1;
+        if (p > 0 && hmmcu_create(0, &cx[p]) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+        if (hmmh_read_list(feat_list, &paths, &nf) != HMMCU_OK) die("file %s not found \n", feat_list);
+        if (nf < U) die("reading error on file %s \n", feat_list);
+        int rc = hmmh_ingest(cx[p], (const char *const *)paths, U, 0, p == 0 ? off : offq, &d, &bad, NULL);
+        if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : feat_list);
+        if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(cx[p]));
+        if (d != probe[p].D) die("reading error on file %s \n", paths[0]);
+        if (p > 0 && memcmp(off, offq, sizeof(int64_t) * ((size_t)U + 1)) != 0) die("reading error on file %s (the streams of an utterance differ in length) \n", feat_list);
+        rc = Pj == 1 ? hmmh_upload_model_set(cx[p], &models) : hmmh_upload_models(cx[p], sm + (size_t)p * V, V);
+        if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(cx[p]));
+        hmmh_free_list(paths, nf);
+      }
+      /* every (utterance, model) forward score in one batch; several streams: the product of their densities */
+      if ((Pj > 1 && hmmcu_link_streams(ctx, cx + 1, Pj - 1) != HMMCU_OK) || hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK)
+        die("GPU error: %s \n", hmmcu_last_error(ctx));
+      for (int p = 1; p < Pj; p++) hmmcu_destroy(cx[p]); /* unlinks */
+      for (size_t k = 0; k < (size_t)U * V; k++) probab[k] += weight[j] * logp[k];
+    }
+    for (int p = 0; p < Pj; p++) hmmh_model_free(&probe[p]);
+    if (sm) {
+      for (size_t k = 0; k < (size_t)Pj * V; k++) hmmh_model_free(&sm[k]);
+      free(sm);
+    }
+    hmmh_model_set_free(&models);
+    fl += Pj;
   }
+  if (fl != argc - 2) die("models_number %s does not match the argument list \n", argv[1]);
   if (U > 0) {
     if (hmmcu_rank(ctx, probab, U, V, 1.0, label, second) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
     hmmcu_destroy(ctx);
@@ -175,7 +223,7 @@ int hmmh_test_main(int argc, char **argv) {
       if (strcmp(last, " ") != 0) {
         double cpu_time = batch_cpu * (correct + error) / U;
         sum_cpu += cpu_time;
-        write_word_block(correct, error, nsecond, V, last, wrong, &models, cpu_time, word_frames);
+        write_word_block(correct, error, nsecond, V, last, wrong, words, cpu_time, word_frames);
         sum_correct += correct; sum_error += error; sum_second += nsecond; total_frames += word_frames;
         word_frames = correct = error = nsecond = 0;
         for (int i = 0; i < V; i++) wrong[i] = 0;
@@ -183,12 +231,12 @@ int hmmh_test_main(int argc, char **argv) {
       fprintf(g_out, "\nSpoken word: %s\n", spoken[u]);
     }
     word_frames += (int)(off[u + 1] - off[u]);
-    printf("\r\nSpoken word: %s -> %s : %f\r\n", spoken[u], models.word[label[u]], probab[(size_t)u * V + label[u]]);
-    if (strncmp(spoken[u], models.word[label[u]], WSTR) == 0) correct++;
+    printf("\r\nSpoken word: %s -> %s : %f\r\n", spoken[u], words[label[u]], probab[(size_t)u * V + label[u]]);
+    if (strncmp(spoken[u], words[label[u]], WSTR) == 0) correct++;
     else {
       error++;
       wrong[label[u]]++;
-      if (V > 1 && strncmp(spoken[u], models.word[second[u]], WSTR) == 0) nsecond++;
+      if (V > 1 && strncmp(spoken[u], words[second[u]], WSTR) == 0) nsecond++;
     }
     strncpy(last, spoken[u], WSTR);
   }
@@ -196,7 +244,7 @@ int hmmh_test_main(int argc, char **argv) {
   if (U > 0) {
     double cpu_time = batch_cpu * (correct + error) / U;
     sum_cpu += cpu_time;
-    write_word_block(correct, error, nsecond, K /* sic, R-FS:400 */, last, wrong, &models, cpu_time, word_frames);
+    write_word_block(correct, error, nsecond, K /* sic, R-FS:400 */, last, wrong, words, cpu_time, word_frames);
     sum_correct += correct; sum_error += error; sum_second += nsecond; total_frames += word_frames;
     /* writing_total_result R-FS:1170-1194 */
     int sum = sum_correct + sum_error;
@@ -211,7 +259,7 @@ int hmmh_test_main(int argc, char **argv) {
     fprintf(g_out, "Average word length: %d frames \n", total_frames / sum);
   }
   fclose(g_out);
-  hmmh_model_set_free(&models);
+  free(words); free(offq);
   free(off); free(spoken); free(logp); free(probab); free(label); free(second); free(wrong);
   return 0;
 }

@@ -3,7 +3,8 @@
  *   hmm_continuous_fs word N P M_1..M_P list_1..list_P out.hmm [init.hmm]
  * Same argv, same list / feature / .hmm / .txt formats, same exit codes (usage or any I/O error:
  * message on stdout, exit(1)).  The E-step runs on the GPU through hmm_cuda.h.
- * Differences, all deliberate: P (feature streams) must be 1 (SURVEY #16); the optional initial
+ * P feature streams are one context each, linked for the E-step (hmmcu_link_streams).
+ * Differences, all deliberate: the optional initial
  * model is read from argv[argc-1] (the reference reads argv[argc] == NULL and would crash,
  * T-FS:216-222); capacity limits are runtime values.
  */
@@ -24,7 +25,7 @@ static void die(const char *fmt, const char *arg) {
 }
 
 /* writing_text T-FS:2168-2265 */
-static void write_report(const char *txt, const char *hmm, const char *word, int N, int M, const char *list,
+static void write_report(const char *txt, const char *hmm, const char *word, int N, int P, const int *M, const char *const *list,
                          const char *t0, const char *t1, const char *cpu, int exemplars, double mean, int iters) {
   FILE *f = fopen(txt, "w");
   if (!f) die("can't open file %s \n", txt);
@@ -32,9 +33,9 @@ static void write_report(const char *txt, const char *hmm, const char *word, int
   fprintf(f, "model file: %s \n", hmm);
   fprintf(f, "word: %s \n", word);
   fprintf(f, "number of states: %d \n", N);
-  fprintf(f, "number of parameters: %d \n", 1);
-  fprintf(f, "number of mixtures %d: %d \n", 1, M);
-  fprintf(f, "parameter %d: %s \n", 1, list);
+  fprintf(f, "number of parameters: %d \n", P);
+  for (int p = 0; p < P; p++) fprintf(f, "number of mixtures %d: %d \n", p + 1, M[p]);
+  for (int p = 0; p < P; p++) fprintf(f, "parameter %d: %s \n", p + 1, list[p]);
   fprintf(f, "threshould to finish training: %f \n", 1.0e-3);
   fprintf(f, "number of exemplars in training sequence: %d \n", exemplars);
   fprintf(f, "mean probability: %f \n", mean);
@@ -66,66 +67,92 @@ int hmmh_train_main(int argc, char **argv) {
   }
   const char *word = argv[1];
   const int N = atoi(argv[2]), P = atoi(argv[3]);
-  if (P != 1) die("param_number %s is not supported: this build handles one feature stream \n", argv[3]);
-  const int M = atoi(argv[4]);
-  const char *list = argv[5], *out = argv[6];
-  if (N < 1 || N > HMMCU_MAX_STATES || M < 1) die("bad states/mixtures number (%s) \n", argv[2]);
+  if (P < 1 || P > HMMH_MAX_STREAMS) die("bad param_number (%s) \n", argv[3]);
+  if (argc < 2 * P + 5) die("param_number %s does not match the argument list \n", argv[3]);
+  int M[HMMH_MAX_STREAMS];
+  const char *list[HMMH_MAX_STREAMS];
+  for (int p = 0; p < P; p++) {
+    M[p] = atoi(argv[4 + p]);
+    list[p] = argv[4 + P + p];
+    if (M[p] < 1) die("bad states/mixtures number (%s) \n", argv[4 + p]);
+  }
+  const char *out = argv[4 + 2 * P];
+  if (N < 1 || N > HMMCU_MAX_STATES) die("bad states/mixtures number (%s) \n", argv[2]);
   char txt[NAME_SIZE + 8];
   strncpy(txt, out, NAME_SIZE);
   txt[NAME_SIZE - 1] = 0;
   strtok(txt, "."); /* T-FS:205-207 */
   strcat(txt, ".txt");
 
-  /* the whole training list, once (the reference re-reads every file twice per iteration): the many-files
-   * reader streams it into HBM through pinned staging, no host copy is kept (ingest.c) */
-  char **paths = NULL;
-  int U = 0, D = 0, bad = -1;
-  if (hmmh_read_list(list, &paths, &U) != HMMCU_OK) die("file %s not found \n", list);
-  if (U == 0) die("file %s not found \n", list);
-  for (int u = 0; u < U; u++) printf("\r\nOpenning %s", paths[u]);
-  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * ((size_t)U + 1));
-  if (!off) die("error on allocating memory. %s\n", "");
-
-  hmmcu_ctx *ctx = NULL;
-  if (hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
-  int rc = hmmh_ingest(ctx, (const char *const *)paths, U, 0, off, &D, &bad, NULL);
-  if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : list);
-  if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
-  int32_t *u2m = (int32_t *)calloc((size_t)U, sizeof(int32_t));
-
-  hmmh_model m;
-  memset(&m, 0, sizeof(m));
-  if (argc == 2 * P + 6) {
-    if (hmmh_read_model(argv[argc - 1], &m, 0) != HMMCU_OK) die("reading error on file %s \n", argv[argc - 1]);
-    if (m.D != D) die("reading error on file %s \n", argv[argc - 1]);
-  } else {
-    if (hmmh_model_alloc(&m, N, M, D) != HMMCU_OK) die("error on allocating memory. %s\n", "");
-    /* creating_initial_model (T-FS:226, 732-1317): on the device (bit-identical to the host version, which stays
-     * as the path for feature widths / mixture counts the device builder does not take) */
-    if (D <= 64 && M <= 255 && N <= 8) {
-      if (hmmcu_init_models(ctx, u2m, 1, N, M) != HMMCU_OK || hmmcu_get_models(ctx, m.A, m.c, m.mu, m.inv_var, m.det) != HMMCU_OK)
-        die("GPU error: %s \n", hmmcu_last_error(ctx));
-    } else { /* shapes the device builder does not take: the host builder, from a host copy of the corpus */
-      double *x = (double *)malloc(sizeof(double) * (size_t)off[U] * D);
-      if (!x) die("error on allocating memory. %s\n", "");
-      for (int u = 0; u < U; u++) {
-        double *xu; int T, d;
-        if (hmmh_read_features(paths[u], &xu, &T, &d) != HMMCU_OK || d != D || T != (int)(off[u + 1] - off[u])) die("reading error on file %s \n", paths[u]);
-        memcpy(x + off[u] * D, xu, sizeof(double) * (size_t)T * D);
-        free(xu);
-      }
-      hmmh_init_model(&m, x, off, U);
-      free(x);
+  /* the whole training list of every feature stream, once (the reference re-reads every file twice per iteration):
+   * the many-files reader streams it into HBM through pinned staging, no host copy is kept (ingest.c).  One context
+   * per stream; line i of every list is the same utterance (T-FS:272-290). */
+  char **paths[HMMH_MAX_STREAMS];
+  hmmcu_ctx *ctxs[HMMH_MAX_STREAMS];
+  int64_t *off = NULL;
+  int U = 0, D[HMMH_MAX_STREAMS];
+  for (int p = 0; p < P; p++) {
+    int Up = 0, bad = -1;
+    if (hmmh_read_list(list[p], &paths[p], &Up) != HMMCU_OK || Up == 0) die("file %s not found \n", list[p]);
+    if (p == 0) U = Up;
+    if (Up < U) die("reading error on file %s \n", list[p]);
+    for (int u = 0; u < U; u++) printf("\r\nOpenning %s", paths[p][u]);
+    int64_t *offp = (int64_t *)malloc(sizeof(int64_t) * ((size_t)U + 1));
+    if (!offp) die("error on allocating memory. %s\n", "");
+    ctxs[p] = NULL;
+    if (hmmcu_create(0, &ctxs[p]) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+    int rc = hmmh_ingest(ctxs[p], (const char *const *)paths[p], U, 0, offp, &D[p], &bad, NULL);
+    if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[p][bad] : list[p]);
+    if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctxs[p]));
+    if (p == 0) off = offp;
+    else {
+      if (memcmp(off, offp, sizeof(int64_t) * ((size_t)U + 1)) != 0) die("reading error on file %s (the streams of an utterance differ in length) \n", list[p]);
+      free(offp);
     }
   }
-  memset(m.word, 0, sizeof(m.word));
-  strncpy(m.word, word, sizeof(m.word) - 1);
+  hmmcu_ctx *ctx = ctxs[0];
+  int32_t *u2m = (int32_t *)calloc((size_t)U, sizeof(int32_t));
+
+  hmmh_model m[HMMH_MAX_STREAMS];
+  memset(m, 0, sizeof(m));
+  if (argc == 2 * P + 6) {
+    int Pf = 0;
+    if (hmmh_read_model_streams(argv[argc - 1], m, P, &Pf, 0) != HMMCU_OK || Pf != P) die("reading error on file %s \n", argv[argc - 1]);
+    for (int p = 0; p < P; p++)
+      if (m[p].D != D[p]) die("reading error on file %s \n", argv[argc - 1]);
+  } else {
+    for (int p = 0; p < P; p++) {
+      if (hmmh_model_alloc(&m[p], N, M[p], D[p]) != HMMCU_OK) die("error on allocating memory. %s\n", "");
+      /* creating_initial_model (T-FS:226, 732-1317), stream by stream: on the device (bit-identical to the host version,
+       * which stays as the path for feature widths / mixture counts the device builder does not take) */
+      if (D[p] <= 64 && M[p] <= 255 && N <= 8) {
+        if (hmmcu_init_models(ctxs[p], u2m, 1, N, M[p]) != HMMCU_OK ||
+            hmmcu_get_models(ctxs[p], m[p].A, m[p].c, m[p].mu, m[p].inv_var, m[p].det) != HMMCU_OK)
+          die("GPU error: %s \n", hmmcu_last_error(ctxs[p]));
+      } else { /* the host builder, from a host copy of the stream */
+        double *x = (double *)malloc(sizeof(double) * (size_t)off[U] * D[p]);
+        if (!x) die("error on allocating memory. %s\n", "");
+        for (int u = 0; u < U; u++) {
+          double *xu; int T, d;
+          if (hmmh_read_features(paths[p][u], &xu, &T, &d) != HMMCU_OK || d != D[p] || T != (int)(off[u + 1] - off[u])) die("reading error on file %s \n", paths[p][u]);
+          memcpy(x + off[u] * D[p], xu, sizeof(double) * (size_t)T * D[p]);
+          free(xu);
+        }
+        hmmh_init_model(&m[p], x, off, U);
+        free(x);
+      }
+    }
+  }
+  for (int p = 0; p < P; p++) {
+    memset(m[p].word, 0, sizeof(m[p].word));
+    strncpy(m[p].word, word, sizeof(m[p].word) - 1);
+  }
 
   double mean = 0.0;
   int iters = 0;
   printf("\r\nCreating HMM using Forward-Backward algorithm (Baum-Welch)");
-  if (hmmh_train(ctx, &m, 1, u2m, U, &mean, &iters, 0, NULL, NULL) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
-  hmmcu_destroy(ctx);
+  if (hmmh_train_streams(ctxs, P, m, 1, u2m, U, &mean, &iters, 0, NULL, NULL) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
+  for (int p = P - 1; p >= 0; p--) hmmcu_destroy(ctxs[p]);
 
   /* cpu time exactly as the reference formats it (T-FS:364-369) */
   struct tms tb;
@@ -137,11 +164,13 @@ int hmmh_train_main(int argc, char **argv) {
   time(&end);
   strftime(t1, sizeof(t1), "%d-%h-%Y %X", localtime(&end));
 
-  if (hmmh_write_model(out, &m) != HMMCU_OK) die("can't open file %s \n", out);
-  write_report(txt, out, word, m.N, m.M, list, t0, t1, cpu, U, mean, iters);
+  if (hmmh_write_model_streams(out, m, P) != HMMCU_OK) die("can't open file %s \n", out);
+  write_report(txt, out, word, N, P, M, list, t0, t1, cpu, U, mean, iters);
   printf("\r\nmean probability: %f, iterations: %d\r\n", mean, iters);
-  hmmh_model_free(&m);
-  hmmh_free_list(paths, U);
+  for (int p = 0; p < P; p++) {
+    hmmh_model_free(&m[p]);
+    hmmh_free_list(paths[p], U);
+  }
   free(off); free(u2m);
   return 0;
 }

@@ -374,6 +374,172 @@ def test_cli_two_model_sets_weighted_sum(tmp_path):
     assert "Correct words: %d\nErrors: 0" % len(labels) in txt.split("Considering all the words:")[1]
 
 
+# ------------------------------------------------------------- multi-stream models (P = 2) ----
+def test_two_stream_model_matches_reference(golden_dir):
+    """param_number = 2: two linked contexts against the reference trainer / recogniser run with two
+    feature streams (tests/golden/synth_p2.npz) and against the multi-stream oracle: first E-step statistics of both
+    streams, the EM loop (iterations, mean log-probability, every trained parameter), forward scores, Viterbi."""
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    V, N, labels, off = int(g["V"]), int(g["N"]), g["train_labels"], g["off"]
+    cs = [api.Context(0), api.Context(0)]
+    init = []
+    for p, c in enumerate(cs):
+        c.set_features(g["x%d" % p], off)
+        init.append(c.init_models(labels, V, N, int(g["M"][p])))
+    assert np.array_equal(init[0].A, init[1].A)
+    cs[0].link_streams([cs[1]])
+    st0, lpu = cs[0].estep(labels)
+    stats = [st0, cs[1].stats_download()]
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        xs = [np.concatenate([g["x%d" % p][off[u]:off[u + 1]] for u in us]) for p in range(2)]
+        want, lp = o.estep_streams([_oracle_model(init[p], v) for p in range(2)], xs, offv)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        for p in range(2):
+            sp = api.split_stats(stats[p][v], N, int(g["M"][p]), int(g["D"][p]))
+            assert abs(sp["sum_logp"] - want[p].sum_logp) <= RTOL * abs(want[p].sum_logp) and sp["n_utt"] == len(us)
+            for name in ("num_trans", "den_trans", "den_mix", "S0"):
+                w = getattr(want[p], name)
+                assert np.allclose(sp[name], w, rtol=RTOL, atol=1e-6 * np.abs(w).max()), (v, p, name)
+    # the EM loop, every word with the reference's stopping rule (T-FS:238-361)
+    for c in cs:
+        c.em_reset()
+    active, its, mean = np.ones(V, bool), np.zeros(V, int), np.zeros(V)
+    for it in range(1, 50):
+        cs[0].estep(np.where(active[labels], labels, -1), download=False, want_logp=False)
+        lp0, nu0, upd0 = cs[0].mstep()
+        lp1, nu1, upd1 = cs[1].mstep()
+        assert np.array_equal(upd0, upd1) and np.array_equal(lp0[active], lp1[active])
+        its[active], mean[active] = it, (lp0 / np.maximum(nu0, 1))[active]
+        active &= upd0.astype(bool)
+        if not active.any():
+            break
+    assert (its == g["iterations"]).all(), (its, g["iterations"])
+    assert np.allclose(mean, g["mean_logp"], rtol=RTOL)
+    trained = [cs[p].get_models(int(g["D"][p])) for p in range(2)]
+    assert np.array_equal(trained[0].A, trained[1].A)
+    for p in range(2):
+        for v in range(V):
+            mo = o.Model(*[g["trained_s%d_%s" % (p, k)][v] for k in ("A", "c", "mu", "iv", "det")])
+            _assert_params_close(trained[p], v, mo)
+    # recognition with the reference-trained models: product of the streams' densities (R-FS:341-364)
+    offt, tl = g["offt"], g["test_labels"]
+    ref_ms = [api.ModelSet(*[g["trained_s%d_%s" % (p, k)] for k in ("A", "c", "mu", "iv", "det")]) for p in range(2)]
+    for p, c in enumerate(cs):
+        c.set_features(g["xt%d" % p], offt)
+        c.set_models(ref_ms[p])
+    fw = cs[0].forward_scores()
+    assert np.allclose(fw, g["score"], rtol=RTOL)
+    assert (cs[0].rank(fw)[0] == tl).all()
+    vs = cs[0].viterbi_scores()
+    score, path = cs[0].viterbi(tl)
+    for u in range(len(tl)):
+        b = None
+        for p in range(2):
+            bp = o.emissions(_oracle_model(ref_ms[p], tl[u]), g["xt%d" % p][offt[u]:offt[u + 1]], want_post=False)[0]
+            b = bp if b is None else b * bp
+        s, pth = o.viterbi(_oracle_model(ref_ms[0], tl[u]), b)
+        assert (path[offt[u]:offt[u + 1]] == pth).all() and abs(score[u] - s) <= 1e-9 * abs(s)
+        assert abs(vs[u, tl[u]] - s) <= 1e-5 * abs(s)
+    # a linked stream refuses to run on its own; unlinking restores the single-stream behaviour
+    with pytest.raises(api.HmmCudaError, match="linked stream"):
+        cs[1].forward_scores()
+    cs[0].link_streams([])
+    single = cs[1].forward_scores()
+    assert np.isfinite(single).all() and not np.allclose(single, fw)
+    for c in cs:
+        c.close()
+
+
+def test_cli_two_streams_match_reference_outputs(golden_dir, tmp_path):
+    """The drop-in programs with param_number = 2 on the case the reference itself was run on (synth_p2.npz): training
+    report (iterations, mean probability), the two-stream .hmm files, and the recogniser's result file line by line."""
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    V, N, off, offt = int(g["V"]), int(g["N"]), g["off"], g["offt"]
+    bindir = os.path.join(os.path.dirname(api.LIB_PATH), "bin")
+    hmms = []
+    for v in range(V):
+        lists = []
+        for p in range(2):
+            files = []
+            for u in np.nonzero(g["train_labels"] == v)[0]:
+                files.append(str(tmp_path / ("tr_s%d_%d.bin" % (p, u))))
+                api.write_features(files[-1], g["x%d" % p][off[u]:off[u + 1]])
+            lists.append(str(tmp_path / ("list_s%d_w%d.txt" % (p, v))))
+            open(lists[-1], "w").write("\n".join(files) + "\n")
+        hmms.append(str(tmp_path / ("w%d.hmm" % v)))
+        subprocess.run([os.path.join(bindir, "hmm_continuous_fs"), "word%d" % v, str(N), "2", str(g["M"][0]), str(g["M"][1]), lists[0], lists[1], hmms[-1]],
+                       check=True, stdout=subprocess.DEVNULL)
+        mean, its = r.parse_train_report(hmms[-1][:-4] + ".txt")
+        assert its == g["iterations"][v] and abs(mean - g["mean_logp"][v]) <= RTOL * abs(g["mean_logp"][v])
+        rep = open(hmms[-1][:-4] + ".txt").read()
+        assert "number of parameters: 2 \nnumber of mixtures 1: %d \nnumber of mixtures 2: %d \n" % (g["M"][0], g["M"][1]) in rep
+        streams = r.read_model_streams(hmms[-1])
+        assert len(streams) == 2 and streams[0].word == "word%d" % v
+        for p in range(2):
+            got = api.ModelSet(*[getattr(streams[p], k)[None] for k in ("A", "c", "mu", "iv", "det")])
+            _assert_params_close(got, 0, o.Model(*[g["trained_s%d_%s" % (p, k)][v] for k in ("A", "c", "mu", "iv", "det")]))
+    feats = []
+    for p in range(2):
+        files = []
+        for u in range(len(g["test_labels"])):
+            files.append(str(tmp_path / ("te_s%d_%d.bin" % (p, u))))
+            api.write_features(files[-1], g["xt%d" % p][offt[u]:offt[u + 1]])
+        feats.append(str(tmp_path / ("feat_s%d.txt" % p)))
+        open(feats[-1], "w").write("\n".join(files) + "\n")
+    open(str(tmp_path / "models.txt"), "w").write("\n".join(hmms) + "\n")
+    open(str(tmp_path / "words.txt"), "w").write("\n".join("word%d" % v for v in g["test_labels"]) + "\n")
+    res = str(tmp_path / "res.txt")
+    out = subprocess.run([os.path.join(bindir, "recognition_continuous_fs"), "1", str(tmp_path / "models.txt"), "1", feats[0], feats[1],
+                          str(tmp_path / "words.txt"), res], check=True, stdout=subprocess.PIPE).stdout.decode()
+    got = re.findall(r"Spoken word: (\S+) -> (\S+) : (\S+)", out)
+    for u, (spoken, rec, score) in enumerate(got):
+        assert rec == spoken == "word%d" % g["test_labels"][u]
+        assert abs(float(score) - g["score"][u].max()) <= RTOL * abs(g["score"][u].max())
+    strip = lambda t: [l for l in t.splitlines() if not l.startswith(("Date and time", "Average recognition time", "Model name"))]
+    assert strip(open(res).read()) == strip(str(g["result_file"]))
+
+
+def test_two_stream_estep_on_the_tensor_core_path():
+    """Linked streams at MFCC-sized widths (D = 39 and D = 13, M = 4 and 2): both contexts take the tcgen05 kernels, the
+    second one accumulates with the first one's state posteriors.  Against the multi-stream oracle."""
+    V, N, U = 2, 5, 24
+    labels = np.arange(U) % V
+    sets = []
+    for p, (M, D) in enumerate(((4, 39), (2, 13))):
+        cen, sc = synth.make_centres(V, N, M, D, seed=900 + p)
+        x, off = synth.make_utterances(cen, sc, labels, seed=55, tmin=90, tmax=140)
+        sets.append((api.ModelSet.from_dict(synth.make_models(cen, sc)), x, off))
+    assert np.array_equal(sets[0][2], sets[1][2])
+    off = sets[0][2]
+    cs = [api.Context(0), api.Context(0)]
+    for c, (ms, x, _) in zip(cs, sets):
+        c.set_features(x, off)
+        c.set_models(ms)
+    cs[0].link_streams([cs[1]])
+    st0, lpu = cs[0].estep(labels)
+    stats = [st0, cs[1].stats_download()]
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        xs = [np.concatenate([sets[p][1][off[u]:off[u + 1]] for u in us]) for p in range(2)]
+        want, lp = o.estep_streams([_oracle_model(sets[p][0], v) for p in range(2)], xs, offv)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        for p in range(2):
+            ms = sets[p][0]
+            sp = api.split_stats(stats[p][v], N, ms.M, ms.D)
+            for name in ("num_trans", "den_trans", "den_mix", "S0"):
+                w = getattr(want[p], name)
+                assert np.allclose(sp[name], w, rtol=RTOL, atol=1e-6 * np.abs(w).max()), (v, p, name)
+            got, mo = ms.copy(), _oracle_model(ms, v)
+            api.mstep(got, stats[p])
+            o.mstep(mo, want[p])
+            _assert_params_close(got, v, mo)
+    for c in cs:
+        c.close()
+
+
 # ------------------------------------------------- full-size, size-independent properties ----
 def test_c2_size_properties(ctx):
     """BASELINE config 2 (N=5, M=16, 1000 utterances of ~300 frames): too big for the CPU oracle in a
