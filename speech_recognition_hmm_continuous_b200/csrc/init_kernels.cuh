@@ -59,7 +59,7 @@ __global__ void k_init_accumulate(const double *__restrict__ x, const int32_t *_
   const int64_t g = (int64_t)vk * M + j;
   const int e0 = lst_off[vk], e1 = lst_off[vk + 1];
   const int d0 = lane, d1 = lane + 32;
-  double s0 = 0.0, s1 = 0.0, ds = 0.0, n = 0.0;
+  double s0 = 0.0, s1 = 0.0, ds = 0.0, n_acc = 0.0;
   const double c0 = (mode == 1 && d0 < D) ? cent[g * D + d0] : 0.0, c1 = (mode == 1 && d1 < D) ? cent[g * D + d1] : 0.0;
   for (int eb = e0; eb < e1; eb += 32) {
     // this block of 32 entries: cell and distortion of entry eb + lane, frame id likewise (one coalesced load each)
@@ -68,27 +68,46 @@ __global__ void k_init_accumulate(const double *__restrict__ x, const int32_t *_
     const int my_frame = (e < e1) ? lst[e] : 0;
     const double my_dd = (e < e1 && dd && !all) ? dd[e] : 0.0;
     unsigned hit = __ballot_sync(0xffffffffu, my_cell == j);
-    while (hit) {  // in entry order
-      const int l = __ffs(hit) - 1;
-      hit &= hit - 1;
-      const int f = __shfl_sync(0xffffffffu, my_frame, l);
-      const double dl = __shfl_sync(0xffffffffu, my_dd, l);
-      const double *xr = x + (int64_t)f * D;
-      if (mode == 0) {
-        if (d0 < D) s0 = __dadd_rn(s0, xr[d0]);
-        if (d1 < D) s1 = __dadd_rn(s1, xr[d1]);
-        ds = __dadd_rn(ds, dl);
-      } else {
-        if (d0 < D) { const double a = __dsub_rn(xr[d0], c0); s0 = __dadd_rn(s0, __dmul_rn(a, a)); }
-        if (d1 < D) { const double a = __dsub_rn(xr[d1], c1); s1 = __dadd_rn(s1, __dmul_rn(a, a)); }
+    // The additions stay in entry order (bit-exactness); the feature loads do not depend on them, so the rows of up to
+    // sixteen hits are fetched together before their sums are formed (a dependent load per addition cost ~500 cycles each).
+    while (hit) {  // `hit` is warp-uniform
+      constexpr int kB = 16;
+      double x0[kB], x1[kB], dl[kB];
+      int n = 0;
+#pragma unroll
+      for (int q = 0; q < kB; q++) {
+        x0[q] = x1[q] = dl[q] = 0.0;
+        if (hit) {
+          const int l = __ffs(hit) - 1;
+          hit &= hit - 1;
+          const int f = __shfl_sync(0xffffffffu, my_frame, l);
+          dl[q] = __shfl_sync(0xffffffffu, my_dd, l);
+          const double *xr = x + (int64_t)f * D;
+          if (d0 < D) x0[q] = xr[d0];
+          if (d1 < D) x1[q] = xr[d1];
+          n = q + 1;
+        }
       }
-      n += 1.0;
+#pragma unroll
+      for (int q = 0; q < kB; q++) {
+        if (q < n) {  // in entry order
+          if (mode == 0) {
+            if (d0 < D) s0 = __dadd_rn(s0, x0[q]);
+            if (d1 < D) s1 = __dadd_rn(s1, x1[q]);
+            ds = __dadd_rn(ds, dl[q]);
+          } else {
+            if (d0 < D) { const double a = __dsub_rn(x0[q], c0); s0 = __dadd_rn(s0, __dmul_rn(a, a)); }
+            if (d1 < D) { const double a = __dsub_rn(x1[q], c1); s1 = __dadd_rn(s1, __dmul_rn(a, a)); }
+          }
+          n_acc += 1.0;
+        }
+      }
     }
   }
   if (d0 < D) sum[g * D + d0] = s0;
   if (d1 < D) sum[g * D + d1] = s1;
   if (lane == 0) {
-    cnt[g] = n;
+    cnt[g] = n_acc;
     if (mode == 0 && dist) dist[g] = ds;
   }
 }
