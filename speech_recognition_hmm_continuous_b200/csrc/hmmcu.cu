@@ -722,8 +722,12 @@ int hmmcu_init_models(hmmcu_ctx *ctx, const int32_t *utt2model, int V, int N, in
   CK(cudaMemsetAsync(ctx->in_dist.p, 0, sizeof(double) * G, ctx->st));
   const double *x = ctx->d_x64;
   auto classify = [&](int have) -> int {
-    k_init_classify<<<(unsigned)((E + 255) / 256), 256, 0, ctx->st>>>(x, ctx->in_lst.as<int32_t>(), ctx->in_vk.as<int32_t>(), E, ctx->in_cent.as<double>(), M, D,
-                                                                     have, ctx->in_idx.as<uint8_t>(), ctx->in_dd.as<double>());
+    if (D == 39)
+      k_init_classify<39><<<(unsigned)((E + 127) / 128), 128, 0, ctx->st>>>(x, ctx->in_lst.as<int32_t>(), ctx->in_vk.as<int32_t>(), E, ctx->in_cent.as<double>(), M, D,
+                                                                           have, ctx->in_idx.as<uint8_t>(), ctx->in_dd.as<double>());
+    else
+      k_init_classify<0><<<(unsigned)((E + 255) / 256), 256, 0, ctx->st>>>(x, ctx->in_lst.as<int32_t>(), ctx->in_vk.as<int32_t>(), E, ctx->in_cent.as<double>(), M, D,
+                                                                          have, ctx->in_idx.as<uint8_t>(), ctx->in_dd.as<double>());
     LAUNCH_CHECK();
     return HMMCU_OK;
   };
@@ -736,7 +740,7 @@ int hmmcu_init_models(hmmcu_ctx *ctx, const int32_t *utt2model, int V, int N, in
     return HMMCU_OK;
   };
   auto update = [&](int have, int have_next) -> int {
-    k_init_update<<<(VN + 63) / 64, 64, 0, ctx->st>>>(ctx->in_cent.as<double>(), ctx->in_sum.as<double>(), ctx->in_dist.as<double>(), ctx->in_cnt.as<double>(),
+    k_init_update<<<(VN * 32 + 127) / 128, 128, 0, ctx->st>>>(ctx->in_cent.as<double>(), ctx->in_sum.as<double>(), ctx->in_dist.as<double>(), ctx->in_cnt.as<double>(),
                                                      VN, M, D, have, have_next, ctx->in_ord.as<int>());
     LAUNCH_CHECK();
     return HMMCU_OK;

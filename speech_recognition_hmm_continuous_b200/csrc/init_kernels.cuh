@@ -24,6 +24,9 @@ namespace hmmk {
 // cent / sum: [V][N][M][D]; cnt / dist: [V][N][M]
 
 // nearest of `have` centroids of each entry's (v, k)   (classifying, T-FS:1179-1215)
+// DT = D at compile time keeps the frame in registers (it is compared with up to M centroids; re-reading it through
+// the cache, a line per lane, made this kernel L1-bound); DT = 0 is the general form.
+template <int DT>
 __global__ void k_init_classify(const double *__restrict__ x, const int32_t *__restrict__ lst, const int32_t *__restrict__ ent_vk,
                                 int64_t E, const double *__restrict__ cent, int M, int D, int have, uint8_t *__restrict__ idx,
                                 double *__restrict__ dd) {
@@ -31,13 +34,26 @@ __global__ void k_init_classify(const double *__restrict__ x, const int32_t *__r
   if (e >= E) return;
   const double *xr = x + (int64_t)lst[e] * D;
   const double *c = cent + (int64_t)ent_vk[e] * M * D;
+  double xv[DT > 0 ? DT : 1];
+  if (DT > 0) {
+#pragma unroll
+    for (int d = 0; d < DT; d++) xv[d] = xr[d];
+  }
   double best = 1.0e20;
   int which = 0;
   for (int i = 0; i < have; i++) {
     double dist = 0.0;
-    for (int d = 0; d < D; d++) {
-      const double a = __dsub_rn(c[(int64_t)i * D + d], xr[d]);
-      dist = __dadd_rn(dist, __dmul_rn(a, a));
+    if (DT > 0) {
+#pragma unroll
+      for (int d = 0; d < DT; d++) {
+        const double a = __dsub_rn(c[(int64_t)i * DT + d], xv[d]);
+        dist = __dadd_rn(dist, __dmul_rn(a, a));
+      }
+    } else {
+      for (int d = 0; d < D; d++) {
+        const double a = __dsub_rn(c[(int64_t)i * D + d], xr[d]);
+        dist = __dadd_rn(dist, __dmul_rn(a, a));
+      }
     }
     if (dist < best) { best = dist; which = i; }
   }
@@ -124,39 +140,48 @@ __device__ inline void init_order_desc(const double *keys, int *idx, int n) {  /
   }
 }
 
-// One thread per (v, k): new centroids = sum / count, the empty-cell rule (T-FS:1236-1269), and -- when this was the
-// last pass of a level and more cells are wanted -- the next split (T-FS:1120-1158).  seed: cent[.][0] = sum / cnt only.
-// have_next = cells after the optional split (== have: no split).
+// One warp per (v, k), lanes over the dimensions (every vector operation of the reference is elementwise in d, and a
+// lane keeps the reference's statement order for its own d): new centroids = sum / count, the empty-cell rule
+// (T-FS:1236-1269), and -- when this was the last pass of a level and more cells are wanted -- the next split
+// (T-FS:1120-1158).  seed: cent[.][0] = sum / cnt only.  have_next = cells after the optional split (== have: no split).
 __global__ void k_init_update(double *__restrict__ cent, const double *__restrict__ sum, const double *__restrict__ dist,
                               const double *__restrict__ cnt, int VN, int M, int D, int have, int have_next, int *__restrict__ ord_ws) {
-  const int vk = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (vk >= VN) return;
   double *ck = cent + (int64_t)vk * M * D;
   const double *sk = sum + (int64_t)vk * M * D, *dk = dist + (int64_t)vk * M, *nk = cnt + (int64_t)vk * M;
   int *ord = ord_ws + (int64_t)vk * M;
   for (int j = 0; j < have; j++)
-    for (int d = 0; d < D; d++) ck[(int64_t)j * D + d] = sk[(int64_t)j * D + d] / nk[j];
-  if (have > 1 || have_next > have) init_order_desc(dk, ord, have);
+    for (int d = lane; d < D; d += 32) ck[(int64_t)j * D + d] = sk[(int64_t)j * D + d] / nk[j];
+  if (have > 1 || have_next > have) {
+    if (lane == 0) init_order_desc(dk, ord, have);
+    __syncwarp();
+  }
   if (have > 1) {  // an empty cell is refilled from the most distorted ones
     int nxt = 0;
     for (int j = 0; j < have; j++)
       if (nk[j] == 0.0) {
         const int src = ord[nxt++];
-        for (int d = 0; d < D; d++) ck[(int64_t)j * D + d] = ck[(int64_t)src * D + d] * (1.005);
-        for (int d = 0; d < D; d++) ck[(int64_t)src * D + d] = ck[(int64_t)src * D + d] * (0.995);
+        for (int d = lane; d < D; d += 32) {
+          ck[(int64_t)j * D + d] = ck[(int64_t)src * D + d] * (1.005);
+          ck[(int64_t)src * D + d] = ck[(int64_t)src * D + d] * (0.995);
+        }
       }
   }
   if (have_next > have) {
     if (have_next == 2 * have && 2 * have < M) {  // doubling
-      for (int j = 0; j < have; j++) {
-        for (int d = 0; d < D; d++) ck[(int64_t)(have + j) * D + d] = ck[(int64_t)j * D + d] * (1.005);
-        for (int d = 0; d < D; d++) ck[(int64_t)j * D + d] = ck[(int64_t)j * D + d] * (0.995);
-      }
+      for (int j = 0; j < have; j++)
+        for (int d = lane; d < D; d += 32) {
+          ck[(int64_t)(have + j) * D + d] = ck[(int64_t)j * D + d] * (1.005);
+          ck[(int64_t)j * D + d] = ck[(int64_t)j * D + d] * (0.995);
+        }
     } else {  // split the M - have most distorted cells
       for (int j = 0; j < have_next - have; j++) {
         const int src = ord[j];
-        for (int d = 0; d < D; d++) ck[(int64_t)(have + j) * D + d] = ck[(int64_t)src * D + d] * (1.005);
-        for (int d = 0; d < D; d++) ck[(int64_t)src * D + d] = ck[(int64_t)src * D + d] * (0.995);
+        for (int d = lane; d < D; d += 32) {
+          ck[(int64_t)(have + j) * D + d] = ck[(int64_t)src * D + d] * (1.005);
+          ck[(int64_t)src * D + d] = ck[(int64_t)src * D + d] * (0.995);
+        }
       }
     }
   }
