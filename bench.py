@@ -142,6 +142,9 @@ def run_ours(args):
     ctx = api.Context(local, timing=False)
     if args.upload_chunks:
         ctx.set_option("upload_chunks", args.upload_chunks)
+    for kv in args.set:  # library A/B switches (hmmcu_set_option), experiments only
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
     ms = api.ModelSet.from_dict(mods)
 
@@ -556,6 +559,7 @@ def main():
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--torch-allreduce", action="store_true", help="all-reduce through torch.distributed instead of the NCCL C API")
     ap.add_argument("--upload-chunks", type=int, default=0, help="override the library's upload chunk count (experiments)")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="hmmcu_set_option switches (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

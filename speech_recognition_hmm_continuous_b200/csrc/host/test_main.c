@@ -238,7 +238,7 @@ int hmmh_test_main(int argc, char **argv) {
       wrong[label[u]]++;
       if (V > 1 && strncmp(spoken[u], words[second[u]], WSTR) == 0) nsecond++;
     }
-    strncpy(last, spoken[u], WSTR);
+    memcpy(last, spoken[u], WSTR);
   }
   printf("\r\nEnding Tests\r\n");
   if (U > 0) {
