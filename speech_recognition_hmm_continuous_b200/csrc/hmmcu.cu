@@ -76,6 +76,10 @@ struct hmmcu_ctx {
   DevBuf logb_joint;  // sum over the streams of the log-emissions [F][N] (training)
   // feature upload pipeline: chunk copies on their own stream, packed on `st` as they land
   cudaStream_t st_copy = nullptr;
+  // side branches of the M-step launch sequence (the accuracy-guard scan and one of the two W packers run beside the
+  // main chain; fork / join by events, inside the captured graph as well)
+  cudaStream_t st_aux[2] = {};
+  cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
   static constexpr int kUpChunks = 16;
   int up_chunks = 4;         // "upload_chunks" option
   cudaEvent_t ev_chunk[kUpChunks] = {};
@@ -274,6 +278,10 @@ int hmmcu_create(int device, hmmcu_ctx **out) {
             cudaEventCreateWithFlags(&ctx->ev_idle, cudaEventDisableTiming) == cudaSuccess &&
             cudaMallocHost((void **)&ctx->ctr_h, sizeof(double) * 256) == cudaSuccess;
   for (int k = 0; ok && k < hmmcu_ctx::kUpChunks; k++) ok = cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; ok && k < 2; k++)
+    ok = cudaStreamCreateWithFlags(&ctx->st_aux[k], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_fork[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     fail(nullptr, HMMCU_ECUDA, "upload pipeline creation: %s", cudaGetErrorString(cudaGetLastError()));
     hmmcu_destroy(ctx);
@@ -329,6 +337,11 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   for (void *p : ctx->stage_h)
     if (p) cudaFreeHost(p);
   if (ctx->st_copy) cudaStreamDestroy(ctx->st_copy);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->ev_fork[k]) cudaEventDestroy(ctx->ev_fork[k]);
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    if (ctx->st_aux[k]) cudaStreamDestroy(ctx->st_aux[k]);
+  }
   cudaStreamDestroy(ctx->st_own);
   delete ctx;
 }
@@ -1709,15 +1722,41 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
                                                                        ctx->iv.as<double>(), ctx->det.as<double>());
     LAUNCH_CHECK();
     int rc2;
-    if ((rc2 = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc2;
+    // The accuracy-guard scan and the second W packer do not feed the main chain (new parameters -> kc -> emission
+    // images): they run on side streams, joined before the control block is read back.  With the per-kernel timers
+    // on everything stays on one stream, so that the timers keep their meaning.
+    const bool fork = !ctx->timing;
+    auto on_stream = [&](cudaStream_t side, auto launch) -> int {
+      cudaStream_t keep = ctx->st;
+      ctx->st = side;
+      const int r = launch();
+      ctx->st = keep;
+      return r;
+    };
+    if (fork) {
+      CK(cudaEventRecord(ctx->ev_fork[0], ctx->st));
+      CK(cudaStreamWaitEvent(ctx->st_aux[0], ctx->ev_fork[0], 0));
+      if ((rc2 = on_stream(ctx->st_aux[0], [&] { return launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V); })) != HMMCU_OK) return rc2;
+      CK(cudaEventRecord(ctx->ev_join[0], ctx->st_aux[0]));
+    } else {
+      if ((rc2 = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc2;
+    }
     t_end(ctx, "mstep");
     if (repack) {
       t_begin(ctx, "pack");
       if ((rc2 = launch_pack_kc(ctx)) != HMMCU_OK) return rc2;
+      if (fork) {
+        CK(cudaEventRecord(ctx->ev_fork[1], ctx->st));
+        CK(cudaStreamWaitEvent(ctx->st_aux[1], ctx->ev_fork[1], 0));
+        if ((rc2 = on_stream(ctx->st_aux[1], [&] { return launch_pack_acc(ctx); })) != HMMCU_OK) return rc2;
+        CK(cudaEventRecord(ctx->ev_join[1], ctx->st_aux[1]));
+      }
       if ((rc2 = launch_pack_ws(ctx, ctx->ws_train)) != HMMCU_OK) return rc2;
-      if ((rc2 = launch_pack_acc(ctx)) != HMMCU_OK) return rc2;
+      if (fork) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[1], 0));
+      else if ((rc2 = launch_pack_acc(ctx)) != HMMCU_OK) return rc2;
       t_end(ctx, "pack");
     }
+    if (fork) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[0], 0));
     CK(cudaMemcpyAsync(ctx->ctl_h, ctx->ctl_d.p, sizeof(double) * (3 * (size_t)V + 1), cudaMemcpyDeviceToHost, ctx->st));
     return HMMCU_OK;
   };
