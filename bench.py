@@ -29,6 +29,10 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (some images export that); stdout carries the one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
