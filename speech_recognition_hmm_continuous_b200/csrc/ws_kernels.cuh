@@ -443,10 +443,24 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
 #pragma unroll
               for (int j = 1; j < MU; j++) m = fmaxf(m, val[g * MP + j]);
               const float ms = (m > kNegInf) ? m : 0.f;
-              float sm_ = 0.f;
+              float sm_;
+              // The largest term of the sum is 2^0 = 1: with up to three mixtures it is cheaper to order the values
+              // (min / max on the ALU) than to send that term through the SFU as well -- the epilogue of the
+              // small-mixture decode regime is bound by its MUFU operations (C4: M = 3, 4 -> 3 per state).
+              if (MU == 1) {
+                sm_ = 1.f;
+              } else if (MU == 2) {
+                sm_ = 1.f + ex2_approx(fminf(val[g * MP], val[g * MP + 1]) - ms);
+              } else if (MU == 3) {
+                const float a = val[g * MP], b = val[g * MP + 1], c3 = val[g * MP + 2];
+                const float lo = fminf(fminf(a, b), c3), mid = fmaxf(fminf(a, b), fminf(fmaxf(a, b), c3));
+                sm_ = 1.f + (ex2_approx(mid - ms) + ex2_approx(lo - ms));
+              } else {
+                sm_ = 0.f;
 #pragma unroll
-              for (int j = 0; j < MU; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
-              lbv[g] = (m > kNegInf) ? (ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
+                for (int j = 0; j < MU; j++) sm_ += ex2_approx(val[g * MP + j] - ms);
+              }
+              lbv[g] = (m > kNegInf) ? (MU == 1 ? ms : ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
             }
             // the chunk's states are contiguous in the output row: 16- / 8-byte stores when the row allows it (a lane
             // per frame makes every 4-byte store its own memory transaction)
