@@ -85,6 +85,7 @@ struct hmmcu_ctx {
   cudaEvent_t ev_chunk[kUpChunks] = {};
   cudaEvent_t ev_idle = nullptr;
   bool stream_open = false;  // between hmmcu_features_begin and _end
+  bool mstep_fork = true;    // "mstep_fork" option: side streams inside the M-step launch sequence
   void *stage_h[4] = {};     // pinned staging buffers of the ingest pipeline (hmmcu_staging), kept for the context's life
   size_t stage_cap[4] = {};
   int64_t stream_frames = 0;
@@ -375,6 +376,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (!ctx || !key) return HMMCU_EINVAL;
   ctx->cfg_epoch++;
   if (strcmp(key, "graphs") == 0) { ctx->use_graph = value; return HMMCU_OK; }
+  if (strcmp(key, "mstep_fork") == 0) { ctx->mstep_fork = value != 0; return HMMCU_OK; }
   if (strcmp(key, "upload_chunks") == 0) { ctx->up_chunks = std::max(1, std::min(value, hmmcu_ctx::kUpChunks)); return HMMCU_OK; }
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
@@ -1725,7 +1727,7 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
     // The accuracy-guard scan and the second W packer do not feed the main chain (new parameters -> kc -> emission
     // images): they run on side streams, joined before the control block is read back.  With the per-kernel timers
     // on everything stays on one stream, so that the timers keep their meaning.
-    const bool fork = !ctx->timing;
+    const bool fork = !ctx->timing && ctx->mstep_fork;
     auto on_stream = [&](cudaStream_t side, auto launch) -> int {
       cudaStream_t keep = ctx->st;
       ctx->st = side;
@@ -1762,7 +1764,7 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   };
   uint64_t tbits;
   memcpy(&tbits, &threshold, sizeof(tbits));
-  if ((rc = run_graphed(ctx, ctx->g_mstep, (tbits * 31u) ^ (repack ? 2u : 0u), enqueue)) != HMMCU_OK) return rc;
+  if ((rc = run_graphed(ctx, ctx->g_mstep, (tbits * 31u) ^ (repack ? 2u : 0u) ^ (ctx->mstep_fork ? 4u : 0u), enqueue)) != HMMCU_OK) return rc;
   CK(cudaStreamSynchronize(ctx->st));
   for (int v = 0; v < V; v++) {
     if (sum_logp) sum_logp[v] = ctx->ctl_h[v];
