@@ -451,6 +451,39 @@ def write_model(path, ms, v=0):
         raise HmmCudaError("hmmh_write_model(%s) failed (%d)" % (path, rc))
 
 
+def read_model_streams(path, len_bytes=0, max_streams=6):
+    """A .hmm file with P >= 1 feature streams -> [ModelSet (V = 1) per stream] (hmmh_read_model_streams)."""
+    lib = load()
+    lib.hmmh_read_model_streams.argtypes = [C.c_char_p, C.POINTER(_CModel), C.c_int, C.POINTER(C.c_int), C.c_int]
+    arr = (_CModel * max_streams)()
+    P = C.c_int()
+    rc = lib.hmmh_read_model_streams(os.fsencode(path), arr, max_streams, C.byref(P), len_bytes)
+    if rc:
+        raise HmmCudaError("hmmh_read_model_streams(%s) failed (%d)" % (path, rc))
+    out = []
+    for p in range(P.value):
+        m = arr[p]
+        N, M, D = m.N, m.M, m.D
+        out.append(ModelSet(np.ctypeslib.as_array(m.A, (1, N, N)).copy(), np.ctypeslib.as_array(m.c, (1, N, M)).copy(),
+                            np.ctypeslib.as_array(m.mu, (1, N, M, D)).copy(), np.ctypeslib.as_array(m.inv_var, (1, N, M, D)).copy(),
+                            np.ctypeslib.as_array(m.det, (1, N, M)).copy(), [m.word.decode()]))
+        lib.hmmh_model_free(C.byref(arr[p]))
+    return out
+
+
+def write_model_streams(path, streams, v=0):
+    """[ModelSet per stream] (word v of each) -> one .hmm file with len(streams) feature streams."""
+    lib = load()
+    lib.hmmh_write_model_streams.argtypes = [C.c_char_p, C.POINTER(_CModel), C.c_int]
+    arr = (_CModel * len(streams))()
+    keep = [ms._cmodels() for ms in streams]
+    for p, cm in enumerate(keep):
+        C.memmove(C.byref(arr[p]), C.byref(cm[v]), C.sizeof(_CModel))
+    rc = lib.hmmh_write_model_streams(os.fsencode(path), arr, len(streams))
+    if rc:
+        raise HmmCudaError("hmmh_write_model_streams(%s) failed (%d)" % (path, rc))
+
+
 def read_model_set(paths, threads=0):
     """V .hmm files of one topology -> ModelSet through the bulk reader (hmmh_read_model_set)."""
     lib = load()

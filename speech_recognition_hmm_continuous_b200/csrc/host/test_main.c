@@ -77,6 +77,17 @@ int hmmh_test_main(int argc, char **argv) {
   for (int j = 0; j < K; j++) weight[j] = atof(argv[K + 2 + j]);
   const char *words_file = argv[argc - 2], *result = argv[argc - 1];
 
+  /* the reference's order of opening: model lists (R-FS:203), feature lists (R-FS:259-266), words file, result file */
+  for (int j = 0; j < K; j++) {
+    FILE *f = fopen(argv[2 + j], "rb");
+    if (!f) die("file %s not found \n", argv[2 + j]);
+    fclose(f);
+  }
+  for (int a = 2 + 2 * K; a < argc - 2; a++) {
+    FILE *f = fopen(argv[a], "r");
+    if (!f) die("file %s not found \n", argv[a]);
+    fclose(f);
+  }
   /* the spoken words: line i pairs with line i of every feature list */
   FILE *fw = fopen(words_file, "r");
   if (!fw) die("file %s not found \n", words_file);
@@ -88,16 +99,6 @@ int hmmh_test_main(int argc, char **argv) {
     strncpy(spoken[U++], w, WSTR);
   }
   fclose(fw);
-  for (int j = 0; j < K; j++) { /* opening_file_read of every list before any work, R-FS:203, 259-266 */
-    FILE *f = fopen(argv[2 + j], "rb");
-    if (!f) die("file %s not found \n", argv[2 + j]);
-    fclose(f);
-  }
-  for (int a = 2 + 2 * K; a < argc - 2; a++) {
-    FILE *f = fopen(argv[a], "r");
-    if (!f) die("file %s not found \n", argv[a]);
-    fclose(f);
-  }
   g_out = fopen(result, "w");
   if (!g_out) die("can't open file %s \n", result);
 

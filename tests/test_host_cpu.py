@@ -261,3 +261,72 @@ def test_model_set_reader_reads_reference_written_files(tmp_path):
         b = r.read_model(paths[w])
         for name, arr in (("A", back.A), ("c", back.c), ("mu", back.mu), ("iv", back.iv), ("det", back.det)):
             assert (arr[w] == getattr(b, name)).all()
+
+
+# ---- feature streams (param_number > 1): the P-stream .hmm file ----
+def test_multi_stream_model_file_round_trip_and_reference_layout(tmp_path, golden_dir):
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    streams = [api.ModelSet(*[g["trained_s%d_%s" % (p, k)][:1] for k in ("A", "c", "mu", "iv", "det")], words=["word0"]) for p in range(2)]
+    path = str(tmp_path / "p2.hmm")
+    api.write_model_streams(path, streams)
+    back = api.read_model_streams(path)
+    assert len(back) == 2 and back[0].words == ["word0"] and (back[0].M, back[0].D, back[1].M, back[1].D) == (2, 6, 3, 4)
+    for p in range(2):
+        for k in ("A", "c", "mu", "iv", "det"):
+            assert np.array_equal(getattr(back[p], k), getattr(streams[p], k)), (p, k)
+    # the layout is the reference's (T-FS:2058-2144): its own parser restated in oracle/ref.py reads the file ...
+    ref = r.read_model_streams(path)
+    assert len(ref) == 2 and ref[0].word == "word0" and np.array_equal(ref[1].mu, streams[1].mu[0])
+    # ... a single-stream reader refuses it, and a one-stream file written through the P-stream writer is the old format
+    with pytest.raises(api.HmmCudaError):
+        api.read_model(path)
+    one, one_s = str(tmp_path / "a.hmm"), str(tmp_path / "b.hmm")
+    api.write_model(one, streams[0])
+    api.write_model_streams(one_s, streams[:1])
+    assert open(one, "rb").read() == open(one_s, "rb").read()
+
+
+def test_multi_stream_model_file_written_by_reference(tmp_path, golden_dir):
+    """The reference trainer run with two streams writes a file our reader takes (and vice versa: byte-identical rewrite)."""
+    if not r.available("p2"):
+        pytest.skip("compiled two-stream reference not present")
+    import subprocess
+    g = np.load(os.path.join(golden_dir, "synth_p2.npz"))
+    off, lists = g["off"], []
+    for p in range(2):
+        files = []
+        for u in np.nonzero(g["train_labels"] == 0)[0]:
+            files.append(str(tmp_path / ("s%d_%d.bin" % (p, u))))
+            api.write_features(files[-1], g["x%d" % p][off[u]:off[u + 1]])
+        lists.append(str(tmp_path / ("l%d.txt" % p)))
+        open(lists[-1], "w").write("\n".join(files) + "\n")
+    hmm = str(tmp_path / "ref.hmm")
+    subprocess.run([os.path.join(r.REF_DIR, "hmm_fs_p2"), "word0", str(int(g["N"])), "2", str(g["M"][0]), str(g["M"][1]), lists[0], lists[1], hmm],
+                   stdout=subprocess.DEVNULL, check=True)
+    back = api.read_model_streams(hmm)
+    for p in range(2):
+        for k in ("A", "c", "mu", "iv", "det"):
+            assert np.array_equal(getattr(back[p], k)[0], g["trained_s%d_%s" % (p, k)][0]), (p, k)
+    again = str(tmp_path / "again.hmm")
+    api.write_model_streams(again, back)
+    assert open(again, "rb").read() == open(hmm, "rb").read()
+
+
+# ---- drop-in programs: argument and file errors happen before any device work (reference: message on stdout, exit(1)) ----
+def test_cli_usage_and_file_errors():
+    import subprocess
+    bindir = os.path.join(os.path.dirname(api.LIB_PATH), "bin")
+    tr, te = os.path.join(bindir, "hmm_continuous_fs"), os.path.join(bindir, "recognition_continuous_fs")
+    p = subprocess.run([tr, "w", "5"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and p.stdout.decode().startswith("Usage: hmm_continuous_fs word states_number param_number")
+    p = subprocess.run([te, "1"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and p.stdout.decode().startswith("Usage: recognition_continuous_fs models_number")
+    p = subprocess.run([tr, "w", "5", "1", "3", "/nonexistent/list.txt", "/tmp/o.hmm"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and "file /nonexistent/list.txt not found" in p.stdout.decode()
+    p = subprocess.run([tr, "w", "5", "2", "3", "3", "/nonexistent/a.txt", "/nonexistent/b.txt", "/tmp/o.hmm"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and "file /nonexistent/a.txt not found" in p.stdout.decode()
+    # the recogniser opens the model lists first, then the feature lists, then the words file (R-FS:203-266)
+    p = subprocess.run([te, "1", "/nonexistent/m.txt", "1", "/nonexistent/f.txt", "/nonexistent/w.txt", "/tmp/r.txt"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and "file /nonexistent/m.txt not found" in p.stdout.decode()
+    p = subprocess.run([te, "2", "/nonexistent/m.txt", "1", "/nonexistent/f.txt", "/nonexistent/w.txt", "/tmp/r.txt"], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and "does not match the argument list" in p.stdout.decode()
