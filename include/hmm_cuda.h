@@ -59,7 +59,8 @@ void hmmcu_host_free(void *p);
  * identical call on; "ws_emis" / "ws_acc": 0 = the older single-buffered tensor-core kernels; "seg_fb": 0 = the windowed
  * forward-backward kernel instead of the time-parallel one; "wide_fb": 0 never / 1 (default) from 1,536 utterances on /
  * 2 always the thread-per-chain forward-backward kernels;
- * "upload_chunks": chunks hmmcu_set_features splits the host-to-device copy into (packing overlaps the copy). */
+ * "upload_chunks": chunks hmmcu_set_features splits the host-to-device copy into (packing overlaps the copy);
+ * "mstep_fork": 1 (default) = the accuracy-guard scan and one of the two model packers of hmmcu_mstep run on side streams. */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 
 /* ---------------------------------------------------------------- inputs ----------------- */
