@@ -168,3 +168,26 @@ def test_two_stream_recognition_matches_reference(golden_dir):
             s = o.forward_score_streams(ms, [x[off[u]:off[u + 1]] for x in xs])
             assert abs(s - g["score"][u, v]) <= 1e-6 + 1e-9 * abs(s)                       # printed with %f
     assert (np.argmax(g["score"], axis=1) == g["test_labels"]).all()
+
+
+def test_multi_stream_restatement_reduces_to_the_single_stream_oracle():
+    """oracle.estep_streams (numpy, on top of the pinned primitives) with ONE stream is the C restatement's E-step."""
+    cen, s = synth.make_centres(1, 4, 3, 7, seed=3)
+    x, off = synth.make_utterances(cen, s, [0] * 5, seed=4, tmin=30, tmax=50)
+    d = synth.make_models(cen, s)
+    m = o.Model(d["A"][0], d["c"][0], d["mu"][0], d["iv"][0], d["det"][0])
+    want, lp = o.estep(m, x, off)
+    (got,), lps = o.estep_streams([m], [x], off)
+    assert np.allclose(lps, lp, rtol=1e-13)
+    for k in ("num_trans", "den_trans", "den_mix", "S0", "S1", "S2c"):
+        assert np.allclose(getattr(got, k), getattr(want, k), rtol=1e-10, atol=1e-12 * np.abs(getattr(want, k)).max()), k
+    assert abs(got.sum_logp - want.sum_logp) <= 1e-12 * abs(want.sum_logp) and got.n_utt == want.n_utt
+    # the order of the streams does not matter to the product (up to rounding)
+    cen2, s2 = synth.make_centres(1, 4, 2, 5, seed=8)
+    x2, off2 = synth.make_utterances(cen2, s2, [0] * 5, seed=4, tmin=30, tmax=50)
+    assert np.array_equal(off, off2)
+    d2 = synth.make_models(cen2, s2)
+    m2 = o.Model(d["A"][0], d2["c"][0], d2["mu"][0], d2["iv"][0], d2["det"][0])
+    (a1, a2), lpa = o.estep_streams([m, m2], [x, x2], off)
+    (b2, b1), lpb = o.estep_streams([m2, m], [x2, x], off)
+    assert np.allclose(lpa, lpb, rtol=1e-12) and np.allclose(a1.S1, b1.S1, rtol=1e-9, atol=1e-9) and np.allclose(a2.S0, b2.S0, rtol=1e-9, atol=1e-12)
