@@ -188,7 +188,7 @@ void hmmcu_enable_timing(hmmcu_ctx *ctx, int on);
 
 typedef struct hmmh_model {
   char word[64];   /* reference: MAX_WORD_SIZE 50 */
-  int N, M, D;     /* states, mixtures per state, coefficients (param_number is 1) */
+  int N, M, D;     /* states, mixtures per state, coefficients of ONE feature stream (a P-stream model is P of these sharing A and word) */
   double *A;       /* [N][N] */
   double *c;       /* [N][M] */
   double *mu;      /* [N][M][D] */
