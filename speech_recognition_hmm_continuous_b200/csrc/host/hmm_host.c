@@ -392,9 +392,9 @@ static int upload_models(hmmcu_ctx *ctx, const hmmh_model *models, int V) {
   double *A = (double *)malloc(sizeof(double) * V * N * N), *c = (double *)malloc(sizeof(double) * V * g);
   double *mu = (double *)malloc(sizeof(double) * V * g * D), *iv = (double *)malloc(sizeof(double) * V * g * D);
   double *det = (double *)malloc(sizeof(double) * V * g);
-  if (!A || !c || !mu || !iv || !det) return HMMCU_ENOMEM;
+  if (!A || !c || !mu || !iv || !det) { free(A); free(c); free(mu); free(iv); free(det); return HMMCU_ENOMEM; }
   for (int v = 0; v < V; v++) {
-    if (models[v].N != N || models[v].M != M || models[v].D != D) return HMMCU_EINVAL;
+    if (models[v].N != N || models[v].M != M || models[v].D != D) { free(A); free(c); free(mu); free(iv); free(det); return HMMCU_EINVAL; }
     memcpy(A + (size_t)v * N * N, models[v].A, sizeof(double) * N * N);
     memcpy(c + v * g, models[v].c, sizeof(double) * g);
     memcpy(mu + v * g * D, models[v].mu, sizeof(double) * g * D);
@@ -420,7 +420,10 @@ int hmmh_train_streams(hmmcu_ctx *const *ctxs, int P, hmmh_model *models, int V,
   int32_t *updated = (int32_t *)malloc(sizeof(int32_t) * V), *updated_q = (int32_t *)malloc(sizeof(int32_t) * V);
   char *active = (char *)malloc(V);
   int32_t *map = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
-  if (!probab || !nutt || !probab_q || !nutt_q || !updated || !updated_q || !active || !map) return HMMCU_ENOMEM;
+  if (!probab || !nutt || !probab_q || !nutt_q || !updated || !updated_q || !active || !map) {
+    free(probab); free(nutt); free(probab_q); free(nutt_q); free(updated); free(updated_q); free(active); free(map);
+    return HMMCU_ENOMEM;
+  }
   for (int v = 0; v < V; v++) { active[v] = 1; if (iterations) iterations[v] = 0; if (mean_logp) mean_logp[v] = 0.0; }
   /* the model sets go up once; the E-step, the all-reduce and the M-step then stay on the device */
   int rc = HMMCU_OK;
