@@ -38,3 +38,19 @@ def test_reader_pools_are_clean_under_sanitizers(tmp_path, san):
     out = err.stdout.decode()
     assert err.returncode == 0 and "Sanitizer" not in out, out[-2000:]
     assert "sink failure: rc=3" in out and "wrong width: rc=5 bad=120" in out and "missing: rc=5 bad=120" in out
+
+
+def test_host_model_code_is_clean_under_asan_ubsan(tmp_path):
+    """Initial-model builder (M = 1..7: doubling, partial splits), host M-step, one- and two-stream .hmm files."""
+    exe = str(tmp_path / "host_model")
+    cmd = ["gcc", "-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-DWITH_HMM_HOST", "-I", os.path.join(ROOT, "include"),
+           os.path.join(NATIVE, "host_model.c"), os.path.join(NATIVE, "device_stubs.c"), os.path.join(HOST, "hmm_host.c"),
+           os.path.join(HOST, "ingest.c"), os.path.join(HOST, "modelset.c"), "-o", exe, "-lpthread", "-lm"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if p.returncode != 0:
+        pytest.skip("no address/undefined sanitizer toolchain: %s" % p.stdout.decode()[-200:])
+    scratch = tmp_path / "data"
+    scratch.mkdir()
+    r = subprocess.run([exe, str(scratch)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    out = r.stdout.decode()
+    assert r.returncode == 0 and "host model code: bad=0" in out and "Sanitizer" not in out and "runtime error" not in out, out[-2000:]
