@@ -118,8 +118,10 @@ int hmmh_train_main(int argc, char **argv) {
   if (argc == 2 * P + 6) {
     int Pf = 0;
     if (hmmh_read_model_streams(argv[argc - 1], m, P, &Pf, 0) != HMMCU_OK || Pf != P) die("reading error on file %s \n", argv[argc - 1]);
-    for (int p = 0; p < P; p++)
+    for (int p = 0; p < P; p++) {
       if (m[p].D != D[p]) die("reading error on file %s \n", argv[argc - 1]);
+      M[p] = m[p].M; /* the model's own sizes go into the report */
+    }
   } else {
     for (int p = 0; p < P; p++) {
       if (hmmh_model_alloc(&m[p], N, M[p], D[p]) != HMMCU_OK) die("error on allocating memory. %s\n", "");
@@ -165,7 +167,7 @@ int hmmh_train_main(int argc, char **argv) {
   strftime(t1, sizeof(t1), "%d-%h-%Y %X", localtime(&end));
 
   if (hmmh_write_model_streams(out, m, P) != HMMCU_OK) die("can't open file %s \n", out);
-  write_report(txt, out, word, N, P, M, list, t0, t1, cpu, U, mean, iters);
+  write_report(txt, out, word, m[0].N, P, M, list, t0, t1, cpu, U, mean, iters);
   printf("\r\nmean probability: %f, iterations: %d\r\n", mean, iters);
   for (int p = 0; p < P; p++) {
     hmmh_model_free(&m[p]);

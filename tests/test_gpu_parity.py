@@ -746,3 +746,32 @@ def test_time_parallel_and_windowed_forward_backward_agree():
     for u in range(2):
         want = o.forward_score(_oracle_model(msl, 0), xl[offl[u]:offl[u + 1]])
         assert abs(lpl[u] - want) <= RTOL * abs(want)
+
+
+# ------------------------------------------------- resume from a model file (optional last argument) ----
+def test_cli_resumes_from_an_initial_model(tmp_path):
+    """hmm_continuous_fs ... out.hmm initial.hmm (T-FS:216-222; the reference reads argv[argc] there and would crash,
+    SURVEY section 5 'checkpoint / resume'): training continues from the model in the file.  Expected values: the oracle's EM
+    loop started from the same file."""
+    N, M = 4, 2
+    cen, sc = synth.make_centres(1, N, M, 39, seed=321)
+    x, off = synth.make_utterances(cen, sc, [0] * 6, seed=322, tmin=50, tmax=80)
+    files = []
+    for u in range(len(off) - 1):
+        files.append(str(tmp_path / ("u%d.bin" % u)))
+        api.write_features(files[-1], x[off[u]:off[u + 1]])
+    lst = str(tmp_path / "list.txt")
+    open(lst, "w").write("\n".join(files) + "\n")
+    exe = os.path.join(os.path.dirname(api.LIB_PATH), "bin", "hmm_continuous_fs")
+    first, second = str(tmp_path / "first.hmm"), str(tmp_path / "second.hmm")
+    subprocess.run([exe, "word", str(N), "1", str(M), lst, first], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([exe, "word", str(N), "1", str(M), lst, second, first], check=True, stdout=subprocess.DEVNULL)
+    mean2, its2 = r.parse_train_report(second[:-4] + ".txt")
+    start = r.read_model(first)
+    its_o, mean_o = o.train(start, x, off)
+    assert abs(its2 - its_o) <= 1 and abs(mean2 - mean_o) <= (RTOL if its2 == its_o else 2e-3) * abs(mean_o)
+    got = api.read_model(second)
+    if its2 == its_o:
+        _assert_params_close(got, 0, start)   # `start` was trained in place by the oracle
+    rep = open(second[:-4] + ".txt").read()
+    assert "number of states: %d \n" % N in rep and "number of mixtures 1: %d \n" % M in rep
