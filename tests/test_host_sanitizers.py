@@ -29,6 +29,8 @@ def test_reader_pools_are_clean_under_sanitizers(tmp_path, san):
     scratch.mkdir()
     ok = subprocess.run([_build(tmp_path, san, "pools_ok"), str(scratch)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
     out = ok.stdout.decode()
+    if "unexpected memory mapping" in out or "failed to allocate" in out:   # a sanitizer runtime this kernel / container cannot host
+        pytest.skip(out[-200:])
     assert ok.returncode == 0 and "Sanitizer" not in out, out[-2000:]
     lines = [l for l in out.splitlines() if l.startswith("rc=")]
     assert len(lines) == 3 and all("rc=0" in l and "sum_ok=1" in l and "frames=30000 got=30000" in l for l in lines), out
