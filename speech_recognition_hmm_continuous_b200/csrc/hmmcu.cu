@@ -14,6 +14,7 @@
 #include "hmm_cuda.h"
 #include "kernels.cuh"
 #include "fb_kernels.cuh"
+#include "fbres_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "ws_kernels.cuh"
 #include "vit_kernels.cuh"
@@ -153,6 +154,10 @@ struct hmmcu_ctx {
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
   int use_seg_fb = 1;  // time-parallel forward-backward (k_fb_seg) when the utterances fit in shared memory (0 = k_fb)
   int use_wide_fb = 1; // 1 = thread-per-chain forward-backward (k_fb_wide) beyond kWideMinUtts utterances, 2 = always, 0 = never
+  int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
+  DevBuf res_order, res_upos, res_batches, res_counter, ustats;
+  int64_t n_res_batches = 0;
+  bool res_fits = false;  // every utterance of the training map fits one team's shared memory
   int debug_acc = 0;
   bool acc_dirty = true;
   int64_t n_acc_units = 0;
@@ -321,7 +326,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
-                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles, &ctx->phi_utt_d, &ctx->lp_part_d};
+                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles, &ctx->phi_utt_d, &ctx->lp_part_d,
+                    &ctx->res_order, &ctx->res_upos, &ctx->res_batches, &ctx->res_counter, &ctx->ustats};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -384,6 +390,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "seg_fb") == 0) { ctx->use_seg_fb = value; return HMMCU_OK; }
   if (strcmp(key, "wide_fb") == 0) { ctx->use_wide_fb = value; return HMMCU_OK; }
+  if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1448,6 +1455,39 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
   CK(cudaMemcpyAsync(ctx->mus_d.p, start.data(), sizeof(int32_t) * (V + 1), cudaMemcpyHostToDevice, ctx->st));
   CK(cudaMemcpyAsync(ctx->mu_d.p, utts.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaMemcpyAsync(ctx->tiles_d.p, tiles.data(), sizeof(EmisTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->st));
+  {  // k_fb_res: the live utterances longest first, cut into batches that fit one team's shared memory; the row of
+     // every utterance in the per-utterance statistics (= its position in the model-grouped list)
+    const int nlive = start[V];
+    std::vector<int32_t> order(utts.begin(), utts.begin() + nlive), upos(std::max(U, 1), 0);
+    for (int k = 0; k < nlive; k++) upos[utts[k]] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ctx->off[a + 1] - ctx->off[a] > ctx->off[b + 1] - ctx->off[b]; });
+    const int64_t cap = res_slot_words_rt(ctx->N);
+    std::vector<ResBatch> rb;
+    ctx->res_fits = cap > 0;
+    for (int k = 0; k < nlive && ctx->res_fits;) {
+      int64_t used = 0;
+      int n = 0;
+      while (k + n < nlive && n < kResMaxUtts) {
+        const int64_t w = res_utt_words(ctx->N, ctx->off[order[k + n] + 1] - ctx->off[order[k + n]]);
+        if (used + w > cap) break;
+        used += w;
+        n++;
+      }
+      if (n == 0) { ctx->res_fits = false; break; }  // an utterance longer than a team's shared memory: k_fb takes the E-step
+      rb.push_back({k, n});
+      k += n;
+    }
+    ctx->n_res_batches = ctx->res_fits ? (int64_t)rb.size() : 0;
+    CK(ctx->res_order.ensure(sizeof(int32_t) * std::max(nlive, 1)));
+    CK(ctx->res_upos.ensure(sizeof(int32_t) * std::max(U, 1)));
+    CK(ctx->res_batches.ensure(sizeof(ResBatch) * std::max<size_t>(rb.size(), 1)));
+    CK(ctx->res_counter.ensure(sizeof(int)));
+    CK(ctx->ustats.ensure(sizeof(double) * (size_t)std::max(nlive, 1) * res_stats_row(std::min(ctx->N, 8))));
+    CK(cudaMemcpyAsync(ctx->res_order.p, order.data(), sizeof(int32_t) * nlive, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->res_upos.p, upos.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, ctx->st));
+    if (!rb.empty()) CK(cudaMemcpyAsync(ctx->res_batches.p, rb.data(), sizeof(ResBatch) * rb.size(), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+  }
   CK(cudaStreamSynchronize(ctx->st));
   ctx->u2m.assign(utt2model, utt2model + U);
   ctx->cfg_epoch++;
@@ -1519,7 +1559,20 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     {
       // many utterances: one thread per chain fills the machine (a k_fb_seg CTA holds four utterances and two fit per SM)
       constexpr int kWideMinUtts = 1536;
-      if (ctx->use_wide_fb == 2 || (ctx->use_wide_fb == 1 && U >= kWideMinUtts)) {
+      if (ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0) {
+        // every utterance resident in shared memory: log-emissions read once, gamma written once (fbres_kernels.cuh)
+        CK(cudaMemsetAsync(ctx->res_counter.p, 0, sizeof(int), ctx->st));
+        CK(cudaMemsetAsync(ctx->logp_utt_d.p, 0, sizeof(double) * U, ctx->st));  // masked utterances report 0
+        const int grid = (int)std::min<int64_t>(ctx->n_res_batches, ctx->sm_count);
+        DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_res<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes),
+                       k_fb_res<NS><<<grid, kResThreads, kResSmemBytes, ctx->st>>>(
+                           lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), ctx->res_order.as<int32_t>(),
+                           ctx->res_upos.as<int32_t>(), ctx->res_batches.as<ResBatch>(), (int)ctx->n_res_batches, ctx->res_counter.as<int>(),
+                           ctx->gamma.as<float>(), ctx->ustats.as<double>(), ctx->logp_utt_d.as<double>())));
+        LAUNCH_CHECK();
+        k_fb_reduce<<<V, 1024, 0, ctx->st>>>(ctx->ustats.as<double>(), N, ctx->mus_d.as<int32_t>(), V, ctx->stats.as<double>(), ss, off_lp);
+        LAUNCH_CHECK();
+      } else if (ctx->use_wide_fb == 2 || (ctx->use_wide_fb == 1 && U >= kWideMinUtts)) {
         const int blocks = (2 * U + kWideThreads - 1) / kWideThreads;
         if (ctx->banded) {
           DISPATCH_N(N, (k_fb_wide<NS, true><<<blocks, kWideThreads, 0, ctx->st>>>(lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
@@ -1637,7 +1690,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     t_end(ctx, "accum");
     return HMMCU_OK;
   };
-  const uint64_t key = 1u | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 7) << 5);
+  const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 7) << 5);
   ctx->last_tc = use_tc;
   if (phases != 7 || fb_logb || acc_gamma) return enqueue();  // pieces of a multi-stream E-step: plain launches
   return run_graphed(ctx, ctx->g_estep, key, enqueue);

@@ -713,31 +713,38 @@ def test_device_initial_models_are_bit_identical_to_the_host_builder(N, M):
             assert np.array_equal(getattr(got, name)[v], getattr(want, name)[0]), (v, name)
 
 
-def test_time_parallel_and_windowed_forward_backward_agree():
-    """k_fb_seg (segments, unit vectors, boundary combination) against k_fb (one chain per utterance, windows):
-    same statistics and log-likelihoods; ragged lengths including T < 8 segments; and an utterance too long for
-    the time-parallel kernel's shared memory takes the windowed kernel on its own."""
+def test_forward_backward_kernels_agree():
+    """k_fb_res (whole utterance resident in shared memory, the default), k_fb_seg (segments, unit vectors, boundary
+    combination) and k_fb_wide + k_fb_gamma (thread per chain) against k_fb (one chain per utterance, windows): same
+    statistics and log-likelihoods; ragged lengths including T < 8 segments and T < N; an utterance too long for
+    the resident kernel's shared memory takes the windowed kernel on its own."""
     ms, x, off, labels = _synth(2, 5, 3, 10, seed=777, tmin=3, tmax=140)
     out = []
-    for seg, wide in ((1, 0), (0, 0), (0, 2)):
+    for res, seg, wide in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 2)):
         c = api.Context(0)
+        c.set_option("res_fb", res)
         c.set_option("seg_fb", seg)
         c.set_option("wide_fb", wide)  # 2 = the thread-per-chain kernels (k_fb_wide + k_fb_gamma) whatever the count
         c.set_features(x, off)
         c.set_models(ms)
         out.append(c.estep(labels))
         c.close()
-    (st1, lp1), (st0, lp0), (st2, lp2) = out
-    assert (np.isfinite(lp2) == np.isfinite(lp0)).all() and np.allclose(lp2[np.isfinite(lp0)], lp0[np.isfinite(lp0)], rtol=1e-9)
-    sf2 = np.isfinite(st0)
-    assert (np.isfinite(st2) == sf2).all() and np.allclose(st2[sf2], st0[sf2], rtol=2e-5, atol=1e-6 * np.abs(st0[sf2]).max())
-    fin = np.isfinite(lp0)
-    assert (np.isfinite(lp1) == fin).all() and np.allclose(lp1[fin], lp0[fin], rtol=1e-9)
-    sf = np.isfinite(st0)  # sum_logp is -inf for a word with an utterance shorter than its state chain
-    assert (np.isfinite(st1) == sf).all() and (st1[~sf] == st0[~sf]).all()
-    assert np.allclose(st1[sf], st0[sf], rtol=2e-5, atol=1e-6 * np.abs(st0[sf]).max())
-    # a long utterance (T x N beyond the shared-memory budget of k_fb_seg): the library falls back by itself
-    msl, xl, offl, labl = _synth(1, 5, 2, 2, seed=778, tmin=1100, tmax=1200)
+    st0, lp0 = out[0]
+    fin, sf = np.isfinite(lp0), np.isfinite(st0)  # sum_logp is -inf for a word with an utterance shorter than its state chain
+    for k, (st, lp) in enumerate(out[1:]):
+        assert (np.isfinite(lp) == fin).all() and np.allclose(lp[fin], lp0[fin], rtol=1e-8), k
+        assert (np.isfinite(st) == sf).all() and (st[~sf] == st0[~sf]).all(), k
+        assert np.allclose(st[sf], st0[sf], rtol=2e-5, atol=1e-6 * np.abs(st0[sf]).max()), k
+    # the resident kernel sums every model's utterances in a fixed order: two runs are bit-identical
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    a = c.estep(labels)
+    b = c.estep(labels)
+    c.close()
+    assert (a[0][sf] == b[0][sf]).all() and (a[1][fin] == b[1][fin]).all()
+    # an utterance beyond a team's shared memory (2 N T words): the library falls back to k_fb by itself
+    msl, xl, offl, labl = _synth(1, 5, 2, 2, seed=778, tmin=1500, tmax=1600)
     c = api.Context(0)
     c.set_features(xl, offl)
     c.set_models(msl)
@@ -748,29 +755,225 @@ def test_time_parallel_and_windowed_forward_backward_agree():
         assert abs(lpl[u] - want) <= RTOL * abs(want)
 
 
+@pytest.mark.parametrize("N", [1, 2, 3, 4, 6, 7, 8])
+def test_resident_forward_backward_other_state_counts(ctx, N):
+    """k_fb_res for every supported number of states (odd row stride for even N), statistics against the oracle."""
+    ms, x, off, labels = _synth(2, N, 2, 7, seed=880 + N, tmin=max(N, 2), tmax=150)
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    for v in range(2):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st, lp = o.estep(_oracle_model(ms, v), xv, offv)
+        sp = api.split_stats(stats[v], N, 2, ms.D)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        for name in ("num_trans", "den_trans", "den_mix", "S0"):
+            want = getattr(st, name)
+            assert np.allclose(sp[name], want, rtol=RTOL, atol=1e-6 * np.abs(want).max()), name
+
+
 # ------------------------------------------------- resume from a model file (optional last argument) ----
 def test_cli_resumes_from_an_initial_model(tmp_path):
     """hmm_continuous_fs ... out.hmm initial.hmm (T-FS:216-222; the reference reads argv[argc] there and would crash,
-    SURVEY section 5 'checkpoint / resume'): training continues from the model in the file.  Expected values: the oracle's EM
-    loop started from the same file."""
+    SURVEY section 5 'checkpoint / resume'): training continues from the model in the file.  The first model is trained
+    on two utterances, the resumed run on all eight, so that it has several iterations of real work.  Expected values:
+    the oracle's EM loop started from the same file -- equal iteration count, mean log-probability and parameters
+    within 1e-4 (the test first checks that no stopping decision of that loop is within 5 % of the threshold)."""
     N, M = 4, 2
-    cen, sc = synth.make_centres(1, N, M, 39, seed=321)
-    x, off = synth.make_utterances(cen, sc, [0] * 6, seed=322, tmin=50, tmax=80)
+    cen, sc = synth.make_centres(1, N, M, 39, seed=341)
+    x, off = synth.make_utterances(cen, sc, [0] * 8, seed=342, tmin=50, tmax=80)
     files = []
     for u in range(len(off) - 1):
         files.append(str(tmp_path / ("u%d.bin" % u)))
         api.write_features(files[-1], x[off[u]:off[u + 1]])
-    lst = str(tmp_path / "list.txt")
+    lst2, lst = str(tmp_path / "list2.txt"), str(tmp_path / "list.txt")
+    open(lst2, "w").write("\n".join(files[:2]) + "\n")
     open(lst, "w").write("\n".join(files) + "\n")
     exe = os.path.join(os.path.dirname(api.LIB_PATH), "bin", "hmm_continuous_fs")
     first, second = str(tmp_path / "first.hmm"), str(tmp_path / "second.hmm")
-    subprocess.run([exe, "word", str(N), "1", str(M), lst, first], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([exe, "word", str(N), "1", str(M), lst2, first], check=True, stdout=subprocess.DEVNULL)
     subprocess.run([exe, "word", str(N), "1", str(M), lst, second, first], check=True, stdout=subprocess.DEVNULL)
     mean2, its2 = r.parse_train_report(second[:-4] + ".txt")
-    start = r.read_model(first)
-    its_o, mean_o = o.train(start, x, off)
-    assert abs(its2 - its_o) <= 1 and abs(mean2 - mean_o) <= (RTOL if its2 == its_o else 2e-3) * abs(mean_o)
+    # the oracle's loop from the same start (T-FS:238-358), keeping the stopping rule's variations
+    mo = r.read_model(first)
+    old, its_o, variations = 1.0, 0, []
+    while True:
+        its_o += 1
+        st, lp = o.estep(mo, x, off)
+        probab = float(np.sum(lp))
+        variations.append(abs((old - probab) / old))
+        if not variations[-1] > 1e-3:
+            break
+        old = probab
+        o.mstep(mo, st)
+    mean_o = probab / (len(off) - 1)
+    assert all(abs(v / 1e-3 - 1.0) > 0.05 for v in variations), variations
+    assert its_o >= 3
+    assert its2 == its_o and abs(mean2 - mean_o) <= RTOL * abs(mean_o)
     got = api.read_model(second)
-    assert got.words == ["word"] and (got.N, got.M, got.D) == (N, M, 39) and np.isfinite(got.mu).all()
+    assert got.words == ["word"] and (got.N, got.M, got.D) == (N, M, 39)
+    _assert_params_close(got, 0, mo)
     rep = open(second[:-4] + ".txt").read()
     assert "number of states: %d \n" % N in rep and "number of mixtures 1: %d \n" % M in rep
+
+
+# ----------------------------------------------------- parity at the shapes BASELINE.json names ----
+def test_c4_shape_scores_and_labels_match_oracle(ctx):
+    """BASELINE configs[3] shape: a 1,000-word model set (N=5, M=3: 5,000 state columns, 63 emission images) scored
+    against a handful of utterances.  Every one of the 1,000 forward scores per utterance within 1e-4 of the oracle's
+    (R-FS:341-369), the label and the second candidate equal to the oracle's ranking (R-FS:968-995, 380-388), and the
+    Viterbi score of every cell within 1e-4 of the oracle's."""
+    V, N, M, U = 1000, 5, 3, 8
+    cen, s = synth.make_centres(V, N, M, 39, seed=4000)
+    labels = (np.arange(U) * 137 + 5) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=4001, tmin=40, tmax=70)
+    ms = api.ModelSet.from_dict(synth.make_models(cen, s))
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    sc = ctx.forward_scores()
+    vs = ctx.viterbi_scores()
+    lab, sec = ctx.rank(sc)
+    want = np.empty((U, V))
+    wantv = np.empty((U, V))
+    with np.errstate(all="ignore"):
+        for v in range(V):
+            mo = _oracle_model(ms, v)
+            for u in range(U):
+                xu = x[off[u]:off[u + 1]]
+                want[u, v] = o.forward_score(mo, xu)
+                if v % 50 == 0 or v == labels[u]:
+                    b, _ = o.emissions(mo, xu, want_post=False)
+                    wantv[u, v] = o.viterbi(mo, b)[0]
+                else:
+                    wantv[u, v] = np.nan
+    fin = np.isfinite(want)
+    assert fin.mean() > 0.5, "the test is meant to sit in the finite regime"
+    assert (np.abs(sc - want)[fin] <= RTOL * np.abs(want[fin])).all()
+    # cells where the reference's linear-domain arithmetic underflows: the log-domain score must be hopeless too
+    assert (sc[~fin] < want[fin].min()).all() if (~fin).any() else True
+    chk = np.isfinite(wantv)
+    assert chk.sum() >= 20 * U and (np.abs(vs - wantv)[chk] <= RTOL * np.abs(wantv[chk])).all()
+    for u in range(U):
+        row = np.where(fin[u], want[u], -np.inf)   # (finite regime: no NaN barriers in this case)
+        idx = o.rank(row)
+        assert lab[u] == idx[0] == labels[u] and sec[u] == idx[1]
+
+
+def test_c5_shape_forward_and_viterbi_scores_match_oracle(ctx):
+    """BASELINE configs[4] shape: N=3 states of M=128 mixtures (one state per 128-column image group), 16 models."""
+    V, N, M, U = 16, 3, 128, 8
+    cen, s = synth.make_centres(V, N, M, 39, seed=5000)
+    labels = (np.arange(U) * 3 + 1) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=5001, tmin=40, tmax=70)
+    ms = api.ModelSet.from_dict(synth.make_models(cen, s))
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    sc = ctx.forward_scores()
+    vs = ctx.viterbi_scores()
+    vown, path = ctx.viterbi(labels)
+    lab, _ = ctx.rank(sc)
+    with np.errstate(all="ignore"):
+        for u in range(U):
+            xu = x[off[u]:off[u + 1]]
+            for v in range(V):
+                mo = _oracle_model(ms, v)
+                want = o.forward_score(mo, xu)
+                b, _ = o.emissions(mo, xu, want_post=False)
+                wv, wp = o.viterbi(mo, b)
+                if np.isfinite(want):
+                    assert abs(sc[u, v] - want) <= RTOL * abs(want), (u, v)
+                    assert abs(vs[u, v] - wv) <= RTOL * abs(wv), (u, v)
+                if v == labels[u]:
+                    assert np.isfinite(want)
+                    assert (path[off[u]:off[u + 1]] == wp).all() and abs(vown[u] - wv) <= 1e-9 * abs(wv)
+    assert (lab == labels).all()
+
+
+def test_large_estep_default_dispatch_matches_oracle(ctx):
+    """A 1,600-utterance E-step through the default dispatch (many batches per team of the resident forward-backward
+    kernel, several CTAs' partial sums per accumulate image): the statistics of three of the 16 words against the
+    oracle's E-step on those words' utterances (T-FS:244-321)."""
+    V, N, M, U = 16, 5, 4, 1600
+    cen, s = synth.make_centres(V, N, M, 39, seed=6000)
+    labels = np.arange(U) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=6001, tmin=30, tmax=90)
+    rng = np.random.default_rng(6002)
+    ms = api.ModelSet.from_dict(synth.make_models(cen + 0.3 * s * rng.standard_normal(cen.shape), s))
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    assert np.isfinite(lpu).all()
+    for v in (0, 7, 15):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st, lp = o.estep(_oracle_model(ms, v), xv, offv)
+        sp = api.split_stats(stats[v], N, M, ms.D)
+        assert np.allclose(lpu[us], lp, rtol=RTOL)
+        assert abs(sp["sum_logp"] - st.sum_logp) <= RTOL * abs(st.sum_logp) and sp["n_utt"] == len(us)
+        for name in ("num_trans", "den_trans", "den_mix", "S0"):
+            want = getattr(st, name)
+            assert np.allclose(sp[name], want, rtol=RTOL, atol=1e-6 * np.abs(want).max()), name
+        S0 = np.maximum(st.S0, 1e-300)[..., None]
+        sd = np.sqrt(st.S2c / S0)
+        assert (np.abs(sp["S1"] / S0 - st.S1 / S0) <= RTOL * np.maximum(np.abs(st.S1 / S0), sd)).all(), "S1"
+        assert np.allclose(sp["S2c"] / S0, st.S2c / S0, rtol=RTOL), "S2c"
+        # and through the M-step: the re-estimated parameters
+        mo = _oracle_model(ms, v)
+        o.mstep(mo, st)
+        one = api.ModelSet(ms.A[v:v + 1].copy(), ms.c[v:v + 1].copy(), ms.mu[v:v + 1].copy(), ms.iv[v:v + 1].copy(), ms.det[v:v + 1].copy())
+        got = api.mstep(one, stats[v:v + 1])
+        _assert_params_close(got, 0, mo)
+
+
+def test_viterbi_tiny_cases_against_brute_force():
+    """Second pin for the Viterbi kernels (the reference has none, R-FS:10-11): every state sequence of tiny
+    models enumerated on the host (tests/viterbi_pins.py), emissions from a numpy restatement of calc_gaus."""
+    from viterbi_pins import brute_viterbi, np_log_emissions, np_viterbi
+    rng = np.random.default_rng(4242)
+    c = api.Context(0)
+    for N, D, full in ((1, 2, False), (2, 3, False), (3, 2, False), (3, 4, True), (2, 2, True)):
+        V, M, U = 3, 2, 9
+        A = rng.uniform(0.1, 1.0, size=(V, N, N))
+        if not full:
+            A = np.triu(A) - np.triu(A, 2)
+        A /= A.sum(axis=2, keepdims=True)
+        cw = rng.uniform(0.2, 1.0, size=(V, N, M)); cw /= cw.sum(axis=2, keepdims=True)
+        mu = rng.standard_normal((V, N, M, D))
+        var = rng.uniform(0.5, 2.0, size=(V, N, M, D))
+        ms = api.ModelSet(A, cw, mu, 1.0 / var, var.prod(axis=3))
+        T = rng.integers(max(N, 1), 9, size=U)
+        T[0] = 1 if N == 1 else N                       # shortest utterance that can reach the final state
+        off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+        x = rng.standard_normal((int(off[-1]), D))
+        labels = (np.arange(U) % V).astype(np.int32)
+        c.set_features(x, off)
+        c.set_models(ms)
+        score, path = c.viterbi(labels)
+        allsc = c.viterbi_scores()
+        for u in range(U):
+            v = labels[u]
+            lb = np_log_emissions(ms.c[v], ms.mu[v], ms.iv[v], ms.det[v], x[off[u]:off[u + 1]])
+            sb, pb = brute_viterbi(ms.A[v], lb)
+            sn, pn = np_viterbi(ms.A[v], lb)
+            assert sb == sn and (pb == pn).all()
+            assert (path[off[u]:off[u + 1]] == pb).all(), (N, D, full, u)
+            assert abs(score[u] - sb) <= 1e-9 * abs(sb)
+            for w in range(V):
+                lw = np_log_emissions(ms.c[w], ms.mu[w], ms.iv[w], ms.det[w], x[off[u]:off[u + 1]])
+                assert abs(allsc[u, w] - brute_viterbi(ms.A[w], lw)[0]) <= 1e-5 * abs(sb) + 1e-4
+    # exact ties: identical states and equal transition entries -> the lowest predecessor (R-FS:984's strict compare)
+    A = np.array([[[0.25, 0.25, 0.5], [0.0, 0.5, 0.5], [0.0, 0.0, 1.0]]])
+    ms = api.ModelSet(A, np.ones((1, 3, 1)), np.zeros((1, 3, 1, 2)), np.ones((1, 3, 1, 2)), np.ones((1, 3, 1)))
+    off = np.array([0, 3, 7, 13, 21], dtype=np.int64)
+    x = np.tile(rng.standard_normal((1, 2)), (21, 1))     # the same frame everywhere: equal emissions in every state
+    c.set_features(x, off)
+    c.set_models(ms)
+    score, path = c.viterbi(np.zeros(4, dtype=np.int32))
+    for u in range(4):
+        lb = np_log_emissions(ms.c[0], ms.mu[0], ms.iv[0], ms.det[0], x[off[u]:off[u + 1]])
+        sb, pb = brute_viterbi(A[0], lb)
+        assert (path[off[u]:off[u + 1]] == pb).all() and abs(score[u] - sb) <= 1e-9 * abs(sb)
+    c.close()
