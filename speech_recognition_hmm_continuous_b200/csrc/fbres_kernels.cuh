@@ -24,8 +24,10 @@
 // double range at 4 bytes per value, read back into a double for free.  The 2^-21 rounding is below the noise of
 // the single-precision log-emissions these values are made from (one ulp of a log-density of -80 is 7.6e-6).
 //
-// One persistent CTA per SM = four TEAMS of four warps; warp w belongs to team w & 3, so the four chain warps
-// (w < 4) sit on the four sub-partitions of the SM and each has a double-precision pipe to itself.  A team takes
+// One persistent CTA per SM = four TEAMS of four warps; warp w belongs to team w >> 2 and the chain warp of team k is
+// its warp with w & 3 == k: every team has a warp on each of the four sub-partitions of the SM (staging and the gamma
+// phase use all four schedulers), and the four chain warps sit on four different sub-partitions, each with a
+// double-precision pipe to itself.  A team takes
 // a batch of utterances (as many as fit its quarter of the shared memory, longest first, from a global queue),
 // stages them, runs the chains (two lanes per utterance), then forms gamma and the transition sums with all 128
 // threads over frames, and writes gamma out through a small staging buffer.  Per-utterance sums go to a row of
@@ -53,7 +55,7 @@ struct ResTeamShared {
   double phi[kResMaxUtts], lp[kResMaxUtts];
   int64_t base[kResMaxUtts];
   int32_t T[kResMaxUtts], woff[kResMaxUtts], utt[kResMaxUtts], model[kResMaxUtts], pos[kResMaxUtts];
-  int32_t batch, pad_[3];
+  int32_t batch, next, pad_[2];
   float stg[kResTeamThreads * NS];  // gamma of one round of frames, [frame][state] as in global memory
 };
 
@@ -112,10 +114,11 @@ __global__ void __launch_bounds__(kResThreads, 1)
 k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
          const double *__restrict__ Aall, const int32_t *__restrict__ order, const int32_t *__restrict__ upos,
          const ResBatch *__restrict__ batches, int nbatches, int *__restrict__ counter, float *__restrict__ gamma,
-         double *__restrict__ ustats, double *__restrict__ logp_utt) {
+         double *__restrict__ ustats, double *__restrict__ logp_utt, long long *__restrict__ dbg) {
   extern __shared__ __align__(16) uint8_t res_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int team = warp & 3, role = warp >> 2, tt = role * 32 + lane;  // tt: thread index within the team
+  const int team = warp >> 2, role = warp & 3, tt = role * 32 + lane;  // tt: thread index within the team
+  const bool chain_warp = role == team;
   constexpr size_t FX = res_fixed_bytes<NS>();
   constexpr int SW = res_slot_words<NS>();
   constexpr int K = 4 * NS + 1;
@@ -123,11 +126,21 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
   ResTeamShared<NS> &S = *reinterpret_cast<ResTeamShared<NS> *>(res_smem + (size_t)team * FX);
   uint32_t *slot = reinterpret_cast<uint32_t *>(res_smem + kResTeams * FX) + (size_t)team * SW;
   auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kResTeamThreads) : "memory"); };
+  // diagnostic time stamps (ns) of the phases of this team's first batches: dbg[(block * 4 + team) * 32 + k]
+  int nstamp = 0;
+  auto stamp = [&]() {
+    if (dbg != nullptr && tt == 0 && nstamp < 32) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[((size_t)blockIdx.x * kResTeams + team) * 32 + nstamp++] = t;
+    }
+  };
 
+  if (tt == 0) S.next = atomicAdd(counter, 1);
   for (;;) {
-    if (tt == 0) S.batch = atomicAdd(counter, 1);
+    stamp();
     team_sync();
-    const int b = S.batch;
+    const int b = S.next;
     if (b >= nbatches) break;
     const ResBatch bd = batches[b];
     if (tt < bd.count) {
@@ -150,13 +163,14 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
       const int T = S.T[j], n = T * NS;
       const uint32_t *src = reinterpret_cast<const uint32_t *>(logb) + S.base[j] * NS;
       uint32_t *F = slot + S.woff[j];
-#pragma unroll 4
-      for (int w = tt; w < n; w += kResTeamThreads) {
+      for (int w = tt; w < n; w += kResTeamThreads) {  // asynchronous 4-byte copies: all of them in flight at once
         const int t = w / NS, i = w - t * NS;
-        F[t * RS + i] = __ldg(src + w);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(F + t * RS + i)), "l"(src + w) : "memory");
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     team_sync();
+    stamp();
     // ---------------- staging 2: b~ in place into F, reversed into B; sum_t m_t ----------------
     for (int j = 0; j < bd.count; j++) {
       const int T = S.T[j];
@@ -183,8 +197,24 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
       if (lane == 0) S.msum[j][role] = macc;
     }
     team_sync();
+    stamp();
     // ---------------- the chains: lanes 2j (forward) and 2j + 1 (backward) of the team's first warp ----------------
-    if (role == 0) {
+    if (!chain_warp) {
+      // the three idle warps claim the team's next batch and pull its log-emissions into L2 while the chains run
+      const int h = ((role - team - 1) & 3) * 32 + lane;  // 0 .. 95
+      int nb = 0;
+      if (h == 0) { nb = atomicAdd(counter, 1); S.next = nb; }
+      nb = __shfl_sync(0xffffffffu, nb, 0);
+      if (role == ((team + 1) & 3) && nb < nbatches) {
+        const ResBatch nd = batches[nb];
+        for (int j = 0; j < nd.count; j++) {
+          const int u = order[nd.first + j];
+          const char *q0 = reinterpret_cast<const char *>(logb + off[u] * NS);
+          const char *q1 = reinterpret_cast<const char *>(logb + off[u + 1] * NS);
+          for (const char *q = q0 + 128 * lane; q < q1; q += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+      }
+    } else {
       const int j = lane >> 1, dir = lane & 1;
       const bool act = j < bd.count;
       const int T = act ? S.T[j] : 0;
@@ -252,6 +282,7 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
       }
     }
     team_sync();
+    stamp();
     // ---------------- gamma, transition and den sums: all threads of the team, lanes over frames ----------------
     for (int j = 0; j < bd.count; j++) {
       const int T = S.T[j];

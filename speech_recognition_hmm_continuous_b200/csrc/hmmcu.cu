@@ -142,6 +142,7 @@ struct hmmcu_ctx {
   bool last_tc = false;   // whether the most recent emission launch used the tensor-core kernel
   struct TcSet {
     DevBuf images, kc, s0, ns;
+    std::vector<int32_t> s0_h, ns_h;  // what the device tables hold
     int TN = 0, SCt = 0, nimg = 0;
     bool dirty = true;
   } tc_train, tc_dec, ws_train, ws_dec;
@@ -1010,8 +1011,10 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
     for (int s = 0; s < S; s += ts.SCt) { s0.push_back(s); ns.push_back(std::min(ts.SCt, S - s)); }
   }
   const int KP = 2 * ctx->DP;
-  if (TN != ts.TN || (int)s0.size() != ts.nimg) {  // geometry changed: (re)upload the image table
+  if (TN != ts.TN || s0 != ts.s0_h || ns != ts.ns_h) {  // geometry changed: (re)upload the image table
     ts.TN = TN;
+    ts.s0_h = s0;
+    ts.ns_h = ns;
     ts.nimg = (int)s0.size();
     CK(ts.images.ensure(ws_image_bytes(ts.TN, KP) * ts.nimg));
     CK(ts.s0.ensure(sizeof(int32_t) * ts.nimg));
@@ -1534,7 +1537,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     } else {
       if ((rc = ensure_simt_pack(ctx)) != HMMCU_OK) return rc;
     }
-    if (ctx->debug_acc & 5) CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
+    if (ctx->debug_acc & 13) CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
   }
   ctx->train_path = ws_emis ? 2 : use_tc ? 1 : 0;
   // ---- the launch sequence: statistics cleared, emissions, forward-backward, accumulators ----
@@ -1562,13 +1565,15 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
       if (ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0) {
         // every utterance resident in shared memory: log-emissions read once, gamma written once (fbres_kernels.cuh)
         CK(cudaMemsetAsync(ctx->res_counter.p, 0, sizeof(int), ctx->st));
+        if (ctx->debug_acc & 8) CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
         CK(cudaMemsetAsync(ctx->logp_utt_d.p, 0, sizeof(double) * U, ctx->st));  // masked utterances report 0
         const int grid = (int)std::min<int64_t>(ctx->n_res_batches, ctx->sm_count);
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_res<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes),
                        k_fb_res<NS><<<grid, kResThreads, kResSmemBytes, ctx->st>>>(
                            lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), ctx->res_order.as<int32_t>(),
                            ctx->res_upos.as<int32_t>(), ctx->res_batches.as<ResBatch>(), (int)ctx->n_res_batches, ctx->res_counter.as<int>(),
-                           ctx->gamma.as<float>(), ctx->ustats.as<double>(), ctx->logp_utt_d.as<double>())));
+                           ctx->gamma.as<float>(), ctx->ustats.as<double>(), ctx->logp_utt_d.as<double>(),
+                           (ctx->debug_acc & 8) ? (long long *)ctx->acc_dbg.p : nullptr)));
         LAUNCH_CHECK();
         k_fb_reduce<<<V, 1024, 0, ctx->st>>>(ctx->ustats.as<double>(), N, ctx->mus_d.as<int32_t>(), V, ctx->stats.as<double>(), ss, off_lp);
         LAUNCH_CHECK();
@@ -1690,7 +1695,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     t_end(ctx, "accum");
     return HMMCU_OK;
   };
-  const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 7) << 5);
+  const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 15) << 9);
   ctx->last_tc = use_tc;
   if (phases != 7 || fb_logb || acc_gamma) return enqueue();  // pieces of a multi-stream E-step: plain launches
   return run_graphed(ctx, ctx->g_estep, key, enqueue);
