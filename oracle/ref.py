@@ -316,3 +316,40 @@ def parse_train_report(txt_path):
         if line.startswith("number of iterations:"):
             its = int(line.split(":")[1])
     return mean, its
+
+
+def run_train_cli_timed(tag, word, N, M, list_file, out_hmm, stack_unlimited=False):
+    """Runs the reference trainer and returns the wall-clock duration of each of its EM iterations (E-step over the
+    whole list + M-step; the initial-model builder before the first iteration is not in any of them).  The trainer
+    announces every iteration on stdout ("Starting training sequence", T-FS:271) and the end of the loop ("Final
+    Probability", T-FS:359); its stdout is attached to a pseudo-terminal so that libc flushes every line as it is
+    written, and the lines are time-stamped as they arrive."""
+    import pty
+    import time
+    exe = os.path.join(REF_DIR, "hmm_fs_%s" % tag)
+    cmd = "%s %s %d 1 %d %s %s" % (exe, word, N, M, list_file, out_hmm)
+    if stack_unlimited:
+        cmd = "ulimit -s unlimited; " + cmd
+    master, slave = pty.openpty()
+    p = subprocess.Popen(["bash", "-c", cmd], stdout=slave, stderr=subprocess.DEVNULL, stdin=subprocess.DEVNULL, close_fds=True)
+    os.close(slave)
+    starts, final, tail = [], None, b""
+    while True:
+        try:
+            chunk = os.read(master, 65536)
+        except OSError:
+            break
+        if not chunk:
+            break
+        now = time.perf_counter()
+        data = tail + chunk
+        for _ in range(data.count(b"Starting training sequence")):
+            starts.append(now)
+        if b"Final Probability" in data and final is None:
+            final = now
+        tail = data[-32:] if b"Starting training sequence" not in data[-32:] and b"Final Probability" not in data[-32:] else b""
+    os.close(master)
+    if p.wait() != 0 or final is None or not starts:
+        raise RuntimeError("reference trainer failed: %s" % cmd)
+    edges = starts + [final]
+    return [edges[k + 1] - edges[k] for k in range(len(starts))]

@@ -46,10 +46,12 @@ t0 = t[live, 0].min()
 print("teams with work:", int(live.sum()))
 names = ["fetch+meta+stage1", "stage2", "chains", "gamma"]
 # stamps per batch: top, after stage 1, after stage 2, after chains; the next batch's top closes the gamma phase
+r0 = t[live][0]
+print("SM clock during the kernel: %.0f MHz (clock64 / globaltimer over the first team's stamps)" % ((r0[16 + 4] - r0[16]) / max(r0[4] - r0[0], 1) * 1e3))
 d = []
 for row in t[live]:
     k = 0
-    while k + 4 < 32 and row[k + 4] > 0:
+    while k + 4 < 16 and row[k + 4] > 0:
         d.append([row[k + 1] - row[k], row[k + 2] - row[k + 1], row[k + 3] - row[k + 2], row[k + 4] - row[k + 3]])
         k += 4
 d = np.array(d, dtype=np.float64)

@@ -50,13 +50,12 @@ struct ResBatch {
 
 template <int NS>
 struct ResTeamShared {
-  double red[4][4 * NS + 2];   // per-warp partial sums of one utterance
-  double msum[kResMaxUtts][4];  // sum_t m_t, per warp
+  double msum[kResMaxUtts];    // sum_t m_t
   double phi[kResMaxUtts], lp[kResMaxUtts];
   int64_t base[kResMaxUtts];
   int32_t T[kResMaxUtts], woff[kResMaxUtts], utt[kResMaxUtts], model[kResMaxUtts], pos[kResMaxUtts];
-  int32_t batch, next, pad_[2];
-  float stg[kResTeamThreads * NS];  // gamma of one round of frames, [frame][state] as in global memory
+  int32_t next, pad_[3];
+  uint32_t dummy[32 * (NS | 1)];  // rows the idle lanes of the chain warp walk in place
 };
 
 template <int NS> __host__ __device__ constexpr size_t res_fixed_bytes() { return (sizeof(ResTeamShared<NS>) + 15) / 16 * 16; }
@@ -89,24 +88,113 @@ __device__ __forceinline__ uint32_t d32_pack(double v) {
 }
 __device__ __forceinline__ double d32_unpack(uint32_t w) { return __hiloint2double((int)w, 0); }
 
-// one chain step in place: row p holds b~ (this lane's state order) on entry and the scaled vector on exit
+// One chain step.  The state y is carried UNSCALED by its own step's factor: the power of two r that normalises y is
+// folded into the b~ of the step that consumes it, so the exponent arithmetic (integer pipe) runs beside the matrix-vector
+// product instead of in front of it:      y' = (A-part of y) o (b~ r),   r = 2^-e,  e = largest exponent field of y.
+// Any per-frame power of two drops out of gamma / xi; log P collects the e's (res_chain).
 template <int NS>
-__device__ __forceinline__ void res_step(uint32_t *__restrict__ p, const double (&bc)[NS], double (&z)[NS], const double (&cs)[NS],
-                                         const double (&cn)[NS], int &esum) {
-  double raw[NS];
+__device__ __forceinline__ void res_step(const double (&bb)[NS], double (&y)[NS], const double (&cs)[NS], const double (&cn)[NS], int &esum) {
+  double u[NS], c[NS];
 #pragma unroll
   for (int i = 0; i < NS; i++) {
-    double aux = z[i] * cs[i];
-    if (i > 0) aux = fma(z[i - 1], cn[i], aux);
-    raw[i] = aux * bc[i];
+    double aux = y[i] * cs[i];
+    if (i > 0) aux = fma(y[i - 1], cn[i], aux);
+    u[i] = aux;
   }
   int e;
-  const double r = pow2_scale_max<NS>(raw, e);
+  const double r = pow2_scale_max<NS>(y, e);
 #pragma unroll
-  for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
+  for (int i = 0; i < NS; i++) c[i] = bb[i] * r;
+#pragma unroll
+  for (int i = 0; i < NS; i++) y[i] = u[i] * c[i];
   esum += e;
+}
+
+// The two chains of every utterance of a batch: lanes 2j (forward) and 2j + 1 (backward) of one warp; the idle lanes
+// walk in place on dummy rows, so that all 32 lanes share one control flow (per-lane bounds inside the loop cost a factor
+// of two: scripts/ubench/chain_step.cu).  The utterances of a batch are sorted by length, so the common part [1, Tmin)
+// is nearly everything; the ragged rest runs with per-lane bounds.  Every row is read (b~) and later written (the chain's
+// vector) in place; a step's stores are issued one step late, inside the next step's arithmetic.
+template <int NS>
+__device__ __forceinline__ void res_chain(int lane, int count, const int32_t *Tarr, const int32_t *woff, const int32_t *model,
+                                          const double *__restrict__ Aall, uint32_t *slot, uint32_t *dummy, double *phi, double *lp) {
+  constexpr int RS = res_row_stride(NS);
+  const int j = lane >> 1, dir = lane & 1;
+  const bool act = j < count;
+  const int T = act ? Tarr[j] : 0;
+  int Tmax = T, Tmin = act ? T : 0x7fffffff;
 #pragma unroll
-  for (int i = 0; i < NS; i++) p[i] = d32_pack(z[i]);
+  for (int o = 16; o > 0; o >>= 1) {
+    Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, o));
+  }
+  double cs[NS], cn[NS], y[NS];  // self / neighbour coefficients in this lane's state order
+  {
+    const double *A = Aall + (int64_t)(act ? model[j] : model[0]) * NS * NS;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      const int js = dir ? NS - 1 - i : i;
+      cs[i] = A[js * NS + js];
+      if (dir) cn[i] = (js + 1 < NS) ? A[js * NS + js + 1] : 0.0;
+      else cn[i] = (js > 0) ? A[(js - 1) * NS + js] : 0.0;
+    }
+  }
+  // this lane's array, walked from its first frame: forward F[0..T), backward B[T-1..0]
+  int step = act ? (dir ? -RS : RS) : 0;
+  asm volatile("mov.b32 %0, %0;" : "+r"(step));  // keep it in a register (recomputing it from %tid costs an S2R per step)
+  uint32_t *p = act ? slot + woff[j] + (dir ? RS * T + RS * (T - 1) : 0) : dummy + lane * RS;
+  int esum = 0;
+  double b0[NS], b1[NS];
+  uint32_t w[NS];
+  // first step: pi = e_0 (forward, T-FS:232-234) / final state only (backward, T-FS:1484-1490): y = b~ o e_0 in this lane's order
+#pragma unroll
+  for (int i = 0; i < NS; i++) y[i] = (i == 0) ? d32_unpack(p[0]) : 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; i++) w[i] = d32_pack(y[i]);
+  uint32_t *pw = p;  // the row the pending words w[] belong to
+#pragma unroll
+  for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[(T > 1 ? step : 0) + i]);
+  int s = 1;
+  for (; s + 2 < Tmin; s += 2) {  // steps s and s + 1; b~ of s + 1 and s + 2 are in flight meanwhile
+#pragma unroll
+    for (int i = 0; i < NS; i++) b1[i] = d32_unpack(p[2 * step + i]);
+    res_step<NS>(b0, y, cs, cn, esum);
+#pragma unroll
+    for (int i = 0; i < NS; i++) pw[i] = w[i];
+#pragma unroll
+    for (int i = 0; i < NS; i++) w[i] = d32_pack(y[i]);
+#pragma unroll
+    for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[3 * step + i]);
+    res_step<NS>(b1, y, cs, cn, esum);
+#pragma unroll
+    for (int i = 0; i < NS; i++) p[step + i] = w[i];
+#pragma unroll
+    for (int i = 0; i < NS; i++) w[i] = d32_pack(y[i]);
+    p += 2 * step;
+    pw = p;
+  }
+#pragma unroll
+  for (int i = 0; i < NS; i++) pw[i] = w[i];
+  // ragged rest: p is the row of step s - 1, b0 holds the b~ of step s (when s < T)
+  for (; s < Tmax; s++) {
+    if (s < T) {
+      res_step<NS>(b0, y, cs, cn, esum);
+#pragma unroll
+      for (int i = 0; i < NS; i++) p[step + i] = d32_pack(y[i]);
+      if (s + 1 < T) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[2 * step + i]);
+      }
+    }
+    p += step;
+  }
+  if (act && dir == 0) {
+    double sm = y[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) sm += y[i];
+    phi[j] = y[NS - 1] / sm;                                          // alpha^_{T-1}(N-1)
+    lp[j] = 0.6931471805599453 * (double)esum + log(y[NS - 1]);      // + sum m_t (k_fb_res)
+  }
 }
 
 template <int NS>
@@ -126,16 +214,18 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
   ResTeamShared<NS> &S = *reinterpret_cast<ResTeamShared<NS> *>(res_smem + (size_t)team * FX);
   uint32_t *slot = reinterpret_cast<uint32_t *>(res_smem + kResTeams * FX) + (size_t)team * SW;
   auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kResTeamThreads) : "memory"); };
-  // diagnostic time stamps (ns) of the phases of this team's first batches: dbg[(block * 4 + team) * 32 + k]
+  // diagnostic time stamps of the phases of this team's first batches: dbg[(block * 4 + team) * 32 + k]
   int nstamp = 0;
   auto stamp = [&]() {
-    if (dbg != nullptr && tt == 0 && nstamp < 32) {
+    if (dbg != nullptr && tt == 0 && nstamp < 16) {  // [0..16) globaltimer ns, [16..32) clock64 of the same instants
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      dbg[((size_t)blockIdx.x * kResTeams + team) * 32 + nstamp++] = t;
+      dbg[((size_t)blockIdx.x * kResTeams + team) * 32 + nstamp] = t;
+      dbg[((size_t)blockIdx.x * kResTeams + team) * 32 + 16 + nstamp] = clock64();
+      nstamp++;
     }
   };
-
+  for (int i = tt; i < 32 * RS; i += kResTeamThreads) S.dummy[i] = 0x3fe00000u;  // 0.5
   if (tt == 0) S.next = atomicAdd(counter, 1);
   for (;;) {
     stamp();
@@ -143,41 +233,48 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
     const int b = S.next;
     if (b >= nbatches) break;
     const ResBatch bd = batches[b];
-    if (tt < bd.count) {
-      const int u = order[bd.first + tt];
-      const int64_t f0 = off[u];
-      S.utt[tt] = u;
-      S.pos[tt] = upos[u];
-      S.model[tt] = u2m[u];
-      S.base[tt] = f0;
-      S.T[tt] = (int)(off[u + 1] - f0);
+    if (role == 0) {  // the batch's utterances: one lane each; word offsets by a prefix sum over the lanes
+      int T = 0;
+      if (lane < bd.count) {
+        const int u = order[bd.first + lane];
+        const int64_t f0 = off[u];
+        T = (int)(off[u + 1] - f0);
+        S.utt[lane] = u;
+        S.pos[lane] = upos[u];
+        S.model[lane] = u2m[u];
+        S.base[lane] = f0;
+        S.T[lane] = T;
+      }
+      int w = 2 * RS * T;
+#pragma unroll
+      for (int o = 1; o < kResMaxUtts; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += v;
+      }
+      if (lane < bd.count) S.woff[lane] = w - 2 * RS * T;
     }
     team_sync();
-    if (tt == 0) {
-      int w = 0;
-      for (int j = 0; j < bd.count; j++) { S.woff[j] = w; w += 2 * RS * S.T[j]; }
-    }
-    team_sync();
-    // ---------------- staging 1: raw log-emissions into the rows of F (coalesced 4-byte words) ----------------
-    for (int j = 0; j < bd.count; j++) {
+    // ---------------- staging, one warp per utterance: raw log-emissions into the rows of F by asynchronous 4-byte
+    // copies (coalesced, all in flight at once), then b~ in place into F and reversed into B, and sum_t m_t ----------------
+    for (int j = role; j < bd.count; j += 4) {
       const int T = S.T[j], n = T * NS;
       const uint32_t *src = reinterpret_cast<const uint32_t *>(logb) + S.base[j] * NS;
       uint32_t *F = slot + S.woff[j];
-      for (int w = tt; w < n; w += kResTeamThreads) {  // asynchronous 4-byte copies: all of them in flight at once
+      for (int w = lane; w < n; w += 32) {
         const int t = w / NS, i = w - t * NS;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(F + t * RS + i)), "l"(src + w) : "memory");
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    team_sync();
+    __syncwarp();
     stamp();
-    // ---------------- staging 2: b~ in place into F, reversed into B; sum_t m_t ----------------
-    for (int j = 0; j < bd.count; j++) {
+    for (int j = role; j < bd.count; j += 4) {
       const int T = S.T[j];
       uint32_t *F = slot + S.woff[j];
       uint32_t *B = F + RS * T;
       double macc = 0.0;
-      for (int t = tt; t < T; t += kResTeamThreads) {
+#pragma unroll 2
+      for (int t = lane; t < T; t += 32) {
         float l[NS];
 #pragma unroll
         for (int i = 0; i < NS; i++) l[i] = __uint_as_float(F[t * RS + i]);
@@ -194,101 +291,37 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
         }
       }
       macc = warp_sum(macc);
-      if (lane == 0) S.msum[j][role] = macc;
+      if (lane == 0) S.msum[j] = macc;
     }
     team_sync();
     stamp();
-    // ---------------- the chains: lanes 2j (forward) and 2j + 1 (backward) of the team's first warp ----------------
+    // ---------------- the chains; meanwhile the idle warps claim the team's next batch and pull it into L2 ----------------
     if (!chain_warp) {
-      // the three idle warps claim the team's next batch and pull its log-emissions into L2 while the chains run
-      const int h = ((role - team - 1) & 3) * 32 + lane;  // 0 .. 95
-      int nb = 0;
-      if (h == 0) { nb = atomicAdd(counter, 1); S.next = nb; }
-      nb = __shfl_sync(0xffffffffu, nb, 0);
-      if (role == ((team + 1) & 3) && nb < nbatches) {
-        const ResBatch nd = batches[nb];
-        for (int j = 0; j < nd.count; j++) {
-          const int u = order[nd.first + j];
-          const char *q0 = reinterpret_cast<const char *>(logb + off[u] * NS);
-          const char *q1 = reinterpret_cast<const char *>(logb + off[u + 1] * NS);
-          for (const char *q = q0 + 128 * lane; q < q1; q += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      if (role == ((team + 1) & 3)) {
+        int nb = 0;
+        if (lane == 0) { nb = atomicAdd(counter, 1); S.next = nb; }
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        if (nb < nbatches) {
+          const ResBatch nd = batches[nb];
+          for (int j = 0; j < nd.count; j++) {
+            const int u = order[nd.first + j];
+            const char *q0 = reinterpret_cast<const char *>(logb + off[u] * NS);
+            const char *q1 = reinterpret_cast<const char *>(logb + off[u + 1] * NS);
+            for (const char *q = q0 + 128 * lane; q < q1; q += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          }
         }
       }
     } else {
-      const int j = lane >> 1, dir = lane & 1;
-      const bool act = j < bd.count;
-      const int T = act ? S.T[j] : 0;
-      int Tmax = T;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
-      double cs[NS], cn[NS], z[NS];  // self / neighbour coefficients in this lane's state order
-#pragma unroll
-      for (int i = 0; i < NS; i++) { cs[i] = 0.0; cn[i] = 0.0; z[i] = 0.0; }
-      if (act) {
-        const double *A = Aall + (int64_t)S.model[j] * NS * NS;
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          const int js = dir ? NS - 1 - i : i;
-          cs[i] = A[js * NS + js];
-          if (dir) cn[i] = (js + 1 < NS) ? A[js * NS + js + 1] : 0.0;
-          else cn[i] = (js > 0) ? A[(js - 1) * NS + js] : 0.0;
-        }
-      }
-      // this lane's array, walked from its first frame: forward F[0..T), backward B[T-1..0]
-      const int step = dir ? -RS : RS;
-      uint32_t *p = slot + (act ? S.woff[j] : 0) + (dir ? RS * T + RS * (T - 1) : 0);
-      int esum = 0;
-      double b0[NS], b1[NS];
-#pragma unroll
-      for (int i = 0; i < NS; i++) { b0[i] = 0.0; b1[i] = 0.0; }
-      if (T > 0) {  // first step: pi = e_0 (forward) / final state only (backward): x = b~ o e_0 in this lane's order
-#pragma unroll
-        for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[i]);
-        double raw[NS];
-#pragma unroll
-        for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? b0[0] : 0.0;
-        int e;
-        const double r = pow2_scale_max<NS>(raw, e);
-#pragma unroll
-        for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
-        esum += e;
-#pragma unroll
-        for (int i = 0; i < NS; i++) p[i] = d32_pack(z[i]);
-        if (T > 1) {
-#pragma unroll
-          for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[step + i]);
-        }
-      }
-      // two steps per trip (the b~ of the step after next is in flight while a step computes)
-      for (int s = 1; s < Tmax; s += 2) {
-        if (s + 1 < T) {
-#pragma unroll
-          for (int i = 0; i < NS; i++) b1[i] = d32_unpack(p[2 * step + i]);
-        }
-        if (s < T) res_step<NS>(p + step, b0, z, cs, cn, esum);
-        if (s + 2 < T) {
-#pragma unroll
-          for (int i = 0; i < NS; i++) b0[i] = d32_unpack(p[3 * step + i]);
-        }
-        if (s + 1 < T) res_step<NS>(p + 2 * step, b1, z, cs, cn, esum);
-        p += 2 * step;
-      }
-      if (act && dir == 0) {
-        double sm = z[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) sm += z[i];
-        S.phi[j] = z[NS - 1] / sm;                                          // alpha^_{T-1}(N-1)
-        S.lp[j] = 0.6931471805599453 * (double)esum + log(z[NS - 1]);      // + sum m_t below
-      }
+      res_chain<NS>(lane, bd.count, S.T, S.woff, S.model, Aall, slot, S.dummy, S.phi, S.lp);
     }
     team_sync();
     stamp();
-    // ---------------- gamma, transition and den sums: all threads of the team, lanes over frames ----------------
-    for (int j = 0; j < bd.count; j++) {
+    // ---------------- gamma, transition and den sums: one warp per utterance, lanes over frames; gamma replaces alpha~
+    // in its row of F and the rows leave as they lie ([frame][state], coalesced) ----------------
+    for (int j = role; j < bd.count; j += 4) {
       const int T = S.T[j];
-      const uint32_t *F = slot + S.woff[j];   // alpha~_t(i)  at F[t RS + i]
-      const uint32_t *B = F + RS * T;         // q_t(i)       at B[t RS + NS-1-i]
-      const int64_t base = S.base[j];
+      uint32_t *F = slot + S.woff[j];          // alpha~_t(i)  at F[t RS + i]
+      const uint32_t *B = F + RS * T;          // q_t(i)       at B[t RS + NS-1-i]
       const double *A = Aall + (int64_t)S.model[j] * NS * NS;
       double a0[NS], a1[NS];
 #pragma unroll
@@ -300,72 +333,74 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
       double acc_n0[NS], acc_n1[NS], acc_dt[NS], acc_dm[NS];
 #pragma unroll
       for (int i = 0; i < NS; i++) { acc_n0[i] = 0.0; acc_n1[i] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
-      for (int tr = 0; tr < T; tr += kResTeamThreads) {
-        const int t = tr + tt;
-        if (t < T) {
-          double al[NS], n0[NS], n1[NS], gu[NS], Z = 0.0;
+#pragma unroll 2
+      for (int t = lane; t < T; t += 32) {
+        double al[NS], n0[NS], n1[NS], gu[NS], Z = 0.0;
 #pragma unroll
-          for (int i = 0; i < NS; i++) al[i] = d32_unpack(F[t * RS + i]);
-          const bool inner = t + 1 < T;
-          if (inner) {
-            double q[NS];
+        for (int i = 0; i < NS; i++) al[i] = d32_unpack(F[t * RS + i]);
+        int ex;
+        const double ra = pow2_scale_max<NS>(al, ex);  // the chains park their vectors unnormalised: bring them to [1, 2)
 #pragma unroll
-            for (int i = 0; i < NS; i++) q[i] = d32_unpack(B[(t + 1) * RS + NS - 1 - i]);
+        for (int i = 0; i < NS; i++) al[i] *= ra;
+        const bool inner = t + 1 < T;
+        if (inner) {
+          double q[NS];
 #pragma unroll
-            for (int i = 0; i < NS; i++) {
-              n0[i] = al[i] * a0[i] * q[i];                                 // band j = i      T-FS:1611
-              n1[i] = (i + 1 < NS) ? al[i] * a1[i] * q[i + 1] : 0.0;        // j = i + 1
-              gu[i] = n0[i] + n1[i];
-            }
-          } else {  // last frame: beta^ is non-zero for the final state only (T-FS:1484-1490)
+          for (int i = 0; i < NS; i++) q[i] = d32_unpack(B[(t + 1) * RS + NS - 1 - i]);
+          const double rq = pow2_scale_max<NS>(q, ex);
 #pragma unroll
-            for (int i = 0; i < NS; i++) { n0[i] = 0.0; n1[i] = 0.0; gu[i] = (i == NS - 1) ? al[i] : 0.0; }
-          }
-#pragma unroll
-          for (int i = 0; i < NS; i++) Z += gu[i];
-          const double sc = (Z > 0.0) ? phi / Z : 0.0;  // unreachable final state: no occupancy, as the reference
+          for (int i = 0; i < NS; i++) q[i] *= rq;
 #pragma unroll
           for (int i = 0; i < NS; i++) {
-            const double g = gu[i] * sc;                 // alpha^ beta^ / c   T-FS:1617,1658,1709
-            S.stg[tt * NS + i] = (float)g;
-            acc_dm[i] += g;
-            if (inner) {
-              acc_dt[i] += g;
-              acc_n0[i] += n0[i] * sc;
-              acc_n1[i] += n1[i] * sc;
-            }
+            n0[i] = al[i] * a0[i] * q[i];                                 // band j = i      T-FS:1611
+            n1[i] = (i + 1 < NS) ? al[i] * a1[i] * q[i + 1] : 0.0;        // j = i + 1
+            gu[i] = n0[i] + n1[i];
+          }
+        } else {  // last frame: beta^ is non-zero for the final state only (T-FS:1484-1490)
+#pragma unroll
+          for (int i = 0; i < NS; i++) { n0[i] = 0.0; n1[i] = 0.0; gu[i] = (i == NS - 1) ? al[i] : 0.0; }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) Z += gu[i];
+        const double sc = (Z > 0.0) ? phi / Z : 0.0;  // unreachable final state: no occupancy, as the reference
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+          const double g = gu[i] * sc;                 // alpha^ beta^ / c   T-FS:1617,1658,1709
+          F[t * RS + i] = __float_as_uint((float)g);
+          acc_dm[i] += g;
+          if (inner) {
+            acc_dt[i] += g;
+            acc_n0[i] += n0[i] * sc;
+            acc_n1[i] += n1[i] * sc;
           }
         }
-        team_sync();
-        {
-          const int nw = min(kResTeamThreads, T - tr) * NS;
-          float *dst = gamma + (base + tr) * NS;
-          for (int w = tt; w < nw; w += kResTeamThreads) dst[w] = S.stg[w];
-        }
-        team_sync();
       }
+      __syncwarp();
+      {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(gamma) + S.base[j] * NS;
+        const int n = T * NS;
+#pragma unroll 4
+        for (int w = lane; w < n; w += 32) {
+          const int t = w / NS, i = w - t * NS;
+          dst[w] = F[t * RS + i];
+        }
+      }
+      double *row = ustats + (int64_t)S.pos[j] * K;
 #pragma unroll
       for (int i = 0; i < NS; i++) {
         const double v0 = warp_sum(acc_n0[i]), v1 = warp_sum(acc_n1[i]), v2 = warp_sum(acc_dt[i]), v3 = warp_sum(acc_dm[i]);
         if (lane == 0) {
-          S.red[role][i] = v0;
-          S.red[role][NS + i] = v1;
-          S.red[role][2 * NS + i] = v2;
-          S.red[role][3 * NS + i] = v3;
+          row[i] = v0;
+          row[NS + i] = v1;
+          row[2 * NS + i] = v2;
+          row[3 * NS + i] = v3;
         }
       }
-      team_sync();
-      if (tt < K) {
-        double *row = ustats + (int64_t)S.pos[j] * K;
-        if (tt < 4 * NS) {
-          row[tt] = ((S.red[0][tt] + S.red[1][tt]) + S.red[2][tt]) + S.red[3][tt];
-        } else {
-          const double lp = S.lp[j] + (((S.msum[j][0] + S.msum[j][1]) + S.msum[j][2]) + S.msum[j][3]);  // calc_probability T-FS:1546-1549
-          row[4 * NS] = lp;
-          if (logp_utt) logp_utt[S.utt[j]] = lp;
-        }
+      if (lane == 0) {
+        const double lp = S.lp[j] + S.msum[j];  // calc_probability T-FS:1546-1549
+        row[4 * NS] = lp;
+        if (logp_utt) logp_utt[S.utt[j]] = lp;
       }
-      team_sync();
     }
   }
 }

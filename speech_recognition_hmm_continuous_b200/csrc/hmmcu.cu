@@ -52,6 +52,10 @@ struct DevBuf {
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   bool used = false;
+  // every begin / end pair since the last reset (a call that works in batches, hmmcu_forward_scores): "<name>_total"
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pairs;
+  size_t npairs = 0;
+  bool collect = false;
 };
 
 // A launch sequence captured once and replayed: the EM iteration is a dozen short kernels, and launching
@@ -195,6 +199,16 @@ static int fail(hmmcu_ctx *c, int code, const char *fmt, ...) {
 static void t_begin(hmmcu_ctx *ctx, const char *name) {
   if (!ctx->timing) return;
   Timer &t = ctx->timers[name];
+  if (t.collect) {
+    if (t.npairs == t.pairs.size()) {
+      std::pair<cudaEvent_t, cudaEvent_t> pr;
+      cudaEventCreate(&pr.first);
+      cudaEventCreate(&pr.second);
+      t.pairs.push_back(pr);
+    }
+    cudaEventRecord(t.pairs[t.npairs].first, ctx->st);
+    return;
+  }
   if (!t.a) {
     cudaEventCreate(&t.a);
     cudaEventCreate(&t.b);
@@ -204,8 +218,25 @@ static void t_begin(hmmcu_ctx *ctx, const char *name) {
 static void t_end(hmmcu_ctx *ctx, const char *name) {
   if (!ctx->timing) return;
   Timer &t = ctx->timers[name];
+  if (t.collect) {
+    cudaEventRecord(t.pairs[t.npairs++].second, ctx->st);
+    t.used = true;
+    return;
+  }
   cudaEventRecord(t.b, ctx->st);
   t.used = true;
+}
+// back to one begin / end pair per call
+static void t_single(hmmcu_ctx *ctx, const char *name) {
+  if (!ctx->timing) return;
+  ctx->timers[name].collect = false;
+}
+// start collecting every begin / end pair of `name` (until the next call of this)
+static void t_collect(hmmcu_ctx *ctx, const char *name) {
+  if (!ctx->timing) return;
+  Timer &t = ctx->timers[name];
+  t.collect = true;
+  t.npairs = 0;
 }
 
 
@@ -333,6 +364,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
     if (kv.second.b) cudaEventDestroy(kv.second.b);
+    for (auto &pr : kv.second.pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   }
   if (ctx->g_estep.exec) cudaGraphExecDestroy(ctx->g_estep.exec);
   if (ctx->g_mstep.exec) cudaGraphExecDestroy(ctx->g_mstep.exec);
@@ -370,8 +402,37 @@ void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; ctx->c
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
   if (strcmp(name, "kappa") == 0) return ctx->kappa;            // accuracy-guard value of the current pack
   if (strcmp(name, "tc_active") == 0) return ctx->last_tc ? 1.0 : 0.0;
+  {  // "<name>_total": the sum over the batches of the last hmmcu_forward_scores / hmmcu_viterbi_scores call
+    const size_t ln = strlen(name);
+    if (ln > 6 && strcmp(name + ln - 6, "_total") == 0) {
+      auto itt = ctx->timers.find(std::string(name, ln - 6));
+      if (itt == ctx->timers.end() || !itt->second.used) return -1.0;
+      const Timer &t = itt->second;
+      if (!t.collect) return hmmcu_last_kernel_ms(ctx, std::string(name, ln - 6).c_str());
+      double tot = 0.0;
+      for (size_t k = 0; k < t.npairs; k++) {
+        float ms1 = 0.f;
+        if (cudaEventSynchronize(t.pairs[k].second) != cudaSuccess || cudaEventElapsedTime(&ms1, t.pairs[k].first, t.pairs[k].second) != cudaSuccess) {
+          cudaGetLastError();
+          return -1.0;
+        }
+        tot += ms1;
+      }
+      return tot;
+    }
+  }
   auto it = ctx->timers.find(name);
   if (it == ctx->timers.end() || !it->second.used) return -1.0;
+  if (it->second.collect) {  // the last pair
+    const Timer &t = it->second;
+    float ms1 = 0.f;
+    if (t.npairs == 0 || cudaEventSynchronize(t.pairs[t.npairs - 1].second) != cudaSuccess ||
+        cudaEventElapsedTime(&ms1, t.pairs[t.npairs - 1].first, t.pairs[t.npairs - 1].second) != cudaSuccess) {
+      cudaGetLastError();
+      return -1.0;
+    }
+    return (double)ms1;
+  }
   float ms = 0.f;
   if (cudaEventSynchronize(it->second.b) != cudaSuccess || cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) {
     cudaGetLastError();
@@ -1281,6 +1342,8 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   if (ctx->U == 0) return HMMCU_OK;
   const int64_t S = (int64_t)ctx->V * ctx->N;
   CK(ctx->score_d.ensure(sizeof(double) * (size_t)ctx->U * ctx->V));
+  t_collect(ctx, "emis");
+  t_collect(ctx, mode == 0 ? "score" : "viterbi");
   // utterance batches so that the log-emission buffer stays under ~2 GiB
   const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, (int64_t)(2048ll << 20) / (4 * S));
   int u0 = 0;
@@ -1522,11 +1585,13 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     CK(ctx->logb.ensure(sizeof(float) * F * N));
     if (!use_tc) CK(ctx->post.ensure(sizeof(float) * F * G));
     CK(ctx->gamma.ensure(sizeof(float) * F * N));
-    CK(ctx->alpha_ws.ensure(sizeof(float) * F * kFbRow));
-    CK(ctx->beta_ws.ensure(sizeof(float) * F * kFbRow));
+    if (!(ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0)) {  // k_fb_res keeps alpha / beta on the SM
+      CK(ctx->alpha_ws.ensure(sizeof(float) * F * kFbRow));
+      CK(ctx->beta_ws.ensure(sizeof(float) * F * kFbRow));
+      CK(ctx->phi_utt_d.ensure(sizeof(double) * U));
+      CK(ctx->lp_part_d.ensure(sizeof(double) * U));
+    }
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
-    CK(ctx->phi_utt_d.ensure(sizeof(double) * U));
-    CK(ctx->lp_part_d.ensure(sizeof(double) * U));
     if (ws_emis) {
       if ((rc = ensure_ws_images(ctx, 0)) != HMMCU_OK) return rc;
     } else if (use_tc) {
@@ -1540,6 +1605,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (ctx->debug_acc & 13) CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
   }
   ctx->train_path = ws_emis ? 2 : use_tc ? 1 : 0;
+  t_single(ctx, "emis");
   // ---- the launch sequence: statistics cleared, emissions, forward-backward, accumulators ----
   const float *lb_fb = fb_logb ? fb_logb : ctx->logb.as<float>();
   const float *gm_acc = acc_gamma ? acc_gamma : ctx->gamma.as<float>();
@@ -1943,6 +2009,7 @@ int hmmcu_viterbi(hmmcu_ctx *ctx, const int32_t *utt2model, double *score, int32
     k_add_f64<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->st>>>(ctx->logb64.as<double>(), q->logb64.as<double>(), n);
     LAUNCH_CHECK();
   }
+  t_single(ctx, "viterbi");
   CK(ctx->psi_ws.ensure(sizeof(unsigned long long) * ctx->F));
   CK(ctx->path_d.ensure(sizeof(int32_t) * ctx->F));
   CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
