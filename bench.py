@@ -498,7 +498,7 @@ def run_ours(args):
         "tf32_peak_note": "library TF32 GEMM 8192^3 measured in this run (same protocol as MEASURED_PEAKS.json); 3xTF32 issues 3 MMAs per algorithmic MMA",
     }
     ctx.close()
-    del xdev, flush, xpin
+    del xdev, xpin
     torch.cuda.empty_cache()
     if not args.no_configs:
         tools = dict(torch=torch, dist=dist, api=api, synth=synth, dev=dev, local=local, rank=rank, world=world, ar=ar, pk=pk,
