@@ -812,6 +812,7 @@ def c1_cli_wall_clock():
         arms = {"ours": (os.path.join(bindir, "hmm_continuous_fs"), os.path.join(bindir, "recognition_continuous_fs")),
                 "reference": (os.path.join(r.REF_DIR, "hmm_fs_d39m16"), os.path.join(r.REF_DIR, "rec_fs_d39m16"))}
         out = {"workload": "BASELINE configs[0]: 10 words, N=5, M=3, D=39, 20 training + 2 test utterances per word, full CLI train -> test"}
+        arms["ours_one_process"] = arms["ours"]   # the trainer's job-file mode: all ten words in one process, one CUDA context
         for arm, (tr, te) in arms.items():
             if not (os.path.exists(tr) and os.path.exists(te)):
                 out[arm] = {"unavailable": "program missing"}
@@ -819,9 +820,14 @@ def c1_cli_wall_clock():
             d = os.path.join(tmp, arm)
             os.makedirs(d)
             t0 = time.perf_counter()
-            for v in range(V):
-                subprocess.run([tr, "word%d" % v, str(N), "1", str(M), lists[v], os.path.join(d, "w%d.hmm" % v)], check=True,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            if arm == "ours_one_process":
+                jf = os.path.join(d, "jobs.txt")
+                open(jf, "w").write("".join("word%d %d 1 %d %s %s\n" % (v, N, M, lists[v], os.path.join(d, "w%d.hmm" % v)) for v in range(V)))
+                subprocess.run([tr, "@" + jf], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            else:
+                for v in range(V):
+                    subprocess.run([tr, "word%d" % v, str(N), "1", str(M), lists[v], os.path.join(d, "w%d.hmm" % v)], check=True,
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             t_train = time.perf_counter() - t0
             mlist = os.path.join(d, "models.txt")
             open(mlist, "w").write("\n".join(os.path.join(d, "w%d.hmm" % v) for v in range(V)) + "\n")
@@ -834,6 +840,13 @@ def c1_cli_wall_clock():
                 if "otal" in line and "%" in line:
                     acc = line.strip()
             out[arm] = {"train_s": t_train, "test_s": t_test, "total_s": t_train + t_test, "last_total_line": acc}
+        try:  # where one drop-in invocation spends its wall clock (HMMCU_TRACE, train_main.c)
+            tr = arms["ours"][0]
+            pr = subprocess.run([tr, "word0", str(N), "1", str(M), lists[0], os.path.join(tmp, "trace.hmm")], stdout=subprocess.DEVNULL,
+                                stderr=subprocess.PIPE, env=dict(os.environ, HMMCU_TRACE="1"))
+            out["one_invocation_trace"] = [ln.strip() for ln in pr.stderr.decode(errors="replace").splitlines() if ln.startswith("[hmmcu]")]
+        except Exception as e:  # noqa: BLE001
+            out["one_invocation_trace"] = "unavailable: %s" % e
         if "total_s" in out.get("ours", {}) and "total_s" in out.get("reference", {}):
             out["speedup_total"] = out["reference"]["total_s"] / out["ours"]["total_s"]
             out["note"] = ("each drop-in invocation creates its own CUDA context (~0.3-0.5 s); at this size that start-up is most of "

@@ -33,7 +33,9 @@ extern "C" {
 #define HMMCU_ENOMEM 4
 #define HMMCU_EIO 5      /* host-side file error (hmmh_* only) */
 
-#define HMMCU_MAX_STATES 32 /* reference: MAX_STATES_NUMBER 20 (T-FS:41) */
+#define HMMCU_MAX_STATES 8 /* states per model the kernels are built for (reference: MAX_STATES_NUMBER 20 in the trainer, T-FS:41, 15 in the
+                            * recogniser, R-FS:37); larger models are refused by both programs up front, see DESIGN.md */
+#define HMMH_MAX_FILE_STATES 32 /* .hmm files with up to this many states are read and written by the host-side file code */
 
 typedef struct hmmcu_ctx hmmcu_ctx;
 

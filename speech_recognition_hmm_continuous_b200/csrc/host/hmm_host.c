@@ -88,7 +88,7 @@ int hmmh_read_model_streams(const char *path, hmmh_model *streams, int max_strea
   memset(word, 0, sizeof(word));
   int N, P, M[HMMH_MAX_STREAMS], D[HMMH_MAX_STREAMS];
   if (!rd(f, word, len) || !rd(f, &N, 4) || !rd(f, &P, 4)) { fclose(f); return HMMCU_EIO; }
-  if (P < 1 || P > HMMH_MAX_STREAMS || P > max_streams || N < 1 || N > HMMCU_MAX_STATES) { fclose(f); return HMMCU_EINVAL; }
+  if (P < 1 || P > HMMH_MAX_STREAMS || P > max_streams || N < 1 || N > HMMH_MAX_FILE_STATES) { fclose(f); return HMMCU_EINVAL; }
   if (!rd(f, M, 4 * (size_t)P) || !rd(f, D, 4 * (size_t)P)) { fclose(f); return HMMCU_EIO; }
   for (int p = 0; p < P; p++)
     if (M[p] < 1 || D[p] < 1 || M[p] > 4096 || D[p] > 4096) { fclose(f); return HMMCU_EIO; }

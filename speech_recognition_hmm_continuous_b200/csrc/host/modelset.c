@@ -71,7 +71,7 @@ static size_t parse_header(const unsigned char *b, size_t len, char word[64], in
   int P = 0;
   size_t o = hb + wl;
   memcpy(N, b + o, 4); memcpy(&P, b + o + 4, 4);
-  if (P != 1 || *N < 1 || *N > HMMCU_MAX_STATES) return 0;
+  if (P != 1 || *N < 1 || *N > HMMH_MAX_FILE_STATES) return 0;
   memcpy(M, b + o + 8, 4); memcpy(D, b + o + 12, 4);
   if (*M < 1 || *D < 1 || *M > 4096 || *D > 4096) return 0;
   return o + 16;

@@ -140,6 +140,10 @@ int hmmh_test_main(int argc, char **argv) {
     memset(probe, 0, sizeof(probe));
     if (hmmh_read_model_streams(mpaths[0], probe, HMMH_MAX_STREAMS, &Pj, 0) != HMMCU_OK) die("file %s not found \n", mpaths[0]);
     if (fl + Pj > argc - 2) die("the argument list is too short for the feature streams of %s \n", models_list);
+    if (probe[0].N > HMMCU_MAX_STATES) { /* refused up front: the kernels are built for HMMCU_MAX_STATES states */
+      printf("model %s has %d states: beyond this build's limit of %d states per model (HMMCU_MAX_STATES) \n", mpaths[0], probe[0].N, HMMCU_MAX_STATES);
+      exit(1);
+    }
     if (j == 0) {
       V = Vj;
       probab = (double *)calloc((size_t)(U > 0 ? U : 1) * V, sizeof(double)); /* probab[i] = 0.0, R-FS:284 */

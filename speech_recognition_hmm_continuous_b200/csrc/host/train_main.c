@@ -7,6 +7,9 @@
  * Differences, all deliberate: the optional initial
  * model is read from argv[argc-1] (the reference reads argv[argc] == NULL and would crash,
  * T-FS:216-222); capacity limits are runtime values.
+ * One extension: `hmm_continuous_fs @jobs.txt` runs one job per line of jobs.txt (each line = the arguments of one
+ * ordinary invocation) in ONE process, so that the CUDA context (most of the wall clock of a small job) is created once.
+ * HMMCU_TRACE=1 in the environment prints the wall clock of the phases on stderr.
  */
 #include <math.h>
 #include <stdio.h>
@@ -18,6 +21,22 @@
 #include "hmm_cuda.h"
 
 #define NAME_SIZE 100
+
+/* contexts kept across the jobs of a job file (one per feature stream) */
+static hmmcu_ctx *g_keep[HMMH_MAX_STREAMS];
+static int g_batch = 0;
+
+static void trace(const char *what) {
+  static double last = 0.0;
+  static int on = -1;
+  if (on < 0) on = getenv("HMMCU_TRACE") != NULL;
+  if (!on) return;
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+  fprintf(stderr, "[hmmcu] %-22s +%.1f ms\n", what, last > 0.0 ? (now - last) * 1e3 : 0.0);
+  last = now;
+}
 
 static void die(const char *fmt, const char *arg) {
   printf(fmt, arg);
@@ -47,7 +66,31 @@ static void write_report(const char *txt, const char *hmm, const char *word, int
   fclose(f);
 }
 
+static int train_jobs(const char *prog, const char *jobfile) {
+  FILE *f = fopen(jobfile, "r");
+  if (!f) die("file %s not found \n", jobfile);
+  char line[8192];
+  g_batch = 1;
+  while (fgets(line, sizeof(line), f)) {
+    char *av[64];
+    int n = 0;
+    av[n++] = (char *)prog;
+    for (char *tok = strtok(line, " \t\r\n"); tok && n < 63; tok = strtok(NULL, " \t\r\n")) av[n++] = tok;
+    av[n] = NULL;
+    if (n > 1) hmmh_train_main(n, av);
+  }
+  fclose(f);
+  g_batch = 0;
+  for (int p = HMMH_MAX_STREAMS - 1; p >= 0; p--) {
+    if (g_keep[p]) hmmcu_destroy(g_keep[p]);
+    g_keep[p] = NULL;
+  }
+  return 0;
+}
+
 int hmmh_train_main(int argc, char **argv) {
+  if (argc == 2 && argv[1][0] == '@' && !g_batch) return train_jobs(argv[0], argv[1] + 1);
+  trace("start");
   char t0[100], t1[100], cpu[100];
   time_t start, end;
   time(&start);
@@ -77,7 +120,11 @@ int hmmh_train_main(int argc, char **argv) {
     if (M[p] < 1) die("bad states/mixtures number (%s) \n", argv[4 + p]);
   }
   const char *out = argv[4 + 2 * P];
-  if (N < 1 || N > HMMCU_MAX_STATES) die("bad states/mixtures number (%s) \n", argv[2]);
+  if (N < 1) die("bad states/mixtures number (%s) \n", argv[2]);
+  if (N > HMMCU_MAX_STATES) {
+    printf("states_number %d is beyond this build's limit of %d states per model (HMMCU_MAX_STATES) \n", N, HMMCU_MAX_STATES);
+    exit(1);
+  }
   char txt[NAME_SIZE + 8];
   strncpy(txt, out, NAME_SIZE);
   txt[NAME_SIZE - 1] = 0;
@@ -99,11 +146,14 @@ int hmmh_train_main(int argc, char **argv) {
     for (int u = 0; u < U; u++) printf("\r\nOpenning %s", paths[p][u]);
     int64_t *offp = (int64_t *)malloc(sizeof(int64_t) * ((size_t)U + 1));
     if (!offp) die("error on allocating memory. %s\n", "");
-    ctxs[p] = NULL;
-    if (hmmcu_create(0, &ctxs[p]) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+    ctxs[p] = g_batch ? g_keep[p] : NULL;
+    if (!ctxs[p] && hmmcu_create(0, &ctxs[p]) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+    if (g_batch) g_keep[p] = ctxs[p];
+    trace("context");
     int rc = hmmh_ingest(ctxs[p], (const char *const *)paths[p], U, 0, offp, &D[p], &bad, NULL);
     if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[p][bad] : list[p]);
     if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctxs[p]));
+    trace("ingest");
     if (p == 0) off = offp;
     else {
       if (memcmp(off, offp, sizeof(int64_t) * ((size_t)U + 1)) != 0) die("reading error on file %s (the streams of an utterance differ in length) \n", list[p]);
@@ -150,11 +200,15 @@ int hmmh_train_main(int argc, char **argv) {
     strncpy(m[p].word, word, sizeof(m[p].word) - 1);
   }
 
+  trace("initial model");
   double mean = 0.0;
   int iters = 0;
   printf("\r\nCreating HMM using Forward-Backward algorithm (Baum-Welch)");
   if (hmmh_train_streams(ctxs, P, m, 1, u2m, U, &mean, &iters, 0, NULL, NULL) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
-  for (int p = P - 1; p >= 0; p--) hmmcu_destroy(ctxs[p]);
+  trace("EM loop");
+  if (!g_batch)
+    for (int p = P - 1; p >= 0; p--) hmmcu_destroy(ctxs[p]);
+  trace("context released");
 
   /* cpu time exactly as the reference formats it (T-FS:364-369) */
   struct tms tb;
@@ -174,5 +228,6 @@ int hmmh_train_main(int argc, char **argv) {
     hmmh_free_list(paths[p], U);
   }
   free(off); free(u2m);
+  trace("model + report written");
   return 0;
 }

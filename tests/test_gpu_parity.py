@@ -977,3 +977,32 @@ def test_viterbi_tiny_cases_against_brute_force():
         sb, pb = brute_viterbi(A[0], lb)
         assert (path[off[u]:off[u + 1]] == pb).all() and abs(score[u] - sb) <= 1e-9 * abs(sb)
     c.close()
+
+
+def test_cli_job_file_runs_every_line_in_one_process(tmp_path):
+    """`hmm_continuous_fs @jobs.txt` (one ordinary argument list per line, one CUDA context for all of them) writes the same
+    models and reports as one invocation per word."""
+    N, M, V = 5, 3, 3
+    cen, sc = synth.make_centres(V, N, M, 39, seed=901)
+    labels = np.repeat(np.arange(V), 5)
+    x, off = synth.make_utterances(cen, sc, labels, seed=902, tmin=50, tmax=90)
+    exe = os.path.join(os.path.dirname(api.LIB_PATH), "bin", "hmm_continuous_fs")
+    jobs = []
+    for v in range(V):
+        files = []
+        for u in np.nonzero(labels == v)[0]:
+            files.append(str(tmp_path / ("w%d_u%d.bin" % (v, u))))
+            api.write_features(files[-1], x[off[u]:off[u + 1]])
+        lst = str(tmp_path / ("list%d.txt" % v))
+        open(lst, "w").write("\n".join(files) + "\n")
+        subprocess.run([exe, "word%d" % v, str(N), "1", str(M), lst, str(tmp_path / ("single%d.hmm" % v))], check=True, stdout=subprocess.DEVNULL)
+        jobs.append("word%d %d 1 %d %s %s" % (v, N, M, lst, str(tmp_path / ("batch%d.hmm" % v))))
+    jf = str(tmp_path / "jobs.txt")
+    open(jf, "w").write("\n".join(jobs) + "\n\n")
+    subprocess.run([exe, "@" + jf], check=True, stdout=subprocess.DEVNULL)
+    for v in range(V):
+        a, b = api.read_model(str(tmp_path / ("single%d.hmm" % v))), api.read_model(str(tmp_path / ("batch%d.hmm" % v)))
+        assert a.words == b.words == ["word%d" % v]
+        for name in ("A", "c", "mu", "iv", "det"):
+            assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-9, atol=1e-300), (v, name)
+        assert r.parse_train_report(str(tmp_path / ("single%d.txt" % v))) == r.parse_train_report(str(tmp_path / ("batch%d.txt" % v)))

@@ -330,3 +330,34 @@ def test_cli_usage_and_file_errors():
     assert p.returncode == 1 and "file /nonexistent/m.txt not found" in p.stdout.decode()
     p = subprocess.run([te, "2", "/nonexistent/m.txt", "1", "/nonexistent/f.txt", "/nonexistent/w.txt", "/tmp/r.txt"], stdout=subprocess.PIPE)
     assert p.returncode == 1 and "does not match the argument list" in p.stdout.decode()
+
+
+def test_cli_refuses_models_beyond_the_state_limit_up_front(tmp_path):
+    """The kernels are built for HMMCU_MAX_STATES = 8 states per model (the reference allows 20 / 15, T-FS:41, R-FS:37).
+    Both programs say so before reading any feature file or touching the device; .hmm files with more states are still
+    read and written by the host-side file code (HMMH_MAX_FILE_STATES)."""
+    import subprocess
+    bindir = os.path.join(os.path.dirname(api.LIB_PATH), "bin")
+    tr, te = os.path.join(bindir, "hmm_continuous_fs"), os.path.join(bindir, "recognition_continuous_fs")
+    p = subprocess.run([tr, "w", "9", "1", "3", "/nonexistent/list.txt", "/tmp/o.hmm"], stdout=subprocess.PIPE)
+    out = p.stdout.decode()
+    assert p.returncode == 1 and "states_number 9 is beyond this build's limit of 8 states" in out and "not found" not in out
+    # a 12-state model file: written and read back by the file code, refused by the recogniser with its name
+    N, M, Dm = 12, 2, 5
+    rng = np.random.default_rng(3)
+    A = np.triu(np.ones((N, N))) - np.triu(np.ones((N, N)), 2)
+    A /= A.sum(axis=1, keepdims=True)
+    var = rng.uniform(0.5, 2.0, size=(1, N, M, Dm))
+    ms = api.ModelSet(A[None], np.full((1, N, M), 0.5), rng.standard_normal((1, N, M, Dm)), 1.0 / var, var.prod(axis=3), words=["big"])
+    hmm = str(tmp_path / "big.hmm")
+    api.write_model(hmm, ms)
+    back = api.read_model(hmm)
+    assert back.N == N and np.array_equal(back.mu, ms.mu)
+    ml = str(tmp_path / "models.txt")
+    open(ml, "w").write(hmm + "\n")
+    fl, wl = str(tmp_path / "f.txt"), str(tmp_path / "w.txt")   # empty test set: the model check comes before any device work
+    open(fl, "w").close()
+    open(wl, "w").close()
+    p = subprocess.run([te, "1", ml, "1", fl, wl, str(tmp_path / "r.txt")], stdout=subprocess.PIPE)
+    out = p.stdout.decode()
+    assert p.returncode == 1 and "has 12 states: beyond this build's limit of 8" in out
