@@ -242,13 +242,36 @@ def run_ours(args):
             dist.all_reduce(t)
 
     ar = allreduce_torch if world > 1 else None
-    ar_kind = "torch.distributed (nccl)"
+    ar_kind = ["torch.distributed (nccl)"]
     if world > 1 and not args.torch_allreduce:
         try:  # the collective on the context's own stream through the NCCL C API
             ar = api.NcclAllReduce(rank, world)
-            ar_kind = "ncclAllReduce on the context's stream"
+            ar_kind[0] = "ncclAllReduce on the context's stream"
         except Exception as e:  # noqa: BLE001
             print("direct NCCL unavailable (%s); using torch.distributed" % e, file=sys.stderr)
+
+    def setup_allreduce(c):
+        """The sum of the statistics over the ranks for context c (after its set_models): the library's own kernel pair over
+        peer memory (NVLink, CUDA IPC handles exchanged through the process group) unless --nccl-allreduce; else NCCL."""
+        c._ar = None
+        if world == 1:
+            return
+        c._ar = ar
+        if args.nccl_allreduce or args.torch_allreduce:
+            return
+        ok = 1
+        try:
+            hs = [None] * world
+            dist.all_gather_object(hs, c.peer_export(world))
+            c.peer_import(rank, world, hs)
+        except Exception as e:  # noqa: BLE001
+            print("peer all-reduce unavailable on rank %d (%s); using NCCL" % (rank, e), file=sys.stderr)
+            ok = 0
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)   # all ranks or none
+        if int(t.item()) == 1:
+            c._ar = lambda p, n, s: c.peer_allreduce()
+            ar_kind[0] = "hmmcu_peer_allreduce: kernel pair over NVLink peer memory (no library collective)"
     # pinned host copy of the features (e2e leg) and a device-resident copy (value leg)
     xpin = torch.from_numpy(x).pin_memory()
     xdev = xpin.to(dev)
@@ -260,16 +283,16 @@ def run_ours(args):
 
         def em_iteration():
             c.estep(lab, download=False, want_logp=False)
-            if ar is not None:
+            if c._ar is not None:
                 p, n = c.stats_device()
                 if ar_events is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(st)
-                    ar(p, n, c.stream())
+                    c._ar(p, n, c.stream())
                     e1.record(st)
                     ar_events.append((e0, e1))
                 else:
-                    ar(p, n, c.stream())
+                    c._ar(p, n, c.stream())
             return c.mstep(threshold=-1.0)  # reads sum_logp / n_utt / updated back: the step's result
         return em_iteration
 
@@ -323,6 +346,7 @@ def run_ours(args):
     ctx.set_features_device(xdev.data_ptr(), off, D)
     ctx.set_models(ms)
     ctx.em_reset()
+    setup_allreduce(ctx)
     step_resident = make_iteration(ctx, labels)
 
     def step_e2e():
@@ -345,7 +369,7 @@ def run_ours(args):
         ctx.set_models(ms)
         ctx.estep(labels, download=False, want_logp=False)
         p, n = ctx.stats_device()
-        ar(p, n, ctx.stream())
+        ctx._ar(p, n, ctx.stream())
         ctx.synchronize()
         reduced = ctx.stats_download()
         if rank == 0:
@@ -488,7 +512,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "details": {"frames_this_rank": F, "utterances_per_gpu": U, "cpu_affinity": numa,
-                    "parallelism": ("utterances sharded, 1 all-reduce of statistics per iteration (%s)" % ar_kind) if world > 1 else "single GPU"},
+                    "parallelism": ("utterances sharded, the statistics summed over the ranks once per iteration (%s)" % ar_kind[0]) if world > 1 else "single GPU"},
         "e2e": {"value": F * world / (e2e_ms / e2e_steps * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": int(x.nbytes + off.nbytes),
                 "d2h_bytes_per_step": int(8 * (3 * V + 1))},
@@ -501,7 +525,7 @@ def run_ours(args):
     del xdev, xpin
     torch.cuda.empty_cache()
     if not args.no_configs:
-        tools = dict(torch=torch, dist=dist, api=api, synth=synth, dev=dev, local=local, rank=rank, world=world, ar=ar, pk=pk,
+        tools = dict(torch=torch, dist=dist, api=api, synth=synth, dev=dev, local=local, rank=rank, world=world, setup_allreduce=setup_allreduce, pk=pk,
                      tf32_peak=tf32_peak, make_iteration=make_iteration, timed=timed, kernel_pass=kernel_pass, traffic=traffic)
         out["configs"] = {"c3": run_c3(tools, args), "c4": run_c4(tools, args), "c5": run_c5(tools, args)}
     if rank == 0:
@@ -599,6 +623,7 @@ def run_c3(t, args):
     c.set_features_device(x.data_ptr(), off, D)
     c.set_models(ms)
     c.em_reset()
+    t["setup_allreduce"](c)
     steps = max(3, min(args.steps, 10))
     tot_ms, launches, _, _ = t["timed"](c, t["make_iteration"](c, lab), steps, 3)
     kms, ar_ms = t["kernel_pass"](c, lab, 5)
@@ -899,6 +924,7 @@ def main():
     ap.add_argument("--no-cli", action="store_true", help="skip the C1 drop-in CLI wall-clock leg")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's NUMA-local CPUs")
     ap.add_argument("--torch-allreduce", action="store_true", help="all-reduce through torch.distributed instead of the NCCL C API")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="ncclAllReduce instead of the library's peer-memory kernels")
     ap.add_argument("--upload-chunks", type=int, default=0, help="override the library's upload chunk count (experiments)")
     ap.add_argument("--set", action="append", default=[], metavar="KEY=INT", help="hmmcu_set_option switches (experiments)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

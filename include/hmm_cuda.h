@@ -151,6 +151,31 @@ int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double 
 double *hmmcu_stats_device(hmmcu_ctx *ctx, int64_t *n_doubles);
 int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats);
 
+/* The sum of the statistics over the ranks of one NVLink / NVSwitch domain WITHOUT a library collective: every rank
+ * stores its statistics straight into a receive slot of every peer (peer memory mapped through CUDA IPC), raises a flag
+ * there, waits for its own flags and adds the slots in rank order -- one short kernel pair on the context's stream, the
+ * same bytes on every rank (the M-step that follows is bit-identical everywhere).  Set-up, once per model-set geometry:
+ *   hmmcu_peer_export   (after hmmcu_set_models) allocates this rank's receive area and returns its 64-byte IPC handle
+ *   [the caller exchanges the handles of all ranks, e.g. with the all-gather of its process group]
+ *   hmmcu_peer_import   maps the areas of all ranks (handles[world][64]; the entry of `rank` itself is ignored)
+ *   hmmcu_peer_import_pointers   the same for areas that are already addressable in this process (several contexts in
+ *                       one process, tests): areas[world] device pointers from hmmcu_peer_area
+ * Per EM iteration, between hmmcu_estep and hmmcu_mstep (replaces the all-reduce of hmmh_allreduce_fn):
+ *   hmmcu_peer_push     my statistics -> every peer's slot for me, then my flag there
+ *   hmmcu_peer_reduce   wait for every peer's flag, statistics = sum over the ranks in rank order
+ * (hmmcu_peer_allreduce = push + reduce).  Two slot sets alternate, so a rank that runs ahead never overwrites what a
+ * slower rank still reads. */
+#define HMMCU_IPC_HANDLE_BYTES 64
+int hmmcu_peer_export(hmmcu_ctx *ctx, int world, void *handle_out);
+int hmmcu_peer_import(hmmcu_ctx *ctx, int rank, int world, const void *handles);
+void *hmmcu_peer_area(hmmcu_ctx *ctx);
+int hmmcu_peer_import_pointers(hmmcu_ctx *ctx, int rank, int world, void *const *areas);
+int hmmcu_peer_push(hmmcu_ctx *ctx);
+int hmmcu_peer_reduce(hmmcu_ctx *ctx);
+int hmmcu_peer_allreduce(hmmcu_ctx *ctx);
+/* 1 when a hmmcu_peer_reduce gave up waiting for a peer (20 s); synchronises the context's stream */
+int hmmcu_peer_error(hmmcu_ctx *ctx);
+
 /* Device-resident EM iteration.  The M-step of the trainer's main() (T-FS:326-352:
  * updating_transition_probab, updating_mix_param, changing_zero_coef, calc_det, inv_matrix) applied on
  * the device to the model set held by the context, from the statistics of the last hmmcu_estep

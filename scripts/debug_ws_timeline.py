@@ -26,7 +26,7 @@ t = buf.view(np.int64)[:64 * W].reshape(64, W)[:, :15 if mode == "acc" else 8]
 t0 = t[t > 0].min()
 names = ["ld:top", "ld:empty", "ld:arrive", "mma:full", "mma:dempty", "mma:issued", "epi:dfull", "epi:arrive"]
 if mode == "acc":
-    names = ["ld:top", "ld:free", "ld:arrive", "mma:xfull", "mma:g1", "mma:g2", "epi:d1full", "epi:wfull", "g2:start", "g2:issued", "e0:arrive", "e0:top", "e0:ld", "e0:math", "e0:st"]
+    names = ["ld:top", "ld:free", "ld:arrive", "mma:xfull", "mma:g1", "mma:g2", "epi:d1full", "epi:wfull", "g2:start", "g2:issued", "x:stored", "x:cfs", "xt:free", "xt:arrive", "xt:top"]
 print("unit " + " ".join("%10s" % n for n in names))
 for i in range(64):
     if t[i].max() == 0: break

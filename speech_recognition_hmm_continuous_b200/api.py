@@ -27,6 +27,8 @@ EXPORTS = [
     "hmmcu_features_begin", "hmmcu_features_append", "hmmcu_features_wait", "hmmcu_features_end", "hmmcu_staging", "hmmcu_link_streams", "hmmh_read_model_streams", "hmmh_write_model_streams", "hmmh_train_streams",
     "hmmh_model_set_alloc", "hmmh_model_set_free", "hmmh_read_model_set", "hmmh_write_model_set", "hmmh_upload_model_set",
     "hmmh_read_list", "hmmh_free_list", "hmmh_scan_features", "hmmh_ingest_to", "hmmh_ingest",
+    "hmmcu_peer_export", "hmmcu_peer_import", "hmmcu_peer_area", "hmmcu_peer_import_pointers", "hmmcu_peer_push", "hmmcu_peer_reduce",
+    "hmmcu_peer_allreduce", "hmmcu_peer_error",
 ]
 
 
@@ -137,6 +139,13 @@ def load():
     lib.hmmh_upload_models.argtypes = [C.c_void_p, C.POINTER(_CModel), C.c_int]
     lib.hmmh_train.argtypes = [C.c_void_p, C.POINTER(_CModel), C.c_int, _ip, C.c_int, _dp, C.POINTER(C.c_int), C.c_int,
                                C.c_void_p, C.c_void_p]
+    lib.hmmcu_peer_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.hmmcu_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    lib.hmmcu_peer_area.restype = C.c_void_p
+    lib.hmmcu_peer_area.argtypes = [C.c_void_p]
+    lib.hmmcu_peer_import_pointers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    for f in ("hmmcu_peer_push", "hmmcu_peer_reduce", "hmmcu_peer_allreduce", "hmmcu_peer_error"):
+        getattr(lib, f).argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -383,6 +392,37 @@ class Context:
                                      its.ctypes.data_as(C.POINTER(C.c_int)), int(max_iter),
                                      C.cast(cb, C.c_void_p) if cb else None, None), "hmmh_train")
         return its, mean
+
+    # ---- statistics summed over the ranks through peer memory (NVLink), no library collective ----
+    def peer_export(self, world):
+        """-> the 64-byte CUDA IPC handle of this rank's receive area (exchange it with all ranks, then peer_import)."""
+        h = C.create_string_buffer(64)
+        self._ck(self.lib.hmmcu_peer_export(self.h, int(world), h), "hmmcu_peer_export")
+        return h.raw
+
+    def peer_import(self, rank, world, handles):
+        buf = b"".join(handles)
+        assert len(buf) == 64 * world
+        self._ck(self.lib.hmmcu_peer_import(self.h, int(rank), int(world), buf), "hmmcu_peer_import")
+
+    def peer_area(self):
+        return self.lib.hmmcu_peer_area(self.h)
+
+    def peer_import_pointers(self, rank, world, areas):
+        arr = (C.c_void_p * world)(*[C.c_void_p(a) for a in areas])
+        self._ck(self.lib.hmmcu_peer_import_pointers(self.h, int(rank), int(world), arr), "hmmcu_peer_import_pointers")
+
+    def peer_push(self):
+        self._ck(self.lib.hmmcu_peer_push(self.h), "hmmcu_peer_push")
+
+    def peer_reduce(self):
+        self._ck(self.lib.hmmcu_peer_reduce(self.h), "hmmcu_peer_reduce")
+
+    def peer_allreduce(self):
+        self._ck(self.lib.hmmcu_peer_allreduce(self.h), "hmmcu_peer_allreduce")
+
+    def peer_error(self):
+        return bool(self.lib.hmmcu_peer_error(self.h))
 
     def set_option(self, key, value):
         self._ck(self.lib.hmmcu_set_option(self.h, key.encode(), int(value)), "hmmcu_set_option")

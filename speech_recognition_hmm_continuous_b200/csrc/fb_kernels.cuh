@@ -34,15 +34,21 @@ constexpr int kFbRow = 8;         // floats per row of the alpha / beta workspac
 // exp(y) for y <= 0 as a double: single-precision mantissa accuracy (the log-densities it is fed
 // are single precision), double-precision range.  y < -700 -> 0.
 __device__ __forceinline__ double exp_scaled(float y) {
+  // Only ONE operation on the transcendental / conversion unit (ex2): the rounding of y log2(e) to an integer uses
+  // the 1.5 * 2^23 trick on the FMA pipe, and the double is assembled from the float's bits with integer
+  // instructions (a cvt.f64.f32 and a cvt.rni per value made the decode scorers wait on that unit).
   const float yc = fmaxf(y, -700.f);  // branch-free: the chain's five exponentials must overlap
-  const float n = rintf(yc * 1.4426950408889634f);
+  const float t = fmaf(yc, 1.4426950408889634f, 12582912.f);         // 1.5 * 2^23 + rint(yc log2 e)
+  const float n = t - 12582912.f;
+  const int ni = __float_as_int(t) - 0x4B400000;                      // the same integer
   float f = fmaf(yc, 1.4426950216293335f, -n);  // (float)log2(e)
   f = fmaf(yc, 1.9259629911e-8f, f);            // log2(e) - (float)log2(e)
   float p;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));  // |f| <= 0.5: 2 ulp
-  const double d = (double)p;
-  const int hi = __double2hiint(d) + ((int)n << 20);
-  return (y < -700.f) ? 0.0 : __hiloint2double(hi, __double2loint(d));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f));  // |f| <= 0.5: 2 ulp; p in [0.70, 1.42] is a normal float
+  const unsigned pb = (unsigned)__float_as_int(p);
+  const int hi = (int)(pb >> 3) + ((1023 - 127 + ni) << 20);          // exponent re-biased, 20 of the 23 mantissa bits
+  const int lo = (int)(pb << 29);                                     // the other 3
+  return (y < -700.f) ? 0.0 : __hiloint2double(hi, lo);
 }
 
 // r = 2^-e with e the unbiased exponent of s (so that s*r is in [1,2)); e returned.  s == 0, denormal,

@@ -161,6 +161,13 @@ struct hmmcu_ctx {
   int use_wide_fb = 1; // 1 = thread-per-chain forward-backward (k_fb_wide) beyond kWideMinUtts utterances, 2 = always, 0 = never
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
+  // peer all-reduce over NVLink (hmmcu_peer_*): my receive area [2 slot sets][world][stats_n] doubles, then
+  // [2][world] 64-bit flags; the areas of all ranks as mapped here; the iteration counter lives on the device
+  DevBuf peer_area, peer_ptrs_d, peer_seq_d;
+  std::vector<void *> peer_ptrs;        // [world], entry `rank` = my own area
+  std::vector<void *> peer_opened;      // IPC mappings to close
+  int peer_rank = -1, peer_world = 0;
+  int64_t peer_n = 0;                   // doubles per slot the area was sized for
   int64_t n_res_batches = 0;
   bool res_fits = false;  // every utterance of the training map fits one team's shared memory
   int debug_acc = 0;
@@ -350,6 +357,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->st);
   unlink_streams(ctx);
+  for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  ctx->peer_area.release(); ctx->peer_ptrs_d.release(); ctx->peer_seq_d.release();
   ctx->logb_joint.release();
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->kc2, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
@@ -1942,6 +1951,210 @@ int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats) {
   CK(cudaMemcpyAsync(stats, ctx->stats.p, sizeof(double) * ctx->stats_n, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
+}
+
+
+// ------------------------------------------------------- peer all-reduce over NVLink (no library) ----
+// Area of a rank: slots double[2][world][n] | flags u64[2][world].  Iteration `seq` (1, 2, ..) uses slot set seq & 1;
+// flags only ever grow (the latest iteration whose data of that parity has landed), so nothing is reset.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// grid (blocks per peer, world): block (b, q) copies its share of my statistics into peer q's slot for me; the last block
+// to finish for a peer (fence + counter) raises my flag there.
+__global__ void __launch_bounds__(256)
+k_peer_push(const double *__restrict__ stats, int64_t n, void *const *__restrict__ areas, int rank, int world,
+            const unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done) {
+  const int q = blockIdx.y;
+  if (q == rank) return;
+  const unsigned long long seq = *seq_p + 1;
+  const int set = (int)(seq & 1);
+  double *dst = reinterpret_cast<double *>(areas[q]) + ((int64_t)set * world + rank) * n;
+  const int64_t n2 = n >> 1;
+  const double2 *s2 = reinterpret_cast<const double2 *>(stats);
+  double2 *d2 = reinterpret_cast<double2 *>(dst);
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 15) == 0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) d2[i] = s2[i];
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = stats[n - 1];
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = stats[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&done[q], 1u);
+    if (prev == gridDim.x - 1) {
+      done[q] = 0;
+      __threadfence_system();
+      unsigned long long *flags = reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(areas[q]) + 2 * (int64_t)world * n);
+      st_release_sys(flags + set * world + rank, seq);
+    }
+  }
+}
+
+// every block waits for the flags of all peers (bounded: ~20 s, then *err = 1), then statistics = sum over the ranks in rank
+// order; the last block to finish advances the iteration counter
+__global__ void __launch_bounds__(256)
+k_peer_reduce(double *__restrict__ stats, int64_t n, const double *__restrict__ area, int rank, int world,
+              unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done, int *__restrict__ err) {
+  const unsigned long long seq = *seq_p + 1;
+  const int set = (int)(seq & 1);
+  const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(area + 2 * (int64_t)world * n);
+  if (threadIdx.x < world && threadIdx.x != rank) {
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flags + set * world + threadIdx.x) < seq) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ll) { *err = 1; break; }
+    }
+  }
+  __syncthreads();
+  const double *slots = area + (int64_t)set * world * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double sacc = 0.0;
+    for (int q = 0; q < world; q++) sacc += (q == rank) ? stats[i] : slots[(int64_t)q * n + i];
+    stats[i] = sacc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&done[world], 1u);
+    if (prev == gridDim.x - 1) {
+      done[world] = 0;
+      *seq_p = seq;
+    }
+  }
+}
+
+static int64_t peer_slot_doubles(const hmmcu_ctx *ctx) { return hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm) * ctx->V; }
+static size_t peer_area_bytes(int64_t n, int world) { return sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world; }
+
+static void peer_close(hmmcu_ctx *ctx) {
+  for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  ctx->peer_opened.clear();
+  ctx->peer_ptrs.clear();
+  ctx->peer_rank = -1;
+  ctx->peer_world = 0;
+}
+
+int hmmcu_peer_export(hmmcu_ctx *ctx, int world, void *handle_out) {
+  if (!ctx || world < 1 || world > 64) return fail(ctx, HMMCU_EINVAL, "peer_export: bad arguments");
+  if (!ctx->have_models) return fail(ctx, HMMCU_EINVAL, "peer_export: set the models first");
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->st));
+  peer_close(ctx);
+  const int64_t n = peer_slot_doubles(ctx);
+  ctx->peer_area.release();  // a fresh allocation: the handle names the allocation, not a sub-range
+  CK(ctx->peer_area.ensure(peer_area_bytes(n, world)));
+  CK(cudaMemsetAsync(ctx->peer_area.p, 0, peer_area_bytes(n, world), ctx->st));
+  CK(ctx->peer_seq_d.ensure(sizeof(unsigned long long) + sizeof(unsigned int) * 80 + sizeof(int)));  // seq | done[world + 1] | err
+  CK(cudaMemsetAsync(ctx->peer_seq_d.p, 0, sizeof(unsigned long long) + sizeof(unsigned int) * 80 + sizeof(int), ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->peer_n = n;
+  ctx->peer_world = world;
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->peer_area.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == HMMCU_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &h, sizeof(h));
+  }
+  return HMMCU_OK;
+}
+
+void *hmmcu_peer_area(hmmcu_ctx *ctx) { return ctx ? ctx->peer_area.p : nullptr; }
+
+int hmmcu_peer_import_pointers(hmmcu_ctx *ctx, int rank, int world, void *const *areas) {
+  if (!ctx || !areas || world != ctx->peer_world || rank < 0 || rank >= world || !ctx->peer_area.p)
+    return fail(ctx, HMMCU_EINVAL, "peer_import: call hmmcu_peer_export with the same world size first");
+  CK(cudaSetDevice(ctx->dev));
+  ctx->peer_ptrs.assign(areas, areas + world);
+  ctx->peer_ptrs[rank] = ctx->peer_area.p;
+  ctx->peer_rank = rank;
+  CK(ctx->peer_ptrs_d.ensure(sizeof(void *) * world));
+  CK(cudaMemcpyAsync(ctx->peer_ptrs_d.p, ctx->peer_ptrs.data(), sizeof(void *) * world, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return HMMCU_OK;
+}
+
+int hmmcu_peer_import(hmmcu_ctx *ctx, int rank, int world, const void *handles) {
+  if (!ctx || !handles || world != ctx->peer_world || rank < 0 || rank >= world || !ctx->peer_area.p)
+    return fail(ctx, HMMCU_EINVAL, "peer_import: call hmmcu_peer_export with the same world size first");
+  CK(cudaSetDevice(ctx->dev));
+  std::vector<void *> areas(world, nullptr);
+  for (int q = 0; q < world; q++) {
+    if (q == rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)q * HMMCU_IPC_HANDLE_BYTES, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      peer_close(ctx);
+      return fail(ctx, HMMCU_ECUDA, "peer_import: cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+    }
+    ctx->peer_opened.push_back(p);
+    areas[q] = p;
+  }
+  return hmmcu_peer_import_pointers(ctx, rank, world, areas.data());
+}
+
+static int peer_ready(hmmcu_ctx *ctx, const char *what) {
+  if (!ctx) return HMMCU_EINVAL;
+  if (ctx->peer_rank < 0 || ctx->peer_world < 1) return fail(ctx, HMMCU_EINVAL, "%s: no peers (hmmcu_peer_export / _import)", what);
+  if (ctx->stats_n != ctx->peer_n) return fail(ctx, HMMCU_EINVAL, "%s: the statistics changed size since hmmcu_peer_export (%lld vs %lld doubles)", what,
+                                                (long long)ctx->stats_n, (long long)ctx->peer_n);
+  return HMMCU_OK;
+}
+
+int hmmcu_peer_push(hmmcu_ctx *ctx) {
+  int rc = peer_ready(ctx, "peer_push");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->dev));
+  if (ctx->peer_world == 1) return HMMCU_OK;
+  unsigned long long *seq = ctx->peer_seq_d.as<unsigned long long>();
+  unsigned int *done = reinterpret_cast<unsigned int *>(seq + 1);
+  const int bpp = (int)std::max<int64_t>(1, std::min<int64_t>(16, ctx->peer_n / 4096));
+  t_begin(ctx, "allreduce");
+  k_peer_push<<<dim3(bpp, ctx->peer_world), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ctx->peer_n, ctx->peer_ptrs_d.as<void *>(), ctx->peer_rank,
+                                                             ctx->peer_world, seq, done);
+  LAUNCH_CHECK();
+  return HMMCU_OK;
+}
+
+int hmmcu_peer_reduce(hmmcu_ctx *ctx) {
+  int rc = peer_ready(ctx, "peer_reduce");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->dev));
+  if (ctx->peer_world == 1) return HMMCU_OK;
+  unsigned long long *seq = ctx->peer_seq_d.as<unsigned long long>();
+  unsigned int *done = reinterpret_cast<unsigned int *>(seq + 1);
+  int *err = reinterpret_cast<int *>(done + 80);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (ctx->peer_n + 1023) / 1024));
+  k_peer_reduce<<<blocks, 256, 0, ctx->st>>>(ctx->stats.as<double>(), ctx->peer_n, ctx->peer_area.as<double>(), ctx->peer_rank, ctx->peer_world, seq,
+                                             done, err);
+  LAUNCH_CHECK();
+  t_end(ctx, "allreduce");
+  return HMMCU_OK;
+}
+
+int hmmcu_peer_allreduce(hmmcu_ctx *ctx) {
+  int rc = hmmcu_peer_push(ctx);
+  return rc ? rc : hmmcu_peer_reduce(ctx);
+}
+
+int hmmcu_peer_error(hmmcu_ctx *ctx) {
+  if (!ctx || !ctx->peer_seq_d.p) return 0;
+  int e = 0;
+  if (cudaSetDevice(ctx->dev) != cudaSuccess || cudaStreamSynchronize(ctx->st) != cudaSuccess) return 1;
+  const char *p = (const char *)ctx->peer_seq_d.p + sizeof(unsigned long long) + sizeof(unsigned int) * 80;
+  if (cudaMemcpy(&e, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  return e != 0;
 }
 
 // ----------------------------------------------------------------------------------- Viterbi ----

@@ -709,6 +709,7 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
           st_shared_v4(Xl + o, l);
         }
       }
+      if (warp == 8) stamp(i, 10);
       // weight exponent of frame xr per state: log2(gamma) - logb log2(e); -inf = no weight.  cfs[state][frame]
       const uint32_t cfs = Xh + cfs_off + 4 * xr;
 #pragma unroll
@@ -720,6 +721,7 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
           sts_f32(cfs + st * SUB * 4, cf);
         }
       }
+      if (warp == 8) stamp(i, 11);
       fence_async_smem();
       mbar_arrive_a(x_full + 8 * s);
       stamp(i, 2);
@@ -765,7 +767,9 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
     };
     auto expand = [&](int i, const Pre &cur) {
       const int s = i % NST;
+      if (warp == 8 + kAccLdWarps) stamp(i, 14);
       mbar_wait_a(x_free + 8 * s, ((i / NST) & 1) ^ 1);
+      if (warp == 8 + kAccLdWarps) stamp(i, 12);
       const uint32_t XTh = sm0 + (uint32_t)s * stage_bytes + 2 * x_bytes, XTl = XTh + xt_bytes;
 #pragma unroll
       for (int k = 0; k < kTK; k++) {  // rows n (x) and n + DP (x^2), 16-byte chunk = frames 4fg..4fg+3
@@ -794,6 +798,7 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
       }
       fence_async_smem();
       mbar_arrive_a(x_full + 8 * s);
+      if (warp == 8 + kAccLdWarps) stamp(i, 13);
       stamp(i, 2);
     };
     int2 d1 = desc_at(u_begin + 1), d2 = desc_at(u_begin + 2);

@@ -1006,3 +1006,58 @@ def test_cli_job_file_runs_every_line_in_one_process(tmp_path):
         for name in ("A", "c", "mu", "iv", "det"):
             assert np.allclose(getattr(a, name), getattr(b, name), rtol=1e-9, atol=1e-300), (v, name)
         assert r.parse_train_report(str(tmp_path / ("single%d.txt" % v))) == r.parse_train_report(str(tmp_path / ("batch%d.txt" % v)))
+
+
+def test_peer_allreduce_sums_two_ranks_in_rank_order():
+    """hmmcu_peer_push / hmmcu_peer_reduce (the all-reduce of the sufficient statistics through peer memory)
+    with two contexts of one process standing in for two ranks: both end with the same bytes, equal to rank 0's
+    statistics + rank 1's (double addition in rank order), over several iterations (the two slot sets alternate).  The
+    pushes of both ranks are enqueued before either reduce, so no kernel ever waits for one that has not been launched
+    (two spinning kernels must not share one GPU); on several GPUs the calls are simply push + reduce per rank."""
+    ms, x, off, labels = _synth(3, 5, 4, 12, seed=1212)
+    U = len(labels)
+    halves = [(0, U // 2), (U // 2, U)]
+    ctxs = []
+    for r_, (u0, u1) in enumerate(halves):
+        c = api.Context(0)
+        c.set_features(x[off[u0]:off[u1]], off[u0:u1 + 1] - off[u0])
+        c.set_models(ms)
+        c.peer_export(2)
+        ctxs.append(c)
+    areas = [c.peer_area() for c in ctxs]
+    for r_, c in enumerate(ctxs):
+        c.peer_import_pointers(r_, 2, areas)
+    for it in range(3):
+        local = []
+        for r_, (c, (u0, u1)) in enumerate(zip(ctxs, halves)):
+            st, _ = c.estep(labels[u0:u1])
+            local.append(st)
+        for c in ctxs:
+            c.peer_push()
+        for c in ctxs:
+            c.synchronize()
+        for c in ctxs:
+            c.peer_reduce()
+        got = [c.stats_download() for c in ctxs]
+        assert not ctxs[0].peer_error() and not ctxs[1].peer_error()
+        want = local[0] + local[1]
+        assert np.array_equal(got[0], got[1]) and np.array_equal(got[0], want), it
+        for c in ctxs:  # the M-step on the summed statistics: identical models on both ranks
+            c.em_reset() if it == 0 else None
+        outs = [c.mstep(threshold=-1.0) for c in ctxs]
+        assert np.array_equal(outs[0][0], outs[1][0])
+        m0, m1 = ctxs[0].get_models(ms.D), ctxs[1].get_models(ms.D)
+        assert np.array_equal(m0.mu, m1.mu) and np.array_equal(m0.iv, m1.iv) and np.array_equal(m0.A, m1.A)
+    # against one E-step over all utterances
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    full, _ = c.estep(labels)
+    c.close()
+    first = None
+    for c in ctxs:
+        c.set_models(ms)
+    local = [c.estep(labels[u0:u1])[0] for c, (u0, u1) in zip(ctxs, halves)]
+    assert np.allclose(local[0] + local[1], full, rtol=1e-5, atol=1e-6 * np.abs(full).max())
+    for c in ctxs:
+        c.close()
