@@ -58,9 +58,9 @@ void hmmcu_host_free(void *p);
  * CUDA-core kernel, which evaluates (x-mu)^2 directly); 0 = always the CUDA-core kernel;
  * 2 = always tensor cores.  Both are device code.
  * "graphs": 1 (default) = hmmcu_estep / hmmcu_mstep replay their launch sequences as CUDA graphs from the third
- * identical call on; "ws_emis" / "ws_acc": 0 = the older single-buffered tensor-core kernels; "seg_fb": 0 = the windowed
- * forward-backward kernel instead of the time-parallel one; "wide_fb": 0 never / 1 (default) from 1,536 utterances on /
- * 2 always the thread-per-chain forward-backward kernels;
+ * identical call on; "ws_emis" / "ws_acc": 0 = the older single-buffered tensor-core kernels; "res_fb": 0 = the windowed
+ * forward-backward kernel (k_fb) instead of the shared-memory-resident one (k_fb_res, the default whenever the utterances fit
+ * and the transition matrices are banded);
  * "upload_chunks": chunks hmmcu_set_features splits the host-to-device copy into (packing overlaps the copy);
  * "mstep_fork": 1 (default) = the accuracy-guard scan and one of the two model packers of hmmcu_mstep run on side streams. */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);

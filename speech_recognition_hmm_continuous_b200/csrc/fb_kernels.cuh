@@ -376,635 +376,4 @@ k_fb(const float *__restrict__ logb, const int64_t *__restrict__ off, const int3
   }
 }
 
-// ================================================================================================
-// k_fb_seg: the same recursions, parallel in time.
-//
-// The chain of an utterance is a product of T linear maps z -> (z A) o b~_t; the map of a segment of frames can
-// be built without knowing where the segment starts by pushing the N unit vectors through it.  So each
-// utterance is cut into kSegs segments and the recursion runs in two passes of T / kSegs steps instead of one of T:
-//   pass 1   segment 0 runs the true chain (and stores its rows); for every other segment, N threads push the
-//            unit vectors e_0 .. e_{N-1} through it (own power-of-two scaling, cumulative exponent kept) and keep
-//            only the end vectors;
-//   boundary one thread per (utterance, direction) walks the segments: start vector of segment s+1 = sum_i a_i
-//            y_i 2^{E_i}, renormalised; this also yields phi, and log P from pass-1 quantities only;
-//   pass 2   every remaining segment runs its true chain from its start vector and stores its rows.
-// Backward is the mirror image (segments from the end, w_{T-1} = e_{N-1}).  All b~ of the CTA's utterances are staged
-// once in shared memory (4 utterances x T x N doubles) and shared by both directions.  The third phase (gamma, xi,
-// den sums) is k_fb's, two warps per utterance.  Used when the utterances fit (fb_seg_fits); k_fb otherwise.
-// ================================================================================================
-constexpr int kSegs = 8;
-constexpr int kSegUtts = 4;
-constexpr int kSegThreads = 288;  // 9 warps: 2 x 36 chain lanes per utterance in pass 1
-
-__host__ __device__ inline size_t fb_seg_smem_bytes(int NS, int Tmax) { return sizeof(double) * (size_t)kSegUtts * ((size_t)Tmax * NS + 2); }
-__host__ __device__ inline bool fb_seg_fits(int NS, int Tmax) { return fb_seg_smem_bytes(NS, Tmax) <= 160 * 1024; }
-
-__device__ __forceinline__ int seg_begin(int s, int T) { return min(T, max(s, (int)(((long long)s * T) / kSegs))); }
-// v * 2^k for |k| possibly large (k < -1000 -> 0; the operands here never need k > 0 by much)
-__device__ __forceinline__ double scale_pow2(double v, int k) {
-  if (k < -1000) return 0.0;
-  if (k > 1000) k = 1000;
-  return v * __hiloint2double((1023 + k) << 20, 0);
-}
-
-template <int NS, bool BANDED>
-__global__ void __launch_bounds__(kSegThreads, 2)
-k_fb_seg(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-         const double *__restrict__ Aall, int U, int Tcap, float *__restrict__ alpha_ws, float *__restrict__ beta_ws,
-         float *__restrict__ gamma, double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp,
-         double *__restrict__ logp_utt) {
-  extern __shared__ __align__(16) uint8_t fb_smem[];
-  const int US = Tcap * NS + 2;                       // per-utterance stride of the staged b~
-  double *bt = reinterpret_cast<double *>(fb_smem);  // [kSegUtts][US]   b~_i(t), t < T
-  __shared__ double sA[kSegUtts][NS * NS];
-  __shared__ double yend[2][kSegUtts][kSegs][NS][NS];  // pass 1: end vector of (direction, utterance, segment, unit vector)
-  __shared__ int yexp[2][kSegUtts][kSegs][NS];         //         and its cumulative exponent
-  __shared__ double zend[2][kSegUtts][NS];             // end vector of the first segment's true chain
-  __shared__ int zexp[2][kSegUtts];
-  __shared__ double sstart[2][kSegUtts][kSegs][NS];    // start vector of every segment (boundary pass)
-  __shared__ double sphi[kSegUtts], slp[kSegUtts], smsum[kSegUtts];
-  __shared__ int64_t sbase[kSegUtts];
-  __shared__ int sT[kSegUtts];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int u0 = blockIdx.x * kSegUtts;
-  for (int idx = tid; idx < kSegUtts * NS * NS; idx += kSegThreads) {
-    const int uu = idx / (NS * NS), k = idx - uu * NS * NS;
-    const int u = u0 + uu;
-    const int v = (u < U) ? u2m[u] : -1;
-    sA[uu][k] = (v >= 0) ? Aall[(int64_t)v * NS * NS + k] : 0.0;
-  }
-  if (tid < kSegUtts) {
-    const int u = u0 + tid;
-    const bool live = u < U && u2m[u] >= 0;
-    sbase[tid] = live ? off[u] : 0;
-    sT[tid] = live ? (int)(off[u + 1] - off[u]) : 0;
-    smsum[tid] = 0.0;
-  }
-  __syncthreads();
-  // ---------------- staging: b~ of every frame of the CTA's utterances ----------------
-  for (int uu = 0; uu < kSegUtts; uu++) {
-    const int T = sT[uu];
-    const float *src = logb + sbase[uu] * NS;
-    double *dst = bt + (size_t)uu * US;
-    for (int t = tid; t < T; t += 2 * kSegThreads) {  // two frames per trip: their loads are in flight together
-      const int t2 = t + kSegThreads;
-      float l[NS], l2[NS];
-      load_lb<NS>(src + (size_t)t * NS, l);
-      if (t2 < T) load_lb<NS>(src + (size_t)t2 * NS, l2);
-      {
-        float m = l[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
-        const float ms = (m > kNegInf) ? m : 0.f;  // all states at -inf: every b~ is 0 (not NaN)
-#pragma unroll
-        for (int i = 0; i < NS; i++) dst[(size_t)t * NS + i] = exp_scaled(l[i] - ms);
-      }
-      if (t2 < T) {
-        float m = l2[0];
-#pragma unroll
-        for (int i = 1; i < NS; i++) m = fmaxf(m, l2[i]);
-        const float ms = (m > kNegInf) ? m : 0.f;
-#pragma unroll
-        for (int i = 0; i < NS; i++) dst[(size_t)t2 * NS + i] = exp_scaled(l2[i] - ms);
-      }
-    }
-  }
-  __syncthreads();
-
-  // one forward step z <- ((z A) o b) 2^-e (first = the step of frame 0: pi o b); one backward step w <- (A (b o w)) 2^-e
-  auto fwd_step = [&](double (&z)[NS], const double (&a)[NS * NS], const double *b, bool first, int &e) {
-    double raw[NS];
-    if (first) {
-#pragma unroll
-      for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? b[0] : 0.0;  // pi = [1,0,..,0]  T-FS:232-234
-    } else {
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        double aux;
-        if (BANDED) {
-          aux = z[i] * a[i * NS + i];
-          if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
-        } else {
-          aux = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
-        }
-        raw[i] = aux * b[i];
-      }
-    }
-    const double r = pow2_scale_max<NS>(raw, e);
-#pragma unroll
-    for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
-  };
-  auto bwd_step = [&](double (&w)[NS], const double (&a)[NS * NS], const double *b, int &e) {
-    double q[NS], raw[NS];
-#pragma unroll
-    for (int j = 0; j < NS; j++) q[j] = b[j] * w[j];
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      double aux;
-      if (BANDED) {
-        aux = a[i * NS + i] * q[i];
-        if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
-      } else {
-        aux = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
-      }
-      raw[i] = aux;
-    }
-    const double r = pow2_scale_max<NS>(raw, e);
-#pragma unroll
-    for (int i = 0; i < NS; i++) w[i] = raw[i] * r;
-  };
-
-  // ---------------- pass 1: true chain of the first segment, unit vectors through the others ----------------
-  constexpr int CPU_ = 1 + (kSegs - 1) * NS;  // chains per (utterance, direction)
-  for (int cid = tid; cid < 2 * kSegUtts * CPU_; cid += kSegThreads) {  // one round for N <= 5
-    const int dir = cid / (kSegUtts * CPU_), rem = cid - dir * (kSegUtts * CPU_);
-    const int uu = rem / CPU_, k = rem - uu * CPU_;
-    const int T = sT[uu];
-    if (T > 0) {
-      double a[NS * NS];
-#pragma unroll
-      for (int q = 0; q < NS * NS; q++) a[q] = sA[uu][q];
-      const double *bw = bt + (size_t)uu * US;
-      const int64_t base = sbase[uu];
-      double z[NS];
-      int esum = 0, e;
-      if (dir == 0) {
-        if (k == 0) {  // frames [0, fs_1): the true chain, rows stored
-#pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = 0.0;
-          const int t1 = seg_begin(1, T);
-          for (int t = 0; t < t1; t++) {
-            fwd_step(z, a, bw + (size_t)t * NS, t == 0, e);
-            esum += e;
-            store_row<NS>(alpha_ws + (base + t) * kFbRow, z);
-          }
-#pragma unroll
-          for (int i = 0; i < NS; i++) zend[0][uu][i] = z[i];
-          zexp[0][uu] = esum;
-        } else {
-          const int sg = 1 + (k - 1) / NS, bi = (k - 1) % NS;
-#pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = (i == bi) ? 1.0 : 0.0;
-          const int t0 = seg_begin(sg, T), t1 = seg_begin(sg + 1, T);
-          for (int t = t0; t < t1; t++) {
-            fwd_step(z, a, bw + (size_t)t * NS, false, e);
-            esum += e;
-          }
-#pragma unroll
-          for (int i = 0; i < NS; i++) yend[0][uu][sg][bi][i] = z[i];
-          yexp[0][uu][sg][bi] = esum;
-        }
-      } else {
-        // backward: w_t for t = T-2 .. 0; step t uses b~ of frame t + 1.  Segment s owns t in [fs_s, min(fs_{s+1}, T-1)).
-        if (k == 0) {  // the last segment: true chain from w_{T-1} = e_{N-1} (final state only, T-FS:1484-1490)
-#pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = (i == NS - 1) ? 1.0 : 0.0;
-          store_row<NS>(beta_ws + (base + T - 1) * kFbRow, z);
-          const int t0 = seg_begin(kSegs - 1, T);
-          for (int t = T - 2; t >= t0; t--) {
-            bwd_step(z, a, bw + (size_t)(t + 1) * NS, e);
-            store_row<NS>(beta_ws + (base + t) * kFbRow, z);
-          }
-#pragma unroll
-          for (int i = 0; i < NS; i++) zend[1][uu][i] = z[i];
-        } else {
-          const int sg = (k - 1) / NS, bi = (k - 1) % NS;  // segments 0 .. kSegs-2
-#pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = (i == bi) ? 1.0 : 0.0;
-          const int t0 = seg_begin(sg, T), t1 = min(seg_begin(sg + 1, T), T - 1);
-          for (int t = t1 - 1; t >= t0; t--) {
-            bwd_step(z, a, bw + (size_t)(t + 1) * NS, e);
-            esum += e;
-          }
-#pragma unroll
-          for (int i = 0; i < NS; i++) yend[1][uu][sg][bi][i] = z[i];
-          yexp[1][uu][sg][bi] = esum;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---------------- boundaries: start vector of every segment; phi and log P (forward) ----------------
-  // one warp per (direction, utterance), lane j holds component j of the running vector
-  if (warp < 2 * kSegUtts) {
-    const int dir = warp / kSegUtts, uu = warp - dir * kSegUtts;
-    if (sT[uu] > 0) {
-      const int j = lane < NS ? lane : 0;
-      double av = (lane < NS) ? zend[dir][uu][j] : 0.0;
-      int etot = (dir == 0) ? zexp[0][uu] : 0;
-      for (int step = 1; step < kSegs; step++) {
-        const int sg = (dir == 0) ? step : kSegs - 1 - step;  // forward: segments 1 .. ; backward: kSegs-2 .. 0
-        if (lane < NS) sstart[dir][uu][sg][j] = av;
-        // lane i: does unit vector i carry weight and survive the segment?  reference exponent = the largest such
-        double ym = 0.0;
-#pragma unroll
-        for (int q = 0; q < NS; q++) ym = fmax(ym, yend[dir][uu][sg][j][q]);
-        const bool alive = lane < NS && av != 0.0 && ym > 0.0;
-        int ex = alive ? yexp[dir][uu][sg][j] : -(1 << 30);
-        int eref = ex;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) eref = max(eref, __shfl_xor_sync(0xffffffffu, eref, o));  // NS <= 8: lanes 0..7
-        const double ci = alive ? scale_pow2(av, ex - eref) : 0.0;
-        double v = 0.0;
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          const double c = __shfl_sync(0xffffffffu, ci, i);
-          v = fma(c, yend[dir][uu][sg][i][j], v);
-        }
-        if (lane >= NS) v = 0.0;
-        if (eref == -(1 << 30)) eref = 0;
-        int be = __double2hiint(v) >> 20;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) be = max(be, __shfl_xor_sync(0xffffffffu, be, o));
-        const bool ok = be > 0 && be < 0x7ff;
-        av = v * __hiloint2double(ok ? (2046 - be) << 20 : 0x3ff00000, 0);
-        etot += eref + (ok ? be - 1023 : 0);
-      }
-      if (dir == 0) {
-        double sm = av;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-        const double last = __shfl_sync(0xffffffffu, av, NS - 1);
-        if (lane == 0) {
-          sphi[uu] = last / sm;                                           // alpha^_{T-1}(N-1)
-          slp[uu] = 0.6931471805599453 * (double)etot + log(last);       // + sum m_t, added in phase 3
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---------------- pass 2: true chains of the remaining segments, rows stored ----------------
-  if (tid < 2 * kSegUtts * (kSegs - 1)) {
-    const int dir = tid / (kSegUtts * (kSegs - 1)), rem = tid - dir * (kSegUtts * (kSegs - 1));
-    const int uu = rem / (kSegs - 1), sx = rem - uu * (kSegs - 1);
-    const int T = sT[uu];
-    if (T > 0) {
-      double a[NS * NS];
-#pragma unroll
-      for (int q = 0; q < NS * NS; q++) a[q] = sA[uu][q];
-      const double *bw = bt + (size_t)uu * US;
-      const int64_t base = sbase[uu];
-      double z[NS];
-      int e;
-      if (dir == 0) {
-        const int sg = 1 + sx;
-#pragma unroll
-        for (int i = 0; i < NS; i++) z[i] = sstart[0][uu][sg][i];
-        const int t0 = seg_begin(sg, T), t1 = seg_begin(sg + 1, T);
-        for (int t = t0; t < t1; t++) {
-          fwd_step(z, a, bw + (size_t)t * NS, false, e);
-          store_row<NS>(alpha_ws + (base + t) * kFbRow, z);
-        }
-      } else {
-        const int sg = sx;  // segments 0 .. kSegs-2
-#pragma unroll
-        for (int i = 0; i < NS; i++) z[i] = sstart[1][uu][sg][i];
-        const int t0 = seg_begin(sg, T), t1 = min(seg_begin(sg + 1, T), T - 1);
-        for (int t = t1 - 1; t >= t0; t--) {
-          bwd_step(z, a, bw + (size_t)(t + 1) * NS, e);
-          store_row<NS>(beta_ws + (base + t) * kFbRow, z);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // ---------------- phase 3: gamma, transition and den sums; two warps per utterance, lanes over frames ----------------
-  if (warp < 2 * kSegUtts) {
-    const int uu = warp >> 1, half = warp & 1;
-    const int u = u0 + uu;
-    const int v = (u < U) ? u2m[u] : -1;
-    if (u < U && v >= 0) {
-      const int64_t base = sbase[uu];
-      const int T = sT[uu];
-      const double *A = sA[uu];
-      const double phi = sphi[uu];
-      double acc_num[NS][2], acc_dt[NS], acc_dm[NS], acc_m = 0.0;
-#pragma unroll
-      for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
-      for (int t = half * 32 + lane; t < T; t += 64) {
-        double al[NS], be[NS], g[NS], G = 0.0;
-        load_row<NS>(alpha_ws + (base + t) * kFbRow, al);
-        load_row<NS>(beta_ws + (base + t) * kFbRow, be);
-        {
-          const double *b0 = bt + (size_t)uu * US + (size_t)t * NS;  // (b~ is at hand; m_t still comes from logb)
-          (void)b0;
-          float l0[NS];
-          load_lb<NS>(logb + (base + t) * NS, l0);
-          float m = l0[0];
-#pragma unroll
-          for (int i = 1; i < NS; i++) m = fmaxf(m, l0[i]);
-          acc_m += (double)m;
-        }
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          g[i] = al[i] * be[i];
-          G += g[i];
-        }
-        const double sc = (G > 0.0) ? phi / G : 0.0;
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-          g[i] *= sc;
-          gamma[(base + t) * NS + i] = (float)g[i];
-          acc_dm[i] += g[i];
-        }
-        if (t < T - 1) {
-          double q[NS], b1[NS];
-          load_row<NS>(beta_ws + (base + t + 1) * kFbRow, b1);
-          const double *bn = bt + (size_t)uu * US + (size_t)(t + 1) * NS;  // b~ of frame t + 1, staged above
-#pragma unroll
-          for (int j = 0; j < NS; j++) q[j] = bn[j] * b1[j];
-          double Z = 0.0;
-#pragma unroll
-          for (int i = 0; i < NS; i++) {
-            double rb = 0.0;
-#pragma unroll
-            for (int j = 0; j < NS; j++) rb = fma(A[i * NS + j], q[j], rb);
-            Z = fma(al[i], rb, Z);
-          }
-          const double zs = (Z > 0.0) ? phi / Z : 0.0;
-#pragma unroll
-          for (int i = 0; i < NS; i++) {
-            acc_dt[i] += g[i];
-            acc_num[i][0] += al[i] * A[i * NS + i] * q[i] * zs;
-            if (i + 1 < NS) acc_num[i][1] += al[i] * A[i * NS + i + 1] * q[i + 1] * zs;
-          }
-        }
-      }
-      double *st = stats + (int64_t)v * stats_stride;
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        const double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
-        const double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
-        if (lane == 0) {
-          atomicAdd(st + i * NS + i, n0);
-          if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
-          atomicAdd(st + NS * NS + i, dt);
-          atomicAdd(st + NS * NS + NS + i, dm);
-        }
-      }
-      const double msum = warp_sum(acc_m);
-      if (lane == 0) atomicAdd(&smsum[uu], msum);
-    }
-  }
-  __syncthreads();
-  if (tid < kSegUtts) {
-    const int u = u0 + tid;
-    if (u < U) {
-      const int v = u2m[u];
-      if (v < 0) {
-        if (logp_utt) logp_utt[u] = 0.0;
-      } else {
-        const double lp = slp[tid] + smsum[tid];  // calc_probability T-FS:1546-1549
-        double *st = stats + (int64_t)v * stats_stride;
-        atomicAdd(st + off_sumlogp, lp);
-        atomicAdd(st + off_sumlogp + 1, 1.0);
-        if (logp_utt) logp_utt[u] = lp;
-      }
-    }
-  }
-}
-
-// ================================================================================================
-// k_fb_wide + k_fb_gamma: the recursions for MANY utterances (a C3 shard: 12,500 per GPU).
-// With thousands of utterances there are enough independent chains to fill the machine without cutting them up:
-// one thread per (utterance, direction), every lane of every warp busy, log-emissions read straight from global
-// memory four frames ahead (as the decode scorers do), b~ formed on the fly.  The third phase (gamma, xi, den
-// sums) is a kernel of its own, one warp per utterance.  At 1,000 utterances this is slower than k_fb_seg (2,000
-// threads cannot hide a 300-step chain); hmmcu_estep picks by the number of utterances.
-// ================================================================================================
-constexpr int kWideThreads = 128;
-constexpr int kWidePF = 4;
-
-// Log-emissions are fetched in chunks of four frames aligned to the absolute frame index: 4 x NS floats = NS
-// 16-byte loads (a lane per utterance makes every load instruction touch 32 sectors, so the fewer the better).
-// The chunk of the next four frames is in flight while the current one is consumed; a chunk may reach a few
-// frames beyond the utterance or the buffer (the allocation has slack), those frames are skipped.
-template <int NS, bool BANDED>
-__global__ void __launch_bounds__(kWideThreads)
-k_fb_wide(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-          const double *__restrict__ Aall, int U, float *__restrict__ alpha_ws, float *__restrict__ beta_ws,
-          double *__restrict__ phi_utt, double *__restrict__ lp_utt) {
-  const int cid = blockIdx.x * kWideThreads + threadIdx.x;
-  if (cid >= 2 * U) return;
-  const int dir = cid / U, u = cid - dir * U;  // forward chains first: the lanes of a warp share a direction
-  const int v = u2m[u];
-  if (v < 0) return;
-  const int64_t base = off[u];
-  const int T = (int)(off[u + 1] - base);
-  double a[NS * NS];
-#pragma unroll
-  for (int k = 0; k < NS * NS; k++) a[k] = Aall[(int64_t)v * NS * NS + k];
-  double z[NS];
-  const float4 *lb4 = reinterpret_cast<const float4 *>(logb);
-  auto load_chunk = [&](int64_t c, float (&buf)[4 * NS]) {
-    const float4 *p = lb4 + c * NS;
-#pragma unroll
-    for (int q = 0; q < NS; q++) {
-      const float4 x = __ldg(p + q);
-      buf[4 * q] = x.x; buf[4 * q + 1] = x.y; buf[4 * q + 2] = x.z; buf[4 * q + 3] = x.w;
-    }
-  };
-  float nxt[4 * NS], cur[4 * NS];
-  if (dir == 0) {
-#pragma unroll
-    for (int i = 0; i < NS; i++) z[i] = 0.0;
-    int esum = 0;
-    const int64_t c0 = base >> 2, c1 = (base + T - 1) >> 2;
-    load_chunk(c0, nxt);
-    for (int64_t c = c0; c <= c1; c++) {
-#pragma unroll
-      for (int q = 0; q < 4 * NS; q++) cur[q] = nxt[q];
-      if (c < c1) load_chunk(c + 1, nxt);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int64_t f = 4 * c + k;
-        if (f >= base && f < base + T) {
-          const float *l = cur + k * NS;
-          float m = l[0];
-#pragma unroll
-          for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
-          const float ms = (m > kNegInf) ? m : 0.f;
-          double raw[NS];
-          if (f == base) {
-#pragma unroll
-            for (int i = 0; i < NS; i++) raw[i] = (i == 0) ? exp_scaled(l[0] - ms) : 0.0;  // pi = [1,0,..,0]
-          } else {
-#pragma unroll
-            for (int i = 0; i < NS; i++) {
-              double aux;
-              if (BANDED) {
-                aux = z[i] * a[i * NS + i];
-                if (i > 0) aux = fma(z[i - 1], a[(i - 1) * NS + i], aux);
-              } else {
-                aux = 0.0;
-#pragma unroll
-                for (int j = 0; j < NS; j++) aux = fma(z[j], a[j * NS + i], aux);
-              }
-              raw[i] = aux * exp_scaled(l[i] - ms);
-            }
-          }
-          int e;
-          const double r = pow2_scale_max<NS>(raw, e);
-#pragma unroll
-          for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
-          esum += e;
-          store_row<NS>(alpha_ws + f * kFbRow, z);
-        }
-      }
-    }
-    double sm = z[0];
-#pragma unroll
-    for (int i = 1; i < NS; i++) sm += z[i];
-    phi_utt[u] = z[NS - 1] / sm;                                            // alpha^_{T-1}(N-1)
-    lp_utt[u] = 0.6931471805599453 * (double)esum + log(z[NS - 1]);        // + sum m_t, added by k_fb_gamma
-  } else {
-    // backward: w_{T-1} = e_{N-1}; frame f = T-1 .. 1 (relative) turns w_f into w_{f-1} with the emissions of frame f
-#pragma unroll
-    for (int i = 0; i < NS; i++) z[i] = (i == NS - 1) ? 1.0 : 0.0;
-    store_row<NS>(beta_ws + (base + T - 1) * kFbRow, z);
-    if (T > 1) {
-      const int64_t chi = (base + T - 1) >> 2, clo = (base + 1) >> 2;
-      load_chunk(chi, nxt);
-      for (int64_t c = chi; c >= clo; c--) {
-#pragma unroll
-        for (int q = 0; q < 4 * NS; q++) cur[q] = nxt[q];
-        if (c > clo) load_chunk(c - 1, nxt);
-#pragma unroll
-        for (int k = 3; k >= 0; k--) {
-          const int64_t f = 4 * c + k;
-          if (f >= base + 1 && f <= base + T - 1) {
-            const float *l = cur + k * NS;
-            float m = l[0];
-#pragma unroll
-            for (int i = 1; i < NS; i++) m = fmaxf(m, l[i]);
-            const float ms = (m > kNegInf) ? m : 0.f;
-            double q[NS], raw[NS];
-#pragma unroll
-            for (int j = 0; j < NS; j++) q[j] = exp_scaled(l[j] - ms) * z[j];
-#pragma unroll
-            for (int i = 0; i < NS; i++) {
-              double aux;
-              if (BANDED) {
-                aux = a[i * NS + i] * q[i];
-                if (i + 1 < NS) aux = fma(a[i * NS + i + 1], q[i + 1], aux);
-              } else {
-                aux = 0.0;
-#pragma unroll
-                for (int j = 0; j < NS; j++) aux = fma(a[i * NS + j], q[j], aux);
-              }
-              raw[i] = aux;
-            }
-            int e;
-            const double r = pow2_scale_max<NS>(raw, e);
-#pragma unroll
-            for (int i = 0; i < NS; i++) z[i] = raw[i] * r;
-            store_row<NS>(beta_ws + (f - 1) * kFbRow, z);
-          }
-        }
-      }
-    }
-  }
-}
-
-// third phase for k_fb_wide: one warp per utterance, lanes over frames (the same arithmetic as k_fb's phase 2)
-constexpr int kGammaWarps = 8;
-template <int NS>
-__global__ void __launch_bounds__(kGammaWarps * 32, 2)
-k_fb_gamma(const float *__restrict__ logb, const int64_t *__restrict__ off, const int32_t *__restrict__ u2m,
-           const double *__restrict__ Aall, int U, const float *__restrict__ alpha_ws, const float *__restrict__ beta_ws,
-           const double *__restrict__ phi_utt, const double *__restrict__ lp_utt, float *__restrict__ gamma,
-           double *__restrict__ stats, int64_t stats_stride, int64_t off_sumlogp, double *__restrict__ logp_utt) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u = blockIdx.x * kGammaWarps + warp;
-  if (u >= U) return;
-  const int v = u2m[u];
-  if (v < 0) {  // masked utterance (its model has converged)
-    if (lane == 0 && logp_utt) logp_utt[u] = 0.0;
-    return;
-  }
-  const int64_t base = off[u];
-  const int T = (int)(off[u + 1] - base);
-  double A[NS * NS];
-#pragma unroll
-  for (int k = 0; k < NS * NS; k++) A[k] = Aall[(int64_t)v * NS * NS + k];
-  const double phi = phi_utt[u];
-  double acc_num[NS][2], acc_dt[NS], acc_dm[NS], acc_m = 0.0;
-#pragma unroll
-  for (int i = 0; i < NS; i++) { acc_num[i][0] = acc_num[i][1] = 0.0; acc_dt[i] = 0.0; acc_dm[i] = 0.0; }
-  for (int t = lane; t < T; t += 32) {
-    double al[NS], be[NS], g[NS], G = 0.0;
-    load_row<NS>(alpha_ws + (base + t) * kFbRow, al);
-    load_row<NS>(beta_ws + (base + t) * kFbRow, be);
-    {
-      float l0[NS];
-      load_lb<NS>(logb + (base + t) * NS, l0);
-      float m = l0[0];
-#pragma unroll
-      for (int i = 1; i < NS; i++) m = fmaxf(m, l0[i]);
-      acc_m += (double)m;
-    }
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      g[i] = al[i] * be[i];
-      G += g[i];
-    }
-    const double sc = (G > 0.0) ? phi / G : 0.0;  // unreachable final state: no occupancy, as the reference
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-      g[i] *= sc;  // alpha^ beta^ / c   T-FS:1617,1658,1709
-      gamma[(base + t) * NS + i] = (float)g[i];
-      acc_dm[i] += g[i];
-    }
-    if (t < T - 1) {
-      float l1[NS];
-      load_lb<NS>(logb + (base + t + 1) * NS, l1);
-      float m = l1[0];
-#pragma unroll
-      for (int i = 1; i < NS; i++) m = fmaxf(m, l1[i]);
-      double q[NS], b1[NS];
-      load_row<NS>(beta_ws + (base + t + 1) * kFbRow, b1);
-#pragma unroll
-      for (int j = 0; j < NS; j++) q[j] = exp_scaled(l1[j] - ((m > kNegInf) ? m : 0.f)) * b1[j];
-      double Z = 0.0;
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        double rb = 0.0;
-#pragma unroll
-        for (int j = 0; j < NS; j++) rb = fma(A[i * NS + j], q[j], rb);
-        Z = fma(al[i], rb, Z);
-      }
-      const double zs = (Z > 0.0) ? phi / Z : 0.0;
-#pragma unroll
-      for (int i = 0; i < NS; i++) {
-        acc_dt[i] += g[i];
-        acc_num[i][0] += al[i] * A[i * NS + i] * q[i] * zs;                              // band j = i   T-FS:1611
-        if (i + 1 < NS) acc_num[i][1] += al[i] * A[i * NS + i + 1] * q[i + 1] * zs;      // j = i + 1
-      }
-    }
-  }
-  double *st = stats + (int64_t)v * stats_stride;
-#pragma unroll
-  for (int i = 0; i < NS; i++) {
-    const double n0 = warp_sum(acc_num[i][0]), n1 = warp_sum(acc_num[i][1]);
-    const double dt = warp_sum(acc_dt[i]), dm = warp_sum(acc_dm[i]);
-    if (lane == 0) {
-      atomicAdd(st + i * NS + i, n0);
-      if (i + 1 < NS) atomicAdd(st + i * NS + i + 1, n1);
-      atomicAdd(st + NS * NS + i, dt);
-      atomicAdd(st + NS * NS + NS + i, dm);
-    }
-  }
-  const double msum = warp_sum(acc_m);
-  if (lane == 0) {
-    const double lp = lp_utt[u] + msum;  // calc_probability T-FS:1546-1549
-    atomicAdd(st + off_sumlogp, lp);
-    atomicAdd(st + off_sumlogp + 1, 1.0);
-    if (logp_utt) logp_utt[u] = lp;
-  }
-}
-
 }  // namespace hmmk

@@ -362,7 +362,7 @@ k_fb_res(const float *__restrict__ logb, const int64_t *__restrict__ off, const 
         }
 #pragma unroll
         for (int i = 0; i < NS; i++) Z += gu[i];
-        const double sc = (Z > 0.0) ? phi / Z : 0.0;  // unreachable final state: no occupancy, as the reference
+        const double sc = (Z > 0.0) ? phi * __drcp_rn(Z) : 0.0;  // unreachable final state: no occupancy, as the reference
 #pragma unroll
         for (int i = 0; i < NS; i++) {
           const double g = gu[i] * sc;                 // alpha^ beta^ / c   T-FS:1617,1658,1709

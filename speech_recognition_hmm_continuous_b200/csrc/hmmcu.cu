@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -25,7 +26,7 @@ using namespace hmmk;
 namespace {
 
 char g_create_err[512] = "";
-uint64_t g_alloc_epoch = 0;  // bumped whenever a device buffer moves: cached CUDA graphs hold raw pointers
+std::atomic<uint64_t> g_alloc_epoch{0};  // bumped whenever a device buffer moves (any context, any host thread): cached CUDA graphs hold raw pointers
 
 struct DevBuf {
   void *p = nullptr;
@@ -130,7 +131,7 @@ struct hmmcu_ctx {
 
   // training map
   std::vector<int32_t> u2m;
-  DevBuf u2m_d, mus_d, mu_d, tiles_d, phi_utt_d, lp_part_d;
+  DevBuf u2m_d, mus_d, mu_d, tiles_d;
   DevBuf vit_map, vit_tiles;
   std::vector<int32_t> vit_u2m;
   int64_t n_vit_tiles = 0;
@@ -157,8 +158,6 @@ struct hmmcu_ctx {
   DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
-  int use_seg_fb = 1;  // time-parallel forward-backward (k_fb_seg) when the utterances fit in shared memory (0 = k_fb)
-  int use_wide_fb = 1; // 1 = thread-per-chain forward-backward (k_fb_wide) beyond kWideMinUtts utterances, 2 = always, 0 = never
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
   // peer all-reduce over NVLink (hmmcu_peer_*): my receive area [2 slot sets][world][stats_n] doubles, then
@@ -169,6 +168,7 @@ struct hmmcu_ctx {
   int peer_rank = -1, peer_world = 0;
   int64_t peer_n = 0;                   // doubles per slot the area was sized for
   int64_t n_res_batches = 0;
+  int n_live = 0;         // utterances of the training map that belong to a model (the others are masked)
   bool res_fits = false;  // every utterance of the training map fits one team's shared memory
   int debug_acc = 0;
   bool acc_dirty = true;
@@ -253,7 +253,7 @@ template <typename F>
 static int run_graphed(hmmcu_ctx *ctx, GraphSlot &gs, uint64_t key, F &&enqueue) {
   // (per-kernel timing records events between the kernels; events recorded by graph nodes cannot be timed)
   if (!ctx->use_graph || ctx->timing || gs.bad) return enqueue();
-  key = key * 0x9E3779B97F4A7C15ull + g_alloc_epoch * 1000003ull + ctx->cfg_epoch;
+  key = key * 0x9E3779B97F4A7C15ull + g_alloc_epoch.load() * 1000003ull + ctx->cfg_epoch;
   if (gs.key != key) {
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
     gs.exec = nullptr;
@@ -367,7 +367,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
-                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles, &ctx->phi_utt_d, &ctx->lp_part_d,
+                    &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles,
                     &ctx->res_order, &ctx->res_upos, &ctx->res_batches, &ctx->res_counter, &ctx->ustats};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
@@ -459,8 +459,6 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
-  if (strcmp(key, "seg_fb") == 0) { ctx->use_seg_fb = value; return HMMCU_OK; }
-  if (strcmp(key, "wide_fb") == 0) { ctx->use_wide_fb = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
@@ -668,6 +666,7 @@ void *hmmcu_staging(hmmcu_ctx *ctx, int slot, uint64_t bytes) {
 int hmmcu_features_begin(hmmcu_ctx *ctx, const int64_t *frame_off, int U, int D) {
   if (!ctx) return HMMCU_EINVAL;
   if (U < 1 || D < 1 || !frame_off) return fail(ctx, HMMCU_EINVAL, "features_begin: bad arguments");
+  if (ctx->stream_open) CK(cudaStreamSynchronize(ctx->st_copy));  // an abandoned ingest: its copies may still be reading the staging buffers
   int rc = features_geometry(ctx, frame_off, U, D);
   if (rc) return rc;
   ctx->have_features = false;  // until _end
@@ -1533,6 +1532,7 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
   {  // k_fb_res: the live utterances longest first, cut into batches that fit one team's shared memory; the row of
      // every utterance in the per-utterance statistics (= its position in the model-grouped list)
     const int nlive = start[V];
+    ctx->n_live = nlive;
     std::vector<int32_t> order(utts.begin(), utts.begin() + nlive), upos(std::max(U, 1), 0);
     for (int k = 0; k < nlive; k++) upos[utts[k]] = k;
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return ctx->off[a + 1] - ctx->off[a] > ctx->off[b + 1] - ctx->off[b]; });
@@ -1597,8 +1597,6 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (!(ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0)) {  // k_fb_res keeps alpha / beta on the SM
       CK(ctx->alpha_ws.ensure(sizeof(float) * F * kFbRow));
       CK(ctx->beta_ws.ensure(sizeof(float) * F * kFbRow));
-      CK(ctx->phi_utt_d.ensure(sizeof(double) * U));
-      CK(ctx->lp_part_d.ensure(sizeof(double) * U));
     }
     CK(ctx->logp_utt_d.ensure(sizeof(double) * U));
     if (ws_emis) {
@@ -1622,6 +1620,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (phases & 1) CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(double) * ctx->stats_n, ctx->st));
     if (U == 0) return HMMCU_OK;
     int rc2;
+    bool fb_forked = false;
     // 1. emissions (+ per-mixture posteriors on the CUDA-core path)
     if (phases & 1) {
     t_begin(ctx, "emis");
@@ -1635,13 +1634,11 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (phases & 2) {
     t_begin(ctx, "fwdbwd");
     {
-      // many utterances: one thread per chain fills the machine (a k_fb_seg CTA holds four utterances and two fit per SM)
-      constexpr int kWideMinUtts = 1536;
-      if (ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0) {
+        if (ctx->use_res_fb && ctx->banded && ctx->res_fits && ctx->n_res_batches > 0) {
         // every utterance resident in shared memory: log-emissions read once, gamma written once (fbres_kernels.cuh)
         CK(cudaMemsetAsync(ctx->res_counter.p, 0, sizeof(int), ctx->st));
         if (ctx->debug_acc & 8) CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
-        CK(cudaMemsetAsync(ctx->logp_utt_d.p, 0, sizeof(double) * U, ctx->st));  // masked utterances report 0
+        if (ctx->n_live < U) CK(cudaMemsetAsync(ctx->logp_utt_d.p, 0, sizeof(double) * U, ctx->st));  // masked utterances report 0
         const int grid = (int)std::min<int64_t>(ctx->n_res_batches, ctx->sm_count);
         DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_res<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kResSmemBytes),
                        k_fb_res<NS><<<grid, kResThreads, kResSmemBytes, ctx->st>>>(
@@ -1650,40 +1647,16 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
                            ctx->gamma.as<float>(), ctx->ustats.as<double>(), ctx->logp_utt_d.as<double>(),
                            (ctx->debug_acc & 8) ? (long long *)ctx->acc_dbg.p : nullptr)));
         LAUNCH_CHECK();
-        k_fb_reduce<<<V, 1024, 0, ctx->st>>>(ctx->ustats.as<double>(), N, ctx->mus_d.as<int32_t>(), V, ctx->stats.as<double>(), ss, off_lp);
-        LAUNCH_CHECK();
-      } else if (ctx->use_wide_fb == 2 || (ctx->use_wide_fb == 1 && U >= kWideMinUtts)) {
-        const int blocks = (2 * U + kWideThreads - 1) / kWideThreads;
-        if (ctx->banded) {
-          DISPATCH_N(N, (k_fb_wide<NS, true><<<blocks, kWideThreads, 0, ctx->st>>>(lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
-                                                                                  ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
-                                                                                  ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
-        } else {
-          DISPATCH_N(N, (k_fb_wide<NS, false><<<blocks, kWideThreads, 0, ctx->st>>>(lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(),
-                                                                                   ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(),
-                                                                                   ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>())));
+        // the per-model sums of the transition statistics feed nothing before the M-step: beside the accumulate kernel
+        fb_forked = !ctx->timing && (phases & 4) && ctx->mstep_fork;
+        if (fb_forked) {
+          CK(cudaEventRecord(ctx->ev_fork[0], ctx->st));
+          CK(cudaStreamWaitEvent(ctx->st_aux[0], ctx->ev_fork[0], 0));
         }
+        k_fb_reduce<<<V, 1024, 0, fb_forked ? ctx->st_aux[0] : ctx->st>>>(ctx->ustats.as<double>(), N, ctx->mus_d.as<int32_t>(), V, ctx->stats.as<double>(), ss,
+                                                                        off_lp);
         LAUNCH_CHECK();
-        DISPATCH_N(N, (k_fb_gamma<NS><<<(U + kGammaWarps - 1) / kGammaWarps, kGammaWarps * 32, 0, ctx->st>>>(
-                          lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->alpha_ws.as<float>(),
-                          ctx->beta_ws.as<float>(), ctx->phi_utt_d.as<double>(), ctx->lp_part_d.as<double>(), ctx->gamma.as<float>(),
-                          ctx->stats.as<double>(), ss, off_lp, ctx->logp_utt_d.as<double>())));
-        LAUNCH_CHECK();
-      } else if (ctx->use_seg_fb && fb_seg_fits(N, ctx->Tmax)) {
-        const int blocks = (U + kSegUtts - 1) / kSegUtts;
-        const size_t fsm = fb_seg_smem_bytes(N, ctx->Tmax);
-        if (ctx->banded) {
-          DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, true><<<blocks, kSegThreads, fsm, ctx->st>>>(
-                            lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
-                            ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
-                            ss, off_lp, ctx->logp_utt_d.as<double>())));
-        } else {
-          DISPATCH_N(N, (cudaFuncSetAttribute(k_fb_seg<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm), k_fb_seg<NS, false><<<blocks, kSegThreads, fsm, ctx->st>>>(
-                            lb_fb, ctx->off_d.as<int64_t>(), ctx->u2m_d.as<int32_t>(), ctx->A.as<double>(), U, ctx->Tmax,
-                            ctx->alpha_ws.as<float>(), ctx->beta_ws.as<float>(), ctx->gamma.as<float>(), ctx->stats.as<double>(),
-                            ss, off_lp, ctx->logp_utt_d.as<double>())));
-        }
-        LAUNCH_CHECK();
+        if (fb_forked) CK(cudaEventRecord(ctx->ev_join[0], ctx->st_aux[0]));
       } else {
       const int blocks = (U + kFbUtts - 1) / kFbUtts;
       const size_t fsm = fb_smem_bytes(N);
@@ -1704,7 +1677,10 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     t_end(ctx, "fwdbwd");
     }
     // 3. mixture accumulators
-    if (!(phases & 4)) return HMMCU_OK;
+    if (!(phases & 4)) {
+      if (fb_forked) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[0], 0));
+      return HMMCU_OK;
+    }
     t_begin(ctx, "accum");
     if (ws_acc) {
       const size_t smem = ws_acc_smem_bytes(2 * DP);
@@ -1768,6 +1744,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
       LAUNCH_CHECK();
     }
     t_end(ctx, "accum");
+    if (fb_forked) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[0], 0));
     return HMMCU_OK;
   };
   const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 15) << 9);

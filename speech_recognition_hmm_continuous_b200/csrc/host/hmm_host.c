@@ -265,7 +265,10 @@ int hmmh_init_model(hmmh_model *m, const double *x, const int64_t *frame_off, in
   int *seg = (int *)malloc(sizeof(int) * (N + 1));
   int *ord = (int *)malloc(sizeof(int) * (M > 0 ? M : 1));
   int *dur = (int *)calloc((size_t)N, sizeof(int));
-  if (!cent || !sum || !dist || !cnt || !seg || !ord || !dur) return HMMCU_ENOMEM;
+  if (!cent || !sum || !dist || !cnt || !seg || !ord || !dur) {
+    free(cent); free(sum); free(dist); free(cnt); free(seg); free(ord); free(dur);
+    return HMMCU_ENOMEM;
+  }
   int which = 0;
 
   /* one centroid per state: the mean of its segment over all utterances (T-FS:996-1030) */

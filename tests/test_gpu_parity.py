@@ -714,17 +714,14 @@ def test_device_initial_models_are_bit_identical_to_the_host_builder(N, M):
 
 
 def test_forward_backward_kernels_agree():
-    """k_fb_res (whole utterance resident in shared memory, the default), k_fb_seg (segments, unit vectors, boundary
-    combination) and k_fb_wide + k_fb_gamma (thread per chain) against k_fb (one chain per utterance, windows): same
-    statistics and log-likelihoods; ragged lengths including T < 8 segments and T < N; an utterance too long for
-    the resident kernel's shared memory takes the windowed kernel on its own."""
+    """k_fb_res (whole utterance resident in shared memory, the default) against k_fb (one chain per utterance, windows of
+    64 frames): same statistics and log-likelihoods; ragged lengths including T = 3 < N; an utterance too long for the
+    resident kernel's shared memory takes the windowed kernel on its own."""
     ms, x, off, labels = _synth(2, 5, 3, 10, seed=777, tmin=3, tmax=140)
     out = []
-    for res, seg, wide in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 2)):
+    for res in (0, 1):
         c = api.Context(0)
         c.set_option("res_fb", res)
-        c.set_option("seg_fb", seg)
-        c.set_option("wide_fb", wide)  # 2 = the thread-per-chain kernels (k_fb_wide + k_fb_gamma) whatever the count
         c.set_features(x, off)
         c.set_models(ms)
         out.append(c.estep(labels))
