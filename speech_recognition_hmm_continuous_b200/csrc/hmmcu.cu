@@ -103,8 +103,7 @@ struct hmmcu_ctx {
   bool timing = false;
   int use_graph = 1;          // replay the E-step / M-step launch sequences as CUDA graphs ("graphs" option)
   uint64_t cfg_epoch = 0;     // bumped by everything that changes what those sequences launch
-  GraphSlot g_estep, g_mstep[2];  // the M-step alternates between the two halves of the EM state (k_mstep_fused)
-  int em_par = 0;             // half of em_old / em_active that holds the current EM state
+  GraphSlot g_estep, g_mstep;
   int train_path = 0;         // emission / accumulate path of the last E-step: 0 CUDA cores, 1 k_emis_tc, 2 warp-specialised
   std::map<std::string, Timer> timers;
 
@@ -159,7 +158,6 @@ struct hmmcu_ctx {
   DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
-  int use_fused_mstep = 1;  // one launch for the stopping rule, the M-step and the re-packing (k_mstep_fused)
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
   // peer all-reduce over NVLink (hmmcu_peer_*): my receive area [2 slot sets][world][stats_n] doubles, then
@@ -378,8 +376,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
     for (auto &pr : kv.second.pairs) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
   }
   if (ctx->g_estep.exec) cudaGraphExecDestroy(ctx->g_estep.exec);
-  for (int k = 0; k < 2; k++)
-    if (ctx->g_mstep[k].exec) cudaGraphExecDestroy(ctx->g_mstep[k].exec);
+  if (ctx->g_mstep.exec) cudaGraphExecDestroy(ctx->g_mstep.exec);
   if (ctx->ctl_h) cudaFreeHost(ctx->ctl_h);
   if (ctx->ctr_h) cudaFreeHost(ctx->ctr_h);
   if (ctx->path_h) cudaFreeHost(ctx->path_h);
@@ -463,7 +460,6 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
-  if (strcmp(key, "fused_mstep") == 0) { ctx->use_fused_mstep = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1800,14 +1796,12 @@ int hmmcu_em_reset(hmmcu_ctx *ctx) {
   if (!ctx || !ctx->have_models) return fail(ctx, HMMCU_EINVAL, "em_reset: set the models first");
   CK(cudaSetDevice(ctx->dev));
   const int V = ctx->V;
-  CK(ctx->em_old.ensure(sizeof(double) * 2 * V));   // two halves: k_mstep_fused reads one and writes the other
-  CK(ctx->em_active.ensure(sizeof(int) * 2 * V));
-  std::vector<double> one(2 * (size_t)V, 1.0);  // old_probab starts at 1.0, T-FS:228
-  std::vector<int> act(2 * (size_t)V, 1);
-  CK(cudaMemcpyAsync(ctx->em_old.p, one.data(), sizeof(double) * 2 * V, cudaMemcpyHostToDevice, ctx->st));
-  CK(cudaMemcpyAsync(ctx->em_active.p, act.data(), sizeof(int) * 2 * V, cudaMemcpyHostToDevice, ctx->st));
-  ctx->em_par = 0;
-  ctx->cfg_epoch++;
+  CK(ctx->em_old.ensure(sizeof(double) * V));
+  CK(ctx->em_active.ensure(sizeof(int) * V));
+  std::vector<double> one(V, 1.0);  // old_probab starts at 1.0, T-FS:228
+  std::vector<int> act(V, 1);
+  CK(cudaMemcpyAsync(ctx->em_old.p, one.data(), sizeof(double) * V, cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->em_active.p, act.data(), sizeof(int) * V, cudaMemcpyHostToDevice, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }
@@ -1829,16 +1823,20 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   // are rebuilt here, inside the same launch sequence, instead of lazily by the next E-step.
   const bool repack = ctx->train_path == 2 && !ctx->pack_dirty && !ctx->ws_train.dirty && !ctx->acc_dirty && !ctx->kc_dirty &&
                       ctx->have_features && ctx->Dm == ctx->D;
-  const int par = ctx->em_par;
-  double *em_old_cur = ctx->em_old.as<double>() + (size_t)par * V;
-  int *em_act_cur = ctx->em_active.as<int>() + (size_t)par * V;
-  const bool fused = repack && ctx->use_fused_mstep;
   auto enqueue = [&]() -> int {
     t_begin(ctx, "mstep");
+    k_mstep_ctl<<<(V + 127) / 128, 128, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, V, threshold, ctx->em_old.as<double>(),
+                                                      ctx->em_active.as<int>(), ctx->ctl_d.as<double>(), ctx->upd_d.as<int>());
+    LAUNCH_CHECK();
+    k_mstep_apply<<<dim3(1 + (ctx->G + 7) / 8, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, ctx->N, ctx->M, ctx->Dm,
+                                                                       1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->upd_d.as<int>(),
+                                                                       ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(),
+                                                                       ctx->iv.as<double>(), ctx->det.as<double>());
+    LAUNCH_CHECK();
     int rc2;
-    // The accuracy-guard scan (and, on the unfused path, the second W packer) does not feed the main chain (new
-    // parameters -> kc -> emission images): side streams, joined before the control block is read back.  With the
-    // per-kernel timers on everything stays on one stream, so that the timers keep their meaning.
+    // The accuracy-guard scan and the second W packer do not feed the main chain (new parameters -> kc -> emission
+    // images): they run on side streams, joined before the control block is read back.  With the per-kernel timers
+    // on everything stays on one stream, so that the timers keep their meaning.
     const bool fork = !ctx->timing && ctx->mstep_fork;
     auto on_stream = [&](cudaStream_t side, auto launch) -> int {
       cudaStream_t keep = ctx->st;
@@ -1847,26 +1845,6 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
       ctx->st = keep;
       return r;
     };
-    if (fused) {
-      // stopping rule + re-estimation + kc + both W images in one launch; the EM state moves to the other half
-      hmmcu_ctx::TcSet &ts = ctx->ws_train;
-      k_mstep_fused<<<dim3(ctx->N, V), 256, 0, ctx->st>>>(
-          ctx->stats.as<double>(), ssz, V, ctx->N, ctx->M, ctx->Dm, round_up(ctx->Dm + 1, 4), 1.0e-5 /* FINITE_PROBAB, T-FS:39 */, threshold,
-          em_old_cur, em_act_cur, ctx->em_old.as<double>() + (size_t)(par ^ 1) * V, ctx->em_active.as<int>() + (size_t)(par ^ 1) * V,
-          ctx->ctl_d.as<double>(), ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->det.as<double>(),
-          ctx->ctr.as<double>(), ctx->kc2.as<float>(), ts.images.as<float>(), ws_pad_m(ctx->M), ts.TN, ts.SCt, ctx->acc_images.as<float>(),
-          ctx->acc_kc.as<float>());
-      LAUNCH_CHECK();
-    } else {
-      k_mstep_ctl<<<(V + 127) / 128, 128, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, V, threshold, em_old_cur, em_act_cur, ctx->ctl_d.as<double>(),
-                                                        ctx->upd_d.as<int>());
-      LAUNCH_CHECK();
-      k_mstep_apply<<<dim3(1 + (ctx->G + 7) / 8, V), 256, 0, ctx->st>>>(ctx->stats.as<double>(), ssz, ctx->N, ctx->M, ctx->Dm,
-                                                                         1.0e-5 /* FINITE_PROBAB, T-FS:39 */, ctx->upd_d.as<int>(),
-                                                                         ctx->A.as<double>(), ctx->c.as<double>(), ctx->mu.as<double>(),
-                                                                         ctx->iv.as<double>(), ctx->det.as<double>());
-      LAUNCH_CHECK();
-    }
     if (fork) {
       CK(cudaEventRecord(ctx->ev_fork[0], ctx->st));
       CK(cudaStreamWaitEvent(ctx->st_aux[0], ctx->ev_fork[0], 0));
@@ -1876,7 +1854,7 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
       if ((rc2 = launch_kappa(ctx, ctx->ctl_d.as<double>() + 3 * V)) != HMMCU_OK) return rc2;
     }
     t_end(ctx, "mstep");
-    if (repack && !fused) {
+    if (repack) {
       t_begin(ctx, "pack");
       if ((rc2 = launch_pack_kc(ctx)) != HMMCU_OK) return rc2;
       if (fork) {
@@ -1896,9 +1874,7 @@ int hmmcu_mstep(hmmcu_ctx *ctx, double threshold, double *sum_logp, double *n_ut
   };
   uint64_t tbits;
   memcpy(&tbits, &threshold, sizeof(tbits));
-  if ((rc = run_graphed(ctx, ctx->g_mstep[par], (tbits * 31u) ^ (repack ? 2u : 0u) ^ (ctx->mstep_fork ? 4u : 0u) ^ (fused ? 8u : 0u) ^ (par ? 16u : 0u), enqueue)) != HMMCU_OK)
-    return rc;
-  if (fused) ctx->em_par ^= 1;
+  if ((rc = run_graphed(ctx, ctx->g_mstep, (tbits * 31u) ^ (repack ? 2u : 0u) ^ (ctx->mstep_fork ? 4u : 0u), enqueue)) != HMMCU_OK) return rc;
   CK(cudaStreamSynchronize(ctx->st));
   for (int v = 0; v < V; v++) {
     if (sum_logp) sum_logp[v] = ctx->ctl_h[v];

@@ -196,128 +196,6 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_mstep_fused: one launch for what an EM iteration on the warp-specialised path needs between two E-steps --
-// the stopping rule (T-FS:326-358), the M-step (updating_transition_probab, updating_mix_param, changing_zero_coef,
-// calc_det, inv_matrix; T-FS:1862-2022, 1338-1359) and the re-packing of everything that changed (kc, the rows of the
-// emission image and of the accumulate image).  Same arithmetic, in the same order, as k_mstep_ctl + k_mstep_apply +
-// k_pack_kc + k_pack_w_ws + k_pack_wT_tc, which remain for the other paths and for the first packing.
-// grid (N, V): block (i, v) owns state i of model v.  The stopping decision is recomputed by every block of a model from
-// the PREVIOUS EM state (em_*_in) and written by block i = 0 to the next one (em_*_out): no block reads what another
-// writes.  Models that are not re-estimated keep their packed forms.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_mstep_fused(const double *__restrict__ stats, int64_t ss, int V, int N, int M, int D, int DP, double floor_, double threshold,
-              const double *__restrict__ em_old_in, const int *__restrict__ em_active_in, double *__restrict__ em_old_out,
-              int *__restrict__ em_active_out, double *__restrict__ ctl, double *__restrict__ Aall, double *__restrict__ call,
-              double *__restrict__ muall, double *__restrict__ ivall, double *__restrict__ detall, const double *__restrict__ ctr,
-              float *__restrict__ kc2all, float *__restrict__ ws_images, int MP, int TN, int SCt, float *__restrict__ acc_images,
-              float *__restrict__ kcT) {
-  const int i = blockIdx.x, v = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, G = N * M;
-  const double *st = stats + (int64_t)v * ss;
-  const double probab = st[ss - 2], nutt = st[ss - 1];
-  int u = 0, act = em_active_in[v];
-  double old = em_old_in[v];
-  if (act) {
-    const double variation = fabs((old - probab) / old);  // T-FS:326
-    if (variation > threshold) { old = probab; u = 1; }
-    else act = 0;
-  }
-  if (i == 0 && tid == 0) {
-    ctl[v] = probab;
-    ctl[V + v] = nutt;
-    ctl[2 * V + v] = (double)u;
-    em_old_out[v] = old;
-    em_active_out[v] = act;
-  }
-  if (!u) return;
-  const double *num = st, *den = num + (int64_t)N * N, *denmix = den + N, *S0 = denmix + N;
-  const double *S1 = S0 + G, *S2 = S1 + (int64_t)G * D;
-  double *c = call + (int64_t)v * G + i * M;
-  // row i of the transition matrix; the weights of state i (floored and renormalised in index order)
-  if (tid < N && den[i] != 0.0) Aall[(int64_t)v * N * N + i * N + tid] = num[i * N + tid] / den[i];
-  if (tid == 32) {
-    if (denmix[i] != 0.0)
-      for (int k = 0; k < M; k++) c[k] = S0[i * M + k] / denmix[i];
-    double s = 0.0;
-    for (int k = 0; k < M; k++) {
-      if (c[k] < floor_) c[k] = floor_;
-      s += c[k];
-    }
-    for (int k = 0; k < M; k++) c[k] /= s;
-  }
-  __syncthreads();
-  const bool fresh = denmix[i] != 0.0;
-  const int KP = 2 * DP;
-  const uint32_t P = (uint32_t)(KP / 4) * 128;
-  const size_t ws_img_floats = ws_image_bytes(TN, KP) / 4;
-  const int CT = (N + SCt - 1) / SCt, nRB = (G + 127) / 128;
-  for (int m = warp; m < M; m += 8) {  // one warp per Gaussian, lanes over the coefficients
-    const int k = i * M + m;
-    const int64_t gg = (int64_t)v * G + k;
-    double *mu = muall + gg * D, *iv = ivall + gg * D;
-    const double s0 = S0[k];
-    double dt = 1.0, q = 0.0;
-    for (int d0 = 0; d0 < D; d0 += 32) {
-      const int d = d0 + lane;
-      double var = 1.0;
-      if (d < D) {
-        if (fresh) {
-          mu[d] = S1[(int64_t)k * D + d] / s0;
-          var = S2[(int64_t)k * D + d] / s0;
-          if (var < floor_) var = floor_;
-        } else var = iv[d];  // not re-estimated: the stored inverse is inverted again, as the reference does
-        iv[d] = 1.0 / var;
-      }
-      const int nd = min(32, D - d0);
-      for (int j = 0; j < nd; j++) dt *= __shfl_sync(0xffffffffu, var, j);  // calc_det: product in index order
-    }
-    if (lane == 0) detall[gg] = dt;
-    __syncwarp();
-    // kc2 exactly as k_pack_kc forms it (lanes over the dimensions, shuffle reduction)
-    for (int d = lane; d < D; d += 32) {
-      const double mm = mu[d] - ctr[d];
-      q += mm * mm * iv[d];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    double kk = -INFINITY;
-    const double cc = c[m];
-    if (dt != 0.0 && cc > 0.0) kk = (log(cc) - 0.5 * ((double)D * 1.8378770664093453 + log(fabs(dt))) - 0.5 * q) * 1.4426950408889634;
-    const float kcf = (float)kk;
-    // rows of the two W images that belong to this Gaussian
-    const int img_ws = v * CT + i / SCt, ls = i % SCt;
-    int n;
-    if (MP > 16) n = ls * MP + m;
-    else { const int spc = 16 / MP; n = (ls / spc) * 16 + (ls % spc) * MP + m; }
-    float *hi = ws_images + (size_t)img_ws * ws_img_floats;
-    float *lo = hi + (size_t)(TN / 8) * (P / 4);
-    float *kc2 = lo + (size_t)(TN / 8) * (P / 4);
-    const int img_acc = v * nRB + k / 128, r = k % 128;
-    float *im = acc_images + (size_t)img_acc * (tc_accT_image_bytes(KP) / 4) + (size_t)r * 2 * KP;
-    for (int kk2 = lane; kk2 < KP; kk2 += 32) {
-      const int part = kk2 / DP, d = kk2 - part * DP;
-      float val = 0.f;
-      if (d < D) {
-        const double mm = mu[d] - ctr[d], w = iv[d];
-        val = (float)(part == 0 ? mm * w : -0.5 * w);
-      }
-      float h, l;
-      split_tf32(val, h, l);
-      const size_t o = ((size_t)(n & 7) * 16 + (kk2 & 3) * 4 + (size_t)(kk2 >> 2) * 128 + (size_t)(n >> 3) * P) / 4;
-      hi[o] = h;
-      lo[o] = l;
-      im[kk2] = h;
-      im[KP + kk2] = l;
-    }
-    if (lane == 0) {
-      kc2all[gg] = kcf;
-      kc2[n] = kcf;
-      kcT[(size_t)img_acc * 128 + r] = kcf;
-    }
-  }
-}
-
 // units == nullptr: decode, unit u = (image u / ntiles_dec, frames [128 (u % ntiles_dec), ...) of the batch, nframes_dec in all)
 // MP: padded mixtures per state when <= 16 (1, 2, 4, 8, 16); 0 = a multiple of 16 given at run time (M)
 // Warps: 0-7 epilogue (lane quarter w & 3; column groups of parity w >> 2), 8-15 loaders (lane quarter w & 3;

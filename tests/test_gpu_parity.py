@@ -1058,32 +1058,3 @@ def test_peer_allreduce_sums_two_ranks_in_rank_order():
     assert np.allclose(local[0] + local[1], full, rtol=1e-5, atol=1e-6 * np.abs(full).max())
     for c in ctxs:
         c.close()
-
-
-@pytest.mark.parametrize("N,M,V", [(5, 16, 3), (5, 3, 4), (3, 32, 2), (6, 1, 2)])
-def test_fused_mstep_equals_the_separate_kernels(N, M, V):
-    """k_mstep_fused (stopping rule + M-step + kc + both W images in one launch) against k_mstep_ctl + k_mstep_apply + the
-    three packers: the same models, bit for bit, and the same log-likelihoods in the following E-steps (which run on
-    the re-packed images), with words stopping at different iterations (threshold 1e-3)."""
-    ms, x, off, labels = _synth(V, N, M, 6 * V, seed=2020 + N * M, tmin=40, tmax=90)
-    rng = np.random.default_rng(5)
-    start = api.ModelSet(ms.A, ms.c, ms.mu + 0.3 * np.sqrt(1.0 / ms.iv) * rng.standard_normal(ms.mu.shape), ms.iv, ms.det)
-    out = []
-    for fused in (1, 0):
-        c = api.Context(0)
-        c.set_option("fused_mstep", fused)
-        c.set_features(x, off)
-        c.set_models(start)
-        c.em_reset()
-        trace = []
-        for _ in range(7):
-            c.estep(labels, download=False, want_logp=False)
-            trace.append([a.copy() for a in c.mstep(threshold=1e-3)])
-        out.append((trace, c.get_models(ms.D)))
-        c.close()
-    (t1, m1), (t0, m0) = out
-    for a, b in zip(t1, t0):
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    for name in ("A", "c", "mu", "iv", "det"):
-        assert np.array_equal(getattr(m1, name), getattr(m0, name)), name
-    assert any(not t[2].all() for t in t1), "some word should have stopped"
