@@ -18,6 +18,7 @@
 #include "fbres_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "ws_kernels.cuh"
+#include "dec_kernels.cuh"
 #include "vit_kernels.cuh"
 #include "init_kernels.cuh"
 
@@ -158,6 +159,8 @@ struct hmmcu_ctx {
   DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
+  int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
+  int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
   // peer all-reduce over NVLink (hmmcu_peer_*): my receive area [2 slot sets][world][stats_n] doubles, then
@@ -460,6 +463,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
+  if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1169,6 +1173,59 @@ static int launch_emis_tc(hmmcu_ctx *ctx, const TcTile *tiles_dev, int ntiles, f
   return HMMCU_OK;
 }
 
+
+// decode emissions, frames resident in tensor memory, W images multicast over clusters of four CTAs (dec_kernels.cuh)
+template <int MP, int MR>
+static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
+  hmmcu_ctx::TcSet &ts = ctx->ws_dec;
+  const size_t smem = dec_emis_smem_bytes(ts.TN, 2 * ctx->DP);
+  auto kern = k_emis_dec<MP, MR>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kDecCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (ctx->dec_grid == 0) {  // whole clusters that are resident together: one CTA per SM, four SMs of one GPC per cluster
+    cfg.gridDim = dim3((ctx->sm_count / kDecCluster) * kDecCluster);
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl < 1) {
+      cudaGetLastError();
+      ctx->dec_grid = -1;
+    } else {
+      ctx->dec_grid = std::min(ncl, ctx->sm_count / kDecCluster) * kDecCluster;
+    }
+  }
+  if (ctx->dec_grid < 0) return HMMCU_EINVAL;
+  const int want = ((ntiles + kDecCluster - 1) / kDecCluster) * kDecCluster;
+  cfg.gridDim = dim3(std::min(ctx->dec_grid, want));
+  const float *x32 = ctx->x32.as<float>(), *img = ts.images.as<float>();
+  int nimg = ts.nimg, DP = ctx->DP, TN = ts.TN, S_total = ctx->V * ctx->N, SCt = ts.SCt;
+  CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt));
+  ctx->launches++;
+  ctx->last_tc = true;
+  return HMMCU_OK;
+}
+static int launch_emis_dec(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
+  switch (ws_pad_m(ctx->M)) {
+    case 1: return launch_emis_dec_t<1, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 2: return launch_emis_dec_t<2, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 4: return ctx->M == 3 ? launch_emis_dec_t<4, 3>(ctx, ntiles, nframes, logb, fbase, ldb) : launch_emis_dec_t<4, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 8: return launch_emis_dec_t<8, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 16: return launch_emis_dec_t<16, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    default: return HMMCU_EINVAL;
+  }
+}
+static bool dec_supported(const hmmcu_ctx *ctx) {
+  return ctx->use_dec_emis && ws_pad_m(ctx->M) <= 16 && ctx->DP <= 40 && ctx->dec_grid >= 0 && ctx->sm_count >= kDecCluster;
+}
+
 // --------------------------------------------------------------------------------- emissions ----
 static int emis_chunk_states(const hmmcu_ctx *ctx) { return std::max(1, std::min(ctx->N, 128 / ctx->M)); }
 
@@ -1308,7 +1365,9 @@ static int decode_emissions(hmmcu_ctx *ctx, int64_t fb0, int64_t fb1) {
     if ((rc = ensure_ws_images(ctx, 1)) != HMMCU_OK) return rc;
     const int nfr = (int)(fb1 - fb0), ntl = (nfr + kTcRows - 1) / kTcRows;
     t_begin(ctx, "emis");
-    rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+    rc = HMMCU_EINVAL;
+    if (dec_supported(ctx) && ctx->ws_dec.TN <= kWsMaxTN) rc = launch_emis_dec(ctx, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+    if (rc != HMMCU_OK) rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
     if (rc) return rc;
     t_end(ctx, "emis");
   } else if (tc_supported(ctx)) {
