@@ -18,17 +18,20 @@
 // 17 producer (one lane issues the multicast copies).
 // Rounds: round r of CTA b is frame tile r * gridDim + b; every CTA of a cluster runs the same number of rounds and every
 // round runs all images (a CTA without a tile in the last round still fetches and releases its quarters).
-// TMEM columns: operand stage a at 160 a: [x_hi | x2_hi | x_lo | x2_lo] (DP <= 40), two of them (round parity), then two
-// accumulator stages of 96 columns (TN <= 96).  W image layout and the MMA descriptors are k_emis_ws's.
+// TMEM columns: [0, 160) the frame tile [x_hi | x2_hi | x_lo | x2_lo] (DP <= 40), then THREE accumulator stages of 96
+// columns (TN <= 96): the log-sum-exp epilogue of a unit takes longer than its MMAs, and with two stages the tensor pipe
+// waited for it (period = (MMA + epilogue) / 2; measured 54 % pipe activity, the same as k_emis_ws).  W image layout and
+// the MMA descriptors are k_emis_ws's.
 #pragma once
 #include "ws_kernels.cuh"
 
 namespace hmmk {
 
-constexpr int kDecCluster = 4;
+constexpr int kDecClusterMax = 4;  // CTAs per cluster: 4 (a quarter of every image per CTA) or 2, template parameter CL
 constexpr int kDecEpiWarps = 12;
 constexpr int kDecThreads = (kDecEpiWarps + 6) * 32;  // + 4 expanders, MMA issuer, producer
 constexpr int kDecStages = 3;                         // W images in flight per CTA
+constexpr int kDecAcc = 3;                            // accumulator stages in tensor memory
 
 __host__ __device__ inline size_t dec_emis_smem_bytes(int TN, int KP) { return kDecStages * ws_image_bytes(TN, KP) + 1024 + 512; }
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t mbar, uint16_t mask
 }
 
 // MP: padded mixtures per state (1, 2, 4, 8, 16); MR: real mixtures of a state (0 = all MP)
-template <int MP, int MR>
+template <int MP, int MR, int CL>
 __global__ void __launch_bounds__(kDecThreads, 1)
 k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, const float *__restrict__ images, int DP, int TN,
            float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt) {
@@ -68,11 +71,13 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
   const uint32_t w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
   const uint32_t Ws = (smem_u32(smem_raw) + 1023u) & ~1023u;  // NST stages of img_bytes (multiples of 64)
   const uint32_t bars = (Ws + NST * img_bytes + 15u) & ~15u;
-  const uint32_t full = bars, empty = bars + 8 * NST, dfull = bars + 16 * NST, dempty = dfull + 16, xfull = dfull + 32, xempty = dfull + 48,
-                 kfull = dfull + 64, tmem_slot = dfull + 80;
-  __shared__ __align__(16) float skc[2][kWsMaxTN];  // additive constants of the image an accumulator stage belongs to
+  constexpr int NA = kDecAcc;
+  const uint32_t full = bars, empty = bars + 8 * NST, dfull = bars + 16 * NST, dempty = dfull + 8 * NA, kfull = dfull + 16 * NA, xfull = dfull + 24 * NA,
+                 xempty = xfull + 8, tmem_slot = xfull + 16;
+  __shared__ __align__(16) float skc[kDecAcc][kWsMaxTN];  // additive constants of the image an accumulator stage belongs to
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
+  constexpr int kDecCluster = CL;
   constexpr uint16_t kMask = (1u << kDecCluster) - 1;
 
   if (tid == 0) {
@@ -81,13 +86,13 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
       init(full + 8 * s, 1);             // this CTA's producer (arrive.expect_tx); the bytes come from all four CTAs
       init(empty + 8 * s, kDecCluster);  // tcgen05.commit of every CTA of the cluster
     }
-    for (int a = 0; a < 2; a++) {
+    for (int a = 0; a < NA; a++) {
       init(dfull + 8 * a, 1);                   // tcgen05.commit
       init(dempty + 8 * a, kDecEpiWarps * 32);  // every epilogue thread
-      init(xfull + 8 * a, 128);                 // every expander thread
-      init(xempty + 8 * a, 1);                  // tcgen05.commit after the last image of a round
       init(kfull + 8 * a, 32);                  // the MMA warp's lanes (constants copied)
     }
+    init(xfull, 128);   // every expander thread
+    init(xempty, 1);    // tcgen05.commit after the last image of a round
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kDecEpiWarps + 4) {
@@ -99,7 +104,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
   cluster_sync_all();  // every CTA's barriers exist before anybody's copies or commits reach them
   tc_fence_after();
   const uint32_t tmem0 = (uint32_t)lds_i32(tmem_slot);
-  constexpr uint32_t acc0 = 320, ACS = 96;
+  constexpr uint32_t acc0 = 160, ACS = 96;
 
   const int G = gridDim.x;
   const int nrounds = (ntiles + G - 1) / G;
@@ -129,24 +134,23 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
     int n = 0, nu = 0;  // W stage uses; accumulator stage uses (only rounds with a tile)
     for (int r = 0; r < nrounds; r++) {
       const bool have = rows_of(r) > 0;
-      const int sa = r & 1;
       if (have) {
-        mbar_wait_a(xfull + 8 * sa, (r >> 1) & 1);  // the round's frames are in tensor memory
+        mbar_wait_a(xfull, r & 1);  // the round's frames are in tensor memory
         tc_fence_after();
       }
       for (int j = 0; j < nimg; j++, n++) {
         const int s = n % NST;
         mbar_wait_a(full + 8 * s, (n / NST) & 1);  // the image (all four quarters) has landed
         if (have) {
-          const int a = nu & 1;
-          mbar_wait_a(dempty + 8 * a, ((nu >> 1) & 1) ^ 1);  // accumulator stage (and its constants) drained by the epilogue
+          const int a = nu % NA;
+          mbar_wait_a(dempty + 8 * a, ((nu / NA) & 1) ^ 1);  // accumulator stage (and its constants) drained by the epilogue
           // the additive constants leave the stage before it is released
           const uint32_t kc_src = Ws + (uint32_t)s * img_bytes + w_bytes;
           for (int c = lane; c < TN; c += 32) skc[a][c] = lds_f32(kc_src + 4 * c);
           mbar_arrive_a(kfull + 8 * a);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint32_t xh = tb + (uint32_t)sa * 160, xl = xh + 80;
+            const uint32_t xh = tb, xl = xh + 80;
             const uint32_t wbase = Ws + (uint32_t)s * img_bytes;
             const uint64_t wh = make_smem_desc2(wbase, 128, P), wl = make_smem_desc2(wbase + (uint32_t)(TN / 8) * P, 128, P);
             const uint32_t d = tb + acc0 + (uint32_t)a * ACS;
@@ -162,7 +166,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
             }
             tc_commit_multicast(empty + 8 * s, kMask);  // stage s may be refilled once all four CTAs say so
             tc_commit_a(dfull + 8 * a);
-            if (j == nimg - 1) tc_commit_a(xempty + 8 * sa);  // the operand stage is free for the round after next
+            if (j == nimg - 1) tc_commit_a(xempty);  // the frame tile may be replaced
           }
           __syncwarp();
           nu++;
@@ -190,15 +194,14 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
     for (int r = 0; r < nrounds; r++) {
       const int nrows = rows_of(r);
       if (nrows == 0) continue;
-      const int sa = r & 1;
       const int64_t f = fbase + (int64_t)tile_of(r) * kTcRows + row;
       float4 xv[10];
       const float4 *src = reinterpret_cast<const float4 *>(x32 + f * DP);
 #pragma unroll
       for (int j = 0; j < 10; j++) xv[j] = (row < nrows && j < nq) ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_wait_a(xempty + 8 * sa, ((r >> 1) & 1) ^ 1);  // the MMAs of the round before last have retired
+      mbar_wait_a(xempty, (r & 1) ^ 1);  // the MMAs of the previous round have retired (the rows are already in registers)
       tc_fence_after();
-      const uint32_t xa = xa0 + (uint32_t)sa * 160;
+      const uint32_t xa = xa0;
 #pragma unroll
       for (int j = 0; j < 10; j++) {
         if (j < nq) {
@@ -214,7 +217,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive_a(xfull + 8 * sa);
+      mbar_arrive_a(xfull);
     }
   } else {
     // =================================== EPILOGUE (warps 0-11) ===================================
@@ -231,12 +234,12 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
       const bool live = row < nrows;
       float *lrow0 = logb + ((int64_t)tile_of(r) * kTcRows + row) * ldb;
       for (int j = 0; j < nimg; j++, nu++) {
-        const int a = nu & 1;
+        const int a = nu % NA;
         const int state0 = j * SCt;
         const int nst = max(0, min(SCt, S_total - state0));  // states present in this image
         const int ngroups = (nst + SPC - 1) / SPC;
-        mbar_wait_a(kfull + 8 * a, (nu >> 1) & 1);
-        mbar_wait_a(dfull + 8 * a, (nu >> 1) & 1);
+        mbar_wait_a(kfull + 8 * a, (nu / NA) & 1);
+        mbar_wait_a(dfull + 8 * a, (nu / NA) & 1);
         tc_fence_after();
         const uint32_t d = tmem0 + acc0 + (uint32_t)a * ACS + trow;
         const float4 *kc4 = reinterpret_cast<const float4 *>(skc[a]);  // warp-uniform addresses: broadcast loads

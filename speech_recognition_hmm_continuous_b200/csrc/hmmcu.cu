@@ -160,6 +160,7 @@ struct hmmcu_ctx {
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
+  int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
@@ -414,6 +415,7 @@ void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; ctx->c
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
   if (strcmp(name, "kappa") == 0) return ctx->kappa;            // accuracy-guard value of the current pack
   if (strcmp(name, "tc_active") == 0) return ctx->last_tc ? 1.0 : 0.0;
+  if (strcmp(name, "dec_grid") == 0) return (double)ctx->dec_grid;                // CTAs of the last k_emis_dec launch configuration
   {  // "<name>_total": the sum over the batches of the last hmmcu_forward_scores / hmmcu_viterbi_scores call
     const size_t ln = strlen(name);
     if (ln > 6 && strcmp(name + ln - 6, "_total") == 0) {
@@ -464,6 +466,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
+  if (strcmp(key, "dec_cluster") == 0) { ctx->dec_cluster = value == 4 ? 4 : 2; ctx->dec_grid = 0; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
 }
 int64_t hmmcu_stats_size(int N, int M, int D) {
@@ -1175,11 +1178,12 @@ static int launch_emis_tc(hmmcu_ctx *ctx, const TcTile *tiles_dev, int ntiles, f
 
 
 // decode emissions, frames resident in tensor memory, W images multicast over clusters of four CTAs (dec_kernels.cuh)
-template <int MP, int MR>
-static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
+template <int MP, int MR, int CL>
+static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
+  constexpr int kDecCluster = CL;
   hmmcu_ctx::TcSet &ts = ctx->ws_dec;
   const size_t smem = dec_emis_smem_bytes(ts.TN, 2 * ctx->DP);
-  auto kern = k_emis_dec<MP, MR>;
+  auto kern = k_emis_dec<MP, MR, CL>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -1212,6 +1216,11 @@ static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *log
   ctx->last_tc = true;
   return HMMCU_OK;
 }
+template <int MP, int MR>
+static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
+  return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2>(ctx, ntiles, nframes, logb, fbase, ldb)
+                               : launch_emis_dec_c<MP, MR, 4>(ctx, ntiles, nframes, logb, fbase, ldb);
+}
 static int launch_emis_dec(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
   switch (ws_pad_m(ctx->M)) {
     case 1: return launch_emis_dec_t<1, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
@@ -1223,7 +1232,7 @@ static int launch_emis_dec(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb,
   }
 }
 static bool dec_supported(const hmmcu_ctx *ctx) {
-  return ctx->use_dec_emis && ws_pad_m(ctx->M) <= 16 && ctx->DP <= 40 && ctx->dec_grid >= 0 && ctx->sm_count >= kDecCluster;
+  return ctx->use_dec_emis && ws_pad_m(ctx->M) <= 16 && ctx->DP <= 40 && ctx->dec_grid >= 0 && ctx->sm_count >= kDecClusterMax;
 }
 
 // --------------------------------------------------------------------------------- emissions ----
@@ -1411,8 +1420,16 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   CK(ctx->score_d.ensure(sizeof(double) * (size_t)ctx->U * ctx->V));
   t_collect(ctx, "emis");
   t_collect(ctx, mode == 0 ? "score" : "viterbi");
-  // utterance batches so that the log-emission buffer stays under ~2 GiB
-  const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, (int64_t)(2048ll << 20) / (4 * S));
+  // utterance batches so that the log-emission buffer stays under ~6 GiB (a third of the free memory when that is less):
+  // large batches keep the tail of k_emis_dec's rounds small (every CTA walks all images once per frame tile it holds)
+  int64_t budget_bytes = 6144ll << 20;
+  {
+    size_t mem_free = 0, mem_total = 0;
+    if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess) budget_bytes = std::min<int64_t>(budget_bytes, (int64_t)((mem_free + ctx->logb.cap) / 3));
+    else cudaGetLastError();
+    budget_bytes = std::max<int64_t>(budget_bytes, 256ll << 20);
+  }
+  const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, budget_bytes / (4 * S));
   int u0 = 0;
   while (u0 < ctx->U) {
     int u1 = u0;
