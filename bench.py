@@ -500,7 +500,7 @@ def run_ours(args):
         kt = dec[leg]["kernel_ms"].get(kn)
         if per_pair and kt and kt > 0:
             ach = per_pair * V * F / (kt * 1e-3) / 1e9
-            rooflines["decode_" + kn] = {"kernel": "k_fwd_cells", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            rooflines["decode_" + kn] = {"kernel": "k_fwd_cells32", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                          "frac": ach / pk["hbm_gbs"], "ms": kt, "algorithmic_bytes": per_pair * V * F, "traffic": None}
     dom = max(kms, key=lambda k: kms[k])
     roofline = dict(rooflines[dom])
@@ -683,11 +683,11 @@ def _decode_config(t, args, name, desc, V, N, M, U, seed):
             "frames_per_s": Ftot / (dev_ms * 1e-3), "frame_model_pairs_per_s": Ftot * V / (dev_ms * 1e-3),
             "frames_per_s_through_api": Ftot / (wall_max * 1e-3),
             "rooflines": {
-                "emis": {"kernel": "k_emis_ws<decode>", "bound": "tensor", "achieved": flops / (em_ms * 1e-3) / 1e12, "peak": t["tf32_peak"],
+                "emis": {"kernel": "k_emis_dec" if c.kernel_ms("dec_grid") > 0 else "k_emis_ws<decode>", "bound": "tensor", "achieved": flops / (em_ms * 1e-3) / 1e12, "peak": t["tf32_peak"],
                          "unit": "TFLOP/s", "frac": flops / (em_ms * 1e-3) / 1e12 / t["tf32_peak"],
                          "issued_3xtf32": {"achieved": 3 * flops / (em_ms * 1e-3) / 1e12, "frac": 3 * flops / (em_ms * 1e-3) / 1e12 / t["tf32_peak"]},
                          "algorithmic_flops": flops, "traffic": t["traffic"].get(name, {}).get("emis")},
-                "score": {"kernel": "k_fwd_cells" if leg == "forward" else "k_vit_cells", "bound": "hbm", "achieved": sbytes / (sc_ms * 1e-3) / 1e9,
+                "score": {"kernel": "k_fwd_cells32" if leg == "forward" else "k_vit_cells", "bound": "hbm", "achieved": sbytes / (sc_ms * 1e-3) / 1e9,
                           "peak": t["pk"]["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (sc_ms * 1e-3) / 1e9 / t["pk"]["hbm_gbs"],
                           "algorithmic_bytes": sbytes, "traffic": t["traffic"].get(name, {}).get("score" if leg == "forward" else "viterbi")}},
         }

@@ -319,6 +319,132 @@ k_fwd_cells(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const in
   out[(int64_t)u * V + v] = msum + 0.6931471805599453 * (double)esum + log(z[NS - 1]);
 }
 
+// The same score with the chain in SINGLE precision, in the LOG domain (default; k_fwd_cells stays behind the
+// "fwd_f64" option).  The double-precision chain above issues ~140 instructions per (cell, frame) -- five software
+// exponentials assembled into doubles, a scaling pass -- and is bound by instruction issue at half the HBM rate.  A
+// single-precision chain in the linear domain is not an option: against a mismatched model a state's mass falls by
+// e^-100 per frame relative to its neighbour's, and a state that is 2^-126 below the frame's maximum today can carry the
+// best path tomorrow (measured: 2.5 % error in such a cell), where the reference's doubles still hold it.  So every state
+// keeps its own magnitude: with lz_i = log2 of the scaled alpha (max_i lz_i = 0 after every frame),
+//   lz'_i = log2(e) l_i + log2( sum_j 2^(lz_j + log2 a_ji) ),     m = max_i lz'_i,     lz_i <- lz'_i - m,
+// and log P = ln2 (sum m_t + lz_{T-1}(N-1)), sum m_t in double.  The banded topology takes one ex2 and one lg2 per state
+// (log-sum-exp of two terms), a full A takes N ex2 and one lg2.  "No mass" is the finite -1e30 instead of -inf, so that no
+// difference of two infinities can arise.  Per (cell, frame), N = 5 banded: 9 transcendental-unit operations, ~60
+// instructions, 4 N bytes of log-emissions.
+// Error: a rounding of ~2^-17 (values of magnitude ~100) per step, the same size as that of the single-precision
+// log-emissions it reads.
+constexpr float kLzNone = -1e30f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NS, bool BANDED>
+__global__ void __launch_bounds__(kCellThreads)
+k_fwd_cells32(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off, int u0, int nu,
+              int V, const double *__restrict__ Aall, double *__restrict__ out) {
+  const int64_t cell = (int64_t)blockIdx.x * kCellThreads + threadIdx.x;
+  if (cell >= (int64_t)nu * V) return;
+  const int u = u0 + (int)(cell / V), v = (int)(cell % V);
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  float la[NS * NS];  // log2 a_ij, "none" for a_ij = 0
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) {
+    if (!BANDED || k % (NS + 1) == 0 || (k % NS > 0 && k % (NS + 1) == 1)) la[k] = fmaxf(lg2_ftz((float)Aall[(int64_t)v * NS * NS + k]), kLzNone);
+    else la[k] = kLzNone;
+  }
+  float lz[NS];
+  double msum = 0.0;  // sum of m_t (base-2 logarithms)
+  constexpr float kL2E = 1.4426950408889634f;
+  auto first = [&](const float (&l)[NS]) {  // pi = [1,0,..,0]
+    const float m = l[0] * kL2E;            // -inf (density 0 in the entry state): the score is -inf, as log(0) in the reference
+    msum = (double)m;
+    lz[0] = 0.f;
+#pragma unroll
+    for (int i = 1; i < NS; i++) lz[i] = kLzNone;
+  };
+  auto step = [&](const float (&l)[NS]) {
+    float nz[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      float lsum;  // log2 sum_j 2^(lz_j + la_ji)
+      if (BANDED) {
+        const float x = lz[i] + la[i * NS + i];
+        if (i > 0) {
+          const float y = lz[i - 1] + la[(i - 1) * NS + i];
+          lsum = fmaxf(x, y) + lg2_ftz(1.f + ex2_ftz(-fabsf(x - y)));
+        } else {
+          lsum = x;
+        }
+      } else {
+        float t[NS], mx;
+#pragma unroll
+        for (int j = 0; j < NS; j++) t[j] = lz[j] + la[j * NS + i];
+        mx = t[0];
+#pragma unroll
+        for (int j = 1; j < NS; j++) mx = fmaxf(mx, t[j]);
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < NS; j++) sm += ex2_ftz(t[j] - mx);
+        lsum = mx + lg2_ftz(sm);
+      }
+      nz[i] = fmaf(l[i], kL2E, lsum);
+    }
+    float m = nz[0];
+#pragma unroll
+    for (int i = 1; i < NS; i++) m = fmaxf(m, nz[i]);
+#pragma unroll
+    for (int i = 0; i < NS; i++) lz[i] = fmaxf(nz[i] - m, kLzNone);  // also turns -inf (density 0) and NaN (-inf - -inf) into "none"
+    msum += (double)m;
+  };
+  // log-emissions kCellPF frames ahead of the chain; the bulk of the frames runs without index clamps
+  const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
+  float nxt[kCellPF][NS];
+#pragma unroll
+  for (int k = 0; k < kCellPF; k++) cell_load<NS>(p + (int64_t)min(k, T - 1) * ldb, nxt[k]);
+  int t0 = 0;
+  const float *pn = p + (int64_t)kCellPF * ldb;  // frame t0 + kCellPF
+  for (; t0 + 2 * kCellPF <= T; t0 += kCellPF, pn += (int64_t)kCellPF * ldb) {
+    float cur[kCellPF][NS];
+#pragma unroll
+    for (int k = 0; k < kCellPF; k++) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
+    }
+#pragma unroll
+    for (int k = 0; k < kCellPF; k++) cell_load<NS>(pn + (int64_t)k * ldb, nxt[k]);
+    if (t0 == 0) first(cur[0]); else step(cur[0]);
+#pragma unroll
+    for (int k = 1; k < kCellPF; k++) step(cur[k]);
+  }
+  for (; t0 < T; t0 += kCellPF) {
+    float cur[kCellPF][NS];
+#pragma unroll
+    for (int k = 0; k < kCellPF; k++) {
+#pragma unroll
+      for (int i = 0; i < NS; i++) cur[k][i] = nxt[k][i];
+    }
+#pragma unroll
+    for (int k = 0; k < kCellPF; k++) cell_load<NS>(p + (int64_t)min(t0 + kCellPF + k, T - 1) * ldb, nxt[k]);
+#pragma unroll
+    for (int k = 0; k < kCellPF; k++) {
+      if (t0 + k < T) {
+        if (t0 + k == 0) first(cur[k]); else step(cur[k]);
+      }
+    }
+  }
+  // a frame in which no state had mass left m = "none" (or -inf) in the sum
+  const double tot = msum + (double)lz[NS - 1];
+  out[(int64_t)u * V + v] = (tot > -1e29) ? 0.6931471805599453 * tot : -INFINITY;
+}
+
 // Viterbi score of every cell (V1; no reference code): delta in double, log domain.
 template <int NS, bool BANDED>
 __global__ void __launch_bounds__(kCellThreads)

@@ -693,6 +693,34 @@ def test_decode_paths_other_shapes(ctx, N, M, D):
     assert (lab == labels).all()
 
 
+@pytest.mark.parametrize("dense", [False, True])
+def test_forward_cell_scorers_single_and_double_chain(dense):
+    """k_fwd_cells32 (log-domain single-precision chain, the default) and k_fwd_cells (double chain, option
+    "fwd_f64") against the oracle's calc_alpha + calc_probability (R-FS:739-836), for the reference's banded
+    topology and for a dense A, on mismatched models (a state's mass falls by e^-100 per frame there: a linear
+    single-precision chain loses the best path in such cells) and with an utterance shorter than the chain."""
+    ms, x, off, labels = _synth(6, 5, 3, 12, seed=31, tmin=3, tmax=140)
+    if dense:
+        rng = np.random.default_rng(5)
+        A = rng.random(ms.A.shape) + 0.05
+        ms = api.ModelSet(A / A.sum(axis=2, keepdims=True), ms.c, ms.mu, ms.iv, ms.det)
+    want = np.array([[o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]]) for v in range(ms.V)] for u in range(len(labels))])
+    got = {}
+    for f64 in (0, 1):
+        c = api.Context(0)
+        c.set_option("fwd_f64", f64)
+        c.set_features(x, off)
+        c.set_models(ms)
+        got[f64] = c.forward_scores()
+        c.close()
+        fin = np.isfinite(want)
+        assert (np.isfinite(got[f64]) == fin).all()
+        assert np.allclose(got[f64][fin], want[fin], rtol=RTOL, atol=0)
+        assert np.abs(got[f64][fin] / want[fin] - 1).max() < 2e-6
+    fin = np.isfinite(want)
+    assert np.abs(got[0][fin] / got[1][fin] - 1).max() < 1e-6
+
+
 @pytest.mark.parametrize("N,M", [(5, 1), (5, 3), (5, 16), (3, 6), (6, 2)])
 def test_device_initial_models_are_bit_identical_to_the_host_builder(N, M):
     """hmmcu_init_models (creating_initial_model, T-FS:732-1317, for all words at once on the device) against
