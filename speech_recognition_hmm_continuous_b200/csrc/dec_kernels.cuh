@@ -33,6 +33,14 @@ constexpr int kDecThreads = (kDecEpiWarps + 6) * 32;  // + 4 expanders, MMA issu
 constexpr int kDecStages = 3;                         // W images in flight per CTA
 constexpr int kDecAcc = 3;                            // accumulator stages in tensor memory
 
+// Output layout of k_emis_dec ("interleaved"): blocks of 8 frames, state-major inside a block,
+//   logb[((f / 8) * S + s) * 8 + f % 8]        f = frame of the batch, s = state column (model * N + state), S = ldb
+// A thread of the epilogue owns a frame row, so its store of one state is 4 bytes; in the row-per-frame layout every such
+// store is a sector of its own (32 sectors per warp instruction), here 8 lanes share a sector and a warp instruction writes
+// four full sectors.  The cell scorers read a (block, model) as N consecutive sectors with 16-byte loads.
+__host__ __device__ inline int64_t dec_logb_index(int64_t f, int64_t s, int64_t S) { return ((f >> 3) * S + s) * 8 + (f & 7); }
+__host__ __device__ inline size_t dec_logb_floats(int64_t nframes, int64_t S) { return (size_t)((nframes + 7) / 8) * 8 * (size_t)S; }
+
 __host__ __device__ inline size_t dec_emis_smem_bytes(int TN, int KP) { return kDecStages * ws_image_bytes(TN, KP) + 1024 + 512; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -63,7 +71,7 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t mbar, uint16_t mask
 template <int MP, int MR, int CL>
 __global__ void __launch_bounds__(kDecThreads, 1)
 k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, const float *__restrict__ images, int DP, int TN,
-           float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt) {
+           float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NST = kDecStages;
   const int KP = 2 * DP;
@@ -120,6 +128,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
         for (int j = 0; j < nimg; j++, n++) {
           const int s = n % NST;
           mbar_wait_a(empty + 8 * s, ((n / NST) & 1) ^ 1);  // all four CTAs have multiplied what the stage held
+          if ((dbg & 4) && n >= NST) { mbar_arrive_a(full + 8 * s); continue; }  // experiment: no W traffic
           mbar_expect_tx_a(full + 8 * s, img_bytes);
           bulk_copy_multicast(Ws + (uint32_t)s * img_bytes + crank * qbytes,
                               reinterpret_cast<const char *>(images) + (size_t)j * img_bytes + (size_t)crank * qbytes, qbytes, full + 8 * s, kMask);
@@ -155,7 +164,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
             const uint64_t wh = make_smem_desc2(wbase, 128, P), wl = make_smem_desc2(wbase + (uint32_t)(TN / 8) * P, 128, P);
             const uint32_t d = tb + acc0 + (uint32_t)a * ACS;
             uint32_t acc = 0;
-            for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
+            for (int p = 0; p < ((dbg & 2) ? 0 : 3); p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
               const uint32_t a0 = (p == 1) ? xl : xh;
               const uint64_t b0 = (p == 2) ? wl : wh;
 #pragma unroll 10
@@ -232,7 +241,8 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
       const int nrows = rows_of(r);
       if (nrows == 0) continue;
       const bool live = row < nrows;
-      float *lrow0 = logb + ((int64_t)tile_of(r) * kTcRows + row) * ldb;
+      // interleaved output (see dec_logb_index): frame row -> block of 8 frames, 8 consecutive lanes fill one 32-byte sector
+      float *lrow0 = logb + ((int64_t)tile_of(r) * (kTcRows / 8) + (row >> 3)) * ldb * 8 + (row & 7);
       for (int j = 0; j < nimg; j++, nu++) {
         const int a = nu % NA;
         const int state0 = j * SCt;
@@ -243,7 +253,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
         tc_fence_after();
         const uint32_t d = tmem0 + acc0 + (uint32_t)a * ACS + trow;
         const float4 *kc4 = reinterpret_cast<const float4 *>(skc[a]);  // warp-uniform addresses: broadcast loads
-        float *lrow = lrow0 + state0;
+        float *lrow = lrow0 + (int64_t)state0 * 8;
         uint32_t v[kMaxG][16];
 #pragma unroll
         for (int k = 0; k < kMaxG; k++)
@@ -252,7 +262,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
 #pragma unroll
         for (int k = 0; k < kMaxG; k++) {
           const int c = h + EH * k;
-          if (c < ngroups) {
+          if (c < ngroups && !(dbg & 1)) {
             const float4 k0 = kc4[c * 4], k1 = kc4[c * 4 + 1], k2 = kc4[c * 4 + 2], k3 = kc4[c * 4 + 3];
             const float kc[16] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x, k2.y, k2.z, k2.w, k3.x, k3.y, k3.z, k3.w};
             float val[16];  // log2(c_g N_g(x)); -inf for a Gaussian of density 0 and for the pad columns
@@ -282,19 +292,11 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
               }
               lbv[g] = (m > kNegInf) ? (MU == 1 ? ms : ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
             }
-            float *dst = lrow + c * SPC;
+            float *dst = lrow + c * SPC * 8;
             if (live) {
-              if (SPC % 4 == 0 && c * SPC + SPC <= nst && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-                for (int g = 0; g + 3 < SPC; g += 4) *reinterpret_cast<float4 *>(dst + g) = make_float4(lbv[g], lbv[g + 1], lbv[g + 2], lbv[g + 3]);
-              } else if (SPC % 2 == 0 && c * SPC + SPC <= nst && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-#pragma unroll
-                for (int g = 0; g + 1 < SPC; g += 2) *reinterpret_cast<float2 *>(dst + g) = make_float2(lbv[g], lbv[g + 1]);
-              } else {
-#pragma unroll
-                for (int g = 0; g < SPC; g++)
-                  if (c * SPC + g < nst) dst[g] = lbv[g];
-              }
+              for (int g = 0; g < SPC; g++)
+                if (c * SPC + g < nst) dst[g * 8] = lbv[g];
             }
           }
         }

@@ -162,6 +162,7 @@ struct hmmcu_ctx {
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
   int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int fwd_f64 = 0;       // forward cell scorer with the chain in double (k_fwd_cells) instead of k_fwd_cells32
+  int dec_dbg = 0;       // experiments on k_emis_dec: 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no W copies (results are garbage)
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
@@ -467,6 +468,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
+  if (strcmp(key, "dec_dbg") == 0) { ctx->dec_dbg = value; return HMMCU_OK; }
   if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
   if (strcmp(key, "dec_cluster") == 0) { ctx->dec_cluster = value == 4 ? 4 : 2; ctx->dec_grid = 0; return HMMCU_OK; }
   return fail(ctx, HMMCU_EINVAL, "unknown option %s", key);
@@ -1094,13 +1096,13 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
     ts.s0_h = s0;
     ts.ns_h = ns;
     ts.nimg = (int)s0.size();
-    CK(ts.images.ensure(ws_image_bytes(ts.TN, KP) * ts.nimg));
     CK(ts.s0.ensure(sizeof(int32_t) * ts.nimg));
     CK(ts.ns.ensure(sizeof(int32_t) * ts.nimg));
     CK(cudaMemcpyAsync(ts.s0.p, s0.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ts.ns.p, ns.data(), sizeof(int32_t) * ts.nimg, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));  // s0 / ns are stack vectors
   }
+  CK(ts.images.ensure(ws_image_bytes(ts.TN, KP) * ts.nimg));  // not only on a new geometry: the feature width may have changed
   {
     int rc = ensure_kc(ctx);
     if (rc) return rc;
@@ -1148,10 +1150,9 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
   switch (MPd) {
     case 1: WS_LAUNCH(1); break;
     case 2: WS_LAUNCH(2); break;
-    case 4:
-      if (ctx->M == 3 && !(ctx->debug_acc & 2)) WS_LAUNCH3(4, false, 3);  // the baseline configs' M = 3: the pad mixture is skipped
-      else WS_LAUNCH(4);
-      break;
+    case 3: WS_LAUNCH(3); break;
+    case 4: WS_LAUNCH(4); break;
+    case 5: WS_LAUNCH(5); break;
     case 8: WS_LAUNCH(8); break;
     case 16: WS_LAUNCH(16); break;
     default: WS_LAUNCH(0); break;
@@ -1213,7 +1214,8 @@ static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *log
   cfg.gridDim = dim3(std::min(ctx->dec_grid, want));
   const float *x32 = ctx->x32.as<float>(), *img = ts.images.as<float>();
   int nimg = ts.nimg, DP = ctx->DP, TN = ts.TN, S_total = ctx->V * ctx->N, SCt = ts.SCt;
-  CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt));
+  int dbg = ctx->dec_dbg;
+  CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt, dbg));
   ctx->launches++;
   ctx->last_tc = true;
   return HMMCU_OK;
@@ -1227,7 +1229,9 @@ static int launch_emis_dec(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb,
   switch (ws_pad_m(ctx->M)) {
     case 1: return launch_emis_dec_t<1, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
     case 2: return launch_emis_dec_t<2, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
-    case 4: return ctx->M == 3 ? launch_emis_dec_t<4, 3>(ctx, ntiles, nframes, logb, fbase, ldb) : launch_emis_dec_t<4, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 3: return launch_emis_dec_t<3, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 4: return launch_emis_dec_t<4, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
+    case 5: return launch_emis_dec_t<5, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
     case 8: return launch_emis_dec_t<8, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
     case 16: return launch_emis_dec_t<16, 0>(ctx, ntiles, nframes, logb, fbase, ldb);
     default: return HMMCU_EINVAL;
@@ -1312,21 +1316,19 @@ int hmmcu_emissions(hmmcu_ctx *ctx, int u, int v, double *logb, double *post) {
 
 // ----------------------------------------------------------------------- decode (all cells) ----
 template <int NS> struct ScoreLaunch {
-  static void fwd(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, int emulate) {
+  static void fwd(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, int emulate, bool lay8) {
     if (emulate) {  // the reference's linear-domain underflow, cell by cell (slow path, drop-in recogniser)
       dim3 grid((ctx->V + kScoreThreads - 1) / kScoreThreads, nu);
       k_fwd_score<NS><<<grid, kScoreThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, ctx->V,
-                                                           ctx->A.as<double>(), out, emulate);
+                                                           ctx->A.as<double>(), out, emulate, lay8 ? 1 : 0);
       return;
     }
     const unsigned grid = (unsigned)(((int64_t)nu * ctx->V + kCellThreads - 1) / kCellThreads);
-    if (!ctx->fwd_f64) {  // default: the single-precision chain (sum of the scaling exponents in double)
-      if (ctx->banded)
-        k_fwd_cells32<NS, true><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
-                                                                    ctx->A.as<double>(), out);
-      else
-        k_fwd_cells32<NS, false><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
-                                                                     ctx->A.as<double>(), out);
+    if (!ctx->fwd_f64) {  // default: the single-precision log-domain chain (sum of the frame maxima in double)
+#define FWD32(B, L) k_fwd_cells32<NS, B, L><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V, ctx->A.as<double>(), out)
+      if (ctx->banded) { if (lay8) FWD32(true, true); else FWD32(true, false); }
+      else { if (lay8) FWD32(false, true); else FWD32(false, false); }
+#undef FWD32
       return;
     }
     if (ctx->banded)
@@ -1336,8 +1338,17 @@ template <int NS> struct ScoreLaunch {
       k_fwd_cells<NS, false><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
                                                                  ctx->A.as<double>(), out);
   }
-  static void vit(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out) {
+  static void vit(hmmcu_ctx *ctx, const float *logb, int64_t fbase, int64_t ldb, int u0, int nu, double *out, bool lay8) {
     const unsigned grid = (unsigned)(((int64_t)nu * ctx->V + kCellThreads - 1) / kCellThreads);
+    if (lay8) {
+      if (ctx->banded)
+        k_vit_cells8<NS, true><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                   ctx->A.as<double>(), out);
+      else
+        k_vit_cells8<NS, false><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
+                                                                    ctx->A.as<double>(), out);
+      return;
+    }
     if (ctx->banded)
       k_vit_cells<NS, true><<<grid, kCellThreads, 0, ctx->st>>>(logb, fbase, ldb, ctx->off_d.as<int64_t>(), u0, nu, ctx->V,
                                                                 ctx->A.as<double>(), out);
@@ -1377,16 +1388,22 @@ template <int NS> struct ScoreLaunch {
 
 // mode 0: forward score, 1: Viterbi score
 // log-emissions of frames [fb0, fb1) against all V models of context c into c->logb ([frames][V*N])
-static int decode_emissions(hmmcu_ctx *ctx, int64_t fb0, int64_t fb1) {
+// lay8: in = the caller can read k_emis_dec's interleaved layout (dec_logb_index); out = the layout that was written
+static int decode_emissions(hmmcu_ctx *ctx, int64_t fb0, int64_t fb1, bool *lay8) {
   const int64_t S = (int64_t)ctx->V * ctx->N;
   int rc;
-  CK(ctx->logb.ensure(sizeof(float) * (size_t)(fb1 - fb0) * S));
+  const bool want8 = lay8 && *lay8;
+  if (lay8) *lay8 = false;
+  CK(ctx->logb.ensure(sizeof(float) * dec_logb_floats(fb1 - fb0, S)));
   if (tc_supported(ctx) && ws_supported(ctx)) {
     if ((rc = ensure_ws_images(ctx, 1)) != HMMCU_OK) return rc;
     const int nfr = (int)(fb1 - fb0), ntl = (nfr + kTcRows - 1) / kTcRows;
     t_begin(ctx, "emis");
     rc = HMMCU_EINVAL;
-    if (dec_supported(ctx) && ctx->ws_dec.TN <= kWsMaxTN) rc = launch_emis_dec(ctx, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+    if (want8 && dec_supported(ctx) && ctx->ws_dec.TN <= kWsMaxTN) {
+      rc = launch_emis_dec(ctx, ntl, nfr, ctx->logb.as<float>(), fb0, S);
+      if (rc == HMMCU_OK) *lay8 = true;
+    }
     if (rc != HMMCU_OK) rc = launch_emis_ws<false>(ctx, nullptr, (int64_t)ctx->ws_dec.nimg * ntl, ntl, nfr, ctx->logb.as<float>(), fb0, S);
     if (rc) return rc;
     t_end(ctx, "emis");
@@ -1447,19 +1464,27 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     while (u1 < ctx->U && ctx->off[u1 + 1] - ctx->off[u0] <= budget_frames) u1++;
     if (u1 == u0) u1 = u0 + 1;
     const int64_t fb0 = ctx->off[u0], fb1 = ctx->off[u1];
-    if ((rc = decode_emissions(ctx, fb0, fb1)) != HMMCU_OK) return rc;
+    // the interleaved layout of k_emis_dec is read by k_fwd_cells32, k_vit_cells8 and k_fwd_score; with several feature
+    // streams every stream has to write it (their log-emissions are added element by element)
+    auto can8 = [](const hmmcu_ctx *c) { return tc_supported(c) && ws_supported(c) && dec_supported(c); };
+    bool all8 = !(mode == 0 && !emulate && ctx->fwd_f64) && can8(ctx);
+    for (hmmcu_ctx *q : ctx->linked) all8 = all8 && can8(q);
+    bool lay8 = all8;
+    if ((rc = decode_emissions(ctx, fb0, fb1, &lay8)) != HMMCU_OK) return rc;
     for (hmmcu_ctx *q : ctx->linked) {  // multi-stream models: the product of the streams' densities (R-FS:341-364)
-      if ((rc = decode_emissions(q, fb0, fb1)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
-      const int64_t n = (fb1 - fb0) * S;
+      bool l8 = all8;
+      if ((rc = decode_emissions(q, fb0, fb1, &l8)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
+      if (l8 != lay8) return fail(ctx, HMMCU_ECUDA, "linked stream: the streams' log-emissions differ in layout");
+      const int64_t n = (int64_t)dec_logb_floats(fb1 - fb0, S);  // whole blocks of 8 frames (>= the frames either layout holds)
       k_add_logb<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->logb.as<float>(),
                                                                                                      q->logb.as<float>(), n);
       LAUNCH_CHECK();
     }
     t_begin(ctx, mode == 0 ? "score" : "viterbi");
     if (mode == 0) {
-      DISPATCH_N(ctx->N, ScoreLaunch<NS>::fwd(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>(), emulate));
+      DISPATCH_N(ctx->N, ScoreLaunch<NS>::fwd(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>(), emulate, lay8));
     } else {
-      DISPATCH_N(ctx->N, ScoreLaunch<NS>::vit(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>()));
+      DISPATCH_N(ctx->N, ScoreLaunch<NS>::vit(ctx, ctx->logb.as<float>(), fb0, S, u0, u1 - u0, ctx->score_d.as<double>(), lay8));
     }
     LAUNCH_CHECK();
     t_end(ctx, mode == 0 ? "score" : "viterbi");

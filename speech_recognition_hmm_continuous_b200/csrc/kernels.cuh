@@ -341,7 +341,8 @@ constexpr int kScoreThreads = 128;
 template <int NS>
 __global__ void __launch_bounds__(kScoreThreads)
 k_fwd_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off, int u0,
-            int V, const double *__restrict__ Aall, double *__restrict__ out, int emulate) {
+            int V, const double *__restrict__ Aall, double *__restrict__ out, int emulate, int lay8) {
+  // lay8: the interleaved layout k_emis_dec writes (dec_logb_index), ldb = number of state columns
   const int v = blockIdx.x * kScoreThreads + threadIdx.x;
   const int u = u0 + blockIdx.y;
   if (v >= V) return;
@@ -354,13 +355,15 @@ k_fwd_score(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const in
 #pragma unroll
   for (int i = 0; i < NS; i++) al[i] = 0.0;
   double lp = 0.0;
-  const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
-  for (int t = 0; t < T; t++, p += ldb) {
+  for (int t = 0; t < T; t++) {
+    const int64_t f = base - fbase + t;
+    const float *p = lay8 ? logb + ((f >> 3) * ldb + (int64_t)v * NS) * 8 + (f & 7) : logb + f * ldb + (int64_t)v * NS;
+    const int ps = lay8 ? 8 : 1;
     float lbv[NS];
     float mt = kNegInf;
 #pragma unroll
     for (int i = 0; i < NS; i++) {
-      lbv[i] = p[i];
+      lbv[i] = p[i * ps];
       if (emulate && (double)lbv[i] < kLogTrueMin) lbv[i] = kNegInf;  // the reference's density is exactly 0
       mt = fmaxf(mt, lbv[i]);
     }

@@ -345,7 +345,46 @@ __device__ __forceinline__ float lg2_ftz(float x) {
   return y;
 }
 
-template <int NS, bool BANDED>
+// Walks the frames [brel, brel + T) of a cell through the interleaved layout k_emis_dec writes (dec_logb_index: blocks of 8
+// frames, state-major inside a block): a (block, model) is N consecutive 32-byte sectors, read with 2 N 16-byte loads one
+// block ahead of the chain; adjacent threads (models) read adjacent 32 N bytes.  first(l) is called for t = 0, step(l) for
+// 0 < t < T, l = the N log-emissions of the frame.
+template <int NS, class First, class Step>
+__device__ __forceinline__ void cell_walk8(const float *__restrict__ logb8, int64_t S, int64_t brel, int T, int64_t col0, First first, Step step) {
+  const int64_t fb0 = brel >> 3, fb1 = (brel + T - 1) >> 3;
+  const float4 *p = reinterpret_cast<const float4 *>(logb8 + (fb0 * S + col0) * 8);
+  const int64_t stride4 = S * 2;  // 16-byte words per block of 8 frames
+  float4 nx[NS][2];
+#pragma unroll
+  for (int i = 0; i < NS; i++) { nx[i][0] = __ldg(p + 2 * i); nx[i][1] = __ldg(p + 2 * i + 1); }
+  int tb = (int)(fb0 * 8 - brel);  // t of the block's first frame (<= 0 in the first block)
+  for (int64_t fb = fb0; fb <= fb1; fb++, tb += 8) {
+    float cur[8][NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      cur[0][i] = nx[i][0].x; cur[1][i] = nx[i][0].y; cur[2][i] = nx[i][0].z; cur[3][i] = nx[i][0].w;
+      cur[4][i] = nx[i][1].x; cur[5][i] = nx[i][1].y; cur[6][i] = nx[i][1].z; cur[7][i] = nx[i][1].w;
+    }
+    if (fb < fb1) {
+      p += stride4;
+#pragma unroll
+      for (int i = 0; i < NS; i++) { nx[i][0] = __ldg(p + 2 * i); nx[i][1] = __ldg(p + 2 * i + 1); }
+    }
+    if (tb >= 1 && tb + 8 <= T) {  // a block in the interior of the utterance
+#pragma unroll
+      for (int k = 0; k < 8; k++) step(cur[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int t = tb + k;
+        if (t == 0) first(cur[k]);
+        else if (t > 0 && t < T) step(cur[k]);
+      }
+    }
+  }
+}
+
+template <int NS, bool BANDED, bool LAY8>
 __global__ void __launch_bounds__(kCellThreads)
 k_fwd_cells32(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const int64_t *__restrict__ off, int u0, int nu,
               int V, const double *__restrict__ Aall, double *__restrict__ out) {
@@ -354,6 +393,7 @@ k_fwd_cells32(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const 
   const int u = u0 + (int)(cell / V), v = (int)(cell % V);
   const int64_t base = off[u];
   const int T = (int)(off[u + 1] - base);
+  if (T <= 0) { out[(int64_t)u * V + v] = -INFINITY; return; }
   float la[NS * NS];  // log2 a_ij, "none" for a_ij = 0
 #pragma unroll
   for (int k = 0; k < NS * NS; k++) {
@@ -404,6 +444,12 @@ k_fwd_cells32(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const 
     for (int i = 0; i < NS; i++) lz[i] = fmaxf(nz[i] - m, kLzNone);  // also turns -inf (density 0) and NaN (-inf - -inf) into "none"
     msum += (double)m;
   };
+  if (LAY8) {
+    cell_walk8<NS>(logb, ldb, base - fbase, T, (int64_t)v * NS, first, step);
+    const double tot8 = msum + (double)lz[NS - 1];
+    out[(int64_t)u * V + v] = (tot8 > -1e29) ? 0.6931471805599453 * tot8 : -INFINITY;
+    return;
+  }
   // log-emissions kCellPF frames ahead of the chain; the bulk of the frames runs without index clamps
   const float *p = logb + (base - fbase) * ldb + (int64_t)v * NS;
   float nxt[kCellPF][NS];
@@ -500,6 +546,48 @@ k_vit_cells(const float *__restrict__ logb, int64_t fbase, int64_t ldb, const in
       }
     }
   }
+  out[(int64_t)u * V + v] = dl[NS - 1];
+}
+
+// k_vit_cells over the interleaved layout of k_emis_dec (cell_walk8)
+template <int NS, bool BANDED>
+__global__ void __launch_bounds__(kCellThreads)
+k_vit_cells8(const float *__restrict__ logb8, int64_t fbase, int64_t S, const int64_t *__restrict__ off, int u0, int nu,
+             int V, const double *__restrict__ Aall, double *__restrict__ out) {
+  const int64_t cell = (int64_t)blockIdx.x * kCellThreads + threadIdx.x;
+  if (cell >= (int64_t)nu * V) return;
+  const int u = u0 + (int)(cell / V), v = (int)(cell % V);
+  const int64_t base = off[u];
+  const int T = (int)(off[u + 1] - base);
+  if (T <= 0) { out[(int64_t)u * V + v] = 0.0; return; }  // as k_vit_cells: delta starts from 0 and no frame is applied
+  double la[NS * NS];
+#pragma unroll
+  for (int k = 0; k < NS * NS; k++) la[k] = log(Aall[(int64_t)v * NS * NS + k]);
+  double dl[NS];
+#pragma unroll
+  for (int i = 0; i < NS; i++) dl[i] = 0.0;
+  auto first = [&](const float (&l)[NS]) {
+#pragma unroll
+    for (int i = 0; i < NS; i++) dl[i] = (i == 0 ? 0.0 : -INFINITY) + (double)l[i];
+  };
+  auto step = [&](const float (&l)[NS]) {
+    double dn[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+      double best = dl[0] + la[j];
+#pragma unroll
+      for (int i = 1; i < NS; i++) {
+        if (!BANDED || i == j || i + 1 == j) {
+          const double c = dl[i] + la[i * NS + j];
+          if (c > best) best = c;
+        }
+      }
+      dn[j] = best + (double)l[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NS; j++) dl[j] = dn[j];
+  };
+  cell_walk8<NS>(logb8, S, base - fbase, T, (int64_t)v * NS, first, step);
   out[(int64_t)u * V + v] = dl[NS - 1];
 }
 

@@ -54,13 +54,16 @@ constexpr int kWsXch = 6;         // states per image when a state spans several
 __host__ __device__ inline size_t ws_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 4) * 128 + (size_t)TN * 4; }
 __host__ __device__ inline size_t ws_emis_smem_bytes(int TN, int KP) { return ws_image_bytes(TN, KP) + 1024 + 272; }
 
-// Mixtures per state as laid out in the W image.  M <= 16: padded to a power of two, so that a 16-column chunk
-// holds 16 / MP whole states and the epilogue can store a chunk's log b with 16- / 8-byte stores (measured at the
-// 1,000-word decode shape: M = 3 laid out unpadded, five states and one pad column per chunk, needs 4-byte
-// stores and runs 2x slower than M = 3 padded to 4); M > 16: padded to a multiple of 16 (a state spans M / 16
-// chunks).  State boundaries never cut through a chunk.  Pad columns have W = 0 and kc = -inf (density 0).
+// Mixtures per state as laid out in the W image.  A 16-column chunk holds 16 / MP whole states (state boundaries never cut
+// through a chunk; 16 % MP pad columns close it).  M <= 16: padded to a power of two -- except M = 3 and M = 5, where the
+// padding would be a quarter / three eighths of every MMA: they are laid out as they are (five states of 3 and one pad
+// column, three states of 5 and one pad column).  A chunk then holds an odd number of states, so a row-per-frame output
+// needs 4-byte stores (k_emis_ws: measured 2x slower in the 1,000-word decode regime, every store its own sector); the
+// decode kernel k_emis_dec writes an interleaved layout instead in which 4-byte stores of a warp fill whole lines.
+// M > 16: padded to a multiple of 16 (a state spans M / 16 chunks).  Pad columns have W = 0 and kc = -inf (density 0).
 __host__ __device__ inline int ws_pad_m(int M) {
   if (M > 16) return (M + 15) / 16 * 16;
+  if (M == 3 || M == 5) return M;
   int p = 1;
   while (p < M) p <<= 1;
   return p;
