@@ -1458,6 +1458,17 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     budget_bytes = std::max<int64_t>(budget_bytes, 256ll << 20);
   }
   const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, budget_bytes / (4 * S));
+  // the scores of a batch go back to the host (copy stream) while the next batch is computed
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+  struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int k = 0; k < 2; k++) if (e[k]) cudaEventDestroy(e[k]); } } ev_guard{ev_done};
+  int pend_u0 = -1, pend_u1 = -1, nbatch = 0;
+  auto copy_back = [&](int a, int b, cudaEvent_t ev) -> cudaError_t {
+    cudaError_t e = cudaStreamWaitEvent(ctx->st_copy, ev, 0);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(out_host + (size_t)a * ctx->V, ctx->score_d.as<double>() + (size_t)a * ctx->V, sizeof(double) * (size_t)(b - a) * ctx->V,
+                           cudaMemcpyDeviceToHost, ctx->st_copy);
+  };
   int u0 = 0;
   while (u0 < ctx->U) {
     int u1 = u0;
@@ -1488,9 +1499,14 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     }
     LAUNCH_CHECK();
     t_end(ctx, mode == 0 ? "score" : "viterbi");
+    CK(cudaEventRecord(ev_done[nbatch & 1], ctx->st));
+    if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));  // blocks this thread for pageable memory; the device works on
+    pend_u0 = u0; pend_u1 = u1;
+    nbatch++;
     u0 = u1;
   }
-  CK(cudaMemcpyAsync(out_host, ctx->score_d.p, sizeof(double) * (size_t)ctx->U * ctx->V, cudaMemcpyDeviceToHost, ctx->st));
+  if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));
+  CK(cudaStreamSynchronize(ctx->st_copy));
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }
