@@ -138,7 +138,7 @@ def workload_config(name, world):
             "l2": "flushed between timed iterations (256 MiB write)"}
 
 
-def gen_corpus_device(torch, dev, cen, s, labels_all, u0, u1, seed):
+def gen_corpus_device(torch, dev, cen, s, labels_all, u0, u1, seed, block=None):
     """Utterances [u0, u1) of a synthetic corpus of len(labels_all) utterances, generated on the device (SURVEY 8d's
     generator: left-to-right walk with +-20 % jitter, T ~ U{250..350}, a random mixture centre + N(0, s^2) noise).
     The corpus does not depend on how it is sharded: lengths and state cuts come from one host generator over the
@@ -146,6 +146,7 @@ def gen_corpus_device(torch, dev, cen, s, labels_all, u0, u1, seed):
     multiples of GEN_BLOCK or the ends).  -> (x float64 [F][D] on the device, off int64 [u1-u0+1], labels int32)"""
     V, N, M, _ = cen.shape
     Uall = len(labels_all)
+    GEN_BLOCK = block or globals()["GEN_BLOCK"]
     rng = np.random.default_rng(seed)
     T = rng.integers(250, 351, size=Uall)
     wj = 1.0 + 0.4 * (rng.random((Uall, N)) - 0.5)
@@ -600,8 +601,9 @@ def tf32_peak_tflops(device):
 
 
 # ============================================================= the other BASELINE configurations ====
-def _shard(total, rank, world):
+def _shard(total, rank, world, block=None):
     """Contiguous shard of `total` utterances in whole generator blocks (the corpus is the same for every world size)."""
+    GEN_BLOCK = block or globals()["GEN_BLOCK"]
     blocks = (total + GEN_BLOCK - 1) // GEN_BLOCK
     b0, b1 = blocks * rank // world, blocks * (rank + 1) // world
     return min(b0 * GEN_BLOCK, total), min(b1 * GEN_BLOCK, total)
@@ -649,8 +651,9 @@ def _decode_config(t, args, name, desc, V, N, M, U, seed):
     torch, dist, api, synth, dev, world, rank = t["torch"], t["dist"], t["api"], t["synth"], t["dev"], t["world"], t["rank"]
     cen, s = synth.make_centres(V, N, M, D, seed=seed)
     labels_all = (np.arange(U) % V).astype(np.int32)
-    u0, u1 = _shard(U, rank, world)
-    x, off, lab = gen_corpus_device(torch, dev, cen, s, labels_all, u0, u1, seed=seed + 1)
+    block = GEN_BLOCK if U >= 8 * GEN_BLOCK else max(1, U // 8)   # at least eight generator blocks: every rank of 8 gets a shard
+    u0, u1 = _shard(U, rank, world, block)
+    x, off, lab = gen_corpus_device(torch, dev, cen, s, labels_all, u0, u1, seed=seed + 1, block=block)
     F = int(off[-1])
     c = api.Context(t["local"], timing=True)
     c.set_features_device(x.data_ptr(), off, D)

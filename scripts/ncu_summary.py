@@ -1,7 +1,8 @@
-"""Summarise an .ncu-rep: python scripts/ncu_summary.py rep [out.md]"""
+"""Summarise an .ncu-rep (or its `--page raw --csv` export): python scripts/ncu_summary.py rep|raw.csv [out.md]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = raw[raw.index('"ID"'):]
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',

@@ -512,8 +512,16 @@ static int check_linked(hmmcu_ctx *ctx) {
   return HMMCU_OK;
 }
 
-__global__ void k_add_logb(float *__restrict__ out, const float *__restrict__ a, const float *__restrict__ b, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+// flush_a / flush_b: the operand is ONE stream's log-density and the reference's linear-domain density underflows to exactly 0
+// below DBL_TRUE_MIN (it flushes every stream's symbol_probab on its own before multiplying them, R-FS:341-367)
+__global__ void k_add_logb(float *__restrict__ out, const float *__restrict__ a, const float *__restrict__ b, int64_t n, int flush_a = 0,
+                           int flush_b = 0) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x = a[i], y = b[i];
+    if (flush_a && (double)x < kLogTrueMin) x = kNegInf;
+    if (flush_b && (double)y < kLogTrueMin) y = kNegInf;
+    out[i] = x + y;
+  }
 }
 // the per-word statistics every stream shares: [num_trans N*N, den_trans N, den_mix N] at the head, [sum_logP, n_utt] at the tail
 __global__ void k_copy_shared_stats(double *__restrict__ dst, int64_t ss_dst, const double *__restrict__ src, int64_t ss_src, int V, int head) {
@@ -1487,8 +1495,9 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
       if ((rc = decode_emissions(q, fb0, fb1, &l8)) != HMMCU_OK) return fail(ctx, rc, "linked stream: %s", q->err);
       if (l8 != lay8) return fail(ctx, HMMCU_ECUDA, "linked stream: the streams' log-emissions differ in layout");
       const int64_t n = (int64_t)dec_logb_floats(fb1 - fb0, S);  // whole blocks of 8 frames (>= the frames either layout holds)
+      const int fl = (mode == 0 && emulate) ? 1 : 0;  // underflow emulation: per stream, before the product
       k_add_logb<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->st>>>(ctx->logb.as<float>(), ctx->logb.as<float>(),
-                                                                                                     q->logb.as<float>(), n);
+                                                                                                     q->logb.as<float>(), n, fl && q == ctx->linked[0], fl);
       LAUNCH_CHECK();
     }
     t_begin(ctx, mode == 0 ? "score" : "viterbi");

@@ -541,6 +541,40 @@ def test_two_stream_estep_on_the_tensor_core_path():
 
 
 # ------------------------------------------------- full-size, size-independent properties ----
+def test_two_stream_underflow_is_flushed_per_stream():
+    """The reference flushes every stream's density on its own before it multiplies them (R-FS:341-367): a cell in which
+    one stream's density underflows to exactly 0 is dead even when the SUM of the streams' log-densities is
+    representable.  Stream 0 of the wrong word sits 40 sigma off (log density -802 < log DBL_TRUE_MIN = -744.4),
+    stream 1 has a sharp, perfectly matching Gaussian (log density +61): sum = -741."""
+    V, N, T, U = 2, 2, 12, 2
+    A = np.tile(np.array([[0.6, 0.4], [0.0, 1.0]]), (V, 1, 1))
+    c1 = np.ones((V, N, 1))
+    mu0 = np.zeros((V, N, 1, 2)); mu0[1, :, :, 0] += 40.0
+    ms0 = api.ModelSet(A, c1, mu0, np.ones((V, N, 1, 2)), np.ones((V, N, 1)))
+    var1 = 1e-14
+    mu1 = np.zeros((V, N, 1, 4))
+    ms1 = api.ModelSet(A, c1, mu1, np.full((V, N, 1, 4), 1.0 / var1), np.full((V, N, 1), var1 ** 4))
+    off = np.arange(U + 1, dtype=np.int64) * T
+    x0 = np.zeros((U * T, 2)); x0[T:, 0] += 40.0          # utterance 0 = word 0, utterance 1 = word 1
+    x1 = np.zeros((U * T, 4))
+    cs = [api.Context(0), api.Context(0)]
+    cs[0].set_features(x0, off); cs[0].set_models(ms0)
+    cs[1].set_features(x1, off); cs[1].set_models(ms1)
+    cs[0].link_streams([cs[1]])
+    got = cs[0].forward_scores(emulate_underflow=True)
+    plain = cs[0].forward_scores()
+    with np.errstate(all="ignore"):
+        want = np.array([[o.forward_score_streams([_oracle_model(ms0, v), _oracle_model(ms1, v)], [x0[off[u]:off[u + 1]], x1[off[u]:off[u + 1]]])
+                          for v in range(V)] for u in range(U)])
+    assert np.isfinite(want[0, 0]) and np.isfinite(want[1, 1]) and not np.isfinite(want[0, 1]) and not np.isfinite(want[1, 0])
+    assert (np.isfinite(got) == np.isfinite(want)).all(), (got, want)
+    fin = np.isfinite(want)
+    assert np.allclose(got[fin], want[fin], rtol=RTOL)
+    assert np.isfinite(plain).all()                    # without the emulation the log-domain score of the dead cells exists
+    for c in cs:
+        c.close()
+
+
 def test_c2_size_properties(ctx):
     """BASELINE config 2 (N=5, M=16, 1000 utterances of ~300 frames): too big for the CPU oracle in a
     test, so check identities that hold at any size: sum_m S0 = den_mix; band row sums of num_trans =
