@@ -162,6 +162,7 @@ struct hmmcu_ctx {
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
   int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int fwd_f64 = 0;       // forward cell scorer with the chain in double (k_fwd_cells) instead of k_fwd_cells32
+  int dec_budget_kb = 0; // log-emission budget of a decode batch in KiB (0 = 6 GiB or a third of the free memory); tests
   int dec_dbg = 0;       // experiments on k_emis_dec: 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no W copies (results are garbage)
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
@@ -468,6 +469,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
+  if (strcmp(key, "dec_budget_kb") == 0) { ctx->dec_budget_kb = value; return HMMCU_OK; }
   if (strcmp(key, "dec_dbg") == 0) { ctx->dec_dbg = value; return HMMCU_OK; }
   if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
   if (strcmp(key, "dec_cluster") == 0) { ctx->dec_cluster = value == 4 ? 4 : 2; ctx->dec_grid = 0; return HMMCU_OK; }
@@ -1459,7 +1461,8 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   // utterance batches so that the log-emission buffer stays under ~6 GiB (a third of the free memory when that is less):
   // large batches keep the tail of k_emis_dec's rounds small (every CTA walks all images once per frame tile it holds)
   int64_t budget_bytes = 6144ll << 20;
-  {
+  if (ctx->dec_budget_kb > 0) budget_bytes = (int64_t)ctx->dec_budget_kb << 10;  // tests: many small batches
+  else {
     size_t mem_free = 0, mem_total = 0;
     if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess) budget_bytes = std::min<int64_t>(budget_bytes, (int64_t)((mem_free + ctx->logb.cap) / 3));
     else cudaGetLastError();

@@ -727,6 +727,30 @@ def test_decode_paths_other_shapes(ctx, N, M, D):
     assert (lab == labels).all()
 
 
+@pytest.mark.parametrize("M", [3, 5, 4])
+def test_decode_in_many_batches_equals_one_batch(M):
+    """hmmcu_forward_scores / hmmcu_viterbi_scores work in utterance batches (R-FS:283-390 is one loop over the test list);
+    a batch starts at an arbitrary frame, so the interleaved log-emission layout (blocks of 8 frames) is addressed relative
+    to the batch.  With a budget of a few KiB every utterance or two is a batch of its own: the scores must be the
+    bits of the single-batch run, for the unpadded M = 3 / M = 5 image layouts and a padded one, and within 1e-4 of the
+    oracle.  Also with the reference's underflow emulated (k_fwd_score reads the same layout)."""
+    ms, x, off, labels = _synth(7, 5, M, 11, seed=77 + M, tmin=5, tmax=61)
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    one = (c.forward_scores(), c.viterbi_scores(), c.forward_scores(emulate_underflow=True))
+    c.set_option("dec_budget_kb", 16)   # 16 KiB / (4 B * 35 state columns) = 117 frames per batch
+    many = (c.forward_scores(), c.viterbi_scores(), c.forward_scores(emulate_underflow=True))
+    for a, b in zip(one, many):
+        assert np.array_equal(a, b, equal_nan=True)
+    want = np.array([[o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]]) for v in range(ms.V)] for u in range(len(labels))])
+    fin = np.isfinite(want)
+    assert fin.all() and np.allclose(many[0], want, rtol=RTOL, atol=0)
+    lab, _ = c.rank(many[0])
+    assert (lab == labels).all()
+    c.close()
+
+
 @pytest.mark.parametrize("dense", [False, True])
 def test_forward_cell_scorers_single_and_double_chain(dense):
     """k_fwd_cells32 (log-domain single-precision chain, the default) and k_fwd_cells (double chain, option
