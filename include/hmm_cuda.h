@@ -62,7 +62,12 @@ void hmmcu_host_free(void *p);
  * forward-backward kernel (k_fb) instead of the shared-memory-resident one (k_fb_res, the default whenever the utterances fit
  * and the transition matrices are banded);
  * "upload_chunks": chunks hmmcu_set_features splits the host-to-device copy into (packing overlaps the copy);
- * "mstep_fork": 1 (default) = the accuracy-guard scan and one of the two model packers of hmmcu_mstep run on side streams. */
+ * "mstep_fork": 1 (default) = the accuracy-guard scan and one of the two model packers of hmmcu_mstep run on side streams;
+ * "dec_emis": 1 (default) = decode emissions of models with M <= 16 through k_emis_dec (frame tile resident in tensor memory, W
+ * images multicast over a cluster, interleaved log-emission layout), 0 = k_emis_ws; "dec_cluster": 2 (default) or 4 CTAs per
+ * cluster; "fwd_f64": 1 = the forward cell scorer with a double-precision linear chain instead of the single-precision
+ * log-domain one; "dec_budget_kb": log-emission budget of one decode batch in KiB (0 = 6 GiB or a third of the free memory);
+ * "dec_dbg": experiment switches of k_emis_dec (results are garbage: 1 no epilogue arithmetic, 2 no MMAs, 4 no W copies). */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 
 /* ---------------------------------------------------------------- inputs ----------------- */

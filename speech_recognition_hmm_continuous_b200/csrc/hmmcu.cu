@@ -1462,7 +1462,9 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   // large batches keep the tail of k_emis_dec's rounds small (every CTA walks all images once per frame tile it holds)
   int64_t budget_bytes = 6144ll << 20;
   if (ctx->dec_budget_kb > 0) budget_bytes = (int64_t)ctx->dec_budget_kb << 10;  // tests: many small batches
-  else {
+  else if ((int64_t)(sizeof(float) * dec_logb_floats(ctx->off[ctx->U] - ctx->off[0], S)) > std::max<int64_t>((int64_t)ctx->logb.cap, 256ll << 20)) {
+    // (only a call that needs a larger buffer than the context already holds asks the driver: cudaMemGetInfo costs
+    // 0.2-0.5 ms, as much as a whole small decode)
     size_t mem_free = 0, mem_total = 0;
     if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess) budget_bytes = std::min<int64_t>(budget_bytes, (int64_t)((mem_free + ctx->logb.cap) / 3));
     else cudaGetLastError();
@@ -1470,8 +1472,10 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
   }
   const int64_t budget_frames = std::max<int64_t>(ctx->Tmax, budget_bytes / (4 * S));
   // the scores of a batch go back to the host (copy stream) while the next batch is computed
+  // (a call that fits one batch copies on the context's stream: no events, no second stream)
+  const bool one_batch = ctx->off[ctx->U] - ctx->off[0] <= budget_frames;
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
-  for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+  for (int k = 0; k < 2 && !one_batch; k++) CK(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
   struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int k = 0; k < 2; k++) if (e[k]) cudaEventDestroy(e[k]); } } ev_guard{ev_done};
   int pend_u0 = -1, pend_u1 = -1, nbatch = 0;
   auto copy_back = [&](int a, int b, cudaEvent_t ev) -> cudaError_t {
@@ -1511,14 +1515,20 @@ static int score_all(hmmcu_ctx *ctx, double *out_host, int mode, int emulate) {
     }
     LAUNCH_CHECK();
     t_end(ctx, mode == 0 ? "score" : "viterbi");
-    CK(cudaEventRecord(ev_done[nbatch & 1], ctx->st));
-    if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));  // blocks this thread for pageable memory; the device works on
-    pend_u0 = u0; pend_u1 = u1;
+    if (!one_batch) {
+      CK(cudaEventRecord(ev_done[nbatch & 1], ctx->st));
+      if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));  // blocks this thread for pageable memory; the device works on
+      pend_u0 = u0; pend_u1 = u1;
+    }
     nbatch++;
     u0 = u1;
   }
-  if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));
-  CK(cudaStreamSynchronize(ctx->st_copy));
+  if (one_batch) {
+    CK(cudaMemcpyAsync(out_host, ctx->score_d.p, sizeof(double) * (size_t)ctx->U * ctx->V, cudaMemcpyDeviceToHost, ctx->st));
+  } else {
+    if (pend_u0 >= 0) CK(copy_back(pend_u0, pend_u1, ev_done[(nbatch - 1) & 1]));
+    CK(cudaStreamSynchronize(ctx->st_copy));
+  }
   CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }

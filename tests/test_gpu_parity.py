@@ -612,6 +612,55 @@ def test_c2_size_properties(ctx):
         assert abs(lpu[u] - want) <= RTOL * abs(want)
 
 
+def test_c2_full_size_estep_and_decode_match_oracle(ctx):
+    """BASELINE configs[1] in full -- 10 words, N=5, M=16, D=39, 1,000 utterances, ~300,000 frames, the workload of the
+    headline bench line -- against the oracle (the C restatement finishes it in seconds): log P of every utterance, the
+    statistics of EVERY word (T-FS:244-321) and the parameters the M-step makes of them within 1e-4; then the forward
+    scores of every tenth utterance against all 10 models and the labels (R-FS:341-390).  The models are the generating
+    ones moved by 0.3 sigma, so that the posteriors are not trivially sharp."""
+    V, N, M, U = 10, 5, 16, 1000
+    cen, s = synth.make_centres(V, N, M, 39, seed=1234)
+    labels = np.arange(U) % V
+    x, off = synth.make_utterances(cen, s, labels, seed=1234)
+    rng = np.random.default_rng(99)
+    ms = api.ModelSet.from_dict(synth.make_models(cen + 0.3 * s * rng.standard_normal(cen.shape), s))
+    ctx.set_features(x, off)
+    ctx.set_models(ms)
+    stats, lpu = ctx.estep(labels)
+    assert np.isfinite(lpu).all()
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st, lp = o.estep(_oracle_model(ms, v), xv, offv)
+        sp = api.split_stats(stats[v], N, M, ms.D)
+        assert np.allclose(lpu[us], lp, rtol=RTOL), v
+        assert abs(sp["sum_logp"] - st.sum_logp) <= RTOL * abs(st.sum_logp) and sp["n_utt"] == len(us)
+        for name in ("num_trans", "den_trans", "den_mix", "S0"):
+            want = getattr(st, name)
+            assert np.allclose(sp[name], want, rtol=RTOL, atol=1e-6 * np.abs(want).max()), (v, name)
+        S0 = np.maximum(st.S0, 1e-300)[..., None]
+        sd = np.sqrt(st.S2c / S0)
+        assert (np.abs(sp["S1"] / S0 - st.S1 / S0) <= RTOL * np.maximum(np.abs(st.S1 / S0), sd)).all(), (v, "S1")
+        assert np.allclose(sp["S2c"] / S0, st.S2c / S0, rtol=RTOL), (v, "S2c")
+        mo = _oracle_model(ms, v)
+        o.mstep(mo, st)
+        one = api.ModelSet(ms.A[v:v + 1].copy(), ms.c[v:v + 1].copy(), ms.mu[v:v + 1].copy(), ms.iv[v:v + 1].copy(), ms.det[v:v + 1].copy())
+        _assert_params_close(api.mstep(one, stats[v:v + 1]), 0, mo)
+    sc = ctx.forward_scores()
+    vsc = ctx.viterbi_scores()
+    lab, sec = ctx.rank(sc)
+    assert (lab == labels).all()
+    for u in range(0, U, 10):
+        xu = x[off[u]:off[u + 1]]
+        want = np.array([o.forward_score(_oracle_model(ms, v), xu) for v in range(V)])
+        assert np.allclose(sc[u], want, rtol=RTOL, atol=0), u
+        order = o.rank(want)
+        assert lab[u] == order[0] and sec[u] == order[1]
+        assert (vsc[u] <= sc[u] + 1e-6 * np.abs(sc[u])).all()      # the best path is one of the paths the forward score sums
+    assert np.allclose(sc[np.arange(U), labels], lpu, rtol=1e-6)   # the E-step's log P and the decode path's score of the own model
+
+
 # ------------------------------------------------------ new code paths of this round's kernels ----
 def test_graph_replay_gives_the_same_em_iterations():
     """The E-step / M-step launch sequences are replayed as CUDA graphs from the third call on: five EM
