@@ -776,6 +776,31 @@ def test_decode_paths_other_shapes(ctx, N, M, D):
     assert (lab == labels).all()
 
 
+@pytest.mark.parametrize("N,M,D", [(1, 1, 39), (8, 2, 39), (3, 8, 39), (6, 16, 39), (2, 5, 39), (7, 3, 39), (5, 3, 7), (4, 4, 12)])
+def test_decode_kernel_variants_match_oracle(N, M, D):
+    """Every image layout k_emis_dec is built for (1, 2, 3, 4, 5, 8, 16 mixtures per state; 1 to 8 states; feature widths
+    whose padded row is not a multiple of 8 floats) with the interleaved layout and both cell scorers behind it: forward
+    scores within 1e-4 of the oracle (R-FS:341-369, 739-836), Viterbi scores within 1e-4 of the oracle's, labels equal."""
+    ms, x, off, labels = _synth(5, N, M, 10, seed=900 + 10 * N + M, tmin=max(N, 9), tmax=70, D=D)
+    c = api.Context(0)
+    c.set_features(x, off)
+    c.set_models(ms)
+    sc, vs = c.forward_scores(), c.viterbi_scores()
+    assert c.kernel_ms("dec_grid") > 0          # k_emis_dec ran
+    for u in range(len(labels)):
+        xu = x[off[u]:off[u + 1]]
+        for v in range(ms.V):
+            mo = _oracle_model(ms, v)
+            want = o.forward_score(mo, xu)
+            b, _ = o.emissions(mo, xu, want_post=False)
+            wv, _ = o.viterbi(mo, b)
+            assert abs(sc[u, v] - want) <= RTOL * abs(want), (u, v)
+            assert abs(vs[u, v] - wv) <= RTOL * abs(wv), (u, v)
+    lab, _ = c.rank(sc)
+    assert (lab == labels).all()
+    c.close()
+
+
 @pytest.mark.parametrize("M", [3, 5, 4])
 def test_decode_in_many_batches_equals_one_batch(M):
     """hmmcu_forward_scores / hmmcu_viterbi_scores work in utterance batches (R-FS:283-390 is one loop over the test list);
