@@ -23,6 +23,7 @@
 // waited for it (period = (MMA + epilogue) / 2; measured 54 % pipe activity, the same as k_emis_ws).  W image layout and
 // the MMA descriptors are k_emis_ws's.
 #pragma once
+#include <cuda_fp16.h>
 #include "ws_kernels.cuh"
 
 namespace hmmk {
@@ -32,6 +33,10 @@ constexpr int kDecEpiWarps = 12;
 constexpr int kDecThreads = (kDecEpiWarps + 6) * 32;  // + 4 expanders, MMA issuer, producer
 constexpr int kDecStages = 3;                         // W images in flight per CTA
 constexpr int kDecAcc = 3;                            // accumulator stages in tensor memory
+// half-precision operands: an image is half as large and its MMAs take half as long, so twice the stages cover the same
+// refill latency; the frame tile takes 80 tensor-memory columns instead of 160, which leaves room for a fourth accumulator
+constexpr int kDecStages16 = 6;
+constexpr int kDecAcc16 = 4;
 
 // Output layout of k_emis_dec ("interleaved"): blocks of 8 frames, state-major inside a block,
 //   logb[((f / 8) * S + s) * 8 + f % 8]        f = frame of the batch, s = state column (model * N + state), S = ldb
@@ -41,7 +46,9 @@ constexpr int kDecAcc = 3;                            // accumulator stages in t
 __host__ __device__ inline int64_t dec_logb_index(int64_t f, int64_t s, int64_t S) { return ((f >> 3) * S + s) * 8 + (f & 7); }
 __host__ __device__ inline size_t dec_logb_floats(int64_t nframes, int64_t S) { return (size_t)((nframes + 7) / 8) * 8 * (size_t)S; }
 
-__host__ __device__ inline size_t dec_emis_smem_bytes(int TN, int KP) { return kDecStages * ws_image_bytes(TN, KP) + 1024 + 512; }
+__host__ __device__ inline size_t dec_emis_smem_bytes(int TN, int KP, bool h16 = false) {
+  return (h16 ? kDecStages16 * ((size_t)2 * (TN / 8) * (KP / 8) * 128 + (size_t)TN * 4) : kDecStages * ws_image_bytes(TN, KP)) + 1024 + 512;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -67,22 +74,113 @@ __device__ __forceinline__ void tc_commit_multicast(uint32_t mbar, uint16_t mask
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask) : "memory");
 }
 
-// MP: padded mixtures per state (1, 2, 4, 8, 16); MR: real mixtures of a state (0 = all MP)
-template <int MP, int MR, int CL>
+// ---- half-precision operands (H16): the same contraction with kind::f16 MMAs, which run at twice the TF32 rate ----------
+// A TF32 operand keeps 11 significant bits, as a half does; hi + lo of a half split carry the same 22 bits as the 3xTF32
+// split -- provided the halves stay inside the half's narrow exponent range.  Every dimension is therefore rescaled by powers
+// of two (exact): x' = x / s1_d against W' = mu iv s1_d, and x''^2 = (x / s2_d)^2 against -iv s2_d^2 / 2, with s1_d, s2_d
+// chosen so that the two factors of a term have the same magnitude (k_dec16_scales: both at most sqrt(kappa), the accuracy
+// guard's bound, so nothing overflows; a lo part below the normal range costs at most 3e-8 times the other factor).
+// W image: [hi: (TN/8) P16][lo: (TN/8) P16][kc2: TN floats], P16 = (KP/8) 128: K-major, 16-byte chunks of 8 halves.
+__host__ __device__ inline size_t dec16_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 8) * 128 + (size_t)TN * 4; }
+
+// sc[0..DP) = 1/s1, [DP..2DP) = 1/s2, [2DP..3DP) = s1, [3DP..4DP) = s2^2   (powers of two; 1 for the pad dimensions)
+__global__ void k_dec16_scales(const unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs, int D, int DP, float *__restrict__ sc) {
+  const int d = threadIdx.x;
+  if (d >= DP) return;
+  float s1 = 1.f, s2 = 1.f;
+  bool dead = false;  // no frame leaves the centre in this dimension: both of its terms are exactly 0 (the constant kc holds the rest)
+  if (d < D) {
+    const double ivm = __longlong_as_double((long long)ext[d]), mum = __longlong_as_double((long long)ext[DP + d]);
+    const double r = xabs ? (double)__uint_as_float(xabs[d]) : mum;
+    const double wl = mum * ivm;                                  // largest |mu iv|
+    dead = !(r > 0.0);
+    if (r > 0.0 && wl > 0.0 && wl < INFINITY) s1 = exp2f(rintf(0.5f * log2f((float)(r / wl))));
+    if (r > 0.0 && ivm > 0.0 && ivm < INFINITY) s2 = exp2f(rintf(0.25f * log2f((float)(2.0 * r * r / ivm))));
+  }
+  sc[d] = dead ? 0.f : 1.f / s1;
+  sc[DP + d] = dead ? 0.f : 1.f / s2;
+  sc[2 * DP + d] = dead ? 0.f : s1;
+  sc[3 * DP + d] = dead ? 0.f : s2 * s2;
+}
+
+__device__ __forceinline__ void split_half(float v, unsigned short &hi, unsigned short &lo) {
+  const __half h = __float2half_rn(v);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+}
+
+// as k_pack_w_ws, for the half-precision images (column layout of the states, pad columns and kc2 are the same)
+__global__ void k_pack_w_dec16(const double *__restrict__ mu, const double *__restrict__ iv, const float *__restrict__ kc2all,
+                               const double *__restrict__ ctr, const float *__restrict__ sc, int M, int MP, int D, int DP, int TN,
+                               const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
+                               unsigned char *__restrict__ images) {
+  const int img = blockIdx.y;
+  const int KP = 2 * DP;
+  const uint32_t P = (uint32_t)(KP / 8) * 128;
+  unsigned char *hi = images + (size_t)img * dec16_image_bytes(TN, KP);
+  unsigned char *lo = hi + (size_t)(TN / 8) * P;
+  float *kc2 = reinterpret_cast<float *>(lo + (size_t)(TN / 8) * P);
+  const int64_t s0g = img_state0[img];
+  const int nst = img_nstates[img];
+  auto gauss_of = [&](int n) -> int64_t {
+    const int spc = 16 / MP, c = n >> 4, w = n & 15;
+    if (w >= spc * MP) return -1;
+    const int st = c * spc + w / MP, m = w % MP;
+    return (st < nst && m < M) ? (s0g + st) * M + m : -1;
+  };
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TN * KP; idx += gridDim.x * blockDim.x) {
+    const int n = idx / KP, k = idx - n * KP;
+    const int part = k / DP, d = k - part * DP;
+    const int64_t g = gauss_of(n);
+    float val = 0.f;
+    if (g >= 0 && d < D) {
+      const double m = mu[g * D + d] - ctr[d], w = iv[g * D + d];
+      val = (float)(part == 0 ? m * w * (double)sc[2 * DP + d] : -0.5 * w * (double)sc[3 * DP + d]);
+    }
+    unsigned short h, l;
+    split_half(val, h, l);
+    const size_t o = (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2 + (size_t)(k >> 3) * 128 + (size_t)(n >> 3) * P;
+    *reinterpret_cast<unsigned short *>(hi + o) = h;
+    *reinterpret_cast<unsigned short *>(lo + o) = l;
+    if (k == 0) kc2[n] = (g >= 0) ? kc2all[g] : kNegInf;
+  }
+}
+
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// MP: padded mixtures per state (1, 2, 3, 4, 5, 8, 16); MR: real mixtures of a state (0 = all MP); CL: CTAs per cluster;
+// H16: half-precision operands (images of k_pack_w_dec16, `scales` of k_dec16_scales)
+template <int MP, int MR, int CL, bool H16>
 __global__ void __launch_bounds__(kDecThreads, 1)
 k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, const float *__restrict__ images, int DP, int TN,
-           float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt, int dbg) {
+           float *__restrict__ logb, int64_t fbase, int64_t ldb, int S_total, int SCt, int dbg, const float *__restrict__ scales) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int NST = kDecStages;
+  constexpr int NST = H16 ? kDecStages16 : kDecStages;
   const int KP = 2 * DP;
-  const uint32_t P = (uint32_t)(KP / 4) * 128;
+  const uint32_t P = H16 ? (uint32_t)(KP / 8) * 128 : (uint32_t)(KP / 4) * 128;
   const uint32_t w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
   const uint32_t Ws = (smem_u32(smem_raw) + 1023u) & ~1023u;  // NST stages of img_bytes (multiples of 64)
   const uint32_t bars = (Ws + NST * img_bytes + 15u) & ~15u;
-  constexpr int NA = kDecAcc;
+  constexpr int NA = H16 ? kDecAcc16 : kDecAcc;
   const uint32_t full = bars, empty = bars + 8 * NST, dfull = bars + 16 * NST, dempty = dfull + 8 * NA, kfull = dfull + 16 * NA, xfull = dfull + 24 * NA,
                  xempty = xfull + 8, tmem_slot = xfull + 16;
-  __shared__ __align__(16) float skc[kDecAcc][kWsMaxTN];  // additive constants of the image an accumulator stage belongs to
+  __shared__ __align__(16) float skc[kDecAcc16][kWsMaxTN];  // additive constants of the image an accumulator stage belongs to
+  __shared__ float ssc[2][40];                             // H16: 1 / s1_d, 1 / s2_d
+  if (H16) {
+    for (int d = threadIdx.x; d < 80; d += kDecThreads) ssc[d / 40][d % 40] = (d % 40 < DP) ? scales[(d / 40) * DP + d % 40] : 1.f;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
   constexpr int kDecCluster = CL;
@@ -112,7 +210,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
   cluster_sync_all();  // every CTA's barriers exist before anybody's copies or commits reach them
   tc_fence_after();
   const uint32_t tmem0 = (uint32_t)lds_i32(tmem_slot);
-  constexpr uint32_t acc0 = 160, ACS = 96;
+  constexpr uint32_t acc0 = H16 ? 96 : 160, ACS = 96;  // the frame tile: 2 DP (<= 80) columns of halves, 4 DP (<= 160) of TF32
 
   const int G = gridDim.x;
   const int nrounds = (ntiles + G - 1) / G;
@@ -137,9 +235,9 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
     }
   } else if (warp == kDecEpiWarps + 4) {
     // =================================== MMA ISSUER ===================================
-    const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
+    const uint32_t idesc = H16 ? make_idesc_f16(kTcRows, TN) : make_idesc_tf32(kTcRows, TN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
-    const int NSLAB = KP / 8;
+    const int NSLAB = H16 ? KP / 16 : KP / 8;  // K per MMA: 16 halves / 8 TF32 = 8 tensor-memory columns and 256 bytes of a W row group either way
     int n = 0, nu = 0;  // W stage uses; accumulator stage uses (only rounds with a tile)
     for (int r = 0; r < nrounds; r++) {
       const bool have = rows_of(r) > 0;
@@ -159,7 +257,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
           mbar_arrive_a(kfull + 8 * a);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint32_t xh = tb, xl = xh + 80;
+            const uint32_t xh = tb, xl = xh + (H16 ? (uint32_t)DP : 80u);
             const uint32_t wbase = Ws + (uint32_t)s * img_bytes;
             const uint64_t wh = make_smem_desc2(wbase, 128, P), wl = make_smem_desc2(wbase + (uint32_t)(TN / 8) * P, 128, P);
             const uint32_t d = tb + acc0 + (uint32_t)a * ACS;
@@ -169,7 +267,8 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
               const uint64_t b0 = (p == 2) ? wl : wh;
 #pragma unroll 10
               for (int k = 0; k < NSLAB; k++) {
-                tc_mma_tf32_ts(d, a0 + k * 8, b0 + (uint64_t)(k * 16), idesc, acc);
+                if (H16) tc_mma_f16_ts(d, a0 + k * 8, b0 + (uint64_t)(k * 16), idesc, acc);
+                else tc_mma_tf32_ts(d, a0 + k * 8, b0 + (uint64_t)(k * 16), idesc, acc);
                 acc = 1;
               }
             }
@@ -211,6 +310,35 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
       mbar_wait_a(xempty, (r & 1) ^ 1);  // the MMAs of the previous round have retired (the rows are already in registers)
       tc_fence_after();
       const uint32_t xa = xa0;
+      if (H16) {
+        // columns: [x' hi | x''^2 hi | x' lo | x''^2 lo], DP / 2 columns (two halves each) per block; 8 dimensions per store
+        const int hb = DP / 2;
+#pragma unroll
+        for (int j = 0; j < 10; j += 2) {
+          if (j < nq) {
+            const float v[8] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w, xv[j + 1].x, xv[j + 1].y, xv[j + 1].z, xv[j + 1].w};
+            uint32_t ah[4], al[4], qh[4], ql[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              unsigned short h0, l0, h1, l1;
+              const int d0 = 4 * j + 2 * e;
+              split_half(v[2 * e] * ssc[0][d0], h0, l0);
+              split_half(v[2 * e + 1] * ssc[0][d0 + 1], h1, l1);
+              ah[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              al[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              const float s0 = v[2 * e] * ssc[1][d0], s1 = v[2 * e + 1] * ssc[1][d0 + 1];
+              split_half(s0 * s0, h0, l0);
+              split_half(s1 * s1, h1, l1);
+              qh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              ql[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            tmem_st4(xa + 2 * j, ah);
+            tmem_st4(xa + hb + 2 * j, qh);
+            tmem_st4(xa + 2 * hb + 2 * j, al);
+            tmem_st4(xa + 3 * hb + 2 * j, ql);
+          }
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 10; j++) {
         if (j < nq) {
@@ -223,6 +351,7 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
           tmem_st4(xa + DP + 4 * j, vh);
           tmem_st4(xa + 80 + DP + 4 * j, vl);
         }
+      }
       }
       tmem_wait_st();
       tc_fence_before();

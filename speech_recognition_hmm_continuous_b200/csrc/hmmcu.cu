@@ -150,6 +150,7 @@ struct hmmcu_ctx {
     DevBuf images, kc, s0, ns;
     std::vector<int32_t> s0_h, ns_h;  // what the device tables hold
     int TN = 0, SCt = 0, nimg = 0;
+    DevBuf images16, scales16;  // half-precision images of k_emis_dec (decode set only)
     bool dirty = true;
   } tc_train, tc_dec, ws_train, ws_dec;
   int use_ws = 1;  // warp-specialised pipelined emission kernel (0 = the single-buffered k_emis_tc)
@@ -162,6 +163,7 @@ struct hmmcu_ctx {
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
   int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int fwd_f64 = 0;       // forward cell scorer with the chain in double (k_fwd_cells) instead of k_fwd_cells32
+  int dec_f16 = 1;       // k_emis_dec with half-precision operands (kind::f16 MMAs at twice the TF32 rate)
   int dec_budget_kb = 0; // log-emission budget of a decode batch in KiB (0 = 6 GiB or a third of the free memory); tests
   int dec_dbg = 0;       // experiments on k_emis_dec: 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no W copies (results are garbage)
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
@@ -373,7 +375,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->psi_ws, &ctx->path_d, &ctx->tiles_dec, &ctx->rank_in, &ctx->rank_out, &ctx->tc_train.images, &ctx->tc_train.kc, &ctx->tc_train.s0,
                     &ctx->tc_train.ns, &ctx->xabs_d, &ctx->tc_dec.images, &ctx->tc_dec.kc, &ctx->tc_dec.s0, &ctx->tc_dec.ns, &ctx->tc_tiles_train,
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
-                    &ctx->ws_dec.images, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
+                    &ctx->ws_dec.images, &ctx->ws_dec.images16, &ctx->ws_dec.scales16, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
                     &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles,
                     &ctx->res_order, &ctx->res_upos, &ctx->res_batches, &ctx->res_counter, &ctx->ustats};
   for (DevBuf *b : bufs) b->release();
@@ -469,6 +471,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
+  if (strcmp(key, "dec_f16") == 0) { ctx->dec_f16 = value; ctx->ws_dec.dirty = true; return HMMCU_OK; }
   if (strcmp(key, "dec_budget_kb") == 0) { ctx->dec_budget_kb = value; return HMMCU_OK; }
   if (strcmp(key, "dec_dbg") == 0) { ctx->dec_dbg = value; return HMMCU_OK; }
   if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
@@ -1076,6 +1079,13 @@ static bool ws_supported(const hmmcu_ctx *ctx) {
   return ws_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
 }
 
+// half-precision decode images: the padded feature row must be whole groups of 8 (K = 16 halves per MMA), DP <= 40, M <= 16
+static bool dec16_wanted(const hmmcu_ctx *ctx) {
+  // (kappa bounds the scaled operands by ~2 sqrt(kappa): far inside the half's range while the accuracy guard holds)
+  return ctx->dec_f16 && ctx->use_dec_emis && ctx->DP % 8 == 0 && ctx->DP <= 40 && ws_pad_m(ctx->M) <= 16 && ctx->ext_d.p != nullptr &&
+         ctx->kappa <= kTcKappaMax;
+}
+
 static int launch_pack_ws(hmmcu_ctx *ctx, hmmcu_ctx::TcSet &ts) {
   const int KP = 2 * ctx->DP;
   k_pack_w_ws<<<dim3((ts.TN * KP + 255) / 256, ts.nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
@@ -1121,6 +1131,18 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
   {
     int rc = launch_pack_ws(ctx, ts);
     if (rc) return rc;
+  }
+  if (mode == 1 && dec16_wanted(ctx)) {  // half-precision images for k_emis_dec: scales from the extremes the accuracy guard collected
+    CK(ts.images16.ensure(dec16_image_bytes(ts.TN, KP) * ts.nimg));
+    CK(ts.scales16.ensure(sizeof(float) * 4 * ctx->DP));
+    k_dec16_scales<<<1, 64, 0, ctx->st>>>(ctx->ext_d.as<unsigned long long>(), ctx->F > 0 ? ctx->xabs_d.as<unsigned int>() : nullptr, ctx->D, ctx->DP,
+                                         ts.scales16.as<float>());
+    LAUNCH_CHECK();
+    k_pack_w_dec16<<<dim3((ts.TN * KP + 255) / 256, ts.nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                              ctx->ctr.as<double>(), ts.scales16.as<float>(), ctx->M, ws_pad_m(ctx->M), ctx->D,
+                                                                              ctx->DP, ts.TN, ts.s0.as<int32_t>(), ts.ns.as<int32_t>(),
+                                                                              ts.images16.as<unsigned char>());
+    LAUNCH_CHECK();
   }
   t_end(ctx, "pack");
   ts.dirty = false;
@@ -1191,12 +1213,12 @@ static int launch_emis_tc(hmmcu_ctx *ctx, const TcTile *tiles_dev, int ntiles, f
 
 
 // decode emissions, frames resident in tensor memory, W images multicast over clusters of four CTAs (dec_kernels.cuh)
-template <int MP, int MR, int CL>
+template <int MP, int MR, int CL, bool H16>
 static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
   constexpr int kDecCluster = CL;
   hmmcu_ctx::TcSet &ts = ctx->ws_dec;
-  const size_t smem = dec_emis_smem_bytes(ts.TN, 2 * ctx->DP);
-  auto kern = k_emis_dec<MP, MR, CL>;
+  const size_t smem = dec_emis_smem_bytes(ts.TN, 2 * ctx->DP, H16);
+  auto kern = k_emis_dec<MP, MR, CL, H16>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -1222,18 +1244,21 @@ static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *log
   if (ctx->dec_grid < 0) return HMMCU_EINVAL;
   const int want = ((ntiles + kDecCluster - 1) / kDecCluster) * kDecCluster;
   cfg.gridDim = dim3(std::min(ctx->dec_grid, want));
-  const float *x32 = ctx->x32.as<float>(), *img = ts.images.as<float>();
+  const float *x32 = ctx->x32.as<float>(), *img = H16 ? ts.images16.as<float>() : ts.images.as<float>(), *scales = ts.scales16.as<float>();
   int nimg = ts.nimg, DP = ctx->DP, TN = ts.TN, S_total = ctx->V * ctx->N, SCt = ts.SCt;
   int dbg = ctx->dec_dbg;
-  CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt, dbg));
+  CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt, dbg, scales));
   ctx->launches++;
   ctx->last_tc = true;
   return HMMCU_OK;
 }
 template <int MP, int MR>
 static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
-  return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2>(ctx, ntiles, nframes, logb, fbase, ldb)
-                               : launch_emis_dec_c<MP, MR, 4>(ctx, ntiles, nframes, logb, fbase, ldb);
+  if (dec16_wanted(ctx) && ctx->ws_dec.images16.p)
+    return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2, true>(ctx, ntiles, nframes, logb, fbase, ldb)
+                                 : launch_emis_dec_c<MP, MR, 4, true>(ctx, ntiles, nframes, logb, fbase, ldb);
+  return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2, false>(ctx, ntiles, nframes, logb, fbase, ldb)
+                               : launch_emis_dec_c<MP, MR, 4, false>(ctx, ntiles, nframes, logb, fbase, ldb);
 }
 static int launch_emis_dec(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
   switch (ws_pad_m(ctx->M)) {

@@ -801,6 +801,35 @@ def test_decode_kernel_variants_match_oracle(N, M, D):
     c.close()
 
 
+@pytest.mark.parametrize("N,M,spread", [(5, 3, 0.0), (5, 16, 0.0), (3, 8, 2.0), (5, 3, 3.0)])
+def test_half_precision_decode_operands(N, M, spread):
+    """k_emis_dec with half-precision operands (kind::f16 MMAs, per-dimension power-of-two scaling; the default) against
+    the 3xTF32 form of the same kernel and against the oracle (calc_gaus / calc_symbol_probab, R-FS:860-947, through the
+    forward score R-FS:739-836).  `spread` stretches every feature dimension by its own factor 10^U(-spread, spread)
+    (models transformed with it), so that the dimensions' magnitudes differ by up to six decades: the scaling has to bring
+    each of them into the half's range on its own."""
+    ms, x, off, labels = _synth(6, N, M, 12, seed=4100 + N * M, tmin=40, tmax=90)
+    if spread > 0:
+        g = 10.0 ** np.random.default_rng(17).uniform(-spread, spread, size=x.shape[1])
+        x = x * g
+        ms = api.ModelSet(ms.A, ms.c, ms.mu * g, ms.iv / g ** 2, ms.det * np.prod(g ** 2))
+    want = np.array([[o.forward_score(_oracle_model(ms, v), x[off[u]:off[u + 1]]) for v in range(ms.V)] for u in range(len(labels))])
+    got = {}
+    for f16 in (1, 0):
+        c = api.Context(0)
+        c.set_option("dec_f16", f16)
+        c.set_features(x, off)
+        c.set_models(ms)
+        got[f16] = c.forward_scores()
+        assert c.kernel_ms("dec_grid") > 0 and c.kernel_ms("tc_active") == 1
+        lab, _ = c.rank(got[f16])
+        assert (lab == labels).all()
+        c.close()
+        assert np.allclose(got[f16], want, rtol=RTOL, atol=0)
+    e16, e32 = np.abs(got[1] / want - 1).max(), np.abs(got[0] / want - 1).max()
+    assert e16 < 2e-6 and e16 < 4 * e32 + 1e-7, (e16, e32)     # as accurate as the TF32 split, not merely inside the bar
+
+
 @pytest.mark.parametrize("M", [3, 5, 4])
 def test_decode_in_many_batches_equals_one_batch(M):
     """hmmcu_forward_scores / hmmcu_viterbi_scores work in utterance batches (R-FS:283-390 is one loop over the test list);
