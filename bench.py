@@ -646,6 +646,20 @@ def run_c3(t, args):
     return out
 
 
+def _decode_emis_roofline(c, t, flops, em_ms, name):
+    """Emission contraction of a decode leg against the tensor-pipe rate of its operand type: the library TF32 GEMM
+    measured in this run for the 3xTF32 kernels, MEASURED_PEAKS.json's sustained bf16 / fp16 rate for the half-precision
+    form of k_emis_dec (three kind::f16 MMAs per algorithmic one)."""
+    dec = c.kernel_ms("dec_grid") > 0
+    f16 = dec and c.kernel_ms("dec_f16_active") > 0
+    peak = (t["pk"]["bf16_sustained"] or t["pk"]["bf16_tflops"]) if f16 else t["tf32_peak"]
+    ach = flops / (em_ms * 1e-3) / 1e12
+    return {"kernel": ("k_emis_dec<f16>" if f16 else "k_emis_dec") if dec else "k_emis_ws<decode>", "bound": "tensor", "achieved": ach, "peak": peak,
+            "peak_what": "fp16 / bf16 dense, sustained (MEASURED_PEAKS.json)" if f16 else "TF32 dense, library GEMM measured in this run",
+            "unit": "TFLOP/s", "frac": ach / peak, ("issued_3xf16" if f16 else "issued_3xtf32"): {"achieved": 3 * ach, "frac": 3 * ach / peak},
+            "algorithmic_flops": flops, "traffic": t["traffic"].get(name, {}).get("emis")}
+
+
 def _decode_config(t, args, name, desc, V, N, M, U, seed):
     """Forward and Viterbi scores of the rank's shard of U utterances against all V models (R-FS:341-369)."""
     torch, dist, api, synth, dev, world, rank = t["torch"], t["dist"], t["api"], t["synth"], t["dev"], t["world"], t["rank"]
@@ -686,10 +700,7 @@ def _decode_config(t, args, name, desc, V, N, M, U, seed):
             "frames_per_s": Ftot / (dev_ms * 1e-3), "frame_model_pairs_per_s": Ftot * V / (dev_ms * 1e-3),
             "frames_per_s_through_api": Ftot / (wall_max * 1e-3),
             "rooflines": {
-                "emis": {"kernel": "k_emis_dec" if c.kernel_ms("dec_grid") > 0 else "k_emis_ws<decode>", "bound": "tensor", "achieved": flops / (em_ms * 1e-3) / 1e12, "peak": t["tf32_peak"],
-                         "unit": "TFLOP/s", "frac": flops / (em_ms * 1e-3) / 1e12 / t["tf32_peak"],
-                         "issued_3xtf32": {"achieved": 3 * flops / (em_ms * 1e-3) / 1e12, "frac": 3 * flops / (em_ms * 1e-3) / 1e12 / t["tf32_peak"]},
-                         "algorithmic_flops": flops, "traffic": t["traffic"].get(name, {}).get("emis")},
+                "emis": _decode_emis_roofline(c, t, flops, em_ms, name),
                 "score": {"kernel": "k_fwd_cells32" if leg == "forward" else "k_vit_cells", "bound": "hbm", "achieved": sbytes / (sc_ms * 1e-3) / 1e9,
                           "peak": t["pk"]["hbm_gbs"], "unit": "GB/s", "frac": sbytes / (sc_ms * 1e-3) / 1e9 / t["pk"]["hbm_gbs"],
                           "algorithmic_bytes": sbytes, "traffic": t["traffic"].get(name, {}).get("score" if leg == "forward" else "viterbi")}},

@@ -401,25 +401,24 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
 #pragma unroll
             for (int g = 0; g < SPC; g++) {
               constexpr int MU = MR ? MR : MP;  // columns MU .. MP-1 of a state are pad (density 0)
-              float m = val[g * MP];
-#pragma unroll
-              for (int jj = 1; jj < MU; jj++) m = fmaxf(m, val[g * MP + jj]);
-              const float ms = (m > kNegInf) ? m : 0.f;
-              float sm_;
               if (MU == 1) {
-                sm_ = 1.f;
-              } else if (MU == 2) {
-                sm_ = 1.f + ex2_approx(fminf(val[g * MP], val[g * MP + 1]) - ms);
-              } else if (MU == 3) {  // the largest term is 2^0: order the values instead of sending it through the SFU
-                const float aa = val[g * MP], bb = val[g * MP + 1], c3 = val[g * MP + 2];
-                const float lo = fminf(fminf(aa, bb), c3), mid = fmaxf(fminf(aa, bb), fminf(fmaxf(aa, bb), c3));
-                sm_ = 1.f + (ex2_approx(mid - ms) + ex2_approx(lo - ms));
+                lbv[g] = val[g * MP] * 0.6931471805599453f;  // -inf stays -inf
               } else {
-                sm_ = 0.f;
+                // log-sum-exp with ONE guard instruction: the reference point is max(m, -1e30), finite, so a state whose
+                // mixtures are all dead (-inf) gives sum = 0 and lg2(0) = -inf on its own -- no select before, none after
+                // (k_emis_ws orders the values to save an ex2; here the epilogue is bound by instruction issue, not by the
+                // transcendental unit: 16 instead of 23 instructions per state of three mixtures)
+                float m = val[g * MP];
 #pragma unroll
-                for (int jj = 0; jj < MU; jj++) sm_ += ex2_approx(val[g * MP + jj] - ms);
+                for (int jj = 1; jj < MU; jj++) m = fmaxf(m, val[g * MP + jj]);
+                const float ms = fmaxf(m, -1e30f);
+                float sm_ = ex2_approx(val[g * MP] - ms);
+#pragma unroll
+                for (int jj = 1; jj < MU; jj++) sm_ += ex2_approx(val[g * MP + jj] - ms);
+                float lg;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sm_));
+                lbv[g] = (ms + lg) * 0.6931471805599453f;
               }
-              lbv[g] = (m > kNegInf) ? (MU == 1 ? ms : ms + __log2f(sm_)) * 0.6931471805599453f : kNegInf;
             }
             float *dst = lrow + c * SPC * 8;
             if (live) {

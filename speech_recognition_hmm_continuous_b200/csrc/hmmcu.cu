@@ -166,6 +166,7 @@ struct hmmcu_ctx {
   int dec_f16 = 1;       // k_emis_dec with half-precision operands (kind::f16 MMAs at twice the TF32 rate)
   int dec_budget_kb = 0; // log-emission budget of a decode batch in KiB (0 = 6 GiB or a third of the free memory); tests
   int dec_dbg = 0;       // experiments on k_emis_dec: 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no W copies (results are garbage)
+  bool last_dec16 = false;  // the last k_emis_dec launch used half-precision operands
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
@@ -420,6 +421,7 @@ void hmmcu_enable_timing(hmmcu_ctx *ctx, int on) { ctx->timing = on != 0; ctx->c
 double hmmcu_last_kernel_ms(const hmmcu_ctx *ctx, const char *name) {
   if (strcmp(name, "kappa") == 0) return ctx->kappa;            // accuracy-guard value of the current pack
   if (strcmp(name, "tc_active") == 0) return ctx->last_tc ? 1.0 : 0.0;
+  if (strcmp(name, "dec_f16_active") == 0) return ctx->last_dec16 ? 1.0 : 0.0;
   if (strcmp(name, "dec_grid") == 0) return (double)ctx->dec_grid;                // CTAs of the last k_emis_dec launch configuration
   {  // "<name>_total": the sum over the batches of the last hmmcu_forward_scores / hmmcu_viterbi_scores call
     const size_t ln = strlen(name);
@@ -1248,6 +1250,7 @@ static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *log
   int nimg = ts.nimg, DP = ctx->DP, TN = ts.TN, S_total = ctx->V * ctx->N, SCt = ts.SCt;
   int dbg = ctx->dec_dbg;
   CK(cudaLaunchKernelEx(&cfg, kern, ntiles, nframes, nimg, x32, img, DP, TN, logb, fbase, ldb, S_total, SCt, dbg, scales));
+  ctx->last_dec16 = H16;
   ctx->launches++;
   ctx->last_tc = true;
   return HMMCU_OK;
