@@ -65,7 +65,8 @@ void hmmcu_host_free(void *p);
  * "mstep_fork": 1 (default) = the accuracy-guard scan and one of the two model packers of hmmcu_mstep run on side streams;
  * "dec_emis": 1 (default) = decode emissions of models with M <= 16 through k_emis_dec (frame tile resident in tensor memory, W
  * images multicast over a cluster, interleaved log-emission layout), 0 = k_emis_ws; "dec_cluster": 2 (default) or 4 CTAs per
- * cluster; "fwd_f64": 1 = the forward cell scorer with a double-precision linear chain instead of the single-precision
+ * cluster; "dec_f16": 1 (default) = k_emis_dec with half-precision operands (per-dimension power-of-two scaling, as accurate as
+ * the 3xTF32 split; used while the accuracy guard holds and the padded feature row is a multiple of 8), 0 = 3xTF32; "fwd_f64": 1 = the forward cell scorer with a double-precision linear chain instead of the single-precision
  * log-domain one; "dec_budget_kb": log-emission budget of one decode batch in KiB (0 = 6 GiB or a third of the free memory);
  * "dec_dbg": experiment switches of k_emis_dec (results are garbage: 1 no epilogue arithmetic, 2 no MMAs, 4 no W copies). */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
