@@ -651,10 +651,10 @@ def _decode_emis_roofline(c, t, flops, em_ms, name):
     measured in this run for the 3xTF32 kernels, MEASURED_PEAKS.json's sustained bf16 / fp16 rate for the half-precision
     form of k_emis_dec (three kind::f16 MMAs per algorithmic one)."""
     dec = c.kernel_ms("dec_grid") > 0
-    f16 = dec and c.kernel_ms("dec_f16_active") > 0
+    f16 = c.kernel_ms("dec_f16_active") > 0
     peak = (t["pk"]["bf16_sustained"] or t["pk"]["bf16_tflops"]) if f16 else t["tf32_peak"]
     ach = flops / (em_ms * 1e-3) / 1e12
-    return {"kernel": ("k_emis_dec<f16>" if f16 else "k_emis_dec") if dec else "k_emis_ws<decode>", "bound": "tensor", "achieved": ach, "peak": peak,
+    return {"kernel": ("k_emis_dec" if dec else "k_emis_ws<decode>") + ("<f16>" if f16 else ""), "bound": "tensor", "achieved": ach, "peak": peak,
             "peak_what": "fp16 / bf16 dense, sustained (MEASURED_PEAKS.json)" if f16 else "TF32 dense, library GEMM measured in this run",
             "unit": "TFLOP/s", "frac": ach / peak, ("issued_3xf16" if f16 else "issued_3xtf32"): {"achieved": 3 * ach, "frac": 3 * ach / peak},
             "algorithmic_flops": flops, "traffic": t["traffic"].get(name, {}).get("emis")}

@@ -23,7 +23,6 @@
 // waited for it (period = (MMA + epilogue) / 2; measured 54 % pipe activity, the same as k_emis_ws).  W image layout and
 // the MMA descriptors are k_emis_ws's.
 #pragma once
-#include <cuda_fp16.h>
 #include "ws_kernels.cuh"
 
 namespace hmmk {
@@ -72,92 +71,6 @@ __device__ __forceinline__ void bulk_copy_multicast(uint32_t dst_smem, const voi
 // arrive (once) on the barrier at this offset in every CTA of `mask` when all MMAs issued so far by this thread have retired
 __device__ __forceinline__ void tc_commit_multicast(uint32_t mbar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar), "h"(mask) : "memory");
-}
-
-// ---- half-precision operands (H16): the same contraction with kind::f16 MMAs, which run at twice the TF32 rate ----------
-// A TF32 operand keeps 11 significant bits, as a half does; hi + lo of a half split carry the same 22 bits as the 3xTF32
-// split -- provided the halves stay inside the half's narrow exponent range.  Every dimension is therefore rescaled by powers
-// of two (exact): x' = x / s1_d against W' = mu iv s1_d, and x''^2 = (x / s2_d)^2 against -iv s2_d^2 / 2, with s1_d, s2_d
-// chosen so that the two factors of a term have the same magnitude (k_dec16_scales: both at most sqrt(kappa), the accuracy
-// guard's bound, so nothing overflows; a lo part below the normal range costs at most 3e-8 times the other factor).
-// W image: [hi: (TN/8) P16][lo: (TN/8) P16][kc2: TN floats], P16 = (KP/8) 128: K-major, 16-byte chunks of 8 halves.
-__host__ __device__ inline size_t dec16_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 8) * 128 + (size_t)TN * 4; }
-
-// sc[0..DP) = 1/s1, [DP..2DP) = 1/s2, [2DP..3DP) = s1, [3DP..4DP) = s2^2   (powers of two; 1 for the pad dimensions)
-__global__ void k_dec16_scales(const unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs, int D, int DP, float *__restrict__ sc) {
-  const int d = threadIdx.x;
-  if (d >= DP) return;
-  float s1 = 1.f, s2 = 1.f;
-  bool dead = false;  // no frame leaves the centre in this dimension: both of its terms are exactly 0 (the constant kc holds the rest)
-  if (d < D) {
-    const double ivm = __longlong_as_double((long long)ext[d]), mum = __longlong_as_double((long long)ext[DP + d]);
-    const double r = xabs ? (double)__uint_as_float(xabs[d]) : mum;
-    const double wl = mum * ivm;                                  // largest |mu iv|
-    dead = !(r > 0.0);
-    if (r > 0.0 && wl > 0.0 && wl < INFINITY) s1 = exp2f(rintf(0.5f * log2f((float)(r / wl))));
-    if (r > 0.0 && ivm > 0.0 && ivm < INFINITY) s2 = exp2f(rintf(0.25f * log2f((float)(2.0 * r * r / ivm))));
-  }
-  sc[d] = dead ? 0.f : 1.f / s1;
-  sc[DP + d] = dead ? 0.f : 1.f / s2;
-  sc[2 * DP + d] = dead ? 0.f : s1;
-  sc[3 * DP + d] = dead ? 0.f : s2 * s2;
-}
-
-__device__ __forceinline__ void split_half(float v, unsigned short &hi, unsigned short &lo) {
-  const __half h = __float2half_rn(v);
-  hi = __half_as_ushort(h);
-  lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
-}
-
-// as k_pack_w_ws, for the half-precision images (column layout of the states, pad columns and kc2 are the same)
-__global__ void k_pack_w_dec16(const double *__restrict__ mu, const double *__restrict__ iv, const float *__restrict__ kc2all,
-                               const double *__restrict__ ctr, const float *__restrict__ sc, int M, int MP, int D, int DP, int TN,
-                               const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
-                               unsigned char *__restrict__ images) {
-  const int img = blockIdx.y;
-  const int KP = 2 * DP;
-  const uint32_t P = (uint32_t)(KP / 8) * 128;
-  unsigned char *hi = images + (size_t)img * dec16_image_bytes(TN, KP);
-  unsigned char *lo = hi + (size_t)(TN / 8) * P;
-  float *kc2 = reinterpret_cast<float *>(lo + (size_t)(TN / 8) * P);
-  const int64_t s0g = img_state0[img];
-  const int nst = img_nstates[img];
-  auto gauss_of = [&](int n) -> int64_t {
-    const int spc = 16 / MP, c = n >> 4, w = n & 15;
-    if (w >= spc * MP) return -1;
-    const int st = c * spc + w / MP, m = w % MP;
-    return (st < nst && m < M) ? (s0g + st) * M + m : -1;
-  };
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TN * KP; idx += gridDim.x * blockDim.x) {
-    const int n = idx / KP, k = idx - n * KP;
-    const int part = k / DP, d = k - part * DP;
-    const int64_t g = gauss_of(n);
-    float val = 0.f;
-    if (g >= 0 && d < D) {
-      const double m = mu[g * D + d] - ctr[d], w = iv[g * D + d];
-      val = (float)(part == 0 ? m * w * (double)sc[2 * DP + d] : -0.5 * w * (double)sc[3 * DP + d]);
-    }
-    unsigned short h, l;
-    split_half(val, h, l);
-    const size_t o = (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2 + (size_t)(k >> 3) * 128 + (size_t)(n >> 3) * P;
-    *reinterpret_cast<unsigned short *>(hi + o) = h;
-    *reinterpret_cast<unsigned short *>(lo + o) = l;
-    if (k == 0) kc2[n] = (g >= 0) ? kc2all[g] : kNegInf;
-  }
-}
-
-__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
-  // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 
 // MP: padded mixtures per state (1, 2, 3, 4, 5, 8, 16); MR: real mixtures of a state (0 = all MP); CL: CTAs per cluster;
@@ -320,17 +233,10 @@ k_emis_dec(int ntiles, int nframes, int nimg, const float *__restrict__ x32, con
             uint32_t ah[4], al[4], qh[4], ql[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              unsigned short h0, l0, h1, l1;
               const int d0 = 4 * j + 2 * e;
-              split_half(v[2 * e] * ssc[0][d0], h0, l0);
-              split_half(v[2 * e + 1] * ssc[0][d0 + 1], h1, l1);
-              ah[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              al[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              split_half2(v[2 * e] * ssc[0][d0], v[2 * e + 1] * ssc[0][d0 + 1], ah[e], al[e]);
               const float s0 = v[2 * e] * ssc[1][d0], s1 = v[2 * e + 1] * ssc[1][d0 + 1];
-              split_half(s0 * s0, h0, l0);
-              split_half(s1 * s1, h1, l1);
-              qh[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              ql[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+              split_half2(s0 * s0, s1 * s1, qh[e], ql[e]);
             }
             tmem_st4(xa + 2 * j, ah);
             tmem_st4(xa + hb + 2 * j, qh);

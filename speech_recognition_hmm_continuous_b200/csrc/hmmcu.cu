@@ -163,10 +163,10 @@ struct hmmcu_ctx {
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
   int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int fwd_f64 = 0;       // forward cell scorer with the chain in double (k_fwd_cells) instead of k_fwd_cells32
-  int dec_f16 = 1;       // k_emis_dec with half-precision operands (kind::f16 MMAs at twice the TF32 rate)
+  int dec_f16 = 1;       // decode emission kernels with half-precision operands (kind::f16 MMAs at twice the TF32 rate)
   int dec_budget_kb = 0; // log-emission budget of a decode batch in KiB (0 = 6 GiB or a third of the free memory); tests
   int dec_dbg = 0;       // experiments on k_emis_dec: 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no W copies (results are garbage)
-  bool last_dec16 = false;  // the last k_emis_dec launch used half-precision operands
+  bool last_dec16 = false;  // the last decode emission launch (k_emis_dec / k_emis_ws<false>) used half-precision operands
   int dec_grid = 0;      // CTAs of k_emis_dec (whole clusters that fit the device at once), 0 = not asked yet
   int use_res_fb = 1;  // shared-memory-resident forward-backward (k_fb_res) whenever the utterances fit and A is banded
   DevBuf res_order, res_upos, res_batches, res_counter, ustats;
@@ -1082,11 +1082,15 @@ static bool ws_supported(const hmmcu_ctx *ctx) {
 }
 
 // half-precision decode images: the padded feature row must be whole groups of 8 (K = 16 halves per MMA), DP <= 40, M <= 16
-static bool dec16_wanted(const hmmcu_ctx *ctx) {
+static bool f16_possible(const hmmcu_ctx *ctx) {
   // (kappa bounds the scaled operands by ~2 sqrt(kappa): far inside the half's range while the accuracy guard holds)
-  return ctx->dec_f16 && ctx->use_dec_emis && ctx->DP % 8 == 0 && ctx->DP <= 40 && ws_pad_m(ctx->M) <= 16 && ctx->ext_d.p != nullptr &&
-         ctx->kappa <= kTcKappaMax;
+  return ctx->DP % 8 == 0 && ctx->DP <= 40 && ctx->ext_d.p != nullptr && ctx->kappa <= kTcKappaMax;
 }
+static bool dec16_wanted(const hmmcu_ctx *ctx) { return ctx->dec_f16 && f16_possible(ctx); }      // decode set: k_emis_dec, k_emis_ws<false>
+// The training emission kernel keeps its 3xTF32 operands: it is bound by the instruction issue of its loaders and its
+// epilogue, not by the MMAs (measured with half-precision operands: no gain), and its images are re-packed inside the
+// M-step's captured graph.
+static bool train16_wanted(const hmmcu_ctx *) { return false; }
 
 static int launch_pack_ws(hmmcu_ctx *ctx, hmmcu_ctx::TcSet &ts) {
   const int KP = 2 * ctx->DP;
@@ -1134,7 +1138,7 @@ static int ensure_ws_images(hmmcu_ctx *ctx, int mode) {
     int rc = launch_pack_ws(ctx, ts);
     if (rc) return rc;
   }
-  if (mode == 1 && dec16_wanted(ctx)) {  // half-precision images for k_emis_dec: scales from the extremes the accuracy guard collected
+  if (mode == 1 ? dec16_wanted(ctx) : train16_wanted(ctx)) {  // half-precision images: scales from the extremes the accuracy guard collected
     CK(ts.images16.ensure(dec16_image_bytes(ts.TN, KP) * ts.nimg));
     CK(ts.scales16.ensure(sizeof(float) * 4 * ctx->DP));
     k_dec16_scales<<<1, 64, 0, ctx->st>>>(ctx->ext_d.as<unsigned long long>(), ctx->F > 0 ? ctx->xabs_d.as<unsigned int>() : nullptr, ctx->D, ctx->DP,
@@ -1166,20 +1170,23 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
     CK(ctx->acc_dbg.ensure(sizeof(float) * 3 * 16384));
     CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
   }
-#define WS_LAUNCH2(MPT, DBGT) WS_LAUNCH3(MPT, DBGT, 0)
-#define WS_LAUNCH3(MPT, DBGT, MRT)                                                                                                 \
+  const bool h16 = (TRAIN ? train16_wanted(ctx) : dec16_wanted(ctx)) && ts.images16.p != nullptr && !(ctx->debug_acc & 2);
+  if (!TRAIN) ctx->last_dec16 = h16;
+#define WS_LAUNCH4(MPT, DBGT, MRT, HT)                                                                                             \
   do {                                                                                                                             \
-    CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT, DBGT, MRT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-    k_emis_ws<TRAIN, MPT, DBGT, MRT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,         \
+    CK(cudaFuncSetAttribute(k_emis_ws<TRAIN, MPT, DBGT, MRT, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    k_emis_ws<TRAIN, MPT, DBGT, MRT, HT><<<grid, kWsThreads, smem, ctx->st>>>(units_dev, (int)nunits, ntiles_dec, nframes_dec,     \
                                                                      ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),         \
-                                                                     ts.images.as<float>(), ctx->N, MPd, ctx->DP, ts.TN, logb,     \
-                                                                     fbase, ldb, ctx->V * ctx->N, ts.SCt,                          \
-                                                                     DBGT ? (long long *)ctx->acc_dbg.p : nullptr);                \
+                                                                     HT ? ts.images16.as<float>() : ts.images.as<float>(), ctx->N, \
+                                                                     MPd, ctx->DP, ts.TN, logb, fbase, ldb, ctx->V * ctx->N,       \
+                                                                     ts.SCt, DBGT ? (long long *)ctx->acc_dbg.p : nullptr,         \
+                                                                     ts.scales16.as<float>());                                     \
   } while (0)
 #define WS_LAUNCH(MPT)                                         \
   do {                                                         \
-    if (ctx->debug_acc & 2) WS_LAUNCH2(MPT, true);             \
-    else WS_LAUNCH2(MPT, false);                               \
+    if (ctx->debug_acc & 2) WS_LAUNCH4(MPT, true, 0, false);   \
+    else if (h16) WS_LAUNCH4(MPT, false, 0, true);             \
+    else WS_LAUNCH4(MPT, false, 0, false);                     \
   } while (0)
   switch (MPd) {
     case 1: WS_LAUNCH(1); break;
@@ -1191,8 +1198,7 @@ static int launch_emis_ws(hmmcu_ctx *ctx, const TcTile *units_dev, int64_t nunit
     case 16: WS_LAUNCH(16); break;
     default: WS_LAUNCH(0); break;
   }
-#undef WS_LAUNCH2
-#undef WS_LAUNCH3
+#undef WS_LAUNCH4
 #undef WS_LAUNCH
   LAUNCH_CHECK();
   return HMMCU_OK;
@@ -1257,7 +1263,7 @@ static int launch_emis_dec_c(hmmcu_ctx *ctx, int ntiles, int nframes, float *log
 }
 template <int MP, int MR>
 static int launch_emis_dec_t(hmmcu_ctx *ctx, int ntiles, int nframes, float *logb, int64_t fbase, int64_t ldb) {
-  if (dec16_wanted(ctx) && ctx->ws_dec.images16.p)
+  if (dec16_wanted(ctx) && ws_pad_m(ctx->M) <= 16 && ctx->ws_dec.images16.p)
     return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2, true>(ctx, ntiles, nframes, logb, fbase, ldb)
                                  : launch_emis_dec_c<MP, MR, 4, true>(ctx, ntiles, nframes, logb, fbase, ldb);
   return ctx->dec_cluster == 2 ? launch_emis_dec_c<MP, MR, 2, false>(ctx, ntiles, nframes, logb, fbase, ldb)

@@ -40,6 +40,7 @@
 //               accumulator stage a at 320 + 96 a (TN <= 96); an image of one wide state (96 < TN <= 176) has a
 //               single operand stage and its two accumulator stages at 160 + TN a.
 #pragma once
+#include <cuda_fp16.h>
 #include "tc_kernels.cuh"
 
 namespace hmmk {
@@ -199,25 +200,129 @@ __global__ void k_pack_w_ws(const double *__restrict__ mu, const double *__restr
   }
 }
 
+// ---- half-precision operands (H16) of the emission kernels: the same contraction with kind::f16 MMAs (twice the TF32 rate) ----
+// A TF32 operand keeps 11 significant bits, as a half does; hi + lo of a half split carry the same 22 bits as the 3xTF32
+// split -- provided the halves stay inside the half's narrow exponent range.  Every dimension is therefore rescaled by powers
+// of two (exact): x' = x / s1_d against W' = mu iv s1_d, and x''^2 = (x / s2_d)^2 against -iv s2_d^2 / 2, with s1_d, s2_d
+// chosen so that the two factors of a term have the same magnitude (k_dec16_scales: both at most sqrt(kappa), the accuracy
+// guard's bound, so nothing overflows; a lo part below the normal range costs at most 3e-8 times the other factor).
+// W image: [hi: (TN/8) P16][lo: (TN/8) P16][kc2: TN floats], P16 = (KP/8) 128: K-major, 16-byte chunks of 8 halves.
+__host__ __device__ inline size_t dec16_image_bytes(int TN, int KP) { return (size_t)2 * (TN / 8) * (KP / 8) * 128 + (size_t)TN * 4; }
+
+// sc[0..DP) = 1/s1, [DP..2DP) = 1/s2, [2DP..3DP) = s1, [3DP..4DP) = s2^2   (powers of two; 1 for the pad dimensions)
+__global__ void k_dec16_scales(const unsigned long long *__restrict__ ext, const unsigned int *__restrict__ xabs, int D, int DP, float *__restrict__ sc) {
+  const int d = threadIdx.x;
+  if (d >= DP) return;
+  float s1 = 1.f, s2 = 1.f;
+  bool dead = false;  // no frame leaves the centre in this dimension: both of its terms are exactly 0 (the constant kc holds the rest)
+  if (d < D) {
+    const double ivm = __longlong_as_double((long long)ext[d]), mum = __longlong_as_double((long long)ext[DP + d]);
+    const double r = xabs ? (double)__uint_as_float(xabs[d]) : mum;
+    const double wl = mum * ivm;                                  // largest |mu iv|
+    dead = !(r > 0.0);
+    if (r > 0.0 && wl > 0.0 && wl < INFINITY) s1 = exp2f(rintf(0.5f * log2f((float)(r / wl))));
+    if (r > 0.0 && ivm > 0.0 && ivm < INFINITY) s2 = exp2f(rintf(0.25f * log2f((float)(2.0 * r * r / ivm))));
+  }
+  sc[d] = dead ? 0.f : 1.f / s1;
+  sc[DP + d] = dead ? 0.f : 1.f / s2;
+  sc[2 * DP + d] = dead ? 0.f : s1;
+  sc[3 * DP + d] = dead ? 0.f : s2 * s2;
+}
+
+// two values at once: one packed conversion each way (the scalar conversions run on the quarter-rate unit, and an emission
+// kernel that expands its frame tile per unit -- k_emis_ws -- was bound by them: C5 decode 21.0 -> 27.1 ms)
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(a, b);  // low half = a, high half = b
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+__device__ __forceinline__ void split_half(float v, unsigned short &hi, unsigned short &lo) {
+  const __half h = __float2half_rn(v);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+}
+
+// as k_pack_w_ws, for the half-precision images (column layout of the states, pad columns and kc2 are the same)
+__global__ void k_pack_w_dec16(const double *__restrict__ mu, const double *__restrict__ iv, const float *__restrict__ kc2all,
+                               const double *__restrict__ ctr, const float *__restrict__ sc, int M, int MP, int D, int DP, int TN,
+                               const int32_t *__restrict__ img_state0, const int32_t *__restrict__ img_nstates,
+                               unsigned char *__restrict__ images) {
+  const int img = blockIdx.y;
+  const int KP = 2 * DP;
+  const uint32_t P = (uint32_t)(KP / 8) * 128;
+  unsigned char *hi = images + (size_t)img * dec16_image_bytes(TN, KP);
+  unsigned char *lo = hi + (size_t)(TN / 8) * P;
+  float *kc2 = reinterpret_cast<float *>(lo + (size_t)(TN / 8) * P);
+  const int64_t s0g = img_state0[img];
+  const int nst = img_nstates[img];
+  auto gauss_of = [&](int n) -> int64_t {
+    int st, m;
+    if (MP > 16) { st = n / MP; m = n - st * MP; }
+    else {
+      const int spc = 16 / MP, c = n >> 4, w = n & 15;
+      if (w >= spc * MP) return -1;
+      st = c * spc + w / MP; m = w % MP;
+    }
+    return (st < nst && m < M) ? (s0g + st) * M + m : -1;
+  };
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TN * KP; idx += gridDim.x * blockDim.x) {
+    const int n = idx / KP, k = idx - n * KP;
+    const int part = k / DP, d = k - part * DP;
+    const int64_t g = gauss_of(n);
+    float val = 0.f;
+    if (g >= 0 && d < D) {
+      const double m = mu[g * D + d] - ctr[d], w = iv[g * D + d];
+      val = (float)(part == 0 ? m * w * (double)sc[2 * DP + d] : -0.5 * w * (double)sc[3 * DP + d]);
+    }
+    unsigned short h, l;
+    split_half(val, h, l);
+    const size_t o = (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2 + (size_t)(k >> 3) * 128 + (size_t)(n >> 3) * P;
+    *reinterpret_cast<unsigned short *>(hi + o) = h;
+    *reinterpret_cast<unsigned short *>(lo + o) = l;
+    if (k == 0) kc2[n] = (g >= 0) ? kc2all[g] : kNegInf;
+  }
+}
+
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  // c_format F32 (1) @4, a_format F16 (0) @7, b_format F16 (0) @10, K-major A and B, N>>3 @17, M>>4 @24
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // units == nullptr: decode, unit u = (image u / ntiles_dec, frames [128 (u % ntiles_dec), ...) of the batch, nframes_dec in all)
 // MP: padded mixtures per state when <= 16 (1, 2, 4, 8, 16); 0 = a multiple of 16 given at run time (M)
 // Warps: 0-7 epilogue (lane quarter w & 3; column groups of parity w >> 2), 8-15 loaders (lane quarter w & 3;
 // chunks 0-2 / 3-4 of the doubled row), 16 MMA issuer.
 // MR: mixtures of a state that are real (MR <= MP; the others are pad columns the log-sum-exp may skip), 0 = all MP
-template <bool TRAIN, int MP, bool DBG, int MR = 0>
+// H16: half-precision operands (images of k_pack_w_dec16, `scales` of k_dec16_scales; DP a multiple of 8)
+template <bool TRAIN, int MP, bool DBG, int MR = 0, bool H16 = false>
 __global__ void __launch_bounds__(kWsThreads, 1)
 k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nframes_dec, const int32_t *__restrict__ frame_ids,
           const float *__restrict__ x32, const float *__restrict__ images, int N, int M, int DP, int TN, float *__restrict__ logb,
-          int64_t fbase, int64_t ldb, int S_total, int SCt, long long *__restrict__ tdbg) {
+          int64_t fbase, int64_t ldb, int S_total, int SCt, long long *__restrict__ tdbg, const float *__restrict__ scales = nullptr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const int KP = 2 * DP, NSLAB = KP / 8;
+  const int KP = 2 * DP, NSLAB = H16 ? KP / 16 : KP / 8;  // K per MMA: 16 halves / 8 TF32 (8 tensor-memory columns, 256 bytes of a W row group)
   // optional timeline of CTA 0 (diagnostic build): tdbg[unit][8] clock stamps
   auto stamp = [&](int i, int slot) {
     if (DBG && tdbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && i < 64) tdbg[i * 8 + slot] = clock64();
   };
-  const uint32_t P = (uint32_t)(KP / 4) * 128;
+  const uint32_t P = H16 ? (uint32_t)(KP / 8) * 128 : (uint32_t)(KP / 4) * 128;
   const uint32_t w_bytes = 2 * (uint32_t)(TN / 8) * P, img_bytes = w_bytes + (uint32_t)TN * 4;
   const uint32_t Ws = (smem_u32(smem_raw) + 1023u) & ~1023u;  // [hi | lo], shared-window address
+  __shared__ float ssc[2][40];  // H16: 1 / s1_d, 1 / s2_d
+  if (H16) {
+    for (int d = threadIdx.x; d < 80; d += kWsThreads) ssc[d / 40][d % 40] = (d % 40 < DP) ? scales[(d / 40) * DP + d % 40] : 1.f;
+  }
   const uint32_t bars = Ws + w_bytes;
   const uint32_t full = bars, empty = bars + 16, dfull = bars + 32, dempty = bars + 48, tmem_slot = bars + 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,7 +365,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     // =================================== LOADERS ===================================
     const int q = warp & 3, h = (warp - kWsEpiWarps) >> 2;
     const int r = 32 * q + lane;  // frame row of the tile = TMEM lane
-    constexpr int kQ = 5;         // float4 per thread: half a row (DP <= 40)
+    constexpr int kQ = H16 ? 6 : 5;  // float4 per thread: half a row (DP <= 40); halves go in groups of 8 dimensions: 24 + 16
     const int nq = DP / 4;
     const int j0 = h * kQ;        // this thread expands float4 [j0, j0 + kQ) of the row: x -> columns 4j.., x^2 -> columns DP + 4j..
     // Global loads run three levels ahead of the expansion so that no latency is exposed per unit:
@@ -297,6 +402,30 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       if (warp == kWsEpiWarps) stamp(i, 1);
       tc_fence_after();
       // stage s: [x_hi (DP) | x2_hi (DP) | x_lo (DP) | x2_lo (DP)], 4 columns per store
+      if (H16) {
+        // stage s: [x' hi | x''^2 hi | x' lo | x''^2 lo], DP / 2 columns (two halves each) per block; 8 dimensions per store
+        const uint32_t xs = xa0 + (uint32_t)s * 160;
+        const int hb = DP / 2;
+#pragma unroll
+        for (int j = 0; j < kQ; j += 2) {
+          if (j0 + j < nq) {
+            const float v[8] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w, xv[j + 1].x, xv[j + 1].y, xv[j + 1].z, xv[j + 1].w};
+            uint32_t ah[4], al[4], qh[4], ql[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int d0 = 4 * (j0 + j) + 2 * e;
+              split_half2(v[2 * e] * ssc[0][d0], v[2 * e + 1] * ssc[0][d0 + 1], ah[e], al[e]);
+              const float s0 = v[2 * e] * ssc[1][d0], s1 = v[2 * e + 1] * ssc[1][d0 + 1];
+              split_half2(s0 * s0, s1 * s1, qh[e], ql[e]);
+            }
+            const uint32_t c0 = 2 * (j0 + j);
+            tmem_st4(xs + c0, ah);
+            tmem_st4(xs + hb + c0, qh);
+            tmem_st4(xs + 2 * hb + c0, al);
+            tmem_st4(xs + 3 * hb + c0, ql);
+          }
+        }
+      } else {
       const uint32_t xa = xa0 + (uint32_t)s * 160 + 4 * j0;
 #pragma unroll
       for (int j = 0; j < kQ; j++) {
@@ -310,6 +439,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
           tmem_st4(xa + DP + 4 * j, vh);
           tmem_st4(xa + 80 + DP + 4 * j, vl);
         }
+      }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -336,7 +466,7 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
     }
   } else if (warp == kWsEpiWarps + 8) {
     // =================================== MMA ISSUER ===================================
-    const uint32_t idesc = make_idesc_tf32(kTcRows, TN);
+    const uint32_t idesc = H16 ? make_idesc_f16(kTcRows, TN) : make_idesc_tf32(kTcRows, TN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem0, 0);
     for (int ui = u_begin, i = 0; ui < u_end; ui++, i++) {
       const int s = i & 1, sa = i % AST;
@@ -347,10 +477,21 @@ k_emis_ws(const TcTile *__restrict__ units, int nunits, int ntiles_dec, int nfra
       stamp(i, 4);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint32_t xh = tb + (uint32_t)sa * 160, xl = xh + 80;
+        const uint32_t xh = tb + (uint32_t)sa * 160, xl = xh + (H16 ? (uint32_t)DP : 80u);
         const uint64_t wh = make_smem_desc2(Ws, 128, P), wl = make_smem_desc2(Ws + (uint32_t)(TN / 8) * P, 128, P);
         const uint32_t d = tb + acc0 + (uint32_t)s * ACS;
-        if (NSLAB == 10) {  // D = 39: fully unrolled
+        if (H16) {
+          uint32_t acc = 0;
+          for (int p = 0; p < 3; p++) {  // Xh*Wh, Xl*Wh, Xh*Wl
+            const uint32_t a0 = (p == 1) ? xl : xh;
+            const uint64_t b0 = (p == 2) ? wl : wh;
+#pragma unroll 5
+            for (int j = 0; j < NSLAB; j++) {
+              tc_mma_f16_ts(d, a0 + j * 8, b0 + (uint64_t)(j * 16), idesc, acc);
+              acc = 1;
+            }
+          }
+        } else if (NSLAB == 10) {  // D = 39: fully unrolled
 #pragma unroll
           for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, xh + j * 8, wh + (uint64_t)(j * 16), idesc, j > 0);  // Xh*Wh
 #pragma unroll
