@@ -801,10 +801,10 @@ def test_decode_kernel_variants_match_oracle(N, M, D):
     c.close()
 
 
-@pytest.mark.parametrize("N,M,spread", [(5, 3, 0.0), (5, 16, 0.0), (3, 8, 2.0), (5, 3, 3.0)])
+@pytest.mark.parametrize("N,M,spread", [(5, 3, 0.0), (5, 16, 0.0), (3, 8, 2.0), (5, 3, 3.0), (3, 128, 0.0), (2, 32, 2.0), (1, 160, 1.0)])
 def test_half_precision_decode_operands(N, M, spread):
-    """k_emis_dec with half-precision operands (kind::f16 MMAs, per-dimension power-of-two scaling; the default) against
-    the 3xTF32 form of the same kernel and against the oracle (calc_gaus / calc_symbol_probab, R-FS:860-947, through the
+    """The decode emission kernels (k_emis_dec for M <= 16, k_emis_ws<false> above) with half-precision operands (kind::f16
+    MMAs, per-dimension power-of-two scaling; the default) against the 3xTF32 form of the same kernels and against the oracle (calc_gaus / calc_symbol_probab, R-FS:860-947, through the
     forward score R-FS:739-836).  `spread` stretches every feature dimension by its own factor 10^U(-spread, spread)
     (models transformed with it), so that the dimensions' magnitudes differ by up to six decades: the scaling has to bring
     each of them into the half's range on its own."""
@@ -821,7 +821,7 @@ def test_half_precision_decode_operands(N, M, spread):
         c.set_features(x, off)
         c.set_models(ms)
         got[f16] = c.forward_scores()
-        assert c.kernel_ms("dec_grid") > 0 and c.kernel_ms("tc_active") == 1
+        assert (c.kernel_ms("dec_grid") > 0) == (M <= 16) and c.kernel_ms("tc_active") == 1 and c.kernel_ms("dec_f16_active") == f16
         lab, _ = c.rank(got[f16])
         assert (lab == labels).all()
         c.close()
