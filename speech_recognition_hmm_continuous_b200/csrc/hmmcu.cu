@@ -475,6 +475,11 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
   if (strcmp(key, "dec_f16") == 0) { ctx->dec_f16 = value; ctx->ws_dec.dirty = true; return HMMCU_OK; }
   if (strcmp(key, "dec_budget_kb") == 0) { ctx->dec_budget_kb = value; return HMMCU_OK; }
+  if (strcmp(key, "acc_dbg") == 0) {
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaMemcpyToSymbol(g_acc_dbg, &value, sizeof(int)));
+    return HMMCU_OK;
+  }
   if (strcmp(key, "dec_dbg") == 0) { ctx->dec_dbg = value; return HMMCU_OK; }
   if (strcmp(key, "dec_emis") == 0) { ctx->use_dec_emis = value; return HMMCU_OK; }
   if (strcmp(key, "dec_cluster") == 0) { ctx->dec_cluster = value == 4 ? 4 : 2; ctx->dec_grid = 0; return HMMCU_OK; }

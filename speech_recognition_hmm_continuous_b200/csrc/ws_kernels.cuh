@@ -739,6 +739,8 @@ __host__ __device__ inline size_t ws_acc_smem_bytes(int KP) {
   return kAccStages * ws_acc_stage_bytes(KP) + 1024 + 256 + kAccImgCap * 4 + (size_t)tc_kp2(KP) * 128 * 4;
 }
 
+__device__ int g_acc_dbg = 0;  // experiments ("acc_dbg" option; results are garbage): 1 = no weight arithmetic in the epilogue, 2 = no MMAs
+
 template <bool DBG>
 __global__ void __launch_bounds__(kAccWsThreads, 1)
 k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restrict__ frame_ids, const float *__restrict__ x32,
@@ -981,7 +983,8 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
         const uint32_t Xh = sm0 + (uint32_t)s * stage_bytes;
         const uint64_t bh = make_smem_desc2(Xh, 128, PX), bl = make_smem_desc2(Xh + x_bytes, 128, PX);
         const uint32_t d = tb + (uint32_t)s * SUB, wh = tb + kAccTmW, wl = wh + KP;
-        if (NSLAB == 10) {  // D = 39: fully unrolled, addresses are immediates
+        if (g_acc_dbg & 2) {
+        } else if (NSLAB == 10) {  // D = 39: fully unrolled, addresses are immediates
 #pragma unroll
           for (int j = 0; j < 10; j++) tc_mma_tf32_ts(d, wh + j * 8, bh + (uint64_t)(j * 16), idesc1, j > 0);  // Wh*Xh
 #pragma unroll
@@ -1024,12 +1027,14 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
         const uint32_t XTh = sm0 + (uint32_t)sj * stage_bytes + 2 * x_bytes;
         const uint64_t bh = make_smem_desc2(XTh, 128, PT), bl = make_smem_desc2(XTh + xt_bytes, 128, PT);
         const uint32_t wh = tb + (uint32_t)sj * SUB, wl = wh + 128, d = tb + 256;
+        if (!(g_acc_dbg & 2)) {
 #pragma unroll
         for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wh + k * 8, bh + (uint64_t)(k * 16), idesc2, (cnt > 1 || k > 0) ? 1u : 0u);  // wh*Xh
 #pragma unroll
         for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wl + k * 8, bh + (uint64_t)(k * 16), idesc2, 1);                              // wl*Xh
 #pragma unroll
         for (int k = 0; k < SUB / 8; k++) tc_mma_tf32_ts(d, wh + k * 8, bl + (uint64_t)(k * 16), idesc2, 1);                              // wh*Xl
+        }
         if (DBG && tdbg && blockIdx.x == 0 && j < 64) tdbg[j * 16 + 9] = clock64();
         tc_commit_a(x_free + 8 * sj);
         if (drain) tc_commit_a(s_full);
@@ -1079,7 +1084,7 @@ k_accum_ws(const TcTile *__restrict__ units, int nunits, const int32_t *__restri
       }
       mbar_wait_a(d1_full + 8 * s, (i / NST) & 1);
       if (warp == 0) stamp(i, 6);
-      if (!dead) {  // my FH frames: accumulator columns [FH hb, FH hb + FH) of stage s.  (The rows of a dead warp
+      if (!dead && !(g_acc_dbg & 1)) {  // my FH frames: accumulator columns [FH hb, FH hb + FH) of stage s.  (The rows of a dead warp
                     // feed only pad rows of S, which are never read.)
         tc_fence_after();
         const int c0 = hb * FH;
