@@ -19,6 +19,7 @@
 #include "tc_kernels.cuh"
 #include "ws_kernels.cuh"
 #include "dec_kernels.cuh"
+#include "acch_kernels.cuh"
 #include "vit_kernels.cuh"
 #include "init_kernels.cuh"
 
@@ -160,6 +161,11 @@ struct hmmcu_ctx {
   DevBuf acc_images, acc_kc, acc_units, acc_dbg, acc_units64, acc_scratch, acc_slot_start, acc_slot_ids;
   int64_t n_acc_units64 = 0;
   int use_ws_acc = 1;  // warp-specialised accumulate kernel (0 = k_accum_tc)
+  // k_accum_h (acch_kernels.cuh): half-precision operands, the expanded frame tiles of all units packed once per feature set
+  int use_h_acc = 1;
+  DevBuf acc_images16, acc_sc, acc_unitsH, acc_slot_start_h, acc_slot_ids_h, x16, x16_tiles;
+  int64_t n_acc_unitsH = 0, n_x16_tiles = 0;
+  uint64_t x_version = 1, map_version = 1, x16_x = 0, x16_map = 0;  // what x16 was packed from
   int use_dec_emis = 1;  // decode emissions with the frames resident in tensor memory and the W images multicast over a cluster (k_emis_dec)
   int dec_cluster = 2;   // CTAs per cluster of k_emis_dec (2 or 4)
   int fwd_f64 = 0;       // forward cell scorer with the chain in double (k_fwd_cells) instead of k_fwd_cells32
@@ -378,7 +384,8 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
                     &ctx->frame_ids_d, &ctx->tc_tiles_dec, &ctx->acc_images, &ctx->acc_kc, &ctx->acc_units, &ctx->beta_ws, &ctx->acc_dbg, &ctx->em_old, &ctx->em_active, &ctx->ctl_d, &ctx->ext_d, &ctx->upd_d, &ctx->ws_train.images, &ctx->ws_train.s0, &ctx->ws_train.ns,
                     &ctx->ws_dec.images, &ctx->ws_dec.images16, &ctx->ws_dec.scales16, &ctx->ws_dec.s0, &ctx->ws_dec.ns, &ctx->ws_tiles_train, &ctx->acc_units64, &ctx->logb64, &ctx->acc_scratch, &ctx->acc_slot_start, &ctx->acc_slot_ids, &ctx->in_lst, &ctx->in_off, &ctx->in_vk, &ctx->in_cent,
                     &ctx->in_sum, &ctx->in_dist, &ctx->in_cnt, &ctx->in_idx, &ctx->in_dd, &ctx->in_ord, &ctx->vit_map, &ctx->vit_tiles,
-                    &ctx->res_order, &ctx->res_upos, &ctx->res_batches, &ctx->res_counter, &ctx->ustats};
+                    &ctx->res_order, &ctx->res_upos, &ctx->res_batches, &ctx->res_counter, &ctx->ustats,
+                    &ctx->acc_images16, &ctx->acc_sc, &ctx->acc_unitsH, &ctx->acc_slot_start_h, &ctx->acc_slot_ids_h, &ctx->x16, &ctx->x16_tiles};
   for (DevBuf *b : bufs) b->release();
   for (auto &kv : ctx->timers) {
     if (kv.second.a) cudaEventDestroy(kv.second.a);
@@ -470,7 +477,8 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "tc_emis") == 0) { ctx->use_tc = value; return HMMCU_OK; }
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
-  if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; return HMMCU_OK; }
+  if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
+  if (strcmp(key, "h_acc") == 0) { ctx->use_h_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
   if (strcmp(key, "dec_f16") == 0) { ctx->dec_f16 = value; ctx->ws_dec.dirty = true; return HMMCU_OK; }
@@ -573,6 +581,7 @@ static int features_geometry(hmmcu_ctx *ctx, const int64_t *frame_off, int U, in
   ctx->pack_dirty = true;  // the centre may move
   ctx->kappa_stale = true;
   ctx->have_features = true;
+  ctx->x_version++;
   ctx->stream_open = false;
   if (F == 0) return HMMCU_OK;
   CK(ctx->off_d.ensure(sizeof(int64_t) * (U + 1)));
@@ -1010,8 +1019,20 @@ static bool tc_supported(const hmmcu_ctx *ctx) {
   return tc_emis_smem_bytes(TN, 2 * ctx->DP) <= 227 * 1024;
 }
 
+// k_accum_h instead of k_accum_ws: a matter of shapes and options only (the packed forms follow it)
+static bool h_acc_on(const hmmcu_ctx *ctx) {
+  return ctx->use_ws_acc && ctx->use_h_acc && ctx->DP % 8 == 0 && ctx->DP <= 40 && ctx->N <= 8 && ctx->xabs_d.p != nullptr && ctx->F > 0;
+}
+
 static int launch_pack_acc(hmmcu_ctx *ctx) {
   const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
+  if (h_acc_on(ctx)) {
+    k_pack_wT_h<<<dim3((128 * KP + 255) / 256, nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
+                                                                         ctx->ctr.as<double>(), ctx->acc_sc.as<float>(), ctx->G, nRB, ctx->D, ctx->DP,
+                                                                         ctx->acc_images16.as<unsigned short>(), ctx->acc_kc.as<float>());
+    LAUNCH_CHECK();
+    return HMMCU_OK;
+  }
   k_pack_wT_tc<<<dim3((128 * KP + 255) / 256, nimg), 256, 0, ctx->st>>>(ctx->mu.as<double>(), ctx->iv.as<double>(), ctx->kc2.as<float>(),
                                                                         ctx->ctr.as<double>(), ctx->G, nRB, ctx->D, ctx->DP,
                                                                         ctx->acc_images.as<float>(), ctx->acc_kc.as<float>());
@@ -1022,7 +1043,12 @@ static int launch_pack_acc(hmmcu_ctx *ctx) {
 static int ensure_acc_images(hmmcu_ctx *ctx) {
   if (!ctx->acc_dirty) return HMMCU_OK;
   const int KP = 2 * ctx->DP, nRB = (ctx->G + 127) / 128, nimg = ctx->V * nRB;
-  CK(ctx->acc_images.ensure(tc_accT_image_bytes(KP) * nimg));
+  if (h_acc_on(ctx)) {
+    CK(ctx->acc_images16.ensure(ah_image_bytes(KP) * nimg));
+    CK(ctx->acc_sc.ensure(sizeof(float) * kAhScN * ctx->DP));
+  } else {
+    CK(ctx->acc_images.ensure(tc_accT_image_bytes(KP) * nimg));
+  }
   CK(ctx->acc_kc.ensure(sizeof(float) * 128 * (size_t)nimg));
   int rc = ensure_kc(ctx);
   if (rc) return rc;
@@ -1702,6 +1728,47 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
         CK(cudaMemcpyAsync(ctx->acc_slot_ids.p, sids.data(), sizeof(int32_t) * sids.size(), cudaMemcpyHostToDevice, ctx->st));
         CK(ctx->acc_scratch.ensure(sizeof(float) * (size_t)std::max(grid, 1) * kAccSlots * tc_kp2(2 * ctx->DP) * 128));
       }
+      {  // k_accum_h: units of kAhSub frames; state0 = the unit's tile in x16 (the row blocks of a model share its tiles);
+         // the same slot scheme over this kernel's CTA ranges
+        std::vector<TcTile> ah;
+        std::vector<int2> tl;
+        r0 = 0;
+        for (int v = 0; v < V; v++) {
+          int32_t nfr = 0;
+          for (int k = start[v]; k < start[v + 1]; k++) nfr += (int32_t)(ctx->off[utts[k] + 1] - ctx->off[utts[k]]);
+          const int32_t t0 = (int32_t)tl.size();
+          for (int32_t r = 0; r < nfr; r += kAhSub) tl.push_back(make_int2(r0 + r, std::min<int32_t>(kAhSub, nfr - r)));
+          for (int rb = 0; rb < nRB; rb++)
+            for (int32_t r = 0; r < nfr; r += kAhSub) ah.push_back({r0 + r, std::min<int32_t>(kAhSub, nfr - r), v * nRB + rb, t0 + r / kAhSub, v, rb});
+          r0 += nfr;
+        }
+        ctx->n_acc_unitsH = (int64_t)ah.size();
+        ctx->n_x16_tiles = (int64_t)tl.size();
+        CK(ctx->acc_unitsH.ensure(sizeof(TcTile) * std::max<size_t>(ah.size(), 1)));
+        CK(ctx->x16_tiles.ensure(sizeof(int2) * std::max<size_t>(tl.size(), 1)));
+        CK(cudaMemcpyAsync(ctx->acc_unitsH.p, ah.data(), sizeof(TcTile) * ah.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->x16_tiles.p, tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice, ctx->st));
+        const int64_t nun = (int64_t)ah.size();
+        const int grid = (int)std::min<int64_t>(nun, ctx->sm_count);
+        const int nimg = V * nRB;
+        std::vector<std::vector<int32_t>> lists(nimg);
+        if (grid > 0) {
+          const int64_t per = (nun + grid - 1) / grid;
+          for (int c = 0; c < grid; c++) {
+            int j = -1, prev = -1;
+            for (int64_t k = c * per; k < std::min(nun, (c + 1) * per); k++) {
+              if (ah[k].img != prev) { prev = ah[k].img; j++; if (j < kAccSlots) lists[prev].push_back(c * kAccSlots + j); }
+            }
+          }
+        }
+        std::vector<int32_t> sstart(nimg + 1, 0), sids;
+        for (int i = 0; i < nimg; i++) { sids.insert(sids.end(), lists[i].begin(), lists[i].end()); sstart[i + 1] = (int32_t)sids.size(); }
+        CK(ctx->acc_slot_start_h.ensure(sizeof(int32_t) * sstart.size()));
+        CK(ctx->acc_slot_ids_h.ensure(sizeof(int32_t) * std::max<size_t>(sids.size(), 1)));
+        CK(cudaMemcpyAsync(ctx->acc_slot_start_h.p, sstart.data(), sizeof(int32_t) * sstart.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(ctx->acc_slot_ids_h.p, sids.data(), sizeof(int32_t) * sids.size(), cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+      }
       CK(cudaStreamSynchronize(ctx->st));
     }
     CK(ctx->frame_ids_d.ensure(sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
@@ -1755,6 +1822,32 @@ static int set_train_map(hmmcu_ctx *ctx, const int32_t *utt2model) {
   CK(cudaStreamSynchronize(ctx->st));
   ctx->u2m.assign(utt2model, utt2model + U);
   ctx->cfg_epoch++;
+  ctx->map_version++;
+  return HMMCU_OK;
+}
+
+// The expanded half-precision frame tiles of k_accum_h: packed when the features or the training map have changed
+// (not per EM iteration -- the models do not enter), with the data-only scales of k_acc16_scales.
+// Preparation (allocations, the scales): need_pack tells the launch sequence to pack the tiles (launch_pack_x16), which it
+// does beside the emission and forward-backward kernels -- only the accumulate kernel reads them.
+static int prepare_x16(hmmcu_ctx *ctx, bool &need_pack) {
+  need_pack = !(ctx->x16_x == ctx->x_version && ctx->x16_map == ctx->map_version);
+  if (!need_pack) return HMMCU_OK;
+  CK(ctx->acc_sc.ensure(sizeof(float) * kAhScN * ctx->DP));
+  CK(ctx->x16.ensure(ah_tile_bytes(2 * ctx->DP) * (size_t)std::max<int64_t>(ctx->n_x16_tiles, 1)));
+  if (ctx->x16_x != ctx->x_version) {  // the scales follow the data's radius; the W images follow the scales
+    k_acc16_scales<<<1, 64, 0, ctx->st>>>(ctx->xabs_d.as<unsigned int>(), ctx->D, ctx->DP, ctx->acc_sc.as<float>());
+    LAUNCH_CHECK();
+    ctx->acc_dirty = true;
+  }
+  return HMMCU_OK;
+}
+static int launch_pack_x16(hmmcu_ctx *ctx, cudaStream_t st) {
+  if (ctx->n_x16_tiles > 0) {
+    k_pack_x16<<<(unsigned)ctx->n_x16_tiles, 256, 0, st>>>(ctx->x16_tiles.as<int2>(), ctx->frame_ids_d.as<int32_t>(), ctx->x32.as<float>(),
+                                                          ctx->acc_sc.as<float>(), ctx->DP, ctx->x16.as<unsigned char>());
+    LAUNCH_CHECK();
+  }
   return HMMCU_OK;
 }
 
@@ -1776,6 +1869,8 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
   const bool use_tc = U > 0 && tc_supported(ctx);
   const bool ws_emis = use_tc && ws_supported(ctx);
   const bool ws_acc = use_tc && ctx->use_ws_acc && DP <= 40 && ws_acc_smem_bytes(2 * DP) <= 227 * 1024;
+  const bool h_acc = ws_acc && h_acc_on(ctx);
+  bool pack16 = false;
   if (U > 0) {
     rc = set_train_map(ctx, utt2model);
     if (rc) return rc;
@@ -1794,6 +1889,7 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
       if ((rc = ensure_tc_images(ctx, 0)) != HMMCU_OK) return rc;
     }
     if (use_tc) {
+      if (h_acc && (phases & 4) && (rc = prepare_x16(ctx, pack16)) != HMMCU_OK) return rc;
       if ((rc = ensure_acc_images(ctx)) != HMMCU_OK) return rc;
     } else {
       if ((rc = ensure_simt_pack(ctx)) != HMMCU_OK) return rc;
@@ -1810,6 +1906,13 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (U == 0) return HMMCU_OK;
     int rc2;
     bool fb_forked = false;
+    const bool pack_forked = pack16 && !ctx->timing && (phases & 3) && ctx->mstep_fork;
+    if (pack_forked) {  // the half-precision frame tiles, beside the emission and forward-backward kernels
+      CK(cudaEventRecord(ctx->ev_fork[1], ctx->st));
+      CK(cudaStreamWaitEvent(ctx->st_aux[1], ctx->ev_fork[1], 0));
+      if ((rc2 = launch_pack_x16(ctx, ctx->st_aux[1])) != HMMCU_OK) return rc2;
+      CK(cudaEventRecord(ctx->ev_join[1], ctx->st_aux[1]));
+    }
     // 1. emissions (+ per-mixture posteriors on the CUDA-core path)
     if (phases & 1) {
     t_begin(ctx, "emis");
@@ -1870,8 +1973,30 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
       if (fb_forked) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[0], 0));
       return HMMCU_OK;
     }
+    if (pack_forked) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[1], 0));
+    else if (pack16) {
+      t_begin(ctx, "pack_x16");
+      if ((rc2 = launch_pack_x16(ctx, ctx->st)) != HMMCU_OK) return rc2;
+      t_end(ctx, "pack_x16");
+    }
     t_begin(ctx, "accum");
-    if (ws_acc) {
+    if (h_acc) {
+      const size_t smem = ah_smem_bytes(2 * DP);
+      const int grid = (int)std::min<int64_t>(ctx->n_acc_unitsH, ctx->sm_count);
+      const float *dsc = ctx->acc_sc.as<float>() + 5 * DP;
+      if (grid > 0) {
+        CK(cudaFuncSetAttribute(k_accum_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_accum_h<<<grid, kAhThreads, smem, ctx->st>>>(ctx->acc_unitsH.as<TcTile>(), (int)ctx->n_acc_unitsH, ctx->frame_ids_d.as<int32_t>(),
+                                                      ctx->x16.as<unsigned char>(), ctx->acc_images16.as<uint32_t>(), ctx->acc_kc.as<float>(),
+                                                      ctx->logb.as<float>(), gm_acc, N, M, G, D, DP, ctx->stats.as<double>(), ss, off_S0, off_S1,
+                                                      off_S2, ctx->acc_scratch.as<float>(), dsc);
+        LAUNCH_CHECK();
+      }
+      k_finalize_slots<<<dim3(G, V), 64 * kFinParts, 0, ctx->st>>>(ctx->stats.as<double>(), ss, G, D, DP, 2 * DP, (G + 127) / 128, off_S0, off_S1,
+                                                                  off_S2, ctx->ctr.as<double>(), ctx->mu.as<double>(), ctx->acc_scratch.as<float>(),
+                                                                  ctx->acc_slot_start_h.as<int32_t>(), ctx->acc_slot_ids_h.as<int32_t>(), dsc);
+      LAUNCH_CHECK();
+    } else if (ws_acc) {
       const size_t smem = ws_acc_smem_bytes(2 * DP);
       if (ctx->debug_acc & 4) CK(cudaMemsetAsync(ctx->acc_dbg.p, 0, sizeof(float) * 3 * 16384, ctx->st));
       const int grid = (int)std::min<int64_t>(ctx->n_acc_units64, ctx->sm_count);
@@ -1936,10 +2061,12 @@ static int estep_core(hmmcu_ctx *ctx, const int32_t *utt2model, int phases, cons
     if (fb_forked) CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[0], 0));
     return HMMCU_OK;
   };
-  const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 15) << 9);
+  const uint64_t key = 1u | ((ctx->use_res_fb && ctx->banded && ctx->res_fits) ? (1u << 8) : 0u) | (use_tc ? 2u : 0u) | (ws_emis ? 4u : 0u) | (ws_acc ? 8u : 0u) | (h_acc ? 32u : 0u) | (pack16 ? 64u : 0u) | (ctx->banded ? 16u : 0u) | ((uint64_t)(ctx->debug_acc & 15) << 9);
   ctx->last_tc = use_tc;
-  if (phases != 7 || fb_logb || acc_gamma) return enqueue();  // pieces of a multi-stream E-step: plain launches
-  return run_graphed(ctx, ctx->g_estep, key, enqueue);
+  // (pieces of a multi-stream E-step: plain launches)
+  const int rcq = (phases != 7 || fb_logb || acc_gamma) ? enqueue() : run_graphed(ctx, ctx->g_estep, key, enqueue);
+  if (rcq == HMMCU_OK && pack16) { ctx->x16_x = ctx->x_version; ctx->x16_map = ctx->map_version; }
+  return rcq;
 }
 
 int hmmcu_estep(hmmcu_ctx *ctx, const int32_t *utt2model, double *stats, double *logp_utt) {
