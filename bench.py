@@ -496,7 +496,7 @@ def run_ours(args):
     ms_step = tot_ms / args.steps
     value = F * world / (ms_step * 1e-3)
     traffic, traffic_src = traffic_table()
-    rooflines = training_rooflines(kms, F, N, M, V, pk, tf32_peak, traffic.get(args.workload, {}))
+    rooflines = training_rooflines(kms, F, N, M, V, pk, tf32_peak, traffic.get(args.workload, {}), acc_h=ctx.kernel_ms("acc_h_active") > 0)
     for leg, kn, per_pair in (("forward", "score", 4.0 * N), ("viterbi", "viterbi", None)):
         kt = dec[leg]["kernel_ms"].get(kn)
         if per_pair and kt and kt > 0:
@@ -539,19 +539,21 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def training_rooflines(kms, F, N, M, V, pk, tf32_peak, traffic):
+def training_rooflines(kms, F, N, M, V, pk, tf32_peak, traffic, acc_h=False):
     """One entry per kernel of the EM iteration, each against the bound that really limits it.
     F = frames of one launch on this rank."""
     from speech_recognition_hmm_continuous_b200 import api
     G = N * M
     out = {}
 
-    def tensor(name, kernel, flops, ms, hbm_bytes):
+    def tensor(name, kernel, flops, ms, hbm_bytes, f16=False):
         if not ms or ms <= 0:
             return
         ach = flops / (ms * 1e-3) / 1e12
-        out[name] = {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                     "issued_3xtf32": {"achieved": 3 * ach, "frac": 3 * ach / tf32_peak}, "ms": ms, "algorithmic_flops": flops,
+        peak = (pk.get("bf16_sustained") or pk.get("bf16_tflops")) if f16 else tf32_peak
+        out[name] = {"kernel": kernel, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "peak_what": "fp16 / bf16 dense, sustained (MEASURED_PEAKS.json)" if f16 else "TF32 dense, library GEMM measured in this run",
+                     ("issued_3xf16" if f16 else "issued_3xtf32"): {"achieved": 3 * ach, "frac": 3 * ach / peak}, "ms": ms, "algorithmic_flops": flops,
                      "hbm_view": {"algorithmic_bytes": hbm_bytes, "gbs": hbm_bytes / (ms * 1e-3) / 1e9, "frac": hbm_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
                      "traffic": traffic.get(name)}
 
@@ -570,7 +572,20 @@ def training_rooflines(kms, F, N, M, V, pk, tf32_peak, traffic):
     # alpha / beta in shared memory and moves 8 N (logb in, gamma out)
     hbm("fwdbwd", "k_fb_res", F * (16.0 * N + 4.0), kms.get("fwdbwd"), {"bytes_the_kernel_moves": F * 8.0 * N})
     # accumulate: two chained contractions (posteriors recomputed, then S += w Xaug): 4 K G flops per frame
-    tensor("accum", "k_accum_ws", 4.0 * K_AUG * G * F, kms.get("accum"), F * (4.0 * D + 8.0 * N))
+    # (k_accum_h: half-precision operands; it reads its frames as packed tiles, 2 x 2 x 3 DP bytes per frame, instead of 4 D)
+    if acc_h:
+        # HBM is the nearer ceiling (ncu at the C3 shard: DRAM 63 % of its peak, tensor pipe 64 % active): per frame the kernel reads its
+        # tile (3 column blocks x DP x hi / lo halves = 12 DP = 480 bytes) and gamma, logb (8 N); SURVEY 8d counts 496 bytes per frame
+        tensor("accum", "k_accum_h", 4.0 * K_AUG * G * F, kms.get("accum"), F * (12.0 * (K_AUG // 2 + 1) + 8.0 * N), f16=True)
+        a = out.get("accum")
+        if a:
+            tv = {k: a[k] for k in ("achieved", "peak", "unit", "frac", "peak_what", "issued_3xf16", "algorithmic_flops")}
+            hv = a["hbm_view"]
+            out["accum"] = {"kernel": "k_accum_h", "bound": "hbm", "achieved": hv["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hv["frac"],
+                            "ms": a["ms"], "algorithmic_bytes": hv["algorithmic_bytes"], "survey_8d_bytes": F * 496.0, "traffic": a["traffic"],
+                            "tensor_view": tv}
+    else:
+        tensor("accum", "k_accum_ws", 4.0 * K_AUG * G * F, kms.get("accum"), F * (4.0 * D + 8.0 * N))
     hbm("mstep", "k_mstep_ctl+k_mstep_apply+packers", 8.0 * V * api.stats_size(N, M, D), kms.get("mstep"),
         {"note": "a few hundred KB: launch / dependency latency, not bandwidth"})
     return out
@@ -638,7 +653,7 @@ def run_c3(t, args):
            "scaling": "strong", "utterances_total": U, "frames_total": int(Ftot), "frames_this_rank": F, "n_gpus": world,
            "ms_per_step": ms_step, "frames_per_s": Ftot / (ms_step * 1e-3), "steps": steps, "kernel_ms": kms, "allreduce_ms": ar_ms,
            "gpu_launches": int(launches),
-           "rooflines": training_rooflines(kms, F, N, M, V, t["pk"], t["tf32_peak"], t["traffic"].get("c3", {})),
+           "rooflines": training_rooflines(kms, F, N, M, V, t["pk"], t["tf32_peak"], t["traffic"].get("c3", {}), acc_h=c.kernel_ms("acc_h_active") > 0),
            "l2": "flushed between timed iterations; the shard's features alone exceed the L2"}
     c.close()
     del x

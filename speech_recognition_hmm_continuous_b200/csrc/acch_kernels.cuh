@@ -200,7 +200,7 @@ k_accum_h(const TcTile *__restrict__ units, int nunits, const int32_t *__restric
 
   if (warp >= 8 && warp < 8 + kAhCfWarps) {
     // =================================== WEIGHT EXPONENTS ===================================
-    // thread <-> frame row xr of the unit: cf[state][xr] = log2 gamma - logb log2 e (-inf = no weight).  Global loads run
+    // thread <-> frame row xr of the unit: cf[state][xr] = log2 gamma - logb log2 e + 14 (-inf = no weight).  Global loads run
     // ahead of the hand-off: unit descriptor (i+3) -> frame id (i+2) -> gamma, logb (i+1), while unit i is stored.
     const int xr = tid - 256;
     struct Pre { float gm[8], lb[8]; };
@@ -221,7 +221,9 @@ k_accum_h(const TcTile *__restrict__ units, int nunits, const int32_t *__restric
 #pragma unroll
       for (int st = 0; st < 8; st++) {
         float cf = kNegInf;
-        if (cur.gm[st] > 0.f && cur.lb[st] > kNegInf) cf = __log2f(cur.gm[st]) - cur.lb[st] * 1.4426950408889634f;
+        // (+ 14: the weights' scale 2^14.  cf is ~ +200 and rounded to 2^-16 as it is; added to kc in the epilogue the 14 would
+        // cost another rounding of that size)
+        if (cur.gm[st] > 0.f && cur.lb[st] > kNegInf) cf = fmaf(cur.lb[st], -1.4426950408889634f, __log2f(cur.gm[st]) + kAhWLog2);
         sts_f32(cfs + st * SUB * 4, cf);
       }
       mbar_arrive_a(x_full + 8 * s);
@@ -335,7 +337,6 @@ k_accum_h(const TcTile *__restrict__ units, int nunits, const int32_t *__restric
     const int nc8 = KP / 8;
     const int c8_beg = hb ? (nc8 + 1) / 2 : 0, c8_end = hb ? nc8 : (nc8 + 1) / 2;
     const uint32_t my_acc = sacc + 4 * row;  // + 512 per column
-    const float wscale = exp2f(kAhWLog2);  // applied after the exponential: added to kc (~ -200) it would cost 1e-5 of every weight
     int cnt = 0, ndrain = 0, nflush = 0;
     float kcr = kNegInf;
     int st = 0, cur_v = 0, cur_rb = 0;
@@ -378,14 +379,14 @@ k_accum_h(const TcTile *__restrict__ units, int nunits, const int32_t *__restric
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {  // ex2(-inf) = +0 and underflow flushes to 0: no weight; the exponent is never NaN
-          const float a = ex2_approx(fmaf(__uint_as_float(v0[j]), 1.4426950408889634f, kcr + ce[j])) * wscale;
-          const float b = ex2_approx(fmaf(__uint_as_float(v0[j + 1]), 1.4426950408889634f, kcr + ce[j + 1])) * wscale;
+          const float a = ex2_approx(fmaf(__uint_as_float(v0[j]), 1.4426950408889634f, kcr + ce[j]));
+          const float b = ex2_approx(fmaf(__uint_as_float(v0[j + 1]), 1.4426950408889634f, kcr + ce[j + 1]));
           split_half2(a, b, wh[j >> 1], wl[j >> 1]);
         }
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float a = ex2_approx(fmaf(__uint_as_float(v1[j]), 1.4426950408889634f, kcr + ce[16 + j])) * wscale;
-          const float b = ex2_approx(fmaf(__uint_as_float(v1[j + 1]), 1.4426950408889634f, kcr + ce[16 + j + 1])) * wscale;
+          const float a = ex2_approx(fmaf(__uint_as_float(v1[j]), 1.4426950408889634f, kcr + ce[16 + j]));
+          const float b = ex2_approx(fmaf(__uint_as_float(v1[j + 1]), 1.4426950408889634f, kcr + ce[16 + j + 1]));
           split_half2(a, b, wh[8 + (j >> 1)], wl[8 + (j >> 1)]);
         }
         tmem_st16(tl, wh);

@@ -755,6 +755,60 @@ def test_many_small_models_take_the_atomic_flush_path(ctx):
         assert np.allclose(sp["num_trans"], st.num_trans, rtol=RTOL, atol=1e-6 * st.num_trans.max())
 
 
+@pytest.mark.parametrize("N,M,D,spread", [(5, 16, 39, 0.0), (5, 3, 39, 2.0), (3, 128, 39, 0.0), (4, 4, 15, 1.0), (5, 2, 9, 0.0)])
+def test_half_precision_accumulate_operands(N, M, D, spread):
+    """k_accum_h (half-precision operands, frame tiles packed once per feature set; the default for feature widths with
+    D + 1 rounded to a multiple of 8) against k_accum_ws (3xTF32) and against the oracle's calc_mix_param sums
+    (T-FS:1691-1727), also with feature dimensions decades apart (every dimension gets its own power-of-two scales) and
+    through a second E-step after new models (the tiles stay, the W images follow the models).  D = 9 (DP = 12) has no
+    half-precision form: the option must fall back to k_accum_ws by itself."""
+    V, U = 2, 8
+    ms, x, off, labels = _synth(V, N, M, U, seed=5200 + N * M, tmin=50, tmax=110, D=D)
+    if spread > 0:
+        g = 10.0 ** np.random.default_rng(23).uniform(-spread, spread, size=x.shape[1])
+        x = x * g
+        ms = api.ModelSet(ms.A, ms.c, ms.mu * g, ms.iv / g ** 2, ms.det * np.prod(g ** 2))
+    want = []
+    for v in range(V):
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        want.append(o.estep(_oracle_model(ms, v), xv, offv)[0])
+    got = {}
+    for h in (1, 0):
+        c = api.Context(0)
+        c.set_option("h_acc", h)
+        c.set_features(x, off)
+        c.set_models(ms)
+        for rep in range(2):  # the second E-step reuses the packed tiles
+            stats, _ = c.estep(labels)
+        assert c.kernel_ms("tc_active") == 1 and c.kernel_ms("acc_h_active") == (1 if h and (D + 1 + 3) // 4 * 4 % 8 == 0 else 0)
+        got[h] = [api.split_stats(stats[v], N, M, D) for v in range(V)]
+        # new models (every mean moved, variances changed), same features: only the W images are repacked
+        ms2 = api.ModelSet(ms.A, ms.c, ms.mu + 0.05 / np.sqrt(ms.iv), ms.iv * 0.8, ms.det / 0.8 ** D)
+        c.set_models(ms2)
+        st2, _ = c.estep(labels)
+        got[(h, 2)] = [api.split_stats(st2[v], N, M, D) for v in range(V)]
+        c.close()
+    def close(sp, st, mean_x):
+        S0 = np.maximum(st.S0, 1e-300)[..., None]
+        occ = st.S0 > 1e-3 * st.S0.max()
+        sd = np.sqrt(st.S2c / S0)
+        assert np.allclose(sp["S0"], st.S0, rtol=RTOL, atol=1e-6 * st.S0.max()), "S0"
+        assert (np.abs(sp["S1"] / S0 - st.S1 / S0)[occ] <= RTOL * np.maximum(np.abs(st.S1 / S0), sd)[occ]).all(), "S1"
+        want2 = st.S2c / S0
+        scale2 = want2 + (st.S1 / S0 - mean_x) ** 2
+        assert (np.abs(sp["S2c"] / S0 - want2)[occ] <= (RTOL * want2 + 2e-6 * scale2)[occ]).all(), "S2c"
+    for v in range(V):
+        close(got[1][v], want[v], x.mean(0))
+        close(got[0][v], want[v], x.mean(0))
+        us = np.nonzero(labels == v)[0]
+        xv = np.concatenate([x[off[u]:off[u + 1]] for u in us])
+        offv = np.concatenate([[0], np.cumsum([off[u + 1] - off[u] for u in us])])
+        st2 = o.estep(_oracle_model(ms2, v), xv, offv)[0]
+        close(got[(1, 2)][v], st2, x.mean(0))
+
+
 @pytest.mark.parametrize("N,M,D", [(4, 2, 13), (5, 32, 39), (2, 160, 39)])
 def test_decode_paths_other_shapes(ctx, N, M, D):
     """Forward scores / labels and Viterbi paths for feature widths other than 39 (generic k_logb64), for a
