@@ -307,11 +307,18 @@ def run_ours(args):
             dist.barrier()
         l0 = c.launch_count()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        align = torch.zeros(1, device=dev)
         kms = {k: [] for k in kernel_names}
         wall0 = time.perf_counter()
         for i in range(steps):
             flush.fill_(i & 0xFF)  # L2 flush between timed iterations (256 MiB > 126 MB L2), outside the event pair
             torch.cuda.synchronize()
+            if world > 1:
+                # The flush and the host-side synchronisation above end at a different moment on every rank; without a common
+                # start the first rank's step would be charged the wait for the last rank's FLUSH in the step's all-reduce.  A
+                # one-element collective on the step's stream releases all ranks together; the start event follows it.
+                with torch.cuda.stream(st):
+                    dist.all_reduce(align)
             ev[i][0].record(st)
             fn()
             ev[i][1].record(st)
@@ -359,6 +366,28 @@ def run_ours(args):
     tot_ms, launches, _, wall = timed(ctx, step_resident, args.steps, args.warmup)
     clocks = sampler.stop()
     kms, ar_ms = kernel_pass(ctx, labels, max(3, min(args.steps, 20)))
+    ar_alone_ms = None
+    if world > 1 and ctx._ar is not None:
+        # the collective by itself: all ranks released together (one-element collective), nothing in front of it -- what is left
+        # of allreduce_ms above this is the wait for the slowest rank's E-step
+        st_ = torch.cuda.ExternalStream(ctx.stream(), device=local)
+        al_ = torch.zeros(1, device=dev)
+        evs = []
+        p_, n_ = ctx.stats_device()
+        for _ in range(13):
+            torch.cuda.synchronize()
+            with torch.cuda.stream(st_):
+                dist.all_reduce(al_)
+                torch.cuda._sleep(200000)  # ~0.1 ms of device time: the host gets ahead, so its launch latency is not in the interval
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st_)
+            ctx._ar(p_, n_, ctx.stream())
+            e1.record(st_)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t_ = torch.tensor([float(np.mean([a_.elapsed_time(b_) for a_, b_ in evs[3:]]))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ar_alone_ms = float(t_.item())
     e2e_steps = max(3, min(args.steps, 50))
     e2e_ms, _, _, _ = timed(ctx, step_e2e, e2e_steps, max(3, min(args.warmup, 5)))
 
@@ -517,7 +546,7 @@ def run_ours(args):
         "e2e": {"value": F * world / (e2e_ms / e2e_steps * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms / e2e_steps,
                 "h2d_bytes_per_step": int(x.nbytes + off.nbytes),
                 "d2h_bytes_per_step": int(8 * (3 * V + 1))},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "allreduce_ms": ar_ms,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "allreduce_ms": ar_ms, "allreduce_alone_ms": ar_alone_ms,
         "multi_gpu_parity": parity, "decode": dec, "init_model": init, "ingest": ingest,
         "wall_s_timed_region": wall, "tf32_peak_tflops": tf32_peak,
         "tf32_peak_note": "library TF32 GEMM 8192^3 measured in this run (same protocol as MEASURED_PEAKS.json); 3xTF32 issues 3 MMAs per algorithmic MMA",

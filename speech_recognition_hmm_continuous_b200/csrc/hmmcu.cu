@@ -183,6 +183,7 @@ struct hmmcu_ctx {
   std::vector<void *> peer_ptrs;        // [world], entry `rank` = my own area
   std::vector<void *> peer_opened;      // IPC mappings to close
   int peer_rank = -1, peer_world = 0;
+  int peer_fused = 1;                   // hmmcu_peer_allreduce as one launch (k_peer_allreduce1) instead of push + reduce
   int64_t peer_n = 0;                   // doubles per slot the area was sized for
   int64_t n_res_batches = 0;
   int n_live = 0;         // utterances of the training map that belong to a model (the others are masked)
@@ -480,6 +481,7 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "debug_acc") == 0) { ctx->debug_acc = value; return HMMCU_OK; }
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
+  if (strcmp(key, "peer_fused") == 0) { ctx->peer_fused = value; return HMMCU_OK; }
   if (strcmp(key, "h_acc") == 0) { ctx->use_h_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
@@ -2328,8 +2330,67 @@ k_peer_reduce(double *__restrict__ stats, int64_t n, const double *__restrict__ 
   }
 }
 
+// One launch for the whole sum: block b pushes ITS slice of my statistics into every peer's slot for me, fences, raises the
+// slice's flag there, waits for the same slice's flags of all peers in my own area and adds the slices in rank order.  The
+// ranks synchronise slice by slice (no grid-wide hand-off, no second launch).  Blocks depend on remote blocks only, and a
+// block pushes before it waits, so any grid that is resident at once (<= kPeerBlocks <= SM count) cannot dead-lock.
+constexpr int kPeerBlocks = 128;
+__global__ void __launch_bounds__(256)
+k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict__ areas, const double *__restrict__ area, int rank, int world,
+                  unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done, int *__restrict__ err) {
+  const unsigned long long seq = *seq_p + 1;
+  const int set = (int)(seq & 1), b = blockIdx.x, nb = gridDim.x;
+  const int64_t chunk = ((n + nb - 1) / nb + 1) & ~(int64_t)1;  // even: double2 copies stay aligned
+  const int64_t i0 = min(n, (int64_t)b * chunk), i1 = min(n, i0 + chunk);
+  const size_t flag_off = sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world;
+  for (int q = 0; q < world; q++) {
+    if (q == rank) continue;
+    double *dst = reinterpret_cast<double *>(areas[q]) + ((int64_t)set * world + rank) * n;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 15) == 0) {
+      const double2 *s2 = reinterpret_cast<const double2 *>(stats + i0);
+      double2 *d2 = reinterpret_cast<double2 *>(dst + i0);
+      const int64_t m2 = (i1 - i0) >> 1;
+      for (int64_t i = threadIdx.x; i < m2; i += blockDim.x) d2[i] = s2[i];
+      if (((i1 - i0) & 1) && threadIdx.x == 0) dst[i1 - 1] = stats[i1 - 1];
+    } else {
+      for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = stats[i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world && threadIdx.x != rank) {
+    unsigned long long *fq = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(areas[threadIdx.x]) + flag_off);
+    st_release_sys(fq + ((int64_t)set * world + rank) * kPeerBlocks + b, seq);
+    const unsigned long long *fl = reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(area) + flag_off);
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(fl + ((int64_t)set * world + threadIdx.x) * kPeerBlocks + b) < seq) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ll) { *err = 1; break; }
+    }
+  }
+  __syncthreads();
+  const double *slots = area + (int64_t)set * world * n;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    double sacc = 0.0;
+    for (int q = 0; q < world; q++) sacc += (q == rank) ? stats[i] : slots[(int64_t)q * n + i];
+    stats[i] = sacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&done[world], 1u);
+    if (prev == gridDim.x - 1) {  // every block has read the counter by now
+      done[world] = 0;
+      *seq_p = seq;
+    }
+  }
+}
+
 static int64_t peer_slot_doubles(const hmmcu_ctx *ctx) { return hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm) * ctx->V; }
-static size_t peer_area_bytes(int64_t n, int world) { return sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world; }
+// slots [2][world][n] | flags of the two-kernel form [2][world] | per-slice flags of k_peer_allreduce1 [2][world][kPeerBlocks]
+static size_t peer_area_bytes(int64_t n, int world) {
+  return sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world * (1 + kPeerBlocks);
+}
 
 static void peer_close(hmmcu_ctx *ctx) {
   for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
@@ -2440,8 +2501,25 @@ int hmmcu_peer_reduce(hmmcu_ctx *ctx) {
 }
 
 int hmmcu_peer_allreduce(hmmcu_ctx *ctx) {
-  int rc = hmmcu_peer_push(ctx);
-  return rc ? rc : hmmcu_peer_reduce(ctx);
+  int rc = peer_ready(ctx, "peer_allreduce");
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->dev));
+  if (ctx->peer_world == 1) return HMMCU_OK;
+  if (!ctx->peer_fused) {
+    rc = hmmcu_peer_push(ctx);
+    return rc ? rc : hmmcu_peer_reduce(ctx);
+  }
+  unsigned long long *seq = ctx->peer_seq_d.as<unsigned long long>();
+  unsigned int *done = reinterpret_cast<unsigned int *>(seq + 1);
+  int *err = reinterpret_cast<int *>(done + 80);
+  int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(kPeerBlocks, ctx->sm_count), (ctx->peer_n + 2047) / 2048));
+  if (ctx->peer_fused > 1) blocks = std::min(std::min(kPeerBlocks, ctx->sm_count), ctx->peer_fused);  // experiments: the grid size
+  t_begin(ctx, "allreduce");
+  k_peer_allreduce1<<<blocks, 256, 0, ctx->st>>>(ctx->stats.as<double>(), ctx->peer_n, ctx->peer_ptrs_d.as<void *>(), ctx->peer_area.as<double>(),
+                                                 ctx->peer_rank, ctx->peer_world, seq, done, err);
+  LAUNCH_CHECK();
+  t_end(ctx, "allreduce");
+  return HMMCU_OK;
 }
 
 int hmmcu_peer_error(hmmcu_ctx *ctx) {

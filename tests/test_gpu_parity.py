@@ -1272,12 +1272,16 @@ def test_peer_allreduce_sums_two_ranks_in_rank_order():
         for r_, (c, (u0, u1)) in enumerate(zip(ctxs, halves)):
             st, _ = c.estep(labels[u0:u1])
             local.append(st)
-        for c in ctxs:
-            c.peer_push()
-        for c in ctxs:
-            c.synchronize()
-        for c in ctxs:
-            c.peer_reduce()
+        if it == 1:  # the one-launch form (k_peer_allreduce1): both kernels spin on each other's slice flags, on their own streams
+            for c in ctxs:
+                c.peer_allreduce()
+        else:
+            for c in ctxs:
+                c.peer_push()
+            for c in ctxs:
+                c.synchronize()
+            for c in ctxs:
+                c.peer_reduce()
         got = [c.stats_download() for c in ctxs]
         assert not ctxs[0].peer_error() and not ctxs[1].peer_error()
         want = local[0] + local[1]
