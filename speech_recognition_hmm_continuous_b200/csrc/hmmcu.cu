@@ -702,6 +702,9 @@ void *hmmcu_staging(hmmcu_ctx *ctx, int slot, uint64_t bytes) {
   if (ctx->stage_h[slot]) { cudaStreamSynchronize(ctx->st_copy); cudaFreeHost(ctx->stage_h[slot]); }
   ctx->stage_h[slot] = nullptr;
   ctx->stage_cap[slot] = 0;
+  // a quarter of headroom: the jobs of a job file differ by a few per cent in size, and re-pinning three buffers costs 11-12 ms
+  // (measured), as much as the rest of a small job
+  bytes += bytes / 4;
   if (cudaHostAlloc(&ctx->stage_h[slot], bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   ctx->stage_cap[slot] = bytes;
   return ctx->stage_h[slot];

@@ -22,6 +22,19 @@
 #define STR 100
 #define WSTR 50
 
+/* HMMCU_TRACE=1 in the environment prints the wall clock of the phases on stderr (as in the trainer) */
+static void trace(const char *what) {
+  static double last = 0.0;
+  static int on = -1;
+  if (on < 0) on = getenv("HMMCU_TRACE") != NULL;
+  if (!on) return;
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+  fprintf(stderr, "[hmmcu] %-22s +%.1f ms\n", what, last > 0.0 ? (now - last) * 1e3 : 0.0);
+  last = now;
+}
+
 static void die(const char *fmt, const char *arg) {
   printf(fmt, arg);
   exit(1);
@@ -128,7 +141,9 @@ int hmmh_test_main(int argc, char **argv) {
   int64_t *off = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t)), *offq = (int64_t *)calloc((size_t)U + 2, sizeof(int64_t));
   int32_t *label = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1)), *second = (int32_t *)malloc(sizeof(int32_t) * (U > 0 ? U : 1));
   hmmcu_ctx *ctx = NULL;
+  trace("start");
   if (U > 0 && hmmcu_create(0, &ctx) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
+  trace("context");
   int fl = 2 + 2 * K; /* argv index of the set's first feature list: a set with P streams takes P lists (R-FS:259-266) */
   for (int j = 0; j < K; j++) {
     const char *models_list = argv[2 + j];
@@ -190,6 +205,7 @@ int hmmh_test_main(int argc, char **argv) {
         if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[bad] : feat_list);
         if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(cx[p]));
         if (d != probe[p].D) die("reading error on file %s \n", paths[0]);
+        trace("ingest");
         if (p > 0 && memcmp(off, offq, sizeof(int64_t) * ((size_t)U + 1)) != 0) die("reading error on file %s (the streams of an utterance differ in length) \n", feat_list);
         rc = Pj == 1 ? hmmh_upload_model_set(cx[p], &models) : hmmh_upload_models(cx[p], sm + (size_t)p * V, V);
         if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(cx[p]));
@@ -198,6 +214,7 @@ int hmmh_test_main(int argc, char **argv) {
       /* every (utterance, model) forward score in one batch; several streams: the product of their densities */
       if ((Pj > 1 && hmmcu_link_streams(ctx, cx + 1, Pj - 1) != HMMCU_OK) || hmmcu_forward_scores(ctx, logp, 1) != HMMCU_OK)
         die("GPU error: %s \n", hmmcu_last_error(ctx));
+      trace("models + scores");
       for (int p = 1; p < Pj; p++) hmmcu_destroy(cx[p]); /* unlinks */
       for (size_t k = 0; k < (size_t)U * V; k++) probab[k] += weight[j] * logp[k];
     }
@@ -212,7 +229,9 @@ int hmmh_test_main(int argc, char **argv) {
   if (fl != argc - 2) die("models_number %s does not match the argument list \n", argv[1]);
   if (U > 0) {
     if (hmmcu_rank(ctx, probab, U, V, 1.0, label, second) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctx));
+    trace("ranking");
     hmmcu_destroy(ctx);
+    trace("context released");
   }
   times(&tb);
   const double batch_cpu = tb.tms_utime / 60.0 - old_aux; /* spread evenly over the utterances */

@@ -150,7 +150,12 @@ int hmmh_train_main(int argc, char **argv) {
     if (!ctxs[p] && hmmcu_create(0, &ctxs[p]) != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(NULL));
     if (g_batch) g_keep[p] = ctxs[p];
     trace("context");
-    int rc = hmmh_ingest(ctxs[p], (const char *const *)paths[p], U, 0, offp, &D[p], &bad, NULL);
+    hmmh_ingest_stats ist;
+    memset(&ist, 0, sizeof(ist));
+    int rc = hmmh_ingest(ctxs[p], (const char *const *)paths[p], U, 0, offp, &D[p], &bad, &ist);
+    if (getenv("HMMCU_TRACE"))
+      fprintf(stderr, "[hmmcu]   ingest: scan %.1f ms, staging buffers %.1f ms, read + copy %.1f ms, pack %.1f ms\n", ist.scan_s * 1e3, ist.stage_s * 1e3,
+              ist.read_s * 1e3, (ist.total_s - ist.scan_s - ist.stage_s - ist.read_s) * 1e3);
     if (rc == HMMCU_EIO) die("file %s not found \n", bad >= 0 ? paths[p][bad] : list[p]);
     if (rc != HMMCU_OK) die("GPU error: %s \n", hmmcu_last_error(ctxs[p]));
     trace("ingest");
