@@ -68,6 +68,9 @@ void hmmcu_host_free(void *p);
  * cluster; "dec_f16": 1 (default) = k_emis_dec with half-precision operands (per-dimension power-of-two scaling, as accurate as
  * the 3xTF32 split; used while the accuracy guard holds and the padded feature row is a multiple of 8), 0 = 3xTF32; "fwd_f64": 1 = the forward cell scorer with a double-precision linear chain instead of the single-precision
  * log-domain one; "dec_budget_kb": log-emission budget of one decode batch in KiB (0 = 6 GiB or a third of the free memory);
+ * "h_acc": 1 (default) = the mixture accumulators through k_accum_h (half-precision hi / lo operands, frame tiles packed once per
+ * feature set and fetched by bulk copies; taken while the padded feature row is a multiple of 8 and at most 40), 0 = k_accum_ws
+ * (3xTF32, loader warps); "peer_fused": 1 (default) = hmmcu_peer_allreduce as one launch (k_peer_allreduce1), 0 = push + reduce;
  * "dec_dbg": experiment switches of k_emis_dec (results are garbage: 1 no epilogue arithmetic, 2 no MMAs, 4 no W copies). */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 
