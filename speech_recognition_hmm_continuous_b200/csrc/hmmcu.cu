@@ -183,6 +183,9 @@ struct hmmcu_ctx {
   std::vector<void *> peer_ptrs;        // [world], entry `rank` = my own area
   std::vector<void *> peer_opened;      // IPC mappings to close
   int peer_rank = -1, peer_world = 0;
+  int peer_ll = 1;                      // hmmcu_peer_allreduce with tagged 8-byte words (k_peer_allreduce_ll): no fence, no flags
+  int peer_dbg = 0;                     // k_peer_allreduce1 writes phase stamps (experiments)
+  DevBuf peer_stamps;
   int peer_fused = 1;                   // hmmcu_peer_allreduce as one launch (k_peer_allreduce1) instead of push + reduce
   int64_t peer_n = 0;                   // doubles per slot the area was sized for
   int64_t n_res_batches = 0;
@@ -376,7 +379,7 @@ void hmmcu_destroy(hmmcu_ctx *ctx) {
   cudaStreamSynchronize(ctx->st);
   unlink_streams(ctx);
   for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
-  ctx->peer_area.release(); ctx->peer_ptrs_d.release(); ctx->peer_seq_d.release();
+  ctx->peer_area.release(); ctx->peer_ptrs_d.release(); ctx->peer_seq_d.release(); ctx->peer_stamps.release();
   ctx->logb_joint.release();
   DevBuf *bufs[] = {&ctx->x64_own, &ctx->x32, &ctx->ctr, &ctx->off_d, &ctx->A, &ctx->c, &ctx->mu, &ctx->iv, &ctx->det,
                     &ctx->mu32, &ctx->iv32, &ctx->k32, &ctx->kc2, &ctx->u2m_d, &ctx->mus_d, &ctx->mu_d, &ctx->tiles_d, &ctx->logb,
@@ -482,6 +485,16 @@ int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "ws_emis") == 0) { ctx->use_ws = value; return HMMCU_OK; }
   if (strcmp(key, "ws_acc") == 0) { ctx->use_ws_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
   if (strcmp(key, "peer_fused") == 0) { ctx->peer_fused = value; return HMMCU_OK; }
+  if (strcmp(key, "peer_ll") == 0) { ctx->peer_ll = value; return HMMCU_OK; }
+  if (strcmp(key, "peer_dbg") == 0) {
+    ctx->peer_dbg = value;
+    if (value) {
+      CK(cudaSetDevice(ctx->dev));
+      CK(ctx->peer_stamps.ensure(sizeof(long long) * 128 * 8));
+      CK(cudaMemsetAsync(ctx->peer_stamps.p, 0, sizeof(long long) * 128 * 8, ctx->st));
+    }
+    return HMMCU_OK;
+  }
   if (strcmp(key, "h_acc") == 0) { ctx->use_h_acc = value; ctx->acc_dirty = true; return HMMCU_OK; }
   if (strcmp(key, "res_fb") == 0) { ctx->use_res_fb = value; return HMMCU_OK; }
   if (strcmp(key, "fwd_f64") == 0) { ctx->fwd_f64 = value; return HMMCU_OK; }
@@ -571,6 +584,8 @@ static int features_geometry(hmmcu_ctx *ctx, const int64_t *frame_off, int U, in
   }
   CK(cudaSetDevice(ctx->dev));
   const int64_t F = U > 0 ? frame_off[U] : 0;
+  // frame ids are 32-bit on the device (frame_ids, tile rows): 2^31 frames would be 172 GB of doubles at D = 10 already
+  if (F > (int64_t)INT32_MAX - 4096) return fail(ctx, HMMCU_EINVAL, "set_features: %lld frames in one feature set (max 2^31 - 4096 per context)", (long long)F);
   // same utterance geometry as before (the trainer re-reading its feature files every iteration,
   // T-FS:272-321): the training map built from it stays valid
   const bool same_geometry = ctx->have_features && ctx->U == U && ctx->D == D && (int)ctx->off.size() == U + 1 &&
@@ -2340,9 +2355,19 @@ k_peer_reduce(double *__restrict__ stats, int64_t n, const double *__restrict__ 
 constexpr int kPeerBlocks = 128;
 __global__ void __launch_bounds__(256)
 k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict__ areas, const double *__restrict__ area, int rank, int world,
-                  unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done, int *__restrict__ err) {
+                  unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done, int *__restrict__ err,
+                  long long *__restrict__ stamps) {
   const unsigned long long seq = *seq_p + 1;
   const int set = (int)(seq & 1), b = blockIdx.x, nb = gridDim.x;
+  // experiment switch "peer_dbg": %globaltimer of block b at start | stores issued | fenced | peers' flags seen | summed
+  auto stamp = [&](int k) {
+    if (stamps && threadIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      stamps[b * 8 + k] = t;
+    }
+  };
+  stamp(0);
   const int64_t chunk = ((n + nb - 1) / nb + 1) & ~(int64_t)1;  // even: double2 copies stay aligned
   const int64_t i0 = min(n, (int64_t)b * chunk), i1 = min(n, i0 + chunk);
   const size_t flag_off = sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world;
@@ -2359,8 +2384,10 @@ k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict
       for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) dst[i] = stats[i];
     }
   }
+  stamp(1);
   __threadfence_system();
   __syncthreads();
+  stamp(2);
   if (threadIdx.x < world && threadIdx.x != rank) {
     unsigned long long *fq = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(areas[threadIdx.x]) + flag_off);
     st_release_sys(fq + ((int64_t)set * world + rank) * kPeerBlocks + b, seq);
@@ -2373,6 +2400,7 @@ k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict
     }
   }
   __syncthreads();
+  stamp(3);
   const double *slots = area + (int64_t)set * world * n;
   for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     double sacc = 0.0;
@@ -2380,6 +2408,80 @@ k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict
     stats[i] = sacc;
   }
   __syncthreads();
+  stamp(4);
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&done[world], 1u);
+    if (prev == gridDim.x - 1) {  // every block has read the counter by now
+      done[world] = 0;
+      *seq_p = seq;
+    }
+  }
+}
+
+// The same sum with NO fence and NO separate flags ("LL" stores, the scheme of the collective libraries' low-latency protocol):
+// every double travels as two 8-byte words {low half, seq} {high half, seq} written with one 16-byte volatile store; an aligned
+// 8-byte word is written atomically, so a word whose tag equals this iteration's seq carries this iteration's data, and the
+// receiver simply polls the words it is about to add.  k_peer_allreduce1 spends 5-6 us in __threadfence_system and 6-12 us
+// waiting for the peers' slice flags (scripts/peer_stamps.py); here a thread pushes its elements to every peer and then adds the
+// peers' elements in rank order as they land.  Twice the NVLink bytes (1 MB per peer at C2), no block depends on another block.
+__device__ __forceinline__ void st_ll(void *p, uint32_t lo, uint32_t hi, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const void *p, uint32_t tag, double &v) {
+  uint32_t lo, t0, hi, t1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(p) : "memory");
+  v = __hiloint2double((int)hi, (int)lo);
+  return t0 == tag && t1 == tag;
+}
+__global__ void __launch_bounds__(256)
+k_peer_allreduce_ll(double *__restrict__ stats, int64_t n, void *const *__restrict__ areas, size_t ll_off, int rank, int world,
+                    unsigned long long *__restrict__ seq_p, unsigned int *__restrict__ done, int *__restrict__ err, long long *__restrict__ stamps) {
+  const unsigned long long seq = *seq_p + 1;
+  const int set = (int)(seq & 1);
+  const uint32_t tag = (uint32_t)seq;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  auto stamp = [&](int k) {
+    if (stamps && threadIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      stamps[blockIdx.x * 8 + k] = t;
+    }
+  };
+  stamp(0);
+  for (int64_t i = tid; i < n; i += nth) {
+    const double v = stats[i];
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    for (int q = 0; q < world; q++) {
+      if (q == rank) continue;
+      st_ll(reinterpret_cast<char *>(areas[q]) + ll_off + (((int64_t)set * world + rank) * n + i) * 16, lo, hi, tag);
+    }
+  }
+  stamp(1);
+  stamp(2);
+  const char *mine = reinterpret_cast<const char *>(areas[rank]) + ll_off + (int64_t)set * world * n * 16;
+  long long t0 = 0;
+  for (int64_t i = tid; i < n; i += nth) {
+    double sacc = 0.0;
+    for (int q = 0; q < world; q++) {
+      if (q == rank) { sacc += stats[i]; continue; }
+      const char *p = mine + ((int64_t)q * n + i) * 16;
+      double v;
+      unsigned int spins = 0;
+      while (!ld_ll(p, tag, v)) {
+        if ((++spins & 1023u) == 0) {  // bounded: ~20 s, then *err = 1
+          long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t0 == 0) t0 = t1;
+          if (t1 - t0 > 20000000000ll) { *err = 1; v = 0.0; break; }
+        }
+      }
+      sacc += v;
+    }
+    stats[i] = sacc;
+  }
+  __syncthreads();
+  stamp(3);
+  stamp(4);
   if (threadIdx.x == 0) {
     const unsigned int prev = atomicAdd(&done[world], 1u);
     if (prev == gridDim.x - 1) {  // every block has read the counter by now
@@ -2390,10 +2492,13 @@ k_peer_allreduce1(double *__restrict__ stats, int64_t n, void *const *__restrict
 }
 
 static int64_t peer_slot_doubles(const hmmcu_ctx *ctx) { return hmmcu_stats_size(ctx->N, ctx->M, ctx->Dm) * ctx->V; }
-// slots [2][world][n] | flags of the two-kernel form [2][world] | per-slice flags of k_peer_allreduce1 [2][world][kPeerBlocks]
-static size_t peer_area_bytes(int64_t n, int world) {
-  return sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world * (1 + kPeerBlocks);
+// slots [2][world][n] | flags of the two-kernel form [2][world] | per-slice flags of k_peer_allreduce1 [2][world][kPeerBlocks] |
+// (16-byte aligned) tagged words of k_peer_allreduce_ll [2][world][n][2]
+static size_t peer_ll_offset(int64_t n, int world) {
+  const size_t b = sizeof(double) * (size_t)(2 * (int64_t)world * n) + sizeof(unsigned long long) * 2 * (size_t)world * (1 + kPeerBlocks);
+  return (b + 15) & ~(size_t)15;
 }
+static size_t peer_area_bytes(int64_t n, int world) { return peer_ll_offset(n, world) + (size_t)16 * 2 * (size_t)world * (size_t)n; }
 
 static void peer_close(hmmcu_ctx *ctx) {
   for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
@@ -2515,13 +2620,31 @@ int hmmcu_peer_allreduce(hmmcu_ctx *ctx) {
   unsigned long long *seq = ctx->peer_seq_d.as<unsigned long long>();
   unsigned int *done = reinterpret_cast<unsigned int *>(seq + 1);
   int *err = reinterpret_cast<int *>(done + 80);
+  if (ctx->peer_ll) {  // tagged 8-byte words, no fence, no flags
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(kPeerBlocks, ctx->sm_count), (ctx->peer_n + 255) / 256));
+    t_begin(ctx, "allreduce");
+    k_peer_allreduce_ll<<<blocks, 256, 0, ctx->st>>>(ctx->stats.as<double>(), ctx->peer_n, ctx->peer_ptrs_d.as<void *>(), peer_ll_offset(ctx->peer_n, ctx->peer_world),
+                                                     ctx->peer_rank, ctx->peer_world, seq, done, err, ctx->peer_dbg ? ctx->peer_stamps.as<long long>() : nullptr);
+    LAUNCH_CHECK();
+    t_end(ctx, "allreduce");
+    return HMMCU_OK;
+  }
   int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(kPeerBlocks, ctx->sm_count), (ctx->peer_n + 2047) / 2048));
   if (ctx->peer_fused > 1) blocks = std::min(std::min(kPeerBlocks, ctx->sm_count), ctx->peer_fused);  // experiments: the grid size
   t_begin(ctx, "allreduce");
   k_peer_allreduce1<<<blocks, 256, 0, ctx->st>>>(ctx->stats.as<double>(), ctx->peer_n, ctx->peer_ptrs_d.as<void *>(), ctx->peer_area.as<double>(),
-                                                 ctx->peer_rank, ctx->peer_world, seq, done, err);
+                                                 ctx->peer_rank, ctx->peer_world, seq, done, err, ctx->peer_dbg ? ctx->peer_stamps.as<long long>() : nullptr);
   LAUNCH_CHECK();
   t_end(ctx, "allreduce");
+  return HMMCU_OK;
+}
+
+// experiment read-out ("peer_dbg"): the stamps of the last k_peer_allreduce1, [kPeerBlocks][8] (scripts/peer_stamps.py)
+extern "C" int hmmcu_debug_peer_read(hmmcu_ctx *ctx, long long *out) {
+  if (!ctx || !out || !ctx->peer_stamps.p) return HMMCU_EINVAL;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaMemcpyAsync(out, ctx->peer_stamps.p, sizeof(long long) * kPeerBlocks * 8, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
   return HMMCU_OK;
 }
 

@@ -1267,13 +1267,16 @@ def test_peer_allreduce_sums_two_ranks_in_rank_order():
     areas = [c.peer_area() for c in ctxs]
     for r_, c in enumerate(ctxs):
         c.peer_import_pointers(r_, 2, areas)
-    for it in range(3):
+    for it in range(5):
         local = []
         for r_, (c, (u0, u1)) in enumerate(zip(ctxs, halves)):
             st, _ = c.estep(labels[u0:u1])
             local.append(st)
-        if it == 1:  # the one-launch form (k_peer_allreduce1): both kernels spin on each other's slice flags, on their own streams
+        if it in (1, 2, 3):
+            # the one-launch forms, both kernels spinning on each other on their own streams: 1, 3 = tagged 8-byte words
+            # (k_peer_allreduce_ll, the default; iteration 3 reuses the slot set of iteration 1), 2 = slice flags (k_peer_allreduce1)
             for c in ctxs:
+                c.set_option("peer_ll", 0 if it == 2 else 1)
                 c.peer_allreduce()
         else:
             for c in ctxs:
