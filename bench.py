@@ -272,7 +272,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)   # all ranks or none
         if int(t.item()) == 1:
             c._ar = lambda p, n, s: c.peer_allreduce()
-            ar_kind[0] = "hmmcu_peer_allreduce: kernel pair over NVLink peer memory (no library collective)"
+            ar_kind[0] = "hmmcu_peer_allreduce: one kernel over NVLink peer memory, tagged 8-byte words, no fence and no flags (no library collective)"
     # pinned host copy of the features (e2e leg) and a device-resident copy (value leg)
     xpin = torch.from_numpy(x).pin_memory()
     xdev = xpin.to(dev)

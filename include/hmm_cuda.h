@@ -70,7 +70,8 @@ void hmmcu_host_free(void *p);
  * log-domain one; "dec_budget_kb": log-emission budget of one decode batch in KiB (0 = 6 GiB or a third of the free memory);
  * "h_acc": 1 (default) = the mixture accumulators through k_accum_h (half-precision hi / lo operands, frame tiles packed once per
  * feature set and fetched by bulk copies; taken while the padded feature row is a multiple of 8 and at most 40), 0 = k_accum_ws
- * (3xTF32, loader warps); "peer_fused": 1 (default) = hmmcu_peer_allreduce as one launch (k_peer_allreduce1), 0 = push + reduce;
+ * (3xTF32, loader warps); "peer_ll": 1 (default) = hmmcu_peer_allreduce with tagged 8-byte words (k_peer_allreduce_ll: no system fence, no
+ * flags), 0 = k_peer_allreduce1 (slice-wise push, fence, flags) or, with "peer_fused": 0, hmmcu_peer_push + hmmcu_peer_reduce;
  * "dec_dbg": experiment switches of k_emis_dec (results are garbage: 1 no epilogue arithmetic, 2 no MMAs, 4 no W copies). */
 int hmmcu_set_option(hmmcu_ctx *ctx, const char *key, int value);
 
@@ -172,8 +173,11 @@ int hmmcu_stats_download(hmmcu_ctx *ctx, double *stats);
  * Per EM iteration, between hmmcu_estep and hmmcu_mstep (replaces the all-reduce of hmmh_allreduce_fn):
  *   hmmcu_peer_push     my statistics -> every peer's slot for me, then my flag there
  *   hmmcu_peer_reduce   wait for every peer's flag, statistics = sum over the ranks in rank order
- * (hmmcu_peer_allreduce = push + reduce).  Two slot sets alternate, so a rank that runs ahead never overwrites what a
- * slower rank still reads. */
+ *   hmmcu_peer_allreduce  the same sum in ONE launch; by default every double travels as two 8-byte words tagged with the
+ *                       iteration number (an aligned 8-byte store lands atomically), so the kernel needs neither a system
+ *                       fence nor flags: a thread pushes its elements to every peer and adds the peers' copies in rank order
+ *                       as they land (options "peer_ll", "peer_fused" select the older forms)
+ * Two slot sets alternate, so a rank that runs ahead never overwrites what a slower rank still reads. */
 #define HMMCU_IPC_HANDLE_BYTES 64
 int hmmcu_peer_export(hmmcu_ctx *ctx, int world, void *handle_out);
 int hmmcu_peer_import(hmmcu_ctx *ctx, int rank, int world, const void *handles);
